@@ -1,0 +1,153 @@
+/* promonet_b200 -- C ABI of the B200-native ProMoNet hot path.
+ *
+ * The reference (maxrmorrison/promonet) has no FFI: its boundary is the Python
+ * nn.Module / function contract.  Each entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  All
+ * pointers are DEVICE pointers to contiguous row-major tensors unless the name
+ * ends in `_host`; every call is asynchronous on `stream` (a cudaStream_t passed
+ * as void*), allocates nothing, and returns 0 on success or a negative pmn_status
+ * with a thread-local message available from pmn_last_error().
+ */
+#ifndef PROMONET_B200_H_
+#define PROMONET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PMN_OK = 0,
+    PMN_ERR_ARGUMENT = -1,  /* bad shape / null pointer / unknown tensor name */
+    PMN_ERR_STATE = -2,     /* e.g. forward before finalize, missing weights */
+    PMN_ERR_WORKSPACE = -3, /* workspace too small */
+    PMN_ERR_CUDA = -4       /* a CUDA runtime call failed */
+} pmn_status;
+
+const char* pmn_last_error(void);
+/* ABI version; bumped on any signature change */
+int pmn_version(void);
+/* Number of kernels launched by this library in this process (bench gpu_launches) */
+int64_t pmn_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, each launch
+ * of this library is bracketed by CUDA events on its stream.  `kernel` is the
+ * kernel's name (e.g. "conv1d_kernel"); read returns the summed event time. */
+void pmn_profile_enable(int enabled);
+void pmn_profile_reset(void);
+int pmn_profile_read(const char* kernel, double* total_ms, int64_t* launches);
+
+/* ------------------------------------------------------------------------ */
+/* Generator (HiFi-GAN) -- promonet/model/generator.py:116-135,              */
+/* promonet/model/hifigan.py:63-70                                           */
+/* ------------------------------------------------------------------------ */
+
+typedef struct pmn_generator pmn_generator;
+
+/* Precision of the dense residual-block convolutions */
+typedef enum {
+    PMN_MATH_FP32_SIMT = 0,  /* fp32 FMA everywhere */
+    PMN_MATH_BF16X3_TC = 1   /* tcgen05, 3-product bf16 hi/lo split, fp32 accumulate */
+} pmn_math;
+
+/* config/promonet.py defaults (MODEL='hifigan'): replaces Generator.__init__
+ * promonet/model/generator.py:84-114 + HiFiGAN.__init__ hifigan.py:15-61 */
+int pmn_generator_create(pmn_generator** out);
+void pmn_generator_destroy(pmn_generator* g);
+
+/* Load one state_dict entry by its reference name (e.g.
+ * "model.model.0.model.1.weight_g").  fp32 device tensor; copied into
+ * library-owned memory.  Replaces torchutil.checkpoint.load at
+ * promonet/synthesize/core.py:245. */
+int pmn_generator_set_tensor(
+    pmn_generator* g, const char* name, const float* data,
+    const int64_t* shape, int ndim, void* stream);
+
+/* Fold weight norm (w = g * v / ||v||, hifigan.py:100-106,167-183; core.py:43)
+ * and pack weights for the kernels.  Must be called after all tensors are set. */
+int pmn_generator_finalize(pmn_generator* g, int math, void* stream);
+
+size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames);
+
+/* Generator.forward generator.py:116-135.
+ *   loudness     (B, loudness_rows, F) fp32, loudness_rows = 8 or 513 (dB)
+ *   pitch        (B, F) fp32 Hz;  periodicity (B, F) fp32
+ *   ppg          (B, 40, F) fp32
+ *   speakers     (B,) int64;  spectral_balance_ratios, loudness_ratios (B,) fp32
+ *   audio        (B, 1, 256 F) fp32 out */
+int pmn_generator_forward(
+    pmn_generator* g,
+    const float* loudness, int loudness_rows,
+    const float* pitch, const float* periodicity, const float* ppg,
+    const int64_t* speakers,
+    const float* spectral_balance_ratios, const float* loudness_ratios,
+    float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies inputs H2D, runs the
+ * forward, copies audio D2H, all on `stream`; `staging` is a device buffer of
+ * pmn_generator_staging_bytes().  This is what promonet.synthesize.from_features
+ * (promonet/synthesize/core.py:18-59) maps onto. */
+size_t pmn_generator_staging_bytes(int batch, int frames, int loudness_rows);
+int pmn_generator_forward_host(
+    pmn_generator* g,
+    const float* loudness_host, int loudness_rows,
+    const float* pitch_host, const float* periodicity_host, const float* ppg_host,
+    const int64_t* speakers_host,
+    const float* spectral_balance_ratios_host, const float* loudness_ratios_host,
+    float* audio_host, int batch, int frames,
+    void* staging, size_t staging_bytes,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Intermediate of the forward, for unit parity: prepare_features
+ * generator.py:137-197 -> (B, 113, F) */
+int pmn_generator_features(
+    pmn_generator* g,
+    const float* loudness, int loudness_rows,
+    const float* pitch, const float* periodicity, const float* ppg,
+    float* features, int batch, int frames, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Operator-level entry points (unit-test granularity)                       */
+/* ------------------------------------------------------------------------ */
+
+/* w[d0] = g[d0] * v[d0] / ||v[d0]||_2 over the trailing `inner` elements
+ * (torch.nn.utils.weight_norm dim=0; promonet/model/core.py:43-45) */
+int pmn_weight_norm_fold(
+    const float* v, const float* g, float* w, int dim0, int inner, void* stream);
+
+/* Conv1d weight (C_out, C_in, K) -> packed (C_in, K, C_out) for pmn_conv1d */
+int pmn_pack_conv1d_weight(
+    const float* w, float* packed, int c_out, int c_in, int k, void* stream);
+
+/* Fused dilated Conv1d (torch.nn.functional.conv1d semantics, stride 1):
+ *   y[b,o,t] = act_out( bias[o] + bias2[b,o] + residual[b,o,t]
+ *              + sum_{c,j} w[o,c,j] * lrelu_in(x[b,c,t + j*dilation - padding]) )
+ * hifigan.py:198-210 is c1/c2 of Block.forward with in_slope=0.1.
+ *   packed_weight from pmn_pack_conv1d_weight; bias/bias2/residual may be NULL
+ *   in_slope: LeakyReLU slope applied to x (1.0 = none)
+ *   out_act: 0 none, 1 tanh, 2 relu
+ *   accum / accum_mode: optional second output (B, C_out, T_out):
+ *      0 unused, 1 accum = scale*y, 2 accum += scale*y   (MRF mean, hifigan.py:141-145)
+ *   out may be NULL when only accum is wanted; out may alias residual. */
+int pmn_conv1d(
+    const float* x, const float* packed_weight, const float* bias,
+    const float* bias2, const float* residual, float* out,
+    float* accum, int accum_mode, float accum_scale,
+    int batch, int c_in, int c_out, int t_in, int t_out,
+    int k, int dilation, int padding, float in_slope, int out_act,
+    void* stream);
+
+/* LeakyReLU + ConvTranspose1d with kernel = 2*stride, padding = stride/2
+ * (hifigan.py:97-106; PyTorch weight layout (C_in, C_out, K)), T_out = stride*T_in */
+int pmn_conv_transpose1d(
+    const float* x, const float* weight, const float* bias, float* out,
+    int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope,
+    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PROMONET_B200_H_ */

@@ -1,0 +1,115 @@
+"""ctypes binding of libpromonet_b200.so (the C ABI in include/promonet_b200.h)
+
+There is no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+from promonet_b200 import build as _build
+
+MATH_FP32_SIMT = 0
+MATH_BF16X3_TC = 1
+
+
+class Error(RuntimeError):
+    """A libpromonet_b200 call returned a negative status"""
+
+
+# name -> (restype, argtypes); must list every symbol of include/promonet_b200.h
+SIGNATURES = {
+    'pmn_last_error': (c_char_p, []),
+    'pmn_version': (c_int, []),
+    'pmn_launch_count': (c_int64, []),
+    'pmn_profile_enable': (None, [c_int]),
+    'pmn_profile_reset': (None, []),
+    'pmn_profile_read': (c_int, [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64)]),
+    'pmn_generator_create': (c_int, [POINTER(c_void_p)]),
+    'pmn_generator_destroy': (None, [c_void_p]),
+    'pmn_generator_set_tensor': (
+        c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
+    'pmn_generator_finalize': (c_int, [c_void_p, c_int, c_void_p]),
+    'pmn_generator_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int]),
+    'pmn_generator_forward': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'pmn_generator_staging_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pmn_generator_forward_host': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t,
+         c_void_p, c_size_t, c_void_p]),
+    'pmn_generator_features': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_int, c_void_p]),
+    'pmn_weight_norm_fold': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'pmn_pack_conv1d_weight': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_conv1d': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_float, c_int, c_void_p]),
+    'pmn_conv_transpose1d': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+         c_int, c_int, c_float, c_void_p]),
+}
+
+_library = None
+
+
+def library():
+    """Load (building first if the in-tree .so is stale or absent)"""
+    global _library
+    if _library is None:
+        path = _build.build()
+        lib = ctypes.CDLL(str(path))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            function = getattr(lib, name)
+            function.restype = restype
+            function.argtypes = argtypes
+        _library = lib
+    return _library
+
+
+def check(status):
+    if status != 0:
+        message = library().pmn_last_error()
+        raise Error(
+            f'libpromonet_b200 status {status}: '
+            f'{message.decode() if message else "unknown"}')
+
+
+def ptr(tensor):
+    """Device (or host) address of a contiguous tensor; None -> NULL"""
+    if tensor is None:
+        return None
+    if not tensor.is_contiguous():
+        raise ValueError('tensor passed to libpromonet_b200 must be contiguous')
+    return tensor.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(library().pmn_launch_count())
+
+
+def profile(enabled):
+    """Turn per-kernel CUDA-event timing on or off (resets the totals)"""
+    library().pmn_profile_reset()
+    library().pmn_profile_enable(int(bool(enabled)))
+
+
+def profile_read(kernel):
+    """(total device milliseconds, launches) of `kernel` since profile(True)"""
+    total, launches = ctypes.c_double(), c_int64()
+    check(library().pmn_profile_read(
+        kernel.encode(), ctypes.byref(total), ctypes.byref(launches)))
+    return total.value, launches.value

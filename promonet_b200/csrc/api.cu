@@ -1,0 +1,217 @@
+// extern "C" surface of libpromonet_b200.so (declared in include/promonet_b200.h)
+#include <new>
+
+#include "common.cuh"
+#include "generator.cuh"
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace pmn {
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launch_count{0};
+bool g_profile_enabled = false;
+
+namespace {
+struct ProfileEntry {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    cudaEvent_t pending = nullptr;
+};
+std::mutex g_profile_mutex;
+std::map<std::string, ProfileEntry> g_profile;
+}  // namespace
+
+void profile_before(const char* kernel, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    ProfileEntry& entry = g_profile[kernel];
+    cudaEventCreate(&entry.pending);
+    cudaEventRecord(entry.pending, stream);
+}
+
+void profile_after(const char* kernel, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    ProfileEntry& entry = g_profile[kernel];
+    if (!entry.pending) return;
+    cudaEvent_t stop;
+    cudaEventCreate(&stop);
+    cudaEventRecord(stop, stream);
+    entry.events.emplace_back(entry.pending, stop);
+    entry.pending = nullptr;
+}
+}  // namespace pmn
+
+using namespace pmn;
+
+extern "C" {
+
+const char* pmn_last_error(void) { return g_last_error.c_str(); }
+int pmn_version(void) { return 1; }
+int64_t pmn_launch_count(void) { return g_launch_count.load(); }
+
+void pmn_profile_enable(int enabled) { g_profile_enabled = enabled != 0; }
+
+void pmn_profile_reset(void) {
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    for (auto& item : g_profile)
+        for (auto& pair : item.second.events) {
+            cudaEventDestroy(pair.first);
+            cudaEventDestroy(pair.second);
+        }
+    g_profile.clear();
+}
+
+int pmn_profile_read(const char* kernel, double* total_ms, int64_t* launches) {
+    PMN_REQUIRE(kernel && total_ms && launches, "profile_read: null pointer");
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    *total_ms = 0.;
+    *launches = 0;
+    auto it = g_profile.find(kernel);
+    if (it == g_profile.end()) return PMN_OK;
+    for (auto& pair : it->second.events) {
+        PMN_TRY(check_cuda(cudaEventSynchronize(pair.second), "profile event sync"));
+        float ms = 0.f;
+        PMN_TRY(check_cuda(cudaEventElapsedTime(&ms, pair.first, pair.second), "profile elapsed"));
+        *total_ms += ms;
+        *launches += 1;
+    }
+    return PMN_OK;
+}
+
+int pmn_generator_create(pmn_generator** out) {
+    PMN_REQUIRE(out, "generator_create: null out");
+    *out = generator_create();
+    if (!*out) return fail(PMN_ERR_STATE, "out of host memory");
+    return PMN_OK;
+}
+
+void pmn_generator_destroy(pmn_generator* g) { generator_destroy(g); }
+
+int pmn_generator_set_tensor(
+    pmn_generator* g, const char* name, const float* data,
+    const int64_t* shape, int ndim, void* stream) {
+    PMN_REQUIRE(g && name && data && ndim >= 0 && (ndim == 0 || shape), "set_tensor: bad argument");
+    return generator_set_tensor(g, name, data, shape, ndim, (cudaStream_t)stream);
+}
+
+int pmn_generator_finalize(pmn_generator* g, int math, void* stream) {
+    PMN_REQUIRE(g, "finalize: null generator");
+    return generator_finalize(g, math, (cudaStream_t)stream);
+}
+
+size_t pmn_generator_workspace_bytes(const pmn_generator*, int batch, int frames) {
+    if (batch <= 0 || frames <= 0) return 0;
+    return generator_workspace_bytes(batch, frames);
+}
+
+int pmn_generator_forward(
+    pmn_generator* g, const float* loudness, int loudness_rows, const float* pitch,
+    const float* periodicity, const float* ppg, const int64_t* speakers,
+    const float* sbr, const float* lr, float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, void* stream) {
+    PMN_REQUIRE(g, "forward: null generator");
+    return generator_forward(
+        g, loudness, loudness_rows, pitch, periodicity, ppg, speakers, sbr, lr, audio,
+        batch, frames, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+namespace {
+struct Staging {
+    float *loudness, *pitch, *periodicity, *ppg, *sbr, *lr, *audio;
+    int64_t* speakers;
+    size_t bytes;
+};
+Staging carve_staging(void* base, int batch, int frames, int rows) {
+    Staging s;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) {
+        char* r = p;
+        p += align_up(bytes, 256);
+        return r;
+    };
+    s.loudness = (float*)take((size_t)batch * rows * frames * 4);
+    s.pitch = (float*)take((size_t)batch * frames * 4);
+    s.periodicity = (float*)take((size_t)batch * frames * 4);
+    s.ppg = (float*)take((size_t)batch * 40 * frames * 4);
+    s.sbr = (float*)take((size_t)batch * 4);
+    s.lr = (float*)take((size_t)batch * 4);
+    s.speakers = (int64_t*)take((size_t)batch * 8);
+    s.audio = (float*)take((size_t)batch * 256 * frames * 4);
+    s.bytes = (size_t)(p - static_cast<char*>(base));
+    return s;
+}
+}  // namespace
+
+size_t pmn_generator_staging_bytes(int batch, int frames, int loudness_rows) {
+    if (batch <= 0 || frames <= 0 || loudness_rows <= 0) return 0;
+    return carve_staging(nullptr, batch, frames, loudness_rows).bytes;
+}
+
+int pmn_generator_forward_host(
+    pmn_generator* g, const float* loudness, int rows, const float* pitch,
+    const float* periodicity, const float* ppg, const int64_t* speakers,
+    const float* sbr, const float* lr, float* audio, int batch, int frames,
+    void* staging, size_t staging_bytes, void* workspace, size_t workspace_bytes,
+    void* stream_) {
+    PMN_REQUIRE(g && loudness && pitch && periodicity && ppg && speakers && sbr && lr && audio && staging,
+                "forward_host: null pointer");
+    PMN_REQUIRE(batch > 0 && frames > 0 && rows > 0, "forward_host: bad shape");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Staging s = carve_staging(staging, batch, frames, rows);
+    if (s.bytes > staging_bytes) return fail(PMN_ERR_WORKSPACE, "forward_host: staging too small");
+    auto h2d = [&](void* dst, const void* src, size_t bytes) {
+        return check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream), "H2D copy");
+    };
+    PMN_TRY(h2d(s.loudness, loudness, (size_t)batch * rows * frames * 4));
+    PMN_TRY(h2d(s.pitch, pitch, (size_t)batch * frames * 4));
+    PMN_TRY(h2d(s.periodicity, periodicity, (size_t)batch * frames * 4));
+    PMN_TRY(h2d(s.ppg, ppg, (size_t)batch * 40 * frames * 4));
+    PMN_TRY(h2d(s.sbr, sbr, (size_t)batch * 4));
+    PMN_TRY(h2d(s.lr, lr, (size_t)batch * 4));
+    PMN_TRY(h2d(s.speakers, speakers, (size_t)batch * 8));
+    PMN_TRY(generator_forward(
+        g, s.loudness, rows, s.pitch, s.periodicity, s.ppg, s.speakers, s.sbr, s.lr, s.audio,
+        batch, frames, workspace, workspace_bytes, stream));
+    return check_cuda(
+        cudaMemcpyAsync(audio, s.audio, (size_t)batch * 256 * frames * 4, cudaMemcpyDeviceToHost, stream),
+        "D2H copy");
+}
+
+int pmn_generator_features(
+    pmn_generator* g, const float* loudness, int rows, const float* pitch,
+    const float* periodicity, const float* ppg, float* features, int batch, int frames,
+    void* stream) {
+    PMN_REQUIRE(g, "features: null generator");
+    return generator_features(g, loudness, rows, pitch, periodicity, ppg, features, batch, frames,
+                              (cudaStream_t)stream);
+}
+
+int pmn_weight_norm_fold(const float* v, const float* g, float* w, int dim0, int inner, void* stream) {
+    return launch_weight_norm_fold(v, g, w, dim0, inner, (cudaStream_t)stream);
+}
+
+int pmn_pack_conv1d_weight(const float* w, float* packed, int c_out, int c_in, int k, void* stream) {
+    return launch_pack_conv1d_weight(w, packed, c_out, c_in, k, (cudaStream_t)stream);
+}
+
+int pmn_conv1d(
+    const float* x, const float* packed_weight, const float* bias, const float* bias2,
+    const float* residual, float* out, float* accum, int accum_mode, float accum_scale,
+    int batch, int c_in, int c_out, int t_in, int t_out, int k, int dilation, int padding,
+    float in_slope, int out_act, void* stream) {
+    Conv1dArgs a;
+    a.x = x; a.weight = packed_weight; a.bias = bias; a.bias2 = bias2; a.residual = residual;
+    a.out = out; a.accum = accum; a.accum_mode = accum_mode; a.accum_scale = accum_scale;
+    a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_in = t_in; a.t_out = t_out;
+    a.k = k; a.dilation = dilation; a.padding = padding; a.in_slope = in_slope; a.out_act = out_act;
+    return launch_conv1d(a, (cudaStream_t)stream);
+}
+
+int pmn_conv_transpose1d(
+    const float* x, const float* weight, const float* bias, float* out,
+    int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope, void* stream) {
+    return launch_conv_transpose1d(x, weight, bias, out, batch, c_in, c_out, t_in, k, stride,
+                                   in_slope, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// HiFi-GAN generator handle: weight store, weight-norm folding, forward.
+//
+// Replaces promonet.model.Generator (promonet/model/generator.py:84-197) with
+// MODEL='hifigan' (promonet/model/hifigan.py:13-70) for inference.
+#include <map>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "features.cuh"
+#include "generator.cuh"
+
+namespace pmn {
+
+namespace {
+
+constexpr int kNumFeatures = 113;   // config/static.py:47-52
+constexpr int kSpeakerChannels = 256;
+constexpr int kGlobalChannels = 258;  // static.py:40-43
+constexpr int kNumSpeakers = 109;     // static.py:58-59 (vctk)
+constexpr int kInitial = 512;         // HIFIGAN_UPSAMPLE_INITIAL_SIZE defaults.py:256
+constexpr int kStages = 4;
+constexpr int kUpKernel[kStages] = {16, 16, 4, 4};  // :259
+constexpr int kUpRate[kStages] = {8, 8, 2, 2};      // :262
+constexpr int kResKernel[3] = {3, 7, 11};           // :250
+constexpr int kResDilation[3] = {1, 3, 5};          // :253
+constexpr float kSlope = 0.1f;                      // :216
+constexpr int kHop = 256;
+
+struct Tensor {
+    float* data = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+
+struct PackedConv {
+    float* weight = nullptr;  // conv1d: (C_in, K, C_out); conv transpose: (C_in, C_out, K)
+    const float* bias = nullptr;
+    int c_in = 0, c_out = 0, k = 0;
+};
+
+}  // namespace
+
+}  // namespace pmn
+
+struct pmn_generator {
+    std::map<std::string, pmn::Tensor> tensors;
+    std::vector<float*> owned;  // finalize-time allocations
+    bool finalized = false;
+    int math = PMN_MATH_FP32_SIMT;
+    float ppg_threshold = 0.85f;
+
+    pmn::PackedConv up[pmn::kStages];
+    pmn::PackedConv conv1[pmn::kStages][3][3];
+    pmn::PackedConv conv2[pmn::kStages][3][3];
+    float* input_weight = nullptr;  // packed (113, 7, 512)
+
+    ~pmn_generator() {
+        for (auto& item : tensors) cudaFree(item.second.data);
+        for (float* p : owned) cudaFree(p);
+    }
+};
+
+namespace pmn {
+
+namespace {
+
+int alloc(pmn_generator* g, size_t count, float** out) {
+    PMN_TRY(check_cuda(cudaMalloc(out, count * sizeof(float)), "cudaMalloc"));
+    g->owned.push_back(*out);
+    return PMN_OK;
+}
+
+int find(const pmn_generator* g, const std::string& name, const Tensor** out) {
+    auto it = g->tensors.find(name);
+    if (it == g->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
+    *out = &it->second;
+    return PMN_OK;
+}
+
+// Resolve `<prefix>.weight`, folding `<prefix>.weight_g/_v` when that is what the
+// checkpoint holds (weight_norm keys, SURVEY 5 "Checkpoint / resume")
+int folded_weight(pmn_generator* g, const std::string& prefix, const Tensor** v_out,
+                  const float** w_out, cudaStream_t stream) {
+    auto plain = g->tensors.find(prefix + ".weight");
+    if (plain != g->tensors.end()) {
+        *v_out = &plain->second;
+        *w_out = plain->second.data;
+        return PMN_OK;
+    }
+    const Tensor *wg, *wv;
+    PMN_TRY(find(g, prefix + ".weight_g", &wg));
+    PMN_TRY(find(g, prefix + ".weight_v", &wv));
+    if (wv->shape.size() != 3 || wg->numel() != (size_t)wv->shape[0])
+        return fail(PMN_ERR_STATE, "bad weight_g/weight_v shapes at " + prefix);
+    float* w;
+    PMN_TRY(alloc(g, wv->numel(), &w));
+    PMN_TRY(launch_weight_norm_fold(
+        wv->data, wg->data, w, (int)wv->shape[0], (int)(wv->shape[1] * wv->shape[2]), stream));
+    *v_out = wv;
+    *w_out = w;
+    return PMN_OK;
+}
+
+int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int k,
+                 PackedConv* conv, cudaStream_t stream) {
+    const Tensor* shape;
+    const float* w;
+    PMN_TRY(folded_weight(g, prefix, &shape, &w, stream));
+    if (shape->shape[0] != channels || shape->shape[1] != channels || shape->shape[2] != k)
+        return fail(PMN_ERR_STATE, "unexpected conv shape at " + prefix);
+    const Tensor* bias;
+    PMN_TRY(find(g, prefix + ".bias", &bias));
+    conv->c_in = conv->c_out = channels;
+    conv->k = k;
+    conv->bias = bias->data;
+    PMN_TRY(alloc(g, shape->numel(), &conv->weight));
+    return launch_pack_conv1d_weight(w, conv->weight, channels, channels, k, stream);
+}
+
+struct Workspace {
+    float *features, *speaker_bias, *x_in, *x0, *xt, *cur, *mrf;
+    size_t bytes;
+};
+
+Workspace carve(void* base, int batch, int frames) {
+    Workspace w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t count) {
+        float* r = reinterpret_cast<float*>(p);
+        p += align_up(count * sizeof(float), 256);
+        return r;
+    };
+    const size_t stage = (size_t)batch * 8192 * frames;  // max C*T over stages = 32 * 256 F
+    w.features = take((size_t)batch * (kNumFeatures + 1) * frames);
+    w.speaker_bias = take((size_t)batch * kInitial);
+    w.x_in = take((size_t)batch * kInitial * frames);
+    w.x0 = take(stage);
+    w.xt = take(stage);
+    w.cur = take(stage);
+    w.mrf = take(stage);
+    w.bytes = (size_t)(p - static_cast<char*>(base));
+    return w;
+}
+
+}  // namespace
+
+pmn_generator* generator_create() { return new (std::nothrow) pmn_generator(); }
+void generator_destroy(pmn_generator* g) { delete g; }
+
+int generator_set_tensor(
+    pmn_generator* g, const char* name, const float* data, const int64_t* shape, int ndim,
+    cudaStream_t stream) {
+    if (g->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
+    Tensor t;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
+        t.shape.push_back(shape[i]);
+    }
+    const size_t bytes = t.numel() * sizeof(float);
+    PMN_TRY(check_cuda(cudaMalloc(&t.data, bytes), "cudaMalloc"));
+    int status = check_cuda(
+        cudaMemcpyAsync(t.data, data, bytes, cudaMemcpyDeviceToDevice, stream), "set_tensor copy");
+    if (status != PMN_OK) {
+        cudaFree(t.data);
+        return status;
+    }
+    auto old = g->tensors.find(name);
+    if (old != g->tensors.end()) {
+        cudaFree(old->second.data);
+        g->tensors.erase(old);
+    }
+    g->tensors.emplace(name, std::move(t));
+    return PMN_OK;
+}
+
+int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
+    if (g->finalized) return fail(PMN_ERR_STATE, "generator already finalized");
+    if (math != PMN_MATH_FP32_SIMT)
+        return fail(PMN_ERR_ARGUMENT, "generator: unsupported math mode");
+    g->math = math;
+
+    const Tensor* t;
+    PMN_TRY(find(g, "model.input_feature_conv.weight", &t));
+    if (t->shape.size() != 3 || t->shape[0] != kInitial || t->shape[1] != kNumFeatures || t->shape[2] != 7)
+        return fail(PMN_ERR_STATE, "unexpected input_feature_conv shape");
+    PMN_TRY(alloc(g, t->numel(), &g->input_weight));
+    PMN_TRY(launch_pack_conv1d_weight(t->data, g->input_weight, kInitial, kNumFeatures, 7, stream));
+    PMN_TRY(find(g, "model.input_feature_conv.bias", &t));
+    PMN_TRY(find(g, "model.input_speaker_conv.weight", &t));
+    if (t->numel() != (size_t)kInitial * kGlobalChannels)
+        return fail(PMN_ERR_STATE, "unexpected input_speaker_conv shape");
+    PMN_TRY(find(g, "model.input_speaker_conv.bias", &t));
+    PMN_TRY(find(g, "speaker_embedding.weight", &t));
+    if (t->numel() != (size_t)kNumSpeakers * kSpeakerChannels)
+        return fail(PMN_ERR_STATE, "unexpected speaker_embedding shape");
+    PMN_TRY(find(g, "pitch_embedding.weight", &t));
+    if (t->numel() != 256 * 64) return fail(PMN_ERR_STATE, "unexpected pitch_embedding shape");
+    PMN_TRY(find(g, "pitch_distribution", &t));
+    if (t->numel() != 256) return fail(PMN_ERR_STATE, "unexpected pitch_distribution shape");
+    PMN_TRY(find(g, "model.model.5.weight", &t));
+    if (t->numel() != 32 * 7) return fail(PMN_ERR_STATE, "unexpected output conv shape");
+    auto threshold = g->tensors.find("ppg_threshold");
+    if (threshold != g->tensors.end()) {
+        PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
+        PMN_TRY(check_cuda(
+            cudaMemcpy(&g->ppg_threshold, threshold->second.data, sizeof(float), cudaMemcpyDeviceToHost),
+            "read ppg_threshold"));
+    }
+
+    int channels = kInitial;
+    for (int s = 0; s < kStages; ++s) {
+        const std::string stage = "model.model." + std::to_string(s) + ".model";
+        const Tensor* shape;
+        const float* w;
+        PMN_TRY(folded_weight(g, stage + ".1", &shape, &w, stream));
+        if (shape->shape[0] != channels || shape->shape[1] != channels / 2 || shape->shape[2] != kUpKernel[s])
+            return fail(PMN_ERR_STATE, "unexpected upsample shape at " + stage);
+        const Tensor* bias;
+        PMN_TRY(find(g, stage + ".1.bias", &bias));
+        g->up[s].weight = const_cast<float*>(w);
+        g->up[s].bias = bias->data;
+        g->up[s].c_in = channels;
+        g->up[s].c_out = channels / 2;
+        g->up[s].k = kUpKernel[s];
+        channels /= 2;
+        for (int j = 0; j < 3; ++j) {
+            const std::string block = stage + ".2.model." + std::to_string(j);
+            for (int d = 0; d < 3; ++d) {
+                PMN_TRY(prepare_conv(g, block + ".convs1." + std::to_string(d), channels,
+                                     kResKernel[j], &g->conv1[s][j][d], stream));
+                PMN_TRY(prepare_conv(g, block + ".convs2." + std::to_string(d), channels,
+                                     kResKernel[j], &g->conv2[s][j][d], stream));
+            }
+        }
+    }
+    PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "finalize sync"));
+    g->finalized = true;
+    return PMN_OK;
+}
+
+size_t generator_workspace_bytes(int batch, int frames) {
+    return carve(nullptr, batch, frames).bytes;
+}
+
+int generator_features(
+    pmn_generator* g, const float* loudness, int rows, const float* pitch,
+    const float* periodicity, const float* ppg, float* features, int batch, int frames,
+    cudaStream_t stream) {
+    if (!g->finalized) return fail(PMN_ERR_STATE, "generator not finalized");
+    return launch_features(
+        loudness, rows, pitch, periodicity, ppg,
+        g->tensors.at("pitch_distribution").data, g->tensors.at("pitch_embedding.weight").data,
+        g->ppg_threshold, false, features, batch, frames, stream);
+}
+
+int generator_forward(
+    pmn_generator* g, const float* loudness, int rows, const float* pitch,
+    const float* periodicity, const float* ppg, const int64_t* speakers,
+    const float* sbr, const float* lr, float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!g->finalized) return fail(PMN_ERR_STATE, "generator not finalized");
+    PMN_REQUIRE(batch > 0 && frames > 0, "generator: empty batch");
+    PMN_REQUIRE(audio && workspace, "generator: null pointer");
+    Workspace w = carve(workspace, batch, frames);
+    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "generator: workspace too small");
+
+    // G1: features (B, 113, F)
+    PMN_TRY(generator_features(g, loudness, rows, pitch, periodicity, ppg, w.features, batch, frames, stream));
+    // G2 + speaker 1x1 conv: (B, 512) bias
+    PMN_TRY(launch_speaker_bias(
+        g->tensors.at("speaker_embedding.weight").data, speakers, sbr, lr,
+        g->tensors.at("model.input_speaker_conv.weight").data,
+        g->tensors.at("model.input_speaker_conv.bias").data,
+        w.speaker_bias, batch, kSpeakerChannels, kInitial, kNumSpeakers, stream));
+    // G3: input conv k7 + speaker bias
+    {
+        Conv1dArgs a;
+        a.x = w.features; a.weight = g->input_weight;
+        a.bias = g->tensors.at("model.input_feature_conv.bias").data;
+        a.bias2 = w.speaker_bias;
+        a.out = w.x_in;
+        a.batch = batch; a.c_in = kNumFeatures; a.c_out = kInitial;
+        a.t_in = a.t_out = frames; a.k = 7; a.padding = 3;
+        PMN_TRY(launch_conv1d(a, stream));
+    }
+
+    const float* stage_in = w.x_in;
+    int t_len = frames;
+    for (int s = 0; s < kStages; ++s) {
+        // G4: LeakyReLU + ConvTranspose1d
+        const PackedConv& up = g->up[s];
+        PMN_TRY(launch_conv_transpose1d(
+            stage_in, up.weight, up.bias, w.x0, batch, up.c_in, up.c_out, t_len,
+            up.k, kUpRate[s], kSlope, stream));
+        t_len *= kUpRate[s];
+        const int channels = up.c_out;
+        // G5/G6: three Blocks, mean folded into the last conv of each
+        for (int j = 0; j < 3; ++j) {
+            const float* block_in = w.x0;
+            for (int d = 0; d < 3; ++d) {
+                const PackedConv& c1 = g->conv1[s][j][d];
+                const PackedConv& c2 = g->conv2[s][j][d];
+                Conv1dArgs a;
+                a.batch = batch; a.c_in = a.c_out = channels; a.t_in = a.t_out = t_len;
+                a.k = c1.k; a.in_slope = kSlope;
+                a.x = block_in; a.weight = c1.weight; a.bias = c1.bias; a.out = w.xt;
+                a.dilation = kResDilation[d];
+                a.padding = kResDilation[d] * (c1.k - 1) / 2;
+                PMN_TRY(launch_conv1d(a, stream));
+                a.x = w.xt; a.weight = c2.weight; a.bias = c2.bias;
+                a.dilation = 1; a.padding = (c2.k - 1) / 2;
+                a.residual = block_in;
+                if (d < 2) {
+                    a.out = w.cur;
+                } else {
+                    a.out = nullptr;
+                    a.accum = w.mrf;
+                    a.accum_mode = j == 0 ? 1 : 2;
+                    a.accum_scale = 1.f / 3.f;
+                }
+                PMN_TRY(launch_conv1d(a, stream));
+                block_in = w.cur;
+            }
+        }
+        stage_in = w.mrf;
+    }
+    // G7: LeakyReLU + Conv1d(32 -> 1, k7, no bias) + tanh
+    return launch_head(stage_in, g->tensors.at("model.model.5.weight").data, audio, batch, 32,
+                       t_len, kSlope, stream);
+}
+
+}  // namespace pmn

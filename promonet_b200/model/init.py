@@ -1,0 +1,97 @@
+"""Random initialisation of a generator state dict
+
+`promonet.model.Generator()` (promonet/model/generator.py:84-114) is what the
+reference means by a random-init generator.  This builds the same state dict
+(same keys, shapes, distributions) and draws from the torch RNG in the same
+order as that constructor does, so that under the same seed the tensors are
+bit-identical to the reference's -- which is what lets tests/golden pin the
+CUDA path against outputs of the real reference without shipping 57 MB of
+weights.  Order of draws: HiFiGAN (input convs, then per stage the transposed
+conv and the 3 Blocks' convs1/convs2, each ModuleList followed by the
+`init_weights` normal_ draws of hifigan.py:220-223, which land in `.weight`
+and are discarded by weight norm but still advance the RNG), output conv,
+speaker embedding, pitch embedding.
+"""
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from promonet_b200 import config
+
+ASSETS = Path(__file__).resolve().parent.parent / 'assets'
+
+
+def pitch_distribution():
+    """Pitch bin edges (promonet.load.pitch_distribution, load.py:54-71;
+    values of assets/stats/vctk-256-loudness-pitch-viterbi.pt)"""
+    return torch.from_numpy(np.load(ASSETS / 'pitch_distribution.npy'))
+
+
+def _conv(state, name, module):
+    state[f'{name}.weight'] = module.weight.detach().clone()
+    if module.bias is not None:
+        state[f'{name}.bias'] = module.bias.detach().clone()
+
+
+def _weight_norm_conv(state, name, module):
+    """Keys in the order torch.nn.utils.weight_norm registers them"""
+    v = module.weight.detach().clone()
+    g = v.flatten(1).norm(dim=1).reshape(-1, *([1] * (v.ndim - 1)))
+    state[f'{name}.bias'] = module.bias.detach().clone()
+    state[f'{name}.weight_g'] = g
+    state[f'{name}.weight_v'] = v
+
+
+def _discard_init_weights(module):
+    # hifigan.py:220-223 draws normal_(0, 0.01) into `.weight`
+    torch.empty_like(module.weight).normal_(0., 0.01)
+
+
+def hifigan_state(seed=None):
+    """State dict of a freshly constructed hifigan Generator"""
+    if seed is not None:
+        torch.manual_seed(seed)
+    state = OrderedDict()
+    state['default_previous_samples'] = torch.zeros(1, 1, 1)
+    initial = config.HIFIGAN_UPSAMPLE_INITIAL_SIZE
+    _conv(state, 'model.input_feature_conv',
+          torch.nn.Conv1d(config.NUM_FEATURES, initial, 7, 1, padding=3))
+    _conv(state, 'model.input_speaker_conv',
+          torch.nn.Conv1d(config.GLOBAL_CHANNELS, initial, 1))
+    channels = initial
+    for i, (k, s) in enumerate(zip(
+        config.HIFIGAN_UPSAMPLE_KERNEL_SIZES,
+        config.HIFIGAN_UPSAMPLE_RATES
+    )):
+        stage = f'model.model.{i}.model'
+        up = torch.nn.ConvTranspose1d(
+            channels, channels // 2, k, s, padding=(k - s) // 2)
+        channels //= 2
+        blocks = []
+        for j, kernel in enumerate(config.HIFIGAN_RESBLOCK_KERNEL_SIZES):
+            for group in ('convs1', 'convs2'):
+                convs = [
+                    torch.nn.Conv1d(channels, channels, kernel)
+                    for _ in config.HIFIGAN_RESBLOCK_DILATION_SIZES]
+                for conv in convs:
+                    _discard_init_weights(conv)
+                blocks.append((f'{stage}.2.model.{j}.{group}', convs))
+        # MultiReceptiveFieldFusion applies init_weights to the upsampler after
+        # the ResidualBlock has been constructed (hifigan.py:95-112)
+        _discard_init_weights(up)
+        _weight_norm_conv(state, f'{stage}.1', up)
+        for name, convs in blocks:
+            for d, conv in enumerate(convs):
+                _weight_norm_conv(state, f'{name}.{d}', conv)
+    _conv(state, f'model.model.{len(config.HIFIGAN_UPSAMPLE_RATES) + 1}',
+          torch.nn.Conv1d(channels, 1, 7, 1, 3, bias=False))
+    state['speaker_embedding.weight'] = torch.nn.Embedding(
+        config.NUM_SPEAKERS, config.SPEAKER_CHANNELS).weight.detach().clone()
+    state['pitch_embedding.weight'] = torch.nn.Embedding(
+        config.PITCH_BINS, config.PITCH_EMBEDDING_SIZE).weight.detach().clone()
+    state['ppg_threshold'] = torch.tensor(
+        config.SPARSE_PPG_THRESHOLD, dtype=torch.float)
+    state['pitch_distribution'] = pitch_distribution()
+    return state

@@ -1,0 +1,93 @@
+"""Pin the CPU oracle: against the golden vectors frozen from the reference,
+and against the reference itself when /root/reference is present"""
+import pytest
+import torch
+
+from conftest import relative_error
+from oracle import dsp, features, hifigan, inputs, ref_shim
+from promonet_b200.model import init
+
+
+@pytest.fixture(scope='module')
+def state():
+    return init.hifigan_state(1234)
+
+
+def test_seeded_init_matches_reference_checksums(golden, state):
+    g = golden('generator')
+    for name, value in zip(g['checksum_names'], g['checksum_values']):
+        assert float(state[str(name)].double().abs().sum()) == pytest.approx(
+            float(value), rel=1e-12), name
+
+
+@pytest.mark.parametrize('tag', ['r8', 'r513'])
+def test_generator_oracle_matches_reference_output(golden, state, tag):
+    g = golden('generator')
+    args = [g[f'{tag}_{k}'] for k in (
+        'loudness', 'pitch', 'periodicity', 'ppg', 'speakers', 'sbr', 'lr')]
+    with torch.no_grad():
+        feats = features.prepare_features(state, *args[:4])
+        audio = hifigan.generator(state, *args)
+    assert torch.equal(feats, g[f'{tag}_features'])
+    assert relative_error(audio, g[f'{tag}_audio']) < 1e-5
+
+
+@pytest.mark.parametrize('tag,kernel', [('c32k3', 3), ('c64k11', 11)])
+def test_block_oracle_matches_reference(golden, tag, kernel):
+    g = golden('block')
+    state = {
+        k[len(tag) + 1:]: v for k, v in g.items()
+        if k.startswith(tag) and k not in (f'{tag}_x', f'{tag}_y')}
+    state = {f'b.{k}': v for k, v in state.items()}
+    with torch.no_grad():
+        y = hifigan.block(state, 'b', g[f'{tag}_x'], kernel)
+    assert relative_error(y, g[f'{tag}_y']) < 1e-6
+
+
+def test_spectrogram_oracle_matches_reference(golden):
+    g = golden('spectrogram')
+    linear = dsp.magnitude(g['audio'])
+    assert relative_error(linear, g['linear']) < 1e-6
+    assert relative_error(dsp.linear_to_mel(linear), g['mels']) < 1e-5
+
+
+def test_mel_basis_cross_check():
+    import torchaudio
+    other = torchaudio.functional.melscale_fbanks(
+        513, 0., 11025., 80, 22050, norm='slaney', mel_scale='slaney').T
+    assert (other - torch.from_numpy(dsp.mel_basis())).abs().max() < 1e-6
+
+
+def test_band_average_matches_reference(golden):
+    g = golden('loudness_bands')
+    assert torch.equal(features.band_average(g['loudness']), g['averaged'])
+    assert torch.equal(features.normalize(g['loudness']), g['normalized'])
+
+
+def test_sparsify_keeps_top_six():
+    ppg = torch.softmax(torch.randn(3, 40, 7), dim=-2)
+    sparse = features.sparsify(ppg)
+    assert torch.allclose(sparse.sum(-2), torch.ones(3, 7), atol=1e-6)
+    assert ((sparse > 1e-6).sum(-2) == 6).all()
+
+
+def test_loudness_oracle_properties():
+    audio = inputs.audio(1, 22050)
+    loud = dsp.loudness(audio, bands=None)
+    assert loud.shape == (513, 22050 // 256)
+    assert loud.min() >= -100. and loud.max() <= 40.
+    # top_db: nothing more than 80 dB below the loudest bin before weighting
+    assert dsp.loudness(audio).shape == (8, 86)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree absent')
+def test_oracle_against_live_reference(state):
+    promonet = ref_shim.load()
+    torch.manual_seed(promonet.RANDOM_SEED)
+    model = promonet.model.Generator().eval()
+    args = inputs.synthesis(1, 20, seed=7)
+    with torch.no_grad():
+        expected = model(*args, model.default_previous_samples)
+        actual = hifigan.generator(model.state_dict(), *args)
+    assert relative_error(actual, expected) < 1e-5
+    assert all(torch.equal(v, state[k]) for k, v in model.state_dict().items())
