@@ -40,6 +40,7 @@ METRIC = 'audio samples/sec synthesized (22.05 kHz)'
 UNIT = 'samples/s'
 # conv FLOPs (2 x MAC) per output sample, by kernel
 FLOP_PER_SAMPLE_CONV1D = (264.167165952e9 - 8.117e9 - 0.049e9) / SAMPLES
+FLOP_PER_SAMPLE_RESBLOCKS = FLOP_PER_SAMPLE_CONV1D - 0.348e9 / SAMPLES
 FLOP_PER_SAMPLE_TOTAL = 264.167165952e9 / SAMPLES
 
 
@@ -270,12 +271,13 @@ def run_b200(args):
     e2e_seconds = float(e2e_seconds)
 
     # Roofline of the dominant kernel: same steps again with per-launch CUDA events
-    dominant = 'conv1d_kernel' if math == _lib.MATH_FP32_SIMT else 'resblock_tc_kernel'
+    dominant = 'conv1d_kernel' if math == _lib.MATH_FP32_SIMT else 'conv1d_tc_kernel'
     _lib.profile(True)
     timed(resident, args.steps)
     kernel_ms, kernel_launches = _lib.profile_read(dominant)
     shares = {}
-    for name in ('conv1d_kernel', 'resblock_tc_kernel', 'conv_transpose1d_kernel',
+    for name in ('conv1d_kernel', 'conv1d_tc_kernel', 'conv_transpose1d_kernel',
+                 'planes_from_f32_kernel', 'zero_plane_pads_kernel',
                  'head_kernel', 'features_kernel', 'speaker_bias_kernel'):
         total, count = _lib.profile_read(name)
         if count:
@@ -285,7 +287,9 @@ def run_b200(args):
     if rank == 0:
         peak = peaks()
         total_samples = world * BATCH * SAMPLES * args.steps
-        flops = BATCH * SAMPLES * FLOP_PER_SAMPLE_CONV1D * args.steps
+        flop_per_sample = (
+            FLOP_PER_SAMPLE_CONV1D if math == _lib.MATH_FP32_SIMT else FLOP_PER_SAMPLE_RESBLOCKS)
+        flops = BATCH * SAMPLES * flop_per_sample * args.steps
         achieved = flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None
         result = {
             'metric': METRIC,

@@ -140,6 +140,22 @@ int pmn_conv1d(
     int k, int dilation, int padding, float in_slope, int out_act,
     void* stream);
 
+/* The same convolution ("same" padding, odd k, C_in = C_out in {32, 64, 128, 256})
+ * on the tcgen05 tensor cores with a 3-product bf16 hi/lo split and fp32
+ * accumulation in TMEM (promonet_b200/csrc/conv1d_tc.cu).  Takes plain fp32
+ * tensors: x is converted to hi/lo planes of lrelu(x, in_slope) and `weight`
+ * (C_out, C_in, K), already weight-norm folded, is packed into slabs inside
+ * `workspace` (pmn_conv1d_tc_workspace_bytes), so this entry point measures
+ * parity, not speed.  planes_out, if not NULL, receives hi + lo of the bf16
+ * planes of lrelu(y, out_slope) that the next convolution would consume. */
+size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k);
+int pmn_conv1d_tc(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation,
+    float in_slope, float out_slope,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 /* LeakyReLU + ConvTranspose1d with kernel = 2*stride, padding = stride/2
  * (hifigan.py:97-106; PyTorch weight layout (C_in, C_out, K)), T_out = stride*T_in */
 int pmn_conv_transpose1d(

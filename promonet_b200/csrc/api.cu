@@ -2,6 +2,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "conv1d_tc.cuh"
 #include "generator.cuh"
 
 #include <map>
@@ -99,9 +100,9 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream) {
     return generator_finalize(g, math, (cudaStream_t)stream);
 }
 
-size_t pmn_generator_workspace_bytes(const pmn_generator*, int batch, int frames) {
-    if (batch <= 0 || frames <= 0) return 0;
-    return generator_workspace_bytes(batch, frames);
+size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames) {
+    if (!g || batch <= 0 || frames <= 0) return 0;
+    return generator_workspace_bytes(g, batch, frames);
 }
 
 int pmn_generator_forward(
@@ -205,6 +206,59 @@ int pmn_conv1d(
     a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_in = t_in; a.t_out = t_out;
     a.k = k; a.dilation = dilation; a.padding = padding; a.in_slope = in_slope; a.out_act = out_act;
     return launch_conv1d(a, (cudaStream_t)stream);
+}
+
+namespace {
+struct TcOpWorkspace {
+    __nv_bfloat16 *x_planes, *y_planes, *slabs;
+    size_t bytes;
+};
+TcOpWorkspace carve_tc_op(void* base, int batch, int channels, int t_len, int k) {
+    TcOpWorkspace w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t elements) {
+        auto* r = reinterpret_cast<__nv_bfloat16*>(p);
+        p += align_up(elements * sizeof(__nv_bfloat16), 256);
+        return r;
+    };
+    w.x_planes = take(tc_planes_elements(batch, channels, t_len));
+    w.y_planes = take(tc_planes_elements(batch, channels, t_len));
+    w.slabs = take(tc_weight_elements(channels, channels, k));
+    w.bytes = (size_t)(p - static_cast<char*>(base));
+    return w;
+}
+}  // namespace
+
+size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k) {
+    if (batch <= 0 || channels <= 0 || t_len <= 0 || k <= 0) return 0;
+    return carve_tc_op(nullptr, batch, channels, t_len, k).bytes;
+}
+
+int pmn_conv1d_tc(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation, float in_slope, float out_slope,
+    void* workspace, size_t workspace_bytes, void* stream_) {
+    PMN_REQUIRE(x && weight && workspace, "conv1d_tc: null pointer");
+    PMN_REQUIRE(batch > 0 && t_len > 0, "conv1d_tc: empty input");
+    PMN_REQUIRE(tc_supported(channels, channels, k, dilation), "conv1d_tc: unsupported shape");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TcOpWorkspace w = carve_tc_op(workspace, batch, channels, t_len, k);
+    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "conv1d_tc: workspace too small");
+    PMN_TRY(launch_planes_from_f32(x, w.x_planes, batch, channels, t_len, in_slope, stream));
+    PMN_TRY(launch_pack_tc_weight(weight, w.slabs, channels, channels, k, stream));
+    TcConvArgs a;
+    a.x_planes = w.x_planes; a.w_slabs = w.slabs; a.bias = bias; a.residual = residual;
+    a.out = out; a.accum = accum; a.accum_mode = accum_mode; a.accum_scale = accum_scale;
+    a.batch = batch; a.c_in = a.c_out = channels; a.t_len = t_len; a.k = k; a.dilation = dilation;
+    a.out_slope = out_slope;
+    if (planes_out) {
+        a.out_planes = w.y_planes;
+        PMN_TRY(launch_zero_plane_pads(w.y_planes, batch, channels, t_len, stream));
+    }
+    PMN_TRY(launch_conv1d_tc(a, stream));
+    if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, channels, t_len, stream));
+    return PMN_OK;
 }
 
 int pmn_conv_transpose1d(

@@ -1,0 +1,519 @@
+// Dilated Conv1d on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-grade.
+//
+// The dense residual-block convolutions of HiFi-GAN (Block.forward,
+// promonet/model/hifigan.py:198-210; 97 % of the generator's FLOPs) as an
+// implicit GEMM per tap:
+//     D[t, o] = sum_j sum_c A_j[t, c] * W_j[c, o],   A_j[t, c] = a[c, t + (j - h) d]
+// with M = 128 time steps (TMEM lanes), N = C_out (TMEM columns), K = C_in.
+//
+// fp32 parity on bf16 tensor cores: every operand is split a = a_hi + a_lo
+// (bf16 each) and three products a_hi w_hi + a_lo w_hi + a_hi w_lo are
+// accumulated in fp32 in TMEM; the dropped a_lo w_lo term is 2^-16 relative.
+//
+// Operands are K-major, un-swizzled ("interleaved") core matrices laid out as
+// [k / 8][row][8]: rows are contiguous at 16 B, so the tap shift (j - h) d is a
+// plain 16 B-granular offset of the A descriptor's start address and one staged
+// time window (tile + halo) serves all K taps.  The global layout (conv1d_tc.cuh)
+// is the same, so staging is a handful of 1-D bulk async copies
+// (cp.async.bulk, completion on an mbarrier) per slab -- no tensor maps.
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0    producer: bulk copies of activation slabs (per 64-channel block)
+//             and weight slabs (per tap x block) into shared-memory rings
+//   warp 1    MMA issuer: one thread issues tcgen05.mma, commits to mbarriers
+//   warps 2-5 epilogue: tcgen05.ld accumulators, bias + residual + LeakyReLU,
+//             fp32 and/or hi/lo-plane stores, MRF accumulate (hifigan.py:141-145)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps
+// the MMAs of tile i + 1.
+#include "conv1d_tc.cuh"
+
+namespace pmn {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxHalo = 25;  // (11 - 1) / 2 * 5
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t address = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(address), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tc_load32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+        "%12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, "
+        "%30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
+// [0,14) start >> 4 | [16,30) leading byte offset >> 4 (stride between the two
+// 8-element K chunks) | [32,46) stride byte offset >> 4 (stride between 8-row
+// groups) | [46,48) version = 1 | [61,64) layout = 0 (SWIZZLE_NONE)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t address, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((address & 0x3FFFFu) >> 4) |
+           ((uint64_t)(lbo >> 4) << 16) |
+           ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ---------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------
+
+template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
+struct TcConfig {
+    static constexpr int kTile = S * 128;                   // time steps per tile
+    static constexpr int kRowsMax = kTile + 2 * kMaxHalo;
+    static constexpr int kGroups = KB / 8;                   // 8-channel groups per K block
+    static constexpr int kBlocks = C_IN / KB;
+    static constexpr int kXSlab = 2 * kGroups * kRowsMax * 16;  // bytes, both planes
+    static constexpr int kWSlab = KB * C_OUT * 4;               // bytes, both planes
+    static constexpr int kXStages = 2;
+    static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
+    static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128;
+    static constexpr int kColumns = AS * S * C_OUT;
+    static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
+                                  : kColumns <= 256 ? 256 : 512;
+    static_assert(kColumns <= 512, "accumulators exceed TMEM");
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+    static_assert(C_IN % KB == 0 && KB % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "shape");
+};
+
+template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
+__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, int t_pad, int tiles_per_item, int num_tiles) {
+    using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* x_slabs = smem;
+    uint8_t* w_slabs = smem + Cfg::kXStages * Cfg::kXSlab;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_slabs + NW * Cfg::kWSlab);
+    uint64_t* x_full = bars;
+    uint64_t* x_empty = x_full + Cfg::kXStages;
+    uint64_t* w_full = x_empty + Cfg::kXStages;
+    uint64_t* w_empty = w_full + NW;
+    uint64_t* acc_full = w_empty + NW;
+    uint64_t* acc_empty = acc_full + AS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + AS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int halo = (a.k - 1) / 2 * a.dilation;
+    const int rows = Cfg::kTile + 2 * halo;  // staged time window
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::kXStages; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+        for (int i = 0; i < NW; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+        for (int i = 0; i < AS; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kAlloc) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t xcount = 0, wcount = 0;
+            const uint32_t x_bytes = 2 * Cfg::kGroups * rows * 16;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int b = tile / tiles_per_item;
+                const int t0 = (tile % tiles_per_item) * Cfg::kTile;
+                for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
+                    const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
+                    ++xcount;
+                    mbar_wait(x_empty + xs, xphase ^ 1);
+                    mbar_expect_tx(x_full + xs, x_bytes);
+                    uint8_t* dst = x_slabs + xs * Cfg::kXSlab;
+#pragma unroll 1
+                    for (int p = 0; p < 2; ++p) {
+#pragma unroll 1
+                        for (int g = 0; g < Cfg::kGroups; ++g) {
+                            const size_t row0 =
+                                ((size_t)(b * 2 + p) * (C_IN / 8) + kb * Cfg::kGroups + g) * t_pad +
+                                kTcPad + t0 - halo;
+                            bulk_copy(dst + (p * Cfg::kGroups + g) * rows * 16,
+                                      a.x_planes + row0 * 8, rows * 16, x_full + xs);
+                        }
+                    }
+                    for (int tap = 0; tap < a.k; ++tap) {
+                        const uint32_t ws = wcount % NW, wphase = (wcount / NW) & 1;
+                        ++wcount;
+                        mbar_wait(w_empty + ws, wphase ^ 1);
+                        mbar_expect_tx(w_full + ws, Cfg::kWSlab);
+                        bulk_copy(w_slabs + ws * Cfg::kWSlab,
+                                  reinterpret_cast<const uint8_t*>(a.w_slabs) +
+                                      (size_t)(tap * Cfg::kBlocks + kb) * Cfg::kWSlab,
+                                  Cfg::kWSlab, w_full + ws);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(128, C_OUT);
+            uint32_t xcount = 0, wcount = 0, tcount = 0;
+            const uint32_t x_plane = Cfg::kGroups * rows * 16;      // bytes between hi and lo
+            constexpr uint32_t w_plane = Cfg::kGroups * C_OUT * 16;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
+                ++tcount;
+                mbar_wait(acc_empty + as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + as * (S * C_OUT);
+                for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
+                    const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
+                    ++xcount;
+                    mbar_wait(x_full + xs, xphase);
+                    const uint32_t x_addr = smem_u32(x_slabs + xs * Cfg::kXSlab);
+                    for (int tap = 0; tap < a.k; ++tap) {
+                        const uint32_t ws = wcount % NW, wphase = (wcount / NW) & 1;
+                        ++wcount;
+                        mbar_wait(w_full + ws, wphase);
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(w_slabs + ws * Cfg::kWSlab);
+                        const bool first = kb == 0 && tap == 0;
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const uint32_t row = s * 128 + tap * a.dilation;
+#pragma unroll
+                            for (int kk = 0; kk < KB / 16; ++kk) {
+                                const uint32_t xa = x_addr + (2 * kk * rows + row) * 16;
+                                const uint32_t wa = w_addr + 2 * kk * C_OUT * 16;
+                                const uint64_t a_hi = smem_desc(xa, rows * 16, 128);
+                                const uint64_t a_lo = smem_desc(xa + x_plane, rows * 16, 128);
+                                const uint64_t b_hi = smem_desc(wa, C_OUT * 16, 128);
+                                const uint64_t b_lo = smem_desc(wa + w_plane, C_OUT * 16, 128);
+                                const uint32_t d = d_base + s * C_OUT;
+                                tc_mma(d, a_hi, b_hi, idesc, !(first && kk == 0));
+                                tc_mma(d, a_lo, b_hi, idesc, 1);
+                                tc_mma(d, a_hi, b_lo, idesc, 1);
+                            }
+                        }
+                        tc_commit(w_empty + ws);
+                    }
+                    tc_commit(x_empty + xs);
+                }
+                tc_commit(acc_full + as);
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
+        const int quad = warp & 3;
+        uint32_t tcount = 0;
+        const int groups_out = C_OUT / 8;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_item;
+            const int t0 = (tile % tiles_per_item) * Cfg::kTile;
+            const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
+            ++tcount;
+            mbar_wait(acc_full + as, aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) {
+                const int t = t0 + s * 128 + quad * 32 + lane;
+                const bool valid = t < a.t_len;
+#pragma unroll 1
+                for (int c0 = 0; c0 < C_OUT; c0 += 32) {
+                    uint32_t raw[32];
+                    tc_load32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
+                    if (!valid) continue;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = c0 + i;
+                        float y = __uint_as_float(raw[i]);
+                        if (a.bias) y += __ldg(a.bias + c);
+                        const size_t idx = ((size_t)b * C_OUT + c) * a.t_len + t;
+                        if (a.residual) y += a.residual[idx];
+                        if (a.out) a.out[idx] = y;
+                        if (a.accum_mode == 1) a.accum[idx] = y * a.accum_scale;
+                        else if (a.accum_mode == 2) a.accum[idx] += y * a.accum_scale;
+                        v[i] = y;
+                    }
+                    if (a.out_planes) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float y0 = leaky(v[g * 8 + 2 * e], a.out_slope);
+                                const float y1 = leaky(v[g * 8 + 2 * e + 1], a.out_slope);
+                                const __nv_bfloat16 h0 = __float2bfloat16_rn(y0);
+                                const __nv_bfloat16 h1 = __float2bfloat16_rn(y1);
+                                hi[e] = pack_bf16(h0, h1);
+                                lo[e] = pack_bf16(__float2bfloat16_rn(y0 - __bfloat162float(h0)),
+                                                  __float2bfloat16_rn(y1 - __bfloat162float(h1)));
+                            }
+                            const size_t row_hi =
+                                ((size_t)(b * 2) * groups_out + (c0 / 8 + g)) * t_pad + kTcPad + t;
+                            const size_t row_lo = row_hi + (size_t)groups_out * t_pad;
+                            *reinterpret_cast<uint4*>(a.out_planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(a.out_planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + as);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "n"(Cfg::kAlloc) : "memory");
+    }
+}
+
+// fp32 (B, C, T) -> hi/lo planes of lrelu(x); rows outside [0, T) are zeroed
+__global__ void __launch_bounds__(128) planes_from_f32_kernel(
+    const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
+    int channels, int t_len, int t_pad, float slope) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= t_pad) return;
+    const int g = blockIdx.y, b = blockIdx.z;
+    const int groups = channels / 8;
+    const int t = row - kTcPad;
+    uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (t >= 0 && t < t_len) {
+        const float* src = x + ((size_t)b * channels + g * 8) * t_len + t;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float y0 = leaky(__ldg(src + (size_t)(2 * e) * t_len), slope);
+            const float y1 = leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+            hi[e] = pack_bf16(h0, h1);
+            lo[e] = pack_bf16(__float2bfloat16_rn(y0 - __bfloat162float(h0)),
+                              __float2bfloat16_rn(y1 - __bfloat162float(h1)));
+        }
+    }
+    const size_t row_hi = ((size_t)(b * 2) * groups + g) * t_pad + row;
+    const size_t row_lo = row_hi + (size_t)groups * t_pad;
+    *reinterpret_cast<uint4*>(planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// planes -> fp32 (B, C, T): hi + lo (tests / debugging)
+__global__ void __launch_bounds__(128) f32_from_planes_kernel(
+    const __nv_bfloat16* __restrict__ planes, float* __restrict__ x,
+    int channels, int t_len, int t_pad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_len) return;
+    const int g = blockIdx.y, b = blockIdx.z;
+    const int groups = channels / 8;
+    const size_t row_hi = ((size_t)(b * 2) * groups + g) * t_pad + kTcPad + t;
+    const size_t row_lo = row_hi + (size_t)groups * t_pad;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        x[((size_t)b * channels + g * 8 + e) * t_len + t] =
+            __bfloat162float(planes[row_hi * 8 + e]) + __bfloat162float(planes[row_lo * 8 + e]);
+}
+
+// Zero the pad rows [0, kTcPad) and [kTcPad + T, t_pad) of every (b, plane, group)
+__global__ void __launch_bounds__(128) zero_plane_pads_kernel(
+    __nv_bfloat16* __restrict__ planes, int t_len, int t_pad) {
+    uint4* rows = reinterpret_cast<uint4*>(planes) + (size_t)blockIdx.x * t_pad;
+    const int tail = t_pad - kTcPad - t_len;
+    for (int i = threadIdx.x; i < kTcPad + tail; i += blockDim.x)
+        rows[i < kTcPad ? i : t_len + i] = make_uint4(0, 0, 0, 0);
+}
+
+// (C_out, C_in, K) fp32 -> [tap][c_in / KB][plane][KB / 8][c_out][8] bf16
+__global__ void pack_tc_weight_kernel(
+    const float* __restrict__ w, __nv_bfloat16* __restrict__ slabs,
+    int c_out, int c_in, int k, int kb_size) {
+    const size_t total = (size_t)c_out * c_in * k;
+    const int groups = kb_size / 8;
+    const int blocks = c_in / kb_size;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t rest = idx;
+        const int e = rest % 8; rest /= 8;
+        const int o = rest % c_out; rest /= c_out;
+        const int g = rest % groups; rest /= groups;
+        const int kb = rest % blocks; rest /= blocks;
+        const int tap = (int)rest;
+        const int c = kb * kb_size + g * 8 + e;
+        const float value = w[((size_t)o * c_in + c) * k + tap];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(value);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(value - __bfloat162float(hi));
+        const size_t slab = (size_t)(tap * blocks + kb) * 2;
+        const size_t inner = ((size_t)g * c_out + o) * 8 + e;
+        const size_t plane = (size_t)groups * c_out * 8;
+        slabs[slab * plane + inner] = hi;
+        slabs[(slab + 1) * plane + inner] = lo;
+    }
+}
+
+int sm_count() {
+    static int count = 0;
+    if (!count) {
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+    }
+    return count;
+}
+
+template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
+int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
+    using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
+    auto kernel = conv1d_tc_kernel<C_IN, C_OUT, S, KB, NW, AS>;
+    static bool configured = false;
+    if (!configured) {
+        PMN_TRY(check_cuda(
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem),
+            "conv1d_tc smem attribute"));
+        configured = true;
+    }
+    const int tiles_per_item = ceil_div(a.t_len, Cfg::kTile);
+    const int num_tiles = tiles_per_item * a.batch;
+    const int grid = min(num_tiles, sm_count());
+    LaunchScope scope("conv1d_tc_kernel", stream);
+    kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(a, tc_padded_length(a.t_len), tiles_per_item, num_tiles);
+    return launched("conv1d_tc_kernel");
+}
+
+}  // namespace
+
+bool tc_supported(int c_in, int c_out, int k, int dilation) {
+    if (c_in != c_out) return false;
+    if (c_in != 32 && c_in != 64 && c_in != 128 && c_in != 256) return false;
+    return k % 2 == 1 && (k - 1) / 2 * dilation <= kMaxHalo;
+}
+
+int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
+    PMN_REQUIRE(a.x_planes && a.w_slabs, "conv1d_tc: null input");
+    PMN_REQUIRE(a.out || a.out_planes || (a.accum && a.accum_mode), "conv1d_tc: no output");
+    PMN_REQUIRE(a.batch > 0 && a.t_len > 0, "conv1d_tc: empty input");
+    PMN_REQUIRE(tc_supported(a.c_in, a.c_out, a.k, a.dilation), "conv1d_tc: unsupported shape");
+    switch (a.c_in) {
+        case 256: return launch_variant<256, 256, 1, 32, 3, 2>(a, stream);
+        case 128: return launch_variant<128, 128, 2, 64, 2, 2>(a, stream);
+        case 64: return launch_variant<64, 64, 2, 64, 4, 2>(a, stream);
+        default: return launch_variant<32, 32, 4, 32, 4, 2>(a, stream);
+    }
+}
+
+int launch_planes_from_f32(
+    const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
+    cudaStream_t stream) {
+    PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "planes_from_f32: bad argument");
+    const int t_pad = tc_padded_length(t_len);
+    dim3 grid(ceil_div(t_pad, 128), channels / 8, batch);
+    LaunchScope scope("planes_from_f32_kernel", stream);
+    planes_from_f32_kernel<<<grid, 128, 0, stream>>>(x, planes, channels, t_len, t_pad, slope);
+    return launched("planes_from_f32_kernel");
+}
+
+int launch_f32_from_planes(
+    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream) {
+    PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "f32_from_planes: bad argument");
+    dim3 grid(ceil_div(t_len, 128), channels / 8, batch);
+    LaunchScope scope("f32_from_planes_kernel", stream);
+    f32_from_planes_kernel<<<grid, 128, 0, stream>>>(planes, x, channels, t_len, tc_padded_length(t_len));
+    return launched("f32_from_planes_kernel");
+}
+
+int launch_zero_plane_pads(
+    __nv_bfloat16* planes, int batch, int channels, int t_len, cudaStream_t stream) {
+    PMN_REQUIRE(planes && channels % 8 == 0 && batch > 0 && t_len > 0, "zero_plane_pads: bad argument");
+    LaunchScope scope("zero_plane_pads_kernel", stream);
+    zero_plane_pads_kernel<<<batch * 2 * (channels / 8), 128, 0, stream>>>(
+        planes, t_len, tc_padded_length(t_len));
+    return launched("zero_plane_pads_kernel");
+}
+
+int launch_pack_tc_weight(
+    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, cudaStream_t stream) {
+    PMN_REQUIRE(w && slabs && c_in % tc_k_block(c_in) == 0, "pack_tc_weight: bad argument");
+    const size_t total = (size_t)c_out * c_in * k;
+    const int blocks = (int)min((size_t)2048, (total + 255) / 256);
+    LaunchScope scope("pack_tc_weight_kernel", stream);
+    pack_tc_weight_kernel<<<blocks, 256, 0, stream>>>(w, slabs, c_out, c_in, k, tc_k_block(c_in));
+    return launched("pack_tc_weight_kernel");
+}
+
+}  // namespace pmn

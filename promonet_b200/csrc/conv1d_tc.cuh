@@ -1,0 +1,64 @@
+// tcgen05 dilated Conv1d (conv1d_tc.cu): operand layout and launchers
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pmn {
+
+// Activations for the tensor-core path are stored as two bf16 "planes" (hi, lo)
+// with a = hi + lo to ~16 mantissa bits, channel-chunked and time-major:
+//   planes[b][plane][c / 8][kTcPad + t][c % 8],   t in [-kTcPad, t_pad - kTcPad)
+// Rows outside [0, T) are zero: they are the convolution's zero padding.
+// A (time x channel) operand tile is then a set of contiguous runs, one per
+// 8-channel group, and a tap shift is a row shift (16 B) of the operand address.
+constexpr int kTcPad = 32;       // >= max halo (k-1)/2 * dilation = 25
+constexpr int kTcTimeAlign = 512;
+
+inline int tc_padded_length(int t_len) {
+    return kTcPad + (t_len + kTcTimeAlign - 1) / kTcTimeAlign * kTcTimeAlign + kTcPad;
+}
+inline size_t tc_planes_elements(int batch, int channels, int t_len) {
+    return (size_t)batch * 2 * channels * tc_padded_length(t_len);
+}
+// Weight slabs: [tap][c_in / KB][plane][KB / 8][c_out][8] bf16, KB = tc_k_block(c_in)
+inline int tc_k_block(int c_in) { return c_in >= 256 ? 32 : (c_in >= 64 ? 64 : 32); }
+inline size_t tc_weight_elements(int c_out, int c_in, int k) { return (size_t)2 * c_out * c_in * k; }
+bool tc_supported(int c_in, int c_out, int k, int dilation);
+
+struct TcConvArgs {
+    const __nv_bfloat16* x_planes = nullptr;  // lrelu already applied by the producer
+    const __nv_bfloat16* w_slabs = nullptr;
+    const float* bias = nullptr;              // (C_out) or null
+    const float* residual = nullptr;          // (B, C_out, T) fp32 or null
+    float* out = nullptr;                     // (B, C_out, T) fp32 or null
+    __nv_bfloat16* out_planes = nullptr;      // planes of lrelu(y, out_slope) or null
+    float* accum = nullptr;                   // (B, C_out, T) fp32 or null
+    int accum_mode = 0;                       // 0 unused, 1 store, 2 add
+    float accum_scale = 1.f;
+    int batch = 0, c_in = 0, c_out = 0, t_len = 0;
+    int k = 1, dilation = 1;                  // "same" padding (k - 1) / 2 * dilation
+    float out_slope = 1.f;
+};
+
+int launch_conv1d_tc(const TcConvArgs& args, cudaStream_t stream);
+
+// fp32 (B, C, T) -> planes of lrelu(x, slope); also writes the zero pad rows
+int launch_planes_from_f32(
+    const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
+    cudaStream_t stream);
+
+// planes -> fp32 (hi + lo), for tests
+int launch_f32_from_planes(
+    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream);
+
+// Zero only the pad rows of a planes buffer (the kernels never write them)
+int launch_zero_plane_pads(
+    __nv_bfloat16* planes, int batch, int channels, int t_len, cudaStream_t stream);
+
+// folded fp32 weight (C_out, C_in, K) -> hi/lo slabs
+int launch_pack_tc_weight(
+    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, cudaStream_t stream);
+
+}  // namespace pmn

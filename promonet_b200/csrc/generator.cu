@@ -2,11 +2,13 @@
 //
 // Replaces promonet.model.Generator (promonet/model/generator.py:84-197) with
 // MODEL='hifigan' (promonet/model/hifigan.py:13-70) for inference.
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <new>
 #include <vector>
 
+#include "conv1d_tc.cuh"
 #include "features.cuh"
 #include "generator.cuh"
 
@@ -39,6 +41,7 @@ struct Tensor {
 
 struct PackedConv {
     float* weight = nullptr;  // conv1d: (C_in, K, C_out); conv transpose: (C_in, C_out, K)
+    __nv_bfloat16* slabs = nullptr;  // tensor-core path: hi/lo weight slabs (conv1d_tc.cuh)
     const float* bias = nullptr;
     int c_in = 0, c_out = 0, k = 0;
 };
@@ -118,16 +121,23 @@ int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int 
     conv->c_in = conv->c_out = channels;
     conv->k = k;
     conv->bias = bias->data;
+    if (g->math == PMN_MATH_BF16X3_TC) {
+        float* slabs;  // two bf16 planes = the bytes of one fp32 tensor
+        PMN_TRY(alloc(g, shape->numel(), &slabs));
+        conv->slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
+        return launch_pack_tc_weight(w, conv->slabs, channels, channels, k, stream);
+    }
     PMN_TRY(alloc(g, shape->numel(), &conv->weight));
     return launch_pack_conv1d_weight(w, conv->weight, channels, channels, k, stream);
 }
 
 struct Workspace {
     float *features, *speaker_bias, *x_in, *x0, *xt, *cur, *mrf;
+    __nv_bfloat16 *a0, *at, *ac;  // tensor-core path: hi/lo planes of lrelu(x0 / xt / cur)
     size_t bytes;
 };
 
-Workspace carve(void* base, int batch, int frames) {
+Workspace carve(void* base, int batch, int frames, int math) {
     Workspace w;
     char* p = static_cast<char*>(base);
     auto take = [&](size_t count) {
@@ -140,9 +150,26 @@ Workspace carve(void* base, int batch, int frames) {
     w.speaker_bias = take((size_t)batch * kInitial);
     w.x_in = take((size_t)batch * kInitial * frames);
     w.x0 = take(stage);
-    w.xt = take(stage);
     w.cur = take(stage);
     w.mrf = take(stage);
+    w.xt = nullptr;
+    w.a0 = w.at = w.ac = nullptr;
+    if (math == PMN_MATH_BF16X3_TC) {
+        // planes are (B, 2, C, t_pad) bf16; the widest is the last stage (C = 32)
+        size_t planes = 0;
+        int channels = kInitial, t_len = frames;
+        for (int s = 0; s < kStages; ++s) {
+            channels /= 2;
+            t_len *= kUpRate[s];
+            planes = std::max(planes, tc_planes_elements(batch, channels, t_len));
+        }
+        auto take_planes = [&]() { return reinterpret_cast<__nv_bfloat16*>(take((planes + 1) / 2)); };
+        w.a0 = take_planes();
+        w.at = take_planes();
+        w.ac = take_planes();
+    } else {
+        w.xt = take(stage);
+    }
     w.bytes = (size_t)(p - static_cast<char*>(base));
     return w;
 }
@@ -180,7 +207,7 @@ int generator_set_tensor(
 
 int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
     if (g->finalized) return fail(PMN_ERR_STATE, "generator already finalized");
-    if (math != PMN_MATH_FP32_SIMT)
+    if (math != PMN_MATH_FP32_SIMT && math != PMN_MATH_BF16X3_TC)
         return fail(PMN_ERR_ARGUMENT, "generator: unsupported math mode");
     g->math = math;
 
@@ -243,8 +270,8 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
     return PMN_OK;
 }
 
-size_t generator_workspace_bytes(int batch, int frames) {
-    return carve(nullptr, batch, frames).bytes;
+size_t generator_workspace_bytes(const pmn_generator* g, int batch, int frames) {
+    return carve(nullptr, batch, frames, g->math).bytes;
 }
 
 int generator_features(
@@ -266,7 +293,7 @@ int generator_forward(
     if (!g->finalized) return fail(PMN_ERR_STATE, "generator not finalized");
     PMN_REQUIRE(batch > 0 && frames > 0, "generator: empty batch");
     PMN_REQUIRE(audio && workspace, "generator: null pointer");
-    Workspace w = carve(workspace, batch, frames);
+    Workspace w = carve(workspace, batch, frames, g->math);
     if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "generator: workspace too small");
 
     // G1: features (B, 113, F)
@@ -299,6 +326,41 @@ int generator_forward(
             up.k, kUpRate[s], kSlope, stream));
         t_len *= kUpRate[s];
         const int channels = up.c_out;
+        if (g->math == PMN_MATH_BF16X3_TC) {
+            // G5/G6 on tcgen05: activations travel between convs as bf16 hi/lo
+            // planes of lrelu(.), the residual stream stays fp32
+            PMN_TRY(launch_planes_from_f32(w.x0, w.a0, batch, channels, t_len, kSlope, stream));
+            PMN_TRY(launch_zero_plane_pads(w.at, batch, channels, t_len, stream));
+            PMN_TRY(launch_zero_plane_pads(w.ac, batch, channels, t_len, stream));
+            for (int j = 0; j < 3; ++j) {
+                for (int d = 0; d < 3; ++d) {
+                    TcConvArgs a;
+                    a.batch = batch; a.c_in = a.c_out = channels; a.t_len = t_len;
+                    a.k = kResKernel[j]; a.out_slope = kSlope;
+                    a.x_planes = d == 0 ? w.a0 : w.ac;
+                    a.w_slabs = g->conv1[s][j][d].slabs; a.bias = g->conv1[s][j][d].bias;
+                    a.dilation = kResDilation[d];
+                    a.out_planes = w.at;
+                    PMN_TRY(launch_conv1d_tc(a, stream));
+                    a.x_planes = w.at;
+                    a.w_slabs = g->conv2[s][j][d].slabs; a.bias = g->conv2[s][j][d].bias;
+                    a.dilation = 1;
+                    a.residual = d == 0 ? w.x0 : w.cur;
+                    if (d < 2) {
+                        a.out = w.cur;
+                        a.out_planes = w.ac;
+                    } else {
+                        a.out_planes = nullptr;
+                        a.accum = w.mrf;
+                        a.accum_mode = j == 0 ? 1 : 2;
+                        a.accum_scale = 1.f / 3.f;
+                    }
+                    PMN_TRY(launch_conv1d_tc(a, stream));
+                }
+            }
+            stage_in = w.mrf;
+            continue;
+        }
         // G5/G6: three Blocks, mean folded into the last conv of each
         for (int j = 0; j < 3; ++j) {
             const float* block_in = w.x0;

@@ -1,0 +1,100 @@
+"""tcgen05 (bf16 x 3) dilated Conv1d against an fp64 torch convolution.
+Tolerance 1e-4 relative to max|reference| (north_star); measured ~1e-5."""
+import pytest
+import torch
+
+from conftest import relative_error
+
+pytestmark = pytest.mark.gpu
+
+
+def conv1d_tc(x, w, bias=None, residual=None, dilation=1, in_slope=1., out_slope=1.,
+              want_planes=False, accum=None, accum_mode=0, accum_scale=1., want_out=True):
+    from promonet_b200 import _lib
+    lib = _lib.library()
+    batch, channels, t_len = x.shape
+    k = w.shape[-1]
+    xd, wd = x.cuda().contiguous(), w.cuda().contiguous()
+    keep = [t.cuda().contiguous() if t is not None else None for t in (bias, residual)]
+    out = torch.empty_like(xd) if want_out else None
+    planes = torch.empty_like(xd) if want_planes else None
+    size = lib.pmn_conv1d_tc_workspace_bytes(batch, channels, t_len, k)
+    workspace = torch.empty(size, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.pmn_conv1d_tc(
+        xd.data_ptr(), wd.data_ptr(), *[_lib.ptr(t) for t in keep], _lib.ptr(out),
+        _lib.ptr(planes), _lib.ptr(accum), accum_mode, accum_scale,
+        batch, channels, t_len, k, dilation, in_slope, out_slope,
+        workspace.data_ptr(), size, _lib.stream()))
+    torch.cuda.synchronize()
+    return out, planes
+
+
+def reference(x, w, bias, dilation, in_slope):
+    k = w.shape[-1]
+    return torch.nn.functional.conv1d(
+        torch.nn.functional.leaky_relu(x.double(), in_slope), w.double(),
+        None if bias is None else bias.double(),
+        padding=dilation * (k - 1) // 2, dilation=dilation)
+
+
+@pytest.mark.parametrize('channels,k,dilation,t_len,batch', [
+    (32, 3, 1, 512, 1), (32, 11, 5, 1500, 2), (64, 7, 3, 700, 3), (64, 3, 1, 256, 1),
+    (128, 11, 1, 300, 2), (128, 11, 5, 1111, 1), (128, 7, 1, 256, 1),
+    (256, 3, 5, 129, 2), (256, 11, 3, 1000, 1), (256, 7, 1, 128, 1)])
+def test_conv1d_tc_matches_fp64(channels, k, dilation, t_len, batch):
+    torch.manual_seed(channels + k + dilation)
+    x = torch.randn(batch, channels, t_len)
+    w = torch.randn(channels, channels, k) / (channels * k) ** .5
+    bias = torch.randn(channels)
+    expected = reference(x, w, bias, dilation, 0.1)
+    out, _ = conv1d_tc(x, w, bias, dilation=dilation, in_slope=0.1)
+    error = relative_error(out, expected)
+    assert error < 1e-4, error
+
+
+def test_conv1d_tc_many_tiles_per_cta():
+    """More tiles than SMs: exercises ring phase wrap-around and TMEM double buffering"""
+    torch.manual_seed(1)
+    x = torch.randn(8, 128, 256 * 40)
+    w = torch.randn(128, 128, 3) / (128 * 3) ** .5
+    expected = reference(x, w, None, 1, 1.)
+    out, _ = conv1d_tc(x, w, dilation=1)
+    assert relative_error(out, expected) < 1e-4
+
+
+def test_conv1d_tc_epilogue():
+    torch.manual_seed(2)
+    x = torch.randn(2, 64, 600)
+    w = torch.randn(64, 64, 7) / (64 * 7) ** .5
+    bias, residual = torch.randn(64), torch.randn(2, 64, 600)
+    y = reference(x, w, bias, 3, 0.1) + residual.double()
+    accum = torch.ones(2, 64, 600, device='cuda')
+    out, planes = conv1d_tc(
+        x, w, bias, residual, dilation=3, in_slope=0.1, out_slope=0.1, want_planes=True,
+        accum=accum, accum_mode=2, accum_scale=1 / 3)
+    assert relative_error(out, y) < 1e-4
+    assert relative_error(planes, torch.nn.functional.leaky_relu(y, 0.1)) < 1e-4
+    assert relative_error(accum, 1. + y / 3) < 1e-4
+    accum = torch.empty(2, 64, 600, device='cuda')
+    out, _ = conv1d_tc(x, w, bias, dilation=3, in_slope=0.1, accum=accum, accum_mode=1,
+                       accum_scale=0.5, want_out=False)
+    assert out is None
+    assert relative_error(accum, 0.5 * reference(x, w, bias, 3, 0.1)) < 1e-4
+
+
+@pytest.mark.parametrize('tag,kernel', [('c32k3', 3), ('c64k11', 11)])
+def test_block_tc_matches_reference_golden(golden, tag, kernel):
+    """Block.forward hifigan.py:198-210 chained through the hi/lo planes"""
+    from oracle import hifigan
+    g = golden('block')
+    cur = g[f'{tag}_x']
+    for i, dilation in enumerate((1, 3, 5)):
+        def folded(name):
+            return hifigan.fold_weight_norm(
+                g[f'{tag}_{name}.{i}.weight_g'], g[f'{tag}_{name}.{i}.weight_v'])
+        xt, _ = conv1d_tc(cur, folded('convs1'), g[f'{tag}_convs1.{i}.bias'],
+                          dilation=dilation, in_slope=0.1)
+        cur, _ = conv1d_tc(xt, folded('convs2'), g[f'{tag}_convs2.{i}.bias'],
+                           residual=cur, in_slope=0.1)
+        cur = cur.cpu()
+    assert relative_error(cur, g[f'{tag}_y']) < 1e-4

@@ -27,10 +27,12 @@ def state():
     return init.hifigan_state(1234)
 
 
-@pytest.fixture(scope='module')
-def model(state):
+@pytest.fixture(scope='module', params=['fp32', 'bf16x3'])
+def model(state, request, lib):
+    """Both math modes must meet the same parity bar"""
     import promonet_b200
-    return promonet_b200.model.Generator(state=state)
+    math = lib.MATH_FP32_SIMT if request.param == 'fp32' else lib.MATH_BF16X3_TC
+    return promonet_b200.model.Generator(state=state, math=math)
 
 
 def conv1d(lib, x, weight, bias=None, bias2=None, residual=None, dilation=1,
