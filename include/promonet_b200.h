@@ -149,6 +149,10 @@ int pmn_conv1d(
  * parity, not speed.  planes_out, if not NULL, receives hi + lo of the bf16
  * planes of lrelu(y, out_slope) that the next convolution would consume. */
 size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k);
+/* Profiling aid: while `counters` (device, 148 x 10 x 4 int64) is non-NULL every
+ * tensor-core conv launch stores per-warp-role cycle counters there
+ * ([0] total, [1..3] cycles spent waiting on the pipeline barriers). */
+void pmn_debug_tc_counters(void* counters);
 int pmn_conv1d_tc(
     const float* x, const float* weight, const float* bias, const float* residual,
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,

@@ -52,6 +52,7 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
          c_float, c_int, c_void_p]),
+    'pmn_debug_tc_counters': (None, [c_void_p]),
     'pmn_conv1d_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'pmn_conv1d_tc': (
         c_int,

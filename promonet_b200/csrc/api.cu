@@ -229,6 +229,8 @@ TcOpWorkspace carve_tc_op(void* base, int batch, int channels, int t_len, int k)
 }
 }  // namespace
 
+void pmn_debug_tc_counters(void* counters) { tc_set_debug_counters(static_cast<long long*>(counters)); }
+
 size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k) {
     if (batch <= 0 || channels <= 0 || t_len <= 0 || k <= 0) return 0;
     return carve_tc_op(nullptr, batch, channels, t_len, k).bytes;

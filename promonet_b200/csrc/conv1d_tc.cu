@@ -31,7 +31,7 @@ namespace pmn {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // producer, MMA issuer, 8 epilogue warps
 constexpr int kMaxHalo = 25;  // (11 - 1) / 2 * 5
 
 // ---------------------------------------------------------------------------
@@ -108,6 +108,17 @@ __device__ __forceinline__ void tc_load32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_load16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+        "%12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
 // [0,14) start >> 4 | [16,30) leading byte offset >> 4 (stride between the two
 // 8-element K chunks) | [32,46) stride byte offset >> 4 (stride between 8-row
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::kXStages; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
         for (int i = 0; i < NW; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-        for (int i = 0; i < AS; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < AS; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -192,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
         // ===== producer =====
         if (lane == 0) {
             uint32_t xcount = 0, wcount = 0;
+            long long wait_x = 0, wait_w = 0, begin = a.debug ? clock64() : 0, mark = 0;
             const uint32_t x_bytes = 2 * Cfg::kGroups * rows * 16;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int b = tile / tiles_per_item;
@@ -199,7 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
+                    if (a.debug) mark = clock64();
                     mbar_wait(x_empty + xs, xphase ^ 1);
+                    if (a.debug) wait_x += clock64() - mark;
                     mbar_expect_tx(x_full + xs, x_bytes);
                     uint8_t* dst = x_slabs + xs * Cfg::kXSlab;
 #pragma unroll 1
@@ -216,7 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                     for (int tap = 0; tap < a.k; ++tap) {
                         const uint32_t ws = wcount % NW, wphase = (wcount / NW) & 1;
                         ++wcount;
+                        if (a.debug) mark = clock64();
                         mbar_wait(w_empty + ws, wphase ^ 1);
+                        if (a.debug) wait_w += clock64() - mark;
                         mbar_expect_tx(w_full + ws, Cfg::kWSlab);
                         bulk_copy(w_slabs + ws * Cfg::kWSlab,
                                   reinterpret_cast<const uint8_t*>(a.w_slabs) +
@@ -225,29 +241,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                     }
                 }
             }
+            if (a.debug) {
+                long long* d = a.debug + ((size_t)blockIdx.x * 10 + 0) * 4;
+                d[0] = clock64() - begin; d[1] = wait_x; d[2] = wait_w;
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc(128, C_OUT);
             uint32_t xcount = 0, wcount = 0, tcount = 0;
+            long long wait_x = 0, wait_w = 0, wait_acc = 0, begin = a.debug ? clock64() : 0, mark = 0;
             const uint32_t x_plane = Cfg::kGroups * rows * 16;      // bytes between hi and lo
             constexpr uint32_t w_plane = Cfg::kGroups * C_OUT * 16;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
                 ++tcount;
+                if (a.debug) mark = clock64();
                 mbar_wait(acc_empty + as, aphase ^ 1);
+                if (a.debug) wait_acc += clock64() - mark;
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + as * (S * C_OUT);
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
+                    if (a.debug) mark = clock64();
                     mbar_wait(x_full + xs, xphase);
+                    if (a.debug) wait_x += clock64() - mark;
                     const uint32_t x_addr = smem_u32(x_slabs + xs * Cfg::kXSlab);
                     for (int tap = 0; tap < a.k; ++tap) {
                         const uint32_t ws = wcount % NW, wphase = (wcount / NW) & 1;
                         ++wcount;
+                        if (a.debug) mark = clock64();
                         mbar_wait(w_full + ws, wphase);
+                        if (a.debug) wait_w += clock64() - mark;
                         tc_fence_after();
                         const uint32_t w_addr = smem_u32(w_slabs + ws * Cfg::kWSlab);
                         const bool first = kb == 0 && tap == 0;
@@ -274,44 +301,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                 }
                 tc_commit(acc_full + as);
             }
+            if (a.debug) {
+                long long* d = a.debug + ((size_t)blockIdx.x * 10 + 1) * 4;
+                d[0] = clock64() - begin; d[1] = wait_x; d[2] = wait_w; d[3] = wait_acc;
+            }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
+        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and
+        // every other 32-column chunk of the tile =====
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int kW = 16;                    // columns per chunk
+        constexpr int kPerSub = C_OUT / kW;
+        constexpr int kChunks = S * kPerSub;      // (subtile, 16-channel) chunks per tile
+        static_assert(kChunks % 2 == 0, "chunks are split between two warp sets");
         uint32_t tcount = 0;
         const int groups_out = C_OUT / 8;
+        long long wait_cycles = 0, start_cycles = a.debug ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int b = tile / tiles_per_item;
             const int t0 = (tile % tiles_per_item) * Cfg::kTile;
             const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
             ++tcount;
+            // Side inputs do not depend on the accumulators: fetch the first chunk's
+            // before waiting, and chunk i + 1's while chunk i is processed, so the
+            // DRAM latency is paid once per chunk batch instead of once per element
+            float res[kW];
+            auto fetch = [&](const float* source, int chunk, float (&r)[kW]) {
+                const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
+                const int t = t0 + s * 128 + quad * 32 + lane;
+                const bool valid = source != nullptr && t < a.t_len;
+                const size_t idx = ((size_t)b * C_OUT + c0) * a.t_len + t;
+#pragma unroll
+                for (int i = 0; i < kW; ++i)
+                    r[i] = valid ? source[idx + (size_t)i * a.t_len] : 0.f;
+            };
+            fetch(a.residual, half, res);
+            const long long wait_start = a.debug ? clock64() : 0;
             mbar_wait(acc_full + as, aphase);
+            if (a.debug) wait_cycles += clock64() - wait_start;
             tc_fence_after();
 #pragma unroll 1
-            for (int s = 0; s < S; ++s) {
+            for (int chunk = half; chunk < kChunks; chunk += 2) {
+                const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = t0 + s * 128 + quad * 32 + lane;
                 const bool valid = t < a.t_len;
-#pragma unroll 1
-                for (int c0 = 0; c0 < C_OUT; c0 += 32) {
-                    uint32_t raw[32];
-                    tc_load32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
-                    if (!valid) continue;
-                    float v[32];
+                float res_next[kW], acc[kW];
+                if (chunk + 2 < kChunks) fetch(a.residual, chunk + 2, res_next);
+                fetch(a.accum_mode == 2 ? a.accum : nullptr, chunk, acc);
+                uint32_t raw[kW];
+                tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
+                if (valid) {
+                    float v[kW];
+                    const size_t idx = ((size_t)b * C_OUT + c0) * a.t_len + t;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = c0 + i;
-                        float y = __uint_as_float(raw[i]);
-                        if (a.bias) y += __ldg(a.bias + c);
-                        const size_t idx = ((size_t)b * C_OUT + c) * a.t_len + t;
-                        if (a.residual) y += a.residual[idx];
-                        if (a.out) a.out[idx] = y;
-                        if (a.accum_mode == 1) a.accum[idx] = y * a.accum_scale;
-                        else if (a.accum_mode == 2) a.accum[idx] += y * a.accum_scale;
+                    for (int i = 0; i < kW; ++i) {
+                        float y = __uint_as_float(raw[i]) + res[i];
+                        if (a.bias) y += __ldg(a.bias + c0 + i);
                         v[i] = y;
+                    }
+                    if (a.out) {
+#pragma unroll
+                        for (int i = 0; i < kW; ++i) a.out[idx + (size_t)i * a.t_len] = v[i];
+                    }
+                    if (a.accum_mode) {
+#pragma unroll
+                        for (int i = 0; i < kW; ++i)
+                            a.accum[idx + (size_t)i * a.t_len] = fmaf(v[i], a.accum_scale, acc[i]);
                     }
                     if (a.out_planes) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < kW / 8; ++g) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -331,10 +391,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                         }
                     }
                 }
+                if (chunk + 2 < kChunks) {
+#pragma unroll
+                    for (int i = 0; i < kW; ++i) res[i] = res_next[i];
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + as);
+        }
+        if (a.debug && lane == 0) {
+            long long* d = a.debug + ((size_t)blockIdx.x * 10 + warp) * 4;
+            d[0] = clock64() - start_cycles;
+            d[1] = wait_cycles;
         }
     }
 
@@ -427,6 +496,8 @@ __global__ void pack_tc_weight_kernel(
     }
 }
 
+long long* g_tc_debug = nullptr;
+
 int sm_count() {
     static int count = 0;
     if (!count) {
@@ -451,12 +522,16 @@ int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
     const int tiles_per_item = ceil_div(a.t_len, Cfg::kTile);
     const int num_tiles = tiles_per_item * a.batch;
     const int grid = min(num_tiles, sm_count());
+    TcConvArgs args = a;
+    if (!args.debug) args.debug = g_tc_debug;
     LaunchScope scope("conv1d_tc_kernel", stream);
-    kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(a, tc_padded_length(a.t_len), tiles_per_item, num_tiles);
+    kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(args, tc_padded_length(a.t_len), tiles_per_item, num_tiles);
     return launched("conv1d_tc_kernel");
 }
 
 }  // namespace
+
+void tc_set_debug_counters(long long* counters) { g_tc_debug = counters; }
 
 bool tc_supported(int c_in, int c_out, int k, int dilation) {
     if (c_in != c_out) return false;

@@ -40,9 +40,13 @@ struct TcConvArgs {
     int batch = 0, c_in = 0, c_out = 0, t_len = 0;
     int k = 1, dilation = 1;                  // "same" padding (k - 1) / 2 * dilation
     float out_slope = 1.f;
+    // Optional (gridDim.x, 10 warps, 4) cycle counters: [0] total, [1..3] barrier waits
+    long long* debug = nullptr;
 };
 
 int launch_conv1d_tc(const TcConvArgs& args, cudaStream_t stream);
+// Every following launch writes its cycle counters to `counters` (device, SMs x 40 int64); null = off
+void tc_set_debug_counters(long long* counters);
 
 // fp32 (B, C, T) -> planes of lrelu(x, slope); also writes the zero pad rows
 int launch_planes_from_f32(
