@@ -277,6 +277,7 @@ def run_b200(args):
     kernel_ms, kernel_launches = _lib.profile_read(dominant)
     shares = {}
     for name in ('conv1d_kernel', 'conv1d_tc_kernel', 'conv_transpose1d_kernel',
+                 'conv_transpose1d_tc_kernel',
                  'planes_from_f32_kernel', 'zero_plane_pads_kernel',
                  'head_kernel', 'features_kernel', 'speaker_bias_kernel'):
         total, count = _lib.profile_read(name)

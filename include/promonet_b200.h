@@ -167,6 +167,16 @@ int pmn_conv_transpose1d(
     int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope,
     void* stream);
 
+/* The same transposed convolution on the tensor cores (3-tap phase-major
+ * formulation, bf16 x 3; (c_in, stride) in {(512, 8), (256, 8), (128, 2), (64, 2)},
+ * c_out = c_in / 2).  fp32 in and out; planes and weight slabs are built inside
+ * `workspace` (pmn_conv_transpose1d_tc_workspace_bytes): parity entry point. */
+size_t pmn_conv_transpose1d_tc_workspace_bytes(int batch, int c_in, int t_in, int stride);
+int pmn_conv_transpose1d_tc(
+    const float* x, const float* weight, const float* bias, float* out,
+    int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,11 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
          c_int, c_int, c_float, c_void_p]),
+    'pmn_conv_transpose1d_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'pmn_conv_transpose1d_tc': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+         c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
 }
 
 _library = None

@@ -270,4 +270,31 @@ int pmn_conv_transpose1d(
                                    in_slope, (cudaStream_t)stream);
 }
 
+size_t pmn_conv_transpose1d_tc_workspace_bytes(int batch, int c_in, int t_in, int stride) {
+    if (batch <= 0 || c_in <= 0 || t_in <= 0 || stride <= 0) return 0;
+    return align_up(tc_planes_elements(batch, c_in, t_in) * 2, 256) +
+           align_up(tc_transpose_weight_elements(c_in, c_in / 2, stride) * 2, 256);
+}
+
+int pmn_conv_transpose1d_tc(
+    const float* x, const float* weight, const float* bias, float* out,
+    int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope,
+    void* workspace, size_t workspace_bytes, void* stream_) {
+    PMN_REQUIRE(x && weight && out && workspace, "conv_transpose1d_tc: null pointer");
+    PMN_REQUIRE(batch > 0 && t_in > 0, "conv_transpose1d_tc: empty input");
+    PMN_REQUIRE(tc_transpose_supported(c_in, c_out, k, stride), "conv_transpose1d_tc: unsupported shape");
+    if (pmn_conv_transpose1d_tc_workspace_bytes(batch, c_in, t_in, stride) > workspace_bytes)
+        return fail(PMN_ERR_WORKSPACE, "conv_transpose1d_tc: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    auto* planes = static_cast<__nv_bfloat16*>(workspace);
+    auto* slabs = reinterpret_cast<__nv_bfloat16*>(
+        static_cast<char*>(workspace) + align_up(tc_planes_elements(batch, c_in, t_in) * 2, 256));
+    PMN_TRY(launch_planes_from_f32(x, planes, batch, c_in, t_in, in_slope, stream));
+    PMN_TRY(launch_pack_tc_transpose_weight(weight, slabs, c_in, c_out, stride, stream));
+    TcConvArgs a;
+    a.x_planes = planes; a.w_slabs = slabs; a.bias = bias; a.out = out;
+    a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_len = t_in;
+    return launch_conv_transpose1d_tc(a, stride, stream);
+}
+
 }  // extern "C"

@@ -162,8 +162,13 @@ struct TcConfig {
     static_assert(C_IN % KB == 0 && KB % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "shape");
 };
 
-template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
-__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, int t_pad, int tiles_per_item, int num_tiles) {
+// UP == 0: Conv1d with C_OUT output channels (one N tile).  UP == stride > 0:
+// ConvTranspose1d(kernel 2 UP, padding UP / 2) written as a 3-tap convolution over
+// input positions with UP * c_out phase-major output columns, C_OUT of them per
+// N tile (see pack_tc_transpose_weight_kernel).
+template <int C_IN, int C_OUT, int S, int KB, int NW, int AS, int UP>
+__global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
+    TcConvArgs a, int t_pad, int tiles_per_item, int n_tiles, int num_tiles) {
     using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -206,8 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
             long long wait_x = 0, wait_w = 0, begin = a.debug ? clock64() : 0, mark = 0;
             const uint32_t x_bytes = 2 * Cfg::kGroups * rows * 16;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int b = tile / tiles_per_item;
-                const int t0 = (tile % tiles_per_item) * Cfg::kTile;
+                const int nt = tile % n_tiles, rest = tile / n_tiles;
+                const int b = rest / tiles_per_item;
+                const int t0 = (rest % tiles_per_item) * Cfg::kTile;
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
                         mbar_expect_tx(w_full + ws, Cfg::kWSlab);
                         bulk_copy(w_slabs + ws * Cfg::kWSlab,
                                   reinterpret_cast<const uint8_t*>(a.w_slabs) +
-                                      (size_t)(tap * Cfg::kBlocks + kb) * Cfg::kWSlab,
+                                      (size_t)((nt * a.k + tap) * Cfg::kBlocks + kb) * Cfg::kWSlab,
                                   Cfg::kWSlab, w_full + ws);
                     }
                 }
@@ -319,10 +325,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(TcConvArgs a, in
         const int groups_out = C_OUT / 8;
         long long wait_cycles = 0, start_cycles = a.debug ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int b = tile / tiles_per_item;
-            const int t0 = (tile % tiles_per_item) * Cfg::kTile;
+            const int nt = tile % n_tiles, rest = tile / n_tiles;
+            const int b = rest / tiles_per_item;
+            const int t0 = (rest % tiles_per_item) * Cfg::kTile;
             const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
             ++tcount;
+            if constexpr (UP > 0) {
+                // ConvTranspose1d epilogue: column n = o * UP + q is output sample
+                // UP * i + q of channel o; a thread writes UP contiguous floats per o
+                mbar_wait(acc_full + as, aphase);
+                tc_fence_after();
+                const int t_out = UP * a.t_len;
+#pragma unroll 1
+                for (int chunk = half; chunk < kChunks; chunk += 2) {
+                    const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
+                    const int i = t0 + s * 128 + quad * 32 + lane;
+                    uint32_t raw[kW];
+                    tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
+                    if (i < a.t_len) {
+                        const int o0 = (nt * C_OUT + c0) / UP;
+#pragma unroll
+                        for (int j = 0; j < kW / UP; ++j) {
+                            const float bias = a.bias ? __ldg(a.bias + o0 + j) : 0.f;
+                            float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_out + (size_t)UP * i;
+                            if constexpr (UP % 4 == 0) {
+#pragma unroll
+                                for (int q = 0; q < UP; q += 4)
+                                    *reinterpret_cast<float4*>(dst + q) = make_float4(
+                                        __uint_as_float(raw[j * UP + q]) + bias,
+                                        __uint_as_float(raw[j * UP + q + 1]) + bias,
+                                        __uint_as_float(raw[j * UP + q + 2]) + bias,
+                                        __uint_as_float(raw[j * UP + q + 3]) + bias);
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < UP; q += 2)
+                                    *reinterpret_cast<float2*>(dst + q) = make_float2(
+                                        __uint_as_float(raw[j * UP + q]) + bias,
+                                        __uint_as_float(raw[j * UP + q + 1]) + bias);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + as);
+                continue;
+            }
             // Side inputs do not depend on the accumulators: fetch the first chunk's
             // before waiting, and chunk i + 1's while chunk i is processed, so the
             // DRAM latency is paid once per chunk batch instead of once per element
@@ -496,6 +544,43 @@ __global__ void pack_tc_weight_kernel(
     }
 }
 
+// ConvTranspose1d weight (C_in, C_out, 2 UP), already folded ->
+// [n tile][tap 0..2][c_in / KB][plane][KB / 8][N_TILE][8] bf16 with column
+// n = o * UP + q and taps x[i-1], x[i], x[i+1] (conv_transpose1d.cu has the algebra):
+//   tap 1: w[c, o, q + UP/2];  tap 0: q < UP/2 ? w[c, o, q + 3 UP/2] : 0;
+//   tap 2: q >= UP/2 ? w[c, o, q - UP/2] : 0
+__global__ void pack_tc_transpose_weight_kernel(
+    const float* __restrict__ w, __nv_bfloat16* __restrict__ slabs,
+    int c_in, int c_out, int up, int kb_size, int n_tile) {
+    const int n_total = up * c_out;
+    const size_t total = (size_t)3 * c_in * n_total;
+    const int groups = kb_size / 8, blocks = c_in / kb_size, half = up / 2, k = 2 * up;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t rest = idx;
+        const int e = rest % 8; rest /= 8;
+        const int col = rest % n_tile; rest /= n_tile;
+        const int g = rest % groups; rest /= groups;
+        const int kb = rest % blocks; rest /= blocks;
+        const int tap = rest % 3; rest /= 3;
+        const int nt = (int)rest;
+        const int c = kb * kb_size + g * 8 + e;
+        const int n = nt * n_tile + col, o = n / up, q = n % up;
+        int j = -1;
+        if (tap == 1) j = q + half;
+        else if (tap == 0 && q < half) j = q + half + up;
+        else if (tap == 2 && q >= half) j = q - half;
+        const float value = j >= 0 ? w[((size_t)c * c_out + o) * k + j] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(value);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(value - __bfloat162float(hi));
+        const size_t slab = (size_t)((nt * 3 + tap) * blocks + kb) * 2;
+        const size_t plane = (size_t)groups * n_tile * 8;
+        const size_t inner = ((size_t)g * n_tile + col) * 8 + e;
+        slabs[slab * plane + inner] = hi;
+        slabs[(slab + 1) * plane + inner] = lo;
+    }
+}
+
 long long* g_tc_debug = nullptr;
 
 int sm_count() {
@@ -508,10 +593,10 @@ int sm_count() {
     return count;
 }
 
-template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
+template <int C_IN, int C_OUT, int S, int KB, int NW, int AS, int UP = 0>
 int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
     using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
-    auto kernel = conv1d_tc_kernel<C_IN, C_OUT, S, KB, NW, AS>;
+    auto kernel = conv1d_tc_kernel<C_IN, C_OUT, S, KB, NW, AS, UP>;
     static bool configured = false;
     if (!configured) {
         PMN_TRY(check_cuda(
@@ -520,13 +605,16 @@ int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
         configured = true;
     }
     const int tiles_per_item = ceil_div(a.t_len, Cfg::kTile);
-    const int num_tiles = tiles_per_item * a.batch;
+    const int n_tiles = UP > 0 ? UP * a.c_out / C_OUT : 1;
+    const int num_tiles = tiles_per_item * a.batch * n_tiles;
     const int grid = min(num_tiles, sm_count());
     TcConvArgs args = a;
     if (!args.debug) args.debug = g_tc_debug;
-    LaunchScope scope("conv1d_tc_kernel", stream);
-    kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(args, tc_padded_length(a.t_len), tiles_per_item, num_tiles);
-    return launched("conv1d_tc_kernel");
+    const char* name = UP > 0 ? "conv_transpose1d_tc_kernel" : "conv1d_tc_kernel";
+    LaunchScope scope(name, stream);
+    kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(
+        args, tc_padded_length(a.t_len), tiles_per_item, n_tiles, num_tiles);
+    return launched(name);
 }
 
 }  // namespace
@@ -550,6 +638,49 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
         case 64: return launch_variant<64, 64, 2, 64, 4, 2>(a, stream);
         default: return launch_variant<32, 32, 4, 32, 4, 2>(a, stream);
     }
+}
+
+namespace {
+int transpose_n_tile(int c_in) { return c_in >= 256 ? 256 : c_in; }  // = min(256, UP * c_out)
+int transpose_k_block(int c_in) { return c_in >= 256 ? 32 : 64; }
+}  // namespace
+
+bool tc_transpose_supported(int c_in, int c_out, int k, int stride) {
+    if (k != 2 * stride || 2 * c_out != c_in) return false;
+    return (stride == 8 && (c_in == 512 || c_in == 256)) || (stride == 2 && (c_in == 128 || c_in == 64));
+}
+
+size_t tc_transpose_weight_elements(int c_in, int c_out, int stride) {
+    return (size_t)2 * 3 * c_in * stride * c_out;
+}
+
+int launch_conv_transpose1d_tc(const TcConvArgs& args, int stride, cudaStream_t stream) {
+    PMN_REQUIRE(args.x_planes && args.w_slabs && args.out, "conv_transpose1d_tc: null pointer");
+    PMN_REQUIRE(args.batch > 0 && args.t_len > 0, "conv_transpose1d_tc: empty input");
+    PMN_REQUIRE(tc_transpose_supported(args.c_in, args.c_out, 2 * stride, stride),
+                "conv_transpose1d_tc: unsupported shape");
+    TcConvArgs a = args;
+    a.k = 3;
+    a.dilation = 1;
+    a.residual = nullptr; a.accum = nullptr; a.accum_mode = 0; a.out_planes = nullptr;
+    switch (a.c_in) {
+        case 512: return launch_variant<512, 256, 1, 32, 4, 2, 8>(a, stream);
+        case 256: return launch_variant<256, 256, 1, 32, 4, 2, 8>(a, stream);
+        case 128: return launch_variant<128, 128, 2, 64, 2, 2, 2>(a, stream);
+        default: return launch_variant<64, 64, 2, 64, 4, 2, 2>(a, stream);
+    }
+}
+
+int launch_pack_tc_transpose_weight(
+    const float* w, __nv_bfloat16* slabs, int c_in, int c_out, int stride, cudaStream_t stream) {
+    PMN_REQUIRE(w && slabs && tc_transpose_supported(c_in, c_out, 2 * stride, stride),
+                "pack_tc_transpose_weight: bad argument");
+    const size_t total = (size_t)3 * c_in * stride * c_out;
+    const int blocks = (int)min((size_t)4096, (total + 255) / 256);
+    LaunchScope scope("pack_tc_transpose_weight_kernel", stream);
+    pack_tc_transpose_weight_kernel<<<blocks, 256, 0, stream>>>(
+        w, slabs, c_in, c_out, stride, transpose_k_block(c_in), transpose_n_tile(c_in));
+    return launched("pack_tc_transpose_weight_kernel");
 }
 
 int launch_planes_from_f32(

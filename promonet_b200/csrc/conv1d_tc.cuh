@@ -48,6 +48,15 @@ int launch_conv1d_tc(const TcConvArgs& args, cudaStream_t stream);
 // Every following launch writes its cycle counters to `counters` (device, SMs x 40 int64); null = off
 void tc_set_debug_counters(long long* counters);
 
+// LeakyReLU'd planes (B, 2, C_in, .) -> ConvTranspose1d(kernel 2 stride, padding
+// stride / 2) fp32 (B, C_out, stride * T) on the tensor cores.  Uses x_planes,
+// w_slabs (launch_pack_tc_transpose_weight), bias, out, batch, c_in, c_out, t_len.
+bool tc_transpose_supported(int c_in, int c_out, int k, int stride);
+size_t tc_transpose_weight_elements(int c_in, int c_out, int stride);
+int launch_conv_transpose1d_tc(const TcConvArgs& args, int stride, cudaStream_t stream);
+int launch_pack_tc_transpose_weight(
+    const float* w, __nv_bfloat16* slabs, int c_in, int c_out, int stride, cudaStream_t stream);
+
 // fp32 (B, C, T) -> planes of lrelu(x, slope); also writes the zero pad rows
 int launch_planes_from_f32(
     const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,

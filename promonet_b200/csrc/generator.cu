@@ -250,6 +250,14 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
         const Tensor* bias;
         PMN_TRY(find(g, stage + ".1.bias", &bias));
         g->up[s].weight = const_cast<float*>(w);
+        if (g->math == PMN_MATH_BF16X3_TC) {
+            float* slabs;
+            const size_t elements = tc_transpose_weight_elements(channels, channels / 2, kUpRate[s]);
+            PMN_TRY(alloc(g, (elements + 1) / 2, &slabs));
+            g->up[s].slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
+            PMN_TRY(launch_pack_tc_transpose_weight(
+                w, g->up[s].slabs, channels, channels / 2, kUpRate[s], stream));
+        }
         g->up[s].bias = bias->data;
         g->up[s].c_in = channels;
         g->up[s].c_out = channels / 2;
@@ -321,9 +329,17 @@ int generator_forward(
     for (int s = 0; s < kStages; ++s) {
         // G4: LeakyReLU + ConvTranspose1d
         const PackedConv& up = g->up[s];
-        PMN_TRY(launch_conv_transpose1d(
-            stage_in, up.weight, up.bias, w.x0, batch, up.c_in, up.c_out, t_len,
-            up.k, kUpRate[s], kSlope, stream));
+        if (g->math == PMN_MATH_BF16X3_TC) {
+            PMN_TRY(launch_planes_from_f32(stage_in, w.at, batch, up.c_in, t_len, kSlope, stream));
+            TcConvArgs a;
+            a.x_planes = w.at; a.w_slabs = up.slabs; a.bias = up.bias; a.out = w.x0;
+            a.batch = batch; a.c_in = up.c_in; a.c_out = up.c_out; a.t_len = t_len;
+            PMN_TRY(launch_conv_transpose1d_tc(a, kUpRate[s], stream));
+        } else {
+            PMN_TRY(launch_conv_transpose1d(
+                stage_in, up.weight, up.bias, w.x0, batch, up.c_in, up.c_out, t_len,
+                up.k, kUpRate[s], kSlope, stream));
+        }
         t_len *= kUpRate[s];
         const int channels = up.c_out;
         if (g->math == PMN_MATH_BF16X3_TC) {

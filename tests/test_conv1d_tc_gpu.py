@@ -98,3 +98,29 @@ def test_block_tc_matches_reference_golden(golden, tag, kernel):
                            residual=cur, in_slope=0.1)
         cur = cur.cpu()
     assert relative_error(cur, g[f'{tag}_y']) < 1e-4
+
+
+@pytest.mark.parametrize('c_in,k,s,t,batch', [
+    (512, 16, 8, 86, 2), (256, 16, 8, 430, 1), (128, 4, 2, 1000, 2), (64, 4, 2, 2049, 1),
+    (512, 16, 8, 5, 1)])
+def test_conv_transpose1d_tc_matches_fp64(c_in, k, s, t, batch):
+    """MultiReceptiveFieldFusion upsampler hifigan.py:97-106 on the tensor cores"""
+    from promonet_b200 import _lib
+    lib = _lib.library()
+    torch.manual_seed(c_in + t)
+    c_out = c_in // 2
+    x = torch.randn(batch, c_in, t)
+    w = torch.randn(c_in, c_out, k) / c_in ** .5
+    b = torch.randn(c_out)
+    expected = torch.nn.functional.conv_transpose1d(
+        torch.nn.functional.leaky_relu(x.double(), 0.1), w.double(), b.double(),
+        stride=s, padding=(k - s) // 2)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    out = torch.empty(batch, c_out, s * t, device='cuda')
+    size = lib.pmn_conv_transpose1d_tc_workspace_bytes(batch, c_in, t, s)
+    workspace = torch.empty(size, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.pmn_conv_transpose1d_tc(
+        xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+        batch, c_in, c_out, t, k, s, 0.1, workspace.data_ptr(), size, _lib.stream()))
+    error = relative_error(out, expected)
+    assert error < 1e-4, error

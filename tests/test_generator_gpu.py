@@ -80,7 +80,8 @@ def test_conv1d_epilogue(lib):
     x = torch.randn(2, 64, 333)
     w = torch.randn(64, 64, 7) / 21.
     b, b2, r = torch.randn(64), torch.randn(2, 64), torch.randn(2, 64, 333)
-    y = torch.nn.functional.conv1d(x, w, b, padding=3) + b2[:, :, None] + r
+    y = torch.nn.functional.conv1d(
+        x.double(), w.double(), b.double(), padding=3) + b2[:, :, None] + r
     accum = torch.ones(2, 64, 333, device='cuda')
     out = conv1d(lib, x, w, b, b2, r, padding=3, out_act=1, accum=accum,
                  accum_mode=2, accum_scale=0.5)
@@ -89,7 +90,8 @@ def test_conv1d_epilogue(lib):
     accum2 = torch.zeros(2, 64, 333, device='cuda')
     assert conv1d(lib, x, w, b, padding=3, accum=accum2, accum_mode=1,
                   accum_scale=1 / 3, want_out=False) is None
-    assert relative_error(accum2, torch.nn.functional.conv1d(x, w, b, padding=3) / 3) < 1e-5
+    assert relative_error(accum2, torch.nn.functional.conv1d(
+        x.double(), w.double(), b.double(), padding=3) / 3) < 1e-5
 
 
 def test_conv1d_rejects_bad_arguments(lib):
