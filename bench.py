@@ -50,7 +50,7 @@ def parse():
     parser.add_argument('--steps', type=int, default=10)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    parser.add_argument('--math', default='fp32', choices=['fp32', 'bf16x3'])
+    parser.add_argument('--math', default='bf16x3', choices=['fp32', 'bf16x3'])
     parser.add_argument('--no-cpu-baseline', action='store_true')
     return parser.parse_args()
 

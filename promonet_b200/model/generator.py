@@ -14,7 +14,7 @@ from promonet_b200.model import init
 
 class Generator:
 
-    def __init__(self, device=None, math=_lib.MATH_FP32_SIMT, state=None):
+    def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None):
         if not torch.cuda.is_available():
             raise RuntimeError(
                 'promonet_b200.model.Generator needs a CUDA device (sm_100a); '
