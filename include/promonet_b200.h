@@ -110,6 +110,62 @@ int pmn_generator_features(
     float* features, int batch, int frames, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* Feature extraction -- promonet/preprocess/core.py:17-126                  */
+/* ------------------------------------------------------------------------ */
+
+/* STFT-derived features of `batch` equal-length utterances audio (B, T) fp32 at
+ * 22 050 Hz; F = T / 256 frames (reflect padding 384, hann 1024, hop 256).
+ * Any of the three outputs may be NULL:
+ *   magnitude (B, 513, F)  sqrt(re^2 + im^2 + 1e-6)     preprocess/spectrogram.py:35-52
+ *   mels      (B, 80, F)   max(log(mel_basis @ magnitude), mel_floor)  spectrogram.py:111-135
+ *             (mel_floor = -INFINITY when no dynamic-range threshold is configured)
+ *   loudness  (B, bands, F), or (B, 513, F) when bands <= 0: A-weighted dB
+ *             promonet/preprocess/loudness.py:17-55 (top_db 80 per utterance, floor -100)
+ * workspace (pmn_spectral_workspace_bytes) is needed for loudness only. */
+size_t pmn_spectral_workspace_bytes(int batch, int samples);
+int pmn_spectral_features(
+    const float* audio, int batch, int samples,
+    float* magnitude, float* mels, float mel_floor, float* loudness, int loudness_bands,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* linear_to_mel (preprocess/spectrogram.py:111-135) of an existing magnitude
+ * spectrogram (B, 513, F) -> (B, 80, F) */
+int pmn_linear_to_mel(
+    const float* magnitude, float* mels, float mel_floor, int batch, int frames, void* stream);
+
+/* torbi.from_probabilities (call witnessed at promonet/preprocess/harmonics.py:270-276):
+ *   observation (B, T, S), batch_frames (B) int32 valid lengths or NULL,
+ *   transition (S, S) [row i -> column j], initial (S); log_probs = 0 takes logs inside
+ *   indices (B, T) int32 out; ties resolve to the lowest index */
+size_t pmn_viterbi_workspace_bytes(int batch, int frames, int states);
+int pmn_viterbi_decode(
+    const float* observation, const int32_t* batch_frames, const float* transition,
+    const float* initial, int log_probs, int32_t* indices, int batch, int frames, int states,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* penn.from_audio(audio, sample_rate, hopsize, fmin, fmax, center='half-hop',
+ * decoder='viterbi') as called at promonet/preprocess/core.py:71-81: FCNF0++
+ * network + Viterbi + local expected value.  Tensor names: layers.{0..5}.conv.{weight,bias},
+ * layers.{0..5}.norm.{weight,bias}, layers.6.{weight,bias}. */
+typedef struct pmn_pitch pmn_pitch;
+int pmn_pitch_create(pmn_pitch** out);
+void pmn_pitch_destroy(pmn_pitch* p);
+int pmn_pitch_set_tensor(
+    pmn_pitch* p, const char* name, const float* data, const int64_t* shape, int ndim, void* stream);
+int pmn_pitch_finalize(pmn_pitch* p, void* stream);
+int pmn_pitch_frames(int samples, int sample_rate, double hopsize_seconds);
+size_t pmn_pitch_workspace_bytes(
+    int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch);
+/*   audio (B, T) fp32 at sample_rate; transition (1440, 1440), initial (1440) probabilities
+ *   pitch, periodicity (B, F); optional logits_out (B, F, 1440) masked logits and
+ *   bins_out (B, F) int32 decoded bins; frame_batch = frames per network pass */
+int pmn_pitch_forward(
+    pmn_pitch* p, const float* audio, int batch, int samples, int sample_rate,
+    double hopsize_seconds, float fmin, float fmax, const float* transition, const float* initial,
+    float* pitch, float* periodicity, float* logits_out, int32_t* bins_out, int frame_batch,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* Operator-level entry points (unit-test granularity)                       */
 /* ------------------------------------------------------------------------ */
 

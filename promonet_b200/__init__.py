@@ -9,4 +9,5 @@ CPU fallback.
 from .config import *
 from . import _lib
 from . import model
+from . import preprocess
 from . import synthesize

@@ -43,6 +43,30 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_int, c_void_p]),
+    'pmn_spectral_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'pmn_spectral_features': (
+        c_int,
+        [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
+         c_void_p, c_size_t, c_void_p]),
+    'pmn_linear_to_mel': (c_int, [c_void_p, c_void_p, c_float, c_int, c_int, c_void_p]),
+    'pmn_viterbi_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'pmn_viterbi_decode': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+         c_void_p, c_size_t, c_void_p]),
+    'pmn_pitch_create': (c_int, [POINTER(c_void_p)]),
+    'pmn_pitch_destroy': (None, [c_void_p]),
+    'pmn_pitch_set_tensor': (
+        c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
+    'pmn_pitch_finalize': (c_int, [c_void_p, c_void_p]),
+    'pmn_pitch_frames': (c_int, [c_int, c_int, ctypes.c_double]),
+    'pmn_pitch_workspace_bytes': (
+        c_size_t, [c_int, c_int, c_int, ctypes.c_double, c_int]),
+    'pmn_pitch_forward': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_double, c_float, c_float,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+         c_void_p, c_size_t, c_void_p]),
     'pmn_weight_norm_fold': (
         c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pmn_pack_conv1d_weight': (

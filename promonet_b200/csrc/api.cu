@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "conv1d_tc.cuh"
 #include "generator.cuh"
+#include "pitch.cuh"
+#include "spectral.cuh"
 
 #include <map>
 #include <mutex>
@@ -185,6 +187,82 @@ int pmn_generator_features(
     PMN_REQUIRE(g, "features: null generator");
     return generator_features(g, loudness, rows, pitch, periodicity, ppg, features, batch, frames,
                               (cudaStream_t)stream);
+}
+
+size_t pmn_spectral_workspace_bytes(int batch, int samples) {
+    if (batch <= 0 || samples <= 0) return 0;
+    return spectral_workspace_bytes(batch, samples);
+}
+
+int pmn_spectral_features(
+    const float* audio, int batch, int samples, float* magnitude, float* mels, float mel_floor,
+    float* loudness, int loudness_bands, void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_spectral_features(
+        audio, batch, samples, magnitude, mels, mel_floor, loudness, loudness_bands,
+        workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int pmn_linear_to_mel(
+    const float* magnitude, float* mels, float mel_floor, int batch, int frames, void* stream) {
+    return launch_linear_to_mel(magnitude, mels, mel_floor, batch, frames, (cudaStream_t)stream);
+}
+
+size_t pmn_viterbi_workspace_bytes(int batch, int frames, int states) {
+    if (batch <= 0 || frames <= 0 || states <= 0) return 0;
+    return viterbi_workspace_bytes(batch, frames, states);
+}
+
+int pmn_viterbi_decode(
+    const float* observation, const int32_t* batch_frames, const float* transition,
+    const float* initial, int log_probs, int32_t* indices, int batch, int frames, int states,
+    void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_viterbi(
+        observation, batch_frames, transition, initial, log_probs != 0, indices, batch, frames,
+        states, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int pmn_pitch_create(pmn_pitch** out) {
+    PMN_REQUIRE(out, "pitch_create: null out");
+    *out = pitch_create();
+    if (!*out) return fail(PMN_ERR_STATE, "out of host memory");
+    return PMN_OK;
+}
+
+void pmn_pitch_destroy(pmn_pitch* p) { pitch_destroy(p); }
+
+int pmn_pitch_set_tensor(
+    pmn_pitch* p, const char* name, const float* data, const int64_t* shape, int ndim, void* stream) {
+    PMN_REQUIRE(p && name && data && ndim >= 0 && (ndim == 0 || shape), "pitch_set_tensor: bad argument");
+    return pitch_set_tensor(p, name, data, shape, ndim, (cudaStream_t)stream);
+}
+
+int pmn_pitch_finalize(pmn_pitch* p, void* stream) {
+    PMN_REQUIRE(p, "pitch_finalize: null model");
+    return pitch_finalize(p, (cudaStream_t)stream);
+}
+
+int pmn_pitch_frames(int samples, int sample_rate, double hopsize_seconds) {
+    if (samples <= 0 || sample_rate <= 0 || hopsize_seconds <= 0.) return 0;
+    return pitch_frames(samples, sample_rate, hopsize_seconds);
+}
+
+size_t pmn_pitch_workspace_bytes(
+    int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch) {
+    if (batch <= 0 || samples <= 0 || sample_rate <= 0 || hopsize_seconds <= 0. || frame_batch <= 0)
+        return 0;
+    return pitch_workspace_bytes(batch, samples, sample_rate, hopsize_seconds, frame_batch);
+}
+
+int pmn_pitch_forward(
+    pmn_pitch* p, const float* audio, int batch, int samples, int sample_rate,
+    double hopsize_seconds, float fmin, float fmax, const float* transition, const float* initial,
+    float* pitch, float* periodicity, float* logits_out, int32_t* bins_out, int frame_batch,
+    void* workspace, size_t workspace_bytes, void* stream) {
+    PMN_REQUIRE(p, "pitch_forward: null model");
+    return pitch_forward(
+        p, audio, batch, samples, sample_rate, hopsize_seconds, fmin, fmax, transition, initial,
+        pitch, periodicity, logits_out, bins_out, frame_batch, workspace, workspace_bytes,
+        (cudaStream_t)stream);
 }
 
 int pmn_weight_norm_fold(const float* v, const float* g, float* w, int dim0, int inner, void* stream) {

@@ -1,0 +1,514 @@
+// penn-style pitch / periodicity estimation (promonet/preprocess/core.py:64-85:
+// penn.from_audio(..., center='half-hop', decoder='viterbi')), FCNF0++ network.
+//
+// Pipeline (definition pinned in oracle/penn.py; penn itself is un-vendored):
+//   resample to 8 kHz (torchaudio sinc_interp_hann polyphase FIR)
+//   -> 1024-sample frames every int(hopsize * 8000) samples, reflect-padded, crop [16:-15]
+//   -> 6 x [Conv1d k32 -> ReLU -> (MaxPool 2) -> LayerNorm(C, L)] -> Conv1d(512 -> 1440, k4)
+//   -> mask bins outside [fmin, fmax), softmax, entropy periodicity
+//   -> Viterbi (viterbi.cu) -> local expected value in a 19-bin window -> Hz
+//
+// Frames are laid end to end on one time axis per channel ([C][frames * L]) so the
+// k32 convolutions run as long 1-D convolutions (conv1d.cu); the 31 samples that
+// straddle two frames are computed and dropped by the pooling / LayerNorm kernel.
+// The last block writes its (512, 4) activations transposed so that the final
+// layer is a dense 2048 -> 1440 product over all frames (conv1d with k = 1).
+#include <math.h>
+
+#include <map>
+#include <new>
+#include <numeric>
+#include <vector>
+
+#include "pitch.cuh"
+#include "spectral.cuh"
+
+namespace pmn {
+
+namespace {
+
+constexpr int kRate = 8000;          // penn.SAMPLE_RATE
+constexpr int kWindow = 1024;        // penn.WINDOW_SIZE
+constexpr int kCropped = 993;        // frames[:, :, 16:-15]
+constexpr int kCropStart = 16;
+constexpr int kBins = 1440;          // penn.PITCH_BINS
+constexpr int kKernel = 32;
+constexpr int kLayers = 6;
+constexpr int kChannels[kLayers + 1] = {1, 256, 32, 32, 128, 256, 512};
+constexpr bool kPooled[kLayers] = {true, true, true, false, false, false};
+constexpr int kLength[kLayers + 1] = {993, 481, 225, 97, 66, 35, 4};  // per-frame length after block i
+constexpr float kCentsPerBin = 5.f, kFmin = 31.f, kOctave = 1200.f;
+constexpr int kLocalWindow = 19;
+
+struct Tensor {
+    float* data = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+
+}  // namespace
+
+}  // namespace pmn
+
+struct pmn_pitch {
+    std::map<std::string, pmn::Tensor> tensors;
+    std::vector<float*> owned;
+    bool finalized = false;
+    float* conv_weight[pmn::kLayers] = {};   // packed (C_in, 32, C_out)
+    const float* conv_bias[pmn::kLayers] = {};
+    const float* norm_weight[pmn::kLayers] = {};
+    const float* norm_bias[pmn::kLayers] = {};
+    float* head_weight = nullptr;            // packed (2048, 1, 1440)
+    const float* head_bias = nullptr;
+    // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
+    struct Resampler { float* table; int orig, fresh, width; };
+    std::map<int, Resampler> resamplers;
+
+    ~pmn_pitch() {
+        for (auto& item : tensors) cudaFree(item.second.data);
+        for (float* p : owned) cudaFree(p);
+        for (auto& item : resamplers) cudaFree(item.second.table);
+    }
+};
+
+namespace pmn {
+
+namespace {
+
+// y[n], n = q * fresh + p:  sum_k table[k][p] * x[q * orig + k - width]
+__global__ void __launch_bounds__(256) resample_kernel(
+    const float* __restrict__ audio, const float* __restrict__ table,
+    float* __restrict__ out, int samples, int out_samples, int orig, int fresh, int width) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= out_samples) return;
+    const int q = n / fresh, p = n % fresh;
+    const float* x = audio + (size_t)b * samples;
+    const int taps = 2 * width + orig;
+    const int start = q * orig - width;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) {
+        const int i = start + k;
+        if (i >= 0 && i < samples) acc = fmaf(table[(size_t)k * fresh + p], x[i], acc);
+    }
+    out[(size_t)b * out_samples + n] = acc;
+}
+
+// Cropped frames laid end to end: x[g * 993 + n] = padded[b][hop * f + 16 + n], g = first + local
+__global__ void __launch_bounds__(256) frames_kernel(
+    const float* __restrict__ audio, float* __restrict__ out, int samples, int frames_per_item,
+    int first_frame, int count, int hop, int padding) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int local = blockIdx.y;
+    if (n >= kCropped || local >= count) return;
+    const int g = first_frame + local;
+    const int b = g / frames_per_item, f = g % frames_per_item;
+    int i = hop * f + kCropStart + n - padding;  // index into the unpadded audio
+    float value = 0.f;
+    if (i < 0) i = -i;
+    if (i >= samples) {
+        // right reflection covers `padding` samples; beyond that the oracle zero-pads
+        const int beyond = i - (samples - 1);
+        i = beyond <= padding ? samples - 1 - beyond : -1;
+    }
+    if (i >= 0 && i < samples) value = audio[(size_t)b * samples + i];
+    out[(size_t)local * kCropped + n] = value;
+}
+
+// MaxPool(2) (optional) + LayerNorm over (C, L) with elementwise affine, per frame.
+// in: [C][in_row] with frame f at columns f * l_in .. f * l_in + l_conv (already ReLU'd)
+// out: [C][count * l_out] or, transposed, [(c * l_out + t)][count]
+__global__ void __launch_bounds__(256) pool_norm_kernel(
+    const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
+    float* __restrict__ out, int channels, int l_in, int l_out, bool pooled, size_t in_row,
+    int count, bool transposed) {
+    __shared__ double partial[2][8];
+    __shared__ float stats[2];
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = channels * l_out;
+    const float* base = in + (size_t)f * l_in;
+    auto value = [&](int idx) {
+        const int c = idx / l_out, t = idx % l_out;
+        const float* row = base + (size_t)c * in_row;
+        return pooled ? fmaxf(row[2 * t], row[2 * t + 1]) : row[t];
+    };
+    float sum = 0.f, squares = 0.f;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const float v = value(idx);
+        sum += v;
+        squares = fmaf(v, v, squares);
+    }
+    double dsum = sum, dsquares = squares;
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, offset);
+        dsquares += __shfl_xor_sync(0xffffffffu, dsquares, offset);
+    }
+    if ((tid & 31) == 0) { partial[0][tid >> 5] = dsum; partial[1][tid >> 5] = dsquares; }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0., q = 0.;
+        for (int w = 0; w < 8; ++w) { s += partial[0][w]; q += partial[1][w]; }
+        const double mean = s / total;
+        const double variance = fmax(q / total - mean * mean, 0.);
+        stats[0] = (float)mean;
+        stats[1] = (float)(1. / sqrt(variance + 1e-5));
+    }
+    __syncthreads();
+    const float mean = stats[0], rstd = stats[1];
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const float v = (value(idx) - mean) * rstd * weight[idx] + bias[idx];
+        if (transposed) {
+            out[(size_t)idx * count + f] = v;
+        } else {
+            const int c = idx / l_out, t = idx % l_out;
+            out[(size_t)c * count * l_out + (size_t)f * l_out + t] = v;
+        }
+    }
+}
+
+// logits^T (1440, count) -> masked logits, softmax and entropy periodicity, 32 frames per CTA
+__global__ void __launch_bounds__(256) posterior_kernel(
+    const float* __restrict__ logits_t, int count, int min_bin, int max_bin,
+    float* __restrict__ masked, float* __restrict__ distribution, float* __restrict__ periodicity) {
+    __shared__ float tile[32][33];
+    __shared__ float reduce[8][32];
+    __shared__ float row_max[32], row_sum[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int f0 = blockIdx.x * 32;
+    const int f = f0 + tx;
+    const bool live = f < count;
+    auto load = [&](int o) {
+        if (!live || o < min_bin || o >= max_bin) return -INFINITY;
+        return logits_t[(size_t)o * count + f];
+    };
+    float best = -INFINITY;
+    for (int o = ty; o < kBins; o += 8) best = fmaxf(best, load(o));
+    reduce[ty][tx] = best;
+    __syncthreads();
+    if (ty == 0) {
+        for (int w = 1; w < 8; ++w) best = fmaxf(best, reduce[w][tx]);
+        row_max[tx] = best;
+    }
+    __syncthreads();
+    const float maximum = row_max[tx];
+    float sum = 0.f;
+    for (int o = ty; o < kBins; o += 8) sum += expf(load(o) - maximum);
+    __syncthreads();
+    reduce[ty][tx] = sum;
+    __syncthreads();
+    if (ty == 0) {
+        for (int w = 1; w < 8; ++w) sum += reduce[w][tx];
+        row_sum[tx] = sum;
+    }
+    __syncthreads();
+    const float inverse = 1.f / row_sum[tx];
+    float entropy = 0.f;
+    for (int o0 = 0; o0 < kBins; o0 += 32) {
+        // logits pass through the tile first, then probabilities: both are written
+        // row-major (frame, bin) with the bins of a frame contiguous
+        float p[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int o = o0 + ty + 8 * i;
+            l[i] = load(o);
+            p[i] = live ? expf(l[i] - maximum) * inverse : 0.f;
+            entropy += p[i] * logf(p[i] + 1e-7f);
+            tile[ty + 8 * i][tx] = l[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = f0 + ty + 8 * i;
+            if (row < count) masked[(size_t)row * kBins + o0 + tx] = tile[tx][ty + 8 * i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = p[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = f0 + ty + 8 * i;
+            if (row < count) distribution[(size_t)row * kBins + o0 + tx] = tile[tx][ty + 8 * i];
+        }
+        __syncthreads();
+    }
+    reduce[ty][tx] = entropy;
+    __syncthreads();
+    if (ty == 0 && live) {
+        for (int w = 1; w < 8; ++w) entropy += reduce[w][tx];
+        periodicity[f] = 1.f + entropy / logf((float)kBins);
+    }
+}
+
+// Local expected value around the decoded bin -> Hz
+__global__ void __launch_bounds__(128) pitch_kernel(
+    const float* __restrict__ masked, const int* __restrict__ bins, float* __restrict__ pitch, int count) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= count) return;
+    const int centre = bins[f];
+    const float* row = masked + (size_t)f * kBins;
+    float values[kLocalWindow];
+    float best = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kLocalWindow; ++w) {
+        const int i = centre - kLocalWindow / 2 + w;
+        values[w] = (i >= 0 && i < kBins) ? row[i] : -INFINITY;
+        best = fmaxf(best, values[w]);
+    }
+    float sum = 0.f, expected = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLocalWindow; ++w) {
+        const float e = expf(values[w] - best);
+        sum += e;
+        expected += e * (kCentsPerBin * (float)(centre - kLocalWindow / 2 + w));
+    }
+    pitch[f] = kFmin * exp2f(expected / sum / kOctave);
+}
+
+int find(const pmn_pitch* p, const std::string& name, const Tensor** out) {
+    auto it = p->tensors.find(name);
+    if (it == p->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
+    *out = &it->second;
+    return PMN_OK;
+}
+
+int alloc(pmn_pitch* p, size_t count, float** out) {
+    PMN_TRY(check_cuda(cudaMalloc(out, count * sizeof(float)), "cudaMalloc"));
+    p->owned.push_back(*out);
+    return PMN_OK;
+}
+
+// torchaudio.functional.resample kernel bank (sinc_interp_hann, width 6, rolloff 0.99),
+// stored transposed: table[k][phase]
+int resampler(pmn_pitch* p, int sample_rate, const pmn_pitch::Resampler** out) {
+    auto it = p->resamplers.find(sample_rate);
+    if (it == p->resamplers.end()) {
+        const int g = std::gcd(sample_rate, kRate);
+        const int orig = sample_rate / g, fresh = kRate / g;
+        const double base = (double)std::min(orig, fresh) * 0.99;
+        const int width = (int)ceil(6. * orig / base);
+        const int taps = 2 * width + orig;
+        const double pi = 3.14159265358979323846;
+        std::vector<float> table((size_t)taps * fresh);
+        for (int phase = 0; phase < fresh; ++phase) {
+            const double shift = (double)((float)(-phase) / (float)fresh);  // fp32 like torch.arange(...) / new_freq
+            for (int k = 0; k < taps; ++k) {
+                double t = (shift + (double)(k - width) / orig) * base;
+                t = std::max(-6., std::min(6., t));
+                const double window = cos(t * pi / 6. / 2.);
+                t *= pi;
+                const double sinc = t == 0. ? 1. : sin(t) / t;
+                table[(size_t)k * fresh + phase] = (float)(sinc * window * window * (base / orig));
+            }
+        }
+        pmn_pitch::Resampler r{nullptr, orig, fresh, width};
+        PMN_TRY(check_cuda(cudaMalloc(&r.table, table.size() * sizeof(float)), "cudaMalloc resampler"));
+        PMN_TRY(check_cuda(
+            cudaMemcpy(r.table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice),
+            "upload resampler"));
+        it = p->resamplers.emplace(sample_rate, r).first;
+    }
+    *out = &it->second;
+    return PMN_OK;
+}
+
+struct Workspace {
+    float *resampled, *conv, *act, *logits_t, *masked, *distribution;
+    int* bins;
+    void* viterbi;
+    size_t viterbi_bytes, bytes;
+};
+
+Workspace carve(void* base, int batch, int out_samples, int frames, int frame_batch) {
+    Workspace w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) {
+        char* r = p;
+        p += align_up(bytes, 256);
+        return r;
+    };
+    const size_t total = (size_t)batch * frames;
+    const size_t fb = (size_t)std::min<size_t>(frame_batch, total);
+    w.resampled = (float*)take((size_t)batch * out_samples * 4);
+    w.conv = (float*)take(fb * 256 * kCropped * 4);                 // largest conv output (layer 0)
+    w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
+    w.logits_t = (float*)take(fb * kBins * 4);
+    w.masked = (float*)take(total * kBins * 4);
+    w.distribution = (float*)take(total * kBins * 4);
+    w.bins = (int*)take(total * 4);
+    w.viterbi_bytes = viterbi_workspace_bytes(batch, frames, kBins);
+    w.viterbi = take(w.viterbi_bytes);
+    w.bytes = (size_t)(p - static_cast<char*>(base));
+    return w;
+}
+
+}  // namespace
+
+pmn_pitch* pitch_create() { return new (std::nothrow) pmn_pitch(); }
+void pitch_destroy(pmn_pitch* p) { delete p; }
+
+int pitch_set_tensor(pmn_pitch* p, const char* name, const float* data, const int64_t* shape,
+                     int ndim, cudaStream_t stream) {
+    if (p->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
+    Tensor t;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
+        t.shape.push_back(shape[i]);
+    }
+    PMN_TRY(check_cuda(cudaMalloc(&t.data, t.numel() * sizeof(float)), "cudaMalloc"));
+    int status = check_cuda(
+        cudaMemcpyAsync(t.data, data, t.numel() * sizeof(float), cudaMemcpyDeviceToDevice, stream),
+        "set_tensor copy");
+    if (status != PMN_OK) { cudaFree(t.data); return status; }
+    auto old = p->tensors.find(name);
+    if (old != p->tensors.end()) { cudaFree(old->second.data); p->tensors.erase(old); }
+    p->tensors.emplace(name, std::move(t));
+    return PMN_OK;
+}
+
+int pitch_finalize(pmn_pitch* p, cudaStream_t stream) {
+    if (p->finalized) return fail(PMN_ERR_STATE, "pitch model already finalized");
+    for (int i = 0; i < kLayers; ++i) {
+        const std::string prefix = "layers." + std::to_string(i);
+        const Tensor *w, *b, *nw, *nb;
+        PMN_TRY(find(p, prefix + ".conv.weight", &w));
+        PMN_TRY(find(p, prefix + ".conv.bias", &b));
+        PMN_TRY(find(p, prefix + ".norm.weight", &nw));
+        PMN_TRY(find(p, prefix + ".norm.bias", &nb));
+        if (w->numel() != (size_t)kChannels[i + 1] * kChannels[i] * kKernel ||
+            nw->numel() != (size_t)kChannels[i + 1] * kLength[i + 1] || nb->numel() != nw->numel())
+            return fail(PMN_ERR_STATE, "unexpected shapes at " + prefix);
+        PMN_TRY(alloc(p, w->numel(), &p->conv_weight[i]));
+        PMN_TRY(launch_pack_conv1d_weight(
+            w->data, p->conv_weight[i], kChannels[i + 1], kChannels[i], kKernel, stream));
+        p->conv_bias[i] = b->data;
+        p->norm_weight[i] = nw->data;
+        p->norm_bias[i] = nb->data;
+    }
+    const Tensor *w, *b;
+    PMN_TRY(find(p, "layers.6.weight", &w));
+    PMN_TRY(find(p, "layers.6.bias", &b));
+    if (w->numel() != (size_t)kBins * 512 * 4) return fail(PMN_ERR_STATE, "unexpected layers.6 shape");
+    PMN_TRY(alloc(p, w->numel(), &p->head_weight));
+    // (1440, 512, 4) read as (1440, 2048, 1): input index c * 4 + t matches the transposed activations
+    PMN_TRY(launch_pack_conv1d_weight(w->data, p->head_weight, kBins, 2048, 1, stream));
+    p->head_bias = b->data;
+    PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "finalize sync"));
+    p->finalized = true;
+    return PMN_OK;
+}
+
+int pitch_frames(int samples, int sample_rate, double hopsize_seconds) {
+    const int frames = (int)((double)samples / (hopsize_seconds * sample_rate));
+    return frames < 1 ? 1 : frames;
+}
+
+static int resampled_length(int samples, int sample_rate) {
+    const int g = std::gcd(sample_rate, kRate);
+    const long long fresh = kRate / g, orig = sample_rate / g;
+    return (int)((fresh * samples + orig - 1) / orig);
+}
+
+size_t pitch_workspace_bytes(int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch) {
+    return carve(nullptr, batch, resampled_length(samples, sample_rate),
+                 pitch_frames(samples, sample_rate, hopsize_seconds), frame_batch).bytes;
+}
+
+int pitch_forward(
+    pmn_pitch* p, const float* audio, int batch, int samples, int sample_rate,
+    double hopsize_seconds, float fmin, float fmax, const float* transition, const float* initial,
+    float* pitch, float* periodicity, float* logits_out, int* bins_out, int frame_batch,
+    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!p->finalized) return fail(PMN_ERR_STATE, "pitch model not finalized");
+    PMN_REQUIRE(audio && pitch && periodicity && transition && initial && workspace, "pitch: null pointer");
+    PMN_REQUIRE(batch > 0 && batch <= 65535 && samples > 0 && sample_rate > 0 && frame_batch > 0,
+                "pitch: bad shape");
+    const int hop = (int)(hopsize_seconds * kRate);
+    PMN_REQUIRE(hop > 0 && hop < kWindow, "pitch: bad hopsize");
+    const int padding = (kWindow - hop) / 2;
+    const int out_samples = resampled_length(samples, sample_rate);
+    PMN_REQUIRE(out_samples > padding, "pitch: audio shorter than the reflect padding");
+    const int frames = pitch_frames(samples, sample_rate, hopsize_seconds);
+    const int total = batch * frames;
+    Workspace w = carve(workspace, batch, out_samples, frames, frame_batch);
+    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "pitch: workspace too small");
+
+    // 1. resample to 8 kHz
+    const float* audio8k = audio;
+    if (sample_rate != kRate) {
+        const pmn_pitch::Resampler* r;
+        PMN_TRY(resampler(p, sample_rate, &r));
+        dim3 grid(ceil_div(out_samples, 256), batch);
+        LaunchScope scope("resample_kernel", stream);
+        resample_kernel<<<grid, 256, 0, stream>>>(
+            audio, r->table, w.resampled, samples, out_samples, r->orig, r->fresh, r->width);
+        PMN_TRY(launched("resample_kernel"));
+        audio8k = w.resampled;
+    }
+
+    // penn.convert.frequency_to_bins: floor / ceil of 1200 log2(f / 31) / 5
+    const int min_bin = std::max(0, (int)floor(kOctave * log2((double)fmin / kFmin) / kCentsPerBin));
+    const int max_bin = std::min(kBins, (int)ceil(kOctave * log2((double)fmax / kFmin) / kCentsPerBin));
+
+    // 2. network, frame_batch frames at a time
+    for (int first = 0; first < total; first += frame_batch) {
+        const int count = std::min(frame_batch, total - first);
+        {
+            dim3 grid(ceil_div(kCropped, 256), count);
+            LaunchScope scope("frames_kernel", stream);
+            frames_kernel<<<grid, 256, 0, stream>>>(
+                audio8k, w.act, out_samples, frames, first, count, hop, padding);
+            PMN_TRY(launched("frames_kernel"));
+        }
+        for (int i = 0; i < kLayers; ++i) {
+            const int l_in = kLength[i];
+            const size_t row = (size_t)count * l_in - (kKernel - 1);
+            Conv1dArgs a;
+            a.x = w.act; a.weight = p->conv_weight[i]; a.bias = p->conv_bias[i]; a.out = w.conv;
+            a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
+            a.t_in = count * l_in; a.t_out = (int)row; a.k = kKernel; a.out_act = 2;
+            PMN_TRY(launch_conv1d(a, stream));
+            LaunchScope scope("pool_norm_kernel", stream);
+            pool_norm_kernel<<<count, 256, 0, stream>>>(
+                w.conv, p->norm_weight[i], p->norm_bias[i], w.act, kChannels[i + 1], l_in,
+                kLength[i + 1], kPooled[i], row, count, i == kLayers - 1);
+            PMN_TRY(launched("pool_norm_kernel"));
+        }
+        {
+            Conv1dArgs a;
+            a.x = w.act; a.weight = p->head_weight; a.bias = p->head_bias; a.out = w.logits_t;
+            a.batch = 1; a.c_in = 2048; a.c_out = kBins; a.t_in = a.t_out = count; a.k = 1;
+            PMN_TRY(launch_conv1d(a, stream));
+        }
+        {
+            LaunchScope scope("posterior_kernel", stream);
+            posterior_kernel<<<ceil_div(count, 32), 256, 0, stream>>>(
+                w.logits_t, count, min_bin, max_bin, w.masked + (size_t)first * kBins,
+                w.distribution + (size_t)first * kBins, periodicity + first);
+            PMN_TRY(launched("posterior_kernel"));
+        }
+    }
+
+    // 3. Viterbi over the posteriors, 4. local expected value
+    int* bins = bins_out ? bins_out : w.bins;
+    PMN_TRY(launch_viterbi(
+        w.distribution, nullptr, transition, initial, false, bins, batch, frames, kBins,
+        w.viterbi, w.viterbi_bytes, stream));
+    {
+        LaunchScope scope("pitch_kernel", stream);
+        pitch_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(w.masked, bins, pitch, total);
+        PMN_TRY(launched("pitch_kernel"));
+    }
+    if (logits_out)
+        PMN_TRY(check_cuda(
+            cudaMemcpyAsync(logits_out, w.masked, (size_t)total * kBins * 4, cudaMemcpyDeviceToDevice, stream),
+            "copy logits"));
+    return PMN_OK;
+}
+
+}  // namespace pmn

@@ -91,3 +91,35 @@ def test_oracle_against_live_reference(state):
         actual = hifigan.generator(model.state_dict(), *args)
     assert relative_error(actual, expected) < 1e-5
     assert all(torch.equal(v, state[k]) for k, v in model.state_dict().items())
+
+
+def test_viterbi_c_oracle_matches_numpy():
+    import numpy as np
+    from oracle import viterbi
+    rng = np.random.default_rng(0)
+    observation = rng.random((3, 40, 37)).astype(np.float32)
+    observation /= observation.sum(-1, keepdims=True)
+    transition = rng.random((37, 37)).astype(np.float32)
+    index = np.arange(37)
+    transition[np.abs(index[:, None] - index[None]) > 5] = 0
+    transition /= transition.sum(1, keepdims=True)
+    initial = np.full(37, 1 / 37, np.float32)
+    lengths = [40, 17, 1]
+    a = viterbi.decode(observation, lengths, transition, initial)
+    b = viterbi.decode_numpy(observation, lengths, transition, initial)
+    assert np.array_equal(a, b)
+    # a path that can only stay within the band
+    assert (np.abs(np.diff(a[0])) <= 5).all()
+
+
+def test_penn_oracle_shapes():
+    from oracle import penn
+    state = penn.init_state(1234)
+    assert sum(v.numel() for v in state.values()) == 8934624
+    audio = inputs.audio(1, 8000)
+    pitch, periodicity, aux = penn.from_audio(state, audio)
+    assert pitch.shape == periodicity.shape == (1, 31)
+    assert aux['frames'].shape == (31, 1, 1024)
+    assert float(periodicity.min()) >= 0. and float(periodicity.max()) <= 1.
+    transition = penn.transition_matrix(256 / 22050)
+    assert torch.allclose(transition.sum(1), torch.ones(1440))
