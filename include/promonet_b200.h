@@ -110,6 +110,33 @@ int pmn_generator_features(
     float* features, int batch, int frames, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* Generator (FARGAN, config/fargan.py) -- promonet/model/fargan.py:21-131,  */
+/* promonet/model/generator.py:116-135 with MODEL='fargan'                   */
+/* ------------------------------------------------------------------------ */
+
+typedef struct pmn_fargan pmn_fargan;
+int pmn_fargan_create(pmn_fargan** out);
+void pmn_fargan_destroy(pmn_fargan* g);
+/* state_dict entries by reference name, e.g.
+ * "model.subframe_network.gru1.weight_ih", "model.conditioning_network.0.weight" */
+int pmn_fargan_set_tensor(
+    pmn_fargan* g, const char* name, const float* data, const int64_t* shape, int ndim, void* stream);
+int pmn_fargan_finalize(pmn_fargan* g, void* stream);
+size_t pmn_fargan_workspace_bytes(const pmn_fargan* g, int batch, int frames);
+/* Same inputs as pmn_generator_forward plus previous_samples (B, 512) fp32 or NULL
+ * (zeros: generator.py default_previous_samples); audio (B, 1, 256 F).  Inference
+ * semantics: no additive noise (fargan.py:396-403 is training-only). */
+int pmn_fargan_forward(
+    pmn_fargan* g,
+    const float* loudness, int loudness_rows,
+    const float* pitch, const float* periodicity, const float* ppg,
+    const int64_t* speakers,
+    const float* spectral_balance_ratios, const float* loudness_ratios,
+    const float* previous_samples,
+    float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* Feature extraction -- promonet/preprocess/core.py:17-126                  */
 /* ------------------------------------------------------------------------ */
 

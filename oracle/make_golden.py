@@ -88,5 +88,30 @@ def main():
     print('wrote', sorted(p.name for p in GOLDEN.iterdir()))
 
 
+def fargan():
+    """config/fargan.py needs its own process (derived constants freeze at import)"""
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    promonet = ref_shim.load(ref_shim.REFERENCE_ROOT + '/config/fargan.py')
+    assert promonet.MODEL == 'fargan'
+    torch.manual_seed(promonet.RANDOM_SEED)
+    generator = promonet.model.Generator().eval()
+    state = generator.state_dict()
+    loud, pitch, per, ppg, spk, sbr, lr = inputs.synthesis(2, 12, seed=99)
+    previous = 0.1 * torch.randn(2, 1, promonet.NUM_PREVIOUS_SAMPLES)
+    with torch.no_grad():
+        audio = generator(loud, pitch, per, ppg, spk, sbr, lr, torch.zeros_like(previous))
+        audio_previous = generator(loud, pitch, per, ppg, spk, sbr, lr, previous)
+    names = sorted(checksums(state))
+    np.savez_compressed(
+        GOLDEN / 'fargan.npz',
+        loudness=loud.numpy(), pitch=pitch.numpy(), periodicity=per.numpy(), ppg=ppg.numpy(),
+        speakers=spk.numpy(), sbr=sbr.numpy(), lr=lr.numpy(), previous=previous.numpy(),
+        audio=audio.numpy(), audio_previous=audio_previous.numpy(),
+        checksum_names=np.array(names),
+        checksum_values=np.array([checksums(state)[n] for n in names]))
+    print('wrote fargan.npz')
+
+
 if __name__ == '__main__':
-    main()
+    import sys
+    fargan() if '--fargan' in sys.argv else main()

@@ -43,6 +43,16 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_int, c_void_p]),
+    'pmn_fargan_create': (c_int, [POINTER(c_void_p)]),
+    'pmn_fargan_destroy': (None, [c_void_p]),
+    'pmn_fargan_set_tensor': (
+        c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
+    'pmn_fargan_finalize': (c_int, [c_void_p, c_void_p]),
+    'pmn_fargan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int]),
+    'pmn_fargan_forward': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     'pmn_spectral_workspace_bytes': (c_size_t, [c_int, c_int]),
     'pmn_spectral_features': (
         c_int,

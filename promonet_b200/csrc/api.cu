@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "conv1d_tc.cuh"
+#include "fargan.cuh"
 #include "generator.cuh"
 #include "pitch.cuh"
 #include "spectral.cuh"
@@ -187,6 +188,42 @@ int pmn_generator_features(
     PMN_REQUIRE(g, "features: null generator");
     return generator_features(g, loudness, rows, pitch, periodicity, ppg, features, batch, frames,
                               (cudaStream_t)stream);
+}
+
+int pmn_fargan_create(pmn_fargan** out) {
+    PMN_REQUIRE(out, "fargan_create: null out");
+    *out = fargan_create();
+    if (!*out) return fail(PMN_ERR_STATE, "out of host memory");
+    return PMN_OK;
+}
+
+void pmn_fargan_destroy(pmn_fargan* g) { fargan_destroy(g); }
+
+int pmn_fargan_set_tensor(
+    pmn_fargan* g, const char* name, const float* data, const int64_t* shape, int ndim, void* stream) {
+    PMN_REQUIRE(g && name && data && ndim >= 0 && (ndim == 0 || shape), "fargan_set_tensor: bad argument");
+    return fargan_set_tensor(g, name, data, shape, ndim, (cudaStream_t)stream);
+}
+
+int pmn_fargan_finalize(pmn_fargan* g, void* stream) {
+    PMN_REQUIRE(g, "fargan_finalize: null generator");
+    return fargan_finalize(g, (cudaStream_t)stream);
+}
+
+size_t pmn_fargan_workspace_bytes(const pmn_fargan*, int batch, int frames) {
+    if (batch <= 0 || frames <= 0) return 0;
+    return fargan_workspace_bytes(batch, frames);
+}
+
+int pmn_fargan_forward(
+    pmn_fargan* g, const float* loudness, int rows, const float* pitch, const float* periodicity,
+    const float* ppg, const int64_t* speakers, const float* sbr, const float* lr,
+    const float* previous_samples, float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, void* stream) {
+    PMN_REQUIRE(g, "fargan_forward: null generator");
+    return fargan_forward(
+        g, loudness, rows, pitch, periodicity, ppg, speakers, sbr, lr, previous_samples, audio,
+        batch, frames, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t pmn_spectral_workspace_bytes(int batch, int samples) {

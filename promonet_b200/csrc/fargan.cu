@@ -1,0 +1,625 @@
+// FARGAN generator (config/fargan.py): promonet/model/fargan.py, rows F1/F2.
+//
+// The vocoder is strictly sequential: 4 subframes per frame, each consuming the
+// 512 samples before it (pitch lookback) and three GRU states.  Per subframe the
+// network is ~11 dependent matrix-vector layers (2.25 M MAC per utterance), so
+// the cost is latency, not FLOPs.  Design:
+//
+//  * the conditioning MLP (fargan.py:139-160) has no recurrence: it runs for all
+//    frames at once as three k=1 convolutions (conv1d.cu) before the loop;
+//  * the recurrent part is ONE persistent cooperative kernel.  Utterances are
+//    independent, so the batch is cut into groups of 16 and each group gets 64
+//    CTAs that never talk to another group.  Every CTA keeps its slice of every
+//    layer's weights (4 output units per layer, 140 KB) resident in shared
+//    memory for the whole utterance; activations (16 utterances x <= 1152
+//    values) are exchanged through L2 in a [k][utterance] layout and the 64
+//    CTAs of a group meet at a release/acquire counter barrier after each layer;
+//  * the subframe input (conditioning slice, previous subframe, pitch lookback)
+//    is rebuilt by every CTA from the sample history, so the "previous input"
+//    state of FramewiseConv (fargan.py:349-364) never leaves shared memory.
+#include <math.h>
+
+#include <map>
+#include <new>
+#include <vector>
+
+#include "fargan.cuh"
+#include "features.cuh"
+
+namespace pmn {
+
+namespace {
+
+constexpr int kHop = 256;
+constexpr int kSub = 64;            // FARGAN_SUBFRAME_SIZE
+constexpr int kSubframes = 4;       // FARGAN_SUBFRAMES
+constexpr int kHistory = 512;       // NUM_PREVIOUS_SAMPLES
+constexpr int kLookback = kSub + 4;
+constexpr int kInput = 2 * kSub + kSub + kLookback;  // 260: cond slice, previous, lookback
+constexpr int kFeatures = 113, kGlobal = 258, kCondIn = kFeatures + kGlobal;  // 371
+constexpr int kCond = 2 * kHop;     // 512
+constexpr int kGroupItems = 16;     // utterances per CTA group
+constexpr int kGroupCtas = 64;
+constexpr int kUnits = kHop / kGroupCtas;  // 4 output units per CTA per layer
+constexpr int kThreads = 256;
+constexpr int kParts = kThreads / kGroupItems;  // 16 K-partitions
+
+// Per-CTA weight image (floats), every block stored [k][rows]
+constexpr int kWFw = 0;                                   // 520 x 4
+constexpr int kWFwGlu = kWFw + 2 * kInput * kUnits;       // 256 x 4
+constexpr int kWGru = kWFwGlu + kHop * kUnits;            // 3 x (384 x 12 + 256 x 12)
+constexpr int kGruIh = (kHop + 2 * kSub) * 3 * kUnits;    // 4608
+constexpr int kGruHh = kHop * 3 * kUnits;                 // 3072
+constexpr int kWGlu = kWGru + 3 * (kGruIh + kGruHh);      // 3 x 256 x 4
+constexpr int kWSkip = kWGlu + 3 * kHop * kUnits;         // 1152 x 4
+constexpr int kWSkipGlu = kWSkip + (4 * kHop + 2 * kSub) * kUnits;
+constexpr int kWOut = kWSkipGlu + kHop * kUnits;          // 256 x 1
+constexpr int kWeights = kWOut + kHop;                    // 35104
+
+constexpr int kStage = 2 * kHop * kGroupItems;            // staged activations: 512 x 16 floats
+constexpr int kScratch = (kParts / 2) * 24 * kGroupItems; // K-partition partial sums
+constexpr int kSmemFloats = kWeights + 2 * kInput * kGroupItems + kStage + kScratch;
+constexpr int kSmemBytes = kSmemFloats * 4 + 64;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct Tensor {
+    float* data = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+
+// Activations of one group in global memory, all [k][16]
+struct GroupState {
+    float* fw;        // tanh(fwconv)            256
+    float* fwg;       // after GLU               256
+    float* h[3][2];   // GRU states, double-buffered
+    float* g[3];      // GRU GLU outputs         256 each
+    float* skip;      // tanh(skip dense)        256
+    float* skipg;     // after GLU               256
+    float* history;   // (512 + T) samples
+    unsigned int* barrier;
+};
+
+__device__ __forceinline__ float sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// All 64 CTAs of a group arrive; generation-free monotonic counter
+__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int& target) {
+    __syncthreads();
+    target += kGroupCtas;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Copy rows [0, rows) of a [k][16] activation from L2 (never L1: other CTAs wrote it)
+__device__ __forceinline__ void stage(float* dst, const float* src, int rows) {
+    const float4* s = reinterpret_cast<const float4*>(src);
+    float4* d = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < rows * kGroupItems / 4; i += kThreads) d[i] = __ldcg(s + i);
+}
+
+// acc[r] += sum_k w[k][r] * x[k][b] over this thread's K partition
+template <int ROWS>
+__device__ __forceinline__ void dot(
+    float (&acc)[ROWS], const float* __restrict__ w, const float* __restrict__ x, int k_count,
+    int part, int b) {
+    for (int k = part; k < k_count; k += kParts) {
+        const float a = x[k * kGroupItems + b];
+        const float* row = w + k * ROWS;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(row[r], a, acc[r]);
+    }
+}
+
+// Sum the K partitions: results land in scratch[r][b] (r < ROWS), valid after the sync
+template <int ROWS>
+__device__ __forceinline__ void reduce(float (&acc)[ROWS], float* scratch, int part, int b) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+    __syncthreads();  // previous users of scratch are done
+    if ((part & 1) == 0) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) scratch[((part >> 1) * ROWS + r) * kGroupItems + b] = acc[r];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * kGroupItems; idx += kThreads) {
+        float sum = 0.f;
+#pragma unroll
+        for (int p = 0; p < kParts / 2; ++p) sum += scratch[p * ROWS * kGroupItems + idx];
+        scratch[idx] = sum;  // idx < ROWS * 16 <= the p = 0 slab: each thread rewrites its own slot
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
+    const float* __restrict__ weights,   // (64, kWeights) per-CTA images
+    const float* __restrict__ cond,      // (B, 512, F) tanh conditioning
+    const float* __restrict__ features,  // (B, 114, F): row 113 = pitch period
+    const float* __restrict__ previous,  // (B, 512) or null (zeros)
+    GroupState* __restrict__ groups, float* __restrict__ audio, int batch, int frames) {
+    extern __shared__ __align__(16) float smem[];
+    float* w = smem;
+    float* input[2] = {smem + kWeights, smem + kWeights + kInput * kGroupItems};
+    float* staged = smem + kWeights + 2 * kInput * kGroupItems;
+    float* scratch = staged + kStage;
+
+    const int tid = threadIdx.x;
+    const int cta = blockIdx.x % kGroupCtas;
+    const int group = blockIdx.x / kGroupCtas;
+    const int b = tid & (kGroupItems - 1);
+    const int part = tid >> 4;
+    const int item = group * kGroupItems + b;   // utterance of this thread's column
+    const bool live = item < batch;
+    const GroupState gs = groups[group];
+    const int samples = frames * kHop;
+    unsigned int target = 0;
+
+    for (int i = tid; i < kWeights; i += kThreads) w[i] = weights[(size_t)cta * kWeights + i];
+    for (int i = tid; i < 2 * kInput * kGroupItems; i += kThreads) input[0][i] = 0.f;  // state3 = 0
+    // history[0:512] = previous samples; GRU states start at zero (fargan.py:406-415)
+    if (cta == 0) {
+        for (int i = tid; i < kHistory * kGroupItems; i += kThreads) {
+            const int k = i / kGroupItems, col = i % kGroupItems;
+            const int it = group * kGroupItems + col;
+            gs.history[i] = (previous && it < batch) ? previous[(size_t)it * kHistory + k] : 0.f;
+        }
+        for (int s = 0; s < 3; ++s)
+            for (int i = tid; i < kHop * kGroupItems; i += kThreads) gs.h[s][0][i] = 0.f;
+    }
+    group_barrier(gs.barrier, target);
+
+    int current = 0;  // input[current] = this subframe's features, input[current ^ 1] = previous
+    for (int n = 0; n < frames * kSubframes; ++n) {
+        const int f = n / kSubframes, sub = n % kSubframes;
+        const int parity = n & 1;  // GRU state buffer read this subframe
+        float* in = input[current];
+        const float* state3 = input[current ^ 1];
+        const float* hist = gs.history + (size_t)n * kSub * kGroupItems;  // 512-sample window
+
+        // ---- subframe input: cond[:, sub::4] (fargan.py:109-113), previous 64, lookback 68 ----
+        for (int idx = tid; idx < kInput * kGroupItems; idx += kThreads) {
+            const int k = idx / kGroupItems, col = idx % kGroupItems;
+            const int it = group * kGroupItems + col;
+            float v = 0.f;
+            if (it < batch) {
+                if (k < 2 * kSub) {
+                    v = __ldg(cond + ((size_t)it * kCond + 4 * k + sub) * frames + f);
+                } else if (k < 3 * kSub) {
+                    v = __ldcg(hist + (size_t)(kHistory - kSub + (k - 2 * kSub)) * kGroupItems + col);
+                } else {
+                    const int period = (int)rintf(__ldg(features + ((size_t)it * 114 + 113) * frames + f));
+                    int index = kHistory - period + (k - 3 * kSub) - 2;   // fargan.py:233-239
+                    if (index >= kHistory) index -= period;
+                    index = max(index, 0);
+                    v = __ldcg(hist + (size_t)index * kGroupItems + col);
+                }
+            }
+            in[idx] = v;
+        }
+        __syncthreads();
+
+        // ---- framewise conv: tanh(W [in; state3]) (fargan.py:349-364) ----
+        {
+            float acc[kUnits] = {};
+            dot<kUnits>(acc, w + kWFw, in, kInput, part, b);
+            dot<kUnits>(acc, w + kWFw + kInput * kUnits, state3, kInput, part, b);
+            reduce<kUnits>(acc, scratch, part, b);
+            if (tid < kUnits * kGroupItems)
+                gs.fw[(size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems)] =
+                    tanhf(scratch[tid]);
+        }
+        group_barrier(gs.barrier, target);
+
+        // GLU: x * sigmoid(W x) for this CTA's 4 units (fargan.py:375-388)
+        auto glu = [&](const float* wg, const float* x_global, float* out_global) {
+            stage(staged, x_global, kHop);
+            __syncthreads();
+            float acc[kUnits] = {};
+            dot<kUnits>(acc, wg, staged, kHop, part, b);
+            reduce<kUnits>(acc, scratch, part, b);
+            if (tid < kUnits * kGroupItems) {
+                const int unit = cta * kUnits + tid / kGroupItems, col = tid % kGroupItems;
+                const float x = staged[unit * kGroupItems + col];
+                out_global[(size_t)unit * kGroupItems + col] = x * sigmoid(scratch[tid]);
+            }
+        };
+
+        glu(w + kWFwGlu, gs.fw, gs.fwg);
+        group_barrier(gs.barrier, target);
+
+        // ---- three GRU cells + GLUs (fargan.py:267-309) ----
+        const float* lookback = in + (3 * kSub + 2) * kGroupItems;  // pitch_lookback[:, 2:-2]
+        const float* last = in + 2 * kSub * kGroupItems;             // previous subframe
+        for (int s = 0; s < 3; ++s) {
+            const float* wih = w + kWGru + s * (kGruIh + kGruHh);
+            const float* whh = wih + kGruIh;
+            const float* x_global = s == 0 ? gs.fwg : gs.g[s - 1];
+            stage(staged, x_global, kHop);
+            stage(staged + kHop * kGroupItems, gs.h[s][parity], kHop);
+            __syncthreads();
+            float gi[3 * kUnits] = {}, gh[3 * kUnits] = {};
+            dot<3 * kUnits>(gi, wih, staged, kHop, part, b);
+            dot<3 * kUnits>(gi, wih + kHop * 3 * kUnits, lookback, kSub, part, b);
+            dot<3 * kUnits>(gi, wih + (kHop + kSub) * 3 * kUnits, last, kSub, part, b);
+            dot<3 * kUnits>(gh, whh, staged + kHop * kGroupItems, kHop, part, b);
+            float both[6 * kUnits];
+#pragma unroll
+            for (int r = 0; r < 3 * kUnits; ++r) { both[r] = gi[r]; both[3 * kUnits + r] = gh[r]; }
+            reduce<6 * kUnits>(both, scratch, part, b);
+            if (tid < kUnits * kGroupItems) {
+                const int u = tid / kGroupItems, col = tid % kGroupItems;
+                const int unit = cta * kUnits + u;
+                auto at = [&](int row) { return scratch[row * kGroupItems + col]; };
+                const float r = sigmoid(at(3 * u) + at(3 * kUnits + 3 * u));
+                const float z = sigmoid(at(3 * u + 1) + at(3 * kUnits + 3 * u + 1));
+                const float c = tanhf(at(3 * u + 2) + r * at(3 * kUnits + 3 * u + 2));
+                const float h = staged[(kHop + unit) * kGroupItems + col];
+                gs.h[s][parity ^ 1][(size_t)unit * kGroupItems + col] = (1.f - z) * c + z * h;
+            }
+            group_barrier(gs.barrier, target);
+            glu(w + kWGlu + s * kHop * kUnits, gs.h[s][parity ^ 1], gs.g[s]);
+            group_barrier(gs.barrier, target);
+        }
+
+        // ---- skip: tanh(W [g1, g2, g3, fw, lookback, previous]) then GLU (fargan.py:311-325) ----
+        {
+            float acc[kUnits] = {};
+            stage(staged, gs.g[0], kHop);
+            stage(staged + kHop * kGroupItems, gs.g[1], kHop);
+            __syncthreads();
+            dot<kUnits>(acc, w + kWSkip, staged, 2 * kHop, part, b);
+            __syncthreads();
+            stage(staged, gs.g[2], kHop);
+            stage(staged + kHop * kGroupItems, gs.fwg, kHop);
+            __syncthreads();
+            dot<kUnits>(acc, w + kWSkip + 2 * kHop * kUnits, staged, 2 * kHop, part, b);
+            dot<kUnits>(acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
+            dot<kUnits>(acc, w + kWSkip + (4 * kHop + kSub) * kUnits, last, kSub, part, b);
+            reduce<kUnits>(acc, scratch, part, b);
+            if (tid < kUnits * kGroupItems)
+                gs.skip[(size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems)] =
+                    tanhf(scratch[tid]);
+        }
+        group_barrier(gs.barrier, target);
+        glu(w + kWSkipGlu, gs.skip, gs.skipg);
+        group_barrier(gs.barrier, target);
+
+        // ---- output: tanh(W skip), one of the 64 samples per CTA (fargan.py:327-329) ----
+        {
+            stage(staged, gs.skipg, kHop);
+            __syncthreads();
+            float acc[1] = {};
+            dot<1>(acc, w + kWOut, staged, kHop, part, b);
+            reduce<1>(acc, scratch, part, b);
+            if (tid < kGroupItems) {
+                const float y = tanhf(scratch[tid]);
+                gs.history[(size_t)(kHistory + n * kSub + cta) * kGroupItems + tid] = y;
+                const int it = group * kGroupItems + tid;
+                if (it < batch) audio[(size_t)it * samples + n * kSub + cta] = y;
+            }
+        }
+        group_barrier(gs.barrier, target);
+        current ^= 1;
+    }
+    (void)live;
+}
+
+// x (B, 371, F) = [features[:113]; speaker embedding; ratios broadcast over frames]
+__global__ void __launch_bounds__(128) cond_input_kernel(
+    const float* __restrict__ features, const float* __restrict__ speaker_embedding,
+    const int64_t* __restrict__ speakers, const float* __restrict__ sbr, const float* __restrict__ lr,
+    float* __restrict__ out, int frames, int num_speakers) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y, b = blockIdx.z;
+    if (f >= frames) return;
+    float v;
+    if (c < kFeatures) {
+        v = features[((size_t)b * 114 + c) * frames + f];
+    } else if (c < kFeatures + 256) {
+        int64_t speaker = speakers[b];
+        speaker = speaker < 0 ? 0 : (speaker >= num_speakers ? num_speakers - 1 : speaker);
+        v = speaker_embedding[(size_t)speaker * 256 + (c - kFeatures)];
+    } else {
+        v = c == kFeatures + 256 ? sbr[b] : lr[b];
+    }
+    out[((size_t)b * kCondIn + c) * frames + f] = v;
+}
+
+}  // namespace
+
+}  // namespace pmn
+
+struct pmn_fargan {
+    std::map<std::string, pmn::Tensor> tensors;
+    std::vector<void*> owned;
+    bool finalized = false;
+    float ppg_threshold = 0.85f;
+    float* images = nullptr;         // (64, kWeights)
+    float* cond_weight[3] = {};      // packed (C_in, 1, C_out)
+
+    ~pmn_fargan() {
+        for (auto& item : tensors) cudaFree(item.second.data);
+        for (void* p : owned) cudaFree(p);
+    }
+};
+
+namespace pmn {
+
+namespace {
+
+int find(const pmn_fargan* g, const std::string& name, const Tensor** out) {
+    auto it = g->tensors.find(name);
+    if (it == g->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
+    *out = &it->second;
+    return PMN_OK;
+}
+
+// Host copy of `<prefix>.weight`, folding weight norm (Linear: per output row)
+int host_weight(pmn_fargan* g, const std::string& prefix, int rows, int cols,
+                std::vector<float>* out, cudaStream_t stream) {
+    out->resize((size_t)rows * cols);
+    auto plain = g->tensors.find(prefix + ".weight");
+    const float* source;
+    float* folded = nullptr;
+    if (plain != g->tensors.end()) {
+        if (plain->second.numel() != out->size()) return fail(PMN_ERR_STATE, "bad shape at " + prefix);
+        source = plain->second.data;
+    } else {
+        const Tensor *wg, *wv;
+        PMN_TRY(find(g, prefix + ".weight_g", &wg));
+        PMN_TRY(find(g, prefix + ".weight_v", &wv));
+        if (wv->numel() != out->size() || wg->numel() != (size_t)rows)
+            return fail(PMN_ERR_STATE, "bad weight_g/weight_v shapes at " + prefix);
+        PMN_TRY(check_cuda(cudaMalloc(&folded, out->size() * 4), "cudaMalloc"));
+        int status = launch_weight_norm_fold(wv->data, wg->data, folded, rows, cols, stream);
+        if (status != PMN_OK) { cudaFree(folded); return status; }
+        source = folded;
+    }
+    int status = check_cuda(cudaStreamSynchronize(stream), "sync");
+    if (status == PMN_OK)
+        status = check_cuda(cudaMemcpy(out->data(), source, out->size() * 4, cudaMemcpyDeviceToHost), "D2H weight");
+    if (folded) cudaFree(folded);
+    return status;
+}
+
+struct Workspace {
+    float *features, *cond_in, *cond_a, *cond_b, *state;
+    GroupState* groups;       // device array
+    unsigned int* barriers;
+    size_t group_floats, bytes;
+};
+
+Workspace carve(void* base, int batch, int frames) {
+    Workspace w;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t bytes) {
+        char* r = p;
+        p += align_up(bytes, 256);
+        return r;
+    };
+    const int groups = ceil_div(batch, kGroupItems);
+    w.features = (float*)take((size_t)batch * 114 * frames * 4);
+    w.cond_in = (float*)take((size_t)batch * kCondIn * frames * 4);
+    w.cond_a = (float*)take((size_t)batch * kCond * frames * 4);
+    w.cond_b = (float*)take((size_t)batch * kCond * frames * 4);
+    // per group: fw, fwg, 6 h, 3 g, skip, skipg = 13 x 256 x 16, history (512 + T) x 16
+    w.group_floats = (size_t)13 * kHop * kGroupItems + (size_t)(kHistory + frames * kHop) * kGroupItems;
+    w.state = (float*)take((size_t)groups * w.group_floats * 4);
+    w.groups = (GroupState*)take((size_t)groups * sizeof(GroupState));
+    w.barriers = (unsigned int*)take((size_t)groups * 128);
+    w.bytes = (size_t)(p - static_cast<char*>(base));
+    return w;
+}
+
+}  // namespace
+
+pmn_fargan* fargan_create() { return new (std::nothrow) pmn_fargan(); }
+void fargan_destroy(pmn_fargan* g) { delete g; }
+
+int fargan_set_tensor(pmn_fargan* g, const char* name, const float* data, const int64_t* shape,
+                      int ndim, cudaStream_t stream) {
+    if (g->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
+    Tensor t;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
+        t.shape.push_back(shape[i]);
+    }
+    PMN_TRY(check_cuda(cudaMalloc(&t.data, t.numel() * 4), "cudaMalloc"));
+    int status = check_cuda(
+        cudaMemcpyAsync(t.data, data, t.numel() * 4, cudaMemcpyDeviceToDevice, stream), "set_tensor copy");
+    if (status != PMN_OK) { cudaFree(t.data); return status; }
+    auto old = g->tensors.find(name);
+    if (old != g->tensors.end()) { cudaFree(old->second.data); g->tensors.erase(old); }
+    g->tensors.emplace(name, std::move(t));
+    return PMN_OK;
+}
+
+int fargan_finalize(pmn_fargan* g, cudaStream_t stream) {
+    if (g->finalized) return fail(PMN_ERR_STATE, "fargan already finalized");
+    const Tensor* t;
+    PMN_TRY(find(g, "speaker_embedding.weight", &t));
+    PMN_TRY(find(g, "pitch_embedding.weight", &t));
+    PMN_TRY(find(g, "pitch_distribution", &t));
+    auto threshold = g->tensors.find("ppg_threshold");
+    if (threshold != g->tensors.end()) {
+        PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
+        PMN_TRY(check_cuda(
+            cudaMemcpy(&g->ppg_threshold, threshold->second.data, 4, cudaMemcpyDeviceToHost),
+            "read ppg_threshold"));
+    }
+    // conditioning MLP as k = 1 convolutions
+    const int cond_out[3] = {kCondIn, kCondIn, kCond};
+    for (int i = 0; i < 3; ++i) {
+        PMN_TRY(find(g, "model.conditioning_network." + std::to_string(2 * i) + ".weight", &t));
+        if (t->numel() != (size_t)cond_out[i] * kCondIn) return fail(PMN_ERR_STATE, "bad conditioning shape");
+        PMN_TRY(check_cuda(cudaMalloc(&g->cond_weight[i], t->numel() * 4), "cudaMalloc"));
+        g->owned.push_back(g->cond_weight[i]);
+        PMN_TRY(launch_pack_conv1d_weight(t->data, g->cond_weight[i], cond_out[i], kCondIn, 1, stream));
+    }
+    // per-CTA weight images
+    const std::string net = "model.subframe_network.";
+    std::vector<float> fw, fwglu, skip, skipglu, out, ih[3], hh[3], glu[3];
+    PMN_TRY(host_weight(g, net + "framewise_convolution.model.0", kHop, 2 * kInput, &fw, stream));
+    PMN_TRY(host_weight(g, net + "framewise_convolution.model.2.gate", kHop, kHop, &fwglu, stream));
+    for (int s = 0; s < 3; ++s) {
+        const std::string cell = net + "gru" + std::to_string(s + 1);
+        const Tensor *wi, *wh;
+        PMN_TRY(find(g, cell + ".weight_ih", &wi));
+        PMN_TRY(find(g, cell + ".weight_hh", &wh));
+        if (wi->numel() != (size_t)3 * kHop * (kHop + 2 * kSub) || wh->numel() != (size_t)3 * kHop * kHop)
+            return fail(PMN_ERR_STATE, "bad GRU shape at " + cell);
+        ih[s].resize(wi->numel());
+        hh[s].resize(wh->numel());
+        PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
+        PMN_TRY(check_cuda(cudaMemcpy(ih[s].data(), wi->data, wi->numel() * 4, cudaMemcpyDeviceToHost), "D2H"));
+        PMN_TRY(check_cuda(cudaMemcpy(hh[s].data(), wh->data, wh->numel() * 4, cudaMemcpyDeviceToHost), "D2H"));
+        PMN_TRY(host_weight(g, cell + "_glu.gate", kHop, kHop, &glu[s], stream));
+    }
+    PMN_TRY(host_weight(g, net + "skip_dense", kHop, 4 * kHop + 2 * kSub, &skip, stream));
+    PMN_TRY(host_weight(g, net + "skip_glu.gate", kHop, kHop, &skipglu, stream));
+    PMN_TRY(host_weight(g, net + "output_layer", kSub, kHop, &out, stream));
+
+    std::vector<float> images((size_t)kGroupCtas * kWeights);
+    for (int cta = 0; cta < kGroupCtas; ++cta) {
+        float* image = images.data() + (size_t)cta * kWeights;
+        // dense layers: rows cta * 4 .. + 3, stored [k][4]
+        auto dense = [&](float* dst, const std::vector<float>& weight, int cols) {
+            for (int k = 0; k < cols; ++k)
+                for (int u = 0; u < kUnits; ++u)
+                    dst[k * kUnits + u] = weight[(size_t)(cta * kUnits + u) * cols + k];
+        };
+        dense(image + kWFw, fw, 2 * kInput);
+        dense(image + kWFwGlu, fwglu, kHop);
+        for (int s = 0; s < 3; ++s) {
+            float* base = image + kWGru + s * (kGruIh + kGruHh);
+            // GRU: rows (gate * 256 + unit), stored [k][unit * 3 + gate]
+            auto gates = [&](float* dst, const std::vector<float>& weight, int cols) {
+                for (int k = 0; k < cols; ++k)
+                    for (int u = 0; u < kUnits; ++u)
+                        for (int gate = 0; gate < 3; ++gate)
+                            dst[k * 3 * kUnits + 3 * u + gate] =
+                                weight[(size_t)(gate * kHop + cta * kUnits + u) * cols + k];
+            };
+            gates(base, ih[s], kHop + 2 * kSub);
+            gates(base + kGruIh, hh[s], kHop);
+            dense(image + kWGlu + s * kHop * kUnits, glu[s], kHop);
+        }
+        dense(image + kWSkip, skip, 4 * kHop + 2 * kSub);
+        dense(image + kWSkipGlu, skipglu, kHop);
+        for (int k = 0; k < kHop; ++k) image[kWOut + k] = out[(size_t)cta * kHop + k];
+    }
+    PMN_TRY(check_cuda(cudaMalloc(&g->images, images.size() * 4), "cudaMalloc"));
+    g->owned.push_back(g->images);
+    PMN_TRY(check_cuda(cudaMemcpy(g->images, images.data(), images.size() * 4, cudaMemcpyHostToDevice), "H2D images"));
+    g->finalized = true;
+    return PMN_OK;
+}
+
+size_t fargan_workspace_bytes(int batch, int frames) { return carve(nullptr, batch, frames).bytes; }
+
+int fargan_forward(
+    pmn_fargan* g, const float* loudness, int rows, const float* pitch, const float* periodicity,
+    const float* ppg, const int64_t* speakers, const float* sbr, const float* lr,
+    const float* previous_samples, float* audio, int batch, int frames,
+    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!g->finalized) return fail(PMN_ERR_STATE, "fargan not finalized");
+    PMN_REQUIRE(audio && workspace && speakers && sbr && lr, "fargan: null pointer");
+    PMN_REQUIRE(batch > 0 && frames > 0, "fargan: empty batch");
+    int device = 0, sms = 0, cooperative = 0;
+    PMN_TRY(check_cuda(cudaGetDevice(&device), "cudaGetDevice"));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, device);
+    if (!cooperative) return fail(PMN_ERR_STATE, "fargan: device lacks cooperative launch");
+    const int max_items = sms / kGroupCtas * kGroupItems;  // utterances per cooperative launch
+    PMN_REQUIRE(max_items > 0, "fargan: fewer than 64 SMs");
+    Workspace w = carve(workspace, batch, frames);
+    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "fargan: workspace too small");
+
+    // features (B, 114, F) incl. pitch period; conditioning for every frame
+    PMN_TRY(launch_features(
+        loudness, rows, pitch, periodicity, ppg, g->tensors.at("pitch_distribution").data,
+        g->tensors.at("pitch_embedding.weight").data, g->ppg_threshold, true, w.features,
+        batch, frames, stream));
+    {
+        dim3 grid(ceil_div(frames, 128), kCondIn, batch);
+        LaunchScope scope("cond_input_kernel", stream);
+        cond_input_kernel<<<grid, 128, 0, stream>>>(
+            w.features, g->tensors.at("speaker_embedding.weight").data, speakers, sbr, lr,
+            w.cond_in, frames, 109);
+        PMN_TRY(launched("cond_input_kernel"));
+    }
+    const float* x = w.cond_in;
+    float* outs[3] = {w.cond_a, w.cond_b, w.cond_a};
+    const int cond_out[3] = {kCondIn, kCondIn, kCond};
+    for (int i = 0; i < 3; ++i) {
+        Conv1dArgs a;
+        a.x = x; a.weight = g->cond_weight[i]; a.out = outs[i];
+        a.batch = batch; a.c_in = kCondIn; a.c_out = cond_out[i];
+        a.t_in = a.t_out = frames; a.k = 1; a.out_act = 1;
+        PMN_TRY(launch_conv1d(a, stream));
+        x = outs[i];
+    }
+
+    // group state pointers
+    const int groups = ceil_div(batch, kGroupItems);
+    std::vector<GroupState> host(groups);
+    for (int i = 0; i < groups; ++i) {
+        float* p = w.state + (size_t)i * w.group_floats;
+        const size_t unit = (size_t)kHop * kGroupItems;
+        GroupState& s = host[i];
+        s.fw = p; s.fwg = p + unit;
+        for (int j = 0; j < 3; ++j) { s.h[j][0] = p + (2 + 2 * j) * unit; s.h[j][1] = p + (3 + 2 * j) * unit; }
+        for (int j = 0; j < 3; ++j) s.g[j] = p + (8 + j) * unit;
+        s.skip = p + 11 * unit; s.skipg = p + 12 * unit;
+        s.history = p + 13 * unit;
+        s.barrier = w.barriers + (size_t)i * 32;
+    }
+    PMN_TRY(check_cuda(
+        cudaMemcpyAsync(w.groups, host.data(), groups * sizeof(GroupState), cudaMemcpyHostToDevice, stream),
+        "upload group state"));
+    PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));  // `host` must outlive the copy
+    PMN_TRY(check_cuda(cudaMemsetAsync(w.barriers, 0, (size_t)groups * 128, stream), "memset barriers"));
+
+    static bool configured = false;
+    if (!configured) {
+        PMN_TRY(check_cuda(
+            cudaFuncSetAttribute(fargan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
+            "fargan smem attribute"));
+        configured = true;
+    }
+    const int groups_per_launch = max_items / kGroupItems;
+    for (int first = 0; first < groups; first += groups_per_launch) {
+        const int count = std::min(groups_per_launch, groups - first);
+        const float* weights = g->images;
+        const float* cond = x;
+        const float* feats = w.features;
+        const float* prev = previous_samples ? previous_samples + (size_t)first * kGroupItems * kHistory : nullptr;
+        GroupState* gs = w.groups + first;
+        float* out = audio + (size_t)first * kGroupItems * frames * kHop;
+        int items = std::min(batch - first * kGroupItems, count * kGroupItems);
+        // cond / features are indexed by absolute utterance: offset the bases instead
+        cond += (size_t)first * kGroupItems * kCond * frames;
+        feats += (size_t)first * kGroupItems * 114 * frames;
+        int frames_arg = frames;
+        void* args[] = {&weights, &cond, &feats, &prev, &gs, &out, &items, &frames_arg};
+        LaunchScope scope("fargan_kernel", stream);
+        PMN_TRY(check_cuda(
+            cudaLaunchCooperativeKernel(
+                (void*)fargan_kernel, dim3(count * kGroupCtas), dim3(kThreads), args, kSmemBytes, stream),
+            "fargan cooperative launch"));
+    }
+    return PMN_OK;
+}
+
+}  // namespace pmn

@@ -1,2 +1,3 @@
+from .fargan import FarganGenerator
 from .generator import Generator
 from . import init

@@ -95,3 +95,72 @@ def hifigan_state(seed=None):
         config.SPARSE_PPG_THRESHOLD, dtype=torch.float)
     state['pitch_distribution'] = pitch_distribution()
     return state
+
+
+###############################################################################
+# FARGAN (config/fargan.py)
+###############################################################################
+
+
+def _discard_orthogonal(rows, cols):
+    # fargan.py:418-424 init_weights: orthogonal_ lands in the `.weight` that
+    # weight norm recomputes from (g, v), but it still draws rows * cols normals
+    torch.empty(rows, cols).normal_(0, 1)
+
+
+def _weight_norm_linear(state, name, linear):
+    v = linear.weight.detach().clone()
+    state[f'{name}.weight_g'] = v.norm(dim=1, keepdim=True)
+    state[f'{name}.weight_v'] = v
+
+
+def fargan_state(seed=None):
+    """State dict of a freshly constructed fargan Generator
+    (promonet/model/fargan.py:16-19,139-197,349-388; same RNG draw order)"""
+    if seed is not None:
+        torch.manual_seed(seed)
+    hop = config.HOPSIZE
+    state = OrderedDict()
+    state['default_previous_samples'] = torch.zeros(1, 1, 2 * hop)
+    channels = config.NUM_FEATURES + config.GLOBAL_CHANNELS
+    for i, out in zip((0, 2, 4), (channels, channels, 2 * hop)):
+        state[f'model.conditioning_network.{i}.weight'] = torch.nn.Linear(
+            channels, out, bias=False).weight.detach().clone()
+    net = 'model.subframe_network'
+    # FramewiseConv: Linear(520 -> 256), then its GLU (constructed, then GLU.apply),
+    # then FramewiseConv.apply over both
+    fw = torch.nn.Linear(2 * (hop + 4), hop, bias=False)
+    fw_gate = torch.nn.Linear(hop, hop, bias=False)
+    _discard_orthogonal(hop, hop)
+    _discard_orthogonal(hop, 2 * (hop + 4))
+    _discard_orthogonal(hop, hop)
+    _weight_norm_linear(state, f'{net}.framewise_convolution.model.0', fw)
+    _weight_norm_linear(state, f'{net}.framewise_convolution.model.2.gate', fw_gate)
+    for i in (1, 2, 3):
+        cell = torch.nn.GRUCell(hop + hop // 2, hop, bias=False)
+        state[f'{net}.gru{i}.weight_ih'] = cell.weight_ih.detach().clone()
+        state[f'{net}.gru{i}.weight_hh'] = cell.weight_hh.detach().clone()
+    gates = {}
+    for name in ('gru1_glu', 'gru2_glu', 'gru3_glu', 'skip_glu'):
+        gates[name] = torch.nn.Linear(hop, hop, bias=False)
+        _discard_orthogonal(hop, hop)
+    skip = torch.nn.Linear(4 * hop + hop // 2, hop, bias=False)
+    output = torch.nn.Linear(hop, hop // 4, bias=False)
+    # SubframeNetwork.apply(init_weights): children in registration order
+    _discard_orthogonal(hop, 2 * (hop + 4))   # framewise Linear
+    _discard_orthogonal(hop, hop)             # framewise GLU gate
+    for name in gates:
+        _discard_orthogonal(hop, hop)
+    torch.nn.init.orthogonal_(skip.weight.data)
+    torch.nn.init.orthogonal_(output.weight.data)
+    for name, gate in gates.items():
+        _weight_norm_linear(state, f'{net}.{name}.gate', gate)
+    state[f'{net}.skip_dense.weight'] = skip.weight.detach().clone()
+    state[f'{net}.output_layer.weight'] = output.weight.detach().clone()
+    state['speaker_embedding.weight'] = torch.nn.Embedding(
+        config.NUM_SPEAKERS, config.SPEAKER_CHANNELS).weight.detach().clone()
+    state['pitch_embedding.weight'] = torch.nn.Embedding(
+        config.PITCH_BINS, config.PITCH_EMBEDDING_SIZE).weight.detach().clone()
+    state['ppg_threshold'] = torch.tensor(config.SPARSE_PPG_THRESHOLD, dtype=torch.float)
+    state['pitch_distribution'] = pitch_distribution()
+    return state

@@ -123,3 +123,17 @@ def test_penn_oracle_shapes():
     assert float(periodicity.min()) >= 0. and float(periodicity.max()) <= 1.
     transition = penn.transition_matrix(256 / 22050)
     assert torch.allclose(transition.sum(1), torch.ones(1440))
+
+
+def test_fargan_oracle_matches_reference_output(golden):
+    from oracle import fargan
+    g = golden('fargan')
+    state = init.fargan_state(1234)
+    for name, value in zip(g['checksum_names'], g['checksum_values']):
+        assert float(state[str(name)].double().abs().sum()) == pytest.approx(
+            float(value), rel=1e-12), name
+    args = [g[k] for k in ('loudness', 'pitch', 'periodicity', 'ppg', 'speakers', 'sbr', 'lr')]
+    with torch.no_grad():
+        assert relative_error(fargan.generator(state, *args), g['audio']) < 1e-5
+        assert relative_error(
+            fargan.generator(state, *args, g['previous']), g['audio_previous']) < 1e-5
