@@ -31,6 +31,10 @@ ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+# torchrun exports OMP_NUM_THREADS=1; the CPU baseline is entitled to every host core
+# and OpenMP sizes its pool at the first parallel region, so set it before torch loads
+os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
+
 BATCH = 32                      # utterances per GPU (north_star)
 FRAMES = 430                    # 5 s = 110 250 samples -> 430 frames
 HOPSIZE = 256
@@ -323,7 +327,7 @@ def run_b200(args):
                 'hbm_frac_layer_boundary': (total_samples / world / (ms * 1e-3)) * 15830 / (peak['hbm_gbs'] * 1e9),
                 'kernels': shares},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             result['cpu_baseline'], _ = cpu_baseline(2, 1)
         print(json.dumps(result))
     if distributed:
