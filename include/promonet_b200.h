@@ -179,7 +179,8 @@ int pmn_pitch_create(pmn_pitch** out);
 void pmn_pitch_destroy(pmn_pitch* p);
 int pmn_pitch_set_tensor(
     pmn_pitch* p, const char* name, const float* data, const int64_t* shape, int ndim, void* stream);
-int pmn_pitch_finalize(pmn_pitch* p, void* stream);
+/* math: pmn_math (tensor cores run blocks 1..5; block 0 and the head stay fp32 FMA) */
+int pmn_pitch_finalize(pmn_pitch* p, int math, void* stream);
 int pmn_pitch_frames(int samples, int sample_rate, double hopsize_seconds);
 size_t pmn_pitch_workspace_bytes(
     int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch);
@@ -242,6 +243,15 @@ int pmn_conv1d_tc(
     int batch, int channels, int t_len, int k, int dilation,
     float in_slope, float out_slope,
     void* workspace, size_t workspace_bytes, void* stream);
+
+/* General form: C_in -> C_out in {(256,256), (128,128), (64,64), (32,32), (256,32),
+ * (32,128), (128,256)}, k <= 32, valid != 0 for no padding (T_out = T - (k-1) d),
+ * relu != 0 for max(y, 0): the penn FCNF0++ blocks (promonet/preprocess/core.py:71). */
+int pmn_conv1d_tc_general(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int c_in, int c_out, int t_len, int k, int dilation, int valid, int relu,
+    float in_slope, float out_slope, void* workspace, size_t workspace_bytes, void* stream);
 
 /* LeakyReLU + ConvTranspose1d with kernel = 2*stride, padding = stride/2
  * (hifigan.py:97-106; PyTorch weight layout (C_in, C_out, K)), T_out = stride*T_in */

@@ -68,7 +68,7 @@ SIGNATURES = {
     'pmn_pitch_destroy': (None, [c_void_p]),
     'pmn_pitch_set_tensor': (
         c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
-    'pmn_pitch_finalize': (c_int, [c_void_p, c_void_p]),
+    'pmn_pitch_finalize': (c_int, [c_void_p, c_int, c_void_p]),
     'pmn_pitch_frames': (c_int, [c_int, c_int, ctypes.c_double]),
     'pmn_pitch_workspace_bytes': (
         c_size_t, [c_int, c_int, c_int, ctypes.c_double, c_int]),
@@ -93,6 +93,11 @@ SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
          c_void_p, c_size_t, c_void_p]),
+    'pmn_conv1d_tc_general': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+         c_float, c_float, c_void_p, c_size_t, c_void_p]),
     'pmn_conv_transpose1d': (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

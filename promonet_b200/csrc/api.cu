@@ -273,9 +273,9 @@ int pmn_pitch_set_tensor(
     return pitch_set_tensor(p, name, data, shape, ndim, (cudaStream_t)stream);
 }
 
-int pmn_pitch_finalize(pmn_pitch* p, void* stream) {
+int pmn_pitch_finalize(pmn_pitch* p, int math, void* stream) {
     PMN_REQUIRE(p, "pitch_finalize: null model");
-    return pitch_finalize(p, (cudaStream_t)stream);
+    return pitch_finalize(p, math, (cudaStream_t)stream);
 }
 
 int pmn_pitch_frames(int samples, int sample_rate, double hopsize_seconds) {
@@ -328,7 +328,8 @@ struct TcOpWorkspace {
     __nv_bfloat16 *x_planes, *y_planes, *slabs;
     size_t bytes;
 };
-TcOpWorkspace carve_tc_op(void* base, int batch, int channels, int t_len, int k) {
+TcOpWorkspace carve_tc_op(void* base, int batch, int channels, int t_len, int k, int c_out = 0) {
+    if (c_out <= 0) c_out = channels;
     TcOpWorkspace w;
     char* p = static_cast<char*>(base);
     auto take = [&](size_t elements) {
@@ -337,8 +338,8 @@ TcOpWorkspace carve_tc_op(void* base, int batch, int channels, int t_len, int k)
         return r;
     };
     w.x_planes = take(tc_planes_elements(batch, channels, t_len));
-    w.y_planes = take(tc_planes_elements(batch, channels, t_len));
-    w.slabs = take(tc_weight_elements(channels, channels, k));
+    w.y_planes = take(tc_planes_elements(batch, c_out, t_len));
+    w.slabs = take(tc_weight_elements(c_out, channels, k));
     w.bytes = (size_t)(p - static_cast<char*>(base));
     return w;
 }
@@ -348,7 +349,7 @@ void pmn_debug_tc_counters(void* counters) { tc_set_debug_counters(static_cast<l
 
 size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k) {
     if (batch <= 0 || channels <= 0 || t_len <= 0 || k <= 0) return 0;
-    return carve_tc_op(nullptr, batch, channels, t_len, k).bytes;
+    return carve_tc_op(nullptr, batch, channels, t_len, k, 512).bytes;
 }
 
 int pmn_conv1d_tc(
@@ -356,25 +357,40 @@ int pmn_conv1d_tc(
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
     int batch, int channels, int t_len, int k, int dilation, float in_slope, float out_slope,
     void* workspace, size_t workspace_bytes, void* stream_) {
+    return pmn_conv1d_tc_general(
+        x, weight, bias, residual, out, planes_out, accum, accum_mode, accum_scale, batch,
+        channels, channels, t_len, k, dilation, 0, 0, in_slope, out_slope, workspace,
+        workspace_bytes, stream_);
+}
+
+int pmn_conv1d_tc_general(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int c_in, int c_out, int t_len, int k, int dilation, int valid, int relu,
+    float in_slope, float out_slope, void* workspace, size_t workspace_bytes, void* stream_) {
     PMN_REQUIRE(x && weight && workspace, "conv1d_tc: null pointer");
     PMN_REQUIRE(batch > 0 && t_len > 0, "conv1d_tc: empty input");
-    PMN_REQUIRE(tc_supported(channels, channels, k, dilation), "conv1d_tc: unsupported shape");
+    PMN_REQUIRE(tc_supported(c_in, c_out, k, dilation), "conv1d_tc: unsupported shape");
+    PMN_REQUIRE(c_out <= 512, "conv1d_tc: more than 512 output channels");
     cudaStream_t stream = (cudaStream_t)stream_;
-    TcOpWorkspace w = carve_tc_op(workspace, batch, channels, t_len, k);
+    TcOpWorkspace w = carve_tc_op(workspace, batch, c_in, t_len, k, c_out);
     if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "conv1d_tc: workspace too small");
-    PMN_TRY(launch_planes_from_f32(x, w.x_planes, batch, channels, t_len, in_slope, stream));
-    PMN_TRY(launch_pack_tc_weight(weight, w.slabs, channels, channels, k, stream));
+    PMN_TRY(launch_planes_from_f32(x, w.x_planes, batch, c_in, t_len, in_slope, stream));
+    PMN_TRY(launch_pack_tc_weight(weight, w.slabs, c_out, c_in, k, false, stream));
     TcConvArgs a;
     a.x_planes = w.x_planes; a.w_slabs = w.slabs; a.bias = bias; a.residual = residual;
     a.out = out; a.accum = accum; a.accum_mode = accum_mode; a.accum_scale = accum_scale;
-    a.batch = batch; a.c_in = a.c_out = channels; a.t_len = t_len; a.k = k; a.dilation = dilation;
+    a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_len = t_len; a.k = k; a.dilation = dilation;
+    a.valid = valid != 0; a.relu = relu != 0;
     a.out_slope = out_slope;
+    const int t_out = valid ? t_len - (k - 1) * dilation : t_len;
+    PMN_REQUIRE(t_out > 0, "conv1d_tc: input shorter than the kernel");
     if (planes_out) {
         a.out_planes = w.y_planes;
-        PMN_TRY(launch_zero_plane_pads(w.y_planes, batch, channels, t_len, stream));
+        PMN_TRY(launch_zero_plane_pads(w.y_planes, batch, c_out, t_out, stream));
     }
     PMN_TRY(launch_conv1d_tc(a, stream));
-    if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, channels, t_len, stream));
+    if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, c_out, t_out, stream));
     return PMN_OK;
 }
 

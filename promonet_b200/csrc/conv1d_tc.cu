@@ -143,33 +143,49 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 // Kernel
 // ---------------------------------------------------------------------------
 
-template <int C_IN, int C_OUT, int S, int KB, int NW, int AS>
+enum : int {
+    kConv = 0,       // Conv1d, "same" or valid padding, rows = time steps
+    kTranspose = 1,  // ConvTranspose1d as a 3-tap convolution with UP * c_out columns
+    kFrames = 2      // valid Conv1d over frames laid end to end: M = 16 frames x 8 rows
+};
+
+constexpr int kFrameRows = 8;      // output rows computed per frame in kFrames mode
+constexpr int kFramesPerTile = 16;
+constexpr int kMaxFrameLength = 35;
+
+// C_IN input channels (the K of the GEMM), N output columns per tile (TMEM columns
+// of one MMA, or half of them when CONCAT), S x 128 output rows per tile, KB input
+// channels per shared-memory slab, NW weight-slab stages, AS accumulator stages.
+// CONCAT: the B operand is [W_hi; W_lo] (2 N rows), so a_hi w_hi and a_hi w_lo
+// come out of ONE MMA (columns [0, N) and [N, 2 N)) and a_lo w_hi of a second one
+// that accumulates into [0, N): two reads of the 128-row A operand per K chunk
+// instead of three, which is what bounds the narrow (N <= 64) layers.
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT>
 struct TcConfig {
-    static constexpr int kTile = S * 128;                   // time steps per tile
-    static constexpr int kRowsMax = kTile + 2 * kMaxHalo;
-    static constexpr int kGroups = KB / 8;                   // 8-channel groups per K block
+    static constexpr int kTile = S * 128;
+    static constexpr int kRowsMax =
+        MODE == kFrames ? (kFramesPerTile - 1) * kMaxFrameLength + kFrameRows + 31 : kTile + 2 * kMaxHalo;
+    static constexpr int kGroups = KB / 8;                      // 8-channel groups per K block
     static constexpr int kBlocks = C_IN / KB;
     static constexpr int kXSlab = 2 * kGroups * kRowsMax * 16;  // bytes, both planes
-    static constexpr int kWSlab = KB * C_OUT * 4;               // bytes, both planes
+    static constexpr int kWSlab = KB * N * 4;                   // bytes, both planes
     static constexpr int kXStages = 2;
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
     static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128;
-    static constexpr int kColumns = AS * S * C_OUT;
+    static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
+    static constexpr int kColumns = AS * S * kCols;
     static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
                                   : kColumns <= 256 ? 256 : 512;
     static_assert(kColumns <= 512, "accumulators exceed TMEM");
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
-    static_assert(C_IN % KB == 0 && KB % 16 == 0 && C_OUT % 32 == 0 && C_OUT <= 256, "shape");
+    static_assert(C_IN % KB == 0 && KB % 16 == 0 && N % 32 == 0 && kCols <= 256, "shape");
+    static_assert(MODE != kFrames || S == 1, "frame mode computes one 128-row tile");
 };
 
-// UP == 0: Conv1d with C_OUT output channels (one N tile).  UP == stride > 0:
-// ConvTranspose1d(kernel 2 UP, padding UP / 2) written as a 3-tap convolution over
-// input positions with UP * c_out phase-major output columns, C_OUT of them per
-// N tile (see pack_tc_transpose_weight_kernel).
-template <int C_IN, int C_OUT, int S, int KB, int NW, int AS, int UP>
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, int UP, bool CONCAT>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     TcConvArgs a, int t_pad, int tiles_per_item, int n_tiles, int num_tiles) {
-    using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* x_slabs = smem;
@@ -185,8 +201,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int halo = (a.k - 1) / 2 * a.dilation;
-    const int rows = Cfg::kTile + 2 * halo;  // staged time window
+    const int span = (a.k - 1) * a.dilation;               // receptive field minus one
+    const int left = a.valid ? 0 : span / 2;               // rows staged before the tile
+    // rows of the staged window and rows advanced per tile
+    const int rows = MODE == kFrames ? (kFramesPerTile - 1) * a.frame_length + kFrameRows + span
+                                     : Cfg::kTile + span;
+    const int advance = MODE == kFrames ? kFramesPerTile * a.frame_length : Cfg::kTile;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Cfg::kXStages; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % n_tiles, rest = tile / n_tiles;
                 const int b = rest / tiles_per_item;
-                const int t0 = (rest % tiles_per_item) * Cfg::kTile;
+                const int t0 = (rest % tiles_per_item) * advance;
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
@@ -228,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         for (int g = 0; g < Cfg::kGroups; ++g) {
                             const size_t row0 =
                                 ((size_t)(b * 2 + p) * (C_IN / 8) + kb * Cfg::kGroups + g) * t_pad +
-                                kTcPad + t0 - halo;
+                                kTcPad + t0 - left;
                             bulk_copy(dst + (p * Cfg::kGroups + g) * rows * 16,
                                       a.x_planes + row0 * 8, rows * 16, x_full + xs);
                         }
@@ -255,11 +275,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(128, C_OUT);
+            constexpr uint32_t idesc = instr_desc(128, N);
+            constexpr uint32_t idesc_wide = instr_desc(128, Cfg::kCols);
             uint32_t xcount = 0, wcount = 0, tcount = 0;
             long long wait_x = 0, wait_w = 0, wait_acc = 0, begin = a.debug ? clock64() : 0, mark = 0;
             const uint32_t x_plane = Cfg::kGroups * rows * 16;      // bytes between hi and lo
-            constexpr uint32_t w_plane = Cfg::kGroups * C_OUT * 16;
+            // 8-row groups of the A operand: consecutive rows, or one group per frame
+            const uint32_t a_sbo = MODE == kFrames ? a.frame_length * 16 : 128;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
                 ++tcount;
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 mbar_wait(acc_empty + as, aphase ^ 1);
                 if (a.debug) wait_acc += clock64() - mark;
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + as * (S * C_OUT);
+                const uint32_t d_base = tmem_base + as * (S * Cfg::kCols);
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
@@ -287,18 +309,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll
                         for (int s = 0; s < S; ++s) {
                             const uint32_t row = s * 128 + tap * a.dilation;
+                            const uint32_t d = d_base + s * Cfg::kCols;
 #pragma unroll
                             for (int kk = 0; kk < KB / 16; ++kk) {
                                 const uint32_t xa = x_addr + (2 * kk * rows + row) * 16;
-                                const uint32_t wa = w_addr + 2 * kk * C_OUT * 16;
-                                const uint64_t a_hi = smem_desc(xa, rows * 16, 128);
-                                const uint64_t a_lo = smem_desc(xa + x_plane, rows * 16, 128);
-                                const uint64_t b_hi = smem_desc(wa, C_OUT * 16, 128);
-                                const uint64_t b_lo = smem_desc(wa + w_plane, C_OUT * 16, 128);
-                                const uint32_t d = d_base + s * C_OUT;
-                                tc_mma(d, a_hi, b_hi, idesc, !(first && kk == 0));
-                                tc_mma(d, a_lo, b_hi, idesc, 1);
-                                tc_mma(d, a_hi, b_lo, idesc, 1);
+                                const uint64_t a_hi = smem_desc(xa, rows * 16, a_sbo);
+                                const uint64_t a_lo = smem_desc(xa + x_plane, rows * 16, a_sbo);
+                                if constexpr (CONCAT) {
+                                    // slab [k group][hi rows 0..N) | lo rows N..2N)][8]
+                                    const uint32_t wa = w_addr + 2 * kk * (2 * N) * 16;
+                                    const uint64_t b_both = smem_desc(wa, 2 * N * 16, 128);
+                                    tc_mma(d, a_hi, b_both, idesc_wide, !(first && kk == 0));
+                                    tc_mma(d, a_lo, b_both, idesc, 1);
+                                } else {
+                                    // slab [plane][k group][N][8]
+                                    constexpr uint32_t w_plane = Cfg::kGroups * N * 16;
+                                    const uint32_t wa = w_addr + 2 * kk * N * 16;
+                                    const uint64_t b_hi = smem_desc(wa, N * 16, 128);
+                                    const uint64_t b_lo = smem_desc(wa + w_plane, N * 16, 128);
+                                    tc_mma(d, a_hi, b_hi, idesc, !(first && kk == 0));
+                                    tc_mma(d, a_lo, b_hi, idesc, 1);
+                                    tc_mma(d, a_hi, b_lo, idesc, 1);
+                                }
                             }
                         }
                         tc_commit(w_empty + ws);
@@ -314,40 +346,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
         }
     } else {
         // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and
-        // every other 32-column chunk of the tile =====
+        // every other 16-column chunk of the tile =====
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int kW = 16;                    // columns per chunk
-        constexpr int kPerSub = C_OUT / kW;
+        constexpr int kPerSub = N / kW;
         constexpr int kChunks = S * kPerSub;      // (subtile, 16-channel) chunks per tile
         static_assert(kChunks % 2 == 0, "chunks are split between two warp sets");
         uint32_t tcount = 0;
-        const int groups_out = C_OUT / 8;
+        const int groups_out = a.c_out / 8;
+        const int t_out = a.valid ? a.t_len - span : a.t_len;   // output rows per item
+        const int out_row = a.out_row > 0 ? a.out_row : t_out;  // fp32 row length
         long long wait_cycles = 0, start_cycles = a.debug ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int nt = tile % n_tiles, rest = tile / n_tiles;
             const int b = rest / tiles_per_item;
-            const int t0 = (rest % tiles_per_item) * Cfg::kTile;
+            const int tb = rest % tiles_per_item;
+            const int t0 = tb * advance;
             const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
             ++tcount;
-            if constexpr (UP > 0) {
-                // ConvTranspose1d epilogue: column n = o * UP + q is output sample
-                // UP * i + q of channel o; a thread writes UP contiguous floats per o
+            // this thread's output row of subtile s, or -1
+            auto row_of = [&](int s) {
+                const int within = quad * 32 + lane;
+                if constexpr (MODE == kFrames) {
+                    const int frame = tb * kFramesPerTile + within / kFrameRows, t = within % kFrameRows;
+                    return (frame < a.frames && t < a.frame_valid) ? frame * a.frame_length + t : -1;
+                } else {
+                    const int t = t0 + s * 128 + within;
+                    return t < t_out ? t : -1;
+                }
+            };
+            auto load = [&](int s, int c0, uint32_t (&raw)[kW]) {
+                const uint32_t address =
+                    tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * Cfg::kCols) + s * Cfg::kCols + c0;
+                tc_load16(address, raw);
+                if constexpr (CONCAT) {
+                    uint32_t other[kW];
+                    tc_load16(address + N, other);
+#pragma unroll
+                    for (int i = 0; i < kW; ++i)
+                        raw[i] = __float_as_uint(__uint_as_float(raw[i]) + __uint_as_float(other[i]));
+                }
+            };
+            if constexpr (MODE == kTranspose) {
+                // column n = o * UP + q is output sample UP * i + q of channel o;
+                // a thread writes UP contiguous floats per o
                 mbar_wait(acc_full + as, aphase);
                 tc_fence_after();
-                const int t_out = UP * a.t_len;
+                const int t_up = UP * a.t_len;
 #pragma unroll 1
                 for (int chunk = half; chunk < kChunks; chunk += 2) {
                     const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
-                    const int i = t0 + s * 128 + quad * 32 + lane;
+                    const int i = row_of(s);
                     uint32_t raw[kW];
-                    tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
-                    if (i < a.t_len) {
-                        const int o0 = (nt * C_OUT + c0) / UP;
+                    load(s, c0, raw);
+                    if (i >= 0) {
+                        const int o0 = (nt * N + c0) / UP;
 #pragma unroll
                         for (int j = 0; j < kW / UP; ++j) {
                             const float bias = a.bias ? __ldg(a.bias + o0 + j) : 0.f;
-                            float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_out + (size_t)UP * i;
+                            float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_up + (size_t)UP * i;
                             if constexpr (UP % 4 == 0) {
 #pragma unroll
                                 for (int q = 0; q < UP; q += 4)
@@ -377,12 +435,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             float res[kW];
             auto fetch = [&](const float* source, int chunk, float (&r)[kW]) {
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
-                const int t = t0 + s * 128 + quad * 32 + lane;
-                const bool valid = source != nullptr && t < a.t_len;
-                const size_t idx = ((size_t)b * C_OUT + c0) * a.t_len + t;
+                const int t = row_of(s);
+                const bool valid = source != nullptr && t >= 0;
+                const size_t idx = ((size_t)b * a.c_out + nt * N + c0) * out_row + t;
 #pragma unroll
                 for (int i = 0; i < kW; ++i)
-                    r[i] = valid ? source[idx + (size_t)i * a.t_len] : 0.f;
+                    r[i] = valid ? source[idx + (size_t)i * out_row] : 0.f;
             };
             fetch(a.residual, half, res);
             const long long wait_start = a.debug ? clock64() : 0;
@@ -392,32 +450,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll 1
             for (int chunk = half; chunk < kChunks; chunk += 2) {
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
-                const int t = t0 + s * 128 + quad * 32 + lane;
-                const bool valid = t < a.t_len;
+                const int t = row_of(s);
                 float res_next[kW], acc[kW];
                 if (chunk + 2 < kChunks) fetch(a.residual, chunk + 2, res_next);
                 fetch(a.accum_mode == 2 ? a.accum : nullptr, chunk, acc);
                 uint32_t raw[kW];
-                tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * C_OUT) + s * C_OUT + c0, raw);
-                if (valid) {
+                load(s, c0, raw);
+                if (t >= 0) {
                     float v[kW];
-                    const size_t idx = ((size_t)b * C_OUT + c0) * a.t_len + t;
+                    const int c_first = nt * N + c0;
+                    const size_t idx = ((size_t)b * a.c_out + c_first) * out_row + t;
 #pragma unroll
                     for (int i = 0; i < kW; ++i) {
                         float y = __uint_as_float(raw[i]) + res[i];
-                        if (a.bias) y += __ldg(a.bias + c0 + i);
+                        if (a.bias) y += __ldg(a.bias + c_first + i);
+                        if (a.relu) y = fmaxf(y, 0.f);
                         v[i] = y;
                     }
                     if (a.out) {
 #pragma unroll
-                        for (int i = 0; i < kW; ++i) a.out[idx + (size_t)i * a.t_len] = v[i];
+                        for (int i = 0; i < kW; ++i) a.out[idx + (size_t)i * out_row] = v[i];
                     }
                     if (a.accum_mode) {
 #pragma unroll
                         for (int i = 0; i < kW; ++i)
-                            a.accum[idx + (size_t)i * a.t_len] = fmaf(v[i], a.accum_scale, acc[i]);
+                            a.accum[idx + (size_t)i * out_row] = fmaf(v[i], a.accum_scale, acc[i]);
                     }
                     if (a.out_planes) {
+                        const int out_pad = tc_padded_length_device(t_out);
 #pragma unroll
                         for (int g = 0; g < kW / 8; ++g) {
                             uint32_t hi[4], lo[4];
@@ -432,8 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                                                   __float2bfloat16_rn(y1 - __bfloat162float(h1)));
                             }
                             const size_t row_hi =
-                                ((size_t)(b * 2) * groups_out + (c0 / 8 + g)) * t_pad + kTcPad + t;
-                            const size_t row_lo = row_hi + (size_t)groups_out * t_pad;
+                                ((size_t)(b * 2) * groups_out + (c_first / 8 + g)) * out_pad + kTcPad + t;
+                            const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
                             *reinterpret_cast<uint4*>(a.out_planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                             *reinterpret_cast<uint4*>(a.out_planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
@@ -517,30 +577,35 @@ __global__ void __launch_bounds__(128) zero_plane_pads_kernel(
         rows[i < kTcPad ? i : t_len + i] = make_uint4(0, 0, 0, 0);
 }
 
-// (C_out, C_in, K) fp32 -> [tap][c_in / KB][plane][KB / 8][c_out][8] bf16
+// Conv1d weight (C_out, C_in, K) fp32, already folded, -> slabs
+//   [n tile][tap][c_in / KB] x  plain:  [plane][KB / 8][N][8]
+//                               concat: [KB / 8][hi rows N | lo rows N][8]
 __global__ void pack_tc_weight_kernel(
     const float* __restrict__ w, __nv_bfloat16* __restrict__ slabs,
-    int c_out, int c_in, int k, int kb_size) {
+    int c_out, int c_in, int k, int kb_size, int n_tile, int concat) {
     const size_t total = (size_t)c_out * c_in * k;
-    const int groups = kb_size / 8;
-    const int blocks = c_in / kb_size;
+    const int groups = kb_size / 8, blocks = c_in / kb_size;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         size_t rest = idx;
         const int e = rest % 8; rest /= 8;
-        const int o = rest % c_out; rest /= c_out;
+        const int col = rest % n_tile; rest /= n_tile;
         const int g = rest % groups; rest /= groups;
         const int kb = rest % blocks; rest /= blocks;
-        const int tap = (int)rest;
-        const int c = kb * kb_size + g * 8 + e;
+        const int tap = rest % k; rest /= k;
+        const int nt = (int)rest;
+        const int c = kb * kb_size + g * 8 + e, o = nt * n_tile + col;
         const float value = w[((size_t)o * c_in + c) * k + tap];
         const __nv_bfloat16 hi = __float2bfloat16_rn(value);
         const __nv_bfloat16 lo = __float2bfloat16_rn(value - __bfloat162float(hi));
-        const size_t slab = (size_t)(tap * blocks + kb) * 2;
-        const size_t inner = ((size_t)g * c_out + o) * 8 + e;
-        const size_t plane = (size_t)groups * c_out * 8;
-        slabs[slab * plane + inner] = hi;
-        slabs[(slab + 1) * plane + inner] = lo;
+        const size_t slab = ((size_t)(nt * k + tap) * blocks + kb) * (size_t)(2 * groups * n_tile * 8);
+        if (concat) {
+            slabs[slab + ((size_t)g * 2 * n_tile + col) * 8 + e] = hi;
+            slabs[slab + ((size_t)g * 2 * n_tile + n_tile + col) * 8 + e] = lo;
+        } else {
+            slabs[slab + ((size_t)g * n_tile + col) * 8 + e] = hi;
+            slabs[slab + (size_t)groups * n_tile * 8 + ((size_t)g * n_tile + col) * 8 + e] = lo;
+        }
     }
 }
 
@@ -593,10 +658,10 @@ int sm_count() {
     return count;
 }
 
-template <int C_IN, int C_OUT, int S, int KB, int NW, int AS, int UP = 0>
-int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
-    using Cfg = TcConfig<C_IN, C_OUT, S, KB, NW, AS>;
-    auto kernel = conv1d_tc_kernel<C_IN, C_OUT, S, KB, NW, AS, UP>;
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE = kConv, int UP = 0, bool CONCAT = false>
+int launch_variant(const TcConvArgs& a, int n_tiles, cudaStream_t stream) {
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT>;
+    auto kernel = conv1d_tc_kernel<C_IN, N, S, KB, NW, AS, MODE, UP, CONCAT>;
     static bool configured = false;
     if (!configured) {
         PMN_TRY(check_cuda(
@@ -604,13 +669,13 @@ int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
             "conv1d_tc smem attribute"));
         configured = true;
     }
-    const int tiles_per_item = ceil_div(a.t_len, Cfg::kTile);
-    const int n_tiles = UP > 0 ? UP * a.c_out / C_OUT : 1;
+    const int tiles_per_item =
+        MODE == kFrames ? ceil_div(a.frames, kFramesPerTile) : ceil_div(a.t_len, Cfg::kTile);
     const int num_tiles = tiles_per_item * a.batch * n_tiles;
     const int grid = min(num_tiles, sm_count());
     TcConvArgs args = a;
     if (!args.debug) args.debug = g_tc_debug;
-    const char* name = UP > 0 ? "conv_transpose1d_tc_kernel" : "conv1d_tc_kernel";
+    const char* name = MODE == kTranspose ? "conv_transpose1d_tc_kernel" : "conv1d_tc_kernel";
     LaunchScope scope(name, stream);
     kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(
         args, tc_padded_length(a.t_len), tiles_per_item, n_tiles, num_tiles);
@@ -621,23 +686,53 @@ int launch_variant(const TcConvArgs& a, cudaStream_t stream) {
 
 void tc_set_debug_counters(long long* counters) { g_tc_debug = counters; }
 
+// Tile plan of every supported (C_in, C_out): K block, N tile and operand form.
+// Must agree with the template arguments in launch_conv1d_tc.
+bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
+    struct Entry { int c_in, c_out; bool frames; TcPlan plan; };
+    static const Entry table[] = {
+        {256, 256, false, {32, 256, false}}, {128, 128, false, {64, 128, false}},
+        {64, 64, false, {64, 64, true}},     {32, 32, false, {32, 32, true}},
+        // penn FCNF0++ blocks 1..5 (valid convolutions, k = 32)
+        {256, 32, false, {64, 32, true}},    {32, 128, false, {32, 128, false}},
+        {128, 256, false, {32, 256, false}}, {256, 512, true, {32, 256, false}},
+    };
+    for (const Entry& entry : table) {
+        if (entry.c_in == c_in && entry.c_out == c_out && entry.frames == frames) {
+            if (plan) *plan = entry.plan;
+            return true;
+        }
+    }
+    return false;
+}
+
 bool tc_supported(int c_in, int c_out, int k, int dilation) {
-    if (c_in != c_out) return false;
-    if (c_in != 32 && c_in != 64 && c_in != 128 && c_in != 256) return false;
-    return k % 2 == 1 && (k - 1) / 2 * dilation <= kMaxHalo;
+    return tc_conv_plan(c_in, c_out, false, nullptr) && k >= 1 && k <= 32 &&
+           (k - 1) * dilation <= 2 * kMaxHalo;
 }
 
 int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     PMN_REQUIRE(a.x_planes && a.w_slabs, "conv1d_tc: null input");
     PMN_REQUIRE(a.out || a.out_planes || (a.accum && a.accum_mode), "conv1d_tc: no output");
     PMN_REQUIRE(a.batch > 0 && a.t_len > 0, "conv1d_tc: empty input");
-    PMN_REQUIRE(tc_supported(a.c_in, a.c_out, a.k, a.dilation), "conv1d_tc: unsupported shape");
-    switch (a.c_in) {
-        case 256: return launch_variant<256, 256, 1, 32, 3, 2>(a, stream);
-        case 128: return launch_variant<128, 128, 2, 64, 2, 2>(a, stream);
-        case 64: return launch_variant<64, 64, 2, 64, 4, 2>(a, stream);
-        default: return launch_variant<32, 32, 4, 32, 4, 2>(a, stream);
+    PMN_REQUIRE(a.k >= 1 && a.k <= 32 && (a.k - 1) * a.dilation <= 2 * kMaxHalo,
+                "conv1d_tc: receptive field too wide");
+    PMN_REQUIRE(a.valid || a.k % 2 == 1, "conv1d_tc: same padding needs an odd kernel");
+    const bool frames = a.frame_length > 0;
+    PMN_REQUIRE(tc_conv_plan(a.c_in, a.c_out, frames, nullptr), "conv1d_tc: unsupported channel counts");
+    if (frames) {
+        PMN_REQUIRE(a.valid && a.frames > 0 && a.frame_length <= kMaxFrameLength &&
+                        a.frame_valid > 0 && a.frame_valid <= kFrameRows && a.batch == 1,
+                    "conv1d_tc: bad frame-mode arguments");
+        return launch_variant<256, 256, 1, 32, 2, 2, kFrames>(a, 2, stream);
     }
+    if (a.c_in == 256 && a.c_out == 256) return launch_variant<256, 256, 1, 32, 3, 2>(a, 1, stream);
+    if (a.c_in == 128 && a.c_out == 128) return launch_variant<128, 128, 2, 64, 2, 2>(a, 1, stream);
+    if (a.c_in == 64 && a.c_out == 64) return launch_variant<64, 64, 2, 64, 4, 2, kConv, 0, true>(a, 1, stream);
+    if (a.c_in == 32 && a.c_out == 32) return launch_variant<32, 32, 4, 32, 8, 2, kConv, 0, true>(a, 1, stream);
+    if (a.c_in == 256 && a.c_out == 32) return launch_variant<256, 32, 2, 64, 8, 2, kConv, 0, true>(a, 1, stream);
+    if (a.c_in == 32 && a.c_out == 128) return launch_variant<32, 128, 2, 32, 4, 2>(a, 1, stream);
+    return launch_variant<128, 256, 1, 32, 4, 2>(a, 1, stream);
 }
 
 namespace {
@@ -662,12 +757,14 @@ int launch_conv_transpose1d_tc(const TcConvArgs& args, int stride, cudaStream_t 
     TcConvArgs a = args;
     a.k = 3;
     a.dilation = 1;
+    a.valid = false;
     a.residual = nullptr; a.accum = nullptr; a.accum_mode = 0; a.out_planes = nullptr;
+    const int n_tiles = stride * a.c_out / transpose_n_tile(a.c_in);
     switch (a.c_in) {
-        case 512: return launch_variant<512, 256, 1, 32, 4, 2, 8>(a, stream);
-        case 256: return launch_variant<256, 256, 1, 32, 4, 2, 8>(a, stream);
-        case 128: return launch_variant<128, 128, 2, 64, 2, 2, 2>(a, stream);
-        default: return launch_variant<64, 64, 2, 64, 4, 2, 2>(a, stream);
+        case 512: return launch_variant<512, 256, 1, 32, 4, 2, kTranspose, 8>(a, n_tiles, stream);
+        case 256: return launch_variant<256, 256, 1, 32, 4, 2, kTranspose, 8>(a, n_tiles, stream);
+        case 128: return launch_variant<128, 128, 2, 64, 2, 2, kTranspose, 2>(a, n_tiles, stream);
+        default: return launch_variant<64, 64, 2, 64, 4, 2, kTranspose, 2>(a, n_tiles, stream);
     }
 }
 
@@ -713,12 +810,14 @@ int launch_zero_plane_pads(
 }
 
 int launch_pack_tc_weight(
-    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, cudaStream_t stream) {
-    PMN_REQUIRE(w && slabs && c_in % tc_k_block(c_in) == 0, "pack_tc_weight: bad argument");
+    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, bool frames, cudaStream_t stream) {
+    TcPlan plan;
+    PMN_REQUIRE(w && slabs && tc_conv_plan(c_in, c_out, frames, &plan), "pack_tc_weight: bad argument");
     const size_t total = (size_t)c_out * c_in * k;
     const int blocks = (int)min((size_t)2048, (total + 255) / 256);
     LaunchScope scope("pack_tc_weight_kernel", stream);
-    pack_tc_weight_kernel<<<blocks, 256, 0, stream>>>(w, slabs, c_out, c_in, k, tc_k_block(c_in));
+    pack_tc_weight_kernel<<<blocks, 256, 0, stream>>>(
+        w, slabs, c_out, c_in, k, plan.k_block, plan.n_tile, plan.concat ? 1 : 0);
     return launched("pack_tc_weight_kernel");
 }
 

@@ -19,11 +19,19 @@ constexpr int kTcTimeAlign = 512;
 inline int tc_padded_length(int t_len) {
     return kTcPad + (t_len + kTcTimeAlign - 1) / kTcTimeAlign * kTcTimeAlign + kTcPad;
 }
+__device__ __forceinline__ int tc_padded_length_device(int t_len) {
+    return kTcPad + (t_len + kTcTimeAlign - 1) / kTcTimeAlign * kTcTimeAlign + kTcPad;
+}
 inline size_t tc_planes_elements(int batch, int channels, int t_len) {
     return (size_t)batch * 2 * channels * tc_padded_length(t_len);
 }
-// Weight slabs: [tap][c_in / KB][plane][KB / 8][c_out][8] bf16, KB = tc_k_block(c_in)
-inline int tc_k_block(int c_in) { return c_in >= 256 ? 32 : (c_in >= 64 ? 64 : 32); }
+// Weight slabs (bf16 hi + lo = the bytes of the fp32 tensor): see pack_tc_weight_kernel
+struct TcPlan {
+    int k_block;   // input channels per shared-memory slab
+    int n_tile;    // output channels per tile
+    bool concat;   // hi and lo rows interleaved per K group (one wide MMA for a_hi)
+};
+bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan);
 inline size_t tc_weight_elements(int c_out, int c_in, int k) { return (size_t)2 * c_out * c_in * k; }
 bool tc_supported(int c_in, int c_out, int k, int dilation);
 
@@ -38,7 +46,13 @@ struct TcConvArgs {
     int accum_mode = 0;                       // 0 unused, 1 store, 2 add
     float accum_scale = 1.f;
     int batch = 0, c_in = 0, c_out = 0, t_len = 0;
-    int k = 1, dilation = 1;                  // "same" padding (k - 1) / 2 * dilation
+    int k = 1, dilation = 1;
+    bool valid = false;                       // false: "same" padding (odd k); true: no padding
+    bool relu = false;                        // max(y, 0) before any store
+    int out_row = 0;                          // fp32 row length of out / residual / accum (0 = output length)
+    // Frame mode (valid conv over frames laid end to end, a few output rows per
+    // frame): frames of frame_length rows each, the first frame_valid outputs kept
+    int frames = 0, frame_length = 0, frame_valid = 0;
     float out_slope = 1.f;
     // Optional (gridDim.x, 10 warps, 4) cycle counters: [0] total, [1..3] barrier waits
     long long* debug = nullptr;
@@ -72,6 +86,6 @@ int launch_zero_plane_pads(
 
 // folded fp32 weight (C_out, C_in, K) -> hi/lo slabs
 int launch_pack_tc_weight(
-    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, cudaStream_t stream);
+    const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, bool frames, cudaStream_t stream);
 
 }  // namespace pmn

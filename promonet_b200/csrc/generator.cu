@@ -125,7 +125,7 @@ int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int 
         float* slabs;  // two bf16 planes = the bytes of one fp32 tensor
         PMN_TRY(alloc(g, shape->numel(), &slabs));
         conv->slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
-        return launch_pack_tc_weight(w, conv->slabs, channels, channels, k, stream);
+        return launch_pack_tc_weight(w, conv->slabs, channels, channels, k, false, stream);
     }
     PMN_TRY(alloc(g, shape->numel(), &conv->weight));
     return launch_pack_conv1d_weight(w, conv->weight, channels, channels, k, stream);

@@ -20,6 +20,7 @@
 #include <numeric>
 #include <vector>
 
+#include "conv1d_tc.cuh"
 #include "pitch.cuh"
 #include "spectral.cuh"
 
@@ -58,6 +59,8 @@ struct pmn_pitch {
     std::map<std::string, pmn::Tensor> tensors;
     std::vector<float*> owned;
     bool finalized = false;
+    int math = PMN_MATH_FP32_SIMT;
+    __nv_bfloat16* conv_slabs[pmn::kLayers] = {};  // tensor-core path, layers 1..5
     float* conv_weight[pmn::kLayers] = {};   // packed (C_in, 32, C_out)
     const float* conv_bias[pmn::kLayers] = {};
     const float* norm_weight[pmn::kLayers] = {};
@@ -168,6 +171,80 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(
             const int c = idx / l_out, t = idx % l_out;
             out[(size_t)c * count * l_out + (size_t)f * l_out + t] = v;
         }
+    }
+}
+
+// Same normalisation, written as the bf16 hi/lo planes the next tensor-core conv
+// reads (conv1d_tc.cuh): planes[plane][c / 8][kTcPad + f * l_out + t][c % 8].
+// Frames f >= count (padding up to a multiple of 16 frames) are written as zeros.
+__global__ void __launch_bounds__(256) pool_norm_planes_kernel(
+    const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
+    __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
+    int count, int t_pad) {
+    __shared__ double partial[2][8];
+    __shared__ float stats[2];
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int groups = channels / 8;
+    uint4* hi_plane = reinterpret_cast<uint4*>(planes);
+    uint4* lo_plane = hi_plane + (size_t)groups * t_pad;
+    if (f >= count) {
+        for (int idx = tid; idx < groups * l_out; idx += blockDim.x) {
+            const size_t row = (size_t)(idx / l_out) * t_pad + kTcPad + (size_t)f * l_out + idx % l_out;
+            hi_plane[row] = make_uint4(0, 0, 0, 0);
+            lo_plane[row] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+    const int total = channels * l_out;
+    const float* base = in + (size_t)f * l_in;
+    auto value = [&](int c, int t) {
+        const float* row = base + (size_t)c * in_row;
+        return pooled ? fmaxf(row[2 * t], row[2 * t + 1]) : row[t];
+    };
+    float sum = 0.f, squares = 0.f;
+    for (int idx = tid; idx < total; idx += blockDim.x) {
+        const float v = value(idx / l_out, idx % l_out);
+        sum += v;
+        squares = fmaf(v, v, squares);
+    }
+    double dsum = sum, dsquares = squares;
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, offset);
+        dsquares += __shfl_xor_sync(0xffffffffu, dsquares, offset);
+    }
+    if ((tid & 31) == 0) { partial[0][tid >> 5] = dsum; partial[1][tid >> 5] = dsquares; }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0., q = 0.;
+        for (int w = 0; w < 8; ++w) { s += partial[0][w]; q += partial[1][w]; }
+        const double mean = s / total;
+        const double variance = fmax(q / total - mean * mean, 0.);
+        stats[0] = (float)mean;
+        stats[1] = (float)(1. / sqrt(variance + 1e-5));
+    }
+    __syncthreads();
+    const float mean = stats[0], rstd = stats[1];
+    for (int idx = tid; idx < groups * l_out; idx += blockDim.x) {
+        const int g = idx / l_out, t = idx % l_out;
+        unsigned int hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float y[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = g * 8 + 2 * e + h;
+                y[h] = (value(c, t) - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
+            }
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
+            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+        }
+        const size_t row = (size_t)g * t_pad + kTcPad + (size_t)f * l_out + t;
+        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -319,6 +396,7 @@ int resampler(pmn_pitch* p, int sample_rate, const pmn_pitch::Resampler** out) {
 
 struct Workspace {
     float *resampled, *conv, *act, *logits_t, *masked, *distribution;
+    __nv_bfloat16* planes;
     int* bins;
     void* viterbi;
     size_t viterbi_bytes, bytes;
@@ -337,6 +415,8 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     w.resampled = (float*)take((size_t)batch * out_samples * 4);
     w.conv = (float*)take(fb * 256 * kCropped * 4);                 // largest conv output (layer 0)
     w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
+    // tensor-core operand planes: the widest is block 0's output (256 channels x 481 rows per frame)
+    w.planes = (__nv_bfloat16*)take(tc_planes_elements(1, 256, (int)(fb + 16) * 481) * 2);
     w.logits_t = (float*)take(fb * kBins * 4);
     w.masked = (float*)take(total * kBins * 4);
     w.distribution = (float*)take(total * kBins * 4);
@@ -371,8 +451,11 @@ int pitch_set_tensor(pmn_pitch* p, const char* name, const float* data, const in
     return PMN_OK;
 }
 
-int pitch_finalize(pmn_pitch* p, cudaStream_t stream) {
+int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
     if (p->finalized) return fail(PMN_ERR_STATE, "pitch model already finalized");
+    if (math != PMN_MATH_FP32_SIMT && math != PMN_MATH_BF16X3_TC)
+        return fail(PMN_ERR_ARGUMENT, "pitch: unsupported math mode");
+    p->math = math;
     for (int i = 0; i < kLayers; ++i) {
         const std::string prefix = "layers." + std::to_string(i);
         const Tensor *w, *b, *nw, *nb;
@@ -383,9 +466,18 @@ int pitch_finalize(pmn_pitch* p, cudaStream_t stream) {
         if (w->numel() != (size_t)kChannels[i + 1] * kChannels[i] * kKernel ||
             nw->numel() != (size_t)kChannels[i + 1] * kLength[i + 1] || nb->numel() != nw->numel())
             return fail(PMN_ERR_STATE, "unexpected shapes at " + prefix);
-        PMN_TRY(alloc(p, w->numel(), &p->conv_weight[i]));
-        PMN_TRY(launch_pack_conv1d_weight(
-            w->data, p->conv_weight[i], kChannels[i + 1], kChannels[i], kKernel, stream));
+        if (math == PMN_MATH_BF16X3_TC && i > 0) {
+            float* slabs;  // bf16 hi + lo = the bytes of the fp32 tensor
+            PMN_TRY(alloc(p, w->numel(), &slabs));
+            p->conv_slabs[i] = reinterpret_cast<__nv_bfloat16*>(slabs);
+            PMN_TRY(launch_pack_tc_weight(
+                w->data, p->conv_slabs[i], kChannels[i + 1], kChannels[i], kKernel,
+                i == kLayers - 1, stream));
+        } else {
+            PMN_TRY(alloc(p, w->numel(), &p->conv_weight[i]));
+            PMN_TRY(launch_pack_conv1d_weight(
+                w->data, p->conv_weight[i], kChannels[i + 1], kChannels[i], kKernel, stream));
+        }
         p->conv_bias[i] = b->data;
         p->norm_weight[i] = nw->data;
         p->norm_bias[i] = nb->data;
@@ -465,19 +557,48 @@ int pitch_forward(
                 audio8k, w.act, out_samples, frames, first, count, hop, padding);
             PMN_TRY(launched("frames_kernel"));
         }
+        const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
+        const int padded = (count + 15) / 16 * 16;  // frame-mode tiles cover 16 frames
         for (int i = 0; i < kLayers; ++i) {
             const int l_in = kLength[i];
             const size_t row = (size_t)count * l_in - (kKernel - 1);
-            Conv1dArgs a;
-            a.x = w.act; a.weight = p->conv_weight[i]; a.bias = p->conv_bias[i]; a.out = w.conv;
-            a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
-            a.t_in = count * l_in; a.t_out = (int)row; a.k = kKernel; a.out_act = 2;
-            PMN_TRY(launch_conv1d(a, stream));
-            LaunchScope scope("pool_norm_kernel", stream);
-            pool_norm_kernel<<<count, 256, 0, stream>>>(
-                w.conv, p->norm_weight[i], p->norm_bias[i], w.act, kChannels[i + 1], l_in,
-                kLength[i + 1], kPooled[i], row, count, i == kLayers - 1);
-            PMN_TRY(launched("pool_norm_kernel"));
+            if (tensor_cores && i > 0) {
+                TcConvArgs a;
+                a.x_planes = w.planes; a.w_slabs = p->conv_slabs[i]; a.bias = p->conv_bias[i];
+                a.out = w.conv; a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
+                a.k = kKernel; a.valid = true; a.relu = true; a.out_row = (int)row;
+                a.t_len = count * l_in;
+                if (i == kLayers - 1) {
+                    // block 5 keeps 4 of 35 rows per frame: 16 frames x 8 rows per MMA tile
+                    a.t_len = padded * l_in;
+                    a.frames = count; a.frame_length = l_in; a.frame_valid = kLength[i + 1];
+                }
+                PMN_TRY(launch_conv1d_tc(a, stream));
+            } else {
+                Conv1dArgs a;
+                a.x = w.act; a.weight = p->conv_weight[i]; a.bias = p->conv_bias[i]; a.out = w.conv;
+                a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
+                a.t_in = count * l_in; a.t_out = (int)row; a.k = kKernel; a.out_act = 2;
+                PMN_TRY(launch_conv1d(a, stream));
+            }
+            if (tensor_cores && i < kLayers - 1) {
+                // the next block runs on the tensor cores: write its operand planes
+                const int l_out = kLength[i + 1];
+                const int frames_out = i + 1 == kLayers - 1 ? padded : count;
+                const int t_next = frames_out * l_out;
+                PMN_TRY(launch_zero_plane_pads(w.planes, 1, kChannels[i + 1], t_next, stream));
+                LaunchScope scope("pool_norm_planes_kernel", stream);
+                pool_norm_planes_kernel<<<frames_out, 256, 0, stream>>>(
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_in,
+                    l_out, kPooled[i], row, count, tc_padded_length(t_next));
+                PMN_TRY(launched("pool_norm_planes_kernel"));
+            } else {
+                LaunchScope scope("pool_norm_kernel", stream);
+                pool_norm_kernel<<<count, 256, 0, stream>>>(
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.act, kChannels[i + 1], l_in,
+                    kLength[i + 1], kPooled[i], row, count, i == kLayers - 1);
+                PMN_TRY(launched("pool_norm_kernel"));
+            }
         }
         {
             Conv1dArgs a;

@@ -11,7 +11,7 @@ pmn_pitch* pitch_create();
 void pitch_destroy(pmn_pitch* p);
 int pitch_set_tensor(pmn_pitch* p, const char* name, const float* data, const int64_t* shape,
                      int ndim, cudaStream_t stream);
-int pitch_finalize(pmn_pitch* p, cudaStream_t stream);
+int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream);
 int pitch_frames(int samples, int sample_rate, double hopsize_seconds);
 size_t pitch_workspace_bytes(int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch);
 int pitch_forward(

@@ -61,7 +61,8 @@ def initial_distribution():
 class Model:
     """Owns a libpromonet_b200 pitch-network handle"""
 
-    def __init__(self, device=None, state=None):
+    def __init__(self, device=None, state=None, math=_lib.MATH_BF16X3_TC):
+        self.math = math
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200 requires a CUDA device; there is no CPU path')
         self.device = torch.device(
@@ -91,7 +92,7 @@ class Model:
                 shape = (ctypes.c_int64 * max(1, value.ndim))(*value.shape)
                 _lib.check(lib.pmn_pitch_set_tensor(
                     handle, name.encode(), value.data_ptr(), shape, value.ndim, _lib.stream()))
-            _lib.check(lib.pmn_pitch_finalize(handle, _lib.stream()))
+            _lib.check(lib.pmn_pitch_finalize(handle, self.math, _lib.stream()))
             torch.cuda.current_stream().synchronize()
         return self
 

@@ -124,3 +124,26 @@ def test_conv_transpose1d_tc_matches_fp64(c_in, k, s, t, batch):
         batch, c_in, c_out, t, k, s, 0.1, workspace.data_ptr(), size, _lib.stream()))
     error = relative_error(out, expected)
     assert error < 1e-4, error
+
+
+@pytest.mark.parametrize('c_in,c_out,k,t_len,batch', [
+    (256, 32, 32, 481 * 3, 1), (32, 32, 32, 225 * 5, 1), (32, 128, 32, 97 * 7, 2),
+    (128, 256, 32, 66 * 9, 1), (256, 32, 5, 300, 2), (32, 128, 1, 130, 1)])
+def test_conv1d_tc_valid_relu_rectangular(c_in, c_out, k, t_len, batch):
+    """penn FCNF0++ block shapes: valid convolution + ReLU, C_in != C_out"""
+    from promonet_b200 import _lib
+    lib = _lib.library()
+    torch.manual_seed(c_in + c_out + k)
+    x = torch.randn(batch, c_in, t_len)
+    w = torch.randn(c_out, c_in, k) / (c_in * k) ** .5
+    bias = torch.randn(c_out)
+    expected = torch.relu(torch.nn.functional.conv1d(x.double(), w.double(), bias.double()))
+    xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+    out = torch.empty(batch, c_out, t_len - k + 1, device='cuda')
+    size = lib.pmn_conv1d_tc_workspace_bytes(batch, c_in, t_len, k)
+    workspace = torch.empty(size, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.pmn_conv1d_tc_general(
+        xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, out.data_ptr(), None, None, 0, 1.,
+        batch, c_in, c_out, t_len, k, 1, 1, 1, 1., 1., workspace.data_ptr(), size, _lib.stream()))
+    error = relative_error(out, expected)
+    assert error < 1e-4, error

@@ -160,9 +160,11 @@ def pitch_state(pb):
     return pb.preprocess.penn.init_state(1234)
 
 
-@pytest.fixture(scope='module')
-def pitch_model(pb, pitch_state):
-    return pb.preprocess.penn.Model(state=pitch_state)
+@pytest.fixture(scope='module', params=['fp32', 'bf16x3'])
+def pitch_model(pb, pitch_state, request):
+    """fp32 FMA convolutions, or blocks 1-5 on the tensor cores: same parity bar"""
+    math = pb._lib.MATH_FP32_SIMT if request.param == 'fp32' else pb._lib.MATH_BF16X3_TC
+    return pb.preprocess.penn.Model(state=pitch_state, math=math)
 
 
 def test_seeded_pitch_state_equals_oracle_state(pitch_state):
@@ -170,7 +172,7 @@ def test_seeded_pitch_state_equals_oracle_state(pitch_state):
     assert all(torch.equal(pitch_state[k], other[k]) for k in other)
 
 
-@pytest.mark.parametrize('batch,samples,frame_batch', [(1, 22050, 2048), (2, 33000, 64), (1, 3000, 7)])
+@pytest.mark.parametrize('batch,samples,frame_batch', [(1, 22050, 2048), (2, 33000, 64), (1, 3000, 7), (1, 44100, 50)])
 def test_pitch_pipeline_stages_match_oracle(pitch_model, pitch_state, batch, samples, frame_batch):
     audio = inputs.audio(batch, samples, seed=samples)
     pitch, periodicity, logits, bins = pitch_model(
