@@ -171,7 +171,7 @@ struct TcConfig {
     static constexpr int kWSlab = KB * N * 4;                   // bytes, both planes
     static constexpr int kXStages = 2;
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
-    static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128;
+    static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 2048;
     static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
     static constexpr int kColumns = AS * S * kCols;
     static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     uint64_t* acc_full = w_empty + NW;
     uint64_t* acc_empty = acc_full + AS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + AS);
+    float* bias_smem = reinterpret_cast<float*>(tmem_slot + 4);  // c_out (<= 512) floats
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -214,6 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
         for (int i = 0; i < AS; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < 512; i += kThreads)
+        bias_smem[i] = (a.bias && i < (MODE == kTranspose ? a.c_out : a.c_out)) ? a.bias[i] : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kAlloc) : "memory");
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         const int o0 = (nt * N + c0) / UP;
 #pragma unroll
                         for (int j = 0; j < kW / UP; ++j) {
-                            const float bias = a.bias ? __ldg(a.bias + o0 + j) : 0.f;
+                            const float bias = bias_smem[o0 + j];
                             float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_up + (size_t)UP * i;
                             if constexpr (UP % 4 == 0) {
 #pragma unroll
@@ -432,7 +435,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             // Side inputs do not depend on the accumulators: fetch the first chunk's
             // before waiting, and chunk i + 1's while chunk i is processed, so the
             // DRAM latency is paid once per chunk batch instead of once per element
-            float res[kW];
+            constexpr int kMine = kChunks / 2;                 // chunks of this warp set per tile
+            constexpr int kDepth = kMine < 4 ? kMine : 4;      // residual chunks in flight
+            float res[kDepth][kW];
             auto fetch = [&](const float* source, int chunk, float (&r)[kW]) {
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = row_of(s);
@@ -442,28 +447,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 for (int i = 0; i < kW; ++i)
                     r[i] = valid ? source[idx + (size_t)i * out_row] : 0.f;
             };
-            fetch(a.residual, half, res);
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) fetch(a.residual, half + 2 * d, res[d]);
             const long long wait_start = a.debug ? clock64() : 0;
             mbar_wait(acc_full + as, aphase);
             if (a.debug) wait_cycles += clock64() - wait_start;
             tc_fence_after();
-#pragma unroll 1
-            for (int chunk = half; chunk < kChunks; chunk += 2) {
+#pragma unroll
+            for (int mine = 0; mine < kMine; ++mine) {
+                const int chunk = half + 2 * mine;
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = row_of(s);
-                float res_next[kW], acc[kW];
-                if (chunk + 2 < kChunks) fetch(a.residual, chunk + 2, res_next);
+                float acc[kW];
                 fetch(a.accum_mode == 2 ? a.accum : nullptr, chunk, acc);
                 uint32_t raw[kW];
                 load(s, c0, raw);
+                float (&r)[kW] = res[mine % kDepth];
                 if (t >= 0) {
                     float v[kW];
                     const int c_first = nt * N + c0;
                     const size_t idx = ((size_t)b * a.c_out + c_first) * out_row + t;
 #pragma unroll
                     for (int i = 0; i < kW; ++i) {
-                        float y = __uint_as_float(raw[i]) + res[i];
-                        if (a.bias) y += __ldg(a.bias + c_first + i);
+                        float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
                         if (a.relu) y = fmaxf(y, 0.f);
                         v[i] = y;
                     }
@@ -499,10 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         }
                     }
                 }
-                if (chunk + 2 < kChunks) {
-#pragma unroll
-                    for (int i = 0; i < kW; ++i) res[i] = res_next[i];
-                }
+                if (mine + kDepth < kMine) fetch(a.residual, half + 2 * (mine + kDepth), r);
             }
             tc_fence_before();
             __syncwarp();

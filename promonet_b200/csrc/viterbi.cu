@@ -15,6 +15,8 @@
 // are bit-exact against the CPU recurrence on the same log inputs.
 #include <math.h>
 
+#include <cooperative_groups.h>
+
 #include "spectral.cuh"
 
 namespace pmn {
@@ -22,6 +24,22 @@ namespace pmn {
 namespace {
 
 constexpr int kThreads = 1024;
+
+// Banded fast path (viterbi_cluster_kernel below)
+constexpr int kClusterSize = 8;
+constexpr int kSplit = 4;                       // threads per state
+constexpr int kClusterThreads = 768;
+constexpr int kClusterSmem = 200 * 1024;
+
+__host__ __device__ inline int cluster_slice(int states) {
+    return (states + kClusterSize - 1) / kClusterSize;
+}
+// floats of shared memory the fast path needs for a given band width
+__host__ __device__ inline size_t cluster_floats(int states, int max_width) {
+    const int slice = cluster_slice(states);
+    return (size_t)max_width * (slice | 1) + 2 * (size_t)slice + (size_t)kClusterSize * slice;
+}
+
 
 // Per column j: first and one-past-last row with a finite log-probability
 __global__ void band_range_kernel(
@@ -60,7 +78,12 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(
     const float* __restrict__ observation, const int* __restrict__ batch_frames,
     const float* __restrict__ initial, bool log_probs,
     const float* __restrict__ band, const int* __restrict__ lo, const int* __restrict__ width,
+    const int* __restrict__ max_width_ptr,
     short* __restrict__ psi, int* __restrict__ indices, int frames, int states) {
+    if (max_width_ptr != nullptr &&
+        cluster_floats(states, *max_width_ptr) * sizeof(float) <= (size_t)kClusterSmem &&
+        kSplit * cluster_slice(states) <= kClusterThreads)
+        return;  // the banded cluster kernel decoded this batch
     extern __shared__ float delta[];  // [2][states]
     __shared__ float best_value[32];
     __shared__ int best_index[32];
@@ -113,7 +136,6 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(
         const float value = final_scores[j];
         if (value > best) { best = value; arg = j; }
     }
-    if (arg == 0x7fffffff) arg = tid < states ? tid : 0x7fffffff;  // all -inf: candidates by index
     for (int offset = 16; offset > 0; offset >>= 1) {
         const float other = __shfl_xor_sync(0xffffffffu, best, offset);
         const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
@@ -136,6 +158,135 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(
         }
         for (int t = length; t < frames; ++t) path[t] = 0;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Banded fast path: one cluster of 8 CTAs per utterance.
+//
+// Each CTA owns a contiguous slice of the next-states and keeps the band of the
+// log-transition matrix for its columns resident in shared memory for the whole
+// utterance (181 x 180 floats for penn's pitch transition), so the per-frame
+// work is shared-memory only: every state is scanned by 4 threads (a quarter of
+// the band each, combined with two shuffles, lowest index winning ties), the new
+// scores are published in the CTA's own shared memory, and after one cluster
+// barrier every CTA gathers the full score vector from its peers through
+// distributed shared memory.  Exits immediately when the band does not fit
+// (dense transition matrices): viterbi_kernel then does the work.
+// ---------------------------------------------------------------------------
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClusterThreads, 1)
+viterbi_cluster_kernel(
+    const float* __restrict__ observation, const int* __restrict__ batch_frames,
+    const float* __restrict__ initial, bool log_probs,
+    const float* __restrict__ band, const int* __restrict__ lo, const int* __restrict__ width,
+    const int* __restrict__ max_width_ptr,
+    short* __restrict__ psi, int* __restrict__ indices, int frames, int states) {
+    namespace cg = cooperative_groups;
+    const int max_width = *max_width_ptr;
+    const int slice = cluster_slice(states);
+    if (cluster_floats(states, max_width) * sizeof(float) > (size_t)kClusterSmem ||
+        kSplit * slice > kClusterThreads)
+        return;  // uniform across the grid: the general kernel handles it
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / kClusterSize;
+    const int tid = threadIdx.x;
+    const int pitch = slice | 1;                 // odd row pitch: conflict-free column reads
+
+    extern __shared__ float smem[];
+    float* band_s = smem;                        // [max_width][pitch]
+    float* mine = band_s + (size_t)max_width * pitch;  // [2][slice] scores of my states
+    float* full = mine + 2 * slice;              // [kClusterSize * slice] gathered scores
+
+    const int j0 = rank * slice;
+    const int length = batch_frames ? min(batch_frames[b], frames) : frames;
+    const float* obs = observation + (size_t)b * frames * states;
+    short* back = psi + (size_t)b * frames * states;
+    int* path = indices + (size_t)b * frames;
+
+    for (int idx = tid; idx < max_width * slice; idx += kClusterThreads) {
+        const int k = idx / slice, jl = idx % slice;
+        band_s[k * pitch + jl] = j0 + jl < states ? band[(size_t)k * states + j0 + jl] : -INFINITY;
+    }
+    const int jl = tid / kSplit, part = tid % kSplit;
+    const int j = j0 + jl;
+    const bool owner = jl < slice && j < states;
+    int first = 0, count = 0;
+    if (owner) { first = lo[j]; count = width[j]; }
+    const int chunk = (count + kSplit - 1) / kSplit;
+    const int begin = min(part * chunk, count), end = min(begin + chunk, count);
+
+    if (owner && part == 0) {
+        const float o = log_probs ? obs[j] : logf(obs[j]);
+        const float p = log_probs ? initial[j] : logf(initial[j]);
+        mine[jl] = p + o;
+    } else if (jl < slice && part == 0) {
+        mine[jl] = -INFINITY;
+    }
+    cluster.sync();
+
+    int current = 0;
+    for (int t = 1; t < max(length, 1); ++t) {
+        // gather the previous scores of every CTA of the cluster
+        for (int idx = tid; idx < kClusterSize * slice; idx += kClusterThreads) {
+            const int peer = idx / slice;
+            const float* remote = cluster.map_shared_rank(mine + current * slice, peer);
+            full[idx] = remote[idx % slice];
+        }
+        __syncthreads();
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
+        if (owner) {
+            const float* column = band_s + jl;
+            const float* source = full + first;
+            for (int k = begin; k < end; ++k) {
+                const float value = source[k] + column[k * pitch];
+                if (value > best) { best = value; arg = first + k; }
+            }
+        }
+        // combine the kSplit parts of a state (adjacent lanes), lowest index on ties
+#pragma unroll
+        for (int offset = 1; offset < kSplit; offset <<= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, best, offset);
+            const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
+            if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
+        }
+        if (owner && part == 0) {
+            const float o = log_probs ? obs[(size_t)t * states + j] : logf(obs[(size_t)t * states + j]);
+            mine[(current ^ 1) * slice + jl] = best + o;
+            back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
+        }
+        current ^= 1;
+        cluster.sync();  // new scores visible cluster-wide; everyone is done reading the old ones
+    }
+
+    // final argmax and backtrace on the first CTA of the cluster
+    __threadfence();
+    cluster.sync();
+    if (rank == 0) {
+        for (int idx = tid; idx < kClusterSize * slice; idx += kClusterThreads) {
+            const int peer = idx / slice;
+            const float* remote = cluster.map_shared_rank(mine + current * slice, peer);
+            full[idx] = (peer * slice + idx % slice) < states ? remote[idx % slice] : -INFINITY;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int state = 0;
+            float best = -INFINITY;
+            if (length > 0) {
+                for (int k = 0; k < kClusterSize * slice; ++k) {
+                    const int global = (k / slice) * slice + k % slice;  // = k: slices are contiguous
+                    if (global < states && full[k] > best) { best = full[k]; state = global; }
+                }
+            }
+            for (int t = length - 1; t >= 0; --t) {
+                path[t] = state;
+                if (t > 0) state = back[(size_t)t * states + state];
+            }
+            for (int t = max(length, 0); t < frames; ++t) path[t] = 0;
+        }
+    }
+    cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 struct Workspace {
@@ -200,10 +351,26 @@ int launch_viterbi(
             "viterbi smem attribute"));
         configured = true;
     }
+    static bool cluster_configured = false;
+    if (!cluster_configured) {
+        PMN_TRY(check_cuda(
+            cudaFuncSetAttribute(
+                viterbi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClusterSmem),
+            "viterbi cluster smem attribute"));
+        cluster_configured = true;
+    }
+    {
+        // banded fast path (returns at once if the band does not fit in shared memory)
+        LaunchScope scope("viterbi_cluster_kernel", stream);
+        viterbi_cluster_kernel<<<batch * kClusterSize, kClusterThreads, kClusterSmem, stream>>>(
+            observation, batch_frames, initial, log_probs, w.band, w.lo, w.width, w.max_width,
+            w.psi, indices, frames, states);
+        PMN_TRY(launched("viterbi_cluster_kernel"));
+    }
     LaunchScope scope("viterbi_kernel", stream);
     viterbi_kernel<<<batch, kThreads, smem, stream>>>(
-        observation, batch_frames, initial, log_probs, w.band, w.lo, w.width, w.psi, indices,
-        frames, states);
+        observation, batch_frames, initial, log_probs, w.band, w.lo, w.width, w.max_width, w.psi,
+        indices, frames, states);
     return launched("viterbi_kernel");
 }
 
