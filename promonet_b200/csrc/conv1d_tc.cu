@@ -171,7 +171,7 @@ struct TcConfig {
     static constexpr int kWSlab = KB * N * 4;                   // bytes, both planes
     static constexpr int kXStages = 2;
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
-    static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 2048;
+    static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 6144;
     static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
     static constexpr int kColumns = AS * S * kCols;
     static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
@@ -179,6 +179,7 @@ struct TcConfig {
     static_assert(kColumns <= 512, "accumulators exceed TMEM");
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
     static_assert(C_IN % KB == 0 && KB % 16 == 0 && N % 32 == 0 && kCols <= 256, "shape");
+    static_assert(C_IN / 8 * 1 > 0, "shape");
     static_assert(MODE != kFrames || S == 1, "frame mode computes one 128-row tile");
 };
 
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     uint64_t* acc_full = w_empty + NW;
     uint64_t* acc_empty = acc_full + AS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + AS);
-    float* bias_smem = reinterpret_cast<float*>(tmem_slot + 4);  // c_out (<= 512) floats
+    float* bias_smem = reinterpret_cast<float*>(tmem_slot + 4);  // c_out (<= 1536) floats
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -215,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
         for (int i = 0; i < AS; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 512; i += kThreads)
-        bias_smem[i] = (a.bias && i < (MODE == kTranspose ? a.c_out : a.c_out)) ? a.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 1536; i += kThreads)
+        bias_smem[i] = (a.bias && i < a.c_out) ? a.bias[i] : 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kAlloc) : "memory");
@@ -699,6 +700,8 @@ bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
         // penn FCNF0++ blocks 1..5 (valid convolutions, k = 32)
         {256, 32, false, {64, 32, true}},    {32, 128, false, {32, 128, false}},
         {128, 256, false, {32, 256, false}}, {256, 512, true, {32, 256, false}},
+        // block 0 as a 32-"channel" (tap) 1x1 conv over im2col rows; head 2048 -> 1440
+        {32, 256, false, {32, 256, false}},  {2048, 1440, false, {64, 160, false}},
     };
     for (const Entry& entry : table) {
         if (entry.c_in == c_in && entry.c_out == c_out && entry.frames == frames) {
@@ -735,6 +738,8 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 32) return launch_variant<32, 32, 4, 32, 8, 2, kConv, 0, true>(a, 1, stream);
     if (a.c_in == 256 && a.c_out == 32) return launch_variant<256, 32, 2, 64, 8, 2, kConv, 0, true>(a, 1, stream);
     if (a.c_in == 32 && a.c_out == 128) return launch_variant<32, 128, 2, 32, 4, 2>(a, 1, stream);
+    if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
+    if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
     return launch_variant<128, 256, 1, 32, 4, 2>(a, 1, stream);
 }
 

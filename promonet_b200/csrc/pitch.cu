@@ -66,6 +66,7 @@ struct pmn_pitch {
     const float* norm_weight[pmn::kLayers] = {};
     const float* norm_bias[pmn::kLayers] = {};
     float* head_weight = nullptr;            // packed (2048, 1, 1440)
+    __nv_bfloat16* head_slabs = nullptr;     // tensor-core path
     const float* head_bias = nullptr;
     // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
     struct Resampler { float* table; int orig, fresh, width; };
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(
 __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
-    int count, int t_pad) {
+    int count, int t_pad, bool transposed) {
     __shared__ double partial[2][8];
     __shared__ float stats[2];
     const int f = blockIdx.x;
@@ -225,6 +226,32 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     }
     __syncthreads();
     const float mean = stats[0], rstd = stats[1];
+    if (transposed) {
+        // head operand: 2048 "channels" c * l_out + t, one row per frame
+        const int wide = channels * l_out / 8;
+        uint4* hi_wide = reinterpret_cast<uint4*>(planes);
+        uint4* lo_wide = hi_wide + (size_t)wide * t_pad;
+        for (int g = tid; g < wide; g += blockDim.x) {
+            unsigned int hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int flat = g * 8 + 2 * e + h;
+                    y[h] = (value(flat / l_out, flat % l_out) - mean) * rstd * weight[flat] + bias[flat];
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
+                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            }
+            hi_wide[(size_t)g * t_pad + kTcPad + f] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            lo_wide[(size_t)g * t_pad + kTcPad + f] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        return;
+    }
     for (int idx = tid; idx < groups * l_out; idx += blockDim.x) {
         const int g = idx / l_out, t = idx % l_out;
         unsigned int hi[4], lo[4];
@@ -246,6 +273,38 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
         hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+}
+
+// Block 0 on the tensor cores: its 32 taps become 32 "channels" of a 1x1 conv.
+// planes[plane][tap / 8][kTcPad + r][tap % 8] = x[r + tap] over the frames laid
+// end to end (x is the cropped-frame buffer), r < rows; pad rows are zero.
+__global__ void __launch_bounds__(128) im2col_planes_kernel(
+    const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, int samples, int rows, int t_pad) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= t_pad) return;
+    const int g = blockIdx.y;
+    const int r = row - kTcPad;
+    unsigned int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    if (r >= 0 && r < rows) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float y[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = r + g * 8 + 2 * e + h;
+                y[h] = i < samples ? x[i] : 0.f;
+            }
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
+            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+        }
+    }
+    uint4* hi_plane = reinterpret_cast<uint4*>(planes);
+    uint4* lo_plane = hi_plane + (size_t)4 * t_pad;
+    hi_plane[(size_t)g * t_pad + row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    lo_plane[(size_t)g * t_pad + row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // logits^T (1440, count) -> masked logits, softmax and entropy periodicity, 32 frames per CTA
@@ -466,13 +525,14 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
         if (w->numel() != (size_t)kChannels[i + 1] * kChannels[i] * kKernel ||
             nw->numel() != (size_t)kChannels[i + 1] * kLength[i + 1] || nb->numel() != nw->numel())
             return fail(PMN_ERR_STATE, "unexpected shapes at " + prefix);
-        if (math == PMN_MATH_BF16X3_TC && i > 0) {
+        if (math == PMN_MATH_BF16X3_TC) {
             float* slabs;  // bf16 hi + lo = the bytes of the fp32 tensor
             PMN_TRY(alloc(p, w->numel(), &slabs));
             p->conv_slabs[i] = reinterpret_cast<__nv_bfloat16*>(slabs);
+            // block 0: (256, 1, 32) is read as a (256, 32, 1) 1x1 conv over the 32 taps
             PMN_TRY(launch_pack_tc_weight(
-                w->data, p->conv_slabs[i], kChannels[i + 1], kChannels[i], kKernel,
-                i == kLayers - 1, stream));
+                w->data, p->conv_slabs[i], kChannels[i + 1], i == 0 ? kKernel : kChannels[i],
+                i == 0 ? 1 : kKernel, i == kLayers - 1, stream));
         } else {
             PMN_TRY(alloc(p, w->numel(), &p->conv_weight[i]));
             PMN_TRY(launch_pack_conv1d_weight(
@@ -486,9 +546,16 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
     PMN_TRY(find(p, "layers.6.weight", &w));
     PMN_TRY(find(p, "layers.6.bias", &b));
     if (w->numel() != (size_t)kBins * 512 * 4) return fail(PMN_ERR_STATE, "unexpected layers.6 shape");
-    PMN_TRY(alloc(p, w->numel(), &p->head_weight));
     // (1440, 512, 4) read as (1440, 2048, 1): input index c * 4 + t matches the transposed activations
-    PMN_TRY(launch_pack_conv1d_weight(w->data, p->head_weight, kBins, 2048, 1, stream));
+    if (math == PMN_MATH_BF16X3_TC) {
+        float* slabs;
+        PMN_TRY(alloc(p, w->numel(), &slabs));
+        p->head_slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
+        PMN_TRY(launch_pack_tc_weight(w->data, p->head_slabs, kBins, 2048, 1, false, stream));
+    } else {
+        PMN_TRY(alloc(p, w->numel(), &p->head_weight));
+        PMN_TRY(launch_pack_conv1d_weight(w->data, p->head_weight, kBins, 2048, 1, stream));
+    }
     p->head_bias = b->data;
     PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "finalize sync"));
     p->finalized = true;
@@ -562,7 +629,24 @@ int pitch_forward(
         for (int i = 0; i < kLayers; ++i) {
             const int l_in = kLength[i];
             const size_t row = (size_t)count * l_in - (kKernel - 1);
-            if (tensor_cores && i > 0) {
+            if (tensor_cores && i == 0) {
+                // 32 taps as 32 channels of a 1x1 conv over im2col rows of the frame buffer
+                const int samples = count * l_in;
+                const int t_pad = tc_padded_length((int)row);
+                dim3 grid(ceil_div(t_pad, 128), 4);
+                {
+                    LaunchScope scope("im2col_planes_kernel", stream);
+                    im2col_planes_kernel<<<grid, 128, 0, stream>>>(
+                        w.act, w.planes, samples, (int)row, t_pad);
+                    PMN_TRY(launched("im2col_planes_kernel"));
+                }
+                TcConvArgs a;
+                a.x_planes = w.planes; a.w_slabs = p->conv_slabs[0]; a.bias = p->conv_bias[0];
+                a.out = w.conv; a.batch = 1; a.c_in = 32; a.c_out = kChannels[1];
+                a.k = 1; a.valid = true; a.relu = true; a.out_row = (int)row;
+                a.t_len = (int)row;
+                PMN_TRY(launch_conv1d_tc(a, stream));
+            } else if (tensor_cores) {
                 TcConvArgs a;
                 a.x_planes = w.planes; a.w_slabs = p->conv_slabs[i]; a.bias = p->conv_bias[i];
                 a.out = w.conv; a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
@@ -590,7 +674,15 @@ int pitch_forward(
                 LaunchScope scope("pool_norm_planes_kernel", stream);
                 pool_norm_planes_kernel<<<frames_out, 256, 0, stream>>>(
                     w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_in,
-                    l_out, kPooled[i], row, count, tc_padded_length(t_next));
+                    l_out, kPooled[i], row, count, tc_padded_length(t_next), false);
+                PMN_TRY(launched("pool_norm_planes_kernel"));
+            } else if (tensor_cores) {
+                // last block: (512, 4) per frame becomes one 2048-channel row of the head's operand
+                PMN_TRY(launch_zero_plane_pads(w.planes, 1, 2048, count, stream));
+                LaunchScope scope("pool_norm_planes_kernel", stream);
+                pool_norm_planes_kernel<<<count, 256, 0, stream>>>(
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_in,
+                    kLength[i + 1], kPooled[i], row, count, tc_padded_length(count), true);
                 PMN_TRY(launched("pool_norm_planes_kernel"));
             } else {
                 LaunchScope scope("pool_norm_kernel", stream);
@@ -600,7 +692,12 @@ int pitch_forward(
                 PMN_TRY(launched("pool_norm_kernel"));
             }
         }
-        {
+        if (tensor_cores) {
+            TcConvArgs a;
+            a.x_planes = w.planes; a.w_slabs = p->head_slabs; a.bias = p->head_bias; a.out = w.logits_t;
+            a.batch = 1; a.c_in = 2048; a.c_out = kBins; a.k = 1; a.valid = true; a.t_len = count;
+            PMN_TRY(launch_conv1d_tc(a, stream));
+        } else {
             Conv1dArgs a;
             a.x = w.act; a.weight = p->head_weight; a.bias = p->head_bias; a.out = w.logits_t;
             a.batch = 1; a.c_in = 2048; a.c_out = kBins; a.t_in = a.t_out = count; a.k = 1;
