@@ -191,6 +191,15 @@ def run_reference(args):
     }))
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, from the
+    committed ncu capture of this same workload (profiles/r1_conv1d_tc_traffic.json)"""
+    file = ROOT / 'profiles' / 'r1_conv1d_tc_traffic.json'
+    if kernel != 'conv1d_tc_kernel' or not file.exists():
+        return None
+    return json.loads(file.read_text())['traffic_bytes_per_launch']
+
+
 def workload_config(gpus):
     return {
         'workload': (
@@ -318,7 +327,8 @@ def run_b200(args):
                 'achieved': achieved, 'peak': peak['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / peak['bf16_tflops_sustained'] if achieved else None,
                 'peak_source': f"{peak['source']} sustained bf16 cuBLAS (kernel timed inside a long step)",
-                'traffic': None,
+                'traffic': measured_traffic(dominant),
+                'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/)',
                 'launches_per_step': kernel_launches / args.steps,
                 'avg_launch_ms': kernel_ms / kernel_launches if kernel_launches else None,
                 'flop_per_launch': flops / kernel_launches if kernel_launches else None,

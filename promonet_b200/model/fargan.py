@@ -25,9 +25,9 @@ class FarganGenerator:
         self.load_state_dict(init.fargan_state() if state is None else state)
 
     def __del__(self):
-        if getattr(self, 'handle', None):
-            _lib.library().pmn_fargan_destroy(self.handle)
-            self.handle = None
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle and _lib is not None and getattr(_lib, '_library', None) is not None:
+            _lib._library.pmn_fargan_destroy(handle)  # no-op at interpreter shutdown
 
     def load_state_dict(self, state):
         """Accepts promonet.model.Generator().state_dict() keys under config/fargan.py"""

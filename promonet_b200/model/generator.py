@@ -33,9 +33,9 @@ class Generator:
         self._destroy()
 
     def _destroy(self):
-        if getattr(self, 'handle', None):
-            _lib.library().pmn_generator_destroy(self.handle)
-            self.handle = None
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle and _lib is not None and getattr(_lib, '_library', None) is not None:
+            _lib._library.pmn_generator_destroy(handle)  # no-op at interpreter shutdown
 
     ###########################################################################
     # Weights

@@ -73,9 +73,9 @@ class Model:
         self.load_state_dict(init_state() if state is None else state)
 
     def __del__(self):
-        if getattr(self, 'handle', None):
-            _lib.library().pmn_pitch_destroy(self.handle)
-            self.handle = None
+        handle, self.handle = getattr(self, 'handle', None), None
+        if handle and _lib is not None and getattr(_lib, '_library', None) is not None:
+            _lib._library.pmn_pitch_destroy(handle)  # no-op at interpreter shutdown
 
     def load_state_dict(self, state):
         lib = _lib.library()
