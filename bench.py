@@ -224,15 +224,14 @@ def run_b200(args):
     from promonet_b200 import _lib
     from oracle import inputs  # synthetic inputs only; the oracle is not on this path
 
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
+    from promonet_b200 import parallel
+    rank, local_rank, world = parallel.environment()
     distributed = world > 1
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
+    parallel.initialize('nccl', device)
     if distributed:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=device)
 
     math = _lib.MATH_BF16X3_TC if args.math == 'bf16x3' else _lib.MATH_FP32_SIMT
     state = promonet_b200.model.init.hifigan_state(promonet_b200.RANDOM_SEED)
@@ -241,10 +240,7 @@ def run_b200(args):
     dev = [t.to(device) for t in host]
     audio_host = torch.empty(BATCH, 1, SAMPLES, pin_memory=True)
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = parallel.barrier
 
     def timed(step, steps):
         """Device time of `steps` calls, max over ranks (ms)"""
@@ -255,10 +251,7 @@ def run_b200(args):
             step()
         stop.record()
         barrier()
-        elapsed = torch.tensor([start.elapsed_time(stop)], device=device)
-        if distributed:
-            dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-        return float(elapsed)
+        return parallel.max_over_ranks(start.elapsed_time(stop), device)
 
     resident = lambda: model(*dev)
     end_to_end = lambda: model.forward_host(*host, out=audio_host)
@@ -278,10 +271,7 @@ def run_b200(args):
     for _ in range(args.steps):
         end_to_end()
     barrier()
-    e2e_seconds = torch.tensor([time.perf_counter() - start], device=device)
-    if distributed:
-        dist.all_reduce(e2e_seconds, op=dist.ReduceOp.MAX)
-    e2e_seconds = float(e2e_seconds)
+    e2e_seconds = parallel.max_over_ranks(time.perf_counter() - start, device)
 
     # Roofline of the dominant kernel: same steps again with per-launch CUDA events
     dominant = 'conv1d_kernel' if math == _lib.MATH_FP32_SIMT else 'conv1d_tc_kernel'
