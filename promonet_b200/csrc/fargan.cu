@@ -25,6 +25,7 @@
 
 #include "fargan.cuh"
 #include "features.cuh"
+#include "tensor_store.cuh"
 
 namespace pmn {
 
@@ -61,16 +62,6 @@ constexpr int kScratch = (kParts / 2) * 24 * kGroupItems; // K-partition partial
 constexpr int kSmemFloats = kWeights + 2 * kInput * kGroupItems + kStage + kScratch;
 constexpr int kSmemBytes = kSmemFloats * 4 + 64;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-
-struct Tensor {
-    float* data = nullptr;
-    std::vector<int64_t> shape;
-    size_t numel() const {
-        size_t n = 1;
-        for (auto s : shape) n *= (size_t)s;
-        return n;
-    }
-};
 
 // Activations of one group in global memory, all [k][16]
 struct GroupState {
@@ -159,8 +150,6 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     const int group = blockIdx.x / kGroupCtas;
     const int b = tid & (kGroupItems - 1);
     const int part = tid >> 4;
-    const int item = group * kGroupItems + b;   // utterance of this thread's column
-    const bool live = item < batch;
     const GroupState gs = groups[group];
     const int samples = frames * kHop;
     unsigned int target = 0;
@@ -312,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         group_barrier(gs.barrier, target);
         current ^= 1;
     }
-    (void)live;
 }
 
 // x (B, 371, F) = [features[:113]; speaker embedding; ratios broadcast over frames]
@@ -341,17 +329,11 @@ __global__ void __launch_bounds__(128) cond_input_kernel(
 }  // namespace pmn
 
 struct pmn_fargan {
-    std::map<std::string, pmn::Tensor> tensors;
-    std::vector<void*> owned;
+    pmn::TensorStore store;
     bool finalized = false;
     float ppg_threshold = 0.85f;
     float* images = nullptr;         // (64, kWeights)
     float* cond_weight[3] = {};      // packed (C_in, 1, C_out)
-
-    ~pmn_fargan() {
-        for (auto& item : tensors) cudaFree(item.second.data);
-        for (void* p : owned) cudaFree(p);
-    }
 };
 
 namespace pmn {
@@ -359,22 +341,20 @@ namespace pmn {
 namespace {
 
 int find(const pmn_fargan* g, const std::string& name, const Tensor** out) {
-    auto it = g->tensors.find(name);
-    if (it == g->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
-    *out = &it->second;
-    return PMN_OK;
+    return g->store.find(name, out);
 }
 
 // Host copy of `<prefix>.weight`, folding weight norm (Linear: per output row)
 int host_weight(pmn_fargan* g, const std::string& prefix, int rows, int cols,
                 std::vector<float>* out, cudaStream_t stream) {
     out->resize((size_t)rows * cols);
-    auto plain = g->tensors.find(prefix + ".weight");
     const float* source;
     float* folded = nullptr;
-    if (plain != g->tensors.end()) {
-        if (plain->second.numel() != out->size()) return fail(PMN_ERR_STATE, "bad shape at " + prefix);
-        source = plain->second.data;
+    if (g->store.has(prefix + ".weight")) {
+        const Tensor* plain;
+        PMN_TRY(find(g, prefix + ".weight", &plain));
+        if (plain->numel() != out->size()) return fail(PMN_ERR_STATE, "bad shape at " + prefix);
+        source = plain->data;
     } else {
         const Tensor *wg, *wv;
         PMN_TRY(find(g, prefix + ".weight_g", &wg));
@@ -430,19 +410,7 @@ void fargan_destroy(pmn_fargan* g) { delete g; }
 int fargan_set_tensor(pmn_fargan* g, const char* name, const float* data, const int64_t* shape,
                       int ndim, cudaStream_t stream) {
     if (g->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
-    Tensor t;
-    for (int i = 0; i < ndim; ++i) {
-        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
-        t.shape.push_back(shape[i]);
-    }
-    PMN_TRY(check_cuda(cudaMalloc(&t.data, t.numel() * 4), "cudaMalloc"));
-    int status = check_cuda(
-        cudaMemcpyAsync(t.data, data, t.numel() * 4, cudaMemcpyDeviceToDevice, stream), "set_tensor copy");
-    if (status != PMN_OK) { cudaFree(t.data); return status; }
-    auto old = g->tensors.find(name);
-    if (old != g->tensors.end()) { cudaFree(old->second.data); g->tensors.erase(old); }
-    g->tensors.emplace(name, std::move(t));
-    return PMN_OK;
+    return g->store.set(name, data, shape, ndim, stream);
 }
 
 int fargan_finalize(pmn_fargan* g, cudaStream_t stream) {
@@ -451,11 +419,10 @@ int fargan_finalize(pmn_fargan* g, cudaStream_t stream) {
     PMN_TRY(find(g, "speaker_embedding.weight", &t));
     PMN_TRY(find(g, "pitch_embedding.weight", &t));
     PMN_TRY(find(g, "pitch_distribution", &t));
-    auto threshold = g->tensors.find("ppg_threshold");
-    if (threshold != g->tensors.end()) {
+    if (g->store.has("ppg_threshold")) {
         PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
         PMN_TRY(check_cuda(
-            cudaMemcpy(&g->ppg_threshold, threshold->second.data, 4, cudaMemcpyDeviceToHost),
+            cudaMemcpy(&g->ppg_threshold, g->store.data("ppg_threshold"), 4, cudaMemcpyDeviceToHost),
             "read ppg_threshold"));
     }
     // conditioning MLP as k = 1 convolutions
@@ -463,8 +430,7 @@ int fargan_finalize(pmn_fargan* g, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) {
         PMN_TRY(find(g, "model.conditioning_network." + std::to_string(2 * i) + ".weight", &t));
         if (t->numel() != (size_t)cond_out[i] * kCondIn) return fail(PMN_ERR_STATE, "bad conditioning shape");
-        PMN_TRY(check_cuda(cudaMalloc(&g->cond_weight[i], t->numel() * 4), "cudaMalloc"));
-        g->owned.push_back(g->cond_weight[i]);
+        PMN_TRY(g->store.alloc(t->numel(), &g->cond_weight[i]));
         PMN_TRY(launch_pack_conv1d_weight(t->data, g->cond_weight[i], cond_out[i], kCondIn, 1, stream));
     }
     // per-CTA weight images
@@ -519,8 +485,7 @@ int fargan_finalize(pmn_fargan* g, cudaStream_t stream) {
         dense(image + kWSkipGlu, skipglu, kHop);
         for (int k = 0; k < kHop; ++k) image[kWOut + k] = out[(size_t)cta * kHop + k];
     }
-    PMN_TRY(check_cuda(cudaMalloc(&g->images, images.size() * 4), "cudaMalloc"));
-    g->owned.push_back(g->images);
+    PMN_TRY(g->store.alloc(images.size(), &g->images));
     PMN_TRY(check_cuda(cudaMemcpy(g->images, images.data(), images.size() * 4, cudaMemcpyHostToDevice), "H2D images"));
     g->finalized = true;
     return PMN_OK;
@@ -548,14 +513,14 @@ int fargan_forward(
 
     // features (B, 114, F) incl. pitch period; conditioning for every frame
     PMN_TRY(launch_features(
-        loudness, rows, pitch, periodicity, ppg, g->tensors.at("pitch_distribution").data,
-        g->tensors.at("pitch_embedding.weight").data, g->ppg_threshold, true, w.features,
+        loudness, rows, pitch, periodicity, ppg, g->store.data("pitch_distribution"),
+        g->store.data("pitch_embedding.weight"), g->ppg_threshold, true, w.features,
         batch, frames, stream));
     {
         dim3 grid(ceil_div(frames, 128), kCondIn, batch);
         LaunchScope scope("cond_input_kernel", stream);
         cond_input_kernel<<<grid, 128, 0, stream>>>(
-            w.features, g->tensors.at("speaker_embedding.weight").data, speakers, sbr, lr,
+            w.features, g->store.data("speaker_embedding.weight"), speakers, sbr, lr,
             w.cond_in, frames, 109);
         PMN_TRY(launched("cond_input_kernel"));
     }

@@ -11,6 +11,7 @@
 #include "conv1d_tc.cuh"
 #include "features.cuh"
 #include "generator.cuh"
+#include "tensor_store.cuh"
 
 namespace pmn {
 
@@ -29,16 +30,6 @@ constexpr int kResDilation[3] = {1, 3, 5};          // :253
 constexpr float kSlope = 0.1f;                      // :216
 constexpr int kHop = 256;
 
-struct Tensor {
-    float* data = nullptr;
-    std::vector<int64_t> shape;
-    size_t numel() const {
-        size_t n = 1;
-        for (auto s : shape) n *= (size_t)s;
-        return n;
-    }
-};
-
 struct PackedConv {
     float* weight = nullptr;  // conv1d: (C_in, K, C_out); conv transpose: (C_in, C_out, K)
     __nv_bfloat16* slabs = nullptr;  // tensor-core path: hi/lo weight slabs (conv1d_tc.cuh)
@@ -51,8 +42,7 @@ struct PackedConv {
 }  // namespace pmn
 
 struct pmn_generator {
-    std::map<std::string, pmn::Tensor> tensors;
-    std::vector<float*> owned;  // finalize-time allocations
+    pmn::TensorStore store;
     bool finalized = false;
     int math = PMN_MATH_FP32_SIMT;
     float ppg_threshold = 0.85f;
@@ -61,38 +51,25 @@ struct pmn_generator {
     pmn::PackedConv conv1[pmn::kStages][3][3];
     pmn::PackedConv conv2[pmn::kStages][3][3];
     float* input_weight = nullptr;  // packed (113, 7, 512)
-
-    ~pmn_generator() {
-        for (auto& item : tensors) cudaFree(item.second.data);
-        for (float* p : owned) cudaFree(p);
-    }
 };
 
 namespace pmn {
 
 namespace {
 
-int alloc(pmn_generator* g, size_t count, float** out) {
-    PMN_TRY(check_cuda(cudaMalloc(out, count * sizeof(float)), "cudaMalloc"));
-    g->owned.push_back(*out);
-    return PMN_OK;
-}
+int alloc(pmn_generator* g, size_t count, float** out) { return g->store.alloc(count, out); }
 
 int find(const pmn_generator* g, const std::string& name, const Tensor** out) {
-    auto it = g->tensors.find(name);
-    if (it == g->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
-    *out = &it->second;
-    return PMN_OK;
+    return g->store.find(name, out);
 }
 
 // Resolve `<prefix>.weight`, folding `<prefix>.weight_g/_v` when that is what the
 // checkpoint holds (weight_norm keys, SURVEY 5 "Checkpoint / resume")
 int folded_weight(pmn_generator* g, const std::string& prefix, const Tensor** v_out,
                   const float** w_out, cudaStream_t stream) {
-    auto plain = g->tensors.find(prefix + ".weight");
-    if (plain != g->tensors.end()) {
-        *v_out = &plain->second;
-        *w_out = plain->second.data;
+    if (g->store.has(prefix + ".weight")) {
+        PMN_TRY(find(g, prefix + ".weight", v_out));
+        *w_out = (*v_out)->data;
         return PMN_OK;
     }
     const Tensor *wg, *wv;
@@ -183,26 +160,7 @@ int generator_set_tensor(
     pmn_generator* g, const char* name, const float* data, const int64_t* shape, int ndim,
     cudaStream_t stream) {
     if (g->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
-    Tensor t;
-    for (int i = 0; i < ndim; ++i) {
-        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
-        t.shape.push_back(shape[i]);
-    }
-    const size_t bytes = t.numel() * sizeof(float);
-    PMN_TRY(check_cuda(cudaMalloc(&t.data, bytes), "cudaMalloc"));
-    int status = check_cuda(
-        cudaMemcpyAsync(t.data, data, bytes, cudaMemcpyDeviceToDevice, stream), "set_tensor copy");
-    if (status != PMN_OK) {
-        cudaFree(t.data);
-        return status;
-    }
-    auto old = g->tensors.find(name);
-    if (old != g->tensors.end()) {
-        cudaFree(old->second.data);
-        g->tensors.erase(old);
-    }
-    g->tensors.emplace(name, std::move(t));
-    return PMN_OK;
+    return g->store.set(name, data, shape, ndim, stream);
 }
 
 int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
@@ -231,11 +189,10 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
     if (t->numel() != 256) return fail(PMN_ERR_STATE, "unexpected pitch_distribution shape");
     PMN_TRY(find(g, "model.model.5.weight", &t));
     if (t->numel() != 32 * 7) return fail(PMN_ERR_STATE, "unexpected output conv shape");
-    auto threshold = g->tensors.find("ppg_threshold");
-    if (threshold != g->tensors.end()) {
+    if (g->store.has("ppg_threshold")) {
         PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
         PMN_TRY(check_cuda(
-            cudaMemcpy(&g->ppg_threshold, threshold->second.data, sizeof(float), cudaMemcpyDeviceToHost),
+            cudaMemcpy(&g->ppg_threshold, g->store.data("ppg_threshold"), sizeof(float), cudaMemcpyDeviceToHost),
             "read ppg_threshold"));
     }
 
@@ -289,7 +246,7 @@ int generator_features(
     if (!g->finalized) return fail(PMN_ERR_STATE, "generator not finalized");
     return launch_features(
         loudness, rows, pitch, periodicity, ppg,
-        g->tensors.at("pitch_distribution").data, g->tensors.at("pitch_embedding.weight").data,
+        g->store.data("pitch_distribution"), g->store.data("pitch_embedding.weight"),
         g->ppg_threshold, false, features, batch, frames, stream);
 }
 
@@ -308,15 +265,15 @@ int generator_forward(
     PMN_TRY(generator_features(g, loudness, rows, pitch, periodicity, ppg, w.features, batch, frames, stream));
     // G2 + speaker 1x1 conv: (B, 512) bias
     PMN_TRY(launch_speaker_bias(
-        g->tensors.at("speaker_embedding.weight").data, speakers, sbr, lr,
-        g->tensors.at("model.input_speaker_conv.weight").data,
-        g->tensors.at("model.input_speaker_conv.bias").data,
+        g->store.data("speaker_embedding.weight"), speakers, sbr, lr,
+        g->store.data("model.input_speaker_conv.weight"),
+        g->store.data("model.input_speaker_conv.bias"),
         w.speaker_bias, batch, kSpeakerChannels, kInitial, kNumSpeakers, stream));
     // G3: input conv k7 + speaker bias
     {
         Conv1dArgs a;
         a.x = w.features; a.weight = g->input_weight;
-        a.bias = g->tensors.at("model.input_feature_conv.bias").data;
+        a.bias = g->store.data("model.input_feature_conv.bias");
         a.bias2 = w.speaker_bias;
         a.out = w.x_in;
         a.batch = batch; a.c_in = kNumFeatures; a.c_out = kInitial;
@@ -408,7 +365,7 @@ int generator_forward(
         stage_in = w.mrf;
     }
     // G7: LeakyReLU + Conv1d(32 -> 1, k7, no bias) + tanh
-    return launch_head(stage_in, g->tensors.at("model.model.5.weight").data, audio, batch, 32,
+    return launch_head(stage_in, g->store.data("model.model.5.weight"), audio, batch, 32,
                        t_len, kSlope, stream);
 }
 

@@ -23,6 +23,7 @@
 #include "conv1d_tc.cuh"
 #include "pitch.cuh"
 #include "spectral.cuh"
+#include "tensor_store.cuh"
 
 namespace pmn {
 
@@ -41,23 +42,12 @@ constexpr int kLength[kLayers + 1] = {993, 481, 225, 97, 66, 35, 4};  // per-fra
 constexpr float kCentsPerBin = 5.f, kFmin = 31.f, kOctave = 1200.f;
 constexpr int kLocalWindow = 19;
 
-struct Tensor {
-    float* data = nullptr;
-    std::vector<int64_t> shape;
-    size_t numel() const {
-        size_t n = 1;
-        for (auto s : shape) n *= (size_t)s;
-        return n;
-    }
-};
-
 }  // namespace
 
 }  // namespace pmn
 
 struct pmn_pitch {
-    std::map<std::string, pmn::Tensor> tensors;
-    std::vector<float*> owned;
+    pmn::TensorStore store;
     bool finalized = false;
     int math = PMN_MATH_FP32_SIMT;
     __nv_bfloat16* conv_slabs[pmn::kLayers] = {};  // tensor-core path, layers 1..5
@@ -73,8 +63,6 @@ struct pmn_pitch {
     std::map<int, Resampler> resamplers;
 
     ~pmn_pitch() {
-        for (auto& item : tensors) cudaFree(item.second.data);
-        for (float* p : owned) cudaFree(p);
         for (auto& item : resamplers) cudaFree(item.second.table);
     }
 };
@@ -407,17 +395,10 @@ __global__ void __launch_bounds__(128) pitch_kernel(
 }
 
 int find(const pmn_pitch* p, const std::string& name, const Tensor** out) {
-    auto it = p->tensors.find(name);
-    if (it == p->tensors.end()) return fail(PMN_ERR_STATE, "missing tensor: " + name);
-    *out = &it->second;
-    return PMN_OK;
+    return p->store.find(name, out);
 }
 
-int alloc(pmn_pitch* p, size_t count, float** out) {
-    PMN_TRY(check_cuda(cudaMalloc(out, count * sizeof(float)), "cudaMalloc"));
-    p->owned.push_back(*out);
-    return PMN_OK;
-}
+int alloc(pmn_pitch* p, size_t count, float** out) { return p->store.alloc(count, out); }
 
 // torchaudio.functional.resample kernel bank (sinc_interp_hann, width 6, rolloff 0.99),
 // stored transposed: table[k][phase]
@@ -494,20 +475,7 @@ void pitch_destroy(pmn_pitch* p) { delete p; }
 int pitch_set_tensor(pmn_pitch* p, const char* name, const float* data, const int64_t* shape,
                      int ndim, cudaStream_t stream) {
     if (p->finalized) return fail(PMN_ERR_STATE, "set_tensor after finalize");
-    Tensor t;
-    for (int i = 0; i < ndim; ++i) {
-        if (shape[i] <= 0) return fail(PMN_ERR_ARGUMENT, std::string("set_tensor: empty dimension in ") + name);
-        t.shape.push_back(shape[i]);
-    }
-    PMN_TRY(check_cuda(cudaMalloc(&t.data, t.numel() * sizeof(float)), "cudaMalloc"));
-    int status = check_cuda(
-        cudaMemcpyAsync(t.data, data, t.numel() * sizeof(float), cudaMemcpyDeviceToDevice, stream),
-        "set_tensor copy");
-    if (status != PMN_OK) { cudaFree(t.data); return status; }
-    auto old = p->tensors.find(name);
-    if (old != p->tensors.end()) { cudaFree(old->second.data); p->tensors.erase(old); }
-    p->tensors.emplace(name, std::move(t));
-    return PMN_OK;
+    return p->store.set(name, data, shape, ndim, stream);
 }
 
 int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
