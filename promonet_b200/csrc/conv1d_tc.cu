@@ -449,16 +449,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 uint32_t raw[kW];
                 load(s, c0, raw);
                 float (&r)[kW] = res[mine % kDepth];
-                if (t >= 0) {
-                    float v[kW];
-                    const int c_first = nt * N + c0;
-                    const size_t idx = ((size_t)b * a.c_out + c_first) * out_row + t;
+                float v[kW];
+                const int c_first = nt * N + c0;
 #pragma unroll
-                    for (int i = 0; i < kW; ++i) {
-                        float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
-                        if (a.relu) y = fmaxf(y, 0.f);
-                        v[i] = y;
-                    }
+                for (int i = 0; i < kW; ++i) {
+                    float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
+                    if (a.relu) y = fmaxf(y, 0.f);
+                    v[i] = y;
+                }
+                int row = t;
+                if (a.pool) {
+                    // MaxPool1d(2) over row pairs (2 i, 2 i + 1): adjacent lanes; even lanes store
+#pragma unroll
+                    for (int i = 0; i < kW; ++i)
+                        v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                    row = (t >= 0 && (lane & 1) == 0 && t + 1 < t_out) ? t / 2 : -1;
+                }
+                if (row >= 0) {
+                    const size_t idx = ((size_t)b * a.c_out + c_first) * out_row + row;
                     if (a.out) {
 #pragma unroll
                         for (int i = 0; i < kW; ++i) a.out[idx + (size_t)i * out_row] = v[i];

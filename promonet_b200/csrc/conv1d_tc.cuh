@@ -49,6 +49,7 @@ struct TcConvArgs {
     int k = 1, dilation = 1;
     bool valid = false;                       // false: "same" padding (odd k); true: no padding
     bool relu = false;                        // max(y, 0) before any store
+    bool pool = false;                        // MaxPool1d(2) over row pairs: out row t / 2, out_row = pooled length
     int out_row = 0;                          // fp32 row length of out / residual / accum (0 = output length)
     // Frame mode (valid conv over frames laid end to end, a few output rows per
     // frame): frames of frame_length rows each, the first frame_valid outputs kept

@@ -28,7 +28,7 @@ constexpr int kUpRate[kStages] = {8, 8, 2, 2};      // :262
 constexpr int kResKernel[3] = {3, 7, 11};           // :250
 constexpr int kResDilation[3] = {1, 3, 5};          // :253
 constexpr float kSlope = 0.1f;                      // :216
-constexpr int kHop = 256;
+
 
 struct PackedConv {
     float* weight = nullptr;  // conv1d: (C_in, K, C_out); conv transpose: (C_in, C_out, K)

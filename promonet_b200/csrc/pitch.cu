@@ -93,10 +93,14 @@ __global__ void __launch_bounds__(256) resample_kernel(
 // Cropped frames laid end to end: x[g * 993 + n] = padded[b][hop * f + 16 + n], g = first + local
 __global__ void __launch_bounds__(256) frames_kernel(
     const float* __restrict__ audio, float* __restrict__ out, int samples, int frames_per_item,
-    int first_frame, int count, int hop, int padding) {
+    int first_frame, int count, int hop, int padding, int stride) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int local = blockIdx.y;
-    if (n >= kCropped || local >= count) return;
+    if (n >= stride || local >= count) return;
+    if (n >= kCropped) {  // pad sample that keeps frame starts on even rows
+        out[(size_t)local * stride + n] = 0.f;
+        return;
+    }
     const int g = first_frame + local;
     const int b = g / frames_per_item, f = g % frames_per_item;
     int i = hop * f + kCropStart + n - padding;  // index into the unpadded audio
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) frames_kernel(
         i = beyond <= padding ? samples - 1 - beyond : -1;
     }
     if (i >= 0 && i < samples) value = audio[(size_t)b * samples + i];
-    out[(size_t)local * kCropped + n] = value;
+    out[(size_t)local * stride + n] = value;
 }
 
 // MaxPool(2) (optional) + LayerNorm over (C, L) with elementwise affine, per frame.
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(
 __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
-    int count, int t_pad, bool transposed) {
+    int count, int t_pad, bool transposed, int stride_out) {
     __shared__ double partial[2][8];
     __shared__ float stats[2];
     const int f = blockIdx.x;
@@ -177,25 +181,37 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const int groups = channels / 8;
     uint4* hi_plane = reinterpret_cast<uint4*>(planes);
     uint4* lo_plane = hi_plane + (size_t)groups * t_pad;
-    if (f >= count) {
-        for (int idx = tid; idx < groups * l_out; idx += blockDim.x) {
-            const size_t row = (size_t)(idx / l_out) * t_pad + kTcPad + (size_t)f * l_out + idx % l_out;
+    // rows [l_out, stride_out) of a frame and whole frames >= count are zero padding
+    for (int idx = tid; idx < groups * stride_out; idx += blockDim.x) {
+        const int t = idx % stride_out;
+        if (!transposed && (f >= count || t >= l_out)) {
+            const size_t row = (size_t)(idx / stride_out) * t_pad + kTcPad + (size_t)f * stride_out + t;
             hi_plane[row] = make_uint4(0, 0, 0, 0);
             lo_plane[row] = make_uint4(0, 0, 0, 0);
         }
-        return;
     }
+    if (f >= count) return;
     const int total = channels * l_out;
     const float* base = in + (size_t)f * l_in;
     auto value = [&](int c, int t) {
         const float* row = base + (size_t)c * in_row;
         return pooled ? fmaxf(row[2 * t], row[2 * t + 1]) : row[t];
     };
+    // statistics: one warp per channel row, 4 independent loads in flight per lane
+    const int warp = tid >> 5, lane = tid & 31;
     float sum = 0.f, squares = 0.f;
-    for (int idx = tid; idx < total; idx += blockDim.x) {
-        const float v = value(idx / l_out, idx % l_out);
-        sum += v;
-        squares = fmaf(v, v, squares);
+    for (int c = warp; c < channels; c += 8) {
+        int t = lane;
+        for (; t + 96 < l_out; t += 128) {
+            const float v0 = value(c, t), v1 = value(c, t + 32), v2 = value(c, t + 64), v3 = value(c, t + 96);
+            sum += (v0 + v1) + (v2 + v3);
+            squares = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, squares))));
+        }
+        for (; t < l_out; t += 32) {
+            const float v = value(c, t);
+            sum += v;
+            squares = fmaf(v, v, squares);
+        }
     }
     double dsum = sum, dsquares = squares;
     for (int offset = 16; offset > 0; offset >>= 1) {
@@ -240,26 +256,30 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
         }
         return;
     }
-    for (int idx = tid; idx < groups * l_out; idx += blockDim.x) {
-        const int g = idx / l_out, t = idx % l_out;
-        unsigned int hi[4], lo[4];
+    for (int g = warp; g < groups; g += 8) {
+        for (int t = lane; t < l_out; t += 32) {
+            float y[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float y[2];
+            for (int e = 0; e < 8; ++e) y[e] = value(g * 8 + e, t);   // 8 independent loads
+            unsigned int hi[4], lo[4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = g * 8 + 2 * e + h;
-                y[h] = (value(c, t) - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
+            for (int e = 0; e < 4; ++e) {
+                float z[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = g * 8 + 2 * e + h;
+                    z[h] = (y[2 * e + h] - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
+                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
             }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
-            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            const size_t row = (size_t)g * t_pad + kTcPad + (size_t)f * stride_out + t;
+            hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const size_t row = (size_t)g * t_pad + kTcPad + (size_t)f * l_out + t;
-        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -453,10 +473,10 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     const size_t total = (size_t)batch * frames;
     const size_t fb = (size_t)std::min<size_t>(frame_batch, total);
     w.resampled = (float*)take((size_t)batch * out_samples * 4);
-    w.conv = (float*)take(fb * 256 * kCropped * 4);                 // largest conv output (layer 0)
+    w.conv = (float*)take(fb * 256 * (kCropped + 1) * 4);                 // largest conv output (layer 0)
     w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
     // tensor-core operand planes: the widest is block 0's output (256 channels x 481 rows per frame)
-    w.planes = (__nv_bfloat16*)take(tc_planes_elements(1, 256, (int)(fb + 16) * 481) * 2);
+    w.planes = (__nv_bfloat16*)take(tc_planes_elements(1, 256, (int)(fb + 16) * 482) * 2);
     w.logits_t = (float*)take(fb * kBins * 4);
     w.masked = (float*)take(total * kBins * 4);
     w.distribution = (float*)take(total * kBins * 4);
@@ -585,41 +605,42 @@ int pitch_forward(
     // 2. network, frame_batch frames at a time
     for (int first = 0; first < total; first += frame_batch) {
         const int count = std::min(frame_batch, total - first);
+        const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
+        // Tensor-core path: frame strides are even where a MaxPool follows, so pooling
+        // pairs never straddle two frames and the conv epilogue can pool adjacent lanes
+        auto stride_of = [&](int i) { return tensor_cores && i < 3 ? kLength[i] + 1 : kLength[i]; };
         {
-            dim3 grid(ceil_div(kCropped, 256), count);
+            const int stride = stride_of(0);
+            dim3 grid(ceil_div(stride, 256), count);
             LaunchScope scope("frames_kernel", stream);
             frames_kernel<<<grid, 256, 0, stream>>>(
-                audio8k, w.act, out_samples, frames, first, count, hop, padding);
+                audio8k, w.act, out_samples, frames, first, count, hop, padding, stride);
             PMN_TRY(launched("frames_kernel"));
         }
-        const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
         const int padded = (count + 15) / 16 * 16;  // frame-mode tiles cover 16 frames
         for (int i = 0; i < kLayers; ++i) {
-            const int l_in = kLength[i];
-            const size_t row = (size_t)count * l_in - (kKernel - 1);
-            if (tensor_cores && i == 0) {
-                // 32 taps as 32 channels of a 1x1 conv over im2col rows of the frame buffer
-                const int samples = count * l_in;
-                const int t_pad = tc_padded_length((int)row);
-                dim3 grid(ceil_div(t_pad, 128), 4);
-                {
-                    LaunchScope scope("im2col_planes_kernel", stream);
-                    im2col_planes_kernel<<<grid, 128, 0, stream>>>(
-                        w.act, w.planes, samples, (int)row, t_pad);
-                    PMN_TRY(launched("im2col_planes_kernel"));
-                }
-                TcConvArgs a;
-                a.x_planes = w.planes; a.w_slabs = p->conv_slabs[0]; a.bias = p->conv_bias[0];
-                a.out = w.conv; a.batch = 1; a.c_in = 32; a.c_out = kChannels[1];
-                a.k = 1; a.valid = true; a.relu = true; a.out_row = (int)row;
-                a.t_len = (int)row;
-                PMN_TRY(launch_conv1d_tc(a, stream));
-            } else if (tensor_cores) {
+            const int l_in = stride_of(i);                       // frame stride of the input rows
+            const size_t conv_rows = (size_t)count * l_in - (kKernel - 1);
+            const bool pool_in_conv = tensor_cores && kPooled[i];
+            const size_t row = pool_in_conv ? conv_rows / 2 : conv_rows;  // row length of w.conv
+            const int l_conv = pool_in_conv ? l_in / 2 : l_in;   // frame stride inside w.conv
+            if (tensor_cores) {
                 TcConvArgs a;
                 a.x_planes = w.planes; a.w_slabs = p->conv_slabs[i]; a.bias = p->conv_bias[i];
-                a.out = w.conv; a.batch = 1; a.c_in = kChannels[i]; a.c_out = kChannels[i + 1];
-                a.k = kKernel; a.valid = true; a.relu = true; a.out_row = (int)row;
-                a.t_len = count * l_in;
+                a.out = w.conv; a.batch = 1; a.c_out = kChannels[i + 1];
+                a.valid = true; a.relu = true; a.pool = pool_in_conv; a.out_row = (int)row;
+                if (i == 0) {
+                    // 32 taps as 32 channels of a 1x1 conv over im2col rows of the frame buffer
+                    const int t_pad = tc_padded_length((int)conv_rows);
+                    dim3 grid(ceil_div(t_pad, 128), 4);
+                    LaunchScope scope("im2col_planes_kernel", stream);
+                    im2col_planes_kernel<<<grid, 128, 0, stream>>>(
+                        w.act, w.planes, count * l_in, (int)conv_rows, t_pad);
+                    PMN_TRY(launched("im2col_planes_kernel"));
+                    a.c_in = kKernel; a.k = 1; a.t_len = (int)conv_rows;
+                } else {
+                    a.c_in = kChannels[i]; a.k = kKernel; a.t_len = count * l_in;
+                }
                 if (i == kLayers - 1) {
                     // block 5 keeps 4 of 35 rows per frame: 16 frames x 8 rows per MMA tile
                     a.t_len = padded * l_in;
@@ -635,22 +656,22 @@ int pitch_forward(
             }
             if (tensor_cores && i < kLayers - 1) {
                 // the next block runs on the tensor cores: write its operand planes
-                const int l_out = kLength[i + 1];
+                const int stride_next = stride_of(i + 1);
                 const int frames_out = i + 1 == kLayers - 1 ? padded : count;
-                const int t_next = frames_out * l_out;
+                const int t_next = frames_out * stride_next;
                 PMN_TRY(launch_zero_plane_pads(w.planes, 1, kChannels[i + 1], t_next, stream));
                 LaunchScope scope("pool_norm_planes_kernel", stream);
                 pool_norm_planes_kernel<<<frames_out, 256, 0, stream>>>(
-                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_in,
-                    l_out, kPooled[i], row, count, tc_padded_length(t_next), false);
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_conv,
+                    kLength[i + 1], false, row, count, tc_padded_length(t_next), false, stride_next);
                 PMN_TRY(launched("pool_norm_planes_kernel"));
             } else if (tensor_cores) {
                 // last block: (512, 4) per frame becomes one 2048-channel row of the head's operand
                 PMN_TRY(launch_zero_plane_pads(w.planes, 1, 2048, count, stream));
                 LaunchScope scope("pool_norm_planes_kernel", stream);
                 pool_norm_planes_kernel<<<count, 256, 0, stream>>>(
-                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_in,
-                    kLength[i + 1], kPooled[i], row, count, tc_padded_length(count), true);
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_conv,
+                    kLength[i + 1], false, row, count, tc_padded_length(count), true, kLength[i + 1]);
                 PMN_TRY(launched("pool_norm_planes_kernel"));
             } else {
                 LaunchScope scope("pool_norm_kernel", stream);
