@@ -270,6 +270,137 @@ int pmn_conv_transpose1d_tc(
     int batch, int c_in, int c_out, int t_in, int k, int stride, float in_slope,
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------ */
+/* Training step -- promonet/train/core.py:183-369 (operator level; the      */
+/* step itself is sequenced by promonet_b200/train/)                         */
+/* ------------------------------------------------------------------------ */
+
+/* Geometry of a FORWARD 2-D convolution (torch.nn.functional.conv2d semantics,
+ * zero padding).  A Conv1d over (B, C, T) is the case w_in = w_out = kw = 1 with
+ * time on the H axis: hifigan.py:167-183 (dilated), discriminator.py:67-72
+ * ((5,1) kernels, stride (3,1) over (B, C, T/p, p)), :160-170 ((3,9), stride (1,2)). */
+typedef struct {
+    int batch, c_in, c_out;
+    int h_in, w_in, h_out, w_out;
+    int kh, kw, sh, sw, dh, dw, ph, pw;
+} pmn_conv_geometry;
+
+/* Activation fused into an operand load */
+typedef enum {
+    PMN_ACT_NONE = 0,
+    PMN_ACT_LRELU = 1,       /* lrelu(value, slope) */
+    PMN_ACT_LRELU_MASK = 2,  /* value * (companion > 0 ? 1 : slope): backward of an output LeakyReLU,
+                                companion = the activated output */
+    PMN_ACT_TANH_MASK = 3    /* value * (1 - companion^2): backward of an output tanh */
+} pmn_operand_act;
+typedef enum { PMN_OUT_NONE = 0, PMN_OUT_LRELU = 1, PMN_OUT_TANH = 2 } pmn_output_act;
+
+/* Implicit-GEMM convolution.
+ *   transposed = 0 (forward): a = x (B, c_in, h_in, w_in), wmat = weight (c_out, c_in, kh, kw),
+ *       out (B, c_out, h_out, w_out)
+ *   transposed = 1 (data gradient; also the forward of ConvTranspose, hifigan.py:100-106):
+ *       a = dy (B, c_out, h_out, w_out), wmat = weight transposed to (c_in, c_out, kh, kw)
+ *       (pmn_transpose_weight), out = dx (B, c_in, h_in, w_in)
+ *   out = [out +] alpha * (mask(out_act(conv + bias[n] + bias2[b, n])) + residual)
+ *   mask: value *= (mask_src > 0 ? 1 : mask_slope), the backward of an INPUT LeakyReLU
+ *   bias, bias2, mask_src, residual, a_companion may be NULL; residual and mask_src must not
+ *   alias out (use accumulate). */
+int pmn_conv_gemm(
+    const pmn_conv_geometry* geometry, int transposed,
+    const float* a, const float* a_companion, int a_act, float a_slope,
+    const float* wmat, const float* bias, const float* bias2,
+    int out_act, float out_slope, const float* mask_src, float mask_slope,
+    const float* residual, float alpha, int accumulate, float* out, void* stream);
+
+/* Weight (and bias) gradient, ACCUMULATED atomically into gw (c_out, c_in, kh, kw) and
+ * gbias (c_out, may be NULL):  gw[n, c, i, j] += sum_{b, p} act(dy)[b, n, p] act(x)[b, c, in(p, i, j)].
+ * The weight gradient of a ConvTranspose (C_in, C_out, k) is this call on the geometry of the
+ * convolution it transposes, with the roles of input and output gradient exchanged. */
+int pmn_conv_wgrad(
+    const pmn_conv_geometry* geometry,
+    const float* dy, const float* dy_companion, int dy_act, float dy_slope,
+    const float* x, const float* x_companion, int x_act, float x_slope,
+    float* gw, float* gbias, void* stream);
+
+/* (dim0, dim1, taps) -> (dim1, dim0, taps) */
+int pmn_transpose_weight(
+    const float* w, float* wt, int dim0, int dim1, int taps, void* stream);
+
+/* Backward of pmn_weight_norm_fold (model/core.py:43-45): gv (dim0, inner), gg (dim0) written */
+int pmn_weight_norm_backward(
+    const float* v, const float* g, const float* gw, float* gv, float* gg, int dim0, int inner,
+    void* stream);
+
+/* torch.nn.functional.pad(x, (left, right), 'reflect') over rows of length t_in
+ * (discriminator.py:78-81) and its adjoint */
+int pmn_reflect_pad(
+    const float* x, float* out, int rows, int t_in, int left, int right, void* stream);
+int pmn_reflect_pad_backward(
+    const float* gout, float* gx, int rows, int t_in, int left, int right, int accumulate,
+    void* stream);
+
+/* y = a x + b y (x may be NULL: y = b y) */
+int pmn_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
+
+/* LSGAN terms, promonet/train/loss.py:29-53: *loss += weight * mean((x - target)^2),
+ * grad = d/dx (written; may be NULL) */
+int pmn_mse_to_target(
+    const float* x, int64_t n, float target, float weight, float* loss, float* grad, void* stream);
+/* Feature matching / L1, loss.py:11-26: *loss += weight * mean|fake - real|,
+ * gfake (+)= d/dfake (may be NULL) */
+int pmn_l1_mean(
+    const float* fake, const float* real, int64_t n, float weight, float* loss, float* gfake,
+    int accumulate, void* stream);
+
+/* torch.optim.AdamW step over a flat parameter buffer (train/core.py:63-64,256,366;
+ * config/defaults.py:390-394); grad is multiplied by grad_scale first (1 / world size) */
+int pmn_adamw(
+    float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+    void* stream);
+
+/* out[r] (+)= sum_c x[r, c] */
+int pmn_row_sum(const float* x, float* out, int rows, int cols, int accumulate, void* stream);
+
+/* Generator.prepare_features (generator.py:137-197) with explicit tables, for training where
+ * pitch_embedding is a parameter: -> features (B, 113, F) */
+int pmn_features(
+    const float* loudness, int loudness_rows, const float* pitch, const float* periodicity,
+    const float* ppg, const float* pitch_distribution, const float* pitch_embedding,
+    float ppg_threshold, float* features, int batch, int frames, void* stream);
+/* bins (B, F) int64 = clip(searchsorted(edges, clip(pitch, fmin, fmax)), 0, n - 1), generator.py:153-157 */
+int pmn_pitch_bins(
+    const float* pitch, const float* edges, int64_t* bins, int n, int num_edges,
+    float fmin, float fmax, void* stream);
+/* gtable[index[b, f], e] += gout[b, channel_offset + e, f]: backward of an embedding lookup
+ * whose rows were written to channels [channel_offset, channel_offset + channels) of
+ * gout (B, out_channels, F) */
+int pmn_embedding_backward(
+    const float* gout, const int64_t* index, float* gtable, int batch, int channels, int frames,
+    int rows, int out_channels, int channel_offset, void* stream);
+/* prepare_global_features (generator.py:49-70): out (B, speaker_channels + 2) */
+int pmn_global_features(
+    const float* speaker_embedding, const int64_t* speakers, const float* spectral_balance_ratios,
+    const float* loudness_ratios, float* out, int batch, int speaker_channels, int num_speakers,
+    void* stream);
+
+/* Differentiable STFT magnitude over audio (B, T): reflect pad 384, 1024-point frames, hop 256.
+ *   window_kind 0 = periodic hann (preprocess/spectrogram.py:36-52, eps 1e-6),
+ *               1 = rectangular (discriminator.py:175-195, eps 0)
+ *   layout 0: magnitude (B, 513, F); 1: (B, F, 513) (the CMB discriminator's (B, 1, F, 513))
+ *   spectrum (B, F, 513, 2) complex, kept for the backward; either output may be NULL */
+int pmn_stft_magnitude(
+    const float* audio, int batch, int samples, int window_kind, float eps, int layout,
+    float* spectrum, float* magnitude, void* stream);
+int pmn_stft_magnitude_backward(
+    const float* gmagnitude, const float* spectrum, int batch, int samples, int window_kind,
+    float eps, int layout, float* gaudio, int accumulate, void* stream);
+/* Mel loss (train/core.py:277-305): *loss += weight * mean|log(mel_basis @ magnitude) - target|;
+ * magnitude (B, 513, F), target_mels (B, 80, F), gmagnitude (B, 513, F) written (may be NULL) */
+int pmn_mel_loss(
+    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
+    float* loss, float* gmagnitude, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,7 +107,58 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
          c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
+    # ---- training-step operators ----
+    'pmn_conv_gemm': (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+         c_int, c_float, c_void_p, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    'pmn_conv_wgrad': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,
+         c_void_p, c_void_p, c_void_p]),
+    'pmn_transpose_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_weight_norm_backward': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'pmn_reflect_pad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'pmn_reflect_pad_backward': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'pmn_axpby': (c_int, [c_float, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
+    'pmn_mse_to_target': (
+        c_int, [c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    'pmn_l1_mean': (
+        c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    'pmn_adamw': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+         c_float, c_int, c_float, c_void_p]),
+    'pmn_row_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_features': (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+         c_void_p, c_int, c_int, c_void_p]),
+    'pmn_pitch_bins': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    'pmn_embedding_backward': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'pmn_global_features': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_stft_magnitude': (
+        c_int, [c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    'pmn_stft_magnitude_backward': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p]),
+    'pmn_mel_loss': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
+
+
+class ConvGeometry(ctypes.Structure):
+    """pmn_conv_geometry"""
+    _fields_ = [(name, c_int) for name in (
+        'batch', 'c_in', 'c_out', 'h_in', 'w_in', 'h_out', 'w_out',
+        'kh', 'kw', 'sh', 'sw', 'dh', 'dw', 'ph', 'pw')]
+
 
 _library = None
 

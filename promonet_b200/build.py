@@ -19,8 +19,8 @@ STAMP = ROOT / 'lib' / 'libpromonet_b200.stamp'
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo', '-O3', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-shared',
-    '-lcuda']
+    '-Xcompiler', '-fPIC']
+OBJECTS = ROOT / 'lib' / 'obj'
 
 
 def nvcc():
@@ -30,13 +30,26 @@ def nvcc():
     return path
 
 
-def digest():
+def header_digest():
     sha = hashlib.sha256()
-    for file in SOURCES + HEADERS:
+    for file in HEADERS:
         sha.update(file.name.encode())
         sha.update(file.read_bytes())
     sha.update(' '.join(NVCC_FLAGS).encode())
+    return sha
+
+
+def source_digest(source, headers=None):
+    sha = (headers or header_digest()).copy()
+    sha.update(source.name.encode())
+    sha.update(source.read_bytes())
     return sha.hexdigest()
+
+
+def digest():
+    headers = header_digest()
+    return hashlib.sha256(
+        ''.join(source_digest(s, headers) for s in SOURCES).encode()).hexdigest()
 
 
 def is_current():
@@ -46,20 +59,45 @@ def is_current():
         STAMP.read_text().strip() == digest())
 
 
-def build(force=False, verbose=False):
-    """Compile every kernel into one shared library; returns its path"""
-    if not force and is_current():
-        return LIBRARY
-    LIBRARY.parent.mkdir(exist_ok=True)
-    command = [nvcc(), *NVCC_FLAGS, '-o', str(LIBRARY)] + [str(s) for s in SOURCES]
+def compile_one(source, verbose=False):
+    """source.cu -> lib/obj/source.o unless an object of the same digest exists"""
+    obj = OBJECTS / (source.stem + '.o')
+    stamp = OBJECTS / (source.stem + '.stamp')
+    wanted = source_digest(source)
+    if obj.exists() and stamp.exists() and stamp.read_text().strip() == wanted:
+        return obj, ''
+    command = [nvcc(), *NVCC_FLAGS, '-c', '-o', str(obj), str(source)]
     if verbose:
         command.insert(1, '-Xptxas=-v')
     result = subprocess.run(command, capture_output=True, text=True)
     if result.returncode:
         raise RuntimeError(
             'nvcc failed:\n' + ' '.join(command) + '\n' + result.stdout + result.stderr)
+    stamp.write_text(wanted)
+    return obj, result.stderr
+
+
+def build(force=False, verbose=False):
+    """Compile every kernel (one object per source, in parallel) and link them
+    into one shared library; returns its path"""
+    if not force and is_current():
+        return LIBRARY
+    from concurrent.futures import ThreadPoolExecutor
+    OBJECTS.mkdir(parents=True, exist_ok=True)
+    if force:
+        for stamp in OBJECTS.glob('*.stamp'):
+            stamp.unlink()
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(lambda s: compile_one(s, verbose), SOURCES))
+    command = [
+        nvcc(), '-shared', '-o', str(LIBRARY), *[str(obj) for obj, _ in results],
+        '-lcuda']
+    result = subprocess.run(command, capture_output=True, text=True)
+    if result.returncode:
+        raise RuntimeError(
+            'link failed:\n' + ' '.join(command) + '\n' + result.stdout + result.stderr)
     if verbose:
-        print(result.stderr)
+        print('\n'.join(log for _, log in results))
     STAMP.write_text(digest())
     return LIBRARY
 

@@ -32,13 +32,7 @@ constexpr int kThreads = 256;
 constexpr float kMinDb = -100.f;  // MIN_DB :37
 constexpr double kSampleRate = 22050.;
 
-struct Tables {
-    float* window = nullptr;       // (1024) periodic hann
-    float2* twiddle = nullptr;     // (512) exp(-2 pi i k / 1024)
-    float* mel_weights = nullptr;  // (80, 513) Slaney basis
-    int* mel_range = nullptr;      // (80, 2) first / one-past-last nonzero bin
-    float* a_weights = nullptr;    // (513) A-weighting(f_k) - REF_DB
-};
+using Tables = SpectralTables;
 
 std::mutex g_tables_mutex;
 std::vector<Tables> g_tables(64);
@@ -109,6 +103,12 @@ int tables(const Tables** out) {
     *out = &t;
     return PMN_OK;
 }
+
+}  // namespace
+
+int spectral_tables(const SpectralTables** out) { return tables(out); }
+
+namespace {
 
 // Order-preserving float <-> int map for atomicMax on floats of either sign
 __device__ __forceinline__ int float_key(float v) {

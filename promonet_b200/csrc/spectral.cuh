@@ -5,6 +5,16 @@
 
 namespace pmn {
 
+// Device tables shared by the STFT kernels, built once per device
+struct SpectralTables {
+    float* window = nullptr;       // (1024) periodic hann
+    float2* twiddle = nullptr;     // (512) exp(-2 pi i k / 1024)
+    float* mel_weights = nullptr;  // (80, 513) Slaney basis
+    int* mel_range = nullptr;      // (80, 2) first / one-past-last nonzero bin
+    float* a_weights = nullptr;    // (513) A-weighting(f_k) - REF_DB
+};
+int spectral_tables(const SpectralTables** out);
+
 int spectral_frames(int samples);
 size_t spectral_workspace_bytes(int batch, int samples);
 int launch_spectral_features(

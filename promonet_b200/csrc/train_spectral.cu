@@ -1,0 +1,213 @@
+// Differentiable STFT magnitude and the mel loss of the training step.
+//
+//   mel loss        promonet/train/core.py:277-305: L1(log(M @ |STFT(y)|), log(M @ S)) * 45 with
+//                   |X| = sqrt(re^2 + im^2 + 1e-6), hann 1024 / hop 256, reflect pad 384
+//                   (promonet/preprocess/spectrogram.py:15-60,111-135)
+//   CMB spectrogram promonet/model/discriminator.py:175-195: the same framing with no
+//                   window (rectangular) and |X| = sqrt(re^2 + im^2), laid out (B, 1, F, 513)
+//
+// Forward keeps the complex spectrum; backward turns dL/d|X| into dL/dX = g X / |X|,
+// runs one more 1024-point transform per frame (the adjoint of the one-sided DFT is
+// the real part of a DFT of the conjugated, zero-extended gradient) and scatters the
+// windowed result back through the overlap and the reflect padding.
+#include "spectral.cuh"
+#include "train.cuh"
+
+namespace pmn {
+
+namespace {
+
+constexpr int kFft = 1024;
+constexpr int kHop = 256;
+constexpr int kBins = kFft / 2 + 1;
+constexpr int kMels = 80;
+constexpr int kPad = (kFft - kHop) / 2;
+constexpr int kThreads = 256;
+
+// In-place-pair Stockham radix-2 over buffer[2][1024]; returns which half holds the result
+__device__ __forceinline__ int fft1024(float2 (*buffer)[kFft], const float2* twiddle, int tid) {
+    int source = 0;
+#pragma unroll 1
+    for (int half = 1; half < kFft; half <<= 1) {
+        __syncthreads();
+        const int stride = kFft / (2 * half);
+        for (int j = tid; j < kFft / 2; j += kThreads) {
+            const int k = j & (half - 1);
+            const int group = j / half;
+            const float2 a = buffer[source][group * half + k];
+            const float2 c = buffer[source][group * half + k + kFft / 2];
+            const float2 w = twiddle[k * stride];
+            const float2 wc = make_float2(w.x * c.x - w.y * c.y, w.x * c.y + w.y * c.x);
+            buffer[source ^ 1][2 * group * half + k] = make_float2(a.x + wc.x, a.y + wc.y);
+            buffer[source ^ 1][2 * group * half + k + half] = make_float2(a.x - wc.x, a.y - wc.y);
+        }
+        source ^= 1;
+    }
+    __syncthreads();
+    return source;
+}
+
+__device__ __forceinline__ int reflect_index(int i, int samples) {
+    if (i < 0) i = -i;
+    if (i >= samples) i = 2 * (samples - 1) - i;
+    return min(max(i, 0), samples - 1);
+}
+
+// One frame per CTA.  magnitude layout: 0 -> (B, 513, F), 1 -> (B, F, 513)
+__global__ void __launch_bounds__(kThreads) stft_train_kernel(
+    const float* __restrict__ audio, int samples, int frames, SpectralTables t, int window_kind,
+    float eps, int layout, float2* __restrict__ spectrum, float* __restrict__ magnitude) {
+    __shared__ float2 buffer[2][kFft];
+    __shared__ float2 twiddle[kFft / 2];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x, b = blockIdx.y;
+    const float* x = audio + (size_t)b * samples;
+    for (int k = tid; k < kFft / 2; k += kThreads) twiddle[k] = t.twiddle[k];
+    for (int n = tid; n < kFft; n += kThreads) {
+        const int i = reflect_index(f * kHop - kPad + n, samples);
+        const float w = window_kind == 0 ? t.window[n] : 1.f;
+        buffer[0][n] = make_float2(x[i] * w, 0.f);
+    }
+    const int source = fft1024(buffer, twiddle, tid);
+    for (int k = tid; k < kBins; k += kThreads) {
+        const float2 v = buffer[source][k];
+        if (spectrum) spectrum[((size_t)b * frames + f) * kBins + k] = v;
+        const float mag = sqrtf(v.x * v.x + v.y * v.y + eps);
+        if (magnitude) {
+            const size_t idx = layout == 0 ? ((size_t)b * kBins + k) * frames + f
+                                           : ((size_t)b * frames + f) * kBins + k;
+            magnitude[idx] = mag;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) stft_train_backward_kernel(
+    const float* __restrict__ gmagnitude, const float2* __restrict__ spectrum, int samples,
+    int frames, SpectralTables t, int window_kind, float eps, int layout,
+    float* __restrict__ gaudio) {
+    __shared__ float2 buffer[2][kFft];
+    __shared__ float2 twiddle[kFft / 2];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x, b = blockIdx.y;
+    for (int k = tid; k < kFft / 2; k += kThreads) twiddle[k] = t.twiddle[k];
+    for (int k = tid; k < kFft; k += kThreads) {
+        float2 value = make_float2(0.f, 0.f);
+        if (k < kBins) {
+            const float2 v = spectrum[((size_t)b * frames + f) * kBins + k];
+            const size_t idx = layout == 0 ? ((size_t)b * kBins + k) * frames + f
+                                           : ((size_t)b * frames + f) * kBins + k;
+            const float mag = sqrtf(v.x * v.x + v.y * v.y + eps);
+            // torch.norm's subgradient at 0 is 0
+            const float scale = mag > 0.f ? gmagnitude[idx] / mag : 0.f;
+            value = make_float2(scale * v.x, -scale * v.y);  // conj(dL/dX)
+        }
+        buffer[0][k] = value;
+    }
+    const int source = fft1024(buffer, twiddle, tid);
+    float* gx = gaudio + (size_t)b * samples;
+    for (int n = tid; n < kFft; n += kThreads) {
+        const float w = window_kind == 0 ? t.window[n] : 1.f;
+        const float v = buffer[source][n].x * w;
+        const int i = reflect_index(f * kHop - kPad + n, samples);
+        if (v != 0.f) atomicAdd(gx + i, v);
+    }
+}
+
+// loss += weight * mean|log(M @ mag) - target|, gmagnitude = dloss / dmag   (one frame per CTA)
+__global__ void __launch_bounds__(128) mel_loss_kernel(
+    const float* __restrict__ magnitude, const float* __restrict__ target, int frames, int batch,
+    SpectralTables t, float weight, float* __restrict__ loss, float* __restrict__ gmagnitude) {
+    __shared__ float mag[kBins];
+    __shared__ float gmel[kMels];
+    __shared__ float partial[4];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x, b = blockIdx.y;
+    const float* src = magnitude + (size_t)b * kBins * frames + f;
+    for (int k = tid; k < kBins; k += blockDim.x) mag[k] = src[(size_t)k * frames];
+    __syncthreads();
+    const float scale = weight / ((float)batch * kMels * frames);
+    float local = 0.f;
+    if (tid < kMels) {
+        const float* w = t.mel_weights + (size_t)tid * kBins;
+        float sum = 0.f;
+        for (int k = t.mel_range[2 * tid]; k < t.mel_range[2 * tid + 1]; ++k)
+            sum = fmaf(w[k], mag[k], sum);
+        const float d = logf(sum) - target[((size_t)b * kMels + tid) * frames + f];
+        local = fabsf(d) * scale;
+        const float sign = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        gmel[tid] = sign * scale / sum;
+    }
+    for (int offset = 16; offset > 0; offset >>= 1) local += __shfl_xor_sync(0xffffffffu, local, offset);
+    if ((tid & 31) == 0) partial[tid >> 5] = local;
+    __syncthreads();
+    if (tid == 0 && loss) atomicAdd(loss, partial[0] + partial[1] + partial[2] + partial[3]);
+    if (gmagnitude) {
+        float* dst = gmagnitude + (size_t)b * kBins * frames + f;
+        for (int k = tid; k < kBins; k += blockDim.x) {
+            float sum = 0.f;
+            for (int m = 0; m < kMels; ++m) {
+                if (k >= t.mel_range[2 * m] && k < t.mel_range[2 * m + 1])
+                    sum = fmaf(t.mel_weights[(size_t)m * kBins + k], gmel[m], sum);
+            }
+            dst[(size_t)k * frames] = sum;
+        }
+    }
+}
+
+}  // namespace
+
+size_t stft_train_frames(int samples) { return (size_t)(samples / kHop); }
+
+int launch_stft_train(
+    const float* audio, int batch, int samples, int window_kind, float eps, int layout,
+    float* spectrum, float* magnitude, cudaStream_t stream) {
+    PMN_REQUIRE(audio && batch > 0 && batch <= 65535, "stft_train: bad argument");
+    PMN_REQUIRE(samples > kPad && samples >= kHop, "stft_train: audio too short");
+    PMN_REQUIRE(spectrum || magnitude, "stft_train: no output");
+    const int frames = samples / kHop;
+    const SpectralTables* t;
+    PMN_TRY(spectral_tables(&t));
+    dim3 grid(frames, batch);
+    LaunchScope scope("stft_train_kernel", stream);
+    stft_train_kernel<<<grid, kThreads, 0, stream>>>(
+        audio, samples, frames, *t, window_kind, eps, layout,
+        reinterpret_cast<float2*>(spectrum), magnitude);
+    return launched("stft_train_kernel");
+}
+
+int launch_stft_train_backward(
+    const float* gmagnitude, const float* spectrum, int batch, int samples, int window_kind,
+    float eps, int layout, float* gaudio, int accumulate, cudaStream_t stream) {
+    PMN_REQUIRE(gmagnitude && spectrum && gaudio && batch > 0 && batch <= 65535,
+                "stft_train_backward: bad argument");
+    PMN_REQUIRE(samples > kPad && samples >= kHop, "stft_train_backward: audio too short");
+    const int frames = samples / kHop;
+    const SpectralTables* t;
+    PMN_TRY(spectral_tables(&t));
+    if (!accumulate)
+        PMN_TRY(check_cuda(
+            cudaMemsetAsync(gaudio, 0, (size_t)batch * samples * sizeof(float), stream),
+            "stft_train_backward memset"));
+    dim3 grid(frames, batch);
+    LaunchScope scope("stft_train_backward_kernel", stream);
+    stft_train_backward_kernel<<<grid, kThreads, 0, stream>>>(
+        gmagnitude, reinterpret_cast<const float2*>(spectrum), samples, frames, *t, window_kind,
+        eps, layout, gaudio);
+    return launched("stft_train_backward_kernel");
+}
+
+int launch_mel_loss(
+    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
+    float* loss, float* gmagnitude, cudaStream_t stream) {
+    PMN_REQUIRE(magnitude && target_mels && (loss || gmagnitude) && batch > 0 && batch <= 65535 &&
+                frames > 0, "mel_loss: bad argument");
+    const SpectralTables* t;
+    PMN_TRY(spectral_tables(&t));
+    dim3 grid(frames, batch);
+    LaunchScope scope("mel_loss_kernel", stream);
+    mel_loss_kernel<<<grid, 128, 0, stream>>>(
+        magnitude, target_mels, frames, batch, *t, weight, loss, gmagnitude);
+    return launched("mel_loss_kernel");
+}
+
+}  // namespace pmn

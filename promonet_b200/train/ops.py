@@ -1,0 +1,202 @@
+"""Tensor-level wrappers of the training-step operators of libpromonet_b200
+(include/promonet_b200.h, "Training step").  Every function launches CUDA
+kernels on the current stream; torch only owns the memory."""
+import ctypes
+
+import torch
+
+from promonet_b200 import _lib
+from promonet_b200._lib import ConvGeometry
+
+ACT_NONE, ACT_LRELU, ACT_LRELU_MASK, ACT_TANH_MASK = 0, 1, 2, 3
+OUT_NONE, OUT_LRELU, OUT_TANH = 0, 1, 2
+
+
+def _pair(value):
+    return tuple(value) if isinstance(value, (tuple, list)) else (value, value)
+
+
+def geometry(batch, c_in, c_out, size_in, kernel, stride=1, dilation=1, padding=0,
+             size_out=None):
+    """pmn_conv_geometry of a forward convolution; sizes are (H, W)"""
+    (h_in, w_in), (kh, kw) = _pair(size_in), _pair(kernel)
+    (sh, sw), (dh, dw), (ph, pw) = _pair(stride), _pair(dilation), _pair(padding)
+    if size_out is None:
+        h_out = (h_in + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+        w_out = (w_in + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    else:
+        h_out, w_out = _pair(size_out)
+    return ConvGeometry(
+        batch, c_in, c_out, h_in, w_in, h_out, w_out, kh, kw, sh, sw, dh, dw, ph, pw)
+
+
+def _check(status):
+    _lib.check(status)
+
+
+def conv_gemm(geom, transposed, a, wmat, out, a_companion=None, a_act=ACT_NONE, a_slope=1.,
+              bias=None, bias2=None, out_act=OUT_NONE, out_slope=1., mask_src=None,
+              mask_slope=1., residual=None, alpha=1., accumulate=False):
+    _check(_lib.library().pmn_conv_gemm(
+        ctypes.byref(geom), int(transposed), _lib.ptr(a), _lib.ptr(a_companion), a_act, a_slope,
+        _lib.ptr(wmat), _lib.ptr(bias), _lib.ptr(bias2), out_act, out_slope,
+        _lib.ptr(mask_src), mask_slope, _lib.ptr(residual), alpha, int(accumulate),
+        _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def conv_wgrad(geom, dy, x, gw, gbias=None, dy_companion=None, dy_act=ACT_NONE, dy_slope=1.,
+               x_companion=None, x_act=ACT_NONE, x_slope=1.):
+    _check(_lib.library().pmn_conv_wgrad(
+        ctypes.byref(geom), _lib.ptr(dy), _lib.ptr(dy_companion), dy_act, dy_slope,
+        _lib.ptr(x), _lib.ptr(x_companion), x_act, x_slope, _lib.ptr(gw), _lib.ptr(gbias),
+        _lib.stream()))
+
+
+def transpose_weight(w, wt, dim0, dim1, taps):
+    _check(_lib.library().pmn_transpose_weight(
+        _lib.ptr(w), _lib.ptr(wt), dim0, dim1, taps, _lib.stream()))
+    return wt
+
+
+def weight_norm_fold(v, g, w, dim0, inner):
+    _check(_lib.library().pmn_weight_norm_fold(
+        _lib.ptr(v), _lib.ptr(g), _lib.ptr(w), dim0, inner, _lib.stream()))
+    return w
+
+
+def weight_norm_backward(v, g, gw, gv, gg, dim0, inner):
+    _check(_lib.library().pmn_weight_norm_backward(
+        _lib.ptr(v), _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gv), _lib.ptr(gg), dim0, inner,
+        _lib.stream()))
+
+
+def reflect_pad(x, left, right):
+    """x (..., T) -> (..., left + T + right)"""
+    t_in = x.shape[-1]
+    rows = x.numel() // t_in
+    out = torch.empty(*x.shape[:-1], left + t_in + right, device=x.device, dtype=x.dtype)
+    _check(_lib.library().pmn_reflect_pad(
+        _lib.ptr(x), _lib.ptr(out), rows, t_in, left, right, _lib.stream()))
+    return out
+
+
+def reflect_pad_backward(gout, gx, left, right, accumulate=False):
+    t_in = gx.shape[-1]
+    rows = gx.numel() // t_in
+    _check(_lib.library().pmn_reflect_pad_backward(
+        _lib.ptr(gout), _lib.ptr(gx), rows, t_in, left, right, int(accumulate), _lib.stream()))
+    return gx
+
+
+def axpby(a, x, b, y):
+    _check(_lib.library().pmn_axpby(a, _lib.ptr(x), b, _lib.ptr(y), y.numel(), _lib.stream()))
+    return y
+
+
+def mse_to_target(x, target, weight, loss, grad=None):
+    _check(_lib.library().pmn_mse_to_target(
+        _lib.ptr(x), x.numel(), target, weight, _lib.ptr(loss), _lib.ptr(grad), _lib.stream()))
+
+
+def l1_mean(fake, real, weight, loss, gfake=None, accumulate=False):
+    _check(_lib.library().pmn_l1_mean(
+        _lib.ptr(fake), _lib.ptr(real), fake.numel(), weight, _lib.ptr(loss), _lib.ptr(gfake),
+        int(accumulate), _lib.stream()))
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.):
+    _check(_lib.library().pmn_adamw(
+        _lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), param.numel(),
+        lr, betas[0], betas[1], eps, weight_decay, step, grad_scale, _lib.stream()))
+
+
+def row_sum(x, out, rows, cols, accumulate=False):
+    _check(_lib.library().pmn_row_sum(
+        _lib.ptr(x), _lib.ptr(out), rows, cols, int(accumulate), _lib.stream()))
+    return out
+
+
+def features(loudness, pitch, periodicity, ppg, pitch_distribution, pitch_embedding, threshold):
+    batch, rows, frames = loudness.shape
+    out = torch.empty(batch, 113, frames, device=loudness.device)
+    _check(_lib.library().pmn_features(
+        _lib.ptr(loudness), rows, _lib.ptr(pitch), _lib.ptr(periodicity), _lib.ptr(ppg),
+        _lib.ptr(pitch_distribution), _lib.ptr(pitch_embedding), threshold, _lib.ptr(out),
+        batch, frames, _lib.stream()))
+    return out
+
+
+def pitch_bins(pitch, edges, fmin, fmax):
+    bins = torch.empty(pitch.shape, dtype=torch.int64, device=pitch.device)
+    _check(_lib.library().pmn_pitch_bins(
+        _lib.ptr(pitch), _lib.ptr(edges), _lib.ptr(bins), pitch.numel(), edges.numel(),
+        fmin, fmax, _lib.stream()))
+    return bins
+
+
+def embedding_backward(gout, index, gtable, channel_offset=0):
+    """gtable[index[b, f]] += gout[b, offset:offset + channels, f]"""
+    batch, out_channels, frames = gout.shape
+    rows, channels = gtable.shape
+    _check(_lib.library().pmn_embedding_backward(
+        _lib.ptr(gout), _lib.ptr(index), _lib.ptr(gtable), batch, channels, frames, rows,
+        out_channels, channel_offset, _lib.stream()))
+
+
+def global_features(speaker_embedding, speakers, sbr, lr):
+    num_speakers, channels = speaker_embedding.shape
+    out = torch.empty(speakers.shape[0], channels + 2, device=speaker_embedding.device)
+    _check(_lib.library().pmn_global_features(
+        _lib.ptr(speaker_embedding), _lib.ptr(speakers), _lib.ptr(sbr), _lib.ptr(lr),
+        _lib.ptr(out), speakers.shape[0], channels, num_speakers, _lib.stream()))
+    return out
+
+
+def stft_magnitude(audio, window='hann', eps=1e-6, layout=0, want_spectrum=True):
+    """audio (B, T) -> magnitude ((B, 513, F) or (B, F, 513)), spectrum (B, F, 513, 2)"""
+    batch, samples = audio.shape
+    frames = samples // 256
+    shape = (batch, 513, frames) if layout == 0 else (batch, frames, 513)
+    magnitude = torch.empty(shape, device=audio.device)
+    spectrum = torch.empty(batch, frames, 513, 2, device=audio.device) if want_spectrum else None
+    _check(_lib.library().pmn_stft_magnitude(
+        _lib.ptr(audio), batch, samples, 0 if window == 'hann' else 1, eps, layout,
+        _lib.ptr(spectrum), _lib.ptr(magnitude), _lib.stream()))
+    return magnitude, spectrum
+
+
+def stft_magnitude_backward(gmagnitude, spectrum, gaudio, window='hann', eps=1e-6, layout=0,
+                            accumulate=False):
+    batch, samples = gaudio.shape
+    _check(_lib.library().pmn_stft_magnitude_backward(
+        _lib.ptr(gmagnitude), _lib.ptr(spectrum), batch, samples,
+        0 if window == 'hann' else 1, eps, layout, _lib.ptr(gaudio), int(accumulate),
+        _lib.stream()))
+    return gaudio
+
+
+def mel_loss(magnitude, target_mels, weight, loss, gmagnitude=None):
+    batch, _, frames = magnitude.shape
+    _check(_lib.library().pmn_mel_loss(
+        _lib.ptr(magnitude), _lib.ptr(target_mels), batch, frames, weight, _lib.ptr(loss),
+        _lib.ptr(gmagnitude), _lib.stream()))
+
+
+def linear_to_mel(magnitude, floor=float('-inf')):
+    batch, _, frames = magnitude.shape
+    mels = torch.empty(batch, 80, frames, device=magnitude.device)
+    _check(_lib.library().pmn_linear_to_mel(
+        _lib.ptr(magnitude), _lib.ptr(mels), floor, batch, frames, _lib.stream()))
+    return mels
+
+
+def conv_transpose1d(x, weight, bias, stride, in_slope):
+    """LeakyReLU + ConvTranspose1d (kernel 2 * stride, padding stride / 2), hifigan.py:97-106"""
+    batch, c_in, t_in = x.shape
+    _, c_out, k = weight.shape
+    out = torch.empty(batch, c_out, t_in * stride, device=x.device)
+    _check(_lib.library().pmn_conv_transpose1d(
+        _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(out), batch, c_in, c_out, t_in,
+        k, stride, in_slope, _lib.stream()))
+    return out

@@ -1,0 +1,292 @@
+"""Training-step operators (C ABI, include/promonet_b200.h "Training step") against
+plain PyTorch fp32/fp64 references of the same op on the CPU.  Tolerance 1e-4
+relative to max|reference| unless stated (fp32 accumulation order differs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relative_error
+
+pytestmark = pytest.mark.gpu
+
+TOLERANCE = 1e-4
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from promonet_b200.train import ops
+    return ops
+
+
+# (c_in, c_out, size_in, kernel, stride, dilation, padding): the shapes of the hot path
+CONVS = [
+    # HiFi-GAN dilated Conv1d as (k, 1) over (T, 1): hifigan.py:167-183
+    (32, 32, (700, 1), (11, 1), 1, (5, 1), (25, 0)),
+    (64, 64, (300, 1), (7, 1), 1, (3, 1), (9, 0)),
+    (113, 512, (64, 1), (7, 1), 1, 1, (3, 0)),
+    (32, 1, (900, 1), (7, 1), 1, 1, (3, 0)),
+    # MPD Conv2d (5, 1) stride (3, 1): discriminator.py:67-72
+    (1, 32, (301, 3), (5, 1), (3, 1), 1, (2, 0)),
+    (32, 128, (101, 5), (5, 1), (3, 1), 1, (2, 0)),
+    (128, 96, (34, 2), (5, 1), 1, 1, (2, 0)),
+    (96, 1, (34, 7), (3, 1), 1, 1, (1, 0)),
+    # CMB Conv2d (3, 9), stride (1, 2): discriminator.py:160-170
+    (1, 32, (16, 77), (3, 9), (1, 1), 1, (1, 4)),
+    (32, 32, (16, 51), (3, 9), (1, 2), 1, (1, 4)),
+    (32, 1, (16, 40), (3, 3), 1, 1, (1, 1)),
+    # strided Conv1d: the data gradient of the upsampling ConvTranspose1d
+    (16, 24, (96, 1), (16, 1), (8, 1), 1, (4, 0)),
+]
+
+
+@pytest.mark.parametrize('c_in,c_out,size,kernel,stride,dilation,padding', CONVS)
+def test_conv_forward_dgrad_wgrad(ops, c_in, c_out, size, kernel, stride, dilation, padding):
+    torch.manual_seed(0)
+    batch = 3
+    x = torch.randn(batch, c_in, *size)
+    w = torch.randn(c_out, c_in, *kernel) / (c_in * kernel[0] * kernel[1]) ** .5
+    bias = torch.randn(c_out)
+    residual_slope, out_slope = .1, .2
+
+    # reference: y = lrelu_out(conv(lrelu_in(x)) + bias), loss = <y, dy>
+    xr = x.double().requires_grad_()
+    wr = w.double().requires_grad_()
+    br = bias.double().requires_grad_()
+    y = F.leaky_relu(
+        F.conv2d(F.leaky_relu(xr, residual_slope), wr, br, stride, padding, dilation), out_slope)
+    dy = torch.randn(y.shape)
+    (y * dy.double()).sum().backward()
+
+    geom = ops.geometry(batch, c_in, c_out, size, kernel, stride, dilation, padding)
+    assert (geom.h_out, geom.w_out) == tuple(y.shape[2:])
+    xd, wd, bd, dyd = (t.cuda().contiguous() for t in (x, w, bias, dy))
+    out = torch.empty(y.shape, device='cuda')
+    ops.conv_gemm(geom, False, xd, wd, out, a_act=ops.ACT_LRELU, a_slope=residual_slope,
+                  bias=bd, out_act=ops.OUT_LRELU, out_slope=out_slope)
+    assert relative_error(out, y) < TOLERANCE
+
+    taps = kernel[0] * kernel[1]
+    wt = ops.transpose_weight(wd, torch.empty(c_in, c_out, *kernel, device='cuda'), c_out, c_in, taps)
+    assert torch.equal(wt.cpu(), w.transpose(0, 1).contiguous())
+    dx = torch.empty(x.shape, device='cuda')
+    ops.conv_gemm(geom, True, dyd, wt, dx, a_companion=out, a_act=ops.ACT_LRELU_MASK,
+                  a_slope=out_slope, mask_src=xd, mask_slope=residual_slope)
+    assert relative_error(dx, xr.grad) < TOLERANCE
+
+    gw = torch.zeros(w.shape, device='cuda')
+    gb = torch.zeros(c_out, device='cuda')
+    ops.conv_wgrad(geom, dyd, xd, gw, gb, dy_companion=out, dy_act=ops.ACT_LRELU_MASK,
+                   dy_slope=out_slope, x_act=ops.ACT_LRELU, x_slope=residual_slope)
+    assert relative_error(gw, wr.grad) < TOLERANCE
+    assert relative_error(gb, br.grad) < TOLERANCE
+
+
+def test_conv_epilogue_residual_alpha_accumulate_tanh(ops):
+    torch.manual_seed(1)
+    x = torch.randn(2, 24, 130, 1)
+    w = torch.randn(24, 24, 3, 1) / 8
+    bias2 = torch.randn(2, 24)
+    residual = torch.randn(2, 24, 130, 1)
+    previous = torch.randn(2, 24, 130, 1)
+    geom = ops.geometry(2, 24, 24, (130, 1), (3, 1), 1, 1, (1, 0))
+    out = previous.cuda().clone()
+    ops.conv_gemm(geom, False, x.cuda(), w.cuda(), out, bias2=bias2.cuda(),
+                  residual=residual.cuda(), alpha=1 / 3, accumulate=True)
+    expected = previous + (F.conv2d(x, w, None, 1, (1, 0)) + bias2[:, :, None, None] + residual) / 3
+    assert relative_error(out, expected) < TOLERANCE
+
+    out = torch.empty(2, 24, 130, 1, device='cuda')
+    ops.conv_gemm(geom, False, x.cuda(), w.cuda(), out, out_act=ops.OUT_TANH)
+    y = torch.tanh(F.conv2d(x, w, None, 1, (1, 0)))
+    assert relative_error(out, y) < TOLERANCE
+    # tanh mask on the gradient operand
+    dy = torch.randn(y.shape)
+    gw = torch.zeros(w.shape, device='cuda')
+    ops.conv_wgrad(geom, dy.cuda(), x.cuda(), gw, None, dy_companion=out, dy_act=ops.ACT_TANH_MASK)
+    wr = w.double().requires_grad_()
+    (torch.tanh(F.conv2d(x.double(), wr, None, 1, (1, 0))) * dy.double()).sum().backward()
+    assert relative_error(gw, wr.grad) < TOLERANCE
+
+
+@pytest.mark.parametrize('c_in,c_out,k,stride,t', [(64, 32, 16, 8, 40), (32, 16, 4, 2, 300)])
+def test_conv_transpose_forward_and_gradients(ops, c_in, c_out, k, stride, t):
+    """LeakyReLU + ConvTranspose1d (hifigan.py:97-106): forward through the transposed
+    gather, data gradient as a strided convolution, weight gradient with exchanged roles"""
+    torch.manual_seed(2)
+    batch, pad, slope = 2, (k - stride) // 2, .1
+    x = torch.randn(batch, c_in, t)
+    w = torch.randn(c_in, c_out, k) / (c_in * k / stride) ** .5
+    bias = torch.randn(c_out)
+    xr, wr, br = (v.double().requires_grad_() for v in (x, w, bias))
+    y = F.conv_transpose1d(F.leaky_relu(xr, slope), wr, br, stride, pad)
+    dy = torch.randn(y.shape)
+    (y * dy.double()).sum().backward()
+
+    # the convolution this transposes: C_out channels over s*T -> C_in channels over T
+    geom = ops.geometry(batch, c_out, c_in, (t * stride, 1), (k, 1), (stride, 1), 1, (pad, 0),
+                        size_out=(t, 1))
+    xd, wd, bd, dyd = (v.cuda().contiguous() for v in (x, w, bias, dy))
+    wt = ops.transpose_weight(wd, torch.empty(c_out, c_in, k, device='cuda'), c_in, c_out, k)
+    out = torch.empty(y.shape, device='cuda')
+    ops.conv_gemm(geom, True, xd, wt, out, a_act=ops.ACT_LRELU, a_slope=slope, bias=bd)
+    assert relative_error(out, y) < TOLERANCE
+    fast = ops.conv_transpose1d(xd, wd, bd, stride, slope)
+    assert relative_error(fast, y) < TOLERANCE
+
+    dx = torch.empty(x.shape, device='cuda')
+    ops.conv_gemm(geom, False, dyd, wd, dx, mask_src=xd, mask_slope=slope)
+    assert relative_error(dx, xr.grad) < TOLERANCE
+
+    gw = torch.zeros(w.shape, device='cuda')
+    ops.conv_wgrad(geom, xd, dyd, gw, None, dy_act=ops.ACT_LRELU, dy_slope=slope)
+    assert relative_error(gw, wr.grad) < TOLERANCE
+    gb = torch.empty(c_out, device='cuda')
+    ops.row_sum(dyd.transpose(0, 1).contiguous(), gb, c_out, batch * t * stride)
+    assert relative_error(gb, br.grad) < TOLERANCE
+
+
+def test_weight_norm_backward(ops):
+    torch.manual_seed(3)
+    v = torch.randn(48, 40 * 5)
+    g = torch.rand(48) + .5
+    gw = torch.randn(48, 40 * 5)
+    vr, gr = v.double().requires_grad_(), g.double().requires_grad_()
+    w = gr[:, None] * vr / vr.norm(dim=1, keepdim=True)
+    (w * gw.double()).sum().backward()
+    folded = ops.weight_norm_fold(v.cuda(), g.cuda(), torch.empty(48, 200, device='cuda'), 48, 200)
+    assert relative_error(folded, w) < 1e-6
+    gv, gg = torch.empty(48, 200, device='cuda'), torch.empty(48, device='cuda')
+    ops.weight_norm_backward(v.cuda(), g.cuda(), gw.cuda(), gv, gg, 48, 200)
+    assert relative_error(gv, vr.grad) < 1e-5
+    assert relative_error(gg, gr.grad) < 1e-5
+
+
+@pytest.mark.parametrize('t,left,right', [(16384, 0, 1), (16384, 0, 9), (700, 384, 384), (50, 0, 0)])
+def test_reflect_pad_and_adjoint(ops, t, left, right):
+    torch.manual_seed(4)
+    x = torch.randn(3, 2, t)
+    xr = x.double().requires_grad_()
+    y = F.pad(xr, (left, right), 'reflect')
+    out = ops.reflect_pad(x.cuda(), left, right)
+    assert torch.equal(out.cpu(), y.detach().float())
+    dy = torch.randn(y.shape)
+    (y * dy.double()).sum().backward()
+    gx = ops.reflect_pad_backward(dy.cuda(), torch.empty(x.shape, device='cuda'), left, right)
+    assert relative_error(gx, xr.grad) < 1e-6
+    gx = ops.reflect_pad_backward(dy.cuda(), torch.ones(x.shape, device='cuda'), left, right, True)
+    assert relative_error(gx, xr.grad + 1) < 1e-6
+
+
+def test_losses(ops):
+    torch.manual_seed(5)
+    x = torch.randn(4, 1000)
+    xr = x.double().requires_grad_()
+    loss = torch.zeros(1, device='cuda')
+    grad = torch.empty(x.shape, device='cuda')
+    ops.mse_to_target(x.cuda(), 1., 1., loss, grad)
+    expected = torch.mean((1. - xr) ** 2.)
+    expected.backward()
+    assert relative_error(loss, expected.reshape(1)) < 1e-5
+    assert relative_error(grad, xr.grad) < 1e-5
+    ops.mse_to_target(x.cuda(), 0., 2., loss)   # accumulates
+    assert relative_error(loss, (expected + 2 * torch.mean(xr ** 2.)).reshape(1)) < 1e-5
+
+    fake, real = torch.randn(3, 7, 500), torch.randn(3, 7, 500)
+    fr = fake.double().requires_grad_()
+    expected = 2.5 * torch.mean(torch.abs(real.double() - fr))
+    expected.backward()
+    loss.zero_()
+    gfake = torch.ones(fake.shape, device='cuda')
+    ops.l1_mean(fake.cuda(), real.cuda(), 2.5, loss, gfake, accumulate=True)
+    assert relative_error(loss, expected.reshape(1)) < 1e-5
+    assert relative_error(gfake, fr.grad + 1) < 1e-6
+
+
+def test_adamw_matches_torch(ops):
+    torch.manual_seed(6)
+    param = torch.nn.Parameter(torch.randn(5000))
+    # config/defaults.py:390-394
+    optimizer = torch.optim.AdamW([param], lr=2e-4, betas=(.8, .99), eps=1e-9)
+    p = param.detach().clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(5000)
+        param.grad = grad.clone()
+        optimizer.step()
+        ops.adamw(p, (grad * 4).cuda(), m, v, 2e-4, (.8, .99), 1e-9, .01, step, grad_scale=.25)
+        assert relative_error(p, param) < 1e-6
+
+
+def test_axpby_row_sum(ops):
+    torch.manual_seed(7)
+    x, y = torch.randn(1000), torch.randn(1000)
+    out = ops.axpby(2., x.cuda(), .5, y.cuda())
+    assert relative_error(out, 2 * x + .5 * y) < 1e-6
+    out = ops.axpby(2., x.cuda(), 0., torch.full((1000,), float('nan'), device='cuda'))
+    assert relative_error(out, 2 * x) < 1e-6
+    m = torch.randn(37, 300)
+    assert relative_error(ops.row_sum(m.cuda(), torch.empty(37, device='cuda'), 37, 300), m.sum(1)) < 1e-5
+
+
+def test_feature_assembly_backward_pieces(ops):
+    from promonet_b200.model import init
+    torch.manual_seed(8)
+    edges = init.pitch_distribution()
+    pitch = 40. + 600. * torch.rand(2, 50)
+    bins = ops.pitch_bins(pitch.cuda(), edges.cuda(), 50., 550.)
+    expected = torch.clip(torch.searchsorted(edges, torch.clip(pitch, 50., 550.)), 0, 255)
+    assert torch.equal(bins.cpu(), expected)
+    gout = torch.randn(2, 113, 50)
+    gtable = torch.zeros(256, 64, device='cuda')
+    ops.embedding_backward(gout.cuda(), bins, gtable, channel_offset=40)
+    table = torch.zeros(256, 64, dtype=torch.double, requires_grad=True)
+    (table[expected].permute(0, 2, 1) * gout[:, 40:104].double()).sum().backward()
+    assert relative_error(gtable, table.grad) < 1e-5
+
+    embedding = torch.randn(109, 256)
+    speakers = torch.tensor([3, 108])
+    sbr, lr = torch.rand(2), torch.rand(2)
+    g = ops.global_features(embedding.cuda(), speakers.cuda(), sbr.cuda(), lr.cuda())
+    assert torch.equal(g.cpu(), torch.cat([embedding[speakers], sbr[:, None], lr[:, None]], 1))
+
+
+@pytest.mark.parametrize('window,eps,layout', [('hann', 1e-6, 0), ('rect', 0., 1)])
+def test_stft_magnitude_and_backward(ops, window, eps, layout):
+    """preprocess/spectrogram.py:36-52 (hann) and discriminator.py:175-195 (no window)"""
+    torch.manual_seed(9)
+    audio = .3 * torch.randn(2, 4096)
+    ar = audio.double().requires_grad_()
+    padded = F.pad(ar[:, None], (384, 384), mode='reflect')[:, 0]
+    spec = torch.stft(
+        padded, 1024, 256, 1024, torch.hann_window(1024, dtype=torch.double) if window == 'hann' else None,
+        center=False, return_complex=True)
+    real = torch.view_as_real(spec)
+    mag = torch.sqrt(real.pow(2).sum(-1) + eps)
+    if layout == 1:
+        mag = mag.permute(0, 2, 1)
+    g = torch.randn(mag.shape)
+    (mag * g.double()).sum().backward()
+    magnitude, spectrum = ops.stft_magnitude(audio.cuda(), window, eps, layout)
+    assert relative_error(magnitude, mag) < TOLERANCE
+    gaudio = ops.stft_magnitude_backward(
+        g.cuda().contiguous(), spectrum, torch.empty(audio.shape, device='cuda'), window, eps, layout)
+    assert relative_error(gaudio, ar.grad) < TOLERANCE
+
+
+def test_mel_loss(ops):
+    """train/core.py:277-305 against the oracle's mel basis"""
+    from oracle import dsp
+    torch.manual_seed(10)
+    basis = torch.from_numpy(dsp.mel_basis(22050, 1024, 80)).double()
+    magnitude = torch.rand(2, 513, 20) + .05
+    target = torch.log(basis.float() @ (torch.rand(2, 513, 20) + .05))
+    mr = magnitude.double().requires_grad_()
+    expected = 45. * F.l1_loss(target.double(), torch.log(basis @ mr))
+    expected.backward()
+    loss = torch.zeros(1, device='cuda')
+    gmag = torch.empty(magnitude.shape, device='cuda')
+    ops.mel_loss(magnitude.cuda(), target.cuda(), 45., loss, gmag)
+    assert relative_error(loss, expected.reshape(1)) < 1e-5
+    assert relative_error(gmag, mr.grad) < 1e-4
+    mels = ops.linear_to_mel(magnitude.cuda())
+    assert relative_error(mels, torch.log(basis @ magnitude.double())) < 1e-5
