@@ -387,7 +387,9 @@ int pmn_global_features(
 /* Differentiable STFT magnitude over audio (B, T): reflect pad 384, 1024-point frames, hop 256.
  *   window_kind 0 = periodic hann (preprocess/spectrogram.py:36-52, eps 1e-6),
  *               1 = rectangular (discriminator.py:175-195, eps 0)
- *   layout 0: magnitude (B, 513, F); 1: (B, F, 513) (the CMB discriminator's (B, 1, F, 513))
+ *   layout 0: magnitude (B, 513, F); 1: (B, F, 513) (the CMB discriminator's (B, 1, F, 513));
+ *          2: the five CMB bands [0,51) [51,128) [128,256) [256,384) [384,513) of layout 1 stored
+ *             one after the other, each a contiguous (B, F, width) tensor (discriminator.py:195)
  *   spectrum (B, F, 513, 2) complex, kept for the backward; either output may be NULL */
 int pmn_stft_magnitude(
     const float* audio, int batch, int samples, int window_kind, float eps, int layout,
@@ -395,11 +397,21 @@ int pmn_stft_magnitude(
 int pmn_stft_magnitude_backward(
     const float* gmagnitude, const float* spectrum, int batch, int samples, int window_kind,
     float eps, int layout, float* gaudio, int accumulate, void* stream);
-/* Mel loss (train/core.py:277-305): *loss += weight * mean|log(mel_basis @ magnitude) - target|;
- * magnitude (B, 513, F), target_mels (B, 80, F), gmagnitude (B, 513, F) written (may be NULL) */
+/* Mel loss (train/core.py:277-305): L = mean|log(mel_basis @ magnitude) - target|;
+ * *loss += loss_weight * L, gmagnitude (B, 513, F) = grad_weight * dL/dmagnitude (may be NULL);
+ * magnitude (B, 513, F), target_mels (B, 80, F) */
 int pmn_mel_loss(
-    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
-    float* loss, float* gmagnitude, void* stream);
+    const float* magnitude, const float* target_mels, int batch, int frames, float loss_weight,
+    float grad_weight, float* loss, float* gmagnitude, void* stream);
+
+/* out[c] (+)= sum_{b, i} x[b, c, i] over x (batch, channels, inner) */
+int pmn_channel_sum(
+    const float* x, float* out, int batch, int channels, int inner, int accumulate, void* stream);
+/* dst[r, dst_offset + j] (+)= src[r, src_offset + j] for j < cols: torch.cat / split along the
+ * last axis (discriminator.py:204) */
+int pmn_copy_columns(
+    const float* src, int src_width, int src_offset, float* dst, int dst_width, int dst_offset,
+    int64_t rows, int cols, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,94 @@ def fargan():
     print('wrote fargan.npz')
 
 
+TRAIN_BATCH, TRAIN_FRAMES, TRAIN_SEED, TRAIN_STEPS = 2, 32, 77, 2
+# small tensors whose full gradients are stored (the rest are pinned by their norms)
+TRAIN_FULL_GRADIENTS = (
+    'generator:model.model.5.weight',
+    'generator:model.input_speaker_conv.bias',
+    'generator:model.model.3.model.2.model.1.convs1.2.weight_g',
+    'generator:model.model.0.model.1.weight_g',
+    'discriminator:discriminators.0.conv_post.weight_v',
+    'discriminator:discriminators.3.convs.0.weight_v',
+    'discriminator:discriminators.5.band_convs.2.1.0.weight_g',
+    'discriminator:discriminators.5.conv_post.bias')
+
+
+def train():
+    """Two iterations of the reference training step (promonet/train/core.py:183-369)
+    composed from the UNMODIFIED reference modules: promonet.model.Generator,
+    promonet.model.Discriminator, promonet.loss.*, promonet.preprocess.spectrogram.*,
+    promonet.OPTIMIZER; fp32, no autocast (GradScaler is the identity on finite fp32)."""
+    from oracle import train as oracle_train
+    promonet = ref_shim.load()
+    torch.manual_seed(promonet.RANDOM_SEED)
+    generator = promonet.model.Generator()
+    torch.manual_seed(promonet.RANDOM_SEED)
+    discriminators = promonet.model.Discriminator()
+    generator.train()
+    discriminators.train()
+    discriminator_optimizer = promonet.OPTIMIZER(discriminators.parameters())
+    generator_optimizer = promonet.OPTIMIZER(generator.parameters())
+    batch = oracle_train.batch(TRAIN_BATCH, TRAIN_FRAMES, TRAIN_SEED)
+    (loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio) = batch
+    result = {
+        'speakers': speakers.numpy(), 'sbr': sbr.numpy(), 'lr': lr.numpy(),
+        'pitch': pitch.numpy(), 'periodicity': periodicity.numpy(), 'audio': audio.numpy(),
+        'input_checksums': np.array([float(t.double().abs().sum()) for t in batch])}
+    previous_samples = torch.zeros(promonet.HOPSIZE)
+    for step in range(TRAIN_STEPS):
+        # train/core.py:223-256
+        generated = generator(
+            loudness, pitch, periodicity, ppg, speakers, sbr, lr, previous_samples)
+        real_logits, fake_logits, _, _ = discriminators(audio, generated.detach())
+        discriminator_losses, _, _ = promonet.loss.discriminator(
+            [logit.float() for logit in real_logits], [logit.float() for logit in fake_logits])
+        discriminator_optimizer.zero_grad()
+        discriminator_losses.backward()
+        d_grads = {k: v.grad.clone() for k, v in discriminators.named_parameters()}
+        discriminator_optimizer.step()
+        # :262-369
+        _, fake_logits, real_feature_maps, fake_feature_maps = discriminators(audio, generated)
+        mels = promonet.preprocess.spectrogram.linear_to_mel(spectrograms, None)
+        generated_mels = promonet.preprocess.spectrogram.from_audio(generated, True, None)
+        mel_loss = torch.nn.functional.l1_loss(mels, generated_mels)
+        feature_matching_loss = promonet.loss.feature_matching(real_feature_maps, fake_feature_maps)
+        adversarial_loss, _ = promonet.loss.generator([logit.float() for logit in fake_logits])
+        generator_losses = (
+            promonet.MEL_LOSS_WEIGHT * mel_loss +
+            promonet.FEATURE_MATCHING_LOSS_WEIGHT * feature_matching_loss +
+            promonet.ADVERSARIAL_LOSS_WEIGHT * adversarial_loss)
+        generator_optimizer.zero_grad()
+        generator_losses.backward()
+        g_grads = {k: v.grad.clone() for k, v in generator.named_parameters()}
+        generator_optimizer.step()
+        result[f'losses_{step}'] = np.array([
+            float(discriminator_losses), float(mel_loss), float(feature_matching_loss),
+            float(adversarial_loss), float(generator_losses)])
+        result[f'generated_{step}'] = generated.detach().numpy()
+        for kind, grads in (('generator', g_grads), ('discriminator', d_grads)):
+            names = sorted(grads)
+            result[f'{kind}_names'] = np.array(names)
+            result[f'{kind}_grad_norms_{step}'] = np.array(
+                [float(grads[n].double().norm()) for n in names])
+            if step == 0:
+                for full in TRAIN_FULL_GRADIENTS:
+                    owner, name = full.split(':')
+                    if owner == kind:
+                        result[f'grad:{full}'] = grads[name].numpy()
+    for kind, module in (('generator', generator), ('discriminator', discriminators)):
+        params = dict(module.named_parameters())
+        result[f'{kind}_param_checksums'] = np.array(
+            [float(params[n].detach().double().abs().sum()) for n in sorted(params)])
+    np.savez_compressed(GOLDEN / 'train.npz', **result)
+    print('wrote train.npz', {k: result[k] for k in ('losses_0', 'losses_1')})
+
+
 if __name__ == '__main__':
     import sys
-    fargan() if '--fargan' in sys.argv else main()
+    if '--fargan' in sys.argv:
+        fargan()
+    elif '--train' in sys.argv:
+        train()
+    else:
+        main()

@@ -149,7 +149,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_int, c_void_p]),
     'pmn_mel_loss': (
-        c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    'pmn_channel_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'pmn_copy_columns': (
+        c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
 }
 
 

@@ -80,6 +80,12 @@ int launch_adamw(
     cudaStream_t stream);
 int launch_row_sum(
     const float* x, float* out, int rows, int cols, int accumulate, cudaStream_t stream);
+int launch_channel_sum(
+    const float* x, float* out, int batch, int channels, int inner, int accumulate,
+    cudaStream_t stream);
+int launch_copy_columns(
+    const float* src, int src_width, int src_offset, float* dst, int dst_width, int dst_offset,
+    int64_t rows, int cols, int accumulate, cudaStream_t stream);
 int launch_embedding_backward(
     const float* gout, const int64_t* index, float* gtable, int batch, int channels, int frames,
     int rows, int out_channels, int channel_offset, cudaStream_t stream);
@@ -100,7 +106,7 @@ int launch_stft_train_backward(
     const float* gmagnitude, const float* spectrum, int batch, int samples, int window_kind,
     float eps, int layout, float* gaudio, int accumulate, cudaStream_t stream);
 int launch_mel_loss(
-    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
-    float* loss, float* gmagnitude, cudaStream_t stream);
+    const float* magnitude, const float* target_mels, int batch, int frames, float loss_weight,
+    float grad_weight, float* loss, float* gmagnitude, cudaStream_t stream);
 
 }  // namespace pmn

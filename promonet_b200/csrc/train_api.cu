@@ -140,10 +140,24 @@ int pmn_stft_magnitude_backward(
 }
 
 int pmn_mel_loss(
-    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
-    float* loss, float* gmagnitude, void* stream) {
+    const float* magnitude, const float* target_mels, int batch, int frames, float loss_weight,
+    float grad_weight, float* loss, float* gmagnitude, void* stream) {
     return launch_mel_loss(
-        magnitude, target_mels, batch, frames, weight, loss, gmagnitude, (cudaStream_t)stream);
+        magnitude, target_mels, batch, frames, loss_weight, grad_weight, loss, gmagnitude,
+        (cudaStream_t)stream);
+}
+
+int pmn_channel_sum(
+    const float* x, float* out, int batch, int channels, int inner, int accumulate, void* stream) {
+    return launch_channel_sum(x, out, batch, channels, inner, accumulate, (cudaStream_t)stream);
+}
+
+int pmn_copy_columns(
+    const float* src, int src_width, int src_offset, float* dst, int dst_width, int dst_offset,
+    int64_t rows, int cols, int accumulate, void* stream) {
+    return launch_copy_columns(
+        src, src_width, src_offset, dst, dst_width, dst_offset, rows, cols, accumulate,
+        (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -136,6 +136,37 @@ __global__ void __launch_bounds__(256) row_sum_kernel(
     if (threadIdx.x == 0) out[blockIdx.x] = accumulate ? out[blockIdx.x] + sum : sum;
 }
 
+// out[c] (+)= sum_{b, i} x[b, c, i]   (bias gradient of a transposed convolution)
+__global__ void __launch_bounds__(256) channel_sum_kernel(
+    const float* __restrict__ x, float* __restrict__ out, int batch, int channels, int inner,
+    int accumulate) {
+    __shared__ float scratch[32];
+    const int c = blockIdx.x;
+    float sum = 0.f;
+    for (int b = 0; b < batch; ++b) {
+        const float* row = x + ((size_t)b * channels + c) * inner;
+        for (int i = threadIdx.x; i < inner; i += blockDim.x) sum += row[i];
+    }
+    sum = block_sum(sum, scratch);
+    if (threadIdx.x == 0) out[c] = accumulate ? out[c] + sum : sum;
+}
+
+// dst[r, dst_offset + j] (+)= src[r, src_offset + j], j < cols: concatenation / split
+// along the last axis (torch.cat(..., dim=-1), discriminator.py:204)
+__global__ void copy_columns_kernel(
+    const float* __restrict__ src, int src_width, int src_offset, float* __restrict__ dst,
+    int dst_width, int dst_offset, int64_t rows, int cols, int accumulate) {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / cols;
+        const int j = (int)(idx - r * cols);
+        const float v = src[r * src_width + src_offset + j];
+        float* d = dst + r * dst_width + dst_offset + j;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
 // gtable[index[b, f], e] += gout[b, channel_offset + e, f]  (backward of the pitch
 // embedding lookup, generator.py:158-164)
 __global__ void embedding_backward_kernel(
@@ -257,6 +288,27 @@ int launch_row_sum(
     LaunchScope scope("row_sum_kernel", stream);
     row_sum_kernel<<<rows, 256, 0, stream>>>(x, out, cols, accumulate);
     return launched("row_sum_kernel");
+}
+
+int launch_channel_sum(
+    const float* x, float* out, int batch, int channels, int inner, int accumulate,
+    cudaStream_t stream) {
+    PMN_REQUIRE(x && out && batch > 0 && channels > 0 && inner > 0, "channel_sum: bad argument");
+    LaunchScope scope("channel_sum_kernel", stream);
+    channel_sum_kernel<<<channels, 256, 0, stream>>>(x, out, batch, channels, inner, accumulate);
+    return launched("channel_sum_kernel");
+}
+
+int launch_copy_columns(
+    const float* src, int src_width, int src_offset, float* dst, int dst_width, int dst_offset,
+    int64_t rows, int cols, int accumulate, cudaStream_t stream) {
+    PMN_REQUIRE(src && dst && rows > 0 && cols > 0 && src_offset >= 0 && dst_offset >= 0 &&
+                src_offset + cols <= src_width && dst_offset + cols <= dst_width,
+                "copy_columns: bad argument");
+    LaunchScope scope("copy_columns_kernel", stream);
+    copy_columns_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(
+        src, src_width, src_offset, dst, dst_width, dst_offset, rows, cols, accumulate);
+    return launched("copy_columns_kernel");
 }
 
 int launch_embedding_backward(

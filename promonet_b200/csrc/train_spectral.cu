@@ -53,7 +53,23 @@ __device__ __forceinline__ int reflect_index(int i, int samples) {
     return min(max(i, 0), samples - 1);
 }
 
-// One frame per CTA.  magnitude layout: 0 -> (B, 513, F), 1 -> (B, F, 513)
+// Band edges of the complex multi-band discriminator: int(fraction * 513),
+// fractions 0, .1, .25, .5, .75, 1 (discriminator.py:150,161-163)
+__constant__ int kBandEdges[6] = {0, 51, 128, 256, 384, 513};
+
+// magnitude layouts: 0 -> (B, 513, F); 1 -> (B, F, 513); 2 -> the five bands of layout 1
+// stored one after the other, band i as a contiguous (B, F, hi_i - lo_i) tensor
+__device__ __forceinline__ size_t magnitude_index(
+    int layout, int b, int k, int f, int frames, int batch) {
+    if (layout == 0) return ((size_t)b * kBins + k) * frames + f;
+    if (layout == 1) return ((size_t)b * frames + f) * kBins + k;
+    int band = 0;
+    while (k >= kBandEdges[band + 1]) ++band;
+    const int lo = kBandEdges[band], width = kBandEdges[band + 1] - lo;
+    return (size_t)batch * frames * lo + ((size_t)b * frames + f) * width + (k - lo);
+}
+
+// One frame per CTA
 __global__ void __launch_bounds__(kThreads) stft_train_kernel(
     const float* __restrict__ audio, int samples, int frames, SpectralTables t, int window_kind,
     float eps, int layout, float2* __restrict__ spectrum, float* __restrict__ magnitude) {
@@ -73,11 +89,7 @@ __global__ void __launch_bounds__(kThreads) stft_train_kernel(
         const float2 v = buffer[source][k];
         if (spectrum) spectrum[((size_t)b * frames + f) * kBins + k] = v;
         const float mag = sqrtf(v.x * v.x + v.y * v.y + eps);
-        if (magnitude) {
-            const size_t idx = layout == 0 ? ((size_t)b * kBins + k) * frames + f
-                                           : ((size_t)b * frames + f) * kBins + k;
-            magnitude[idx] = mag;
-        }
+        if (magnitude) magnitude[magnitude_index(layout, b, k, f, frames, gridDim.y)] = mag;
     }
 }
 
@@ -94,8 +106,7 @@ __global__ void __launch_bounds__(kThreads) stft_train_backward_kernel(
         float2 value = make_float2(0.f, 0.f);
         if (k < kBins) {
             const float2 v = spectrum[((size_t)b * frames + f) * kBins + k];
-            const size_t idx = layout == 0 ? ((size_t)b * kBins + k) * frames + f
-                                           : ((size_t)b * frames + f) * kBins + k;
+            const size_t idx = magnitude_index(layout, b, k, f, frames, gridDim.y);
             const float mag = sqrtf(v.x * v.x + v.y * v.y + eps);
             // torch.norm's subgradient at 0 is 0
             const float scale = mag > 0.f ? gmagnitude[idx] / mag : 0.f;
@@ -113,10 +124,12 @@ __global__ void __launch_bounds__(kThreads) stft_train_backward_kernel(
     }
 }
 
-// loss += weight * mean|log(M @ mag) - target|, gmagnitude = dloss / dmag   (one frame per CTA)
+// loss += loss_weight * mean|log(M @ mag) - target|, gmagnitude = grad_weight * dmean / dmag
+// (one frame per CTA)
 __global__ void __launch_bounds__(128) mel_loss_kernel(
     const float* __restrict__ magnitude, const float* __restrict__ target, int frames, int batch,
-    SpectralTables t, float weight, float* __restrict__ loss, float* __restrict__ gmagnitude) {
+    SpectralTables t, float loss_weight, float grad_weight, float* __restrict__ loss,
+    float* __restrict__ gmagnitude) {
     __shared__ float mag[kBins];
     __shared__ float gmel[kMels];
     __shared__ float partial[4];
@@ -125,7 +138,9 @@ __global__ void __launch_bounds__(128) mel_loss_kernel(
     const float* src = magnitude + (size_t)b * kBins * frames + f;
     for (int k = tid; k < kBins; k += blockDim.x) mag[k] = src[(size_t)k * frames];
     __syncthreads();
-    const float scale = weight / ((float)batch * kMels * frames);
+    const float count = (float)batch * kMels * frames;
+    const float scale = loss_weight / count;
+    const float gscale = grad_weight / count;
     float local = 0.f;
     if (tid < kMels) {
         const float* w = t.mel_weights + (size_t)tid * kBins;
@@ -135,7 +150,7 @@ __global__ void __launch_bounds__(128) mel_loss_kernel(
         const float d = logf(sum) - target[((size_t)b * kMels + tid) * frames + f];
         local = fabsf(d) * scale;
         const float sign = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-        gmel[tid] = sign * scale / sum;
+        gmel[tid] = sign * gscale / sum;
     }
     for (int offset = 16; offset > 0; offset >>= 1) local += __shfl_xor_sync(0xffffffffu, local, offset);
     if ((tid & 31) == 0) partial[tid >> 5] = local;
@@ -197,8 +212,8 @@ int launch_stft_train_backward(
 }
 
 int launch_mel_loss(
-    const float* magnitude, const float* target_mels, int batch, int frames, float weight,
-    float* loss, float* gmagnitude, cudaStream_t stream) {
+    const float* magnitude, const float* target_mels, int batch, int frames, float loss_weight,
+    float grad_weight, float* loss, float* gmagnitude, cudaStream_t stream) {
     PMN_REQUIRE(magnitude && target_mels && (loss || gmagnitude) && batch > 0 && batch <= 65535 &&
                 frames > 0, "mel_loss: bad argument");
     const SpectralTables* t;
@@ -206,7 +221,7 @@ int launch_mel_loss(
     dim3 grid(frames, batch);
     LaunchScope scope("mel_loss_kernel", stream);
     mel_loss_kernel<<<grid, 128, 0, stream>>>(
-        magnitude, target_mels, frames, batch, *t, weight, loss, gmagnitude);
+        magnitude, target_mels, frames, batch, *t, loss_weight, grad_weight, loss, gmagnitude);
     return launched("mel_loss_kernel");
 }
 

@@ -164,3 +164,38 @@ def fargan_state(seed=None):
     state['ppg_threshold'] = torch.tensor(config.SPARSE_PPG_THRESHOLD, dtype=torch.float)
     state['pitch_distribution'] = pitch_distribution()
     return state
+
+
+###############################################################################
+# Discriminator (config/promonet.py: 5 x DiscriminatorP + DiscriminatorCMB)
+###############################################################################
+
+
+def discriminator_state(seed=None):
+    """State dict of a freshly constructed promonet.model.Discriminator()
+    (promonet/model/discriminator.py:15-34,61-72,148-173): same keys and the same
+    torch RNG draw order (Conv2d.reset_parameters per layer, in construction order)"""
+    if seed is not None:
+        torch.manual_seed(seed)
+    state = OrderedDict()
+    for index, _ in enumerate(config.DISCRIMINATOR_PERIODS):
+        prefix = f'discriminators.{index}'
+        channels = (1, 32, 128, 512, 1024, 1024)
+        for layer in range(5):
+            stride = (3, 1) if layer < 4 else 1
+            _weight_norm_conv(state, f'{prefix}.convs.{layer}', torch.nn.Conv2d(
+                channels[layer], channels[layer + 1], (5, 1), stride, (2, 0)))
+        _weight_norm_conv(
+            state, f'{prefix}.conv_post', torch.nn.Conv2d(1024, 1, (3, 1), 1, (1, 0)))
+    prefix = f'discriminators.{len(config.DISCRIMINATOR_PERIODS)}'
+    for band, _ in enumerate(config.CMB_BANDS):
+        for layer in range(5):
+            kernel = (3, 9) if layer < 4 else (3, 3)
+            stride = (1, 2) if 1 <= layer <= 3 else (1, 1)
+            _weight_norm_conv(
+                state, f'{prefix}.band_convs.{band}.{layer}.0',
+                torch.nn.Conv2d(1 if layer == 0 else 32, 32, kernel, stride,
+                                padding=(1, kernel[1] // 2)))
+    _weight_norm_conv(
+        state, f'{prefix}.conv_post', torch.nn.Conv2d(32, 1, (3, 3), (1, 1), padding=(1, 1)))
+    return state

@@ -1,1 +1,2 @@
 from . import ops
+from .core import Trainer, train

@@ -1,0 +1,193 @@
+"""One GAN training step, sequenced as promonet/train/core.py:183-369
+
+    generated = generator(batch)                                 :223
+    D(audio, generated.detach()) -> LSGAN loss -> D AdamW step   :239-256
+    D(audio, generated) again with the updated D                 :272
+    45 x mel L1 + feature matching + LSGAN generator loss        :277-332
+    generator backward -> G AdamW step                           :335-369
+
+Differences from the reference, all deliberate: fp32 everywhere instead of fp16
+autocast + GradScaler (:118,220,262); the generator step does not deposit (unused)
+gradients in the discriminator (:338 does, :254 clears them); under
+torch.distributed the gradients of each module are averaged with one NCCL
+all-reduce before its optimizer step (the reference is single-GPU).
+"""
+import os
+from pathlib import Path
+
+import torch
+
+from promonet_b200 import config
+from promonet_b200.train import ops
+from promonet_b200.train.discriminator import Discriminator
+from promonet_b200.train.generator import Generator
+
+LOSSES = ('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator')
+
+
+class Trainer:
+
+    def __init__(self, generator_state=None, discriminator_state=None, device=None,
+                 process_group=None):
+        self.generator = Generator(generator_state, device)
+        self.discriminators = Discriminator(discriminator_state, self.generator.device)
+        self.device = self.generator.device
+        self.process_group = process_group
+        self.step_count = 0
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+
+    ###########################################################################
+    # Data-parallel gradient exchange
+    ###########################################################################
+
+    def all_reduce(self, params):
+        """Sum the flat gradient buffer over ranks (NCCL over NVLink); the mean is taken
+        by the optimizer kernel's grad_scale"""
+        if self.world > 1:
+            torch.distributed.all_reduce(params.grad, group=self.process_group)
+
+    def broadcast_parameters(self, source=0):
+        if self.world > 1:
+            for params in (self.generator.params, self.discriminators.params):
+                torch.distributed.broadcast(params.data, source, group=self.process_group)
+
+    def optimize(self, params):
+        self.all_reduce(params)
+        params.adamw(
+            config.LEARNING_RATE, config.ADAM_BETAS, config.ADAM_EPS, config.WEIGHT_DECAY,
+            grad_scale=1. / self.world)
+
+    ###########################################################################
+    # Step
+    ###########################################################################
+
+    def step(self, loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
+             loudness_ratios, spectrograms, audio, update=True):
+        """Batch tensors as collated by the reference (data/collate.py:43-60), on the device.
+        Returns the five losses as a device tensor ordered like LOSSES (no host sync)."""
+        G, D = self.generator, self.discriminators
+        batch, _, samples = audio.shape
+        losses = torch.zeros(len(LOSSES), device=self.device)
+        slot = lambda name: losses[LOSSES.index(name):LOSSES.index(name) + 1]
+
+        # ---- generator forward (:223), written next to the real audio ----
+        G.refresh()
+        both = torch.empty(2 * batch, 1, samples, device=self.device)
+        both[:batch].copy_(audio)
+        G.forward(loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
+                  loudness_ratios, out=both[batch:])
+
+        # ---- discriminator step (:239-256) ----
+        D.refresh()
+        records = D.forward(both)
+        gmaps = []
+        for logits, maps in zip(D.logits(records), D.feature_maps(records)):
+            glogits = torch.empty_like(logits)
+            ops.mse_to_target(logits[:batch], 1., 1., slot('discriminator'), glogits[:batch])
+            ops.mse_to_target(logits[batch:], 0., 1., slot('discriminator'), glogits[batch:])
+            gmaps.append([None] * (len(maps) - 1) + [glogits.view(maps[-1].shape)])
+        D.layers.zero_grad()
+        D.backward(records, gmaps, 0, 2 * batch, weights=True)
+        if update:
+            self.optimize(D.params)
+            D.refresh()
+
+        # ---- generator step (:262-369) ----
+        records = D.forward(both)
+        ggenerated = torch.zeros(batch, 1, samples, device=self.device)
+        gmaps = []
+        for logits, maps in zip(D.logits(records), D.feature_maps(records)):
+            # feature matching (loss.py:11-26) seeds the gradient of every generated map
+            gradients = []
+            for fmap in maps:
+                g = torch.empty_like(fmap[batch:])
+                ops.l1_mean(fmap[batch:], fmap[:batch], config.FEATURE_MATCHING_LOSS_WEIGHT,
+                            slot('feature_matching'), g)
+                gradients.append(g)
+            # adversarial (loss.py:43-53) adds to the gradient of the logits
+            gadversarial = torch.empty_like(logits[batch:])
+            ops.mse_to_target(logits[batch:], 1., config.ADVERSARIAL_LOSS_WEIGHT,
+                              slot('adversarial'), gadversarial)
+            ops.axpby(1., gadversarial.view(-1), 1., gradients[-1].view(-1))
+            gmaps.append(gradients)
+        D.backward(records, gmaps, batch, 2 * batch, weights=False, gaudio=ggenerated)
+        # mel loss (:277-305)
+        target_mels = ops.linear_to_mel(spectrograms)
+        magnitude, spectrum = ops.stft_magnitude(both[batch:].view(batch, samples), 'hann', 1e-6, 0)
+        gmagnitude = torch.empty_like(magnitude)
+        ops.mel_loss(magnitude, target_mels, 1., slot('mel'), gmagnitude, config.MEL_LOSS_WEIGHT)
+        ops.stft_magnitude_backward(
+            gmagnitude, spectrum, ggenerated.view(batch, samples), 'hann', 1e-6, 0, accumulate=True)
+        G.layers.zero_grad()
+        G.backward(ggenerated)
+        if update:
+            self.optimize(G.params)
+        self.step_count += 1
+        self.generated = both[batch:]
+        # total generator loss (:291,323-332), on the device
+        ops.axpby(config.MEL_LOSS_WEIGHT, slot('mel'), 0., slot('generator'))
+        ops.axpby(1., slot('feature_matching'), 1., slot('generator'))
+        ops.axpby(1., slot('adversarial'), 1., slot('generator'))
+        return losses
+
+    ###########################################################################
+    # Checkpoints (torchutil.checkpoint layout: train/core.py:426-438)
+    ###########################################################################
+
+    def save(self, directory, epoch=0):
+        directory = Path(directory)
+        directory.mkdir(parents=True, exist_ok=True)
+        for name, module in (('generator', self.generator), ('discriminator', self.discriminators)):
+            torch.save(
+                {'model': module.state_dict(), 'optimizer': module.params.optimizer_state(),
+                 'step': self.step_count, 'epoch': epoch},
+                directory / f'{name}-{self.step_count:08d}.pt')
+
+    def load(self, directory):
+        """Resume from the newest generator-*.pt / discriminator-*.pt (train/core.py:70-105)"""
+        directory = Path(directory)
+        for name, module in (('generator', self.generator), ('discriminator', self.discriminators)):
+            files = sorted(directory.glob(f'{name}-*.pt'))
+            if not files:
+                continue
+            checkpoint = torch.load(files[-1], map_location='cpu')
+            module.load_state_dict(checkpoint['model'])
+            optimizer = checkpoint.get('optimizer')
+            if isinstance(optimizer, dict) and 'exp_avg' in optimizer:
+                module.params.load_optimizer_state(optimizer)
+            self.step_count = int(checkpoint.get('step', 0))
+
+
+def train(directory, dataset='vctk', train_partition='train', valid_partition='valid',
+          adapt_from=None, gpu=None, loader=None, steps=None):
+    """promonet.train (promonet/train/core.py:17-24).  The reference builds its loader
+    from a preprocessed dataset on disk (promonet/data, out of scope here): pass `loader`,
+    an iterable of batches laid out as data/collate.py:43-60
+    (text, loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
+    loudness_ratios, spectrograms, audio, stems)."""
+    if loader is None:
+        raise ValueError(
+            'promonet_b200.train needs `loader`: the dataset pipeline of the reference '
+            '(promonet.data) is outside the accelerated path')
+    device = torch.device('cuda', 0 if gpu is None else gpu)
+    torch.cuda.set_device(device)
+    trainer = Trainer(device=device)
+    trainer.load(adapt_from if adapt_from is not None else directory)
+    trainer.broadcast_parameters()
+    steps = config.STEPS if steps is None else steps
+    while trainer.step_count < steps:
+        for batch in loader:
+            (_, loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio, _) = batch
+            if audio.shape[-1] < config.CHUNK_SIZE:   # :154
+                continue
+            tensors = [t.to(device, non_blocking=True) for t in (
+                loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio)]
+            trainer.step(*tensors)
+            if trainer.step_count % config.CHECKPOINT_INTERVAL == 0:
+                trainer.save(directory)
+            if trainer.step_count >= steps:
+                break
+    trainer.save(directory)
+    return trainer

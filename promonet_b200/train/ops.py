@@ -157,7 +157,7 @@ def stft_magnitude(audio, window='hann', eps=1e-6, layout=0, want_spectrum=True)
     """audio (B, T) -> magnitude ((B, 513, F) or (B, F, 513)), spectrum (B, F, 513, 2)"""
     batch, samples = audio.shape
     frames = samples // 256
-    shape = (batch, 513, frames) if layout == 0 else (batch, frames, 513)
+    shape = {0: (batch, 513, frames), 1: (batch, frames, 513), 2: (batch * frames * 513,)}[layout]
     magnitude = torch.empty(shape, device=audio.device)
     spectrum = torch.empty(batch, frames, 513, 2, device=audio.device) if want_spectrum else None
     _check(_lib.library().pmn_stft_magnitude(
@@ -176,11 +176,30 @@ def stft_magnitude_backward(gmagnitude, spectrum, gaudio, window='hann', eps=1e-
     return gaudio
 
 
-def mel_loss(magnitude, target_mels, weight, loss, gmagnitude=None):
+def mel_loss(magnitude, target_mels, weight, loss, gmagnitude=None, grad_weight=None):
     batch, _, frames = magnitude.shape
     _check(_lib.library().pmn_mel_loss(
-        _lib.ptr(magnitude), _lib.ptr(target_mels), batch, frames, weight, _lib.ptr(loss),
+        _lib.ptr(magnitude), _lib.ptr(target_mels), batch, frames, weight,
+        weight if grad_weight is None else grad_weight, _lib.ptr(loss),
         _lib.ptr(gmagnitude), _lib.stream()))
+
+
+def channel_sum(x, out, accumulate=False):
+    """out[c] (+)= sum over batch and trailing axes of x (B, C, ...)"""
+    batch, channels = x.shape[:2]
+    _check(_lib.library().pmn_channel_sum(
+        _lib.ptr(x), _lib.ptr(out), batch, channels, x.numel() // (batch * channels),
+        int(accumulate), _lib.stream()))
+    return out
+
+
+def copy_columns(src, dst, src_offset, dst_offset, cols, accumulate=False):
+    """dst[..., dst_offset:dst_offset + cols] (+)= src[..., src_offset:src_offset + cols]"""
+    rows = src.numel() // src.shape[-1]
+    _check(_lib.library().pmn_copy_columns(
+        _lib.ptr(src), src.shape[-1], src_offset, _lib.ptr(dst), dst.shape[-1], dst_offset,
+        rows, cols, int(accumulate), _lib.stream()))
+    return dst
 
 
 def linear_to_mel(magnitude, floor=float('-inf')):
