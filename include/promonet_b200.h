@@ -312,6 +312,24 @@ int pmn_conv_gemm(
     int out_act, float out_slope, const float* mask_src, float mask_slope,
     const float* residual, float alpha, int accumulate, float* out, void* stream);
 
+/* pmn_conv_gemm on the tcgen05 tensor cores: tf32 operands (10-bit mantissa), fp32
+ * accumulation in TMEM (promonet_b200/csrc/train_conv_tc.cu).  Same arguments, except that the
+ * weight is the tap-major packing made by pmn_pack_weight_taps (16-byte aligned):
+ *   transposed = 0: pack(weight (c_out, c_in, kh, kw), transposed = 0) -> (c_out, taps, pad(c_in))
+ *   transposed = 1: pack(weight (c_out, c_in, kh, kw), transposed = 1) -> (c_in, taps, pad(c_out))
+ * pad(c) = pmn_conv_tc_channel_pad(c) (multiple of 32). */
+int pmn_conv_gemm_tc(
+    const pmn_conv_geometry* geometry, int transposed,
+    const float* a, const float* a_companion, int a_act, float a_slope,
+    const float* wpacked, const float* bias, const float* bias2,
+    int out_act, float out_slope, const float* mask_src, float mask_slope,
+    const float* residual, float alpha, int accumulate, float* out, void* stream);
+int pmn_conv_tc_channel_pad(int channels);
+/* w (d0, d1, taps) -> out[a][tap][b] (transposed = 0, b padded to pad(d1)) or out[b][tap][a]
+ * (transposed = 1, a padded to pad(d0)); padding is written as zeros */
+int pmn_pack_weight_taps(
+    const float* w, float* out, int d0, int d1, int taps, int transposed, void* stream);
+
 /* Weight (and bias) gradient, ACCUMULATED atomically into gw (c_out, c_in, kh, kw) and
  * gbias (c_out, may be NULL):  gw[n, c, i, j] += sum_{b, p} act(dy)[b, n, p] act(x)[b, c, in(p, i, j)].
  * The weight gradient of a ConvTranspose (C_in, C_out, k) is this call on the geometry of the

@@ -27,6 +27,7 @@ from promonet_b200.train.core import Trainer  # noqa: E402
 from oracle import train as oracle_train  # noqa: E402
 
 KERNELS = (
+    'conv_fprop_tc_kernel', 'conv_dgrad_tc_kernel', 'conv_wgrad_tc_kernel', 'pack_weight_taps_kernel',
     'conv_fprop_kernel', 'conv_dgrad_kernel', 'conv_wgrad_kernel', 'conv_transpose1d_kernel',
     'weight_norm_fold_kernel', 'weight_norm_backward_kernel', 'transpose_weight_kernel',
     'stft_train_kernel', 'stft_train_backward_kernel', 'mel_loss_kernel', 'mel_kernel',
@@ -48,12 +49,13 @@ def main():
     parser.add_argument('--steps', type=int, default=5)
     parser.add_argument('--warmup', type=int, default=2)
     parser.add_argument('--no-cpu', action='store_true')
+    parser.add_argument('--math', default='tf32', choices=['tf32', 'fp32'])
     args = parser.parse_args()
     rank, local_rank, world = parallel.environment()
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     parallel.initialize('nccl', device)
-    trainer = Trainer(init.hifigan_state(1234), init.discriminator_state(1234), device)
+    trainer = Trainer(init.hifigan_state(1234), init.discriminator_state(1234), device, math=args.math)
     trainer.broadcast_parameters()
     batch = [t.to(device).contiguous() for t in oracle_train.batch(args.batch, args.frames, 1234 + rank)]
     for _ in range(args.warmup):
@@ -82,7 +84,8 @@ def main():
         result = {
             'metric': 'training items/sec (16 384-sample chunks)', 'value': items / (ms * 1e-3),
             'unit': 'items/s', 'n_gpus': world, 'ms_per_step': ms, 'batch_per_gpu': args.batch,
-            'global_batch': items, 'frames': args.frames, 'dtype': 'f32',
+            'global_batch': items, 'frames': args.frames,
+            'dtype': 'f32 (tf32 tensor-core products, fp32 accumulate)' if args.math == 'tf32' else 'f32',
             'gpu_launches_per_step': launches,
             'losses': dict(zip(('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator'),
                                [float(v) for v in losses.cpu()])),

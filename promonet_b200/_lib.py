@@ -112,6 +112,13 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
          c_int, c_float, c_void_p, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    'pmn_conv_gemm_tc': (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p,
+         c_int, c_float, c_void_p, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    'pmn_conv_tc_channel_pad': (c_int, [c_int]),
+    'pmn_pack_weight_taps': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_conv_wgrad': (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,

@@ -38,6 +38,13 @@ struct ConvGemmArgs {
 
 int launch_conv_gemm(const ConvGemmArgs& args, cudaStream_t stream);
 
+// train_conv_tc.cu: the same contract on tcgen05 (tf32 operands); args.wmat is the
+// tap-major packed weight (rows, taps, conv_tc_channel_pad(reduction channels))
+int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream);
+int conv_tc_channel_pad(int channels);
+int launch_pack_weight_taps(
+    const float* w, float* out, int d0, int d1, int taps, int transposed, cudaStream_t stream);
+
 struct ConvWgradArgs {
     pmn_conv_geometry g;
     const float* dy = nullptr;     // (B, c_out, h_out, w_out)

@@ -26,6 +26,34 @@ int pmn_conv_gemm(
     return launch_conv_gemm(args, (cudaStream_t)stream);
 }
 
+int pmn_conv_gemm_tc(
+    const pmn_conv_geometry* geometry, int transposed,
+    const float* a, const float* a_companion, int a_act, float a_slope,
+    const float* wpacked, const float* bias, const float* bias2,
+    int out_act, float out_slope, const float* mask_src, float mask_slope,
+    const float* residual, float alpha, int accumulate, float* out, void* stream) {
+    PMN_REQUIRE(geometry, "conv_gemm_tc: null geometry");
+    PMN_REQUIRE(a_act >= 0 && a_act <= 3 && out_act >= 0 && out_act <= 2, "conv_gemm_tc: bad activation");
+    PMN_REQUIRE(((uintptr_t)wpacked & 15) == 0, "conv_gemm_tc: packed weights must be 16-byte aligned");
+    ConvGemmArgs args;
+    args.g = *geometry;
+    args.transposed = transposed != 0;
+    args.a = a; args.a_companion = a_companion; args.a_act = a_act; args.a_slope = a_slope;
+    args.wmat = wpacked; args.bias = bias; args.bias2 = bias2;
+    args.out_act = out_act; args.out_slope = out_slope;
+    args.mask_src = mask_src; args.mask_slope = mask_slope;
+    args.residual = residual; args.alpha = alpha; args.accumulate = accumulate != 0;
+    args.out = out;
+    return launch_conv_gemm_tc(args, (cudaStream_t)stream);
+}
+
+int pmn_conv_tc_channel_pad(int channels) { return conv_tc_channel_pad(channels); }
+
+int pmn_pack_weight_taps(
+    const float* w, float* out, int d0, int d1, int taps, int transposed, void* stream) {
+    return launch_pack_weight_taps(w, out, d0, d1, taps, transposed, (cudaStream_t)stream);
+}
+
 int pmn_conv_wgrad(
     const pmn_conv_geometry* geometry,
     const float* dy, const float* dy_companion, int dy_act, float dy_slope,

@@ -28,9 +28,13 @@ LOSSES = ('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator'
 class Trainer:
 
     def __init__(self, generator_state=None, discriminator_state=None, device=None,
-                 process_group=None):
-        self.generator = Generator(generator_state, device)
-        self.discriminators = Discriminator(discriminator_state, self.generator.device)
+                 process_group=None, math='tf32'):
+        """math: 'tf32' runs the convolutions' forward and data gradients on the tensor
+        cores (tf32 operands, fp32 accumulation; the reference trains under fp16 autocast,
+        train/core.py:220); 'fp32' is the exact FMA path used for parity"""
+        self.math = math
+        self.generator = Generator(generator_state, device, math)
+        self.discriminators = Discriminator(discriminator_state, self.generator.device, math)
         self.device = self.generator.device
         self.process_group = process_group
         self.step_count = 0

@@ -45,8 +45,8 @@ class Period:
             geometry = ops.geometry(
                 n, conv.dim1, conv.dim0, source.shape[2:], kernel, stride, 1, padding)
             out = torch.empty(n, conv.dim0, geometry.h_out, geometry.w_out, device=x.device)
-            ops.conv_gemm(
-                geometry, False, source, conv.w, out, bias=conv.bias,
+            conv.apply(
+                        geometry, False, source, out, bias=conv.bias,
                 out_act=ops.OUT_LRELU if i < 5 else ops.OUT_NONE, out_slope=SLOPE)
             maps.append(out)
             geometries.append(geometry)
@@ -71,7 +71,8 @@ class Period:
             accumulate = target is not None
             if target is None:
                 target = torch.empty_like(x)
-            ops.conv_gemm(geometry, True, g, layers[i].wt, target, a_companion=y,
+            layers[i].apply_transposed(
+                        geometry, True, g, target, a_companion=y,
                           a_act=act[0], a_slope=act[1], accumulate=accumulate)
             if i > 0:
                 gmaps[i - 1] = target
@@ -109,7 +110,8 @@ class ComplexMultiBand:
                     n, conv.dim1, conv.dim0, chain[-1].shape[2:], kernel, stride, 1,
                     (1, kernel[1] // 2))
                 out = torch.empty(n, conv.dim0, geometry.h_out, geometry.w_out, device=x.device)
-                ops.conv_gemm(geometry, False, chain[-1], conv.w, out, bias=conv.bias,
+                conv.apply(
+                        geometry, False, chain[-1], out, bias=conv.bias,
                               out_act=ops.OUT_LRELU, out_slope=SLOPE)
                 chain.append(out)
                 chain_geometry.append(geometry)
@@ -124,7 +126,8 @@ class ComplexMultiBand:
             column += o.shape[-1]
         post_geometry = ops.geometry(n, 32, 1, (frames, total), (3, 3), 1, 1, (1, 1))
         logits = torch.empty(n, 1, frames, total, device=x.device)
-        ops.conv_gemm(post_geometry, False, joined, self.post.w, logits, bias=self.post.bias)
+        self.post.apply(
+                        post_geometry, False, joined, logits, bias=self.post.bias)
         return {
             'maps': maps, 'geometries': geometries, 'joined': joined, 'logits': logits,
             'post_geometry': post_geometry, 'spectrum': spectrum, 'samples': t, 'frames': frames}
@@ -144,7 +147,8 @@ class ComplexMultiBand:
         joined = record['joined'][lo:hi]
         if weights:
             ops.conv_wgrad(geometry, glogits, joined, self.post.gw, self.post.gbias)
-        gjoined = ops.conv_gemm(geometry, True, glogits, self.post.wt, torch.empty_like(joined))
+        gjoined = self.post.apply_transposed(
+                        geometry, True, glogits, torch.empty_like(joined))
         gbanded = torch.zeros(n * frames * 513, device=gjoined.device) if gaudio is not None else None
         column = 0
         for b, ((first, last), stack) in enumerate(zip(config.CMB_BANDS, self.bands)):
@@ -173,7 +177,8 @@ class ComplexMultiBand:
                 else:
                     target = gbanded[n * frames * first:n * frames * last].view(x.shape)
                     accumulate = False
-                ops.conv_gemm(geometry, True, g, stack[i].wt, target, a_companion=y,
+                stack[i].apply_transposed(
+                        geometry, True, g, target, a_companion=y,
                               a_act=ops.ACT_LRELU_MASK, a_slope=SLOPE, accumulate=accumulate)
                 g = target
         if gaudio is not None:
@@ -192,14 +197,14 @@ def _with_batch(geometry, batch):
 
 class Discriminator:
 
-    def __init__(self, state=None, device=None):
+    def __init__(self, state=None, device=None, math='tf32'):
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.train needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
         state = init.discriminator_state() if state is None else state
         self.params = ParamSet(state, self.device)
-        self.layers = Layers(self.params)
+        self.layers = Layers(self.params, math)
         self.periods = [
             Period(self.layers, f'discriminators.{i}', period)
             for i, period in enumerate(config.DISCRIMINATOR_PERIODS)]

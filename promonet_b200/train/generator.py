@@ -18,14 +18,14 @@ SLOPE = config.LRELU_SLOPE
 
 class Generator:
 
-    def __init__(self, state=None, device=None):
+    def __init__(self, state=None, device=None, math='tf32'):
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.train needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
         state = init.hifigan_state() if state is None else state
         self.params = ParamSet(state, self.device, BUFFERS)
-        self.layers = Layers(self.params)
+        self.layers = Layers(self.params, math)
         conv = self.layers.conv
         self.input_conv = conv('model.input_feature_conv')
         self.speaker_conv = conv('model.input_speaker_conv')
@@ -78,14 +78,13 @@ class Generator:
             P['speaker_embedding.weight'], speakers, spectral_balance_ratios, loudness_ratios)
         speaker_geometry = ops.geometry(
             batch, config.GLOBAL_CHANNELS, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE, (1, 1), (1, 1))
-        speaker_bias = ops.conv_gemm(
-            speaker_geometry, False, gvec, self.speaker_conv.w,
-            new(batch, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE), bias=self.speaker_conv.bias)
+        speaker_bias = self.speaker_conv.apply(
+                        speaker_geometry, False, gvec, new(batch, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE), bias=self.speaker_conv.bias)
         channels = config.HIFIGAN_UPSAMPLE_INITIAL_SIZE
         input_geometry = ops.geometry(
             batch, config.NUM_FEATURES, channels, (frames, 1), (7, 1), 1, 1, (3, 0))
-        x = ops.conv_gemm(
-            input_geometry, False, features, self.input_conv.w, new(batch, channels, frames),
+        x = self.input_conv.apply(
+                        input_geometry, False, features, new(batch, channels, frames),
             bias=self.input_conv.bias, bias2=speaker_bias)
         saved.update(features=features, gvec=gvec, speaker_geometry=speaker_geometry,
                      input_geometry=input_geometry, stages=[])
@@ -105,18 +104,18 @@ class Generator:
                         zip(block, config.HIFIGAN_RESBLOCK_DILATION_SIZES)):
                     g1 = self._conv_geometry(batch, channels, t, kernel, dilation)
                     g2 = self._conv_geometry(batch, channels, t, kernel, 1)
-                    hidden = ops.conv_gemm(
-                        g1, False, current, c1.w, new(batch, channels, t),
+                    hidden = c1.apply(
+                        g1, False, current, new(batch, channels, t),
                         a_act=ops.ACT_LRELU, a_slope=SLOPE, bias=c1.bias)
                     record.append((current, hidden, g1, g2))
                     if m < last:
-                        current = ops.conv_gemm(
-                            g2, False, hidden, c2.w, new(batch, channels, t),
+                        current = c2.apply(
+                        g2, False, hidden, new(batch, channels, t),
                             a_act=ops.ACT_LRELU, a_slope=SLOPE, bias=c2.bias, residual=current)
                     else:
                         # ResidualBlock.forward hifigan.py:141-145: mean over the kernels
-                        ops.conv_gemm(
-                            g2, False, hidden, c2.w, mrf, a_act=ops.ACT_LRELU, a_slope=SLOPE,
+                        c2.apply(
+                        g2, False, hidden, mrf, a_act=ops.ACT_LRELU, a_slope=SLOPE,
                             bias=c2.bias, residual=current,
                             alpha=1. / len(blocks), accumulate=j > 0)
                 records.append(record)
@@ -124,8 +123,8 @@ class Generator:
             x = mrf
         head_geometry = ops.geometry(batch, channels, 1, (t, 1), (7, 1), 1, 1, (3, 0))
         audio = new(batch, 1, t) if out is None else out
-        ops.conv_gemm(
-            head_geometry, False, x, self.head.w, audio, a_act=ops.ACT_LRELU, a_slope=SLOPE,
+        self.head.apply(
+                        head_geometry, False, x, audio, a_act=ops.ACT_LRELU, a_slope=SLOPE,
             out_act=ops.OUT_TANH)
         saved.update(x_last=x, audio=audio, head_geometry=head_geometry)
         self.saved = saved
@@ -146,8 +145,8 @@ class Generator:
         ops.conv_wgrad(
             geometry, gaudio, x_last, self.head.gw, None, dy_companion=audio,
             dy_act=ops.ACT_TANH_MASK, x_act=ops.ACT_LRELU, x_slope=SLOPE)
-        g = ops.conv_gemm(
-            geometry, True, gaudio, self.head.wt, new(x_last), a_companion=audio,
+        g = self.head.apply_transposed(
+                        geometry, True, gaudio, new(x_last), a_companion=audio,
             a_act=ops.ACT_TANH_MASK, mask_src=x_last, mask_slope=SLOPE)
         for (up, blocks), (x_in, xu, records), rate, kernel_size in reversed(list(zip(
                 self.stages, saved['stages'], config.HIFIGAN_UPSAMPLE_RATES,
@@ -163,18 +162,18 @@ class Generator:
                     # x_next = current + c2(lrelu(hidden)) + b2
                     ops.conv_wgrad(g2, gcurrent, hidden, c2.gw, c2.gbias,
                                    x_act=ops.ACT_LRELU, x_slope=SLOPE)
-                    ghidden = ops.conv_gemm(
-                        g2, True, gcurrent, c2.wt, new(hidden), mask_src=hidden, mask_slope=SLOPE)
+                    ghidden = c2.apply_transposed(
+                        g2, True, gcurrent, new(hidden), mask_src=hidden, mask_slope=SLOPE)
                     # hidden = c1(lrelu(current)) + b1
                     ops.conv_wgrad(g1, ghidden, current, c1.gw, c1.gbias,
                                    x_act=ops.ACT_LRELU, x_slope=SLOPE)
                     if m > 0:
-                        gcurrent = ops.conv_gemm(
-                            g1, True, ghidden, c1.wt, new(current), mask_src=current,
+                        gcurrent = c1.apply_transposed(
+                        g1, True, ghidden, new(current), mask_src=current,
                             mask_slope=SLOPE, residual=gcurrent)
                     else:
-                        ops.conv_gemm(
-                            g1, True, ghidden, c1.wt, gxu, mask_src=current, mask_slope=SLOPE,
+                        c1.apply_transposed(
+                        g1, True, ghidden, gxu, mask_src=current, mask_slope=SLOPE,
                             residual=gcurrent, accumulate=j > 0)
             # xu = ConvTranspose1d(lrelu(x_in)) + b: gradients through the convolution it transposes
             batch, c_in, t_in = x_in.shape
@@ -184,14 +183,14 @@ class Generator:
                 ((kernel_size - rate) // 2, 0), size_out=(t_in, 1))
             ops.conv_wgrad(geometry, x_in, gxu, up.gw, None, dy_act=ops.ACT_LRELU, dy_slope=SLOPE)
             ops.channel_sum(gxu, up.gbias, accumulate=True)
-            g = ops.conv_gemm(
-                geometry, False, gxu, up.w, new(x_in), mask_src=x_in, mask_slope=SLOPE)
+            g = up.apply(
+                        geometry, False, gxu, new(x_in), mask_src=x_in, mask_slope=SLOPE)
         # input layer: x0 = conv7(features) + b + speaker projection
         P = self.params
         features, gvec = saved['features'], saved['gvec']
         ops.conv_wgrad(saved['input_geometry'], g, features, self.input_conv.gw, self.input_conv.gbias)
-        gfeatures = ops.conv_gemm(
-            saved['input_geometry'], True, g, self.input_conv.wt, new(features))
+        gfeatures = self.input_conv.apply_transposed(
+                        saved['input_geometry'], True, g, new(features))
         ops.embedding_backward(
             gfeatures, saved['bins'], P.gradient('pitch_embedding.weight'),
             channel_offset=config.PPG_CHANNELS)
@@ -200,8 +199,8 @@ class Generator:
             g, torch.empty(batch, channels, device=self.device), batch * channels, frames)
         ops.conv_wgrad(saved['speaker_geometry'], gspeaker, gvec, self.speaker_conv.gw,
                        self.speaker_conv.gbias)
-        ggvec = ops.conv_gemm(
-            saved['speaker_geometry'], True, gspeaker, self.speaker_conv.wt, new(gvec))
+        ggvec = self.speaker_conv.apply_transposed(
+                        saved['speaker_geometry'], True, gspeaker, new(gvec))
         ops.embedding_backward(
             ggvec.view(batch, config.GLOBAL_CHANNELS, 1), saved['speakers'].view(batch, 1),
             P.gradient('speaker_embedding.weight'), channel_offset=0)

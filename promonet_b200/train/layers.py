@@ -26,7 +26,8 @@ class Conv:
         self.numel = self.dim0 * self.dim1 * self.taps
         self.has_bias = f'{prefix}.bias' in params
         # assigned by Layers.allocate()
-        self.w = self.wt = self.gw = None
+        self.w = self.wt = self.gw = self.packed = self.packed_t = None
+        self.tensor_cores = False
 
     @property
     def bias(self):
@@ -43,6 +44,23 @@ class Conv:
                 self.params[f'{self.prefix}.weight_v'], self.params[f'{self.prefix}.weight_g'],
                 self.w, self.dim0, self.dim1 * self.taps)
         ops.transpose_weight(self.w, self.wt, self.dim0, self.dim1, self.taps)
+        if self.packed is not None:
+            ops.pack_weight_taps(self.w, self.packed, self.dim0, self.dim1, self.taps, False)
+        if self.packed_t is not None:
+            ops.pack_weight_taps(self.w, self.packed_t, self.dim0, self.dim1, self.taps, True)
+
+    def apply(self, geometry, transposed, a, out, **kwargs):
+        """Implicit GEMM with rows = dim 0 of the weight, reducing over dim 1 (forward of a
+        Conv, data gradient of a ConvTranspose).  `transposed` is the gather direction."""
+        if self.packed is not None:
+            return ops.conv_gemm_tc(geometry, transposed, a, self.packed, out, **kwargs)
+        return ops.conv_gemm(geometry, transposed, a, self.w, out, **kwargs)
+
+    def apply_transposed(self, geometry, transposed, a, out, **kwargs):
+        """Rows = dim 1 of the weight, reducing over dim 0 (data gradient of a Conv)"""
+        if self.packed_t is not None:
+            return ops.conv_gemm_tc(geometry, transposed, a, self.packed_t, out, **kwargs)
+        return ops.conv_gemm(geometry, transposed, a, self.wt, out, **kwargs)
 
     def finish(self):
         """Weight-norm backward: gw -> gradients of weight_g and weight_v"""
@@ -57,8 +75,14 @@ class Conv:
 class Layers:
     """The convolutions of one module, with flat derived / scratch storage"""
 
-    def __init__(self, params):
+    # a GEMM goes to the tensor cores when both its row and reduction channel counts reach this
+    TENSOR_CORE_MIN_CHANNELS = 16
+
+    def __init__(self, params, math='tf32'):
+        if math not in ('tf32', 'fp32'):
+            raise ValueError(f'unknown math mode {math}')
         self.params = params
+        self.math = math
         self.layers = []
 
     def conv(self, prefix):
@@ -73,6 +97,18 @@ class Layers:
         self.folded = torch.empty(normed, device=device)
         self.transposed = torch.empty(total, device=device)
         self.scratch = torch.zeros(normed, device=device)
+        packable = [
+            layer for layer in self.layers
+            if self.math == 'tf32' and min(layer.dim0, layer.dim1) >= self.TENSOR_CORE_MIN_CHANNELS]
+        sizes = [
+            (layer.dim0 * layer.taps * ops.channel_pad(layer.dim1),
+             layer.dim1 * layer.taps * ops.channel_pad(layer.dim0)) for layer in packable]
+        self.packed = torch.empty(sum(a + b for a, b in sizes), device=device)
+        offset = 0
+        for layer, (forward, backward) in zip(packable, sizes):
+            layer.packed = self.packed[offset:offset + forward]
+            layer.packed_t = self.packed[offset + forward:offset + forward + backward]
+            offset += forward + backward
         f = t = 0
         for layer in self.layers:
             layer.wt = self.transposed[t:t + layer.numel]

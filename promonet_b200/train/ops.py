@@ -45,6 +45,28 @@ def conv_gemm(geom, transposed, a, wmat, out, a_companion=None, a_act=ACT_NONE, 
     return out
 
 
+def conv_gemm_tc(geom, transposed, a, wpacked, out, a_companion=None, a_act=ACT_NONE, a_slope=1.,
+                 bias=None, bias2=None, out_act=OUT_NONE, out_slope=1., mask_src=None,
+                 mask_slope=1., residual=None, alpha=1., accumulate=False):
+    """conv_gemm on tcgen05 (tf32); wpacked from pack_weight_taps"""
+    _check(_lib.library().pmn_conv_gemm_tc(
+        ctypes.byref(geom), int(transposed), _lib.ptr(a), _lib.ptr(a_companion), a_act, a_slope,
+        _lib.ptr(wpacked), _lib.ptr(bias), _lib.ptr(bias2), out_act, out_slope,
+        _lib.ptr(mask_src), mask_slope, _lib.ptr(residual), alpha, int(accumulate),
+        _lib.ptr(out), _lib.stream()))
+    return out
+
+
+def channel_pad(channels):
+    return (channels + 31) // 32 * 32
+
+
+def pack_weight_taps(w, out, d0, d1, taps, transposed):
+    _check(_lib.library().pmn_pack_weight_taps(
+        _lib.ptr(w), _lib.ptr(out), d0, d1, taps, int(transposed), _lib.stream()))
+    return out
+
+
 def conv_wgrad(geom, dy, x, gw, gbias=None, dy_companion=None, dy_act=ACT_NONE, dy_slope=1.,
                x_companion=None, x_act=ACT_NONE, x_slope=1.):
     _check(_lib.library().pmn_conv_wgrad(

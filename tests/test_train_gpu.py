@@ -27,7 +27,7 @@ def states():
 @pytest.fixture(scope='module')
 def trainer(states):
     from promonet_b200.train.core import Trainer
-    return Trainer(*states)
+    return Trainer(*states, math='fp32')
 
 
 def to_device(batch):
@@ -69,7 +69,7 @@ def test_generator_training_forward_matches_oracle(states, trainer):
     assert relative_error(audio, expected) < FORWARD_TOLERANCE
 
 
-def compare_gradients(actual, expected, tolerance):
+def compare_gradients(actual, expected, tolerance, far=5e-2):
     """Per-tensor max|a - b| / max|b| against fp64 autograd.  The loss has discrete
     decisions (sign of the L1 terms, LeakyReLU masks) that fp32 rounding can flip at a
     near-zero value and that then move one layer's gradient by ~1e-2 (torch's own fp32
@@ -80,8 +80,8 @@ def compare_gradients(actual, expected, tolerance):
         ((relative_error(actual[name], reference), name) for name, reference in expected.items()),
         reverse=True)
     outliers = [e for e in errors if e[0] >= tolerance]
-    assert len(outliers) <= 4 and errors[0][0] < 5e-2, errors[:8]
-    assert errors[len(errors) // 2][0] < tolerance / 10, errors[len(errors) // 2]
+    assert len(outliers) <= 4 and errors[0][0] < far, errors[:8]
+    assert errors[len(errors) // 2][0] < tolerance / 5, errors[len(errors) // 2]
 
 
 def test_step_gradients_match_autograd(states, trainer):
@@ -109,7 +109,7 @@ def test_two_steps_match_reference_golden(states):
     batch = oracle_train.batch(make_golden.TRAIN_BATCH, make_golden.TRAIN_FRAMES, make_golden.TRAIN_SEED)
     checksums = np.array([float(t.double().abs().sum()) for t in batch])
     np.testing.assert_allclose(checksums, golden['input_checksums'], rtol=1e-6)
-    trainer = Trainer(*states)
+    trainer = Trainer(*states, math='fp32')
     for step in range(make_golden.TRAIN_STEPS):
         losses = trainer.step(*to_device(batch)).cpu().numpy()
         # losses of step 1 depend on both optimizer updates of step 0
@@ -134,6 +134,24 @@ def test_two_steps_match_reference_golden(states):
         names = [str(n) for n in golden[f'{kind}_names']]
         sums = np.array([float(state[n].double().abs().sum()) for n in names])
         np.testing.assert_allclose(sums, golden[f'{kind}_param_checksums'], rtol=1e-4)
+
+
+def test_tensor_core_step_tracks_the_exact_step(states):
+    """math='tf32' (tcgen05 forward and data gradients) against fp64 autograd: the
+    tolerance is the operand precision (2^-11) compounded over ~40 layers"""
+    from promonet_b200.train.core import Trainer
+    batch = oracle_train.batch(2, 8, seed=21)
+    g_state = oracle_train.leaf_state(states[0], torch.float64)
+    d_state = oracle_train.leaf_state(states[1], torch.float64)
+    losses, g_grads, d_grads, generated = oracle_train.step(
+        g_state, d_state, [t.double() if t.is_floating_point() else t for t in batch])
+    trainer = Trainer(*states, math='tf32')
+    ours = trainer.step(*to_device(batch), update=False).cpu()
+    assert relative_error(trainer.generated, generated) < 5e-3
+    for i, name in enumerate(('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator')):
+        assert abs(float(ours[i]) - float(losses[name])) < 5e-3 * abs(float(losses[name])), name
+    compare_gradients(trainer.discriminators.params.gradients(), d_grads, 3e-2, far=.3)
+    compare_gradients(trainer.generator.params.gradients(), g_grads, 3e-2, far=.3)
 
 
 def test_checkpoint_round_trip(states, tmp_path):

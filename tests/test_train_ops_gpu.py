@@ -81,6 +81,71 @@ def test_conv_forward_dgrad_wgrad(ops, c_in, c_out, size, kernel, stride, dilati
     assert relative_error(gb, br.grad) < TOLERANCE
 
 
+TF32_TOLERANCE = 3e-3   # tf32 operands: 2^-11 relative rounding per operand, fp32 accumulation
+
+
+@pytest.mark.parametrize('c_in,c_out,size,kernel,stride,dilation,padding', CONVS)
+def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stride, dilation, padding):
+    """The tcgen05 (tf32) implicit GEMM against the same fp64 reference"""
+    torch.manual_seed(0)
+    batch = 3
+    x = torch.randn(batch, c_in, *size)
+    w = torch.randn(c_out, c_in, *kernel) / (c_in * kernel[0] * kernel[1]) ** .5
+    bias = torch.randn(c_out)
+    in_slope, out_slope = .1, .2
+    xr = x.double().requires_grad_()
+    y = F.leaky_relu(
+        F.conv2d(F.leaky_relu(xr, in_slope), w.double(), bias.double(), stride, padding, dilation),
+        out_slope)
+    dy = torch.randn(y.shape)
+    (y * dy.double()).sum().backward()
+    residual = torch.randn(y.shape)
+
+    geom = ops.geometry(batch, c_in, c_out, size, kernel, stride, dilation, padding)
+    taps = kernel[0] * kernel[1]
+    xd, wd, bd, dyd = (t.cuda().contiguous() for t in (x, w, bias, dy))
+    packed = ops.pack_weight_taps(
+        wd, torch.empty(c_out, taps, ops.channel_pad(c_in), device='cuda'), c_out, c_in, taps, False)
+    expected = torch.zeros(c_out, taps, ops.channel_pad(c_in))
+    expected[:, :, :c_in] = w.flatten(2).permute(0, 2, 1)
+    assert torch.equal(packed.cpu(), expected)
+    out = torch.full(y.shape, float('nan'), device='cuda')
+    ops.conv_gemm_tc(geom, False, xd, packed, out, a_act=ops.ACT_LRELU, a_slope=in_slope,
+                     bias=bd, out_act=ops.OUT_LRELU, out_slope=out_slope)
+    assert relative_error(out, y) < TF32_TOLERANCE
+    # epilogue: residual, alpha, accumulate
+    out2 = out.clone()
+    ops.conv_gemm_tc(geom, False, xd, packed, out2, a_act=ops.ACT_LRELU, a_slope=in_slope,
+                     bias=bd, residual=residual.cuda(), alpha=.5, accumulate=True)
+    pre = F.conv2d(F.leaky_relu(x.double(), in_slope), w.double(), bias.double(), stride, padding, dilation)
+    assert relative_error(out2, y.detach() + .5 * (pre + residual.double())) < TF32_TOLERANCE
+
+    packed_t = ops.pack_weight_taps(
+        wd, torch.empty(c_in, taps, ops.channel_pad(c_out), device='cuda'), c_out, c_in, taps, True)
+    dx = torch.full(x.shape, float('nan'), device='cuda')
+    exact = torch.empty(y.shape, device='cuda')
+    ops.conv_gemm(geom, False, xd, wd, exact, a_act=ops.ACT_LRELU, a_slope=in_slope,
+                  bias=bd, out_act=ops.OUT_LRELU, out_slope=out_slope)
+    ops.conv_gemm_tc(geom, True, dyd, packed_t, dx, a_companion=exact, a_act=ops.ACT_LRELU_MASK,
+                     a_slope=out_slope, mask_src=xd, mask_slope=in_slope)
+    assert relative_error(dx, xr.grad) < TF32_TOLERANCE
+
+
+def test_conv_tensor_core_large_shapes(ops):
+    """Several M and N tiles, K = 5 x 1024 (MPD conv4, discriminator.py:72)"""
+    torch.manual_seed(11)
+    x = torch.randn(4, 1024, 51, 3)
+    w = torch.randn(1024, 1024, 5, 1) / (1024 * 5) ** .5
+    bias = torch.randn(1024)
+    y = F.conv2d(x.double(), w.double(), bias.double(), 1, (2, 0))
+    geom = ops.geometry(4, 1024, 1024, (51, 3), (5, 1), 1, 1, (2, 0))
+    packed = ops.pack_weight_taps(
+        w.cuda(), torch.empty(1024, 5, 1024, device='cuda'), 1024, 1024, 5, False)
+    out = torch.empty(y.shape, device='cuda')
+    ops.conv_gemm_tc(geom, False, x.cuda(), packed, out, bias=bias.cuda())
+    assert relative_error(out, y) < TF32_TOLERANCE
+
+
 def test_conv_epilogue_residual_alpha_accumulate_tanh(ops):
     torch.manual_seed(1)
     x = torch.randn(2, 24, 130, 1)
