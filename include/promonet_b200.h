@@ -314,10 +314,11 @@ int pmn_conv_gemm(
 
 /* pmn_conv_gemm on the tcgen05 tensor cores: tf32 operands (10-bit mantissa), fp32
  * accumulation in TMEM (promonet_b200/csrc/train_conv_tc.cu).  Same arguments, except that the
- * weight is the tap-major packing made by pmn_pack_weight_taps (16-byte aligned):
- *   transposed = 0: pack(weight (c_out, c_in, kh, kw), transposed = 0) -> (c_out, taps, pad(c_in))
- *   transposed = 1: pack(weight (c_out, c_in, kh, kw), transposed = 1) -> (c_in, taps, pad(c_out))
- * pad(c) = pmn_conv_tc_channel_pad(c) (multiple of 32). */
+ * weight is the packing made by pmn_pack_weight_taps (16-byte aligned; the shared-memory
+ * images of the kernel's weight tiles, copied with cp.async.bulk):
+ *   transposed = 0: pack(weight (c_out, c_in, kh, kw), transposed = 0): rows c_out, reduce over c_in
+ *   transposed = 1: pack(weight (c_out, c_in, kh, kw), transposed = 1): rows c_in, reduce over c_out
+ * of pmn_conv_tc_packed_floats(rows, reduce, taps) floats.  out_act = PMN_OUT_TANH is not built. */
 int pmn_conv_gemm_tc(
     const pmn_conv_geometry* geometry, int transposed,
     const float* a, const float* a_companion, int a_act, float a_slope,
@@ -325,8 +326,17 @@ int pmn_conv_gemm_tc(
     int out_act, float out_slope, const float* mask_src, float mask_slope,
     const float* residual, float alpha, int accumulate, float* out, void* stream);
 int pmn_conv_tc_channel_pad(int channels);
-/* w (d0, d1, taps) -> out[a][tap][b] (transposed = 0, b padded to pad(d1)) or out[b][tap][a]
- * (transposed = 1, a padded to pad(d0)); padding is written as zeros */
+size_t pmn_conv_tc_packed_floats(int rows, int reduce, int taps);
+/* Profiling aid: while `counters` (device, 8 x int64) is non-NULL, CTA 0 of every tensor-core
+ * training convolution stores cycle counters there: [0] K loop, [1] waiting for the stage, [2] operand
+ * loads, [3] shared-memory stores + proxy fence, [4] CTA barrier, [5] MMA issue, [6] K steps, [7] until
+ * the accumulator is complete */
+void pmn_debug_train_tc_counters(void* counters);
+/* Timing experiments only (results become meaningless): bit 0 skips the activation loads,
+ * bit 1 the weight loads, bit 2 the MMAs */
+void pmn_debug_train_tc_mode(int mode);
+/* w (d0, d1, taps) -> [row tile][tap][32-channel block][k / 4][row in tile][4], rounded to tf32,
+ * rows = d0 (transposed = 0) or d1 (transposed = 1), padding written as zeros */
 int pmn_pack_weight_taps(
     const float* w, float* out, int d0, int d1, int taps, int transposed, void* stream);
 

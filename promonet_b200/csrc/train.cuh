@@ -42,6 +42,9 @@ int launch_conv_gemm(const ConvGemmArgs& args, cudaStream_t stream);
 // tap-major packed weight (rows, taps, conv_tc_channel_pad(reduction channels))
 int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream);
 int conv_tc_channel_pad(int channels);
+size_t conv_tc_packed_floats(int rows, int reduce, int taps);
+void set_train_tc_debug(long long* counters);
+void set_train_tc_debug_mode(int mode);
 int launch_pack_weight_taps(
     const float* w, float* out, int d0, int d1, int taps, int transposed, cudaStream_t stream);
 

@@ -49,6 +49,15 @@ int pmn_conv_gemm_tc(
 
 int pmn_conv_tc_channel_pad(int channels) { return conv_tc_channel_pad(channels); }
 
+size_t pmn_conv_tc_packed_floats(int rows, int reduce, int taps) {
+    if (rows <= 0 || reduce <= 0 || taps <= 0) return 0;
+    return conv_tc_packed_floats(rows, reduce, taps);
+}
+
+void pmn_debug_train_tc_mode(int mode) { set_train_tc_debug_mode(mode); }
+
+void pmn_debug_train_tc_counters(void* counters) { set_train_tc_debug(static_cast<long long*>(counters)); }
+
 int pmn_pack_weight_taps(
     const float* w, float* out, int d0, int d1, int taps, int transposed, void* stream) {
     return launch_pack_weight_taps(w, out, d0, d1, taps, transposed, (cudaStream_t)stream);

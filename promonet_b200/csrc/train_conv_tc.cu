@@ -27,16 +27,30 @@ namespace pmn {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kProducers = 512;        // gather / epilogue threads
+constexpr int kThreads = kProducers + 64;  // + the MMA issuing warp + the weight-copy warp
+constexpr int kStages = 3;
 constexpr int kBM = 128;
-constexpr int kKStep = 32;            // fp32 operands per row per stage
-constexpr int kChunks = kKStep / 4;   // 16-byte chunks per row per stage
+constexpr int kKStep = 32;            // fp32 operands per row per K step (one tap, 32 channels)
+constexpr int kPair = 2;              // K steps per pipeline stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t address = smem_u32(bar);
@@ -99,36 +113,48 @@ __device__ __forceinline__ float operand_act(float v, float companion, int act, 
     return v;
 }
 
+long long* g_debug_counters = nullptr;   // pmn_debug_train_tc_counters
+int g_debug_mode = 0;  // bit 0: skip A loads, bit 1: skip B loads, bit 2: skip MMAs (timing experiments)
+
 struct TcParams {
+    long long* debug;      // 8 cycle counters written by CTA 0 (profiling aid) or null
+    int debug_mode;
     ConvGemmArgs a;        // a.wmat = packed weights (o_ch, taps, c_pad)
     int a_ch, a_h, a_w;    // gathered tensor
     int o_ch, o_h, o_w;    // produced tensor
     int taps, c_pad, m_total, o_positions;
 };
 
-template <int BN, bool TRANSPOSED>
-__global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(TcParams p) {
-    constexpr uint32_t kABytes = kBM * kKStep * 4;
-    constexpr uint32_t kBBytes = BN * kKStep * 4;
+__device__ float g_zero_words[4] = {0.f, 0.f, 0.f, 0.f};  // what rows outside the input read
+
+template <int BN, bool TRANSPOSED, int A_ACT>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
+    constexpr uint32_t kABytes = kBM * kKStep * 4;            // one K step of A
+    constexpr uint32_t kBBytes = BN * kKStep * 4;             // one K step of B = one packed slab
+    constexpr uint32_t kStageBytes = kPair * (kABytes + kBBytes);
+    constexpr int kAPer = kBM * kKStep / kProducers;          // A operands per thread per K step (8)
+    constexpr bool kCompanion = A_ACT == kActLreluMask || A_ACT == kActTanhMask;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t mma_done[2];
+    __shared__ uint64_t full[kStages];    // 16 producer warps + the weight copy (with its bytes)
+    __shared__ uint64_t empty[kStages];   // tcgen05.commit: the MMAs that read the stage are done
     __shared__ uint64_t acc_done;
     __shared__ uint32_t tmem_slot;
-    auto a_stage = [&](int s) { return smem + s * kABytes; };
-    auto b_stage = [&](int s) { return smem + 2 * kABytes + s * kBBytes; };
 
     const pmn_conv_geometry& g = p.a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * kBM;
     const int n0 = blockIdx.y * BN;
+    constexpr int kMmaWarp = kProducers / 32, kCopyWarp = kMmaWarp + 1;
 
     if (tid == 0) {
-        mbar_init(mma_done + 0, 1);
-        mbar_init(mma_done + 1, 1);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(full + i, kProducers / 32 + 1);
+            mbar_init(empty + i, 1);
+        }
         mbar_init(&acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -138,127 +164,196 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // ---- A gather role: row tid % 128, channels (tid / 128) * 16 .. + 16 of each K step ----
-    const int arow = tid & (kBM - 1);
-    const int ahalf = tid >> 7;
-    const int m_load = m0 + arow;
-    const bool m_ok = m_load < p.m_total;
-    int hb, wb;
-    const float* a_base = p.a.a;
-    const float* c_base = p.a.a_companion;
-    {
-        const int mm = m_ok ? m_load : 0;
-        const int b = mm / p.o_positions;
-        const int rem = mm - b * p.o_positions;
-        const int oh = rem / p.o_w, ow = rem - oh * p.o_w;
-        if (TRANSPOSED) { hb = oh + g.ph; wb = ow + g.pw; }
-        else { hb = oh * g.sh - g.ph; wb = ow * g.sw - g.pw; }
-        const size_t offset = (size_t)b * p.a_ch * p.a_h * p.a_w;
-        a_base += offset;
-        if (c_base) c_base += offset;
-    }
-    const size_t plane = (size_t)p.a_h * p.a_w;
     const int blocks_per_tap = p.c_pad / kKStep;
     const int k_steps = p.taps * blocks_per_tap;
-    constexpr uint32_t idesc = instr_desc_tf32(kBM, BN);
+    const int stages_total = (k_steps + kPair - 1) / kPair;
+    const bool timing = p.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+    const long long begin = timing ? clock64() : 0;
+    // stage layout: [A step 0][A step 1][B step 0][B step 1]
+    auto stage_a = [&](int s, int sub) { return smem + s * kStageBytes + sub * kABytes; };
+    auto stage_b = [&](int s, int sub) { return smem + s * kStageBytes + kPair * kABytes + sub * kBBytes; };
 
-    int tap = 0, cb = 0;        // position of the NEXT step to gather
-    bool tap_ok = false;
-    size_t tap_offset = 0;
-    auto enter_tap = [&]() {
-        const int i = tap / g.kw, j = tap - i * g.kw;
-        int hi, wi;
-        bool ok = m_ok;
-        if (TRANSPOSED) {
-            const int th = hb - i * g.dh, tw = wb - j * g.dw;
-            hi = th / g.sh; wi = tw / g.sw;
-            ok = ok && th >= 0 && tw >= 0 && hi * g.sh == th && wi * g.sw == tw;
-        } else {
-            hi = hb + i * g.dh; wi = wb + j * g.dw;
-            ok = ok && hi >= 0 && wi >= 0;
-        }
-        ok = ok && hi < p.a_h && wi < p.a_w;
-        tap_ok = ok;
-        tap_offset = ok ? (size_t)hi * p.a_w + wi : 0;
-    };
-    enter_tap();
-
-    for (int step = 0; step < k_steps; ++step) {
-        const int s = step & 1;
-        if (step >= 2) mbar_wait(mma_done + s, ((step >> 1) - 1) & 1);
-        // ---- gather A: 16 channels of this row ----
-        {
-            const int c_first = cb * kKStep + ahalf * 16;
-            float v[16];
+    if (warp == kMmaWarp) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(kBM, BN);
+            long long t_wait = 0, mark = 0;
+            for (int it = 0; it < stages_total; ++it) {
+                const int s = it % kStages;
+                if (timing) mark = clock64();
+                mbar_wait(full + s, (it / kStages) & 1);
+                if (timing) t_wait += clock64() - mark;
+                tc_fence_after();
+                const int subs = min(kPair, k_steps - it * kPair);
+                for (int sub = 0; sub < subs; ++sub) {
+                    const uint32_t a_addr = smem_u32(stage_a(s, sub));
+                    const uint32_t b_addr = smem_u32(stage_b(s, sub));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int c = c_first + i;
-                float value = 0.f;
-                if (tap_ok && c < p.a_ch) {
-                    const size_t idx = (size_t)c * plane + tap_offset;
-                    value = __ldg(a_base + idx);
-                    if (p.a.a_act != kActNone)
-                        value = operand_act(value, c_base ? __ldg(c_base + idx) : 0.f,
-                                            p.a.a_act, p.a.a_slope);
+                    for (int kk = 0; kk < kKStep / 8; ++kk) {
+                        const uint64_t a_desc = smem_desc(a_addr + 2 * kk * kBM * 16, kBM * 16, 128);
+                        const uint64_t b_desc = smem_desc(b_addr + 2 * kk * BN * 16, BN * 16, 128);
+                        if (!(p.debug_mode & 4))
+                            tc_mma_tf32(tmem_base, a_desc, b_desc, idesc,
+                                        (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+                    }
                 }
+                tc_commit(empty + s);
+            }
+            tc_commit(&acc_done);
+            if (timing) { p.debug[5] = t_wait; p.debug[6] = k_steps; }
+        }
+    } else if (warp == kCopyWarp) {
+        // ===== weight copy: one thread, one bulk copy per stage (slabs are stored in K-step order) =====
+        if (lane == 0) {
+            const float* slabs = p.a.wmat + (size_t)blockIdx.y * k_steps * (BN * kKStep);
+            for (int it = 0; it < stages_total; ++it) {
+                const int s = it % kStages;
+                if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
+                const int subs = min(kPair, k_steps - it * kPair);
+                mbar_expect_tx(full + s, subs * kBBytes);
+                bulk_copy(stage_b(s, 0), slabs + (size_t)it * kPair * (BN * kKStep), subs * kBBytes, full + s);
+            }
+        }
+    } else {
+        // ===== producers: 512 threads gather the A tile of every K step =====
+        // row tid % 128, channels (tid / 128) * 8 .. + 8 of the step's 32 (two 16-byte chunks)
+        const int arow = tid & (kBM - 1);
+        const int aquarter = tid >> 7;
+        const int m_load = m0 + arow;
+        const bool m_ok = m_load < p.m_total;
+        int hb, wb;
+        const float* a_base = p.a.a;
+        const float* c_base = kCompanion ? p.a.a_companion : nullptr;
+        {
+            const int mm = m_ok ? m_load : 0;
+            const int b = mm / p.o_positions;
+            const int rem = mm - b * p.o_positions;
+            const int oh = rem / p.o_w, ow = rem - oh * p.o_w;
+            if (TRANSPOSED) { hb = oh + g.ph; wb = ow + g.pw; }
+            else { hb = oh * g.sh - g.ph; wb = ow * g.sw - g.pw; }
+            const size_t offset = (size_t)b * p.a_ch * p.a_h * p.a_w;
+            a_base += offset;
+            if (kCompanion) c_base += offset;
+        }
+        const int plane = p.a_h * p.a_w;
+        const bool padded = p.c_pad != p.a_ch;     // only then can a channel index run past the tensor
+
+        // (tap, channel block) of the K step being LOADED.  A row that falls outside the input at
+        // this tap reads a word of zeros with stride 0, so the loop has no per-element select.
+        int tap = 0, cb = 0, loaded = 0;
+        const float* tap_a = nullptr;
+        const float* tap_c = nullptr;
+        int tap_stride = 0;
+        auto enter_tap = [&]() {
+            const int i = tap / g.kw, j = tap - i * g.kw;
+            int hi, wi;
+            bool ok = m_ok;
+            if (TRANSPOSED) {
+                const int th = hb - i * g.dh, tw = wb - j * g.dw;
+                hi = th / g.sh; wi = tw / g.sw;
+                ok = ok && th >= 0 && tw >= 0 && hi * g.sh == th && wi * g.sw == tw;
+            } else {
+                hi = hb + i * g.dh; wi = wb + j * g.dw;
+                ok = ok && hi >= 0 && wi >= 0;
+            }
+            ok = ok && hi < p.a_h && wi < p.a_w;
+            const int offset = ok ? hi * p.a_w + wi : 0;
+            tap_a = ok ? a_base + offset : g_zero_words;
+            tap_c = ok ? c_base + offset : g_zero_words;
+            tap_stride = ok ? plane : 0;
+        };
+        enter_tap();
+
+        // issue the loads of the next K step (if any) into the given registers, then advance
+        auto issue_loads = [&](float (&va)[kAPer], float (&vc)[kAPer]) {
+            if (loaded >= k_steps) return;
+            const int c_first = cb * kKStep + aquarter * kAPer;
+#pragma unroll
+            for (int i = 0; i < kAPer; ++i) {
+                int c = c_first + i;
+                if (padded) c = min(c, p.a_ch - 1);   // its weights are zero
+                const size_t idx = (size_t)c * tap_stride;
+                va[i] = (p.debug_mode & 1) ? 1.f : __ldg(tap_a + idx);
+                if (kCompanion) vc[i] = __ldg(tap_c + idx);
+            }
+            ++loaded;
+            if (++cb == blocks_per_tap) {
+                cb = 0;
+                if (++tap < p.taps) enter_tap();
+            }
+        };
+        auto finish = [&](const float (&va)[kAPer], const float (&vc)[kAPer], float4 (&out)[kAPer / 4]) {
+            float v[kAPer];
+#pragma unroll
+            for (int i = 0; i < kAPer; ++i) {
+                float value = va[i];
+                if (A_ACT == kActLrelu) value = fmaxf(value, value * p.a.a_slope);   // slope in [0, 1]
+                else if (A_ACT == kActLreluMask) value = vc[i] > 0.f ? value : value * p.a.a_slope;
+                else if (A_ACT == kActTanhMask) value = value * (1.f - vc[i] * vc[i]);
                 v[i] = to_tf32(value);
             }
-            float4* dst = reinterpret_cast<float4*>(a_stage(s));
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                dst[(ahalf * 4 + q) * kBM + arow] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        // ---- gather B: warp w takes 16-byte chunk w of rows lane, lane + 32, ... ----
-        {
-            const size_t k_offset = (size_t)tap * p.c_pad + cb * kKStep + warp * 4;
-            const size_t row_stride = (size_t)p.taps * p.c_pad;
-            float4* dst = reinterpret_cast<float4*>(b_stage(s));
-#pragma unroll
-            for (int i = 0; i < BN / 32; ++i) {
-                const int n = lane + 32 * i;
-                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n0 + n < p.o_ch)
-                    w = __ldg(reinterpret_cast<const float4*>(p.a.wmat + (size_t)(n0 + n) * row_stride + k_offset));
-                dst[warp * BN + n] = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+            for (int q = 0; q < kAPer / 4; ++q)
+                out[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        };
+
+        float va0[kAPer], vc0[kAPer], va1[kAPer], vc1[kAPer];
+        long long t_wait = 0, t_store = 0, mark = 0;
+        issue_loads(va0, vc0);
+        issue_loads(va1, vc1);
+        for (int it = 0; it < stages_total; ++it) {
+            const int s = it % kStages;
+            const int subs = min(kPair, k_steps - it * kPair);
+            // finish this stage's operands and immediately reuse the registers for the next stage
+            float4 a0[kAPer / 4], a1[kAPer / 4];
+            finish(va0, vc0, a0);
+            issue_loads(va0, vc0);
+            if (subs > 1) {
+                finish(va1, vc1, a1);
+                issue_loads(va1, vc1);
             }
-        }
-        // advance to the next step's (tap, channel block)
-        if (++cb == blocks_per_tap) {
-            cb = 0;
-            if (++tap < p.taps) enter_tap();
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_stage(s)), b_addr = smem_u32(b_stage(s));
+            if (timing && tid == 0) mark = clock64();
+            if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
+            if (timing && tid == 0) { const long long now = clock64(); t_wait += now - mark; mark = now; }
+            float4* dst0 = reinterpret_cast<float4*>(stage_a(s, 0));
 #pragma unroll
-            for (int kk = 0; kk < kKStep / 8; ++kk) {
-                const uint64_t a_desc = smem_desc(a_addr + 2 * kk * kBM * 16, kBM * 16, 128);
-                const uint64_t b_desc = smem_desc(b_addr + 2 * kk * BN * 16, BN * 16, 128);
-                tc_mma_tf32(tmem_base, a_desc, b_desc, idesc, (step > 0 || kk > 0) ? 1u : 0u);
+            for (int q = 0; q < kAPer / 4; ++q)
+                dst0[(aquarter * (kAPer / 4) + q) * kBM + arow] = a0[q];
+            if (subs > 1) {
+                float4* dst1 = reinterpret_cast<float4*>(stage_a(s, 1));
+#pragma unroll
+                for (int q = 0; q < kAPer / 4; ++q)
+                    dst1[(aquarter * (kAPer / 4) + q) * kBM + arow] = a1[q];
             }
-            tc_commit(mma_done + s);
-            if (step == k_steps - 1) tc_commit(&acc_done);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + s);
+            if (timing && tid == 0) t_store += clock64() - mark;
+        }
+        if (timing && tid == 0) {
+            p.debug[0] = clock64() - begin; p.debug[1] = t_wait; p.debug[3] = t_store;
         }
     }
 
-    // ---- epilogue ----
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .., columns of group w / 4 ----
     mbar_wait(&acc_done, 0);
     tc_fence_after();
-    {
-        const int quad = warp & 3, half = warp >> 2;
+    if (timing && tid == 0) p.debug[7] = clock64() - begin;
+    constexpr int kGroups = BN >= 64 ? 4 : BN / 16;
+    constexpr int kGroupCols = BN / kGroups;
+    if (warp < 4 * kGroups) {
+        const int quad = warp & 3, group = warp >> 2;
         const int m = m0 + quad * 32 + lane;
         const bool ok = m < p.m_total;
         const int mm = ok ? m : 0;
         const int b = mm / p.o_positions;
         const int rem = mm - b * p.o_positions;
 #pragma unroll 1
-        for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+        for (int c0 = group * kGroupCols; c0 < (group + 1) * kGroupCols; c0 += 16) {
             uint32_t raw[16];
             __syncwarp();
             tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
-#pragma unroll
+#pragma unroll 4
             for (int i = 0; i < 16; ++i) {
                 const int n = n0 + c0 + i;
                 if (!ok || n >= p.o_ch) continue;
@@ -267,7 +362,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(TcParams p) {
                 if (p.a.bias) v += __ldg(p.a.bias + n);
                 if (p.a.bias2) v += __ldg(p.a.bias2 + (size_t)b * p.o_ch + n);
                 if (p.a.out_act == kOutLrelu) v = leaky(v, p.a.out_slope);
-                else if (p.a.out_act == kOutTanh) v = tanhf(v);
                 if (p.a.mask_src) v = __ldg(p.a.mask_src + idx) > 0.f ? v : v * p.a.mask_slope;
                 if (p.a.residual) v += __ldg(p.a.residual + idx);
                 v *= p.a.alpha;
@@ -278,71 +372,104 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_tc_kernel(TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kProducers / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      ::"r"(tmem_base), "n"(BN) : "memory");
     }
 }
 
-// w (d0, d1, taps) -> tap-major GEMM rows with the reduction channels padded to 32:
-//   transposed = 0: out[a][tap][b] (rows d0, reduce over d1: forward of a Conv, dgrad of a ConvTranspose)
-//   transposed = 1: out[b][tap][a] (rows d1, reduce over d0: data gradient of a Conv)
+__host__ __device__ inline int tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
+
+// w (d0, d1, taps) -> the shared-memory images the kernel copies in bulk.  The GEMM rows are
+// dim 0 (transposed = 0: forward of a Conv, data gradient of a ConvTranspose) or dim 1
+// (transposed = 1: data gradient of a Conv), the reduction runs tap-major over the other
+// dimension padded to 32.  Layout: [row tile][K step = tap x channel block][k / 4][row in tile][4],
+// values rounded to tf32, padding rows / channels zero.
 __global__ void pack_weight_taps_kernel(
     const float* __restrict__ w, float* __restrict__ out, int d0, int d1, int taps, int transposed,
-    int c_pad) {
-    const int rows = transposed ? d1 : d0;
-    const size_t total = (size_t)rows * taps * c_pad;
+    int c_pad, int bn, int row_tiles) {
+    const size_t total = (size_t)row_tiles * bn * taps * c_pad;
+    const int blocks = c_pad / kKStep;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % c_pad);
-        const size_t rest = idx / c_pad;
+        const int e = (int)(idx & 3);
+        size_t rest = idx >> 2;
+        const int local = (int)(rest % bn); rest /= bn;
+        const int chunk = (int)(rest % (kKStep / 4)); rest /= (kKStep / 4);
+        const int cb = (int)(rest % blocks); rest /= blocks;
         const int tap = (int)(rest % taps);
-        const int row = (int)(rest / taps);
-        const int reduce = transposed ? d0 : d1;
+        const int tile = (int)(rest / taps);
+        const int row = tile * bn + local;
+        const int c = cb * kKStep + chunk * 4 + e;
+        const int rows = transposed ? d1 : d0, reduce = transposed ? d0 : d1;
         float v = 0.f;
-        if (c < reduce) {
+        if (row < rows && c < reduce) {
             const int a = transposed ? c : row, b = transposed ? row : c;
-            v = w[((size_t)a * d1 + b) * taps + tap];
+            v = to_tf32(w[((size_t)a * d1 + b) * taps + tap]);
         }
         out[idx] = v;
     }
 }
 
-template <int BN>
-int launch_variant(const TcParams& p, cudaStream_t stream) {
-    const size_t smem = 2 * (kBM * kKStep * 4) + 2 * (BN * kKStep * 4);
-    static bool configured[2] = {false, false};
-    const int t = p.a.transposed ? 1 : 0;
-    if (!configured[t]) {
-        cudaError_t error = t
-            ? cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        PMN_TRY(check_cuda(error, "conv_gemm_tc smem attribute"));
-        configured[t] = true;
+template <int BN, bool TRANSPOSED, int A_ACT>
+int launch_instance(const TcParams& p, cudaStream_t stream) {
+    const size_t smem = (size_t)kStages * kPair * (kBM + BN) * kKStep * 4;
+    static bool configured = false;
+    if (!configured) {
+        PMN_TRY(check_cuda(
+            cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, TRANSPOSED, A_ACT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            "conv_gemm_tc smem attribute"));
+        configured = true;
     }
     dim3 grid(ceil_div(p.m_total, kBM), ceil_div(p.o_ch, BN));
     PMN_REQUIRE(grid.y <= 65535, "conv_gemm_tc: too many output channels");
-    LaunchScope scope(t ? "conv_dgrad_tc_kernel" : "conv_fprop_tc_kernel", stream);
-    if (t) conv_gemm_tc_kernel<BN, true><<<grid, kThreads, smem, stream>>>(p);
-    else conv_gemm_tc_kernel<BN, false><<<grid, kThreads, smem, stream>>>(p);
+    LaunchScope scope(TRANSPOSED ? "conv_dgrad_tc_kernel" : "conv_fprop_tc_kernel", stream);
+    conv_gemm_tc_kernel<BN, TRANSPOSED, A_ACT><<<grid, kThreads, smem, stream>>>(p);
     return launched("conv_gemm_tc_kernel");
+}
+
+template <int BN, bool TRANSPOSED>
+int launch_activation(const TcParams& p, cudaStream_t stream) {
+    switch (p.a.a_act) {
+        case kActNone: return launch_instance<BN, TRANSPOSED, kActNone>(p, stream);
+        case kActLrelu: return launch_instance<BN, TRANSPOSED, kActLrelu>(p, stream);
+        case kActLreluMask: return launch_instance<BN, TRANSPOSED, kActLreluMask>(p, stream);
+        default: return launch_instance<BN, TRANSPOSED, kActTanhMask>(p, stream);
+    }
+}
+
+template <int BN>
+int launch_variant(const TcParams& p, cudaStream_t stream) {
+    return p.a.transposed ? launch_activation<BN, true>(p, stream)
+                          : launch_activation<BN, false>(p, stream);
 }
 
 }  // namespace
 
+void set_train_tc_debug(long long* counters) { g_debug_counters = counters; }
+void set_train_tc_debug_mode(int mode) { g_debug_mode = mode; }
+
 int conv_tc_channel_pad(int channels) { return (channels + kKStep - 1) / kKStep * kKStep; }
+
+size_t conv_tc_packed_floats(int rows, int reduce, int taps) {
+    const int bn = tile_columns(rows);
+    return (size_t)ceil_div(rows, bn) * bn * taps * conv_tc_channel_pad(reduce);
+}
 
 int launch_pack_weight_taps(
     const float* w, float* out, int d0, int d1, int taps, int transposed, cudaStream_t stream) {
     PMN_REQUIRE(w && out && d0 > 0 && d1 > 0 && taps > 0, "pack_weight_taps: bad argument");
-    const int c_pad = conv_tc_channel_pad(transposed ? d0 : d1);
-    const size_t total = (size_t)(transposed ? d1 : d0) * taps * c_pad;
+    const int rows = transposed ? d1 : d0, reduce = transposed ? d0 : d1;
+    const int c_pad = conv_tc_channel_pad(reduce);
+    const int bn = tile_columns(rows);
+    const int row_tiles = ceil_div(rows, bn);
+    const size_t total = conv_tc_packed_floats(rows, reduce, taps);
     const int blocks = (int)min((size_t)2048, (total + 255) / 256);
     LaunchScope scope("pack_weight_taps_kernel", stream);
-    pack_weight_taps_kernel<<<blocks, 256, 0, stream>>>(w, out, d0, d1, taps, transposed, c_pad);
+    pack_weight_taps_kernel<<<blocks, 256, 0, stream>>>(
+        w, out, d0, d1, taps, transposed, c_pad, bn, row_tiles);
     return launched("pack_weight_taps_kernel");
 }
 
@@ -357,7 +484,12 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
                 "conv_gemm_tc: output larger than the padded input allows");
     PMN_REQUIRE(args.a_act == kActNone || args.a_act == kActLrelu || args.a_companion,
                 "conv_gemm_tc: this operand activation needs a companion tensor");
+    PMN_REQUIRE(args.out_act != kOutTanh, "conv_gemm_tc: tanh epilogue is not built (use pmn_conv_gemm)");
+    PMN_REQUIRE(args.a_act != kActLrelu || (args.a_slope >= 0.f && args.a_slope <= 1.f),
+                "conv_gemm_tc: LeakyReLU slope must be in [0, 1]");
     TcParams p;
+    p.debug = g_debug_counters;
+    p.debug_mode = g_debug_mode;
     p.a = args;
     if (args.transposed) {
         p.a_ch = g.c_out; p.a_h = g.h_out; p.a_w = g.w_out;
@@ -371,9 +503,11 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
     p.o_positions = p.o_h * p.o_w;
     PMN_REQUIRE((int64_t)g.batch * p.o_positions < ((int64_t)1 << 31), "conv_gemm_tc: too many positions");
     p.m_total = g.batch * p.o_positions;
-    if (p.o_ch > 64) return launch_variant<128>(p, stream);
-    if (p.o_ch > 32) return launch_variant<64>(p, stream);
-    return launch_variant<32>(p, stream);
+    switch (tile_columns(p.o_ch)) {
+        case 128: return launch_variant<128>(p, stream);
+        case 64: return launch_variant<64>(p, stream);
+        default: return launch_variant<32>(p, stream);
+    }
 }
 
 }  // namespace pmn

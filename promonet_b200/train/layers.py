@@ -101,8 +101,8 @@ class Layers:
             layer for layer in self.layers
             if self.math == 'tf32' and min(layer.dim0, layer.dim1) >= self.TENSOR_CORE_MIN_CHANNELS]
         sizes = [
-            (layer.dim0 * layer.taps * ops.channel_pad(layer.dim1),
-             layer.dim1 * layer.taps * ops.channel_pad(layer.dim0)) for layer in packable]
+            (ops.packed_floats(layer.dim0, layer.dim1, layer.taps),
+             ops.packed_floats(layer.dim1, layer.dim0, layer.taps)) for layer in packable]
         self.packed = torch.empty(sum(a + b for a, b in sizes), device=device)
         offset = 0
         for layer, (forward, backward) in zip(packable, sizes):

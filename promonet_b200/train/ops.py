@@ -61,6 +61,11 @@ def channel_pad(channels):
     return (channels + 31) // 32 * 32
 
 
+def packed_floats(rows, reduce, taps):
+    """Size of pack_weight_taps' output for a GEMM with `rows` output channels"""
+    return int(_lib.library().pmn_conv_tc_packed_floats(rows, reduce, taps))
+
+
 def pack_weight_taps(w, out, d0, d1, taps, transposed):
     _check(_lib.library().pmn_pack_weight_taps(
         _lib.ptr(w), _lib.ptr(out), d0, d1, taps, int(transposed), _lib.stream()))

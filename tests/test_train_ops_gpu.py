@@ -105,10 +105,14 @@ def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stri
     taps = kernel[0] * kernel[1]
     xd, wd, bd, dyd = (t.cuda().contiguous() for t in (x, w, bias, dy))
     packed = ops.pack_weight_taps(
-        wd, torch.empty(c_out, taps, ops.channel_pad(c_in), device='cuda'), c_out, c_in, taps, False)
-    expected = torch.zeros(c_out, taps, ops.channel_pad(c_in))
-    expected[:, :, :c_in] = w.flatten(2).permute(0, 2, 1)
-    assert torch.equal(packed.cpu(), expected)
+        wd, torch.empty(ops.packed_floats(c_out, c_in, taps), device='cuda'), c_out, c_in, taps, False)
+    # [row tile][tap][channel block][k / 4][row in tile][4], rounded to tf32 (10-bit mantissa)
+    bn = 128 if c_out > 64 else (64 if c_out > 32 else 32)
+    tiles, blocks = -(-c_out // bn), ops.channel_pad(c_in) // 32
+    expected = torch.zeros(tiles * bn, taps, blocks * 32)
+    expected[:c_out, :, :c_in] = w.flatten(2).permute(0, 2, 1)
+    expected = expected.view(tiles, bn, taps, blocks, 8, 4).permute(0, 2, 3, 4, 1, 5).reshape(-1)
+    assert float((packed.cpu() - expected).abs().max()) <= 2 ** -11 * float(expected.abs().max())
     out = torch.full(y.shape, float('nan'), device='cuda')
     ops.conv_gemm_tc(geom, False, xd, packed, out, a_act=ops.ACT_LRELU, a_slope=in_slope,
                      bias=bd, out_act=ops.OUT_LRELU, out_slope=out_slope)
@@ -121,7 +125,7 @@ def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stri
     assert relative_error(out2, y.detach() + .5 * (pre + residual.double())) < TF32_TOLERANCE
 
     packed_t = ops.pack_weight_taps(
-        wd, torch.empty(c_in, taps, ops.channel_pad(c_out), device='cuda'), c_out, c_in, taps, True)
+        wd, torch.empty(ops.packed_floats(c_in, c_out, taps), device='cuda'), c_out, c_in, taps, True)
     dx = torch.full(x.shape, float('nan'), device='cuda')
     exact = torch.empty(y.shape, device='cuda')
     ops.conv_gemm(geom, False, xd, wd, exact, a_act=ops.ACT_LRELU, a_slope=in_slope,
@@ -140,7 +144,7 @@ def test_conv_tensor_core_large_shapes(ops):
     y = F.conv2d(x.double(), w.double(), bias.double(), 1, (2, 0))
     geom = ops.geometry(4, 1024, 1024, (51, 3), (5, 1), 1, 1, (2, 0))
     packed = ops.pack_weight_taps(
-        w.cuda(), torch.empty(1024, 5, 1024, device='cuda'), 1024, 1024, 5, False)
+        w.cuda(), torch.empty(ops.packed_floats(1024, 1024, 5), device='cuda'), 1024, 1024, 5, False)
     out = torch.empty(y.shape, device='cuda')
     ops.conv_gemm_tc(geom, False, x.cuda(), packed, out, bias=bias.cuda())
     assert relative_error(out, y) < TF32_TOLERANCE
