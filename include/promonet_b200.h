@@ -350,6 +350,15 @@ int pmn_conv_wgrad(
     const float* x, const float* x_companion, int x_act, float x_slope,
     float* gw, float* gbias, void* stream);
 
+/* pmn_conv_wgrad on the tcgen05 tensor cores (tf32 operands, fp32 accumulation; the bias
+ * gradient rides along as a row of ones).  Built for the activation pairs of the training
+ * step: (dy_act, x_act) in {(NONE, NONE), (NONE, LRELU), (LRELU_MASK, NONE), (LRELU, NONE)}. */
+int pmn_conv_wgrad_tc(
+    const pmn_conv_geometry* geometry,
+    const float* dy, const float* dy_companion, int dy_act, float dy_slope,
+    const float* x, const float* x_companion, int x_act, float x_slope,
+    float* gw, float* gbias, void* stream);
+
 /* (dim0, dim1, taps) -> (dim1, dim0, taps) */
 int pmn_transpose_weight(
     const float* w, float* wt, int dim0, int dim1, int taps, void* stream);

@@ -1,6 +1,6 @@
 """Per-layer throughput of the training convolution kernels on the shapes of one training
 step (8 items x 16 384 samples per GPU): tcgen05 tf32 forward / data gradient
-(train_conv_tc.cu), fp32 FMA weight gradient (train_conv.cu).
+(train_conv_tc.cu), and weight gradient (train_conv_tc.cu).
 
     python profiles/bench_conv_tc.py [--wgrad] [--filter substring]
 """
@@ -95,7 +95,8 @@ def main():
         totals[0] += flop; totals[1] += forward; totals[2] += backward
         if args.wgrad:
             gw = torch.zeros_like(w)
-            weight = timed(lambda: ops.conv_wgrad(geom, dy, x, gw, None, x_act=ops.ACT_LRELU, x_slope=.1))
+            gb = torch.zeros(c_out, device='cuda')
+            weight = timed(lambda: ops.conv_wgrad_tc(geom, dy, x, gw, gb, x_act=ops.ACT_LRELU, x_slope=.1))
             line += f' {weight:9.3f} {flop / weight / 1e9:7.1f}'
             totals[3] += weight
         print(line)

@@ -126,6 +126,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,
          c_void_p, c_void_p, c_void_p]),
+    'pmn_conv_wgrad_tc': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,
+         c_void_p, c_void_p, c_void_p]),
     'pmn_transpose_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pmn_weight_norm_backward': (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

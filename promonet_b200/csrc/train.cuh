@@ -63,6 +63,7 @@ struct ConvWgradArgs {
 };
 
 int launch_conv_wgrad(const ConvWgradArgs& args, cudaStream_t stream);
+int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream);   // train_conv_tc.cu
 
 int launch_transpose_weight(
     const float* w, float* wt, int dim0, int dim1, int taps, cudaStream_t stream);

@@ -78,6 +78,20 @@ int pmn_conv_wgrad(
     return launch_conv_wgrad(args, (cudaStream_t)stream);
 }
 
+int pmn_conv_wgrad_tc(
+    const pmn_conv_geometry* geometry,
+    const float* dy, const float* dy_companion, int dy_act, float dy_slope,
+    const float* x, const float* x_companion, int x_act, float x_slope,
+    float* gw, float* gbias, void* stream) {
+    PMN_REQUIRE(geometry, "conv_wgrad_tc: null geometry");
+    ConvWgradArgs args;
+    args.g = *geometry;
+    args.dy = dy; args.dy_companion = dy_companion; args.dy_act = dy_act; args.dy_slope = dy_slope;
+    args.x = x; args.x_companion = x_companion; args.x_act = x_act; args.x_slope = x_slope;
+    args.gw = gw; args.gbias = gbias;
+    return launch_conv_wgrad_tc(args, (cudaStream_t)stream);
+}
+
 int pmn_transpose_weight(
     const float* w, float* wt, int dim0, int dim1, int taps, void* stream) {
     return launch_transpose_weight(w, wt, dim0, dim1, taps, (cudaStream_t)stream);

@@ -446,6 +446,256 @@ int launch_variant(const TcParams& p, cudaStream_t stream) {
                           : launch_activation<BN, false>(p, stream);
 }
 
+
+// ---------------------------------------------------------------------------
+// Weight gradient on the tensor cores
+// ---------------------------------------------------------------------------
+//   gw[n, (c, tap)] += sum_{b, pos} act(dy)[b, n, pos] * act(x)[b, c, in(pos, tap)]
+// GEMM view: M = 128 (c, tap) columns of the weight matrix per CTA (TMEM lanes; consecutive
+// lanes are consecutive addresses of gw, so the atomic epilogue is coalesced), N = BN output
+// channels, K = positions, 32 consecutive positions of one batch item per K step, the
+// position range split over gridDim.z.  Both operands are gathered by the 512 producer
+// threads into the [k / 4][row][4] layout (k = position).  The bias gradient rides along as
+// one extra row of ones: row `ncols` of the M dimension accumulates sum_pos dy[n, pos].
+
+struct TcWgradParams {
+    ConvWgradArgs a;
+    int taps, ncols, rows_total, o_positions, steps_per_item, steps_total, steps_per_split;
+};
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v, float companion, float slope) {
+    if (ACT == kActLrelu) return fmaxf(v, v * slope);
+    if (ACT == kActLreluMask) return companion > 0.f ? v : v * slope;
+    if (ACT == kActTanhMask) return v * (1.f - companion * companion);
+    return v;
+}
+
+template <int BN, int DY_ACT, int X_ACT>
+__global__ void __launch_bounds__(kProducers + 32, 1) conv_wgrad_tc_kernel(TcWgradParams p) {
+    constexpr uint32_t kABytes = kBM * kKStep * 4;
+    constexpr uint32_t kBBytes = BN * kKStep * 4;
+    constexpr uint32_t kStageBytes = kPair * (kABytes + kBBytes);
+    constexpr int kAPer = 8;                                   // positions per thread per K step
+    constexpr int kBThreads = BN * 4;                          // threads with a dy row segment
+    constexpr bool kDyCompanion = DY_ACT == kActLreluMask || DY_ACT == kActTanhMask;
+    static_assert(X_ACT == kActNone || X_ACT == kActLrelu, "x activation");
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full[kStages];
+    __shared__ uint64_t empty[kStages];
+    __shared__ uint64_t acc_done;
+    __shared__ uint32_t tmem_slot;
+
+    const pmn_conv_geometry& g = p.a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col0 = blockIdx.x * kBM;
+    const int n0 = blockIdx.y * BN;
+    const int t_begin = blockIdx.z * p.steps_per_split;
+    const int t_end = min(t_begin + p.steps_per_split, p.steps_total);
+    const int k_steps = t_end - t_begin;
+    constexpr int kMmaWarp = kProducers / 32;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(full + i, kProducers / 32);
+            mbar_init(empty + i, 1);
+        }
+        mbar_init(&acc_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const int stages_total = (k_steps + kPair - 1) / kPair;
+    auto stage_a = [&](int s, int sub) { return smem + s * kStageBytes + sub * kABytes; };
+    auto stage_b = [&](int s, int sub) { return smem + s * kStageBytes + kPair * kABytes + sub * kBBytes; };
+
+    if (warp == kMmaWarp) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(kBM, BN);
+            for (int it = 0; it < stages_total; ++it) {
+                const int s = it % kStages;
+                mbar_wait(full + s, (it / kStages) & 1);
+                tc_fence_after();
+                const int subs = min(kPair, k_steps - it * kPair);
+                for (int sub = 0; sub < subs; ++sub) {
+                    const uint32_t a_addr = smem_u32(stage_a(s, sub));
+                    const uint32_t b_addr = smem_u32(stage_b(s, sub));
+#pragma unroll
+                    for (int kk = 0; kk < kKStep / 8; ++kk) {
+                        const uint64_t a_desc = smem_desc(a_addr + 2 * kk * kBM * 16, kBM * 16, 128);
+                        const uint64_t b_desc = smem_desc(b_addr + 2 * kk * BN * 16, BN * 16, 128);
+                        tc_mma_tf32(tmem_base, a_desc, b_desc, idesc,
+                                    (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(empty + s);
+            }
+            tc_commit(&acc_done);
+        }
+    } else {
+        // ---- A role: weight-matrix column col0 + tid % 128, positions (tid / 128) * 8 .. + 8 ----
+        const int arow = tid & (kBM - 1);
+        const int aquarter = tid >> 7;
+        const int col = col0 + arow;
+        const bool is_ones = p.a.gbias != nullptr && col == p.ncols;   // the bias-gradient row
+        const bool col_ok = col < p.ncols;
+        int off_h = 0, off_w = 0;
+        size_t channel_offset = 0;
+        {
+            const int cc = col_ok ? col : 0;
+            const int c = cc / p.taps, tap = cc - c * p.taps;
+            const int ti = tap / g.kw, tj = tap - ti * g.kw;
+            off_h = ti * g.dh - g.ph;
+            off_w = tj * g.dw - g.pw;
+            channel_offset = (size_t)c * g.h_in * g.w_in;
+        }
+        const size_t x_item = (size_t)g.c_in * g.h_in * g.w_in;
+        // ---- B role: output channel n0 + tid % BN, positions (tid / BN) * 8 .. + 8 ----
+        const bool b_active = tid < kBThreads;
+        const int brow = tid % BN;
+        const int bsegment = tid / BN;          // 0..3 when active
+        const bool n_ok = b_active && n0 + brow < g.c_out;
+        const size_t dy_item = (size_t)g.c_out * p.o_positions;
+        const size_t dy_row = (size_t)(n_ok ? n0 + brow : 0) * p.o_positions;
+
+        int loaded = 0;
+        auto issue_loads = [&](float (&va)[kAPer], float (&vb)[kAPer], float (&vc)[kAPer]) {
+            if (loaded >= k_steps) return;
+            const int t = t_begin + loaded;
+            ++loaded;
+            const int b = t / p.steps_per_item;
+            const int p0 = (t - b * p.steps_per_item) * kKStep;
+            // x operand
+            {
+                const int first = p0 + aquarter * kAPer;
+                int oh = first / g.w_out, ow = first - oh * g.w_out;
+                const float* base = p.a.x + (size_t)b * x_item + channel_offset;
+#pragma unroll
+                for (int e = 0; e < kAPer; ++e) {
+                    const int hi = oh * g.sh + off_h, wi = ow * g.sw + off_w;
+                    const bool ok = col_ok && first + e < p.o_positions && hi >= 0 && hi < g.h_in &&
+                                    wi >= 0 && wi < g.w_in;
+                    const float* src = ok ? base + (size_t)hi * g.w_in + wi : g_zero_words;
+                    va[e] = __ldg(src);
+                    if (is_ones) va[e] = first + e < p.o_positions ? 1.f : 0.f;
+                    if (++ow == g.w_out) { ow = 0; ++oh; }
+                }
+            }
+            // dy operand
+            if (b_active) {
+                const int first = p0 + bsegment * kAPer;
+                const size_t base = (size_t)b * dy_item + dy_row + first;
+#pragma unroll
+                for (int e = 0; e < kAPer; ++e) {
+                    const bool ok = n_ok && first + e < p.o_positions;
+                    vb[e] = __ldg(ok ? p.a.dy + base + e : g_zero_words);
+                    if (kDyCompanion) vc[e] = __ldg(ok ? p.a.dy_companion + base + e : g_zero_words);
+                }
+            }
+        };
+        auto store = [&](int s, int sub, const float (&va)[kAPer], const float (&vb)[kAPer],
+                         const float (&vc)[kAPer]) {
+            float4* a_dst = reinterpret_cast<float4*>(stage_a(s, sub));
+            float4* b_dst = reinterpret_cast<float4*>(stage_b(s, sub));
+            float v[kAPer];
+#pragma unroll
+            for (int e = 0; e < kAPer; ++e) v[e] = to_tf32(apply_act<X_ACT>(va[e], 0.f, p.a.x_slope));
+            a_dst[(aquarter * 2 + 0) * kBM + arow] = make_float4(v[0], v[1], v[2], v[3]);
+            a_dst[(aquarter * 2 + 1) * kBM + arow] = make_float4(v[4], v[5], v[6], v[7]);
+            if (b_active) {
+#pragma unroll
+                for (int e = 0; e < kAPer; ++e)
+                    v[e] = to_tf32(apply_act<DY_ACT>(vb[e], kDyCompanion ? vc[e] : 0.f, p.a.dy_slope));
+                b_dst[(bsegment * 2 + 0) * BN + brow] = make_float4(v[0], v[1], v[2], v[3]);
+                b_dst[(bsegment * 2 + 1) * BN + brow] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        };
+
+        float va0[kAPer], vb0[kAPer], vc0[kAPer], va1[kAPer], vb1[kAPer], vc1[kAPer];
+        issue_loads(va0, vb0, vc0);
+        issue_loads(va1, vb1, vc1);
+        for (int it = 0; it < stages_total; ++it) {
+            const int s = it % kStages;
+            const int subs = min(kPair, k_steps - it * kPair);
+            if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
+            store(s, 0, va0, vb0, vc0);
+            issue_loads(va0, vb0, vc0);
+            if (subs > 1) {
+                store(s, 1, va1, vb1, vc1);
+                issue_loads(va1, vb1, vc1);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + s);
+        }
+    }
+
+    // ---- epilogue: lanes = weight columns (consecutive addresses), TMEM columns = channels ----
+    mbar_wait(&acc_done, 0);
+    tc_fence_after();
+    constexpr int kGroups = BN >= 64 ? 4 : BN / 16;
+    constexpr int kGroupCols = BN / kGroups;
+    if (warp < 4 * kGroups && k_steps > 0) {
+        const int quad = warp & 3, group = warp >> 2;
+        const int col = col0 + quad * 32 + lane;
+#pragma unroll 1
+        for (int c0 = group * kGroupCols; c0 < (group + 1) * kGroupCols; c0 += 16) {
+            uint32_t raw[16];
+            __syncwarp();
+            tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int n = n0 + c0 + i;
+                const float v = __uint_as_float(raw[i]);
+                if (n >= g.c_out || v == 0.f) continue;
+                if (col < p.ncols) atomicAdd(p.a.gw + (size_t)n * p.ncols + col, v);
+                else if (col == p.ncols && p.a.gbias) atomicAdd(p.a.gbias + n, v);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+template <int BN, int DY_ACT, int X_ACT>
+int launch_wgrad_instance(const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)kStages * kPair * (kBM + BN) * kKStep * 4;
+    static bool configured = false;
+    if (!configured) {
+        PMN_TRY(check_cuda(
+            cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, DY_ACT, X_ACT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+            "conv_wgrad_tc smem attribute"));
+        configured = true;
+    }
+    LaunchScope scope("conv_wgrad_tc_kernel", stream);
+    conv_wgrad_tc_kernel<BN, DY_ACT, X_ACT><<<grid, kProducers + 32, smem, stream>>>(p);
+    return launched("conv_wgrad_tc_kernel");
+}
+
+template <int BN>
+int launch_wgrad_activation(const TcWgradParams& p, dim3 grid, cudaStream_t stream) {
+    const int dy = p.a.dy_act, x = p.a.x_act;
+    if (dy == kActNone && x == kActNone) return launch_wgrad_instance<BN, kActNone, kActNone>(p, grid, stream);
+    if (dy == kActNone && x == kActLrelu) return launch_wgrad_instance<BN, kActNone, kActLrelu>(p, grid, stream);
+    if (dy == kActLreluMask && x == kActNone)
+        return launch_wgrad_instance<BN, kActLreluMask, kActNone>(p, grid, stream);
+    if (dy == kActLrelu && x == kActNone) return launch_wgrad_instance<BN, kActLrelu, kActNone>(p, grid, stream);
+    return fail(PMN_ERR_ARGUMENT, "conv_wgrad_tc: this activation pair is not built (use pmn_conv_wgrad)");
+}
+
 }  // namespace
 
 void set_train_tc_debug(long long* counters) { g_debug_counters = counters; }
@@ -471,6 +721,37 @@ int launch_pack_weight_taps(
     pack_weight_taps_kernel<<<blocks, 256, 0, stream>>>(
         w, out, d0, d1, taps, transposed, c_pad, bn, row_tiles);
     return launched("pack_weight_taps_kernel");
+}
+
+int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream) {
+    const pmn_conv_geometry& g = args.g;
+    PMN_REQUIRE(args.dy && args.x && args.gw, "conv_wgrad_tc: null pointer");
+    PMN_REQUIRE(g.batch > 0 && g.c_in > 0 && g.c_out > 0 && g.h_in > 0 && g.w_in > 0 &&
+                g.h_out > 0 && g.w_out > 0 && g.kh > 0 && g.kw > 0 && g.sh > 0 && g.sw > 0 &&
+                g.dh > 0 && g.dw > 0 && g.ph >= 0 && g.pw >= 0, "conv_wgrad_tc: bad geometry");
+    PMN_REQUIRE(args.dy_act == kActNone || args.dy_act == kActLrelu || args.dy_companion,
+                "conv_wgrad_tc: this dy activation needs a companion tensor");
+    TcWgradParams p;
+    p.a = args;
+    p.taps = g.kh * g.kw;
+    p.ncols = g.c_in * p.taps;
+    p.rows_total = p.ncols + (args.gbias ? 1 : 0);
+    p.o_positions = g.h_out * g.w_out;
+    p.steps_per_item = ceil_div(p.o_positions, kKStep);
+    p.steps_total = g.batch * p.steps_per_item;
+    const int bn = tile_columns(g.c_out);
+    const int tiles = ceil_div(p.rows_total, kBM) * ceil_div(g.c_out, bn);
+    // fill 148 SMs twice over, but keep at least 8 K steps per CTA
+    int splits = max(1, min(ceil_div(296, tiles), ceil_div(p.steps_total, 8)));
+    p.steps_per_split = ceil_div(p.steps_total, splits);
+    splits = ceil_div(p.steps_total, p.steps_per_split);
+    dim3 grid(ceil_div(p.rows_total, kBM), ceil_div(g.c_out, bn), splits);
+    PMN_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv_wgrad_tc: grid too large");
+    switch (bn) {
+        case 128: return launch_wgrad_activation<128>(p, grid, stream);
+        case 64: return launch_wgrad_activation<64>(p, grid, stream);
+        default: return launch_wgrad_activation<32>(p, grid, stream);
+    }
 }
 
 int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {

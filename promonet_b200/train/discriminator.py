@@ -63,8 +63,7 @@ class Period:
             act = (ops.ACT_LRELU_MASK, SLOPE) if i < 5 else (ops.ACT_NONE, 1.)
             g = gmaps[i]
             if weights:
-                ops.conv_wgrad(geometry, g, x, layers[i].gw, layers[i].gbias,
-                               dy_companion=y, dy_act=act[0], dy_slope=act[1])
+                layers[i].wgrad(geometry, g, x, dy_companion=y, dy_act=act[0], dy_slope=act[1])
             if i == 0 and gaudio is None:
                 break
             target = gmaps[i - 1] if i > 0 else None
@@ -146,7 +145,7 @@ class ComplexMultiBand:
         geometry = _with_batch(record['post_geometry'], n)
         joined = record['joined'][lo:hi]
         if weights:
-            ops.conv_wgrad(geometry, glogits, joined, self.post.gw, self.post.gbias)
+            self.post.wgrad(geometry, glogits, joined)
         gjoined = self.post.apply_transposed(
                         geometry, True, glogits, torch.empty_like(joined))
         gbanded = torch.zeros(n * frames * 513, device=gjoined.device) if gaudio is not None else None
@@ -165,8 +164,7 @@ class ComplexMultiBand:
                 geometry = _with_batch(record['geometries'][b][i], n)
                 y, x = chain[i + 1][lo:hi], chain[i][lo:hi]
                 if weights:
-                    ops.conv_wgrad(geometry, g, x, stack[i].gw, stack[i].gbias,
-                                   dy_companion=y, dy_act=ops.ACT_LRELU_MASK, dy_slope=SLOPE)
+                    stack[i].wgrad(geometry, g, x, dy_companion=y, dy_act=ops.ACT_LRELU_MASK, dy_slope=SLOPE)
                 if i == 0 and gaudio is None:
                     break
                 if i > 0:

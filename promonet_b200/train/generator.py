@@ -142,8 +142,7 @@ class Generator:
         new = lambda like: torch.empty_like(like)
         num_kernels = len(config.HIFIGAN_RESBLOCK_KERNEL_SIZES)
         audio, x_last, geometry = saved['audio'], saved['x_last'], saved['head_geometry']
-        ops.conv_wgrad(
-            geometry, gaudio, x_last, self.head.gw, None, dy_companion=audio,
+        self.head.wgrad(geometry, gaudio, x_last, bias=False, dy_companion=audio,
             dy_act=ops.ACT_TANH_MASK, x_act=ops.ACT_LRELU, x_slope=SLOPE)
         g = self.head.apply_transposed(
                         geometry, True, gaudio, new(x_last), a_companion=audio,
@@ -160,13 +159,11 @@ class Generator:
                     c1, c2 = block[m]
                     current, hidden, g1, g2 = record[m]
                     # x_next = current + c2(lrelu(hidden)) + b2
-                    ops.conv_wgrad(g2, gcurrent, hidden, c2.gw, c2.gbias,
-                                   x_act=ops.ACT_LRELU, x_slope=SLOPE)
+                    c2.wgrad(g2, gcurrent, hidden, x_act=ops.ACT_LRELU, x_slope=SLOPE)
                     ghidden = c2.apply_transposed(
                         g2, True, gcurrent, new(hidden), mask_src=hidden, mask_slope=SLOPE)
                     # hidden = c1(lrelu(current)) + b1
-                    ops.conv_wgrad(g1, ghidden, current, c1.gw, c1.gbias,
-                                   x_act=ops.ACT_LRELU, x_slope=SLOPE)
+                    c1.wgrad(g1, ghidden, current, x_act=ops.ACT_LRELU, x_slope=SLOPE)
                     if m > 0:
                         gcurrent = c1.apply_transposed(
                         g1, True, ghidden, new(current), mask_src=current,
@@ -181,14 +178,14 @@ class Generator:
             geometry = ops.geometry(
                 batch, c_out, c_in, (t_in * rate, 1), (kernel_size, 1), (rate, 1), 1,
                 ((kernel_size - rate) // 2, 0), size_out=(t_in, 1))
-            ops.conv_wgrad(geometry, x_in, gxu, up.gw, None, dy_act=ops.ACT_LRELU, dy_slope=SLOPE)
+            up.wgrad(geometry, x_in, gxu, bias=False, dy_act=ops.ACT_LRELU, dy_slope=SLOPE)
             ops.channel_sum(gxu, up.gbias, accumulate=True)
             g = up.apply(
                         geometry, False, gxu, new(x_in), mask_src=x_in, mask_slope=SLOPE)
         # input layer: x0 = conv7(features) + b + speaker projection
         P = self.params
         features, gvec = saved['features'], saved['gvec']
-        ops.conv_wgrad(saved['input_geometry'], g, features, self.input_conv.gw, self.input_conv.gbias)
+        self.input_conv.wgrad(saved['input_geometry'], g, features)
         gfeatures = self.input_conv.apply_transposed(
                         saved['input_geometry'], True, g, new(features))
         ops.embedding_backward(
@@ -197,8 +194,7 @@ class Generator:
         batch, channels, frames = g.shape
         gspeaker = ops.row_sum(
             g, torch.empty(batch, channels, device=self.device), batch * channels, frames)
-        ops.conv_wgrad(saved['speaker_geometry'], gspeaker, gvec, self.speaker_conv.gw,
-                       self.speaker_conv.gbias)
+        self.speaker_conv.wgrad(saved['speaker_geometry'], gspeaker, gvec)
         ggvec = self.speaker_conv.apply_transposed(
                         saved['speaker_geometry'], True, gspeaker, new(gvec))
         ops.embedding_backward(

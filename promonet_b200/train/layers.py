@@ -56,6 +56,18 @@ class Conv:
             return ops.conv_gemm_tc(geometry, transposed, a, self.packed, out, **kwargs)
         return ops.conv_gemm(geometry, transposed, a, self.w, out, **kwargs)
 
+    TENSOR_CORE_WGRAD = {
+        (ops.ACT_NONE, ops.ACT_NONE), (ops.ACT_NONE, ops.ACT_LRELU),
+        (ops.ACT_LRELU_MASK, ops.ACT_NONE), (ops.ACT_LRELU, ops.ACT_NONE)}
+
+    def wgrad(self, geometry, dy, x, bias=True, **kwargs):
+        """Accumulate the weight (and bias) gradient of the convolution `geometry`"""
+        gbias = self.gbias if bias else None
+        pair = (kwargs.get('dy_act', ops.ACT_NONE), kwargs.get('x_act', ops.ACT_NONE))
+        if self.packed is not None and pair in self.TENSOR_CORE_WGRAD:
+            return ops.conv_wgrad_tc(geometry, dy, x, self.gw, gbias, **kwargs)
+        return ops.conv_wgrad(geometry, dy, x, self.gw, gbias, **kwargs)
+
     def apply_transposed(self, geometry, transposed, a, out, **kwargs):
         """Rows = dim 1 of the weight, reducing over dim 0 (data gradient of a Conv)"""
         if self.packed_t is not None:

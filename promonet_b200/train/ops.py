@@ -80,6 +80,14 @@ def conv_wgrad(geom, dy, x, gw, gbias=None, dy_companion=None, dy_act=ACT_NONE, 
         _lib.stream()))
 
 
+def conv_wgrad_tc(geom, dy, x, gw, gbias=None, dy_companion=None, dy_act=ACT_NONE, dy_slope=1.,
+                  x_companion=None, x_act=ACT_NONE, x_slope=1.):
+    _check(_lib.library().pmn_conv_wgrad_tc(
+        ctypes.byref(geom), _lib.ptr(dy), _lib.ptr(dy_companion), dy_act, dy_slope,
+        _lib.ptr(x), _lib.ptr(x_companion), x_act, x_slope, _lib.ptr(gw), _lib.ptr(gbias),
+        _lib.stream()))
+
+
 def transpose_weight(w, wt, dim0, dim1, taps):
     _check(_lib.library().pmn_transpose_weight(
         _lib.ptr(w), _lib.ptr(wt), dim0, dim1, taps, _lib.stream()))

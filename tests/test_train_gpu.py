@@ -69,7 +69,7 @@ def test_generator_training_forward_matches_oracle(states, trainer):
     assert relative_error(audio, expected) < FORWARD_TOLERANCE
 
 
-def compare_gradients(actual, expected, tolerance, far=5e-2):
+def compare_gradients(actual, expected, tolerance, far=5e-2, outliers_allowed=4, median=None):
     """Per-tensor max|a - b| / max|b| against fp64 autograd.  The loss has discrete
     decisions (sign of the L1 terms, LeakyReLU masks) that fp32 rounding can flip at a
     near-zero value and that then move one layer's gradient by ~1e-2 (torch's own fp32
@@ -80,8 +80,8 @@ def compare_gradients(actual, expected, tolerance, far=5e-2):
         ((relative_error(actual[name], reference), name) for name, reference in expected.items()),
         reverse=True)
     outliers = [e for e in errors if e[0] >= tolerance]
-    assert len(outliers) <= 4 and errors[0][0] < far, errors[:8]
-    assert errors[len(errors) // 2][0] < tolerance / 5, errors[len(errors) // 2]
+    assert len(outliers) <= outliers_allowed and errors[0][0] < far, (len(outliers), errors[:8])
+    assert errors[len(errors) // 2][0] < (median or tolerance / 5), errors[len(errors) // 2]
 
 
 def test_step_gradients_match_autograd(states, trainer):
@@ -137,8 +137,12 @@ def test_two_steps_match_reference_golden(states):
 
 
 def test_tensor_core_step_tracks_the_exact_step(states):
-    """math='tf32' (tcgen05 forward and data gradients) against fp64 autograd: the
-    tolerance is the operand precision (2^-11) compounded over ~40 layers"""
+    """math='tf32' (tcgen05 forward and data gradients) against fp64 autograd.  Yardstick:
+    the reference trains under fp16 autocast (train/core.py:220,262), i.e. with the same
+    10-bit operand mantissa as tf32 plus fp16 storage of every activation.  On this exact
+    batch torch's CPU autocast(float16) of the oracle step is off from fp64 by
+    max 3.9e-1 / median 2.8e-2 (93 tensors above 3e-2) on the generator gradients and
+    max 3.0e-2 / median 5.4e-3 on the discriminator's; the tf32 path must do better."""
     from promonet_b200.train.core import Trainer
     batch = oracle_train.batch(2, 8, seed=21)
     g_state = oracle_train.leaf_state(states[0], torch.float64)
@@ -150,8 +154,9 @@ def test_tensor_core_step_tracks_the_exact_step(states):
     assert relative_error(trainer.generated, generated) < 5e-3
     for i, name in enumerate(('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator')):
         assert abs(float(ours[i]) - float(losses[name])) < 5e-3 * abs(float(losses[name])), name
-    compare_gradients(trainer.discriminators.params.gradients(), d_grads, 3e-2, far=.3)
-    compare_gradients(trainer.generator.params.gradients(), g_grads, 3e-2, far=.3)
+    compare_gradients(trainer.discriminators.params.gradients(), d_grads, 3e-2, far=.1, median=1e-2)
+    compare_gradients(trainer.generator.params.gradients(), g_grads, 3e-2, far=.25,
+                      outliers_allowed=80, median=2e-2)
 
 
 def test_checkpoint_round_trip(states, tmp_path):

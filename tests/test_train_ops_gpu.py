@@ -135,6 +135,92 @@ def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stri
     assert relative_error(dx, xr.grad) < TF32_TOLERANCE
 
 
+EXACT = [
+    # c_in, c_out, size, kernel, stride, dilation, padding, batch: every pipeline shape case
+    (32, 32, (2048, 1), (3, 1), 1, (1, 1), (1, 0), 2),       # 3 K steps (odd), BN 32
+    (32, 32, (2048, 1), (11, 1), 1, (5, 1), (25, 0), 2),     # 11 K steps, halo 25
+    (64, 64, (1024, 1), (7, 1), 1, (3, 1), (9, 0), 2),       # BN 64, 14 K steps
+    (256, 256, (64, 1), (3, 1), 1, (1, 1), (1, 0), 2),       # one M tile, two N tiles, 24 K steps
+    (113, 512, (8, 1), (7, 1), 1, 1, (3, 0), 2),             # padded channels, 16 rows only
+    (128, 512, (38, 2), (5, 1), (3, 1), 1, (2, 0), 4),       # strided, M = 104 < one tile
+    (32, 32, (8, 77), (3, 9), (1, 2), 1, (1, 4), 4),         # 27 taps
+    (258, 512, (1, 1), (1, 1), 1, 1, 0, 2),                  # speaker projection: 2 rows
+]
+
+
+@pytest.mark.parametrize('c_in,c_out,size,kernel,stride,dilation,padding,batch', EXACT)
+def test_conv_tensor_core_is_exact_on_small_integers(
+        ops, c_in, c_out, size, kernel, stride, dilation, padding, batch):
+    """Integer operands are exact in tf32 and their sums exact in fp32, so the tcgen05 path
+    must reproduce the fp64 reference bit for bit: any pipeline race or indexing slip shows"""
+    torch.manual_seed(12)
+    x = torch.randint(-3, 4, (batch, c_in, *size)).float()
+    w = torch.randint(-2, 3, (c_out, c_in, *kernel)).float()
+    y = F.conv2d(x.double(), w.double(), None, stride, padding, dilation)
+    dy = torch.randint(-3, 4, y.shape).float()
+    dx = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), stride, padding, dilation)
+    geom = ops.geometry(batch, c_in, c_out, size, kernel, stride, dilation, padding)
+    taps = kernel[0] * kernel[1]
+    xd, wd, dyd = x.cuda(), w.cuda(), dy.cuda()
+    packed = ops.pack_weight_taps(
+        wd, torch.empty(ops.packed_floats(c_out, c_in, taps), device='cuda'), c_out, c_in, taps, False)
+    packed_t = ops.pack_weight_taps(
+        wd, torch.empty(ops.packed_floats(c_in, c_out, taps), device='cuda'), c_out, c_in, taps, True)
+    for _ in range(3):
+        out = torch.full(y.shape, float('nan'), device='cuda')
+        ops.conv_gemm_tc(geom, False, xd, packed, out)
+        assert torch.equal(out.cpu().double(), y)
+        grad = torch.full(x.shape, float('nan'), device='cuda')
+        ops.conv_gemm_tc(geom, True, dyd, packed_t, grad)
+        assert torch.equal(grad.cpu().double(), dx)
+
+
+@pytest.mark.parametrize('c_in,c_out,size,kernel,stride,dilation,padding,batch', EXACT)
+def test_wgrad_tensor_core_is_exact_on_small_integers(
+        ops, c_in, c_out, size, kernel, stride, dilation, padding, batch):
+    torch.manual_seed(13)
+    x = torch.randint(-2, 3, (batch, c_in, *size)).float()
+    geom = ops.geometry(batch, c_in, c_out, size, kernel, stride, dilation, padding)
+    dy = torch.randint(-2, 3, (batch, c_out, geom.h_out, geom.w_out)).float()
+    gw = torch.nn.grad.conv2d_weight(
+        x.double(), (c_out, c_in, *kernel), dy.double(), stride, padding, dilation)
+    gb = dy.double().sum((0, 2, 3))
+    for _ in range(2):
+        out = torch.zeros(c_out, c_in, *kernel, device='cuda')
+        bias = torch.zeros(c_out, device='cuda')
+        ops.conv_wgrad_tc(geom, dy.cuda(), x.cuda(), out, bias)
+        assert torch.equal(out.cpu().double(), gw)
+        assert torch.equal(bias.cpu().double(), gb)
+
+
+@pytest.mark.parametrize('c_in,c_out,size,kernel,stride,dilation,padding', CONVS)
+def test_wgrad_tensor_core_with_activations(ops, c_in, c_out, size, kernel, stride, dilation, padding):
+    """The activation pairs of the training step against fp64 autograd"""
+    torch.manual_seed(14)
+    batch, slope = 3, .1
+    x = torch.randn(batch, c_in, *size)
+    w = torch.randn(c_out, c_in, *kernel) / (c_in * kernel[0] * kernel[1]) ** .5
+    geom = ops.geometry(batch, c_in, c_out, size, kernel, stride, dilation, padding)
+    # (NONE, LRELU): y = conv(lrelu(x)); (LRELU_MASK, NONE): y = lrelu(conv(x))
+    for dy_act, x_act in ((ops.ACT_NONE, ops.ACT_LRELU), (ops.ACT_LRELU_MASK, ops.ACT_NONE)):
+        wr = w.double().requires_grad_()
+        br = torch.zeros(c_out, dtype=torch.double, requires_grad=True)
+        source = F.leaky_relu(x.double(), slope) if x_act == ops.ACT_LRELU else x.double()
+        y = F.conv2d(source, wr, br, stride, padding, dilation)
+        if dy_act == ops.ACT_LRELU_MASK:
+            y = F.leaky_relu(y, slope)
+        dy = torch.randn(y.shape)
+        (y * dy.double()).sum().backward()
+        gw = torch.zeros(w.shape, device='cuda')
+        gb = torch.zeros(c_out, device='cuda')
+        ops.conv_wgrad_tc(
+            geom, dy.cuda(), x.cuda(), gw, gb,
+            dy_companion=y.detach().float().cuda() if dy_act == ops.ACT_LRELU_MASK else None,
+            dy_act=dy_act, dy_slope=slope, x_act=x_act, x_slope=slope)
+        assert relative_error(gw, wr.grad) < TF32_TOLERANCE
+        assert relative_error(gb, br.grad) < TF32_TOLERANCE
+
+
 def test_conv_tensor_core_large_shapes(ops):
     """Several M and N tiles, K = 5 x 1024 (MPD conv4, discriminator.py:72)"""
     torch.manual_seed(11)
