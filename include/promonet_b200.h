@@ -359,6 +359,21 @@ int pmn_conv_wgrad_tc(
     const float* x, const float* x_companion, int x_act, float x_slope,
     float* gw, float* gbias, void* stream);
 
+/* Everything a module's convolutions need after an optimizer step, in two launches: for each
+ * entry of the DEVICE table, w = g v / ||v|| when g is not NULL (else w is unused and the weight
+ * is read from v), then packed / packed_t = pmn_pack_weight_taps(weight, transposed = 0 / 1) and
+ * wt = pmn_transpose_weight(weight); any of packed, packed_t, wt may be NULL. */
+typedef struct {
+    const float* v;      /* weight_v, or the plain weight when g is NULL: (dim0, dim1, taps) */
+    const float* g;      /* weight_g (dim0) or NULL */
+    float* w;            /* folded weight out (when g is not NULL) */
+    float* packed;
+    float* packed_t;
+    float* wt;
+    int dim0, dim1, taps, reserved;
+} pmn_weight_desc;
+int pmn_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, void* stream);
+
 /* (dim0, dim1, taps) -> (dim1, dim0, taps) */
 int pmn_transpose_weight(
     const float* w, float* wt, int dim0, int dim1, int taps, void* stream);
@@ -390,11 +405,13 @@ int pmn_l1_mean(
     int accumulate, void* stream);
 
 /* torch.optim.AdamW step over a flat parameter buffer (train/core.py:63-64,256,366;
- * config/defaults.py:390-394); grad is multiplied by grad_scale first (1 / world size) */
+ * config/defaults.py:390-394); grad is multiplied by grad_scale first (1 / world size).  The
+ * step count t of the bias corrections is `step`, or *step_device (device float) when that is
+ * not NULL -- so that a captured CUDA graph of the training step stays valid as t advances. */
 int pmn_adamw(
     float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-    void* stream);
+    const float* step_device, void* stream);
 
 /* out[r] (+)= sum_c x[r, c] */
 int pmn_row_sum(const float* x, float* out, int rows, int cols, int accumulate, void* stream);

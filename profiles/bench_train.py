@@ -28,6 +28,7 @@ from oracle import train as oracle_train  # noqa: E402
 
 KERNELS = (
     'conv_fprop_tc_kernel', 'conv_dgrad_tc_kernel', 'conv_wgrad_tc_kernel', 'pack_weight_taps_kernel',
+    'fold_weights_kernel', 'pack_weights_kernel',
     'conv_fprop_kernel', 'conv_dgrad_kernel', 'conv_wgrad_kernel', 'conv_transpose1d_kernel',
     'weight_norm_fold_kernel', 'weight_norm_backward_kernel', 'transpose_weight_kernel',
     'stft_train_kernel', 'stft_train_backward_kernel', 'mel_loss_kernel', 'mel_kernel',
@@ -50,6 +51,7 @@ def main():
     parser.add_argument('--warmup', type=int, default=2)
     parser.add_argument('--no-cpu', action='store_true')
     parser.add_argument('--math', default='tf32', choices=['tf32', 'fp32'])
+    parser.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = parser.parse_args()
     rank, local_rank, world = parallel.environment()
     torch.cuda.set_device(local_rank)
@@ -58,14 +60,15 @@ def main():
     trainer = Trainer(init.hifigan_state(1234), init.discriminator_state(1234), device, math=args.math)
     trainer.broadcast_parameters()
     batch = [t.to(device).contiguous() for t in oracle_train.batch(args.batch, args.frames, 1234 + rank)]
+    run = trainer.step if args.eager else trainer.step_graphed
     for _ in range(args.warmup):
-        trainer.step(*batch)
+        run(*batch)
     start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
     parallel.barrier()
     before = _lib.launch_count()
     start.record()
     for _ in range(args.steps):
-        losses = trainer.step(*batch)
+        losses = run(*batch)
     stop.record()
     parallel.barrier()
     launches = (_lib.launch_count() - before) / args.steps
@@ -86,7 +89,8 @@ def main():
             'unit': 'items/s', 'n_gpus': world, 'ms_per_step': ms, 'batch_per_gpu': args.batch,
             'global_batch': items, 'frames': args.frames,
             'dtype': 'f32 (tf32 tensor-core products, fp32 accumulate)' if args.math == 'tf32' else 'f32',
-            'gpu_launches_per_step': launches,
+            'gpu_launches_per_step': launches if args.eager else None,
+            'launch': 'eager' if args.eager else 'three CUDA graphs per step + two NCCL all-reduces',
             'losses': dict(zip(('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator'),
                                [float(v) for v in losses.cpu()])),
             'tflops': args.batch * FLOP_PER_ITEM * (args.frames / 64) / (ms * 1e-3) / 1e12,

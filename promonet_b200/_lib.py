@@ -130,6 +130,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,
          c_void_p, c_void_p, c_void_p]),
+    'pmn_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pmn_transpose_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pmn_weight_norm_backward': (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -144,7 +145,7 @@ SIGNATURES = {
     'pmn_adamw': (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-         c_float, c_int, c_float, c_void_p]),
+         c_float, c_int, c_float, c_void_p, c_void_p]),
     'pmn_row_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pmn_features': (
         c_int,
@@ -168,6 +169,14 @@ SIGNATURES = {
     'pmn_copy_columns': (
         c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
 }
+
+
+class WeightDesc(ctypes.Structure):
+    """pmn_weight_desc"""
+    _fields_ = [
+        ('v', c_void_p), ('g', c_void_p), ('w', c_void_p), ('packed', c_void_p),
+        ('packed_t', c_void_p), ('wt', c_void_p),
+        ('dim0', c_int), ('dim1', c_int), ('taps', c_int), ('reserved', c_int)]
 
 
 class ConvGeometry(ctypes.Structure):

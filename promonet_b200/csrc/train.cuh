@@ -43,6 +43,7 @@ int launch_conv_gemm(const ConvGemmArgs& args, cudaStream_t stream);
 int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream);
 int conv_tc_channel_pad(int channels);
 size_t conv_tc_packed_floats(int rows, int reduce, int taps);
+int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, cudaStream_t stream);
 void set_train_tc_debug(long long* counters);
 void set_train_tc_debug_mode(int mode);
 int launch_pack_weight_taps(
@@ -88,7 +89,7 @@ int launch_l1_mean(
 int launch_adamw(
     float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-    cudaStream_t stream);
+    const float* step_device, cudaStream_t stream);
 int launch_row_sum(
     const float* x, float* out, int rows, int cols, int accumulate, cudaStream_t stream);
 int launch_channel_sum(

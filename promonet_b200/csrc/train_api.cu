@@ -92,6 +92,10 @@ int pmn_conv_wgrad_tc(
     return launch_conv_wgrad_tc(args, (cudaStream_t)stream);
 }
 
+int pmn_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, void* stream) {
+    return launch_prepare_weights(table, layers, max_dim0, (cudaStream_t)stream);
+}
+
 int pmn_transpose_weight(
     const float* w, float* wt, int dim0, int dim1, int taps, void* stream) {
     return launch_transpose_weight(w, wt, dim0, dim1, taps, (cudaStream_t)stream);
@@ -132,10 +136,10 @@ int pmn_l1_mean(
 int pmn_adamw(
     float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-    void* stream) {
+    const float* step_device, void* stream) {
     return launch_adamw(
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-        (cudaStream_t)stream);
+        step_device, (cudaStream_t)stream);
 }
 
 int pmn_row_sum(const float* x, float* out, int rows, int cols, int accumulate, void* stream) {

@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
 }
 
 __host__ __device__ inline int tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
+__host__ __device__ inline int conv_tc_pad(int channels) { return (channels + kKStep - 1) / kKStep * kKStep; }
 
 // w (d0, d1, taps) -> the shared-memory images the kernel copies in bulk.  The GEMM rows are
 // dim 0 (transposed = 0: forward of a Conv, data gradient of a ConvTranspose) or dim 1
@@ -696,6 +697,76 @@ int launch_wgrad_activation(const TcWgradParams& p, dim3 grid, cudaStream_t stre
     return fail(PMN_ERR_ARGUMENT, "conv_wgrad_tc: this activation pair is not built (use pmn_conv_wgrad)");
 }
 
+
+// One launch for every convolution of a module: fold the weight norm (block per output
+// row) ...
+__global__ void __launch_bounds__(256) fold_weights_kernel(const pmn_weight_desc* table) {
+    const pmn_weight_desc d = table[blockIdx.y];
+    if ((int)blockIdx.x >= d.dim0 || d.g == nullptr) return;
+    __shared__ float partial[32];
+    const int inner = d.dim1 * d.taps;
+    const float* row = d.v + (size_t)blockIdx.x * inner;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) sum = fmaf(row[i], row[i], sum);
+    for (int offset = 16; offset > 0; offset >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, offset);
+    if ((threadIdx.x & 31) == 0) partial[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? partial[threadIdx.x] : 0.f;
+        for (int offset = 16; offset > 0; offset >>= 1) t += __shfl_xor_sync(0xffffffffu, t, offset);
+        if (threadIdx.x == 0) partial[0] = t;
+    }
+    __syncthreads();
+    const float scale = d.g[blockIdx.x] / sqrtf(partial[0]);
+    float* dst = d.w + (size_t)blockIdx.x * inner;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) dst[i] = row[i] * scale;
+}
+
+// ... then write both tensor-core packings (and, for the FMA path, the plain transpose)
+__global__ void __launch_bounds__(256) pack_weights_kernel(const pmn_weight_desc* table) {
+    const pmn_weight_desc d = table[blockIdx.y];
+    const float* w = d.g ? d.w : d.v;
+    const int blocks[2] = {conv_tc_pad(d.dim1) / kKStep, conv_tc_pad(d.dim0) / kKStep};
+    const int bn[2] = {tile_columns(d.dim0), tile_columns(d.dim1)};
+    const int rows[2] = {d.dim0, d.dim1};
+    float* out[2] = {d.packed, d.packed_t};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (!out[t]) continue;
+        const int tiles = (rows[t] + bn[t] - 1) / bn[t];
+        const size_t total = (size_t)tiles * bn[t] * d.taps * blocks[t] * kKStep;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const int e = (int)(idx & 3);
+            size_t rest = idx >> 2;
+            const int local = (int)(rest % bn[t]); rest /= bn[t];
+            const int chunk = (int)(rest % (kKStep / 4)); rest /= (kKStep / 4);
+            const int cb = (int)(rest % blocks[t]); rest /= blocks[t];
+            const int tap = (int)(rest % d.taps);
+            const int tile = (int)(rest / d.taps);
+            const int row = tile * bn[t] + local;
+            const int c = cb * kKStep + chunk * 4 + e;
+            const int reduce = t ? d.dim0 : d.dim1;
+            float v = 0.f;
+            if (row < rows[t] && c < reduce) {
+                const int a = t ? c : row, b = t ? row : c;
+                v = to_tf32(w[((size_t)a * d.dim1 + b) * d.taps + tap]);
+            }
+            out[t][idx] = v;
+        }
+    }
+    if (d.wt) {
+        const size_t total = (size_t)d.dim0 * d.dim1 * d.taps;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+             idx += (size_t)gridDim.x * blockDim.x) {
+            const int tap = (int)(idx % d.taps);
+            const size_t rest = idx / d.taps;
+            const int a = (int)(rest % d.dim0), b = (int)(rest / d.dim0);
+            d.wt[idx] = w[((size_t)a * d.dim1 + b) * d.taps + tap];
+        }
+    }
+}
+
 }  // namespace
 
 void set_train_tc_debug(long long* counters) { g_debug_counters = counters; }
@@ -721,6 +792,18 @@ int launch_pack_weight_taps(
     pack_weight_taps_kernel<<<blocks, 256, 0, stream>>>(
         w, out, d0, d1, taps, transposed, c_pad, bn, row_tiles);
     return launched("pack_weight_taps_kernel");
+}
+
+int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, cudaStream_t stream) {
+    PMN_REQUIRE(table && layers > 0 && layers <= 65535 && max_dim0 > 0, "prepare_weights: bad argument");
+    {
+        LaunchScope scope("fold_weights_kernel", stream);
+        fold_weights_kernel<<<dim3(max_dim0, layers), 256, 0, stream>>>(table);
+        PMN_TRY(launched("fold_weights_kernel"));
+    }
+    LaunchScope scope("pack_weights_kernel", stream);
+    pack_weights_kernel<<<dim3(64, layers), 256, 0, stream>>>(table);
+    return launched("pack_weights_kernel");
 }
 
 int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream) {

@@ -110,7 +110,14 @@ __global__ void __launch_bounds__(256) l1_mean_kernel(
 __global__ void adamw_kernel(
     float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
     float* __restrict__ exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-    float weight_decay, float correction1, float correction2_sqrt, float grad_scale) {
+    float weight_decay, float correction1, float correction2_sqrt, float grad_scale,
+    const float* __restrict__ step_device) {
+    if (step_device) {
+        // step count kept on the device so that a captured CUDA graph stays valid as it advances
+        const double t = (double)*step_device;
+        correction1 = (float)(1. - pow((double)beta1, t));
+        correction2_sqrt = (float)sqrt(1. - pow((double)beta2, t));
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float gr = grad[i] * grad_scale;
@@ -271,14 +278,15 @@ int launch_l1_mean(
 int launch_adamw(
     float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-    cudaStream_t stream) {
-    PMN_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adamw: bad argument");
+    const float* step_device, cudaStream_t stream) {
+    PMN_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_device),
+                "adamw: bad argument");
     const float correction1 = (float)(1. - pow((double)beta1, step));
     const float correction2_sqrt = (float)sqrt(1. - pow((double)beta2, step));
     LaunchScope scope("adamw_kernel", stream);
     adamw_kernel<<<grid_for(n), 256, 0, stream>>>(
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-        correction1, correction2_sqrt, grad_scale);
+        correction1, correction2_sqrt, grad_scale, step_device);
     return launched("adamw_kernel");
 }
 

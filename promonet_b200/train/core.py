@@ -57,12 +57,6 @@ class Trainer:
             for params in (self.generator.params, self.discriminators.params):
                 torch.distributed.broadcast(params.data, source, group=self.process_group)
 
-    def optimize(self, params):
-        self.all_reduce(params)
-        params.adamw(
-            config.LEARNING_RATE, config.ADAM_BETAS, config.ADAM_EPS, config.WEIGHT_DECAY,
-            grad_scale=1. / self.world)
-
     ###########################################################################
     # Step
     ###########################################################################
@@ -71,70 +65,146 @@ class Trainer:
              loudness_ratios, spectrograms, audio, update=True):
         """Batch tensors as collated by the reference (data/collate.py:43-60), on the device.
         Returns the five losses as a device tensor ordered like LOSSES (no host sync)."""
+        batch = (loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
+                 loudness_ratios, spectrograms, audio)
+        self._discriminator_phase(batch)
+        if update:
+            self.all_reduce(self.discriminators.params)
+        self._generator_phase(batch, update)
+        if update:
+            self.all_reduce(self.generator.params)
+        return self._final_phase(update)
+
+    # The step in three pieces, cut where the data-parallel gradient exchange happens, so that
+    # each piece can be captured in a CUDA graph (step_graphed)
+
+    def _discriminator_phase(self, batch):
+        """generator forward (:223), discriminator forward and backward (:239-255)"""
         G, D = self.generator, self.discriminators
-        batch, _, samples = audio.shape
-        losses = torch.zeros(len(LOSSES), device=self.device)
-        slot = lambda name: losses[LOSSES.index(name):LOSSES.index(name) + 1]
-
-        # ---- generator forward (:223), written next to the real audio ----
+        (loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio) = batch
+        count, _, samples = audio.shape
+        self.losses = torch.zeros(len(LOSSES), device=self.device)
+        slot = self._slot
         G.refresh()
-        both = torch.empty(2 * batch, 1, samples, device=self.device)
-        both[:batch].copy_(audio)
-        G.forward(loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
-                  loudness_ratios, out=both[batch:])
-
-        # ---- discriminator step (:239-256) ----
+        # generated audio is written next to the real audio: D runs once over both halves
+        both = torch.empty(2 * count, 1, samples, device=self.device)
+        both[:count].copy_(audio)
+        G.forward(loudness, pitch, periodicity, ppg, speakers, sbr, lr, out=both[count:])
+        self.both = both
         D.refresh()
         records = D.forward(both)
         gmaps = []
         for logits, maps in zip(D.logits(records), D.feature_maps(records)):
             glogits = torch.empty_like(logits)
-            ops.mse_to_target(logits[:batch], 1., 1., slot('discriminator'), glogits[:batch])
-            ops.mse_to_target(logits[batch:], 0., 1., slot('discriminator'), glogits[batch:])
+            ops.mse_to_target(logits[:count], 1., 1., slot('discriminator'), glogits[:count])
+            ops.mse_to_target(logits[count:], 0., 1., slot('discriminator'), glogits[count:])
             gmaps.append([None] * (len(maps) - 1) + [glogits.view(maps[-1].shape)])
         D.layers.zero_grad()
-        D.backward(records, gmaps, 0, 2 * batch, weights=True)
+        D.backward(records, gmaps, 0, 2 * count, weights=True)
+
+    def _generator_phase(self, batch, update=True):
+        """discriminator update (:256), second discriminator forward (:272), generator losses
+        (:277-332) and generator backward (:335-338)"""
+        G, D = self.generator, self.discriminators
+        spectrograms, audio = batch[7], batch[8]
+        count, _, samples = audio.shape
+        slot, both = self._slot, self.both
         if update:
             self.optimize(D.params)
             D.refresh()
-
-        # ---- generator step (:262-369) ----
         records = D.forward(both)
-        ggenerated = torch.zeros(batch, 1, samples, device=self.device)
+        ggenerated = torch.zeros(count, 1, samples, device=self.device)
         gmaps = []
         for logits, maps in zip(D.logits(records), D.feature_maps(records)):
             # feature matching (loss.py:11-26) seeds the gradient of every generated map
             gradients = []
             for fmap in maps:
-                g = torch.empty_like(fmap[batch:])
-                ops.l1_mean(fmap[batch:], fmap[:batch], config.FEATURE_MATCHING_LOSS_WEIGHT,
+                g = torch.empty_like(fmap[count:])
+                ops.l1_mean(fmap[count:], fmap[:count], config.FEATURE_MATCHING_LOSS_WEIGHT,
                             slot('feature_matching'), g)
                 gradients.append(g)
             # adversarial (loss.py:43-53) adds to the gradient of the logits
-            gadversarial = torch.empty_like(logits[batch:])
-            ops.mse_to_target(logits[batch:], 1., config.ADVERSARIAL_LOSS_WEIGHT,
+            gadversarial = torch.empty_like(logits[count:])
+            ops.mse_to_target(logits[count:], 1., config.ADVERSARIAL_LOSS_WEIGHT,
                               slot('adversarial'), gadversarial)
             ops.axpby(1., gadversarial.view(-1), 1., gradients[-1].view(-1))
             gmaps.append(gradients)
-        D.backward(records, gmaps, batch, 2 * batch, weights=False, gaudio=ggenerated)
+        D.backward(records, gmaps, count, 2 * count, weights=False, gaudio=ggenerated)
         # mel loss (:277-305)
         target_mels = ops.linear_to_mel(spectrograms)
-        magnitude, spectrum = ops.stft_magnitude(both[batch:].view(batch, samples), 'hann', 1e-6, 0)
+        magnitude, spectrum = ops.stft_magnitude(both[count:].view(count, samples), 'hann', 1e-6, 0)
         gmagnitude = torch.empty_like(magnitude)
         ops.mel_loss(magnitude, target_mels, 1., slot('mel'), gmagnitude, config.MEL_LOSS_WEIGHT)
         ops.stft_magnitude_backward(
-            gmagnitude, spectrum, ggenerated.view(batch, samples), 'hann', 1e-6, 0, accumulate=True)
+            gmagnitude, spectrum, ggenerated.view(count, samples), 'hann', 1e-6, 0, accumulate=True)
         G.layers.zero_grad()
         G.backward(ggenerated)
+        self.generated = both[count:]
+
+    def _final_phase(self, update=True):
+        """generator update (:366) and the total generator loss (:291,323-332), on the device"""
+        slot = self._slot
         if update:
-            self.optimize(G.params)
-        self.step_count += 1
-        self.generated = both[batch:]
-        # total generator loss (:291,323-332), on the device
+            self.optimize(self.generator.params)
         ops.axpby(config.MEL_LOSS_WEIGHT, slot('mel'), 0., slot('generator'))
         ops.axpby(1., slot('feature_matching'), 1., slot('generator'))
         ops.axpby(1., slot('adversarial'), 1., slot('generator'))
-        return losses
+        self.step_count += 1
+        return self.losses
+
+    def _slot(self, name):
+        index = LOSSES.index(name)
+        return self.losses[index:index + 1]
+
+    def optimize(self, params):
+        params.adamw(
+            config.LEARNING_RATE, config.ADAM_BETAS, config.ADAM_EPS, config.WEIGHT_DECAY,
+            grad_scale=1. / self.world)
+
+    ###########################################################################
+    # CUDA-graph replay of the step
+    ###########################################################################
+
+    def step_graphed(self, *batch):
+        """Same step with its ~1500 kernel launches replayed from three CUDA graphs (cut at the
+        two gradient all-reduces, which stay eager NCCL calls).  Shapes are fixed by the first
+        call; the batch is copied into static buffers."""
+        if getattr(self, 'graphs', None) is None:
+            self.static_batch = [t.clone() for t in batch]
+            stream = torch.cuda.Stream(self.device)
+            stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(stream):
+                for _ in range(2):   # warm-up: lazy tables, kernel attributes, allocator pools
+                    self.step(*self.static_batch, update=False)
+            torch.cuda.current_stream(self.device).wait_stream(stream)
+            self.step_count -= 2
+            self.graphs = []
+            pool = None
+            for phase in (
+                lambda: self._discriminator_phase(self.static_batch),
+                lambda: self._generator_phase(self.static_batch),
+                lambda: self._final_phase(),
+            ):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, pool=pool):
+                    phase()
+                pool = graph.pool()
+                self.graphs.append(graph)
+            # capturing does not execute: undo the host-side counters the phases advanced
+            self.step_count -= 1
+            self.discriminators.params.steps -= 1
+            self.generator.params.steps -= 1
+        for static, tensor in zip(self.static_batch, batch):
+            static.copy_(tensor, non_blocking=True)
+        self.graphs[0].replay()
+        self.all_reduce(self.discriminators.params)
+        self.graphs[1].replay()
+        self.all_reduce(self.generator.params)
+        self.graphs[2].replay()
+        self.step_count += 1
+        self.discriminators.params.steps += 1
+        self.generator.params.steps += 1
+        return self.losses
 
     ###########################################################################
     # Checkpoints (torchutil.checkpoint layout: train/core.py:426-438)

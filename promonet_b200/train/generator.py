@@ -25,6 +25,7 @@ class Generator:
             else torch.device(device)
         state = init.hifigan_state() if state is None else state
         self.params = ParamSet(state, self.device, BUFFERS)
+        self.ppg_threshold = float(state['ppg_threshold'])
         self.layers = Layers(self.params, math)
         conv = self.layers.conv
         self.input_conv = conv('model.input_feature_conv')
@@ -71,7 +72,7 @@ class Generator:
         edges = P.buffers['pitch_distribution']
         features = ops.features(
             loudness, pitch, periodicity, ppg, edges, P['pitch_embedding.weight'],
-            float(P.buffers['ppg_threshold']))
+            self.ppg_threshold)
         saved['bins'] = ops.pitch_bins(pitch, edges, config.FMIN, config.FMAX)
         saved['speakers'] = speakers
         gvec = ops.global_features(

@@ -52,7 +52,7 @@ class Conv:
     def apply(self, geometry, transposed, a, out, **kwargs):
         """Implicit GEMM with rows = dim 0 of the weight, reducing over dim 1 (forward of a
         Conv, data gradient of a ConvTranspose).  `transposed` is the gather direction."""
-        if self.packed is not None:
+        if self.packed is not None and kwargs.get('out_act') != ops.OUT_TANH:
             return ops.conv_gemm_tc(geometry, transposed, a, self.packed, out, **kwargs)
         return ops.conv_gemm(geometry, transposed, a, self.w, out, **kwargs)
 
@@ -88,7 +88,8 @@ class Layers:
     """The convolutions of one module, with flat derived / scratch storage"""
 
     # a GEMM goes to the tensor cores when both its row and reduction channel counts reach this
-    TENSOR_CORE_MIN_CHANNELS = 16
+    # (measured: even the 1-channel first and last layers are faster there than on the FMA tiles)
+    TENSOR_CORE_MIN_CHANNELS = 1
 
     def __init__(self, params, math='tf32'):
         if math not in ('tf32', 'fp32'):
@@ -132,10 +133,24 @@ class Layers:
             else:
                 layer.w = self.params[f'{layer.prefix}.weight']
                 layer.gw = self.params.gradient(f'{layer.prefix}.weight')
+        entries = []
+        for layer in self.layers:
+            key = 'weight_v' if layer.weight_norm else 'weight'
+            fma = layer.packed is None      # the FMA path needs the plain transpose
+            entries.append({
+                'v': self.params[f'{layer.prefix}.{key}'],
+                'g': self.params[f'{layer.prefix}.weight_g'] if layer.weight_norm else None,
+                'w': layer.w if layer.weight_norm else None,
+                'packed': layer.packed, 'packed_t': layer.packed_t,
+                'wt': layer.wt if fma else None,
+                'dim0': layer.dim0, 'dim1': layer.dim1, 'taps': layer.taps})
+        self.table = ops.weight_table(entries, device)
+        self.max_dim0 = max(layer.dim0 for layer in self.layers)
 
     def refresh(self):
-        for layer in self.layers:
-            layer.refresh()
+        """After an optimizer step: fold every weight norm and rebuild the operand
+        packings of every layer (two launches for the whole module)"""
+        ops.prepare_weights(self.table, len(self.layers), self.max_dim0)
 
     def zero_grad(self):
         self.params.zero_grad()

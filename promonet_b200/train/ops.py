@@ -88,6 +88,22 @@ def conv_wgrad_tc(geom, dy, x, gw, gbias=None, dy_companion=None, dy_act=ACT_NON
         _lib.stream()))
 
 
+def weight_table(entries, device):
+    """Device copy of a pmn_weight_desc array; entries are dicts of tensors / ints"""
+    table = (_lib.WeightDesc * len(entries))()
+    for desc, entry in zip(table, entries):
+        for name in ('v', 'g', 'w', 'packed', 'packed_t', 'wt'):
+            tensor = entry.get(name)
+            setattr(desc, name, _lib.ptr(tensor) if tensor is not None else None)
+        desc.dim0, desc.dim1, desc.taps = entry['dim0'], entry['dim1'], entry['taps']
+    raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
+    return raw.to(device)
+
+
+def prepare_weights(table, layers, max_dim0):
+    _check(_lib.library().pmn_prepare_weights(_lib.ptr(table), layers, max_dim0, _lib.stream()))
+
+
 def transpose_weight(w, wt, dim0, dim1, taps):
     _check(_lib.library().pmn_transpose_weight(
         _lib.ptr(w), _lib.ptr(wt), dim0, dim1, taps, _lib.stream()))
@@ -140,10 +156,12 @@ def l1_mean(fake, real, weight, loss, gfake=None, accumulate=False):
         int(accumulate), _lib.stream()))
 
 
-def adamw(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.):
+def adamw(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, grad_scale=1.,
+          step_device=None):
     _check(_lib.library().pmn_adamw(
         _lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), param.numel(),
-        lr, betas[0], betas[1], eps, weight_decay, step, grad_scale, _lib.stream()))
+        lr, betas[0], betas[1], eps, weight_decay, step, grad_scale, _lib.ptr(step_device),
+        _lib.stream()))
 
 
 def row_sum(x, out, rows, cols, accumulate=False):

@@ -36,6 +36,9 @@ class ParamSet:
         self.exp_avg = torch.zeros(offset, device=self.device)
         self.exp_avg_sq = torch.zeros(offset, device=self.device)
         self.steps = 0
+        # the step count also lives on the device (for CUDA-graph replay of the optimizer)
+        self.steps_device = torch.zeros(1, device=self.device)
+        self.one = torch.ones(1, device=self.device)
         self.load_state_dict(state)
 
     def _view(self, flat, name):
@@ -85,10 +88,12 @@ class ParamSet:
         self.exp_avg.copy_(state['exp_avg'])
         self.exp_avg_sq.copy_(state['exp_avg_sq'])
         self.steps = int(state['step'])
+        self.steps_device.fill_(float(self.steps))
 
     def adamw(self, lr, betas, eps, weight_decay, grad_scale=1.):
         """torch.optim.AdamW.step over every parameter (one launch)"""
         self.steps += 1
+        ops.axpby(1., self.one, 1., self.steps_device)
         ops.adamw(
             self.data, self.grad, self.exp_avg, self.exp_avg_sq, lr, betas, eps, weight_decay,
-            self.steps, grad_scale)
+            self.steps, grad_scale, self.steps_device)

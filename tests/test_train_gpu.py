@@ -159,6 +159,28 @@ def test_tensor_core_step_tracks_the_exact_step(states):
                       outliers_allowed=80, median=2e-2)
 
 
+def test_graph_replay_matches_eager_steps(states):
+    """step_graphed (three captured CUDA graphs, optimizer step count on the device) against
+    the eager step over three iterations with different batches"""
+    from promonet_b200.train.core import Trainer
+    eager, graphed = Trainer(*states, math='fp32'), Trainer(*states, math='fp32')
+    for i in range(3):
+        batch = to_device(oracle_train.batch(2, 8, seed=30 + i))
+        expected = eager.step(*batch).cpu()
+        actual = graphed.step_graphed(*batch).cpu()
+        # atomics make the weight gradients differ in the last bits; AdamW's first steps
+        # (update = lr * sign) can amplify that on near-zero gradients
+        assert relative_error(actual, expected) < 1e-3, i
+    assert graphed.step_count == eager.step_count == 3
+    assert graphed.generator.params.steps == 3
+    assert float(graphed.generator.params.steps_device) == 3.
+    for a, b in ((eager.generator, graphed.generator), (eager.discriminators, graphed.discriminators)):
+        difference = (a.params.data - b.params.data).abs()
+        # a parameter moves by at most lr = 2e-4 per step
+        assert float(difference.max()) <= 3 * 2e-4 * 1.01
+        assert float((difference > 1e-5).float().mean()) < 1e-2
+
+
 def test_checkpoint_round_trip(states, tmp_path):
     from promonet_b200.train.core import Trainer
     trainer = Trainer(*states)
