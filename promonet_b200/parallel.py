@@ -1,5 +1,6 @@
 """Multi-GPU host logic: one process per GPU, utterances sharded with no data-path
-collective (synthesis and preprocessing shard over independent utterances).
+collective (synthesis and preprocessing shard over independent utterances);
+training replicas exchange gradients with one all-reduce per optimizer.
 
 torch.distributed is plumbing here: rendezvous, a barrier around timed regions and a
 MAX reduction of per-rank device times.  Works on NCCL (GPU ranks) and gloo (CPU
@@ -72,6 +73,16 @@ def sum_over_ranks(value, device='cpu'):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
     return float(tensor)
+
+
+def all_reduce_sum(flat, group=None):
+    """Sum a module's flat gradient buffer over the data-parallel ranks in place (the
+    exchange step of the training path: one collective per optimizer); the mean
+    is taken by the optimizer kernel's grad_scale = 1 / world size"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
 
 
 def gather_utterances(local, count, rank, world, device='cpu'):

@@ -17,7 +17,7 @@ from pathlib import Path
 
 import torch
 
-from promonet_b200 import config
+from promonet_b200 import config, parallel
 from promonet_b200.train import ops
 from promonet_b200.train.discriminator import Discriminator
 from promonet_b200.train.generator import Generator
@@ -49,8 +49,7 @@ class Trainer:
     def all_reduce(self, params):
         """Sum the flat gradient buffer over ranks (NCCL over NVLink); the mean is taken
         by the optimizer kernel's grad_scale"""
-        if self.world > 1:
-            torch.distributed.all_reduce(params.grad, group=self.process_group)
+        parallel.all_reduce_sum(params.grad, self.process_group)
 
     def broadcast_parameters(self, source=0):
         if self.world > 1:

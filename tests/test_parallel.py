@@ -63,3 +63,58 @@ def test_two_rank_sharding_over_gloo(count):
         assert slowest == 11.      # max over ranks, not this rank's own time
         assert total == count      # every utterance processed exactly once
         assert torch.equal(whole, expected)
+
+
+def _gradient_worker(rank, world, port, queue):
+    """Each rank differentiates the LSGAN discriminator loss (oracle, CPU autograd) on its
+    shard of the batch, packs the gradients into the flat buffer the trainer all-reduces, and
+    averages them the way the optimizer kernel does (grad_scale = 1 / world)"""
+    os.environ.update(
+        RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+        MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    parallel.initialize('gloo')
+    torch.set_num_threads(2)
+    from oracle import train as oracle_train
+    from promonet_b200.model import init
+    from promonet_b200.train.params import ParamSet
+    state = oracle_train.leaf_state(init.discriminator_state(1234))
+    torch.manual_seed(7)
+    audio = .3 * torch.randn(2, 1, 2048)
+    generated = .3 * torch.randn(2, 1, 2048)
+
+    def gradients(real, fake):
+        for p in oracle_train.parameters(state).values():
+            p.grad = None
+        real_logits, fake_logits, _, _ = oracle_train.discriminator(state, real, fake)
+        oracle_train.discriminator_loss(real_logits, fake_logits).backward()
+        return {k: v.grad.clone() for k, v in oracle_train.parameters(state).items()}
+
+    whole = gradients(audio, generated)
+    mine = gradients(*parallel.shard_tensors([audio, generated], rank, world))
+    params = ParamSet({k: v.detach() for k, v in state.items()}, 'cpu')
+    for name, value in mine.items():
+        params.gradient(name).copy_(value)
+    parallel.all_reduce_sum(params.grad)
+    params.grad.mul_(1. / world)
+    worst = max(
+        float((params.gradient(k) - v).abs().max() / v.abs().max().clamp_min(1e-30))
+        for k, v in whole.items())
+    queue.put((rank, worst))
+    parallel.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_gradient_average_equals_the_full_batch_gradient():
+    context = mp.get_context('spawn')
+    queue = context.Queue()
+    port = _free_port()
+    workers = [
+        context.Process(target=_gradient_worker, args=(rank, 2, port, queue)) for rank in range(2)]
+    for worker in workers:
+        worker.start()
+    results = [queue.get(timeout=600) for _ in workers]
+    for worker in workers:
+        worker.join(timeout=60)
+        assert worker.exitcode == 0
+    for rank, worst in results:
+        assert worst < 1e-4, (rank, worst)
