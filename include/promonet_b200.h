@@ -332,9 +332,6 @@ size_t pmn_conv_tc_packed_floats(int rows, int reduce, int taps);
  * loads, [3] shared-memory stores + proxy fence, [4] CTA barrier, [5] MMA issue, [6] K steps, [7] until
  * the accumulator is complete */
 void pmn_debug_train_tc_counters(void* counters);
-/* Timing experiments only (results become meaningless): bit 0 skips the activation loads,
- * bit 1 the weight loads, bit 2 the MMAs */
-void pmn_debug_train_tc_mode(int mode);
 /* w (d0, d1, taps) -> [row tile][tap][32-channel block][k / 4][row in tile][4], rounded to tf32,
  * rows = d0 (transposed = 0) or d1 (transposed = 1), padding written as zeros */
 int pmn_pack_weight_taps(

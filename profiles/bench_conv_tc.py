@@ -52,10 +52,7 @@ def main():
     parser.add_argument('--filter', default='')
     parser.add_argument('--wgrad', action='store_true')
     parser.add_argument('--cycles', action='store_true', help='cycle breakdown of CTA 0 (forward)')
-    parser.add_argument('--mode', type=int, default=0, help='pmn_debug_train_tc_mode bits')
     args = parser.parse_args()
-    from promonet_b200 import _lib
-    _lib.library().pmn_debug_train_tc_mode(args.mode)
     print(f'{"layer":22s} {"GFLOP":>8s} {"fprop ms":>9s} {"TF/s":>7s} {"dgrad ms":>9s} {"TF/s":>7s}'
           + (f' {"wgrad ms":>9s} {"TF/s":>7s}' if args.wgrad else ''))
     totals = [0., 0., 0., 0.]

@@ -119,7 +119,6 @@ SIGNATURES = {
     'pmn_conv_tc_channel_pad': (c_int, [c_int]),
     'pmn_conv_tc_packed_floats': (c_size_t, [c_int, c_int, c_int]),
     'pmn_debug_train_tc_counters': (None, [c_void_p]),
-    'pmn_debug_train_tc_mode': (None, [c_int]),
     'pmn_pack_weight_taps': (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_conv_wgrad': (

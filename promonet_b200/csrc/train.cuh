@@ -45,7 +45,6 @@ int conv_tc_channel_pad(int channels);
 size_t conv_tc_packed_floats(int rows, int reduce, int taps);
 int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, cudaStream_t stream);
 void set_train_tc_debug(long long* counters);
-void set_train_tc_debug_mode(int mode);
 int launch_pack_weight_taps(
     const float* w, float* out, int d0, int d1, int taps, int transposed, cudaStream_t stream);
 

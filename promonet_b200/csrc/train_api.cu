@@ -54,8 +54,6 @@ size_t pmn_conv_tc_packed_floats(int rows, int reduce, int taps) {
     return conv_tc_packed_floats(rows, reduce, taps);
 }
 
-void pmn_debug_train_tc_mode(int mode) { set_train_tc_debug_mode(mode); }
-
 void pmn_debug_train_tc_counters(void* counters) { set_train_tc_debug(static_cast<long long*>(counters)); }
 
 int pmn_pack_weight_taps(

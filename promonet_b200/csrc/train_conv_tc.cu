@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kProducers = 512;        // gather / epilogue threads
 constexpr int kThreads = kProducers + 64;  // + the MMA issuing warp + the weight-copy warp
-constexpr int kStages = 3;
+constexpr int kStages = 3;             // pipeline stages (2 for the 256-column tiles: 96 KB each)
 constexpr int kBM = 128;
 constexpr int kKStep = 32;            // fp32 operands per row per K step (one tap, 32 channels)
 constexpr int kPair = 2;              // K steps per pipeline stage
@@ -114,11 +114,9 @@ __device__ __forceinline__ float operand_act(float v, float companion, int act, 
 }
 
 long long* g_debug_counters = nullptr;   // pmn_debug_train_tc_counters
-int g_debug_mode = 0;  // bit 0: skip A loads, bit 1: skip B loads, bit 2: skip MMAs (timing experiments)
 
 struct TcParams {
     long long* debug;      // 8 cycle counters written by CTA 0 (profiling aid) or null
-    int debug_mode;
     ConvGemmArgs a;        // a.wmat = packed weights (o_ch, taps, c_pad)
     int a_ch, a_h, a_w;    // gathered tensor
     int o_ch, o_h, o_w;    // produced tensor
@@ -129,16 +127,19 @@ __device__ float g_zero_words[4] = {0.f, 0.f, 0.f, 0.f};  // what rows outside t
 
 template <int BN, bool TRANSPOSED, int A_ACT>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
+    constexpr int kNStages = BN > 128 ? 2 : kStages;
     constexpr uint32_t kABytes = kBM * kKStep * 4;            // one K step of A
     constexpr uint32_t kBBytes = BN * kKStep * 4;             // one K step of B = one packed slab
     constexpr uint32_t kStageBytes = kPair * (kABytes + kBBytes);
     constexpr int kAPer = kBM * kKStep / kProducers;          // A operands per thread per K step (8)
     constexpr bool kCompanion = A_ACT == kActLreluMask || A_ACT == kActTanhMask;
+    constexpr int kMaxTaps = 64;                              // taps with a shared-memory offset table
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full[kStages];    // 16 producer warps + the weight copy (with its bytes)
     __shared__ uint64_t empty[kStages];   // tcgen05.commit: the MMAs that read the stage are done
     __shared__ uint64_t acc_done;
     __shared__ uint32_t tmem_slot;
+    __shared__ int2 tap_offsets[kMaxTaps];   // (i dh, j dw) per tap
 
     const pmn_conv_geometry& g = p.a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,12 +148,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     constexpr int kMmaWarp = kProducers / 32, kCopyWarp = kMmaWarp + 1;
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kNStages; ++i) {
             mbar_init(full + i, kProducers / 32 + 1);
             mbar_init(empty + i, 1);
         }
         mbar_init(&acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = tid; t < min(p.taps, kMaxTaps); t += kThreads) {
+        const int i = t / g.kw;
+        tap_offsets[t] = make_int2(i * g.dh, (t - i * g.kw) * g.dw);
     }
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -179,9 +184,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
             constexpr uint32_t idesc = instr_desc_tf32(kBM, BN);
             long long t_wait = 0, mark = 0;
             for (int it = 0; it < stages_total; ++it) {
-                const int s = it % kStages;
+                const int s = it % kNStages;
                 if (timing) mark = clock64();
-                mbar_wait(full + s, (it / kStages) & 1);
+                mbar_wait(full + s, (it / kNStages) & 1);
                 if (timing) t_wait += clock64() - mark;
                 tc_fence_after();
                 const int subs = min(kPair, k_steps - it * kPair);
@@ -192,9 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
                     for (int kk = 0; kk < kKStep / 8; ++kk) {
                         const uint64_t a_desc = smem_desc(a_addr + 2 * kk * kBM * 16, kBM * 16, 128);
                         const uint64_t b_desc = smem_desc(b_addr + 2 * kk * BN * 16, BN * 16, 128);
-                        if (!(p.debug_mode & 4))
-                            tc_mma_tf32(tmem_base, a_desc, b_desc, idesc,
-                                        (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+                        tc_mma_tf32(tmem_base, a_desc, b_desc, idesc,
+                                    (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
                     }
                 }
                 tc_commit(empty + s);
@@ -207,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         if (lane == 0) {
             const float* slabs = p.a.wmat + (size_t)blockIdx.y * k_steps * (BN * kKStep);
             for (int it = 0; it < stages_total; ++it) {
-                const int s = it % kStages;
-                if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
+                const int s = it % kNStages;
+                if (it >= kNStages) mbar_wait(empty + s, ((it / kNStages) - 1) & 1);
                 const int subs = min(kPair, k_steps - it * kPair);
                 mbar_expect_tx(full + s, subs * kBBytes);
                 bulk_copy(stage_b(s, 0), slabs + (size_t)it * kPair * (BN * kKStep), subs * kBBytes, full + s);
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         }
         const int plane = p.a_h * p.a_w;
         const bool padded = p.c_pad != p.a_ch;     // only then can a channel index run past the tensor
+        const bool unit_stride = g.sh == 1 && g.sw == 1;
+        const int c_thread = aquarter * kAPer;
 
         // (tap, channel block) of the K step being LOADED.  A row that falls outside the input at
         // this tap reads a word of zeros with stride 0, so the loop has no per-element select.
@@ -245,21 +251,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         const float* tap_c = nullptr;
         int tap_stride = 0;
         auto enter_tap = [&]() {
-            const int i = tap / g.kw, j = tap - i * g.kw;
+            int2 o;
+            if (tap < kMaxTaps) o = tap_offsets[tap];
+            else { const int i = tap / g.kw; o = make_int2(i * g.dh, (tap - i * g.kw) * g.dw); }
             int hi, wi;
             bool ok = m_ok;
             if (TRANSPOSED) {
-                const int th = hb - i * g.dh, tw = wb - j * g.dw;
-                hi = th / g.sh; wi = tw / g.sw;
-                ok = ok && th >= 0 && tw >= 0 && hi * g.sh == th && wi * g.sw == tw;
+                hi = hb - o.x; wi = wb - o.y;
+                ok = ok && hi >= 0 && wi >= 0;
+                if (!unit_stride) {
+                    const int th = hi, tw = wi;
+                    hi = th / g.sh; wi = tw / g.sw;
+                    ok = ok && hi * g.sh == th && wi * g.sw == tw;
+                }
             } else {
-                hi = hb + i * g.dh; wi = wb + j * g.dw;
+                hi = hb + o.x; wi = wb + o.y;
                 ok = ok && hi >= 0 && wi >= 0;
             }
             ok = ok && hi < p.a_h && wi < p.a_w;
             const int offset = ok ? hi * p.a_w + wi : 0;
             tap_a = ok ? a_base + offset : g_zero_words;
-            tap_c = ok ? c_base + offset : g_zero_words;
+            if (kCompanion) tap_c = ok ? c_base + offset : g_zero_words;
             tap_stride = ok ? plane : 0;
         };
         enter_tap();
@@ -267,14 +279,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         // issue the loads of the next K step (if any) into the given registers, then advance
         auto issue_loads = [&](float (&va)[kAPer], float (&vc)[kAPer]) {
             if (loaded >= k_steps) return;
-            const int c_first = cb * kKStep + aquarter * kAPer;
+            const int c_first = cb * kKStep + c_thread;
+            if (padded && cb == blocks_per_tap - 1) {
 #pragma unroll
-            for (int i = 0; i < kAPer; ++i) {
-                int c = c_first + i;
-                if (padded) c = min(c, p.a_ch - 1);   // its weights are zero
-                const size_t idx = (size_t)c * tap_stride;
-                va[i] = (p.debug_mode & 1) ? 1.f : __ldg(tap_a + idx);
-                if (kCompanion) vc[i] = __ldg(tap_c + idx);
+                for (int i = 0; i < kAPer; ++i) {
+                    const int c = min(c_first + i, p.a_ch - 1);   // the weights of the padding are zero
+                    va[i] = __ldg(tap_a + (long long)c * tap_stride);
+                    if (kCompanion) vc[i] = __ldg(tap_c + (long long)c * tap_stride);
+                }
+            } else {
+                const float* src = tap_a + (long long)c_first * tap_stride;
+#pragma unroll
+                for (int i = 0; i < kAPer; ++i) va[i] = __ldg(src + (long long)i * tap_stride);
+                if (kCompanion) {
+                    const float* src_c = tap_c + (long long)c_first * tap_stride;
+#pragma unroll
+                    for (int i = 0; i < kAPer; ++i) vc[i] = __ldg(src_c + (long long)i * tap_stride);
+                }
             }
             ++loaded;
             if (++cb == blocks_per_tap) {
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         issue_loads(va0, vc0);
         issue_loads(va1, vc1);
         for (int it = 0; it < stages_total; ++it) {
-            const int s = it % kStages;
+            const int s = it % kNStages;
             const int subs = min(kPair, k_steps - it * kPair);
             // finish this stage's operands and immediately reuse the registers for the next stage
             float4 a0[kAPer / 4], a1[kAPer / 4];
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
                 issue_loads(va1, vc1);
             }
             if (timing && tid == 0) mark = clock64();
-            if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
+            if (it >= kNStages) mbar_wait(empty + s, ((it / kNStages) - 1) & 1);
             if (timing && tid == 0) { const long long now = clock64(); t_wait += now - mark; mark = now; }
             float4* dst0 = reinterpret_cast<float4*>(stage_a(s, 0));
 #pragma unroll
@@ -379,7 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     }
 }
 
-__host__ __device__ inline int tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
+__host__ __device__ inline int tile_columns(int rows) {
+    return rows >= 256 ? 256 : (rows > 64 ? 128 : (rows > 32 ? 64 : 32));
+}
+__host__ __device__ inline int wgrad_tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
 __host__ __device__ inline int conv_tc_pad(int channels) { return (channels + kKStep - 1) / kKStep * kKStep; }
 
 // w (d0, d1, taps) -> the shared-memory images the kernel copies in bulk.  The GEMM rows are
@@ -415,7 +439,7 @@ __global__ void pack_weight_taps_kernel(
 
 template <int BN, bool TRANSPOSED, int A_ACT>
 int launch_instance(const TcParams& p, cudaStream_t stream) {
-    const size_t smem = (size_t)kStages * kPair * (kBM + BN) * kKStep * 4;
+    const size_t smem = (size_t)(BN > 128 ? 2 : kStages) * kPair * (kBM + BN) * kKStep * 4;
     static bool configured = false;
     if (!configured) {
         PMN_TRY(check_cuda(
@@ -770,7 +794,6 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const pmn_weight_desc
 }  // namespace
 
 void set_train_tc_debug(long long* counters) { g_debug_counters = counters; }
-void set_train_tc_debug_mode(int mode) { g_debug_mode = mode; }
 
 int conv_tc_channel_pad(int channels) { return (channels + kKStep - 1) / kKStep * kKStep; }
 
@@ -822,7 +845,7 @@ int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream) {
     p.o_positions = g.h_out * g.w_out;
     p.steps_per_item = ceil_div(p.o_positions, kKStep);
     p.steps_total = g.batch * p.steps_per_item;
-    const int bn = tile_columns(g.c_out);
+    const int bn = wgrad_tile_columns(g.c_out);
     const int tiles = ceil_div(p.rows_total, kBM) * ceil_div(g.c_out, bn);
     // fill 148 SMs twice over, but keep at least 8 K steps per CTA
     int splits = max(1, min(ceil_div(296, tiles), ceil_div(p.steps_total, 8)));
@@ -853,7 +876,6 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
                 "conv_gemm_tc: LeakyReLU slope must be in [0, 1]");
     TcParams p;
     p.debug = g_debug_counters;
-    p.debug_mode = g_debug_mode;
     p.a = args;
     if (args.transposed) {
         p.a_ch = g.c_out; p.a_h = g.h_out; p.a_w = g.w_out;
@@ -868,6 +890,7 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
     PMN_REQUIRE((int64_t)g.batch * p.o_positions < ((int64_t)1 << 31), "conv_gemm_tc: too many positions");
     p.m_total = g.batch * p.o_positions;
     switch (tile_columns(p.o_ch)) {
+        case 256: return launch_variant<256>(p, stream);
         case 128: return launch_variant<128>(p, stream);
         case 64: return launch_variant<64>(p, stream);
         default: return launch_variant<32>(p, stream);

@@ -107,7 +107,7 @@ def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stri
     packed = ops.pack_weight_taps(
         wd, torch.empty(ops.packed_floats(c_out, c_in, taps), device='cuda'), c_out, c_in, taps, False)
     # [row tile][tap][channel block][k / 4][row in tile][4], rounded to tf32 (10-bit mantissa)
-    bn = 128 if c_out > 64 else (64 if c_out > 32 else 32)
+    bn = 256 if c_out >= 256 else (128 if c_out > 64 else (64 if c_out > 32 else 32))
     tiles, blocks = -(-c_out // bn), ops.channel_pad(c_in) // 32
     expected = torch.zeros(tiles * bn, taps, blocks * 32)
     expected[:c_out, :, :c_in] = w.flatten(2).permute(0, 2, 1)
