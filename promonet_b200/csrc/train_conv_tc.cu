@@ -129,7 +129,11 @@ template <int BN, bool TRANSPOSED, int A_ACT>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     constexpr int kNStages = BN > 128 ? 2 : kStages;
     constexpr uint32_t kABytes = kBM * kKStep * 4;            // one K step of A
-    constexpr uint32_t kBBytes = BN * kKStep * 4;             // one K step of B = one packed slab
+    // BN = 256: two 128-row weight tiles share one gathered A tile (two N = 128 MMAs per K = 8)
+    constexpr int kSlabRows = BN > 128 ? 128 : BN;
+    constexpr int kSlabs = BN / kSlabRows;
+    constexpr uint32_t kSlabBytes = kSlabRows * kKStep * 4;   // one packed slab: one K step of one tile
+    constexpr uint32_t kBBytes = kSlabs * kSlabBytes;
     constexpr uint32_t kStageBytes = kPair * (kABytes + kBBytes);
     constexpr int kAPer = kBM * kKStep / kProducers;          // A operands per thread per K step (8)
     constexpr bool kCompanion = A_ACT == kActLreluMask || A_ACT == kActTanhMask;
@@ -174,14 +178,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     const int stages_total = (k_steps + kPair - 1) / kPair;
     const bool timing = p.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     const long long begin = timing ? clock64() : 0;
-    // stage layout: [A step 0][A step 1][B step 0][B step 1]
+    // stage layout: [A step 0][A step 1][B tile 0: step 0, step 1][B tile 1: step 0, step 1]
     auto stage_a = [&](int s, int sub) { return smem + s * kStageBytes + sub * kABytes; };
-    auto stage_b = [&](int s, int sub) { return smem + s * kStageBytes + kPair * kABytes + sub * kBBytes; };
+    auto stage_b = [&](int s, int tile, int sub) {
+        return smem + s * kStageBytes + kPair * kABytes + (tile * kPair + sub) * kSlabBytes;
+    };
 
     if (warp == kMmaWarp) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc_tf32(kBM, BN);
+            constexpr uint32_t idesc = instr_desc_tf32(kBM, kSlabRows);
             long long t_wait = 0, mark = 0;
             for (int it = 0; it < stages_total; ++it) {
                 const int s = it % kNStages;
@@ -192,13 +198,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
                 const int subs = min(kPair, k_steps - it * kPair);
                 for (int sub = 0; sub < subs; ++sub) {
                     const uint32_t a_addr = smem_u32(stage_a(s, sub));
-                    const uint32_t b_addr = smem_u32(stage_b(s, sub));
 #pragma unroll
                     for (int kk = 0; kk < kKStep / 8; ++kk) {
                         const uint64_t a_desc = smem_desc(a_addr + 2 * kk * kBM * 16, kBM * 16, 128);
-                        const uint64_t b_desc = smem_desc(b_addr + 2 * kk * BN * 16, BN * 16, 128);
-                        tc_mma_tf32(tmem_base, a_desc, b_desc, idesc,
-                                    (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int tile = 0; tile < kSlabs; ++tile) {
+                            const uint32_t b_addr = smem_u32(stage_b(s, tile, sub));
+                            const uint64_t b_desc =
+                                smem_desc(b_addr + 2 * kk * kSlabRows * 16, kSlabRows * 16, 128);
+                            tc_mma_tf32(tmem_base + tile * kSlabRows, a_desc, b_desc, idesc,
+                                        (it > 0 || sub > 0 || kk > 0) ? 1u : 0u);
+                        }
                     }
                 }
                 tc_commit(empty + s);
@@ -209,13 +219,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     } else if (warp == kCopyWarp) {
         // ===== weight copy: one thread, one bulk copy per stage (slabs are stored in K-step order) =====
         if (lane == 0) {
-            const float* slabs = p.a.wmat + (size_t)blockIdx.y * k_steps * (BN * kKStep);
+            constexpr size_t kSlabFloats = kSlabRows * kKStep;
+            const float* slabs = p.a.wmat + (size_t)blockIdx.y * kSlabs * k_steps * kSlabFloats;
             for (int it = 0; it < stages_total; ++it) {
                 const int s = it % kNStages;
                 if (it >= kNStages) mbar_wait(empty + s, ((it / kNStages) - 1) & 1);
                 const int subs = min(kPair, k_steps - it * kPair);
-                mbar_expect_tx(full + s, subs * kBBytes);
-                bulk_copy(stage_b(s, 0), slabs + (size_t)it * kPair * (BN * kKStep), subs * kBBytes, full + s);
+                mbar_expect_tx(full + s, kSlabs * subs * kSlabBytes);
+#pragma unroll
+                for (int tile = 0; tile < kSlabs; ++tile)
+                    bulk_copy(stage_b(s, tile, 0),
+                              slabs + ((size_t)tile * k_steps + (size_t)it * kPair) * kSlabFloats,
+                              subs * kSlabBytes, full + s);
             }
         }
     } else {
@@ -400,10 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     }
 }
 
-__host__ __device__ inline int tile_columns(int rows) {
-    return rows >= 256 ? 256 : (rows > 64 ? 128 : (rows > 32 ? 64 : 32));
-}
-__host__ __device__ inline int wgrad_tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
+__host__ __device__ inline int tile_columns(int rows) { return rows > 64 ? 128 : (rows > 32 ? 64 : 32); }
 __host__ __device__ inline int conv_tc_pad(int channels) { return (channels + kKStep - 1) / kKStep * kKStep; }
 
 // w (d0, d1, taps) -> the shared-memory images the kernel copies in bulk.  The GEMM rows are
@@ -885,7 +897,7 @@ int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream) {
     p.o_positions = g.h_out * g.w_out;
     p.steps_per_item = ceil_div(p.o_positions, kKStep);
     p.steps_total = g.batch * p.steps_per_item;
-    const int bn = wgrad_tile_columns(g.c_out);
+    const int bn = tile_columns(g.c_out);
     const int tiles = ceil_div(p.rows_total, kBM) * ceil_div(g.c_out, bn);
     // fill 148 SMs twice over, but keep at least 8 K steps per CTA
     int splits = max(1, min(ceil_div(296, tiles), ceil_div(p.steps_total, 8)));
@@ -929,8 +941,11 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
     p.o_positions = p.o_h * p.o_w;
     PMN_REQUIRE((int64_t)g.batch * p.o_positions < ((int64_t)1 << 31), "conv_gemm_tc: too many positions");
     p.m_total = g.batch * p.o_positions;
+    // two 128-column weight tiles per CTA halve the gather work per FLOP; worth it while the
+    // grid still covers most of the 148 SMs
+    if (p.o_ch % 256 == 0 && ceil_div(p.m_total, kBM) * (p.o_ch / 256) >= 100)
+        return launch_variant<256>(p, stream);
     switch (tile_columns(p.o_ch)) {
-        case 256: return launch_variant<256>(p, stream);
         case 128: return launch_variant<128>(p, stream);
         case 64: return launch_variant<64>(p, stream);
         default: return launch_variant<32>(p, stream);

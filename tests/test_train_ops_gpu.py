@@ -107,7 +107,7 @@ def test_conv_tensor_core_forward_and_dgrad(ops, c_in, c_out, size, kernel, stri
     packed = ops.pack_weight_taps(
         wd, torch.empty(ops.packed_floats(c_out, c_in, taps), device='cuda'), c_out, c_in, taps, False)
     # [row tile][tap][channel block][k / 4][row in tile][4], rounded to tf32 (10-bit mantissa)
-    bn = 256 if c_out >= 256 else (128 if c_out > 64 else (64 if c_out > 32 else 32))
+    bn = 128 if c_out > 64 else (64 if c_out > 32 else 32)
     tiles, blocks = -(-c_out // bn), ops.channel_pad(c_in) // 32
     expected = torch.zeros(tiles * bn, taps, blocks * 32)
     expected[:c_out, :, :c_in] = w.flatten(2).permute(0, 2, 1)
@@ -143,6 +143,7 @@ EXACT = [
     (256, 256, (64, 1), (3, 1), 1, (1, 1), (1, 0), 2),       # one M tile, two N tiles, 24 K steps
     (113, 512, (8, 1), (7, 1), 1, 1, (3, 0), 2),             # padded channels, 16 rows only
     (128, 512, (38, 2), (5, 1), (3, 1), 1, (2, 0), 4),       # strided, M = 104 < one tile
+    (64, 512, (1700, 2), (5, 1), 1, 1, (2, 0), 4),           # 107 M tiles x 2: the 256-wide CTAs
     (32, 32, (8, 77), (3, 9), (1, 2), 1, (1, 4), 4),         # 27 taps
     (258, 512, (1, 1), (1, 1), 1, 1, 0, 2),                  # speaker projection: 2 rows
 ]
