@@ -283,6 +283,13 @@ typedef struct {
     int batch, c_in, c_out;
     int h_in, w_in, h_out, w_out;
     int kh, kw, sh, sw, dh, dw, ph, pw;
+    /* Optional element strides of the gathered tensor of pmn_conv_gemm[_tc] (0 = contiguous
+     * (B, C, H, W)): channel c, position (h, w) of item b is read at
+     * b * batch_stride + c * channel_stride + (h * W + w) * position_stride.
+     * With channel_stride = 1 and position_stride = hop a signal (B, T) is read as its overlapping
+     * frames (B, n_fft, frames) without materialising them: an STFT is then a 1 x 1 convolution
+     * with the windowed DFT basis (promonet/train/loss.py:61-80). */
+    int channel_stride, position_stride, batch_stride;
 } pmn_conv_geometry;
 
 /* Activation fused into an operand load */
@@ -367,9 +374,15 @@ typedef struct {
     float* packed;
     float* packed_t;
     float* wt;
-    int dim0, dim1, taps, reserved;
+    float* dense;        /* (dim0, dim1, taps) dense form of a grouped weight, or NULL */
+    int dim0, dim1, taps;
+    int groups;          /* > 1: v / w are (dim0, dim1 / groups, taps) (torch Conv1d groups,
+                            discriminator.py:218-224); the packings are block-diagonal */
 } pmn_weight_desc;
 int pmn_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, void* stream);
+/* gw (dim0, dim1 / groups, taps) = diagonal blocks of a dense weight gradient (dim0, dim1, taps) */
+int pmn_extract_grouped(
+    const float* dense, float* gw, int dim0, int dim1, int taps, int groups, void* stream);
 
 /* (dim0, dim1, taps) -> (dim1, dim0, taps) */
 int pmn_transpose_weight(
@@ -463,6 +476,23 @@ int pmn_channel_sum(
 int pmn_copy_columns(
     const float* src, int src_width, int src_offset, float* dst, int dst_width, int dst_offset,
     int64_t rows, int cols, int accumulate, void* stream);
+
+/* Multi-resolution spectral convergence, promonet/train/loss.py:61-150.  The STFT of one
+ * resolution is a 1 x 1 pmn_conv_gemm[_tc] over the reflect-padded signal read as overlapping
+ * frames (pmn_conv_geometry strides) with this weight: (2 bins, n_fft), bins = n_fft / 2 + 1,
+ * rows [0, bins) = hann[n] cos(2 pi k n / n_fft), rows [bins, 2 bins) = -hann[n] sin(...). */
+int pmn_dft_basis(float* out, int n_fft, void* stream);
+/* spec (2 B, 2 bins, frames): real then imaginary rows; items [0, B) the target y, [B, 2 B) the
+ * prediction x.  With s = sqrt(clamp(|X|, 1e-7)): sums (2 floats, overwritten) = (sum |s_y - s_x|,
+ * sum s_y); *loss += weight sums[0] / sums[1]; gspec (B, 2 bins, frames) = weight times the
+ * gradient of that ratio with respect to the prediction's spectrum (may be NULL). */
+int pmn_spectral_convergence(
+    const float* spec, int batch, int bins, int frames, float weight, float* sums, float* loss,
+    float* gspec, void* stream);
+/* gsignal[b, f hop + n] += gframes[b, n, f]: the adjoint of reading (B, samples) as frames */
+int pmn_frame_overlap_add(
+    const float* gframes, float* gsignal, int batch, int n_fft, int frames, int hop, int samples,
+    void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,9 +195,64 @@ def train():
     print('wrote train.npz', {k: result[k] for k in ('losses_0', 'losses_1')})
 
 
+def train_flags():
+    """One iteration with MULTI_SCALE_DISCRIMINATOR and SPECTRAL_CONVERGENCE_LOSS on (the
+    configuration BASELINE.json words for the training step), from the unmodified reference"""
+    from oracle import train as oracle_train
+    promonet = ref_shim.load()
+    promonet.MULTI_SCALE_DISCRIMINATOR = True
+    promonet.SPECTRAL_CONVERGENCE_LOSS = True
+    torch.manual_seed(promonet.RANDOM_SEED)
+    generator = promonet.model.Generator()
+    torch.manual_seed(promonet.RANDOM_SEED)
+    discriminators = promonet.model.Discriminator()
+    assert len(discriminators.discriminators) == 7
+    spectral_convergence = promonet.loss.MultiResolutionSpectralConvergence('cpu')
+    batch = oracle_train.batch(TRAIN_BATCH, TRAIN_FRAMES, TRAIN_SEED)
+    (loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio) = batch
+    generated = generator(
+        loudness, pitch, periodicity, ppg, speakers, sbr, lr, torch.zeros(promonet.HOPSIZE))
+    real_logits, fake_logits, _, _ = discriminators(audio, generated.detach())
+    discriminator_losses, _, _ = promonet.loss.discriminator(real_logits, fake_logits)
+    discriminator_losses.backward()
+    d_grads = {k: v.grad.clone() for k, v in discriminators.named_parameters()}
+    _, fake_logits, real_feature_maps, fake_feature_maps = discriminators(audio, generated)
+    mels = promonet.preprocess.spectrogram.linear_to_mel(spectrograms, None)
+    generated_mels = promonet.preprocess.spectrogram.from_audio(generated, True, None)
+    mel_loss = torch.nn.functional.l1_loss(mels, generated_mels)
+    spectral_loss = spectral_convergence(generated, audio)
+    feature_matching_loss = promonet.loss.feature_matching(real_feature_maps, fake_feature_maps)
+    adversarial_loss, _ = promonet.loss.generator(fake_logits)
+    generator_losses = (
+        promonet.MEL_LOSS_WEIGHT * mel_loss + spectral_loss +
+        promonet.FEATURE_MATCHING_LOSS_WEIGHT * feature_matching_loss +
+        promonet.ADVERSARIAL_LOSS_WEIGHT * adversarial_loss)
+    generator_losses.backward()
+    g_grads = {k: v.grad.clone() for k, v in generator.named_parameters()}
+    result = {
+        'losses': np.array([
+            float(discriminator_losses), float(mel_loss), float(feature_matching_loss),
+            float(adversarial_loss), float(generator_losses), float(spectral_loss)]),
+        'logit_sizes': np.array([logit.shape[1] for logit in fake_logits]),
+        'feature_maps': np.array([len(maps) for maps in fake_feature_maps])}
+    for kind, grads in (('generator', g_grads), ('discriminator', d_grads)):
+        names = sorted(grads)
+        result[f'{kind}_names'] = np.array(names)
+        result[f'{kind}_grad_norms'] = np.array([float(grads[n].double().norm()) for n in names])
+    state = discriminators.state_dict()
+    result['msd_checksums'] = np.array([
+        float(state[k].double().abs().sum()) for k in sorted(state) if k.startswith('discriminators.5.')])
+    np.savez_compressed(GOLDEN / 'train_flags.npz', **result)
+    promonet.MULTI_SCALE_DISCRIMINATOR = False
+    promonet.SPECTRAL_CONVERGENCE_LOSS = False
+    print('wrote train_flags.npz', result['losses'], result['logit_sizes'])
+
+
 if __name__ == '__main__':
     import sys
-    if '--fargan' in sys.argv:
+    if '--train-flags' in sys.argv:
+        train_flags()
+    elif '--fargan' in sys.argv:
         fargan()
     elif '--train' in sys.argv:
         train()

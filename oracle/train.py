@@ -81,14 +81,37 @@ def discriminator_cmb(state, prefix, x):
     return torch.flatten(x, 1, -1), fmaps
 
 
+# DiscriminatorS discriminator.py:218-225: (kernel, stride, groups, padding)
+MULTI_SCALE_CONVS = ((15, 1, 1, 7), (41, 4, 4, 20), (41, 4, 16, 20), (41, 4, 64, 20), (41, 4, 256, 20), (5, 1, 1, 2))
+
+
+def discriminator_s(state, prefix, x):
+    """DiscriminatorS.forward discriminator.py:227-239"""
+    fmaps = []
+    for i, (_, stride, groups, padding) in enumerate(MULTI_SCALE_CONVS):
+        x = F.conv1d(
+            x, weight(state, f'{prefix}.convs.{i}'), state[f'{prefix}.convs.{i}.bias'],
+            stride, padding, 1, groups)
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        fmaps.append(x)
+    x = F.conv1d(x, weight(state, f'{prefix}.conv_post'), state[f'{prefix}.conv_post.bias'], 1, 1)
+    fmaps.append(x)
+    return torch.flatten(x, 1, -1), fmaps
+
+
 def discriminator(state, y, y_hat):
-    """Discriminator.forward discriminator.py:36-49 (config/promonet.py: MPD x 5 + CMB)"""
+    """Discriminator.forward discriminator.py:36-49 (config/promonet.py: MPD x 5 + CMB; with
+    MULTI_SCALE_DISCRIMINATOR the DiscriminatorS sits between them, :18-28)"""
     logits_real, logits_fake, fmaps_real, fmaps_fake = [], [], [], []
-    for i in range(len(PERIODS) + 1):
+    count = len({k.split('.')[1] for k in state if k.startswith('discriminators.')})
+    multi_scale = count == len(PERIODS) + 2
+    for i in range(count):
         prefix = f'discriminators.{i}'
         for x, logits, fmaps in ((y, logits_real, fmaps_real), (y_hat, logits_fake, fmaps_fake)):
             if i < len(PERIODS):
                 logit, fmap = discriminator_p(state, prefix, x, PERIODS[i])
+            elif multi_scale and i == len(PERIODS):
+                logit, fmap = discriminator_s(state, prefix, x)
             else:
                 logit, fmap = discriminator_cmb(state, prefix, x)
             logits.append(logit)
@@ -125,13 +148,31 @@ def mel_loss(spectrograms, generated):
     return F.l1_loss(target, predicted)
 
 
+SPECTRAL_FFT_SIZES = (2560, 1280, 640, 320, 160, 80)   # loss.py:129-131
+
+
+def spectral_convergence_loss(x, y):
+    """MultiResolutionSpectralConvergence.forward loss.py:124-150: x predicted, y target (B, 1, T)"""
+    total = 0.
+    for n_fft in SPECTRAL_FFT_SIZES:
+        window = torch.hann_window(n_fft, dtype=x.dtype)
+        magnitudes = []
+        for signal in (x, y):
+            magnitude = torch.abs(torch.stft(
+                signal.squeeze(1), n_fft, n_fft // 4, n_fft, window, return_complex=True))
+            magnitudes.append(torch.sqrt(torch.clamp(magnitude, min=1e-7)))
+        x_mag, y_mag = magnitudes
+        total = total + torch.norm(y_mag - x_mag, p=1) / torch.norm(y_mag, p=1)
+    return total / len(SPECTRAL_FFT_SIZES)
+
+
 def parameters(state):
     """The entries torch registers as parameters (everything but the buffers)"""
     buffers = ('default_previous_samples', 'ppg_threshold', 'pitch_distribution')
     return {k: v for k, v in state.items() if k not in buffers}
 
 
-def step(generator_state, discriminator_state, batch, optimizers=None):
+def step(generator_state, discriminator_state, batch, optimizers=None, spectral_convergence=False):
     """One iteration of train/core.py:183-369.  States are dicts of leaf tensors
     (requires_grad on the parameters); returns losses, gradients and the audio.
     When `optimizers` = (discriminator AdamW, generator AdamW) is given they are stepped
@@ -161,6 +202,10 @@ def step(generator_state, discriminator_state, batch, optimizers=None):
     fm = feature_matching_loss(real_fmaps, fake_fmaps)
     adv = generator_loss(fake_logits)
     g_loss = MEL_LOSS_WEIGHT * mel + FEATURE_MATCHING_LOSS_WEIGHT * fm + ADVERSARIAL_LOSS_WEIGHT * adv
+    if spectral_convergence:
+        # train/core.py:308-310 (SPECTRAL_CONVERGENCE_LOSS)
+        spectral = spectral_convergence_loss(generated, audio)
+        g_loss = g_loss + spectral
     for p in g_params.values():
         p.grad = None
     g_loss.backward()
@@ -170,6 +215,8 @@ def step(generator_state, discriminator_state, batch, optimizers=None):
     losses = {
         'discriminator': d_loss.detach(), 'mel': mel.detach(), 'feature_matching': fm.detach(),
         'adversarial': adv.detach(), 'generator': g_loss.detach()}
+    if spectral_convergence:
+        losses['spectral_convergence'] = spectral.detach()
     return losses, g_grads, d_grads, generated.detach()
 
 

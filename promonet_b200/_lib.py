@@ -129,6 +129,7 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_float,
          c_void_p, c_void_p, c_void_p]),
+    'pmn_extract_grouped': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pmn_transpose_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pmn_weight_norm_backward': (
@@ -167,6 +168,11 @@ SIGNATURES = {
     'pmn_channel_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_copy_columns': (
         c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    'pmn_dft_basis': (c_int, [c_void_p, c_int, c_void_p]),
+    'pmn_spectral_convergence': (
+        c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pmn_frame_overlap_add': (
+        c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 
@@ -174,15 +180,16 @@ class WeightDesc(ctypes.Structure):
     """pmn_weight_desc"""
     _fields_ = [
         ('v', c_void_p), ('g', c_void_p), ('w', c_void_p), ('packed', c_void_p),
-        ('packed_t', c_void_p), ('wt', c_void_p),
-        ('dim0', c_int), ('dim1', c_int), ('taps', c_int), ('reserved', c_int)]
+        ('packed_t', c_void_p), ('wt', c_void_p), ('dense', c_void_p),
+        ('dim0', c_int), ('dim1', c_int), ('taps', c_int), ('groups', c_int)]
 
 
 class ConvGeometry(ctypes.Structure):
     """pmn_conv_geometry"""
     _fields_ = [(name, c_int) for name in (
         'batch', 'c_in', 'c_out', 'h_in', 'w_in', 'h_out', 'w_out',
-        'kh', 'kw', 'sh', 'sw', 'dh', 'dw', 'ph', 'pw')]
+        'kh', 'kw', 'sh', 'sw', 'dh', 'dw', 'ph', 'pw',
+        'channel_stride', 'position_stride', 'batch_stride')]
 
 
 _library = None

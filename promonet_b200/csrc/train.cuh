@@ -43,6 +43,8 @@ int launch_conv_gemm(const ConvGemmArgs& args, cudaStream_t stream);
 int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream);
 int conv_tc_channel_pad(int channels);
 size_t conv_tc_packed_floats(int rows, int reduce, int taps);
+int launch_extract_grouped(
+    const float* dense, float* gw, int dim0, int dim1, int taps, int groups, cudaStream_t stream);
 int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, cudaStream_t stream);
 void set_train_tc_debug(long long* counters);
 int launch_pack_weight_taps(
@@ -119,5 +121,13 @@ int launch_stft_train_backward(
 int launch_mel_loss(
     const float* magnitude, const float* target_mels, int batch, int frames, float loss_weight,
     float grad_weight, float* loss, float* gmagnitude, cudaStream_t stream);
+
+int launch_dft_basis(float* out, int n_fft, cudaStream_t stream);
+int launch_spectral_convergence(
+    const float* spec, int batch, int bins, int frames, float weight, float* sums, float* loss,
+    float* gspec, cudaStream_t stream);
+int launch_frame_overlap_add(
+    const float* gframes, float* gsignal, int batch, int n_fft, int frames, int hop, int samples,
+    cudaStream_t stream);
 
 }  // namespace pmn

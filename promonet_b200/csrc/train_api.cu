@@ -90,6 +90,11 @@ int pmn_conv_wgrad_tc(
     return launch_conv_wgrad_tc(args, (cudaStream_t)stream);
 }
 
+int pmn_extract_grouped(
+    const float* dense, float* gw, int dim0, int dim1, int taps, int groups, void* stream) {
+    return launch_extract_grouped(dense, gw, dim0, dim1, taps, groups, (cudaStream_t)stream);
+}
+
 int pmn_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, void* stream) {
     return launch_prepare_weights(table, layers, max_dim0, (cudaStream_t)stream);
 }
@@ -211,6 +216,23 @@ int pmn_copy_columns(
     return launch_copy_columns(
         src, src_width, src_offset, dst, dst_width, dst_offset, rows, cols, accumulate,
         (cudaStream_t)stream);
+}
+
+int pmn_dft_basis(float* out, int n_fft, void* stream) {
+    return launch_dft_basis(out, n_fft, (cudaStream_t)stream);
+}
+
+int pmn_spectral_convergence(
+    const float* spec, int batch, int bins, int frames, float weight, float* sums, float* loss,
+    float* gspec, void* stream) {
+    return launch_spectral_convergence(
+        spec, batch, bins, frames, weight, sums, loss, gspec, (cudaStream_t)stream);
+}
+
+int pmn_frame_overlap_add(
+    const float* gframes, float* gsignal, int batch, int n_fft, int frames, int hop, int samples,
+    void* stream) {
+    return launch_frame_overlap_add(gframes, gsignal, batch, n_fft, frames, hop, samples, (cudaStream_t)stream);
 }
 
 }  // extern "C"

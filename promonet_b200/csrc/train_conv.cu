@@ -41,6 +41,8 @@ struct GemmParams {
     int a_ch, a_h, a_w;   // gathered tensor
     int o_ch, o_h, o_w;   // produced tensor
     int taps, kdim, m_total, o_positions;
+    int channel_stride, position_stride;
+    size_t batch_stride;
 };
 
 template <int BM, int BN, int TM, int TN, bool TRANSPOSED>
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(GemmParams p) {
             hb = oh * g.sh - g.ph;
             wb = ow * g.sw - g.pw;
         }
-        const size_t offset = (size_t)b * p.a_ch * p.a_h * p.a_w;
+        const size_t offset = (size_t)b * p.batch_stride;
         a_base += offset;
         if (c_base) c_base += offset;
     }
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(GemmParams p) {
             if (hi < 0 || wi < 0) return 0.f;
         }
         if (hi >= p.a_h || wi >= p.a_w) return 0.f;
-        const size_t idx = ((size_t)c * p.a_h + hi) * p.a_w + wi;
+        const size_t idx = (size_t)c * p.channel_stride + (size_t)(hi * p.a_w + wi) * p.position_stride;
         const float v = __ldg(a_base + idx);
         if (p.a.a_act == kActNone) return v;
         const float companion = c_base ? __ldg(c_base + idx) : 0.f;
@@ -440,6 +442,12 @@ int launch_conv_gemm(const ConvGemmArgs& args, cudaStream_t stream) {
     p.kdim = p.a_ch * p.taps;
     p.o_positions = p.o_h * p.o_w;
     p.m_total = g.batch * p.o_positions;
+    const bool strided = g.channel_stride || g.position_stride || g.batch_stride;
+    PMN_REQUIRE(!strided || (!args.transposed && g.channel_stride > 0 && g.position_stride > 0 &&
+                             g.batch_stride > 0), "conv_gemm: bad tensor strides");
+    p.channel_stride = strided ? g.channel_stride : p.a_h * p.a_w;
+    p.position_stride = strided ? g.position_stride : 1;
+    p.batch_stride = strided ? (size_t)g.batch_stride : (size_t)p.a_ch * p.a_h * p.a_w;
     if (p.o_ch <= 16) return launch_gemm_variant<256, 16, 4, 4>(p, stream);
     return launch_gemm_variant<128, 64, 8, 4>(p, stream);
 }

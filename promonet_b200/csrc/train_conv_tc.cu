@@ -121,6 +121,8 @@ struct TcParams {
     int a_ch, a_h, a_w;    // gathered tensor
     int o_ch, o_h, o_w;    // produced tensor
     int taps, c_pad, m_total, o_positions;
+    int channel_stride, position_stride;
+    size_t batch_stride;
 };
 
 __device__ float g_zero_words[4] = {0.f, 0.f, 0.f, 0.f};  // what rows outside the input read
@@ -250,11 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
             const int oh = rem / p.o_w, ow = rem - oh * p.o_w;
             if (TRANSPOSED) { hb = oh + g.ph; wb = ow + g.pw; }
             else { hb = oh * g.sh - g.ph; wb = ow * g.sw - g.pw; }
-            const size_t offset = (size_t)b * p.a_ch * p.a_h * p.a_w;
+            const size_t offset = (size_t)b * p.batch_stride;
             a_base += offset;
             if (kCompanion) c_base += offset;
         }
-        const int plane = p.a_h * p.a_w;
+        const int plane = p.channel_stride;
         const bool padded = p.c_pad != p.a_ch;     // only then can a channel index run past the tensor
         const bool unit_stride = g.sh == 1 && g.sw == 1;
         const int c_thread = aquarter * kAPer;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
                 ok = ok && hi >= 0 && wi >= 0;
             }
             ok = ok && hi < p.a_h && wi < p.a_w;
-            const int offset = ok ? hi * p.a_w + wi : 0;
+            const int offset = ok ? (hi * p.a_w + wi) * p.position_stride : 0;
             tap_a = ok ? a_base + offset : g_zero_words;
             if (kCompanion) tap_c = ok ? c_base + offset : g_zero_words;
             tap_stride = ok ? plane : 0;
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(256) fold_weights_kernel(const pmn_weight_desc
     const pmn_weight_desc d = table[blockIdx.y];
     if ((int)blockIdx.x >= d.dim0 || d.g == nullptr) return;
     __shared__ float partial[32];
-    const int inner = d.dim1 * d.taps;
+    const int inner = d.dim1 / max(d.groups, 1) * d.taps;
     const float* row = d.v + (size_t)blockIdx.x * inner;
     float sum = 0.f;
     for (int i = threadIdx.x; i < inner; i += blockDim.x) sum = fmaf(row[i], row[i], sum);
@@ -798,7 +800,18 @@ __global__ void __launch_bounds__(256) fold_weights_kernel(const pmn_weight_desc
     for (int i = threadIdx.x; i < inner; i += blockDim.x) dst[i] = row[i] * scale;
 }
 
-// ... then write both tensor-core packings (and, for the FMA path, the plain transpose)
+// Element (a, b, tap) of the dense (dim0, dim1, taps) weight; a grouped convolution
+// (discriminator.py:218-224) stores (dim0, dim1 / groups, taps) and is zero off its diagonal blocks
+__device__ __forceinline__ float dense_weight(const pmn_weight_desc& d, const float* w, int a, int b, int tap) {
+    if (d.groups <= 1) return w[((size_t)a * d.dim1 + b) * d.taps + tap];
+    const int per_in = d.dim1 / d.groups, per_out = d.dim0 / d.groups;
+    const int group = a / per_out;
+    if (b / per_in != group) return 0.f;
+    return w[((size_t)a * per_in + (b - group * per_in)) * d.taps + tap];
+}
+
+// ... then write both tensor-core packings (and, for the FMA path, the plain transpose and the
+// dense form of a grouped weight)
 __global__ void __launch_bounds__(256) pack_weights_kernel(const pmn_weight_desc* table) {
     const pmn_weight_desc d = table[blockIdx.y];
     const float* w = d.g ? d.w : d.v;
@@ -826,20 +839,41 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const pmn_weight_desc
             float v = 0.f;
             if (row < rows[t] && c < reduce) {
                 const int a = t ? c : row, b = t ? row : c;
-                v = to_tf32(w[((size_t)a * d.dim1 + b) * d.taps + tap]);
+                v = to_tf32(dense_weight(d, w, a, b, tap));
             }
             out[t][idx] = v;
         }
     }
-    if (d.wt) {
+    if (d.wt || d.dense) {
         const size_t total = (size_t)d.dim0 * d.dim1 * d.taps;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
              idx += (size_t)gridDim.x * blockDim.x) {
             const int tap = (int)(idx % d.taps);
             const size_t rest = idx / d.taps;
-            const int a = (int)(rest % d.dim0), b = (int)(rest / d.dim0);
-            d.wt[idx] = w[((size_t)a * d.dim1 + b) * d.taps + tap];
+            if (d.wt) {
+                const int a = (int)(rest % d.dim0), b = (int)(rest / d.dim0);
+                d.wt[idx] = dense_weight(d, w, a, b, tap);
+            }
+            if (d.dense) {
+                const int b = (int)(rest % d.dim1), a = (int)(rest / d.dim1);
+                d.dense[idx] = dense_weight(d, w, a, b, tap);
+            }
         }
+    }
+}
+
+// gw (dim0, dim1 / groups, taps) = the diagonal blocks of the dense gradient (dim0, dim1, taps)
+__global__ void extract_grouped_kernel(
+    const float* __restrict__ dense, float* __restrict__ gw, int dim0, int dim1, int taps, int groups) {
+    const int per_in = dim1 / groups, per_out = dim0 / groups;
+    const size_t total = (size_t)dim0 * per_in * taps;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % taps);
+        const size_t rest = idx / taps;
+        const int local = (int)(rest % per_in), a = (int)(rest / per_in);
+        const int b = (a / per_out) * per_in + local;
+        gw[idx] = dense[((size_t)a * dim1 + b) * taps + tap];
     }
 }
 
@@ -867,6 +901,17 @@ int launch_pack_weight_taps(
     pack_weight_taps_kernel<<<blocks, 256, 0, stream>>>(
         w, out, d0, d1, taps, transposed, c_pad, bn, row_tiles);
     return launched("pack_weight_taps_kernel");
+}
+
+int launch_extract_grouped(
+    const float* dense, float* gw, int dim0, int dim1, int taps, int groups, cudaStream_t stream) {
+    PMN_REQUIRE(dense && gw && dim0 > 0 && dim1 > 0 && taps > 0 && groups > 0 && dim0 % groups == 0 &&
+                dim1 % groups == 0, "extract_grouped: bad argument");
+    const size_t total = (size_t)dim0 * (dim1 / groups) * taps;
+    LaunchScope scope("extract_grouped_kernel", stream);
+    extract_grouped_kernel<<<(int)min((size_t)1024, (total + 255) / 256), 256, 0, stream>>>(
+        dense, gw, dim0, dim1, taps, groups);
+    return launched("extract_grouped_kernel");
 }
 
 int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim0, cudaStream_t stream) {
@@ -941,6 +986,12 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
     p.o_positions = p.o_h * p.o_w;
     PMN_REQUIRE((int64_t)g.batch * p.o_positions < ((int64_t)1 << 31), "conv_gemm_tc: too many positions");
     p.m_total = g.batch * p.o_positions;
+    const bool strided = g.channel_stride || g.position_stride || g.batch_stride;
+    PMN_REQUIRE(!strided || (!args.transposed && g.channel_stride > 0 && g.position_stride > 0 &&
+                             g.batch_stride > 0), "conv_gemm_tc: bad tensor strides");
+    p.channel_stride = strided ? g.channel_stride : p.a_h * p.a_w;
+    p.position_stride = strided ? g.position_stride : 1;
+    p.batch_stride = strided ? (size_t)g.batch_stride : (size_t)p.a_ch * p.a_h * p.a_w;
     // two 128-column weight tiles per CTA halve the gather work per FLOP; worth it while the
     // grid still covers most of the 148 SMs
     if (p.o_ch % 256 == 0 && ceil_div(p.m_total, kBM) * (p.o_ch / 256) >= 100)

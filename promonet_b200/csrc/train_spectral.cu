@@ -169,7 +169,149 @@ __global__ void __launch_bounds__(128) mel_loss_kernel(
     }
 }
 
+// Windowed one-sided DFT basis as a (2 bins, n_fft) weight: rows [0, bins) = hann[n] cos(2 pi k n / N),
+// rows [bins, 2 bins) = -hann[n] sin(2 pi k n / N) (periodic hann, torch.hann_window; loss.py:99)
+__global__ void dft_basis_kernel(float* __restrict__ out, int n_fft, int bins) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (n >= n_fft) return;
+    const double window = 0.5 - 0.5 * cospi(2. * n / n_fft);
+    // k n mod N keeps the argument small: exact phase for every (k, n)
+    const long long phase = ((long long)k * n) % n_fft;
+    double sine, cosine;
+    sincospi(2. * (double)phase / n_fft, &sine, &cosine);
+    out[(size_t)k * n_fft + n] = (float)(window * cosine);
+    out[(size_t)(bins + k) * n_fft + n] = (float)(-window * sine);
+}
+
+__device__ __forceinline__ float root_magnitude(float re, float im, float* magnitude) {
+    // loss.py:73-80: sqrt(clamp(|X|, 1e-7))
+    *magnitude = sqrtf(re * re + im * im);
+    return sqrtf(fmaxf(*magnitude, 1e-7f));
+}
+
+// spec (2 B, 2 bins, frames): items [0, B) are the target y, [B, 2 B) the prediction x.
+// sums[0] += sum |s_y - s_x|, sums[1] += sum s_y   (loss.py:121: ||y - x||_1 / ||y||_1)
+__global__ void __launch_bounds__(256) spectral_convergence_sums_kernel(
+    const float* __restrict__ spec, int batch, int bins, int frames, float* __restrict__ sums) {
+    __shared__ float scratch[2][32];
+    const size_t item = (size_t)2 * bins * frames, half = (size_t)bins * frames;
+    const size_t total = (size_t)batch * half;
+    float difference = 0.f, reference = 0.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / half, rest = idx - b * half;
+        const float* y = spec + b * item + rest;
+        const float* x = spec + (b + batch) * item + rest;
+        float unused;
+        const float sy = root_magnitude(y[0], y[half], &unused);
+        const float sx = root_magnitude(x[0], x[half], &unused);
+        difference += fabsf(sy - sx);
+        reference += sy;
+    }
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        difference += __shfl_xor_sync(0xffffffffu, difference, offset);
+        reference += __shfl_xor_sync(0xffffffffu, reference, offset);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        scratch[0][threadIdx.x >> 5] = difference;
+        scratch[1][threadIdx.x >> 5] = reference;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float a = threadIdx.x < (blockDim.x >> 5) ? scratch[0][threadIdx.x] : 0.f;
+        float c = threadIdx.x < (blockDim.x >> 5) ? scratch[1][threadIdx.x] : 0.f;
+        for (int offset = 16; offset > 0; offset >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, offset);
+            c += __shfl_xor_sync(0xffffffffu, c, offset);
+        }
+        if (threadIdx.x == 0) {
+            atomicAdd(sums, a);
+            atomicAdd(sums + 1, c);
+        }
+    }
+}
+
+// *loss += weight sums[0] / sums[1]; gspec (B, 2 bins, frames) = weight d(sums[0] / sums[1]) / d spec_x
+__global__ void __launch_bounds__(256) spectral_convergence_backward_kernel(
+    const float* __restrict__ spec, int batch, int bins, int frames, const float* __restrict__ sums,
+    float weight, float* __restrict__ loss, float* __restrict__ gspec) {
+    const size_t item = (size_t)2 * bins * frames, half = (size_t)bins * frames;
+    const size_t total = (size_t)batch * half;
+    const float scale = weight / sums[1];
+    if (loss && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(loss, sums[0] * scale);
+    if (!gspec) return;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = idx / half, rest = idx - b * half;
+        const float* y = spec + b * item + rest;
+        const float* x = spec + (b + batch) * item + rest;
+        float unused, magnitude;
+        const float sy = root_magnitude(y[0], y[half], &unused);
+        const float sx = root_magnitude(x[0], x[half], &magnitude);
+        float gre = 0.f, gim = 0.f;
+        if (magnitude > 1e-7f) {
+            const float sign = sx > sy ? 1.f : (sx < sy ? -1.f : 0.f);
+            const float gmagnitude = scale * sign * 0.5f / sx;
+            gre = gmagnitude * x[0] / magnitude;
+            gim = gmagnitude * x[half] / magnitude;
+        }
+        gspec[b * item + rest] = gre;
+        gspec[b * item + rest + half] = gim;
+    }
+}
+
+// gsignal[b, f hop + n] += gframes[b, n, f]: adjoint of reading a signal as overlapping frames
+__global__ void frame_overlap_add_kernel(
+    const float* __restrict__ gframes, float* __restrict__ gsignal, int n_fft, int frames, int hop,
+    int samples) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y, b = blockIdx.z;
+    if (f >= frames) return;
+    atomicAdd(gsignal + (size_t)b * samples + (size_t)f * hop + n,
+              gframes[((size_t)b * n_fft + n) * frames + f]);
+}
+
 }  // namespace
+
+int launch_dft_basis(float* out, int n_fft, cudaStream_t stream) {
+    PMN_REQUIRE(out && n_fft >= 2 && n_fft % 2 == 0, "dft_basis: bad argument");
+    const int bins = n_fft / 2 + 1;
+    dim3 grid(ceil_div(n_fft, 128), bins);
+    LaunchScope scope("dft_basis_kernel", stream);
+    dft_basis_kernel<<<grid, 128, 0, stream>>>(out, n_fft, bins);
+    return launched("dft_basis_kernel");
+}
+
+int launch_spectral_convergence(
+    const float* spec, int batch, int bins, int frames, float weight, float* sums, float* loss,
+    float* gspec, cudaStream_t stream) {
+    PMN_REQUIRE(spec && sums && batch > 0 && bins > 0 && frames > 0, "spectral_convergence: bad argument");
+    const size_t total = (size_t)batch * bins * frames;
+    const int blocks = (int)min((size_t)148 * 4, (total + 255) / 256);
+    PMN_TRY(check_cuda(cudaMemsetAsync(sums, 0, 2 * sizeof(float), stream), "spectral_convergence memset"));
+    {
+        LaunchScope scope("spectral_convergence_sums_kernel", stream);
+        spectral_convergence_sums_kernel<<<blocks, 256, 0, stream>>>(spec, batch, bins, frames, sums);
+        PMN_TRY(launched("spectral_convergence_sums_kernel"));
+    }
+    LaunchScope scope("spectral_convergence_backward_kernel", stream);
+    spectral_convergence_backward_kernel<<<blocks, 256, 0, stream>>>(
+        spec, batch, bins, frames, sums, weight, loss, gspec);
+    return launched("spectral_convergence_backward_kernel");
+}
+
+int launch_frame_overlap_add(
+    const float* gframes, float* gsignal, int batch, int n_fft, int frames, int hop, int samples,
+    cudaStream_t stream) {
+    PMN_REQUIRE(gframes && gsignal && batch > 0 && batch <= 65535 && n_fft > 0 && n_fft <= 65535 &&
+                frames > 0 && hop > 0 && (frames - 1) * hop + n_fft <= samples,
+                "frame_overlap_add: bad argument");
+    dim3 grid(ceil_div(frames, 64), n_fft, batch);
+    LaunchScope scope("frame_overlap_add_kernel", stream);
+    frame_overlap_add_kernel<<<grid, 64, 0, stream>>>(gframes, gsignal, n_fft, frames, hop, samples);
+    return launched("frame_overlap_add_kernel");
+}
 
 size_t stft_train_frames(int samples) { return (size_t)(samples / kHop); }
 

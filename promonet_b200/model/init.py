@@ -171,10 +171,18 @@ def fargan_state(seed=None):
 ###############################################################################
 
 
-def discriminator_state(seed=None):
+# DiscriminatorS, model/discriminator.py:218-225: (c_in, c_out, kernel, stride, groups, padding)
+MULTI_SCALE_CONVS = (
+    (1, 16, 15, 1, 1, 7), (16, 64, 41, 4, 4, 20), (64, 256, 41, 4, 16, 20),
+    (256, 1024, 41, 4, 64, 20), (1024, 1024, 41, 4, 256, 20), (1024, 1024, 5, 1, 1, 2))
+
+
+def discriminator_state(seed=None, multi_scale=False):
     """State dict of a freshly constructed promonet.model.Discriminator()
     (promonet/model/discriminator.py:15-34,61-72,148-173): same keys and the same
-    torch RNG draw order (Conv2d.reset_parameters per layer, in construction order)"""
+    torch RNG draw order (Conv2d.reset_parameters per layer, in construction order).
+    multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180): DiscriminatorS is
+    inserted after the period discriminators (:20-21)"""
     if seed is not None:
         torch.manual_seed(seed)
     state = OrderedDict()
@@ -187,7 +195,15 @@ def discriminator_state(seed=None):
                 channels[layer], channels[layer + 1], (5, 1), stride, (2, 0)))
         _weight_norm_conv(
             state, f'{prefix}.conv_post', torch.nn.Conv2d(1024, 1, (3, 1), 1, (1, 0)))
-    prefix = f'discriminators.{len(config.DISCRIMINATOR_PERIODS)}'
+    index = len(config.DISCRIMINATOR_PERIODS)
+    if multi_scale:
+        prefix = f'discriminators.{index}'
+        for layer, (c_in, c_out, kernel, stride, groups, padding) in enumerate(MULTI_SCALE_CONVS):
+            _weight_norm_conv(state, f'{prefix}.convs.{layer}', torch.nn.Conv1d(
+                c_in, c_out, kernel, stride, groups=groups, padding=padding))
+        _weight_norm_conv(state, f'{prefix}.conv_post', torch.nn.Conv1d(1024, 1, 3, 1, padding=1))
+        index += 1
+    prefix = f'discriminators.{index}'
     for band, _ in enumerate(config.CMB_BANDS):
         for layer in range(5):
             kernel = (3, 9) if layer < 4 else (3, 3)

@@ -22,19 +22,28 @@ from promonet_b200.train import ops
 from promonet_b200.train.discriminator import Discriminator
 from promonet_b200.train.generator import Generator
 
-LOSSES = ('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator')
+LOSSES = (
+    'discriminator', 'mel', 'feature_matching', 'adversarial', 'generator', 'spectral_convergence')
 
 
 class Trainer:
 
     def __init__(self, generator_state=None, discriminator_state=None, device=None,
-                 process_group=None, math='tf32'):
+                 process_group=None, math='tf32', multi_scale_discriminator=False,
+                 spectral_convergence_loss=False):
         """math: 'tf32' runs the convolutions' forward and data gradients on the tensor
         cores (tf32 operands, fp32 accumulation; the reference trains under fp16 autocast,
         train/core.py:220); 'fp32' is the exact FMA path used for parity"""
         self.math = math
         self.generator = Generator(generator_state, device, math)
-        self.discriminators = Discriminator(discriminator_state, self.generator.device, math)
+        # MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180) and SPECTRAL_CONVERGENCE_LOSS (:358)
+        # are off in config/promonet.py; BASELINE.json's wording of the training config names both
+        self.discriminators = Discriminator(
+            discriminator_state, self.generator.device, math, multi_scale_discriminator)
+        self.spectral_convergence = None
+        if spectral_convergence_loss:
+            from promonet_b200.train.losses import MultiResolutionSpectralConvergence
+            self.spectral_convergence = MultiResolutionSpectralConvergence(self.generator.device, math)
         self.device = self.generator.device
         self.process_group = process_group
         self.step_count = 0
@@ -136,6 +145,9 @@ class Trainer:
         ops.mel_loss(magnitude, target_mels, 1., slot('mel'), gmagnitude, config.MEL_LOSS_WEIGHT)
         ops.stft_magnitude_backward(
             gmagnitude, spectrum, ggenerated.view(count, samples), 'hann', 1e-6, 0, accumulate=True)
+        # multi-resolution spectral convergence (:308-310)
+        if self.spectral_convergence is not None:
+            self.spectral_convergence(both, count, 1., slot('spectral_convergence'), ggenerated)
         G.layers.zero_grad()
         G.backward(ggenerated)
         self.generated = both[count:]
@@ -148,6 +160,7 @@ class Trainer:
         ops.axpby(config.MEL_LOSS_WEIGHT, slot('mel'), 0., slot('generator'))
         ops.axpby(1., slot('feature_matching'), 1., slot('generator'))
         ops.axpby(1., slot('adversarial'), 1., slot('generator'))
+        ops.axpby(1., slot('spectral_convergence'), 1., slot('generator'))
         self.step_count += 1
         return self.losses
 

@@ -83,6 +83,58 @@ class Period:
                     ops.axpby(1., ginput, 1., gaudio)
 
 
+class Scale:
+    """DiscriminatorS discriminator.py:211-239 (MULTI_SCALE_DISCRIMINATOR): grouped Conv1d stack
+    over the waveform; the groups run as block-diagonal dense convolutions (train/layers.py)"""
+
+    def __init__(self, layers, prefix):
+        self.specs = init.MULTI_SCALE_CONVS
+        self.convs = [
+            layers.conv(f'{prefix}.convs.{i}', groups=spec[4]) for i, spec in enumerate(self.specs)]
+        self.post = layers.conv(f'{prefix}.conv_post')
+
+    def forward(self, x):
+        n, _, t = x.shape
+        maps = [x.view(n, 1, t, 1)]
+        geometries = []
+        specs = [(k, s, p) for _, _, k, s, _, p in self.specs] + [(3, 1, 1)]
+        for i, (conv, (kernel, stride, padding)) in enumerate(zip(self.convs + [self.post], specs)):
+            source = maps[-1]
+            geometry = ops.geometry(
+                n, conv.dim1, conv.dim0, source.shape[2:], (kernel, 1), (stride, 1), 1, (padding, 0))
+            out = torch.empty(n, conv.dim0, geometry.h_out, 1, device=x.device)
+            conv.apply(geometry, False, source, out, bias=conv.bias,
+                       out_act=ops.OUT_LRELU if i < 6 else ops.OUT_NONE, out_slope=SLOPE)
+            maps.append(out)
+            geometries.append(geometry)
+        return {'maps': maps, 'geometries': geometries, 'pad': 0, 'samples': t}
+
+    def backward(self, record, gmaps, lo, hi, weights, gaudio):
+        layers = self.convs + [self.post]
+        n = hi - lo
+        last = len(layers) - 1
+        for i in reversed(range(len(layers))):
+            geometry = _with_batch(record['geometries'][i], n)
+            y, x = record['maps'][i + 1][lo:hi], record['maps'][i][lo:hi]
+            act = (ops.ACT_LRELU_MASK, SLOPE) if i < last else (ops.ACT_NONE, 1.)
+            g = gmaps[i]
+            if weights:
+                layers[i].wgrad(geometry, g, x, dy_companion=y, dy_act=act[0], dy_slope=act[1])
+            if i == 0 and gaudio is None:
+                break
+            target = gmaps[i - 1] if i > 0 else None
+            accumulate = target is not None
+            if target is None:
+                target = torch.empty_like(x)
+            layers[i].apply_transposed(
+                geometry, True, g, target, a_companion=y, a_act=act[0], a_slope=act[1],
+                accumulate=accumulate)
+            if i > 0:
+                gmaps[i - 1] = target
+            else:
+                ops.axpby(1., target.view(n, 1, -1), 1., gaudio)
+
+
 class ComplexMultiBand:
     """DiscriminatorCMB discriminator.py:146-208"""
 
@@ -195,18 +247,24 @@ def _with_batch(geometry, batch):
 
 class Discriminator:
 
-    def __init__(self, state=None, device=None, math='tf32'):
+    def __init__(self, state=None, device=None, math='tf32', multi_scale=False):
+        """multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180; inferred from the
+        keys when a state dict is given)"""
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.train needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
-        state = init.discriminator_state() if state is None else state
+        state = init.discriminator_state(multi_scale=multi_scale) if state is None else state
+        count = len({k.split('.')[1] for k in state})
+        multi_scale = count == len(config.DISCRIMINATOR_PERIODS) + 2
         self.params = ParamSet(state, self.device)
         self.layers = Layers(self.params, math)
-        self.periods = [
+        self.modules = [
             Period(self.layers, f'discriminators.{i}', period)
             for i, period in enumerate(config.DISCRIMINATOR_PERIODS)]
-        self.cmb = ComplexMultiBand(self.layers, f'discriminators.{len(self.periods)}')
+        if multi_scale:
+            self.modules.append(Scale(self.layers, f'discriminators.{len(self.modules)}'))
+        self.cmb = ComplexMultiBand(self.layers, f'discriminators.{len(self.modules)}')
         self.layers.allocate()
 
     def state_dict(self):
@@ -220,7 +278,7 @@ class Discriminator:
 
     def forward(self, x):
         """x (N, 1, T) -> records (one per sub-discriminator)"""
-        return [p.forward(x) for p in self.periods] + [self.cmb.forward(x)]
+        return [m.forward(x) for m in self.modules] + [self.cmb.forward(x)]
 
     def logits(self, records):
         """Flattened logits per sub-discriminator, (N, n_i) each (discriminator.py:93,208)"""
@@ -235,7 +293,7 @@ class Discriminator:
     def backward(self, records, gmaps, lo, hi, weights, gaudio=None):
         """gmaps: per sub-discriminator, a list aligned with feature_maps() holding the
         gradient of each map over items lo:hi or None"""
-        for module, record, g in zip(self.periods + [self.cmb], records, gmaps):
+        for module, record, g in zip(self.modules + [self.cmb], records, gmaps):
             module.backward(record, g, lo, hi, weights, gaudio)
         if weights:
             self.layers.finish()

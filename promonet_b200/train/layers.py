@@ -2,9 +2,15 @@
 
 A layer holds views into a ParamSet (weight_g / weight_v / bias, or weight / bias),
 the folded weight `w = g v / ||v||` (model/core.py:43-45; recomputed whenever the
-parameters change, as torch's weight_norm hook does every forward), its transpose
-for the data gradient, and a scratch buffer the weight-gradient kernel accumulates
-into before the weight-norm backward turns it into gradients of g and v.
+parameters change, as torch's weight_norm hook does every forward), the operand
+packings of the tensor-core kernels (or the plain transpose for the FMA path), and a
+scratch buffer the weight-gradient kernel accumulates into before the weight-norm
+backward turns it into gradients of g and v.
+
+A grouped convolution (DiscriminatorS, model/discriminator.py:218-224) is run as the dense
+convolution with a block-diagonal weight: its parameters keep torch's (C_out, C_in / groups, k)
+shape, the packings are written with zeros off the diagonal, and the dense weight gradient
+is reduced to its diagonal blocks before the weight-norm backward.
 """
 import torch
 
@@ -13,21 +19,23 @@ from promonet_b200.train import ops
 
 class Conv:
 
-    def __init__(self, params, prefix):
+    def __init__(self, params, prefix, groups=1):
         self.params = params
         self.prefix = prefix
+        self.groups = groups
         self.weight_norm = f'{prefix}.weight_v' in params
         key = f'{prefix}.weight_v' if self.weight_norm else f'{prefix}.weight'
         self.shape = params.index[key][1]
-        self.dim0, self.dim1 = self.shape[0], self.shape[1]
+        self.dim0, self.dim1 = self.shape[0], self.shape[1] * groups   # dense GEMM dimensions
         self.taps = 1
         for s in self.shape[2:]:
             self.taps *= s
-        self.numel = self.dim0 * self.dim1 * self.taps
+        self.numel = self.dim0 * self.dim1 * self.taps            # dense
+        self.stored = self.numel // groups                         # as the parameters store it
         self.has_bias = f'{prefix}.bias' in params
         # assigned by Layers.allocate()
         self.w = self.wt = self.gw = self.packed = self.packed_t = None
-        self.tensor_cores = False
+        self.dense = self.gw_dense = None
 
     @property
     def bias(self):
@@ -37,24 +45,19 @@ class Conv:
     def gbias(self):
         return self.params.gradient(f'{self.prefix}.bias') if self.has_bias else None
 
-    def refresh(self):
-        """Fold weight norm and transpose (after every optimizer step)"""
-        if self.weight_norm:
-            ops.weight_norm_fold(
-                self.params[f'{self.prefix}.weight_v'], self.params[f'{self.prefix}.weight_g'],
-                self.w, self.dim0, self.dim1 * self.taps)
-        ops.transpose_weight(self.w, self.wt, self.dim0, self.dim1, self.taps)
-        if self.packed is not None:
-            ops.pack_weight_taps(self.w, self.packed, self.dim0, self.dim1, self.taps, False)
-        if self.packed_t is not None:
-            ops.pack_weight_taps(self.w, self.packed_t, self.dim0, self.dim1, self.taps, True)
-
     def apply(self, geometry, transposed, a, out, **kwargs):
         """Implicit GEMM with rows = dim 0 of the weight, reducing over dim 1 (forward of a
         Conv, data gradient of a ConvTranspose).  `transposed` is the gather direction."""
         if self.packed is not None and kwargs.get('out_act') != ops.OUT_TANH:
             return ops.conv_gemm_tc(geometry, transposed, a, self.packed, out, **kwargs)
-        return ops.conv_gemm(geometry, transposed, a, self.w, out, **kwargs)
+        weight = self.dense if self.groups > 1 else self.w
+        return ops.conv_gemm(geometry, transposed, a, weight, out, **kwargs)
+
+    def apply_transposed(self, geometry, transposed, a, out, **kwargs):
+        """Rows = dim 1 of the weight, reducing over dim 0 (data gradient of a Conv)"""
+        if self.packed_t is not None:
+            return ops.conv_gemm_tc(geometry, transposed, a, self.packed_t, out, **kwargs)
+        return ops.conv_gemm(geometry, transposed, a, self.wt, out, **kwargs)
 
     TENSOR_CORE_WGRAD = {
         (ops.ACT_NONE, ops.ACT_NONE), (ops.ACT_NONE, ops.ACT_LRELU),
@@ -63,33 +66,26 @@ class Conv:
     def wgrad(self, geometry, dy, x, bias=True, **kwargs):
         """Accumulate the weight (and bias) gradient of the convolution `geometry`"""
         gbias = self.gbias if bias else None
+        target = self.gw_dense if self.groups > 1 else self.gw
         pair = (kwargs.get('dy_act', ops.ACT_NONE), kwargs.get('x_act', ops.ACT_NONE))
         if self.packed is not None and pair in self.TENSOR_CORE_WGRAD:
-            return ops.conv_wgrad_tc(geometry, dy, x, self.gw, gbias, **kwargs)
-        return ops.conv_wgrad(geometry, dy, x, self.gw, gbias, **kwargs)
-
-    def apply_transposed(self, geometry, transposed, a, out, **kwargs):
-        """Rows = dim 1 of the weight, reducing over dim 0 (data gradient of a Conv)"""
-        if self.packed_t is not None:
-            return ops.conv_gemm_tc(geometry, transposed, a, self.packed_t, out, **kwargs)
-        return ops.conv_gemm(geometry, transposed, a, self.wt, out, **kwargs)
+            return ops.conv_wgrad_tc(geometry, dy, x, target, gbias, **kwargs)
+        return ops.conv_wgrad(geometry, dy, x, target, gbias, **kwargs)
 
     def finish(self):
         """Weight-norm backward: gw -> gradients of weight_g and weight_v"""
+        if self.groups > 1:
+            ops.extract_grouped(self.gw_dense, self.gw, self.dim0, self.dim1, self.taps, self.groups)
         if self.weight_norm:
             ops.weight_norm_backward(
                 self.params[f'{self.prefix}.weight_v'], self.params[f'{self.prefix}.weight_g'],
                 self.gw, self.params.gradient(f'{self.prefix}.weight_v'),
                 self.params.gradient(f'{self.prefix}.weight_g'), self.dim0,
-                self.dim1 * self.taps)
+                self.stored // self.dim0)
 
 
 class Layers:
     """The convolutions of one module, with flat derived / scratch storage"""
-
-    # a GEMM goes to the tensor cores when both its row and reduction channel counts reach this
-    # (measured: even the 1-channel first and last layers are faster there than on the FMA tiles)
-    TENSOR_CORE_MIN_CHANNELS = 1
 
     def __init__(self, params, math='tf32'):
         if math not in ('tf32', 'fp32'):
@@ -98,52 +94,62 @@ class Layers:
         self.math = math
         self.layers = []
 
-    def conv(self, prefix):
-        layer = Conv(self.params, prefix)
+    def conv(self, prefix, groups=1):
+        layer = Conv(self.params, prefix, groups)
         self.layers.append(layer)
         return layer
 
     def allocate(self):
         device = self.params.device
-        total = sum(layer.numel for layer in self.layers)
-        normed = sum(layer.numel for layer in self.layers if layer.weight_norm)
-        self.folded = torch.empty(normed, device=device)
-        self.transposed = torch.empty(total, device=device)
-        self.scratch = torch.zeros(normed, device=device)
-        packable = [
-            layer for layer in self.layers
-            if self.math == 'tf32' and min(layer.dim0, layer.dim1) >= self.TENSOR_CORE_MIN_CHANNELS]
+        tensor_cores = self.math == 'tf32'   # every layer: even the 1-channel ones are faster there
+        flat = lambda count, zero=False: (torch.zeros if zero else torch.empty)(count, device=device)
+        normed = [layer for layer in self.layers if layer.weight_norm]
+        grouped = [layer for layer in self.layers if layer.groups > 1]
+        self.folded = flat(sum(layer.stored for layer in normed))
+        # one buffer cleared per backward: weight-gradient scratch of the weight-normed layers and
+        # the dense gradients of the grouped ones
+        self.scratch = flat(
+            sum(layer.stored for layer in normed) + sum(layer.numel for layer in grouped), zero=True)
         sizes = [
             (ops.packed_floats(layer.dim0, layer.dim1, layer.taps),
-             ops.packed_floats(layer.dim1, layer.dim0, layer.taps)) for layer in packable]
-        self.packed = torch.empty(sum(a + b for a, b in sizes), device=device)
-        offset = 0
-        for layer, (forward, backward) in zip(packable, sizes):
-            layer.packed = self.packed[offset:offset + forward]
-            layer.packed_t = self.packed[offset + forward:offset + forward + backward]
-            offset += forward + backward
-        f = t = 0
-        for layer in self.layers:
-            layer.wt = self.transposed[t:t + layer.numel]
-            t += layer.numel
+             ops.packed_floats(layer.dim1, layer.dim0, layer.taps)) if tensor_cores else (0, 0)
+            for layer in self.layers]
+        self.packed = flat(sum(a + b for a, b in sizes))
+        self.transposed = flat(0 if tensor_cores else sum(layer.numel for layer in self.layers))
+        self.dense = flat(0 if tensor_cores else sum(layer.numel for layer in grouped))
+        f = s = k = t = d = 0
+        entries = []
+        for layer, (forward, backward) in zip(self.layers, sizes):
+            if tensor_cores:
+                layer.packed = self.packed[k:k + forward]
+                layer.packed_t = self.packed[k + forward:k + forward + backward]
+                k += forward + backward
+            else:
+                layer.wt = self.transposed[t:t + layer.numel]
+                t += layer.numel
+                if layer.groups > 1:
+                    layer.dense = self.dense[d:d + layer.numel]
+                    d += layer.numel
             if layer.weight_norm:
-                layer.w = self.folded[f:f + layer.numel]
-                layer.gw = self.scratch[f:f + layer.numel]
-                f += layer.numel
+                layer.w = self.folded[f:f + layer.stored]
+                layer.gw = self.scratch[s:s + layer.stored]
+                f += layer.stored
+                s += layer.stored
             else:
                 layer.w = self.params[f'{layer.prefix}.weight']
                 layer.gw = self.params.gradient(f'{layer.prefix}.weight')
-        entries = []
-        for layer in self.layers:
+            if layer.groups > 1:
+                layer.gw_dense = self.scratch[s:s + layer.numel]
+                s += layer.numel
             key = 'weight_v' if layer.weight_norm else 'weight'
-            fma = layer.packed is None      # the FMA path needs the plain transpose
             entries.append({
                 'v': self.params[f'{layer.prefix}.{key}'],
                 'g': self.params[f'{layer.prefix}.weight_g'] if layer.weight_norm else None,
                 'w': layer.w if layer.weight_norm else None,
                 'packed': layer.packed, 'packed_t': layer.packed_t,
-                'wt': layer.wt if fma else None,
-                'dim0': layer.dim0, 'dim1': layer.dim1, 'taps': layer.taps})
+                'wt': layer.wt, 'dense': layer.dense,
+                'dim0': layer.dim0, 'dim1': layer.dim1, 'taps': layer.taps,
+                'groups': layer.groups})
         self.table = ops.weight_table(entries, device)
         self.max_dim0 = max(layer.dim0 for layer in self.layers)
 

@@ -17,7 +17,7 @@ def _pair(value):
 
 
 def geometry(batch, c_in, c_out, size_in, kernel, stride=1, dilation=1, padding=0,
-             size_out=None):
+             size_out=None, strides=(0, 0, 0)):
     """pmn_conv_geometry of a forward convolution; sizes are (H, W)"""
     (h_in, w_in), (kh, kw) = _pair(size_in), _pair(kernel)
     (sh, sw), (dh, dw), (ph, pw) = _pair(stride), _pair(dilation), _pair(padding)
@@ -27,7 +27,7 @@ def geometry(batch, c_in, c_out, size_in, kernel, stride=1, dilation=1, padding=
     else:
         h_out, w_out = _pair(size_out)
     return ConvGeometry(
-        batch, c_in, c_out, h_in, w_in, h_out, w_out, kh, kw, sh, sw, dh, dw, ph, pw)
+        batch, c_in, c_out, h_in, w_in, h_out, w_out, kh, kw, sh, sw, dh, dw, ph, pw, *strides)
 
 
 def _check(status):
@@ -92,16 +92,23 @@ def weight_table(entries, device):
     """Device copy of a pmn_weight_desc array; entries are dicts of tensors / ints"""
     table = (_lib.WeightDesc * len(entries))()
     for desc, entry in zip(table, entries):
-        for name in ('v', 'g', 'w', 'packed', 'packed_t', 'wt'):
+        for name in ('v', 'g', 'w', 'packed', 'packed_t', 'wt', 'dense'):
             tensor = entry.get(name)
             setattr(desc, name, _lib.ptr(tensor) if tensor is not None else None)
         desc.dim0, desc.dim1, desc.taps = entry['dim0'], entry['dim1'], entry['taps']
+        desc.groups = entry.get('groups', 1)
     raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
     return raw.to(device)
 
 
 def prepare_weights(table, layers, max_dim0):
     _check(_lib.library().pmn_prepare_weights(_lib.ptr(table), layers, max_dim0, _lib.stream()))
+
+
+def extract_grouped(dense, gw, dim0, dim1, taps, groups):
+    _check(_lib.library().pmn_extract_grouped(
+        _lib.ptr(dense), _lib.ptr(gw), dim0, dim1, taps, groups, _lib.stream()))
+    return gw
 
 
 def transpose_weight(w, wt, dim0, dim1, taps):
@@ -272,3 +279,26 @@ def conv_transpose1d(x, weight, bias, stride, in_slope):
         _lib.ptr(x), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(out), batch, c_in, c_out, t_in,
         k, stride, in_slope, _lib.stream()))
     return out
+
+
+def dft_basis(n_fft, device):
+    """(2 bins, n_fft) windowed DFT weight (loss.py:61-80 as a 1 x 1 convolution over frames)"""
+    out = torch.empty(2 * (n_fft // 2 + 1), n_fft, device=device)
+    _check(_lib.library().pmn_dft_basis(_lib.ptr(out), n_fft, _lib.stream()))
+    return out
+
+
+def spectral_convergence(spec, batch, weight, sums, loss, gspec=None):
+    """spec (2 B, 2 bins, frames): target items first; see pmn_spectral_convergence"""
+    _, rows, frames = spec.shape
+    _check(_lib.library().pmn_spectral_convergence(
+        _lib.ptr(spec), batch, rows // 2, frames, weight, _lib.ptr(sums), _lib.ptr(loss),
+        _lib.ptr(gspec), _lib.stream()))
+
+
+def frame_overlap_add(gframes, gsignal, hop):
+    batch, n_fft, frames = gframes.shape
+    _check(_lib.library().pmn_frame_overlap_add(
+        _lib.ptr(gframes), _lib.ptr(gsignal), batch, n_fft, frames, hop, gsignal.shape[-1],
+        _lib.stream()))
+    return gsignal

@@ -92,3 +92,24 @@ def test_discriminator_state_layout():
     assert len(state) == 168
     assert sum(v.numel() for v in state.values()) == 41572780
     assert state['discriminators.5.band_convs.4.1.0.weight_v'].shape == (32, 32, 3, 9)
+
+
+def test_oracle_with_multi_scale_and_spectral_convergence_matches_reference():
+    """tests/golden/train_flags.npz: MULTI_SCALE_DISCRIMINATOR + SPECTRAL_CONVERGENCE_LOSS on"""
+    golden = np.load(GOLDEN / 'train_flags.npz')
+    d_state = init.discriminator_state(1234, multi_scale=True)
+    sums = np.array([
+        float(d_state[k].double().abs().sum()) for k in sorted(d_state)
+        if k.startswith('discriminators.5.')])
+    np.testing.assert_allclose(sums, golden['msd_checksums'], rtol=1e-12)
+    g = oracle_train.leaf_state(init.hifigan_state(1234))
+    d = oracle_train.leaf_state(d_state)
+    batch = oracle_train.batch(make_golden.TRAIN_BATCH, make_golden.TRAIN_FRAMES, make_golden.TRAIN_SEED)
+    losses, g_grads, d_grads, _ = oracle_train.step(g, d, batch, spectral_convergence=True)
+    actual = [float(losses[k]) for k in (
+        'discriminator', 'mel', 'feature_matching', 'adversarial', 'generator', 'spectral_convergence')]
+    np.testing.assert_allclose(actual, golden['losses'], rtol=1e-4)
+    for kind, grads in (('generator', g_grads), ('discriminator', d_grads)):
+        names = [str(n) for n in golden[f'{kind}_names']]
+        norms = np.array([float(grads[n].double().norm()) for n in names])
+        np.testing.assert_allclose(norms, golden[f'{kind}_grad_norms'], rtol=1e-3)

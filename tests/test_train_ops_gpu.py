@@ -446,3 +446,77 @@ def test_mel_loss(ops):
     assert relative_error(gmag, mr.grad) < 1e-4
     mels = ops.linear_to_mel(magnitude.cuda())
     assert relative_error(mels, torch.log(basis @ magnitude.double())) < 1e-5
+
+
+@pytest.mark.parametrize('n_fft', [80, 320, 2560])
+def test_spectral_convergence_pieces(ops, n_fft):
+    """promonet/train/loss.py:61-121 for one resolution: the STFT as a 1 x 1 convolution over
+    frames read in place, the loss ratio and its gradient back to the signal"""
+    from oracle import train as oracle_train
+    torch.manual_seed(15)
+    batch, samples, hop = 2, 4096, n_fft // 4
+    y = .3 * torch.randn(batch, 1, samples)
+    x = (y + .1 * torch.randn(batch, 1, samples)).double().requires_grad_()
+    window = torch.hann_window(n_fft, dtype=torch.double)
+    magnitudes = [
+        torch.sqrt(torch.clamp(torch.abs(torch.stft(
+            s.squeeze(1), n_fft, hop, n_fft, window, return_complex=True)), min=1e-7))
+        for s in (x, y.double())]
+    expected = torch.norm(magnitudes[1] - magnitudes[0], p=1) / torch.norm(magnitudes[1], p=1)
+    expected.backward()
+
+    basis = ops.dft_basis(n_fft, 'cuda')
+    rows, frames = basis.shape[0], 1 + samples // hop
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.double)[:, None] * torch.arange(n_fft, dtype=torch.double)
+    reference = torch.cat([window * torch.cos(2 * torch.pi * k / n_fft), -window * torch.sin(2 * torch.pi * k / n_fft)])
+    assert relative_error(basis, reference) < 1e-6
+    both = torch.cat([y, x.detach().float()]).cuda().view(2 * batch, samples)
+    padded = ops.reflect_pad(both, n_fft // 2, n_fft // 2)
+    geom = ops.geometry(2 * batch, n_fft, rows, (frames, 1), (1, 1), strides=(1, hop, samples + n_fft))
+    spec = ops.conv_gemm(geom, False, padded, basis, torch.empty(2 * batch, rows, frames, device='cuda'))
+    stft = torch.stft(torch.cat([y, x.detach().float()]).squeeze(1).double(), n_fft, hop, n_fft, window,
+                      return_complex=True)
+    assert relative_error(spec, torch.cat([stft.real, stft.imag], 1)) < TOLERANCE
+    sums, loss = torch.zeros(2, device='cuda'), torch.zeros(1, device='cuda')
+    gspec = torch.empty(batch, rows, frames, device='cuda')
+    ops.spectral_convergence(spec, batch, 1., sums, loss, gspec)
+    assert relative_error(loss, expected.detach().reshape(1)) < TOLERANCE
+    basis_t = ops.transpose_weight(basis, torch.empty_like(basis), rows, n_fft, 1)
+    gframes = ops.conv_gemm(
+        ops.geometry(batch, rows, n_fft, (frames, 1), (1, 1)), False, gspec, basis_t,
+        torch.empty(batch, n_fft, frames, device='cuda'))
+    gpadded = ops.frame_overlap_add(gframes, torch.zeros(batch, samples + n_fft, device='cuda'), hop)
+    gx = ops.reflect_pad_backward(
+        gpadded, torch.empty(batch, samples, device='cuda'), n_fft // 2, n_fft // 2)
+    assert relative_error(gx, x.grad.squeeze(1)) < 5e-4
+
+
+def test_grouped_weight_preparation(ops):
+    """Grouped Conv1d (discriminator.py:218-224) as a block-diagonal dense convolution"""
+    torch.manual_seed(16)
+    groups, c_in, c_out, k = 4, 16, 64, 5
+    conv = torch.nn.utils.weight_norm(torch.nn.Conv1d(c_in, c_out, k, 2, groups=groups, padding=2))
+    v, g = conv.weight_v.detach(), conv.weight_g.detach()
+    x = torch.randn(3, c_in, 50)
+    expected = conv(x).detach()
+    dense = torch.empty(c_out, c_in, k, device='cuda')
+    folded = torch.empty(c_out, c_in // groups, k, device='cuda')
+    packed = torch.empty(ops.packed_floats(c_out, c_in, k), device='cuda')
+    table = ops.weight_table([{
+        'v': v.cuda().contiguous(), 'g': g.cuda().contiguous(), 'w': folded, 'packed': packed,
+        'dense': dense, 'dim0': c_out, 'dim1': c_in, 'taps': k, 'groups': groups}], 'cuda')
+    keep = table  # the descriptors point into these tensors
+    ops.prepare_weights(table, 1, c_out)
+    reference = torch.zeros(c_out, c_in, k)
+    per_in, per_out = c_in // groups, c_out // groups
+    for group in range(groups):
+        reference[group * per_out:(group + 1) * per_out, group * per_in:(group + 1) * per_in] = \
+            conv.weight.detach()[group * per_out:(group + 1) * per_out]
+    assert relative_error(dense, reference) < 1e-6
+    geom = ops.geometry(3, c_in, c_out, (50, 1), (k, 1), (2, 1), 1, (2, 0))
+    out = torch.empty(3, c_out, geom.h_out, 1, device='cuda')
+    ops.conv_gemm_tc(geom, False, x.cuda().view(3, c_in, 50, 1), packed, out, bias=conv.bias.detach().cuda())
+    assert relative_error(out.view(expected.shape), expected) < TF32_TOLERANCE
+    extracted = ops.extract_grouped(
+        reference.cuda(), torch.empty(c_out, per_in, k, device='cuda'), c_out, c_in, k, groups)
+    assert torch.equal(extracted.cpu(), conv.weight.detach())
