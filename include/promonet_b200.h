@@ -494,6 +494,15 @@ int pmn_frame_overlap_add(
     const float* gframes, float* gsignal, int batch, int n_fft, int frames, int hop, int samples,
     void* stream);
 
+/* promonet.edit.grid.sample (promonet/edit/grid.py:12-43): 1-D grid sampling of
+ * sequence (items, channels, t_in) at grid (t_out) positions (frames, fractional) ->
+ * out (items, channels, t_out); nearest = 0: linear with the final frame replicated, 1: nearest.
+ * renormalize != 0 applies softmax(log(p + 1e-8)) over channels afterwards (the PPG resampling of
+ * promonet/preprocess/core.py:97-103, the step before synthesize.from_features on the file path). */
+int pmn_grid_sample(
+    const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
+    int t_out, int nearest, int renormalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,3 +80,24 @@ def prepare_global_features(state, speakers, spectral_balance_ratios, loudness_r
         speakers, state['speaker_embedding.weight']).unsqueeze(-1)
     g = torch.cat((g, spectral_balance_ratios[:, None, None].to(g.dtype)), dim=1)
     return torch.cat((g, loudness_ratios[:, None, None].to(g.dtype)), dim=1)
+
+
+def grid_sample(sequence, grid, method='linear'):
+    """promonet.edit.grid.sample, promonet/edit/grid.py:12-43 (pinned: in-repo code)"""
+    if method == 'linear':
+        xp = torch.arange(sequence.shape[-1], device=sequence.device)
+        i = torch.searchsorted(xp, grid, side='right')
+        fp = torch.nn.functional.pad(sequence, (0, 1), mode='replicate')
+        xp = torch.cat((xp, xp[-1:] + 1))
+        return fp[..., i - 1] * (xp[i] - grid) + fp[..., i] * (grid - xp[i - 1])
+    if method == 'nearest':
+        return sequence[..., torch.round(grid).to(torch.long)]
+    raise ValueError(f'Grid sampling method {method} is not defined')
+
+
+def resample_ppg(ppg, length):
+    """promonet/preprocess/core.py:97-103: grid resample to `length` frames, then
+    softmax(log(p + 1e-8)) over the phoneme axis (of_length: ppgs, un-vendored, PARITY UNPINNED:
+    restated as linspace(0, T - 1, length))"""
+    grid = torch.linspace(0., ppg.shape[-1] - 1., length)
+    return torch.softmax(torch.log(grid_sample(ppg, grid) + 1e-8), -2)

@@ -85,6 +85,14 @@ def main():
         loudness=loudness.numpy(),
         averaged=promonet.preprocess.loudness.band_average(loudness, 8).numpy(),
         normalized=promonet.preprocess.loudness.normalize(loudness).numpy())
+    # edit.grid.sample (promonet/edit/grid.py:12-43): time-stretch of a PPG-shaped sequence
+    torch.manual_seed(99)
+    sequence = torch.softmax(2. * torch.randn(2, 40, 57), dim=-2)
+    grid = torch.linspace(0., 56., 91)
+    np.savez_compressed(
+        GOLDEN / 'grid.npz', sequence=sequence.numpy(), grid=grid.numpy(),
+        linear=promonet.edit.grid.sample(sequence, grid, 'linear').numpy(),
+        nearest=promonet.edit.grid.sample(sequence, grid, 'nearest').numpy())
     print('wrote', sorted(p.name for p in GOLDEN.iterdir()))
 
 

@@ -8,6 +8,8 @@ CPU fallback.
 """
 from .config import *
 from . import _lib
+from . import edit
+from . import load
 from . import model
 from . import preprocess
 from . import synthesize

@@ -168,6 +168,8 @@ SIGNATURES = {
     'pmn_channel_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_copy_columns': (
         c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    'pmn_grid_sample': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_dft_basis': (c_int, [c_void_p, c_int, c_void_p]),
     'pmn_spectral_convergence': (
         c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

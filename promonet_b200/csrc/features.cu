@@ -217,7 +217,63 @@ __global__ void pack_conv1d_weight_kernel(
     }
 }
 
+// promonet.edit.grid.sample (edit/grid.py:12-38), linear: out[r, t] = lerp of sequence[r, :] at
+// grid[t], with the final frame replicated; optionally followed by the distribution-preserving
+// renormalisation softmax(log(p + 1e-8)) over the `channels` rows of each item
+// (preprocess/core.py:97-103): (p + 1e-8) / sum_c (p + 1e-8).  One thread per (item, t).
+__global__ void __launch_bounds__(128) grid_sample_kernel(
+    const float* __restrict__ sequence, const float* __restrict__ grid, float* __restrict__ out,
+    int channels, int t_in, int t_out, int nearest, int renormalize) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int item = blockIdx.y;
+    if (t >= t_out) return;
+    const float x = grid[t];
+    const float* src = sequence + (size_t)item * channels * t_in;
+    float* dst = out + (size_t)item * channels * t_out + t;
+    int lower, upper;
+    float wl, wu;
+    if (nearest) {
+        lower = upper = min(max((int)rintf(x), 0), t_in - 1);   // torch.round: half to even
+        wl = 1.f; wu = 0.f;
+    } else {
+        // i = searchsorted(arange(T), x, right) = number of integers k in [0, T) with k <= x
+        int i = x < 0.f ? 0 : min((int)floorf(x) + 1, t_in);
+        i = max(i, 1);                      // x < 0 indexes from the end in torch; clamp instead
+        lower = i - 1;
+        upper = min(i, t_in - 1);           // replicate padding of the final frame
+        wl = (float)i - x;                  // xp[i] - x
+        wu = x - (float)(i - 1);            // x - xp[i - 1]
+    }
+    float total = 0.f;
+    for (int c = 0; c < channels; ++c) {
+        const float* row = src + (size_t)c * t_in;
+        const float v = row[lower] * wl + row[upper] * wu;
+        if (renormalize) total += v + 1e-8f;
+        else dst[(size_t)c * t_out] = v;
+    }
+    if (renormalize) {
+        const float inv = 1.f / total;
+        for (int c = 0; c < channels; ++c) {
+            const float* row = src + (size_t)c * t_in;
+            dst[(size_t)c * t_out] = (row[lower] * wl + row[upper] * wu + 1e-8f) * inv;
+        }
+    }
+}
+
 }  // namespace
+
+int launch_grid_sample(
+    const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
+    int t_out, bool nearest, bool renormalize, cudaStream_t stream) {
+    PMN_REQUIRE(sequence && grid && out, "grid_sample: null pointer");
+    PMN_REQUIRE(items > 0 && items <= 65535 && channels > 0 && t_in > 0, "grid_sample: bad shape");
+    if (t_out <= 0) return PMN_OK;
+    dim3 blocks(ceil_div(t_out, 128), items);
+    LaunchScope scope("grid_sample_kernel", stream);
+    grid_sample_kernel<<<blocks, 128, 0, stream>>>(
+        sequence, grid, out, channels, t_in, t_out, nearest ? 1 : 0, renormalize ? 1 : 0);
+    return launched("grid_sample_kernel");
+}
 
 int launch_features(
     const float* loudness, int rows, const float* pitch, const float* periodicity,

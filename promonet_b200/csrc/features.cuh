@@ -20,4 +20,8 @@ int launch_head(
     const float* x, const float* weight, float* out, int batch, int channels,
     int t_len, float slope, cudaStream_t stream);
 
+int launch_grid_sample(
+    const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
+    int t_out, bool nearest, bool renormalize, cudaStream_t stream);
+
 }  // namespace pmn

@@ -235,4 +235,12 @@ int pmn_frame_overlap_add(
     return launch_frame_overlap_add(gframes, gsignal, batch, n_fft, frames, hop, samples, (cudaStream_t)stream);
 }
 
+int pmn_grid_sample(
+    const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
+    int t_out, int nearest, int renormalize, void* stream) {
+    return launch_grid_sample(
+        sequence, grid, out, items, channels, t_in, t_out, nearest != 0, renormalize != 0,
+        (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -3,14 +3,16 @@
 (its generate() is hard-wired to batch 1, synthesize/core.py:256-268)."""
 import os
 from pathlib import Path
-from typing import Optional, Union
+from typing import List, Optional, Union
 
 import torch
 
 import promonet_b200
 from promonet_b200 import _lib
 
-__all__ = ['from_features', 'from_features_batch', 'generate']
+__all__ = [
+    'from_features', 'from_features_batch', 'from_file', 'from_file_to_file',
+    'from_files_to_files', 'generate']
 
 
 def from_features(
@@ -85,6 +87,104 @@ def from_features_batch(
     return model.forward_host(
         loudness, pitch, periodicity, ppg, speakers,
         spectral_balance_ratios.cpu(), loudness_ratios.cpu())
+
+
+def from_file(
+    loudness_file: Union[str, os.PathLike],
+    pitch_file: Union[str, os.PathLike],
+    periodicity_file: Union[str, os.PathLike],
+    ppg_file: Union[str, os.PathLike],
+    speaker: int = 0,
+    spectral_balance_ratio: float = 1.,
+    loudness_ratio: float = 1.,
+    checkpoint: Optional[Union[str, os.PathLike]] = None,
+    gpu: Optional[int] = None
+) -> torch.Tensor:
+    """Perform speech synthesis from features on disk (promonet/synthesize/core.py:62-111):
+    `*-loudness.pt` (8 | 513, F), `*-pitch.pt` (1, F), `*-periodicity.pt` (1, F), `*-ppg.pt`
+    (40, F'), the PPG resampled to the pitch's frame count (promonet/load.py:172-188)"""
+    device = _device(gpu)
+    loudness, pitch, periodicity, ppg = _load_features(
+        loudness_file, pitch_file, periodicity_file, ppg_file, device)
+    return from_features(
+        loudness, pitch, periodicity, ppg[None], speaker, spectral_balance_ratio, loudness_ratio,
+        checkpoint, gpu)
+
+
+def from_file_to_file(
+    loudness_file, pitch_file, periodicity_file, ppg_file, output_file, speaker=0,
+    spectral_balance_ratio=1., loudness_ratio=1., checkpoint=None, gpu=None
+) -> None:
+    """Perform speech synthesis from features on disk and save (synthesize/core.py:114-155)"""
+    generated = from_file(
+        loudness_file, pitch_file, periodicity_file, ppg_file, speaker, spectral_balance_ratio,
+        loudness_ratio, checkpoint, gpu)
+    _save(output_file, generated.cpu())
+
+
+def from_files_to_files(
+    loudness_files: List[Union[str, os.PathLike]],
+    pitch_files: List[Union[str, os.PathLike]],
+    periodicity_files: List[Union[str, os.PathLike]],
+    ppg_files: List[Union[str, os.PathLike]],
+    output_files: List[Union[str, os.PathLike]],
+    speakers: Optional[List[int]] = None,
+    spectral_balance_ratio: float = 1.,
+    loudness_ratio: float = 1.,
+    checkpoint: Optional[Union[str, os.PathLike]] = None,
+    gpu: Optional[int] = None,
+    max_batch: int = 32
+) -> None:
+    """Perform batched speech synthesis from features on disk and save
+    (synthesize/core.py:158-201, where it is a per-file loop at batch 1).  Utterances with the
+    same number of frames are synthesized together, up to `max_batch` per launch; the vocoder
+    is fully convolutional, so a batch gives each utterance exactly its batch-1 result."""
+    device = _device(gpu)
+    if speakers is None:
+        speakers = [0] * len(pitch_files)
+    features = [
+        _load_features(*files, device) for files in zip(
+            loudness_files, pitch_files, periodicity_files, ppg_files)]
+    buckets = {}
+    for index, (loudness, pitch, _, _) in enumerate(features):
+        buckets.setdefault((pitch.shape[-1], loudness.shape[-2]), []).append(index)
+    for members in buckets.values():
+        for start in range(0, len(members), max_batch):
+            chunk = members[start:start + max_batch]
+            count = len(chunk)
+            generated = from_features_batch(
+                torch.stack([features[i][0] for i in chunk]),
+                torch.cat([features[i][1] for i in chunk]),
+                torch.cat([features[i][2] for i in chunk]),
+                torch.stack([features[i][3] for i in chunk]),
+                torch.tensor([int(speakers[i]) for i in chunk], device=device),
+                torch.full((count,), spectral_balance_ratio, device=device),
+                torch.full((count,), loudness_ratio, device=device),
+                checkpoint, gpu).cpu()
+            for i, audio in zip(chunk, generated):
+                _save(output_files[i], audio)
+
+
+def _load_features(loudness_file, pitch_file, periodicity_file, ppg_file, device):
+    loudness = torch.load(loudness_file, map_location='cpu').to(device, torch.float32)
+    pitch = torch.load(pitch_file, map_location='cpu').to(device, torch.float32)
+    periodicity = torch.load(periodicity_file, map_location='cpu').to(device, torch.float32)
+    ppg = promonet_b200.load.ppg(ppg_file, resample_length=pitch.shape[-1], device=device)
+    return loudness, pitch, periodicity, ppg.to(torch.float32)
+
+
+def _save(output_file, audio):
+    """torchaudio.save(output_file, generated, SAMPLE_RATE) (synthesize/core.py:155): 16-bit PCM
+    wav written directly (torchaudio's save backends are optional dependencies)"""
+    import wave
+    output_file = Path(output_file)
+    output_file.parent.mkdir(exist_ok=True, parents=True)
+    samples = (audio.reshape(-1).clamp(-1., 1.) * 32767.).round().to(torch.int16)
+    with wave.open(str(output_file), 'wb') as file:
+        file.setnchannels(1)
+        file.setsampwidth(2)
+        file.setframerate(promonet_b200.SAMPLE_RATE)
+        file.writeframes(samples.numpy().tobytes())
 
 
 def generate(

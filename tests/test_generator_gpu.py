@@ -222,3 +222,35 @@ def test_generator_reports_errors(model, lib):
     with pytest.raises(lib.Error, match='missing tensor'):
         lib.check(lib.library().pmn_generator_finalize(handle, 0, lib.stream()))
     lib.library().pmn_generator_destroy(handle)
+
+
+def test_from_files_to_files_batches_equal_lengths(tmp_path):
+    """synthesize/core.py:62-201: features on disk -> wav files, utterances of equal length in one
+    batch, each identical to its own batch-1 synthesis"""
+    import wave
+    import promonet_b200
+    from promonet_b200 import synthesize
+    files = {k: [] for k in ('loudness', 'pitch', 'periodicity', 'ppg', 'output')}
+    expected = []
+    for index, frames in enumerate((20, 33, 20, 20)):
+        loud, pitch, per, ppg, _, _, _ = inputs.synthesis(1, frames, seed=50 + index)
+        stretched = torch.softmax(2. * torch.randn(40, frames + 7), dim=-2)   # needs resampling
+        for name, value in (('loudness', loud[0]), ('pitch', pitch), ('periodicity', per),
+                            ('ppg', stretched)):
+            file = tmp_path / f'{index}-{name}.pt'
+            torch.save(value, file)
+            files[name].append(file)
+        files['output'].append(tmp_path / 'out' / f'{index}.wav')
+        expected.append(synthesize.from_file(
+            files['loudness'][-1], files['pitch'][-1], files['periodicity'][-1], files['ppg'][-1],
+            speaker=index))
+    synthesize.from_files_to_files(
+        files['loudness'], files['pitch'], files['periodicity'], files['ppg'], files['output'],
+        speakers=[0, 1, 2, 3])
+    for file, audio in zip(files['output'], expected):
+        with wave.open(str(file), 'rb') as handle:
+            assert handle.getframerate() == promonet_b200.SAMPLE_RATE
+            data = torch.frombuffer(bytearray(handle.readframes(handle.getnframes())), dtype=torch.int16)
+        assert data.shape[0] == audio.shape[-1]
+        quantized = (audio.cpu().reshape(-1).clamp(-1., 1.) * 32767.).round()
+        assert (data.float() - quantized).abs().max() <= 1.

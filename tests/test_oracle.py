@@ -137,3 +137,20 @@ def test_fargan_oracle_matches_reference_output(golden):
         assert relative_error(fargan.generator(state, *args), g['audio']) < 1e-5
         assert relative_error(
             fargan.generator(state, *args, g['previous']), g['audio_previous']) < 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present')
+@pytest.mark.parametrize('method', ['linear', 'nearest'])
+def test_grid_sample_oracle_matches_live_reference(method):
+    promonet = ref_shim.load()
+    torch.manual_seed(3)
+    sequence = torch.rand(2, 40, 57)
+    grid = torch.linspace(0., 56., 91)
+    assert torch.equal(
+        features.grid_sample(sequence, grid, method), promonet.edit.grid.sample(sequence, grid, method))
+
+
+def test_grid_sample_oracle_matches_golden(golden):
+    g = golden('grid')
+    for method in ('linear', 'nearest'):
+        assert torch.equal(features.grid_sample(g['sequence'], g['grid'], method), g[method])

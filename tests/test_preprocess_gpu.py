@@ -222,3 +222,30 @@ def test_preprocess_batch_items_are_independent(pb):
     single = pb.preprocess.from_audio_batch(audio[1:2], features=['loudness', 'pitch', 'periodicity', 'mels'])
     for a, b in zip(full, single):
         assert torch.equal(a[1:2], b)
+
+
+@pytest.mark.parametrize('method', ['linear', 'nearest'])
+def test_grid_sample_matches_reference_golden(golden, method):
+    """promonet.edit.grid.sample (edit/grid.py:12-43): golden frozen from the reference"""
+    import promonet_b200
+    g = golden('grid')
+    out = promonet_b200.edit.grid.sample(g['sequence'].cuda(), g['grid'].cuda(), method)
+    assert out.shape == g[method].shape
+    assert relative_error(out, g[method]) < 1e-6
+
+
+def test_ppg_resampling_matches_oracle(tmp_path):
+    """preprocess/core.py:97-103 (resample + softmax(log(p + 1e-8))) and load.ppg (load.py:172-188)"""
+    import promonet_b200
+    from oracle import features as oracle_features
+    torch.manual_seed(4)
+    ppg = torch.softmax(2. * torch.randn(40, 130), dim=-2)
+    for length in (87, 130, 301):
+        grid = promonet_b200.edit.grid.of_length(ppg, length)
+        out = promonet_b200.edit.grid.sample(ppg.cuda(), grid, 'linear', renormalize=True)
+        assert relative_error(out, oracle_features.resample_ppg(ppg, length)) < 1e-6
+    torch.save(ppg, tmp_path / 'x-ppg.pt')
+    loaded = promonet_b200.load.ppg(tmp_path / 'x-ppg.pt', resample_length=87)
+    expected = oracle_features.grid_sample(ppg, torch.linspace(0., 129., 87))
+    assert relative_error(loaded, expected) < 1e-6
+    assert promonet_b200.load.ppg(tmp_path / 'x-ppg.pt', resample_length=130).shape == (40, 130)
