@@ -9,7 +9,7 @@ import torch
 from promonet_b200 import config
 from promonet_b200.preprocess import loudness, penn, spectrogram
 
-__all__ = ['from_audio', 'from_audio_batch']
+__all__ = ['from_audio', 'from_audio_batch', 'from_file', 'from_file_to_file', 'from_files_to_files']
 
 SUPPORTED = ('loudness', 'pitch', 'periodicity', 'spectrogram', 'mels')
 
@@ -84,6 +84,69 @@ def from_audio_batch(
     if 'mels' in features:
         result.append(spectrogram.from_audio(audio[:, None], mels=True))
     return tuple(result)
+
+
+def from_file(file, gpu=None, features=['loudness', 'pitch', 'periodicity'],
+              loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None) -> Tuple:
+    """Preprocess audio on disk (promonet/preprocess/core.py:129-166); 22.05 kHz PCM wav"""
+    return from_audio(
+        load_audio(file), gpu=gpu, features=features, loudness_bands=loudness_bands)
+
+
+def from_file_to_file(file, output_prefix=None, gpu=None,
+                      features=['loudness', 'pitch', 'periodicity'],
+                      loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None) -> None:
+    """Preprocess audio on disk and save (preprocess/core.py:169-224)"""
+    from_files_to_files(
+        [file], None if output_prefix is None else [output_prefix], gpu, features, loudness_bands)
+
+
+def from_files_to_files(files, output_prefixes=None, gpu=None,
+                        features=['loudness', 'pitch', 'periodicity'],
+                        loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None,
+                        max_batch=32) -> None:
+    """Preprocess multiple audio files on disk and save (preprocess/core.py:227-319): writes
+    `{prefix}-loudness.pt`, `{prefix}-viterbi-pitch.pt`, `{prefix}-viterbi-periodicity.pt` (the
+    names of the reference under VITERBI_DECODE_PITCH, :262-268), `{prefix}-spectrogram.pt`,
+    `{prefix}-mels.pt`.  Files of equal length are processed as one batch (every feature is
+    computed per utterance, so batching does not change a result)."""
+    from pathlib import Path
+    files = [Path(file) for file in files]
+    if output_prefixes is None:
+        output_prefixes = [file.parent / file.stem for file in files]
+    suffixes = {
+        'loudness': '-loudness.pt', 'pitch': '-viterbi-pitch.pt',
+        'periodicity': '-viterbi-periodicity.pt', 'spectrogram': '-spectrogram.pt',
+        'mels': '-mels.pt'}
+    audio = [load_audio(file) for file in files]
+    buckets = {}
+    for index, item in enumerate(audio):
+        buckets.setdefault(item.shape[-1], []).append(index)
+    order = [f for f in SUPPORTED if f in features]
+    for members in buckets.values():
+        for start in range(0, len(members), max_batch):
+            chunk = members[start:start + max_batch]
+            results = from_audio_batch(
+                torch.cat([audio[i] for i in chunk]), config.SAMPLE_RATE, gpu, features, loudness_bands)
+            for name, values in zip(order, results):
+                for i, value in zip(chunk, values.cpu()):
+                    # pitch and periodicity are stored (1, F) like penn's outputs
+                    value = value[None] if name in ('pitch', 'periodicity') else value
+                    torch.save(value.clone(), f'{output_prefixes[i]}{suffixes[name]}')
+
+
+def load_audio(file):
+    """promonet.load.audio (promonet/load.py:16-36) for 16-bit PCM wav at the model's rate -> (1, T)"""
+    import wave
+    with wave.open(str(file), 'rb') as handle:
+        if handle.getframerate() != config.SAMPLE_RATE or handle.getsampwidth() != 2:
+            raise ValueError(
+                f'{file}: expected 16-bit PCM at {config.SAMPLE_RATE} Hz (resampling of other '
+                'rates is outside the accelerated path)')
+        channels = handle.getnchannels()
+        data = torch.frombuffer(
+            bytearray(handle.readframes(handle.getnframes())), dtype=torch.int16)
+    return (data.float() / 32768.).reshape(-1, channels).mean(1)[None]
 
 
 def _pitch_model(device):

@@ -249,3 +249,33 @@ def test_ppg_resampling_matches_oracle(tmp_path):
     expected = oracle_features.grid_sample(ppg, torch.linspace(0., 129., 87))
     assert relative_error(loaded, expected) < 1e-6
     assert promonet_b200.load.ppg(tmp_path / 'x-ppg.pt', resample_length=130).shape == (40, 130)
+
+
+def test_from_files_to_files(tmp_path):
+    """preprocess/core.py:227-319: wav files in, feature files out, equal lengths batched"""
+    import wave
+    import promonet_b200
+    from promonet_b200 import preprocess
+    files = []
+    for index, samples in enumerate((8192, 6400, 8192)):
+        audio = inputs.audio(1, samples, seed=70 + index)
+        file = tmp_path / f'utt{index}.wav'
+        with wave.open(str(file), 'wb') as handle:
+            handle.setnchannels(1)
+            handle.setsampwidth(2)
+            handle.setframerate(22050)
+            handle.writeframes((audio[0] * 32767.).round().to(torch.int16).numpy().tobytes())
+        files.append(file)
+    features = ['loudness', 'pitch', 'periodicity', 'mels']
+    preprocess.from_files_to_files(files, features=features)
+    for file in files:
+        expected = preprocess.from_file(file, features=features)
+        prefix = file.parent / file.stem
+        loudness = torch.load(f'{prefix}-loudness.pt')
+        pitch = torch.load(f'{prefix}-viterbi-pitch.pt')
+        periodicity = torch.load(f'{prefix}-viterbi-periodicity.pt')
+        mels = torch.load(f'{prefix}-mels.pt')
+        frames = preprocess.core.load_audio(file).shape[-1] // 256
+        assert loudness.shape == (8, frames) and pitch.shape == (1, frames) and mels.shape == (80, frames)
+        for saved, value in zip((loudness, pitch, periodicity, mels), expected):
+            assert relative_error(saved, value.reshape(saved.shape)) < 1e-5
