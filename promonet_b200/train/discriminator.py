@@ -45,8 +45,7 @@ class Period:
             geometry = ops.geometry(
                 n, conv.dim1, conv.dim0, source.shape[2:], kernel, stride, 1, padding)
             out = torch.empty(n, conv.dim0, geometry.h_out, geometry.w_out, device=x.device)
-            conv.apply(
-                        geometry, False, source, out, bias=conv.bias,
+            conv.apply(geometry, False, source, out, bias=conv.bias,
                 out_act=ops.OUT_LRELU if i < 5 else ops.OUT_NONE, out_slope=SLOPE)
             maps.append(out)
             geometries.append(geometry)
@@ -70,8 +69,7 @@ class Period:
             accumulate = target is not None
             if target is None:
                 target = torch.empty_like(x)
-            layers[i].apply_transposed(
-                        geometry, True, g, target, a_companion=y,
+            layers[i].apply_transposed(geometry, True, g, target, a_companion=y,
                           a_act=act[0], a_slope=act[1], accumulate=accumulate)
             if i > 0:
                 gmaps[i - 1] = target
@@ -161,8 +159,7 @@ class ComplexMultiBand:
                     n, conv.dim1, conv.dim0, chain[-1].shape[2:], kernel, stride, 1,
                     (1, kernel[1] // 2))
                 out = torch.empty(n, conv.dim0, geometry.h_out, geometry.w_out, device=x.device)
-                conv.apply(
-                        geometry, False, chain[-1], out, bias=conv.bias,
+                conv.apply(geometry, False, chain[-1], out, bias=conv.bias,
                               out_act=ops.OUT_LRELU, out_slope=SLOPE)
                 chain.append(out)
                 chain_geometry.append(geometry)
@@ -177,8 +174,7 @@ class ComplexMultiBand:
             column += o.shape[-1]
         post_geometry = ops.geometry(n, 32, 1, (frames, total), (3, 3), 1, 1, (1, 1))
         logits = torch.empty(n, 1, frames, total, device=x.device)
-        self.post.apply(
-                        post_geometry, False, joined, logits, bias=self.post.bias)
+        self.post.apply(post_geometry, False, joined, logits, bias=self.post.bias)
         return {
             'maps': maps, 'geometries': geometries, 'joined': joined, 'logits': logits,
             'post_geometry': post_geometry, 'spectrum': spectrum, 'samples': t, 'frames': frames}
@@ -198,8 +194,7 @@ class ComplexMultiBand:
         joined = record['joined'][lo:hi]
         if weights:
             self.post.wgrad(geometry, glogits, joined)
-        gjoined = self.post.apply_transposed(
-                        geometry, True, glogits, torch.empty_like(joined))
+        gjoined = self.post.apply_transposed(geometry, True, glogits, torch.empty_like(joined))
         gbanded = torch.zeros(n * frames * 513, device=gjoined.device) if gaudio is not None else None
         column = 0
         for b, ((first, last), stack) in enumerate(zip(config.CMB_BANDS, self.bands)):
@@ -216,7 +211,8 @@ class ComplexMultiBand:
                 geometry = _with_batch(record['geometries'][b][i], n)
                 y, x = chain[i + 1][lo:hi], chain[i][lo:hi]
                 if weights:
-                    stack[i].wgrad(geometry, g, x, dy_companion=y, dy_act=ops.ACT_LRELU_MASK, dy_slope=SLOPE)
+                    stack[i].wgrad(
+                        geometry, g, x, dy_companion=y, dy_act=ops.ACT_LRELU_MASK, dy_slope=SLOPE)
                 if i == 0 and gaudio is None:
                     break
                 if i > 0:
@@ -227,8 +223,7 @@ class ComplexMultiBand:
                 else:
                     target = gbanded[n * frames * first:n * frames * last].view(x.shape)
                     accumulate = False
-                stack[i].apply_transposed(
-                        geometry, True, g, target, a_companion=y,
+                stack[i].apply_transposed(geometry, True, g, target, a_companion=y,
                               a_act=ops.ACT_LRELU_MASK, a_slope=SLOPE, accumulate=accumulate)
                 g = target
         if gaudio is not None:

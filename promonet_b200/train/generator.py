@@ -80,12 +80,13 @@ class Generator:
         speaker_geometry = ops.geometry(
             batch, config.GLOBAL_CHANNELS, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE, (1, 1), (1, 1))
         speaker_bias = self.speaker_conv.apply(
-                        speaker_geometry, False, gvec, new(batch, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE), bias=self.speaker_conv.bias)
+            speaker_geometry, False, gvec, new(batch, config.HIFIGAN_UPSAMPLE_INITIAL_SIZE),
+            bias=self.speaker_conv.bias)
         channels = config.HIFIGAN_UPSAMPLE_INITIAL_SIZE
         input_geometry = ops.geometry(
             batch, config.NUM_FEATURES, channels, (frames, 1), (7, 1), 1, 1, (3, 0))
         x = self.input_conv.apply(
-                        input_geometry, False, features, new(batch, channels, frames),
+            input_geometry, False, features, new(batch, channels, frames),
             bias=self.input_conv.bias, bias2=speaker_bias)
         saved.update(features=features, gvec=gvec, speaker_geometry=speaker_geometry,
                      input_geometry=input_geometry, stages=[])
@@ -105,18 +106,15 @@ class Generator:
                         zip(block, config.HIFIGAN_RESBLOCK_DILATION_SIZES)):
                     g1 = self._conv_geometry(batch, channels, t, kernel, dilation)
                     g2 = self._conv_geometry(batch, channels, t, kernel, 1)
-                    hidden = c1.apply(
-                        g1, False, current, new(batch, channels, t),
+                    hidden = c1.apply(g1, False, current, new(batch, channels, t),
                         a_act=ops.ACT_LRELU, a_slope=SLOPE, bias=c1.bias)
                     record.append((current, hidden, g1, g2))
                     if m < last:
-                        current = c2.apply(
-                        g2, False, hidden, new(batch, channels, t),
+                        current = c2.apply(g2, False, hidden, new(batch, channels, t),
                             a_act=ops.ACT_LRELU, a_slope=SLOPE, bias=c2.bias, residual=current)
                     else:
                         # ResidualBlock.forward hifigan.py:141-145: mean over the kernels
-                        c2.apply(
-                        g2, False, hidden, mrf, a_act=ops.ACT_LRELU, a_slope=SLOPE,
+                        c2.apply(g2, False, hidden, mrf, a_act=ops.ACT_LRELU, a_slope=SLOPE,
                             bias=c2.bias, residual=current,
                             alpha=1. / len(blocks), accumulate=j > 0)
                 records.append(record)
@@ -124,8 +122,7 @@ class Generator:
             x = mrf
         head_geometry = ops.geometry(batch, channels, 1, (t, 1), (7, 1), 1, 1, (3, 0))
         audio = new(batch, 1, t) if out is None else out
-        self.head.apply(
-                        head_geometry, False, x, audio, a_act=ops.ACT_LRELU, a_slope=SLOPE,
+        self.head.apply(head_geometry, False, x, audio, a_act=ops.ACT_LRELU, a_slope=SLOPE,
             out_act=ops.OUT_TANH)
         saved.update(x_last=x, audio=audio, head_geometry=head_geometry)
         self.saved = saved
@@ -145,8 +142,7 @@ class Generator:
         audio, x_last, geometry = saved['audio'], saved['x_last'], saved['head_geometry']
         self.head.wgrad(geometry, gaudio, x_last, bias=False, dy_companion=audio,
             dy_act=ops.ACT_TANH_MASK, x_act=ops.ACT_LRELU, x_slope=SLOPE)
-        g = self.head.apply_transposed(
-                        geometry, True, gaudio, new(x_last), a_companion=audio,
+        g = self.head.apply_transposed(geometry, True, gaudio, new(x_last), a_companion=audio,
             a_act=ops.ACT_TANH_MASK, mask_src=x_last, mask_slope=SLOPE)
         for (up, blocks), (x_in, xu, records), rate, kernel_size in reversed(list(zip(
                 self.stages, saved['stages'], config.HIFIGAN_UPSAMPLE_RATES,
@@ -167,11 +163,11 @@ class Generator:
                     c1.wgrad(g1, ghidden, current, x_act=ops.ACT_LRELU, x_slope=SLOPE)
                     if m > 0:
                         gcurrent = c1.apply_transposed(
-                        g1, True, ghidden, new(current), mask_src=current,
+                            g1, True, ghidden, new(current), mask_src=current,
                             mask_slope=SLOPE, residual=gcurrent)
                     else:
                         c1.apply_transposed(
-                        g1, True, ghidden, gxu, mask_src=current, mask_slope=SLOPE,
+                            g1, True, ghidden, gxu, mask_src=current, mask_slope=SLOPE,
                             residual=gcurrent, accumulate=j > 0)
             # xu = ConvTranspose1d(lrelu(x_in)) + b: gradients through the convolution it transposes
             batch, c_in, t_in = x_in.shape
@@ -181,14 +177,13 @@ class Generator:
                 ((kernel_size - rate) // 2, 0), size_out=(t_in, 1))
             up.wgrad(geometry, x_in, gxu, bias=False, dy_act=ops.ACT_LRELU, dy_slope=SLOPE)
             ops.channel_sum(gxu, up.gbias, accumulate=True)
-            g = up.apply(
-                        geometry, False, gxu, new(x_in), mask_src=x_in, mask_slope=SLOPE)
+            g = up.apply(geometry, False, gxu, new(x_in), mask_src=x_in, mask_slope=SLOPE)
         # input layer: x0 = conv7(features) + b + speaker projection
         P = self.params
         features, gvec = saved['features'], saved['gvec']
         self.input_conv.wgrad(saved['input_geometry'], g, features)
         gfeatures = self.input_conv.apply_transposed(
-                        saved['input_geometry'], True, g, new(features))
+            saved['input_geometry'], True, g, new(features))
         ops.embedding_backward(
             gfeatures, saved['bins'], P.gradient('pitch_embedding.weight'),
             channel_offset=config.PPG_CHANNELS)
@@ -197,7 +192,7 @@ class Generator:
             g, torch.empty(batch, channels, device=self.device), batch * channels, frames)
         self.speaker_conv.wgrad(saved['speaker_geometry'], gspeaker, gvec)
         ggvec = self.speaker_conv.apply_transposed(
-                        saved['speaker_geometry'], True, gspeaker, new(gvec))
+            saved['speaker_geometry'], True, gspeaker, new(gvec))
         ops.embedding_backward(
             ggvec.view(batch, config.GLOBAL_CHANNELS, 1), saved['speakers'].view(batch, 1),
             P.gradient('speaker_embedding.weight'), channel_offset=0)
