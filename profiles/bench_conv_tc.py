@@ -52,6 +52,7 @@ def main():
     parser.add_argument('--filter', default='')
     parser.add_argument('--wgrad', action='store_true')
     parser.add_argument('--cycles', action='store_true', help='cycle breakdown of CTA 0 (forward)')
+    parser.add_argument('--plain', action='store_true', help='no fused activation / residual / mask')
     args = parser.parse_args()
     print(f'{"layer":22s} {"GFLOP":>8s} {"fprop ms":>9s} {"TF/s":>7s} {"dgrad ms":>9s} {"TF/s":>7s}'
           + (f' {"wgrad ms":>9s} {"TF/s":>7s}' if args.wgrad else ''))
@@ -71,10 +72,10 @@ def main():
         packed_t = ops.pack_weight_taps(
             w, torch.empty(ops.packed_floats(c_in, c_out, taps), device='cuda'), c_out, c_in, taps, True)
         flop = 2. * batch * geom.h_out * geom.w_out * c_out * c_in * taps
-        forward = timed(lambda: ops.conv_gemm_tc(
-            geom, False, x, packed, y, a_act=ops.ACT_LRELU, a_slope=.1, residual=dy))
-        backward = timed(lambda: ops.conv_gemm_tc(
-            geom, True, dy, packed_t, dx, mask_src=x, mask_slope=.1))
+        fused = {} if args.plain else dict(a_act=ops.ACT_LRELU, a_slope=.1, residual=dy)
+        forward = timed(lambda: ops.conv_gemm_tc(geom, False, x, packed, y, **fused))
+        fused = {} if args.plain else dict(mask_src=x, mask_slope=.1)
+        backward = timed(lambda: ops.conv_gemm_tc(geom, True, dy, packed_t, dx, **fused))
         if args.cycles:
             from promonet_b200 import _lib
             counters = torch.zeros(8, dtype=torch.int64, device='cuda')
@@ -84,9 +85,8 @@ def main():
             _lib.library().pmn_debug_train_tc_counters(None)
             c = counters.tolist()
             steps = max(c[6], 1)
-            print(f'    cycles/step: loop {c[0] / steps:.0f} = wait {c[1] / steps:.0f} + load {c[2] / steps:.0f}'
-                  f' + store {c[3] / steps:.0f} + sync {c[4] / steps:.0f} + mma {c[5] / steps:.0f};'
-                  f' steps {steps}; until accumulators done {c[7]}')
+            print(f'    CTA 0 cycles: producers done {c[0]} (waiting for a stage {c[1]}, storing {c[3]}), '
+                  f'MMA thread waited {c[5]}, accumulators done {c[7]}, epilogue done {c[4]}; {steps} K steps')
         line = (f'{name:22s} {flop / 1e9:8.2f} {forward:9.3f} {flop / forward / 1e9:7.1f} '
                 f'{backward:9.3f} {flop / backward / 1e9:7.1f}')
         totals[0] += flop; totals[1] += forward; totals[2] += backward

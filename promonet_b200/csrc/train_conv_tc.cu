@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
             uint32_t raw[16];
             __syncwarp();
             tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int n = n0 + c0 + i;
                 if (!ok || n >= p.o_ch) continue;
@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (timing && tid == 0) p.debug[4] = clock64() - begin;   // end of the epilogue
     if (warp == kProducers / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(kProducers + 32, 1) conv_wgrad_tc_kernel(TcWgr
             uint32_t raw[16];
             __syncwarp();
             tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int n = n0 + c0 + i;
                 const float v = __uint_as_float(raw[i]);
