@@ -31,6 +31,7 @@ constexpr int kProducers = 512;        // gather / epilogue threads
 constexpr int kThreads = kProducers + 64;  // + the MMA issuing warp + the weight-copy warp
 constexpr int kStages = 3;             // pipeline stages (2 for the 256-column tiles: 96 KB each)
 constexpr int kBM = 128;
+constexpr int kMaxPhases = 9;          // stride (3, 3) at most
 constexpr int kKStep = 32;            // fp32 operands per row per K step (one tap, 32 channels)
 constexpr int kPair = 2;              // K steps per pipeline stage
 
@@ -123,6 +124,12 @@ struct TcParams {
     int taps, c_pad, m_total, o_positions;
     int channel_stride, position_stride;
     size_t batch_stride;
+    // Strided data gradient: output rows grouped by phase ((h + ph) mod sh, (w + pw) mod sw) so that
+    // a tile only walks the taps that can reach it (1 / (sh sw) of them).  phases = 0: off.
+    int phases;
+    int phase_tile_start[kMaxPhases + 1];
+    int phase_h0[kMaxPhases], phase_w0[kMaxPhases];   // first output row / column of the phase
+    int phase_qh[kMaxPhases], phase_qw[kMaxPhases];   // rows / columns of the phase
 };
 
 __device__ float g_zero_words[4] = {0.f, 0.f, 0.f, 0.f};  // what rows outside the input read
@@ -149,9 +156,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
 
     const pmn_conv_geometry& g = p.a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * kBM;
     const int n0 = blockIdx.y * BN;
     constexpr int kMmaWarp = kProducers / 32, kCopyWarp = kMmaWarp + 1;
+    __shared__ int tap_ids[kMaxTaps];        // the taps this tile walks (all, or those of its phase)
+    __shared__ int tap_count;
+
+    // Row mapping: tile-local row -> (batch item, output position).  Phased: rows enumerate
+    // (item, q_h, q_w) of one phase, position = (h0 + q_h sh, w0 + q_w sw).
+    int phase = -1, m0 = blockIdx.x * kBM, rows_total = p.m_total;
+    if (TRANSPOSED && p.phases > 0) {
+        phase = 0;
+        while (phase + 1 < p.phases && (int)blockIdx.x >= p.phase_tile_start[phase + 1]) ++phase;
+        m0 = ((int)blockIdx.x - p.phase_tile_start[phase]) * kBM;
+        rows_total = p.a.g.batch * p.phase_qh[phase] * p.phase_qw[phase];
+    }
+    auto decode_row = [&](int m, int* b, int* oh, int* ow) {
+        if (phase < 0) {
+            *b = m / p.o_positions;
+            const int rem = m - *b * p.o_positions;
+            *oh = rem / p.o_w;
+            *ow = rem - *oh * p.o_w;
+        } else {
+            const int per_item = p.phase_qh[phase] * p.phase_qw[phase];
+            *b = m / per_item;
+            const int rem = m - *b * per_item;
+            const int qh = rem / p.phase_qw[phase];
+            *oh = p.phase_h0[phase] + qh * p.a.g.sh;
+            *ow = p.phase_w0[phase] + (rem - qh * p.phase_qw[phase]) * p.a.g.sw;
+        }
+    };
 
     if (tid == 0) {
         for (int i = 0; i < kNStages; ++i) {
@@ -161,9 +194,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         mbar_init(&acc_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = tid; t < min(p.taps, kMaxTaps); t += kThreads) {
-        const int i = t / g.kw;
-        tap_offsets[t] = make_int2(i * g.dh, (t - i * g.kw) * g.dw);
+    if (tid == 0) {
+        // taps in order; a phased tile keeps those with i = (h + ph) mod sh, j = (w + pw) mod sw
+        int count = 0;
+        const int rh = phase < 0 ? 0 : (p.phase_h0[phase] + g.ph) % g.sh;
+        const int rw = phase < 0 ? 0 : (p.phase_w0[phase] + g.pw) % g.sw;
+        for (int t = 0; t < min(p.taps, kMaxTaps); ++t) {
+            const int i = t / g.kw, j = t - i * g.kw;
+            if (phase >= 0 && (i % g.sh != rh || j % g.sw != rw)) continue;
+            tap_ids[count] = t;
+            tap_offsets[count] = make_int2(i * g.dh, j * g.dw);
+            ++count;
+        }
+        tap_count = p.taps > kMaxTaps ? p.taps : count;
     }
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -176,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     const uint32_t tmem_base = tmem_slot;
 
     const int blocks_per_tap = p.c_pad / kKStep;
-    const int k_steps = p.taps * blocks_per_tap;
+    const int taps = tap_count;
+    const int k_steps = taps * blocks_per_tap;
     const int stages_total = (k_steps + kPair - 1) / kPair;
     const bool timing = p.debug != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
     const long long begin = timing ? clock64() : 0;
@@ -222,17 +266,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         // ===== weight copy: one thread, one bulk copy per stage (slabs are stored in K-step order) =====
         if (lane == 0) {
             constexpr size_t kSlabFloats = kSlabRows * kKStep;
-            const float* slabs = p.a.wmat + (size_t)blockIdx.y * kSlabs * k_steps * kSlabFloats;
+            const size_t all_steps = (size_t)p.taps * blocks_per_tap;   // slabs per 128-row tile
+            const float* slabs = p.a.wmat + (size_t)blockIdx.y * kSlabs * all_steps * kSlabFloats;
             for (int it = 0; it < stages_total; ++it) {
                 const int s = it % kNStages;
                 if (it >= kNStages) mbar_wait(empty + s, ((it / kNStages) - 1) & 1);
                 const int subs = min(kPair, k_steps - it * kPair);
                 mbar_expect_tx(full + s, kSlabs * subs * kSlabBytes);
+                for (int sub = 0; sub < subs; ++sub) {
+                    // K step -> (tap of this tile's list, channel block) -> slab of the packed weight
+                    const int step = it * kPair + sub;
+                    const int k = step / blocks_per_tap, cb = step - k * blocks_per_tap;
+                    const size_t slab = (size_t)(p.taps > kMaxTaps ? k : tap_ids[k]) * blocks_per_tap + cb;
 #pragma unroll
-                for (int tile = 0; tile < kSlabs; ++tile)
-                    bulk_copy(stage_b(s, tile, 0),
-                              slabs + ((size_t)tile * k_steps + (size_t)it * kPair) * kSlabFloats,
-                              subs * kSlabBytes, full + s);
+                    for (int tile = 0; tile < kSlabs; ++tile)
+                        bulk_copy(stage_b(s, tile, sub), slabs + ((size_t)tile * all_steps + slab) * kSlabFloats,
+                                  kSlabBytes, full + s);
+                }
             }
         }
     } else {
@@ -241,15 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         const int arow = tid & (kBM - 1);
         const int aquarter = tid >> 7;
         const int m_load = m0 + arow;
-        const bool m_ok = m_load < p.m_total;
+        const bool m_ok = m_load < rows_total;
         int hb, wb;
         const float* a_base = p.a.a;
         const float* c_base = kCompanion ? p.a.a_companion : nullptr;
         {
-            const int mm = m_ok ? m_load : 0;
-            const int b = mm / p.o_positions;
-            const int rem = mm - b * p.o_positions;
-            const int oh = rem / p.o_w, ow = rem - oh * p.o_w;
+            int b, oh, ow;
+            decode_row(m_ok ? m_load : 0, &b, &oh, &ow);
             if (TRANSPOSED) { hb = oh + g.ph; wb = ow + g.pw; }
             else { hb = oh * g.sh - g.ph; wb = ow * g.sw - g.pw; }
             const size_t offset = (size_t)b * p.batch_stride;
@@ -269,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
         int tap_stride = 0;
         auto enter_tap = [&]() {
             int2 o;
-            if (tap < kMaxTaps) o = tap_offsets[tap];
+            if (p.taps <= kMaxTaps) o = tap_offsets[tap];
             else { const int i = tap / g.kw; o = make_int2(i * g.dh, (tap - i * g.kw) * g.dw); }
             int hi, wi;
             bool ok = m_ok;
@@ -317,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
             ++loaded;
             if (++cb == blocks_per_tap) {
                 cb = 0;
-                if (++tap < p.taps) enter_tap();
+                if (++tap < taps) enter_tap();
             }
         };
         auto finish = [&](const float (&va)[kAPer], const float (&vc)[kAPer], float4 (&out)[kAPer / 4]) {
@@ -382,10 +430,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
     if (warp < 4 * kGroups) {
         const int quad = warp & 3, group = warp >> 2;
         const int m = m0 + quad * 32 + lane;
-        const bool ok = m < p.m_total;
-        const int mm = ok ? m : 0;
-        const int b = mm / p.o_positions;
-        const int rem = mm - b * p.o_positions;
+        const bool ok = m < rows_total;
+        int b, oh, ow;
+        decode_row(ok ? m : 0, &b, &oh, &ow);
+        const int rem = oh * p.o_w + ow;
 #pragma unroll 1
         for (int c0 = group * kGroupCols; c0 < (group + 1) * kGroupCols; c0 += 16) {
             uint32_t raw[16];
@@ -396,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
                 const int n = n0 + c0 + i;
                 if (!ok || n >= p.o_ch) continue;
                 const size_t idx = ((size_t)b * p.o_ch + n) * p.o_positions + rem;
-                float v = __uint_as_float(raw[i]);
+                float v = k_steps > 0 ? __uint_as_float(raw[i]) : 0.f;   // no tap reaches this phase
                 if (p.a.bias) v += __ldg(p.a.bias + n);
                 if (p.a.bias2) v += __ldg(p.a.bias2 + (size_t)b * p.o_ch + n);
                 if (p.a.out_act == kOutLrelu) v = leaky(v, p.a.out_slope);
@@ -463,7 +511,8 @@ int launch_instance(const TcParams& p, cudaStream_t stream) {
             "conv_gemm_tc smem attribute"));
         configured = true;
     }
-    dim3 grid(ceil_div(p.m_total, kBM), ceil_div(p.o_ch, BN));
+    const int m_tiles = p.phases > 0 ? p.phase_tile_start[p.phases] : ceil_div(p.m_total, kBM);
+    dim3 grid(m_tiles, ceil_div(p.o_ch, BN));
     PMN_REQUIRE(grid.y <= 65535, "conv_gemm_tc: too many output channels");
     LaunchScope scope(TRANSPOSED ? "conv_dgrad_tc_kernel" : "conv_fprop_tc_kernel", stream);
     conv_gemm_tc_kernel<BN, TRANSPOSED, A_ACT><<<grid, kThreads, smem, stream>>>(p);
@@ -993,9 +1042,28 @@ int launch_conv_gemm_tc(const ConvGemmArgs& args, cudaStream_t stream) {
     p.channel_stride = strided ? g.channel_stride : p.a_h * p.a_w;
     p.position_stride = strided ? g.position_stride : 1;
     p.batch_stride = strided ? (size_t)g.batch_stride : (size_t)p.a_ch * p.a_h * p.a_w;
+    p.phases = 0;
+    if (args.transposed && (g.sh > 1 || g.sw > 1) && g.dh == 1 && g.dw == 1 &&
+        g.sh * g.sw <= kMaxPhases && p.taps <= 64) {
+        int tiles = 0;
+        for (int rh = 0; rh < g.sh; ++rh)
+            for (int rw = 0; rw < g.sw; ++rw) {
+                // rows h with (h + ph) mod sh = rh start at h0 and step by sh
+                const int h0 = ((rh - g.ph) % g.sh + g.sh) % g.sh, w0 = ((rw - g.pw) % g.sw + g.sw) % g.sw;
+                const int qh = h0 < p.o_h ? (p.o_h - h0 + g.sh - 1) / g.sh : 0;
+                const int qw = w0 < p.o_w ? (p.o_w - w0 + g.sw - 1) / g.sw : 0;
+                if (qh == 0 || qw == 0) continue;
+                const int k = p.phases++;
+                p.phase_tile_start[k] = tiles;
+                p.phase_h0[k] = h0; p.phase_w0[k] = w0; p.phase_qh[k] = qh; p.phase_qw[k] = qw;
+                tiles += ceil_div(g.batch * qh * qw, kBM);
+            }
+        p.phase_tile_start[p.phases] = tiles;
+    }
+    const int m_tiles_all = p.phases > 0 ? p.phase_tile_start[p.phases] : ceil_div(p.m_total, kBM);
     // two 128-column weight tiles per CTA halve the gather work per FLOP; worth it while the
     // grid still covers most of the 148 SMs
-    if (p.o_ch % 256 == 0 && ceil_div(p.m_total, kBM) * (p.o_ch / 256) >= 100)
+    if (p.o_ch % 256 == 0 && m_tiles_all * (p.o_ch / 256) >= 100)
         return launch_variant<256>(p, stream);
     switch (tile_columns(p.o_ch)) {
         case 128: return launch_variant<128>(p, stream);
