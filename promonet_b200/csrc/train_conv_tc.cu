@@ -683,12 +683,25 @@ __global__ void __launch_bounds__(kProducers + 32, 1) conv_wgrad_tc_kernel(TcWgr
                 } else if (linear) {
                     const int start = first * lin_stride + lin_shift;
                     const int count = col_ok ? p.o_positions - first : 0;   // valid positions from `first`
+                    const int end = start + (kAPer - 1) * lin_stride;
+                    if (count >= kAPer && start >= 0 && end < x_plane) {
+                        // interior (almost every step): no per-element predicate
+                        const float* src = base + start;
+                        if (lin_stride == 1) {
 #pragma unroll
-                    for (int e = 0; e < kAPer; ++e) {
-                        const int idx = start + e * lin_stride;
-                        float value = 0.f;
-                        if (e < count && (unsigned)idx < (unsigned)x_plane) value = __ldg(base + idx);
-                        va[e] = value;
+                            for (int e = 0; e < kAPer; ++e) va[e] = __ldg(src + e);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < kAPer; ++e) va[e] = __ldg(src + e * lin_stride);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < kAPer; ++e) {
+                            const int idx = start + e * lin_stride;
+                            float value = 0.f;
+                            if (e < count && (unsigned)idx < (unsigned)x_plane) value = __ldg(base + idx);
+                            va[e] = value;
+                        }
                     }
                 } else {
                     int oh = first / g.w_out, ow = first - oh * g.w_out;
