@@ -228,3 +228,27 @@ def test_checkpoint_round_trip(states, tmp_path):
     import promonet_b200
     checkpoint = torch.load(next(tmp_path.glob('generator-*.pt')))
     promonet_b200.model.Generator(state=checkpoint['model'])
+
+
+def test_train_entry_point_runs_saves_and_resumes(tmp_path):
+    """promonet_b200.train.train(directory, ..., loader=, steps=): the reference's entry
+    (promonet/train/core.py:17-24) over batches collated like data/collate.py:43-60"""
+    from promonet_b200.train import train
+
+    def loader():
+        for seed in (61, 62, 63):
+            yield (None, *oracle_train.batch(1, 64, seed=seed), None)   # text ... stems
+
+    trainer = train(tmp_path, loader=list(loader()), steps=2)
+    assert trainer.step_count == 2
+    assert (tmp_path / 'generator-00000002.pt').exists()
+    assert (tmp_path / 'discriminator-00000002.pt').exists()
+    resumed = train(tmp_path, loader=list(loader()), steps=3)
+    assert resumed.step_count == 3
+    assert resumed.generator.params.steps == 3
+    assert (tmp_path / 'generator-00000003.pt').exists()
+    checkpoint = torch.load(tmp_path / 'generator-00000003.pt')
+    assert set(checkpoint) >= {'model', 'optimizer', 'step', 'epoch'} and checkpoint['step'] == 3
+    # a batch shorter than CHUNK_SIZE is skipped like train/core.py:154
+    short = [(None, *oracle_train.batch(1, 8, seed=64), None)] + list(loader())
+    assert train(tmp_path, loader=short, steps=4).step_count == 4
