@@ -423,6 +423,20 @@ int pmn_adamw(
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
     const float* step_device, void* stream);
 
+/* The data-parallel exchange of the training step (the all-reduce a DDP wrapper would put after
+ * promonet/train/core.py:255 and :338) fused with the optimizer, over NVLink peer memory:
+ * grad_peers[r] / param_peers[r] (HOST arrays of `world` DEVICE pointers, e.g. the buffer_ptrs of
+ * a symmetric-memory allocation) are rank r's flat gradient / parameter buffers.  This rank
+ * averages elements [begin, end) of all gradient buffers, takes the AdamW step on them with its
+ * own moments (only that slice of exp_avg / exp_avg_sq is maintained: ZeRO-1) and writes the new
+ * parameters into every rank's parameter buffer: reduce-scatter + AdamW + all-gather in one
+ * kernel, no NCCL on the data path.  The caller brackets it with cross-rank barriers (gradients
+ * complete before, parameter writes landed after).  begin, end multiples of 4; world <= 8. */
+int pmn_adamw_peer(
+    const float* const* grad_peers, float* const* param_peers, int world, int rank, float* exp_avg,
+    float* exp_avg_sq, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+    float weight_decay, int step, const float* step_device, void* stream);
+
 /* out[r] (+)= sum_c x[r, c] */
 int pmn_row_sum(const float* x, float* out, int rows, int cols, int accumulate, void* stream);
 

@@ -146,6 +146,10 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
          c_float, c_int, c_float, c_void_p, c_void_p]),
+    'pmn_adamw_peer': (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float,
+         c_float, c_float, c_float, c_int, c_void_p, c_void_p]),
     'pmn_row_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pmn_features': (
         c_int,

@@ -91,6 +91,10 @@ int launch_adamw(
     float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
     float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
     const float* step_device, cudaStream_t stream);
+int launch_adamw_peer(
+    const float* const* grad_peers, float* const* param_peers, int world, int rank, float* exp_avg,
+    float* exp_avg_sq, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+    float weight_decay, int step, const float* step_device, cudaStream_t stream);
 int launch_row_sum(
     const float* x, float* out, int rows, int cols, int accumulate, cudaStream_t stream);
 int launch_channel_sum(

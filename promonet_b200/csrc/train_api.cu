@@ -145,6 +145,15 @@ int pmn_adamw(
         step_device, (cudaStream_t)stream);
 }
 
+int pmn_adamw_peer(
+    const float* const* grad_peers, float* const* param_peers, int world, int rank, float* exp_avg,
+    float* exp_avg_sq, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+    float weight_decay, int step, const float* step_device, void* stream) {
+    return launch_adamw_peer(
+        grad_peers, param_peers, world, rank, exp_avg, exp_avg_sq, begin, end, lr, beta1, beta2, eps,
+        weight_decay, step, step_device, (cudaStream_t)stream);
+}
+
 int pmn_row_sum(const float* x, float* out, int rows, int cols, int accumulate, void* stream) {
     return launch_row_sum(x, out, rows, cols, accumulate, (cudaStream_t)stream);
 }

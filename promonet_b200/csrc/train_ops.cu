@@ -7,6 +7,8 @@ namespace pmn {
 
 namespace {
 
+constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch domain
+
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
     for (int offset = 16; offset > 0; offset >>= 1) v += __shfl_xor_sync(0xffffffffu, v, offset);
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
@@ -129,6 +131,53 @@ __global__ void adamw_kernel(
         const float denom = sqrtf(v) / correction2_sqrt + eps;
         pv -= (lr / correction1) * (m / denom);
         param[i] = pv;
+    }
+}
+
+// Data-parallel AdamW over NVLink peer memory: reduce-scatter + optimizer + all-gather in one
+// kernel.  Every rank owns the elements [begin, end) of the flat parameter buffer: it reads that
+// slice of every rank's gradient buffer through peer pointers, averages, takes the AdamW step
+// with its (shard-local) moments and writes the new parameters into every rank's buffer.
+struct PeerBuffers {
+    const float* grad[kMaxPeers];
+    float* param[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256) adamw_peer_kernel(
+    PeerBuffers peers, int world, int rank, float* __restrict__ exp_avg,
+    float* __restrict__ exp_avg_sq, int64_t begin, int64_t end, float lr, float beta1, float beta2,
+    float eps, float weight_decay, float correction1, float correction2_sqrt,
+    const float* __restrict__ step_device) {
+    if (step_device) {
+        const double t = (double)*step_device;
+        correction1 = (float)(1. - pow((double)beta1, t));
+        correction2_sqrt = (float)sqrt(1. - pow((double)beta2, t));
+    }
+    const float inv_world = 1.f / (float)world;
+    // begin and end are multiples of 4 (the flat buffers are 16-byte aligned and padded)
+    for (int64_t i = begin + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < end;
+         i += 4 * (int64_t)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(peers.grad[r] + i);
+            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+        }
+        float4 pv = *reinterpret_cast<const float4*>(peers.param[rank] + i);
+        float4 m = *reinterpret_cast<const float4*>(exp_avg + i);
+        float4 v = *reinterpret_cast<const float4*>(exp_avg_sq + i);
+        float* pe = &pv.x; float* me = &m.x; float* ve = &v.x; const float* ge = &g.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gr = ge[e] * inv_world;
+            float value = pe[e] * (1.f - lr * weight_decay);
+            me[e] = beta1 * me[e] + (1.f - beta1) * gr;
+            ve[e] = beta2 * ve[e] + (1.f - beta2) * gr * gr;
+            value -= (lr / correction1) * (me[e] / (sqrtf(ve[e]) / correction2_sqrt + eps));
+            pe[e] = value;
+        }
+        *reinterpret_cast<float4*>(exp_avg + i) = m;
+        *reinterpret_cast<float4*>(exp_avg_sq + i) = v;
+        for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(peers.param[r] + i) = pv;
     }
 }
 
@@ -288,6 +337,29 @@ int launch_adamw(
         param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
         correction1, correction2_sqrt, grad_scale, step_device);
     return launched("adamw_kernel");
+}
+
+int launch_adamw_peer(
+    const float* const* grad_peers, float* const* param_peers, int world, int rank, float* exp_avg,
+    float* exp_avg_sq, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+    float weight_decay, int step, const float* step_device, cudaStream_t stream) {
+    PMN_REQUIRE(grad_peers && param_peers && exp_avg && exp_avg_sq && world >= 1 && world <= kMaxPeers &&
+                rank >= 0 && rank < world && begin >= 0 && end >= begin && begin % 4 == 0 && end % 4 == 0 &&
+                (step >= 1 || step_device), "adamw_peer: bad argument");
+    if (end == begin) return PMN_OK;
+    PeerBuffers peers;
+    for (int r = 0; r < world; ++r) {
+        PMN_REQUIRE(grad_peers[r] && param_peers[r], "adamw_peer: null peer pointer");
+        peers.grad[r] = grad_peers[r];
+        peers.param[r] = param_peers[r];
+    }
+    const float correction1 = step_device ? 1.f : (float)(1. - pow((double)beta1, step));
+    const float correction2_sqrt = step_device ? 1.f : (float)sqrt(1. - pow((double)beta2, step));
+    LaunchScope scope("adamw_peer_kernel", stream);
+    adamw_peer_kernel<<<grid_for((end - begin) / 4), 256, 0, stream>>>(
+        peers, world, rank, exp_avg, exp_avg_sq, begin, end, lr, beta1, beta2, eps, weight_decay,
+        correction1, correction2_sqrt, step_device);
+    return launched("adamw_peer_kernel");
 }
 
 int launch_row_sum(

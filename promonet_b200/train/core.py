@@ -30,35 +30,47 @@ class Trainer:
 
     def __init__(self, generator_state=None, discriminator_state=None, device=None,
                  process_group=None, math='tf32', multi_scale_discriminator=False,
-                 spectral_convergence_loss=False):
+                 spectral_convergence_loss=False, peer_optimizer=True, data_parallel=True):
         """math: 'tf32' runs the convolutions' forward and data gradients on the tensor
         cores (tf32 operands, fp32 accumulation; the reference trains under fp16 autocast,
         train/core.py:220); 'fp32' is the exact FMA path used for parity"""
         self.math = math
-        self.generator = Generator(generator_state, device, math)
+        self.process_group = process_group
+        self.world = 1
+        if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        # Data parallel (data_parallel=False: a replica that ignores the process group): by default the gradient exchange is fused with the optimizer in one kernel
+        # over NVLink peer memory (ParamSet.adamw_peer); peer_optimizer=False uses an NCCL
+        # all-reduce of the flat gradient buffer followed by the local AdamW kernel
+        peer_group = None
+        if self.world > 1 and peer_optimizer:
+            peer_group = process_group or torch.distributed.group.WORLD
+        self.generator = Generator(generator_state, device, math, peer_group)
         # MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180) and SPECTRAL_CONVERGENCE_LOSS (:358)
         # are off in config/promonet.py; BASELINE.json's wording of the training config names both
         self.discriminators = Discriminator(
-            discriminator_state, self.generator.device, math, multi_scale_discriminator)
+            discriminator_state, self.generator.device, math, multi_scale_discriminator, peer_group)
         self.spectral_convergence = None
         if spectral_convergence_loss:
             from promonet_b200.train.losses import MultiResolutionSpectralConvergence
             self.spectral_convergence = MultiResolutionSpectralConvergence(self.generator.device, math)
         self.device = self.generator.device
-        self.process_group = process_group
         self.step_count = 0
-        self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world = torch.distributed.get_world_size(process_group)
 
     ###########################################################################
     # Data-parallel gradient exchange
     ###########################################################################
 
-    def all_reduce(self, params):
-        """Sum the flat gradient buffer over ranks (NCCL over NVLink); the mean is taken
-        by the optimizer kernel's grad_scale"""
-        parallel.all_reduce_sum(params.grad, self.process_group)
+    def optimize(self, params):
+        """Exchange the gradients of one module over the data-parallel ranks and take its AdamW
+        step (train/core.py:256,366; torch.optim.AdamW of config/defaults.py:390-394)"""
+        settings = (config.LEARNING_RATE, config.ADAM_BETAS, config.ADAM_EPS, config.WEIGHT_DECAY)
+        if params.peers is not None:
+            params.adamw_peer(*settings)          # one kernel over NVLink peer memory
+        else:
+            if self.world > 1:
+                parallel.all_reduce_sum(params.grad, self.process_group)   # NCCL over NVLink
+            params.adamw(*settings, grad_scale=1. / self.world)
 
     def broadcast_parameters(self, source=0):
         if self.world > 1:
@@ -77,14 +89,14 @@ class Trainer:
                  loudness_ratios, spectrograms, audio)
         self._discriminator_phase(batch)
         if update:
-            self.all_reduce(self.discriminators.params)
-        self._generator_phase(batch, update)
+            self.optimize(self.discriminators.params)
+        self._generator_phase(batch)
         if update:
-            self.all_reduce(self.generator.params)
-        return self._final_phase(update)
+            self.optimize(self.generator.params)
+        return self._final_phase()
 
-    # The step in three pieces, cut where the data-parallel gradient exchange happens, so that
-    # each piece can be captured in a CUDA graph (step_graphed)
+    # The step in three pieces, cut at the two optimizer steps (where the data-parallel exchange
+    # happens), so that each piece can be captured in a CUDA graph (step_graphed)
 
     def _discriminator_phase(self, batch):
         """generator forward (:223), discriminator forward and backward (:239-255)"""
@@ -110,16 +122,14 @@ class Trainer:
         D.layers.zero_grad()
         D.backward(records, gmaps, 0, 2 * count, weights=True)
 
-    def _generator_phase(self, batch, update=True):
-        """discriminator update (:256), second discriminator forward (:272), generator losses
+    def _generator_phase(self, batch):
+        """second discriminator forward with the updated discriminator (:272), generator losses
         (:277-332) and generator backward (:335-338)"""
         G, D = self.generator, self.discriminators
         spectrograms, audio = batch[7], batch[8]
         count, _, samples = audio.shape
         slot, both = self._slot, self.both
-        if update:
-            self.optimize(D.params)
-            D.refresh()
+        D.refresh()
         records = D.forward(both)
         ggenerated = torch.zeros(count, 1, samples, device=self.device)
         gmaps = []
@@ -152,11 +162,9 @@ class Trainer:
         G.backward(ggenerated)
         self.generated = both[count:]
 
-    def _final_phase(self, update=True):
-        """generator update (:366) and the total generator loss (:291,323-332), on the device"""
+    def _final_phase(self):
+        """the total generator loss (:291,323-332), on the device"""
         slot = self._slot
-        if update:
-            self.optimize(self.generator.params)
         ops.axpby(config.MEL_LOSS_WEIGHT, slot('mel'), 0., slot('generator'))
         ops.axpby(1., slot('feature_matching'), 1., slot('generator'))
         ops.axpby(1., slot('adversarial'), 1., slot('generator'))
@@ -168,18 +176,14 @@ class Trainer:
         index = LOSSES.index(name)
         return self.losses[index:index + 1]
 
-    def optimize(self, params):
-        params.adamw(
-            config.LEARNING_RATE, config.ADAM_BETAS, config.ADAM_EPS, config.WEIGHT_DECAY,
-            grad_scale=1. / self.world)
-
     ###########################################################################
     # CUDA-graph replay of the step
     ###########################################################################
 
     def step_graphed(self, *batch):
-        """Same step with its ~1500 kernel launches replayed from three CUDA graphs (cut at the
-        two gradient all-reduces, which stay eager NCCL calls).  Shapes are fixed by the first
+        """Same step with its ~790 kernel launches replayed from three CUDA graphs, cut at the two
+        optimizer steps, which stay eager (a fused peer-memory kernel between two device-side
+        barriers, or an NCCL all-reduce and the AdamW kernel).  Shapes are fixed by the first
         call; the batch is copied into static buffers."""
         if getattr(self, 'graphs', None) is None:
             self.static_batch = [t.clone() for t in batch]
@@ -202,20 +206,15 @@ class Trainer:
                     phase()
                 pool = graph.pool()
                 self.graphs.append(graph)
-            # capturing does not execute: undo the host-side counters the phases advanced
-            self.step_count -= 1
-            self.discriminators.params.steps -= 1
-            self.generator.params.steps -= 1
+            self.step_count -= 1   # capturing _final_phase advanced the host counter without running
         for static, tensor in zip(self.static_batch, batch):
             static.copy_(tensor, non_blocking=True)
         self.graphs[0].replay()
-        self.all_reduce(self.discriminators.params)
+        self.optimize(self.discriminators.params)
         self.graphs[1].replay()
-        self.all_reduce(self.generator.params)
+        self.optimize(self.generator.params)
         self.graphs[2].replay()
         self.step_count += 1
-        self.discriminators.params.steps += 1
-        self.generator.params.steps += 1
         return self.losses
 
     ###########################################################################
@@ -224,12 +223,16 @@ class Trainer:
 
     def save(self, directory, epoch=0):
         directory = Path(directory)
-        directory.mkdir(parents=True, exist_ok=True)
+        rank = torch.distributed.get_rank(self.process_group) if self.world > 1 else 0
+        if rank == 0:
+            directory.mkdir(parents=True, exist_ok=True)
         for name, module in (('generator', self.generator), ('discriminator', self.discriminators)):
-            torch.save(
-                {'model': module.state_dict(), 'optimizer': module.params.optimizer_state(),
-                 'step': self.step_count, 'epoch': epoch},
-                directory / f'{name}-{self.step_count:08d}.pt')
+            optimizer = module.params.optimizer_state()    # a collective when the step is sharded
+            if rank == 0:
+                torch.save(
+                    {'model': module.state_dict(), 'optimizer': optimizer,
+                     'step': self.step_count, 'epoch': epoch},
+                    directory / f'{name}-{self.step_count:08d}.pt')
 
     def load(self, directory):
         """Resume from the newest generator-*.pt / discriminator-*.pt (train/core.py:70-105)"""

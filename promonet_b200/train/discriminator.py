@@ -242,7 +242,7 @@ def _with_batch(geometry, batch):
 
 class Discriminator:
 
-    def __init__(self, state=None, device=None, math='tf32', multi_scale=False):
+    def __init__(self, state=None, device=None, math='tf32', multi_scale=False, peer_group=None):
         """multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180; inferred from the
         keys when a state dict is given)"""
         if not torch.cuda.is_available():
@@ -252,7 +252,7 @@ class Discriminator:
         state = init.discriminator_state(multi_scale=multi_scale) if state is None else state
         count = len({k.split('.')[1] for k in state})
         multi_scale = count == len(config.DISCRIMINATOR_PERIODS) + 2
-        self.params = ParamSet(state, self.device)
+        self.params = ParamSet(state, self.device, peer_group=peer_group)
         self.layers = Layers(self.params, math)
         self.modules = [
             Period(self.layers, f'discriminators.{i}', period)

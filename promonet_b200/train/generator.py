@@ -18,13 +18,13 @@ SLOPE = config.LRELU_SLOPE
 
 class Generator:
 
-    def __init__(self, state=None, device=None, math='tf32'):
+    def __init__(self, state=None, device=None, math='tf32', peer_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.train needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
         state = init.hifigan_state() if state is None else state
-        self.params = ParamSet(state, self.device, BUFFERS)
+        self.params = ParamSet(state, self.device, BUFFERS, peer_group)
         self.ppg_threshold = float(state['ppg_threshold'])
         self.layers = Layers(self.params, math)
         conv = self.layers.conv

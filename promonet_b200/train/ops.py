@@ -171,6 +171,18 @@ def adamw(param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, 
         _lib.stream()))
 
 
+def adamw_peer(grad_ptrs, param_ptrs, rank, exp_avg, exp_avg_sq, begin, end, lr, betas, eps,
+               weight_decay, step, step_device=None):
+    """Fused reduce-scatter + AdamW + all-gather over peer memory (pmn_adamw_peer); grad_ptrs /
+    param_ptrs are the per-rank device addresses (ints) of the flat buffers"""
+    world = len(grad_ptrs)
+    grads = (ctypes.c_void_p * world)(*grad_ptrs)
+    params = (ctypes.c_void_p * world)(*param_ptrs)
+    _check(_lib.library().pmn_adamw_peer(
+        grads, params, world, rank, _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), begin, end, lr,
+        betas[0], betas[1], eps, weight_decay, step, _lib.ptr(step_device), _lib.stream()))
+
+
 def row_sum(x, out, rows, cols, accumulate=False):
     _check(_lib.library().pmn_row_sum(
         _lib.ptr(x), _lib.ptr(out), rows, cols, int(accumulate), _lib.stream()))

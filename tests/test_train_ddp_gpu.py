@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, queue):
+def _worker(rank, world, port, queue, peer_optimizer):
     os.environ.update(
         RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
         MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -30,8 +30,9 @@ def _worker(rank, world, port, queue):
     parallel.initialize('nccl', device)
     states = init.hifigan_state(1234), init.discriminator_state(1234)
     batch = oracle_train.batch(4, 8, seed=41)
-    trainer = Trainer(*states, device=device, math='fp32')
+    trainer = Trainer(*states, device=device, math='fp32', peer_optimizer=peer_optimizer)
     assert trainer.world == world
+    assert (trainer.generator.params.peers is not None) == peer_optimizer
     trainer.broadcast_parameters()
     mine = [t.to(device).contiguous() for t in parallel.shard_tensors(list(batch), rank, world)]
     for _ in range(2):
@@ -40,10 +41,7 @@ def _worker(rank, world, port, queue):
     if rank == 0:
         torch.distributed.barrier()
         # single-process yardstick on the same device, outside the process group's reach
-        single = Trainer(*states, device=device, math='fp32')
-        single.world = 1
-        single.process_group = None
-        single.all_reduce = lambda params: None
+        single = Trainer(*states, device=device, math='fp32', data_parallel=False)
         whole = [t.to(device).contiguous() for t in batch]
         for _ in range(2):
             single.step(*whole)
@@ -58,15 +56,22 @@ def _worker(rank, world, port, queue):
         torch.distributed.barrier()
     queue.put((rank, result))
     parallel.barrier()
-    torch.distributed.destroy_process_group()
+    # leave without tearing the process group down: with live symmetric-memory mappings the
+    # teardown can block on the other rank, and the parent only needs the exit code
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
-def test_two_rank_step_matches_single_gpu_full_batch():
+@pytest.mark.parametrize('peer_optimizer', [True, False])
+def test_two_rank_step_matches_single_gpu_full_batch(peer_optimizer):
+    """peer_optimizer=True: gradient exchange fused with AdamW in one kernel over NVLink peer
+    memory (pmn_adamw_peer); False: NCCL all-reduce + local AdamW"""
     context = mp.get_context('spawn')
     queue = context.Queue()
     port = _free_port()
-    workers = [context.Process(target=_worker, args=(rank, 2, port, queue)) for rank in range(2)]
+    workers = [
+        context.Process(target=_worker, args=(rank, 2, port, queue, peer_optimizer))
+        for rank in range(2)]
     for worker in workers:
         worker.start()
     results = dict(queue.get(timeout=900) for _ in workers)
