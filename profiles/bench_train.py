@@ -32,7 +32,7 @@ KERNELS = (
     'conv_fprop_kernel', 'conv_dgrad_kernel', 'conv_wgrad_kernel', 'conv_transpose1d_kernel',
     'weight_norm_fold_kernel', 'weight_norm_backward_kernel', 'transpose_weight_kernel',
     'stft_train_kernel', 'stft_train_backward_kernel', 'mel_loss_kernel', 'mel_kernel',
-    'l1_mean_kernel', 'mse_to_target_kernel', 'axpby_kernel', 'adamw_kernel',
+    'l1_mean_kernel', 'mse_to_target_kernel', 'axpby_kernel', 'adamw_kernel', 'adamw_peer_kernel',
     'reflect_pad_kernel', 'reflect_pad_backward_kernel', 'copy_columns_kernel',
     'channel_sum_kernel', 'row_sum_kernel', 'features_kernel', 'embedding_backward_kernel',
     'pitch_bins_kernel', 'global_features_kernel')
@@ -51,13 +51,16 @@ def main():
     parser.add_argument('--warmup', type=int, default=2)
     parser.add_argument('--no-cpu', action='store_true')
     parser.add_argument('--math', default='tf32', choices=['tf32', 'fp32'])
+    parser.add_argument('--nccl', action='store_true', help='N > 1: NCCL all-reduce + AdamW instead of the fused peer-memory optimizer step')
     parser.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying CUDA graphs')
     args = parser.parse_args()
     rank, local_rank, world = parallel.environment()
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     parallel.initialize('nccl', device)
-    trainer = Trainer(init.hifigan_state(1234), init.discriminator_state(1234), device, math=args.math)
+    trainer = Trainer(
+        init.hifigan_state(1234), init.discriminator_state(1234), device, math=args.math,
+        peer_optimizer=not args.nccl)
     trainer.broadcast_parameters()
     batch = [t.to(device).contiguous() for t in oracle_train.batch(args.batch, args.frames, 1234 + rank)]
     run = trainer.step if args.eager else trainer.step_graphed
@@ -90,7 +93,10 @@ def main():
             'global_batch': items, 'frames': args.frames,
             'dtype': 'f32 (tf32 tensor-core products, fp32 accumulate)' if args.math == 'tf32' else 'f32',
             'gpu_launches_per_step': launches if args.eager else None,
-            'launch': 'eager' if args.eager else 'three CUDA graphs per step + two NCCL all-reduces',
+            'launch': 'eager' if args.eager else 'three CUDA graphs per step, optimizer steps between them',
+            'exchange': None if world == 1 else (
+                'NCCL all-reduce + AdamW kernel' if args.nccl else
+                'pmn_adamw_peer: reduce-scatter + AdamW + all-gather in one kernel over NVLink peer memory'),
             'losses': dict(zip(('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator'),
                                [float(v) for v in losses.cpu()])),
             'tflops': args.batch * FLOP_PER_ITEM * (args.frames / 64) / (ms * 1e-3) / 1e12,
@@ -112,7 +118,7 @@ def main():
         print(json.dumps(result))
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        os._exit(0)   # symmetric-memory mappings make an orderly teardown block on the peers
 
 
 if __name__ == '__main__':
