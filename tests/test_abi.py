@@ -39,3 +39,24 @@ def test_errors_are_reported_without_a_device():
         1., 0, None)
     assert status == -1
     assert b'null' in lib.pmn_last_error()
+
+
+def test_product_paths_refuse_to_run_without_a_gpu():
+    """No CPU fallback anywhere: without CUDA the entry points raise instead of computing"""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import promonet_b200
+    from promonet_b200.train import Trainer
+    with pytest.raises(RuntimeError, match='CUDA'):
+        Trainer()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        promonet_b200.model.Generator()
+    with pytest.raises(RuntimeError, match='CUDA'):
+        promonet_b200.edit.grid.sample(torch.rand(40, 10), torch.linspace(0., 9., 5))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        promonet_b200.preprocess.from_audio(torch.zeros(1, 4096))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        promonet_b200.synthesize.from_features(
+            torch.zeros(8, 4), torch.zeros(1, 4), torch.zeros(1, 4), torch.zeros(1, 40, 4))
