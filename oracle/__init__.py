@@ -13,6 +13,10 @@ arithmetic, citing the reference ``file:line`` it follows.  Pinning status:
   unmodified from ``/root/reference`` through ``oracle.ref_shim`` in the build
   container; the generated vectors live in ``tests/golden`` together with the
   generating script ``oracle/make_golden.py``.
+* ``oracle.train`` (discriminators, losses, one GAN training step with AdamW) is pinned
+  against the reference's own modules composed as ``promonet/train/core.py:183-369``
+  (``oracle/make_golden.py --train`` / ``--train-flags`` -> ``tests/golden/train*.npz``);
+  ``oracle.features.grid_sample`` against ``promonet.edit.grid.sample`` (``grid.npz``).
 * ``ppgs.sparsify``, the librosa pieces of ``oracle.dsp`` (A-weighting, dB,
   mel basis), ``oracle.penn`` and ``oracle.viterbi`` restate third-party
   packages that are absent from ``/root/reference`` (unpinned versions in
