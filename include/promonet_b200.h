@@ -517,6 +517,41 @@ int pmn_grid_sample(
     const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
     int t_out, int nearest, int renormalize, void* stream);
 
+/* ---- In-training validation ----
+ * promonet.evaluate.Metrics.update (promonet/evaluate/metrics.py:38-61) in one pass over
+ * `items` utterances of `frames` frames: adds into sums[PMN_METRICS_SLOTS] (device doubles)
+ *   [0, 1]  loudness: squared error of the row means, count         (metrics.py:185-204)
+ *   [2, 3]  the same over frames where both means exceed loudness_threshold ("loud")
+ *   [4, 5]  ... over the other frames ("quiet")
+ *   [6, 7]  periodicity: squared error, count                        (metrics.py:20,55)
+ *   [8, 9]  |log2 predicted_pitch - log2 target_pitch| over frames where both periodicities
+ *           exceed voicing_threshold (penn.voicing.threshold), count (metrics.py:249-261)
+ *   [10, 11] Jensen-Shannon distance of the sparsified PPGs (ppgs.sparsify 'percentile'
+ *           ppg_threshold, then ppgs.distance reduction='sum'), frames (metrics.py:287-312);
+ *           similarity: optional (40, 40) phoneme-similarity matrix, already raised to
+ *           ppgs.SIMILARITY_EXPONENT, applied as p <- S^T p (ppgs is un-vendored: restated)
+ * loudness (items, bands, frames) — predicted and target may have different row counts, each
+ * is averaged over its own (metrics.py:192-193); pitch, periodicity (items, frames);
+ * ppg (items, 40, frames).  Any predicted/target pair may be NULL (its slots are left alone).
+ * RMSE = sqrt(sums[0] / sums[1]) etc. are formed on the host by the caller. */
+#define PMN_METRICS_SLOTS 12
+int pmn_metrics_update(
+    const float* predicted_loudness, int predicted_bands,
+    const float* target_loudness, int target_bands,
+    const float* predicted_pitch, const float* target_pitch,
+    const float* predicted_periodicity, const float* target_periodicity,
+    const float* predicted_ppg, const float* target_ppg, int ppg_channels,
+    const float* similarity, int items, int frames,
+    float loudness_threshold, float voicing_threshold, float ppg_threshold,
+    double* sums, void* stream);
+/* promonet.edit.from_features for one contour (promonet/edit/core.py:113-128):
+ * sequence (items, t_in) resampled at grid (t_out) like pmn_grid_sample (grid == NULL: no
+ * resampling, t_out == t_in), in the log2 domain when log2_domain != 0 (pitch), then
+ * out = scale * value + shift, clipped to [lo, hi] when lo < hi (pitch shift: FMIN, FMAX). */
+int pmn_edit_contour(
+    const float* sequence, const float* grid, float* out, int items, int t_in, int t_out,
+    int log2_domain, float scale, float shift, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,8 @@ def sparsify(ppg, method='percentile', threshold=torch.tensor(0.85)):
     greater, renormalise through softmax(log(p + 1e-8)).
     """
     if method == 'percentile':
-        cutoff = torch.quantile(ppg, threshold.to(ppg.dtype), dim=-2, keepdim=True)
+        cutoff = torch.quantile(
+            ppg, torch.as_tensor(threshold, dtype=ppg.dtype), dim=-2, keepdim=True)
         ppg = torch.where(ppg > cutoff, ppg, torch.zeros_like(ppg))
     elif method == 'constant':
         ppg = torch.where(ppg > threshold, ppg, torch.zeros_like(ppg))
@@ -95,9 +96,14 @@ def grid_sample(sequence, grid, method='linear'):
     raise ValueError(f'Grid sampling method {method} is not defined')
 
 
+def grid_of_length(frames, length):
+    """ppgs.edit.grid.of_length (un-vendored, PARITY UNPINNED): `length` positions over [0, T - 1]"""
+    return torch.linspace(0., frames - 1., int(length))
+
+
 def resample_ppg(ppg, length):
     """promonet/preprocess/core.py:97-103: grid resample to `length` frames, then
     softmax(log(p + 1e-8)) over the phoneme axis (of_length: ppgs, un-vendored, PARITY UNPINNED:
     restated as linspace(0, T - 1, length))"""
-    grid = torch.linspace(0., ppg.shape[-1] - 1., length)
+    grid = grid_of_length(ppg.shape[-1], length)
     return torch.softmax(torch.log(grid_sample(ppg, grid) + 1e-8), -2)

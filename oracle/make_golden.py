@@ -256,9 +256,64 @@ def train_flags():
     print('wrote train_flags.npz', result['losses'], result['logit_sizes'])
 
 
+def metric_inputs(seed, frames, rows):
+    """Seeded (loudness, pitch, periodicity, ppg) straddling the loudness and voicing thresholds"""
+    generator = torch.Generator().manual_seed(seed)
+    rand = lambda *shape: torch.rand(*shape, generator=generator)
+    return (
+        rand(rows, frames) * 70. - 100.,                        # dB around the -60 dB threshold
+        50. * 11. ** rand(1, frames),                           # 50-550 Hz
+        rand(1, frames) * .4,                                   # around VOICING_THRESHOLD .1625
+        torch.softmax(2. * torch.randn(1, 40, frames, generator=generator), 1))
+
+
+METRIC_CASES = ((37, 8, 8), (200, 8, 513), (1, 513, 8), (64, 8, 8))   # frames, rows, rows
+
+
+def metrics():
+    """promonet.evaluate.Metrics (evaluate/metrics.py:17-312) and promonet.edit.from_features
+    (edit/core.py:17-132) of the UNMODIFIED reference, on top of the restated third-party
+    primitives the shim provides (torchutil.metrics, penn.voicing.threshold, ppgs.distance,
+    ppgs.edit.grid)"""
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    promonet = ref_shim.load()
+    result = {'cases': np.array(METRIC_CASES)}
+    accumulated = promonet.evaluate.Metrics()
+    for index, (frames, rows, target_rows) in enumerate(METRIC_CASES):
+        predicted = metric_inputs(100 + index, frames, rows)
+        target = metric_inputs(200 + index, frames, target_rows)
+        single = promonet.evaluate.Metrics()
+        single.update(*predicted, *target)
+        if index < 3:
+            accumulated.update(*predicted, *target)
+        names = sorted(single())
+        result['names'] = np.array(names)
+        result[f'single_{index}'] = np.array([single()[name] for name in names])
+    result['accumulated'] = np.array([accumulated()[name] for name in names])
+    # edits: the two evaluation ratios (config/defaults.py:204) and a pitch shift + loudness scale
+    loudness, pitch, periodicity, ppg = metric_inputs(300, 57, 8)
+    ppg = ppg[0]
+    edits = (
+        {'time_stretch_ratio': .717}, {'time_stretch_ratio': 1.414},
+        {'pitch_shift_cents': 600., 'loudness_scale_db': 5.},
+        {'pitch_shift_cents': -900., 'time_stretch_ratio': 2.})
+    for index, kwargs in enumerate(edits):
+        outputs = promonet.edit.from_features(
+            loudness.clone(), pitch.clone(), periodicity.clone(), ppg.clone(), **kwargs)
+        for name, value in zip(('loudness', 'pitch', 'periodicity', 'ppg'), outputs):
+            result[f'edit_{index}_{name}'] = value.numpy()
+    result['edit_arguments'] = np.array([
+        [kwargs.get(key, np.nan) for key in
+         ('pitch_shift_cents', 'time_stretch_ratio', 'loudness_scale_db')] for kwargs in edits])
+    np.savez_compressed(GOLDEN / 'metrics.npz', **result)
+    print('wrote metrics.npz', dict(zip(names, result['accumulated'])))
+
+
 if __name__ == '__main__':
     import sys
-    if '--train-flags' in sys.argv:
+    if '--metrics' in sys.argv:
+        metrics()
+    elif '--train-flags' in sys.argv:
         train_flags()
     elif '--fargan' in sys.argv:
         fargan()

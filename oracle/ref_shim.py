@@ -8,8 +8,11 @@ pin the restatements against the reference when the reference tree is present.
 The reference cannot be imported as-is: ``promonet/__init__.py:7-35`` imports
 yapecs, GPUtil, ppgs, penn, librosa, torchutil, matplotlib, pypar, pyworld,
 resampy, soundfile, jiwer, umap, whisper -- none installed, no network.  The
-stubs below provide only import-time surface; ``ppgs.sparsify`` is the one stub
-with arithmetic and it forwards to our restatement in ``oracle.features``.
+stubs below provide only import-time surface, except for the few third-party
+primitives the reference's own arithmetic is built on, which forward to our
+restatements: ``ppgs.sparsify`` (``oracle.features``), and for
+``promonet.evaluate.Metrics`` ``torchutil.metrics.{L1, Average, RMSE}``,
+``penn.voicing.threshold`` and ``ppgs.distance`` (``oracle.metrics``).
 """
 import argparse
 import os
@@ -52,7 +55,7 @@ def load(config_file=None):
     if not available():
         raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
 
-    from oracle import features
+    from oracle import features, metrics
 
     def configure(name, defaults):
         # yapecs.configure restatement (promonet/__init__.py:10-11)
@@ -70,10 +73,15 @@ def load(config_file=None):
         configure=configure,
         ArgumentParser=argparse.ArgumentParser)
     _module('GPUtil', getGPUs=lambda: [])
+    grids = types.SimpleNamespace(
+        constant=lambda tensor, ratio: metrics.grid_constant(tensor.shape[-1], ratio),
+        of_length=lambda tensor, length: features.grid_of_length(tensor.shape[-1], length))
     _module(
         'ppgs',
+        edit=types.SimpleNamespace(grid=grids),
         REPRESENTATION_KIND='ppg',
         sparsify=features.sparsify,
+        distance=metrics.ppg_distance,
         PHONEMES=[str(i) for i in range(40)],
         SIMILARITY_EXPONENT=1.2,
         representation_file_extension=lambda: '-ppg.pt')
@@ -95,8 +103,9 @@ def load(config_file=None):
     torchutil.notify = lambda name: (lambda function: function)
     torchutil.metrics = types.ModuleType('torchutil.metrics')
     for cls in ('L1', 'Average', 'RMSE'):
-        setattr(torchutil.metrics, cls, type(cls, (), {}))
+        setattr(torchutil.metrics, cls, getattr(metrics, cls))
     sys.modules['torchutil'] = torchutil
+    sys.modules['penn'].voicing.threshold = metrics.voicing_threshold
 
     argv = sys.argv
     sys.argv = argv[:1]

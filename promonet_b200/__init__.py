@@ -9,6 +9,7 @@ CPU fallback.
 from .config import *
 from . import _lib
 from . import edit
+from . import evaluate
 from . import load
 from . import model
 from . import preprocess

@@ -179,7 +179,17 @@ SIGNATURES = {
         c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pmn_frame_overlap_add': (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    # ---- in-training validation ----
+    'pmn_metrics_update': (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    'pmn_edit_contour': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+         c_float, c_void_p]),
 }
+METRICS_SLOTS = 12    # PMN_METRICS_SLOTS
 
 
 class WeightDesc(ctypes.Structure):

@@ -50,7 +50,7 @@ using namespace pmn;
 extern "C" {
 
 const char* pmn_last_error(void) { return g_last_error.c_str(); }
-int pmn_version(void) { return 2; }
+int pmn_version(void) { return 3; }
 int64_t pmn_launch_count(void) { return g_launch_count.load(); }
 
 void pmn_profile_enable(int enabled) { g_profile_enabled = enabled != 0; }

@@ -1,1 +1,2 @@
 from . import grid
+from .core import contour, from_features, from_file

@@ -1,2 +1,3 @@
 from . import ops
 from .core import Trainer, train
+from .evaluate import evaluate

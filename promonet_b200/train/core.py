@@ -250,12 +250,14 @@ class Trainer:
 
 
 def train(directory, dataset='vctk', train_partition='train', valid_partition='valid',
-          adapt_from=None, gpu=None, loader=None, steps=None):
+          adapt_from=None, gpu=None, loader=None, steps=None, valid_loader=None):
     """promonet.train (promonet/train/core.py:17-24).  The reference builds its loader
     from a preprocessed dataset on disk (promonet/data, out of scope here): pass `loader`,
     an iterable of batches laid out as data/collate.py:43-60
     (text, loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
-    loudness_ratios, spectrograms, audio, stems)."""
+    loudness_ratios, spectrograms, audio, stems).  With `valid_loader` (batch-1 batches of the same
+    layout) the generator is evaluated every EVALUATION_INTERVAL steps like train/core.py:387-426
+    (promonet_b200.train.evaluate)"""
     if loader is None:
         raise ValueError(
             'promonet_b200.train needs `loader`: the dataset pipeline of the reference '
@@ -273,7 +275,13 @@ def train(directory, dataset='vctk', train_partition='train', valid_partition='v
                 continue
             tensors = [t.to(device, non_blocking=True) for t in (
                 loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio)]
+            step = trainer.step_count
             trainer.step(*tensors)
+            if valid_loader is not None and step % config.EVALUATION_INTERVAL == 0:
+                from promonet_b200.train.evaluate import evaluate
+                evaluate(
+                    directory, step, trainer.generator, valid_loader, device.index,
+                    config.DEFAULT_EVALUATION_STEPS)
             if trainer.step_count % config.CHECKPOINT_INTERVAL == 0:
                 trainer.save(directory)
             if trainer.step_count >= steps:
