@@ -25,7 +25,7 @@ def contour(sequence, grid=None, log2_domain=False, scale=1., shift=0., clip=Non
         return out
     lo, hi = (0., 0.) if clip is None else clip
     with torch.cuda.device(sequence.device):
-        _lib.check(_lib.library().pmn_editcontour(
+        _lib.check(_lib.library().pmn_edit_contour(
             _lib.ptr(sequence), _lib.ptr(grid), _lib.ptr(out), sequence.numel() // t_in, t_in,
             t_out, int(log2_domain), scale, shift, lo, hi, _lib.stream()))
     return out
