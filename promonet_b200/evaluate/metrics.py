@@ -24,11 +24,13 @@ NAMES = ('loudness', 'loudness-loud', 'loudness-quiet', 'periodicity', 'pitch', 
 
 class Metrics:
 
-    def __init__(self, device=None, loudness_threshold=-60., similarity=None):
+    def __init__(self, device=None, loudness_threshold=-60., similarity=None, sums=None):
         """loudness_threshold: metrics.py:172; similarity: optional (40, 40) phoneme
         similarity matrix, already raised to ppgs.SIMILARITY_EXPONENT (a data asset
         of the un-vendored ppgs package; without it the distance is the plain
-        Jensen-Shannon distance of the sparsified PPGs)"""
+        Jensen-Shannon distance of the sparsified PPGs); sums: optional device buffer of
+        PMN_METRICS_SLOTS doubles to accumulate into (a row of a table shared by several
+        Metrics, so that data-parallel ranks combine all of them with one all-reduce)"""
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.evaluate.Metrics needs a CUDA device; there is no CPU path')
         self.device = torch.device(
@@ -39,7 +41,12 @@ class Metrics:
         if self.similarity is not None and self.similarity.shape != (
                 config.PPG_CHANNELS, config.PPG_CHANNELS):
             raise ValueError('similarity must be (40, 40)')
-        self.sums = torch.zeros(_lib.METRICS_SLOTS, dtype=torch.float64, device=self.device)
+        if sums is None:
+            sums = torch.zeros(_lib.METRICS_SLOTS, dtype=torch.float64, device=self.device)
+        if sums.shape != (_lib.METRICS_SLOTS,) or sums.dtype != torch.float64 or \
+                not sums.is_contiguous() or sums.device != self.device:
+            raise ValueError(f'sums must be {_lib.METRICS_SLOTS} contiguous doubles on {self.device}')
+        self.sums = sums
 
     def reset(self):
         self.sums.zero_()
@@ -97,13 +104,19 @@ class Metrics:
     def __call__(self):
         """-> {'pitch', 'periodicity', 'ppg' (when PPGs were given), 'loudness', 'loudness-loud',
         'loudness-quiet'} (metrics.py:26-36,180-183); a metric that saw no frame is nan"""
-        sums = self.sums.cpu().tolist()       # the one device-to-host copy
-        mean = lambda i: sums[i] / sums[i + 1] if sums[i + 1] else math.nan
-        result = {'pitch': 1200. * mean(8), 'periodicity': math.sqrt(mean(6))}
-        if sums[11]:
-            result['ppg'] = mean(10)
-        result.update({
-            'loudness': math.sqrt(mean(0)),
-            'loudness-loud': math.sqrt(mean(2)),
-            'loudness-quiet': math.sqrt(mean(4))})
-        return result
+        return finish(self.sums.cpu().tolist())       # the one device-to-host copy
+
+
+def finish(sums):
+    """The scalars of metrics.py:26-36 from the PMN_METRICS_SLOTS running sums
+    (include/promonet_b200.h, pmn_metrics_update): RMSE = sqrt(squares / count), pitch in cents =
+    1200 x mean |log2 ratio| (metrics.py:221-228), PPG distance = total / frames"""
+    mean = lambda i: sums[i] / sums[i + 1] if sums[i + 1] else math.nan
+    result = {'pitch': 1200. * mean(8), 'periodicity': math.sqrt(mean(6))}
+    if sums[11]:
+        result['ppg'] = mean(10)
+    result.update({
+        'loudness': math.sqrt(mean(0)),
+        'loudness-loud': math.sqrt(mean(2)),
+        'loudness-quiet': math.sqrt(mean(4))})
+    return result

@@ -43,6 +43,14 @@ def shard(count, rank, world):
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def owns(index, rank, world):
+    """Round-robin ownership of the items of a stream whose length is not known in advance
+    (validation loaders): item i belongs to rank i mod world"""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f'bad rank {rank} of {world}')
+    return index % world == rank
+
+
 def shard_tensors(tensors, rank, world):
     """Slice every (B, ...) tensor to this rank's utterances"""
     block = shard(tensors[0].shape[0], rank, world)

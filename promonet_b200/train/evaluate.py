@@ -13,6 +13,11 @@ Outside the accelerated path, as everywhere in this package: the PPG of the gene
 audio comes from the foreign pretrained `ppgs` model — pass `ppg_model` (audio (B, T) ->
 (B, 40, F) on the device) to get the 'ppg' metric — and figures / tensorboard
 (torchutil, matplotlib): the scalars are written as JSON and returned with the audio.
+
+Data parallel (the reference is single-GPU): validation items are independent, so under an
+initialised process group rank r takes items r, r + world, ... of the loader, every metric of
+every condition accumulates into one (7, 12) table of doubles on the device, and ONE all-reduce
+of that table (672 bytes) gives every rank the scalars of the whole validation set.
 """
 import json
 import math
@@ -20,7 +25,7 @@ from pathlib import Path
 
 import torch
 
-from promonet_b200 import config, edit, evaluate as evaluation, model, preprocess
+from promonet_b200 import _lib, config, edit, evaluate as evaluation, model, parallel, preprocess
 
 
 def conditions():
@@ -39,7 +44,8 @@ def inference_generator(generator, device):
     return model.Generator(device=device, state=generator.state_dict())
 
 
-def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None, ppg_model=None):
+def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None, ppg_model=None,
+             process_group=None, data_parallel=True):
     """Perform model evaluation (train/core.py:487-813)
 
     Arguments
@@ -50,16 +56,26 @@ def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None
         gpu: the GPU index (None = current CUDA device)
         evaluation_steps: stop after this many items (None = the whole loader)
         ppg_model: optional callable audio (B, T) -> ppg (B, 40, F)
+        process_group, data_parallel: under torch.distributed the items are dealt round-robin to
+            the ranks of `process_group` and the sums are all-reduced (data_parallel=False: every
+            rank evaluates everything on its own)
 
     Returns
         scalars: {f'{condition}/{metric}': value}
-        waveforms: {f'{condition}/{index:02d}-audio': (1, T) device tensor}
+        waveforms: {f'{condition}/{index:02d}-audio': (1, T) device tensor} of this rank's items
     """
     if not torch.cuda.is_available():
         raise RuntimeError('promonet_b200.train.evaluate needs a CUDA device; there is no CPU path')
     device = torch.device('cuda', torch.cuda.current_device() if gpu is None else gpu)
     generator = inference_generator(generator, device)
-    metrics = {condition: evaluation.Metrics(device) for condition in conditions()}
+    rank, world = 0, 1
+    if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank(process_group)
+        world = torch.distributed.get_world_size(process_group)
+    table = torch.zeros(len(conditions()), _lib.METRICS_SLOTS, dtype=torch.float64, device=device)
+    metrics = {
+        condition: evaluation.Metrics(device, sums=table[index])
+        for index, condition in enumerate(conditions())}
     ratios = config.EVALUATION_RATIOS
     waveforms = {}
     ones = lambda count: torch.ones(count, device=device)
@@ -74,6 +90,10 @@ def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None
     reference_ppg = lambda tensor: None if ppg_model is None else tensor
 
     for i, batch in enumerate(loader):
+        if evaluation_steps is not None and i == evaluation_steps:        # :802-803
+            break
+        if not parallel.owns(i, rank, world):
+            continue
         (_, loudness, pitch, periodicity, ppg, speakers, _, _, _, audio, _) = batch
         loudness, pitch, periodicity, ppg, speakers, audio = (
             item.to(device) for item in (loudness, pitch, periodicity, ppg, speakers, audio))
@@ -124,14 +144,13 @@ def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None
             metrics[key].update(
                 *stretched[:3], reference_ppg(stretched[3]), *analyze(generated))
 
-        if evaluation_steps is not None and i + 1 == evaluation_steps:    # :802-803
-            break
-
+    if world > 1:
+        parallel.all_reduce_sum(table, process_group)      # every sum of every condition at once
     scalars = {}
     for condition, metric in metrics.items():                            # :806-808
         for key, value in metric().items():
             scalars[f'{condition}/{key}'] = value
-    if directory is not None:
+    if directory is not None and rank == 0:
         directory = Path(directory)
         directory.mkdir(parents=True, exist_ok=True)
         with open(directory / f'evaluation-{step:08d}.json', 'w') as file:

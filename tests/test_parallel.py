@@ -118,3 +118,79 @@ def test_two_rank_gradient_average_equals_the_full_batch_gradient():
         assert worker.exitcode == 0
     for rank, worst in results:
         assert worst < 1e-4, (rank, worst)
+
+
+###############################################################################
+# Data-parallel validation: items dealt round-robin, one all-reduce of the sums
+###############################################################################
+
+
+def _oracle_sums(metrics):
+    """The 12 running sums of pmn_metrics_update (include/promonet_b200.h) out of the oracle"""
+    pairs = (
+        metrics.loudness.both, metrics.loudness.loud, metrics.loudness.quiet, metrics.periodicity,
+        metrics.pitch, metrics.ppg)
+    return torch.tensor(
+        [value for metric in pairs for value in (metric.total, metric.count)], dtype=torch.float64)
+
+
+def _validation_items(count):
+    from oracle import make_golden
+    return [
+        (make_golden.metric_inputs(50 + i, 20 + 7 * i, 8), make_golden.metric_inputs(70 + i, 20 + 7 * i, 8))
+        for i in range(count)]
+
+
+def _validation_worker(rank, world, port, count, queue):
+    from oracle import metrics as oracle_metrics
+    os.environ.update(
+        RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+        MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    parallel.initialize('gloo')
+    mine = oracle_metrics.Metrics()
+    for index, (predicted, target) in enumerate(_validation_items(count)):
+        if parallel.owns(index, rank, world):
+            mine.update(*predicted, *target)
+    table = _oracle_sums(mine)[None].repeat(7, 1)        # the (conditions, slots) table of evaluate
+    parallel.all_reduce_sum(table)
+    queue.put((rank, table))
+    parallel.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_round_robin_ownership():
+    for world in (1, 2, 3, 8):
+        owners = [[r for r in range(world) if parallel.owns(i, r, world)] for i in range(20)]
+        assert owners == [[i % world] for i in range(20)]
+    with pytest.raises(ValueError):
+        parallel.owns(0, 2, 2)
+
+
+def test_two_rank_validation_sums_equal_the_single_process_metrics():
+    """evaluate() under data parallelism: per-rank sums of the round-robin items, all-reduced,
+    give the scalars promonet.evaluate.Metrics gives over all items in one process"""
+    from oracle import metrics as oracle_metrics
+    from promonet_b200.evaluate import metrics as product_metrics
+    count = 5
+    context = mp.get_context('spawn')
+    queue = context.Queue()
+    port = _free_port()
+    workers = [
+        context.Process(target=_validation_worker, args=(rank, 2, port, count, queue))
+        for rank in range(2)]
+    for worker in workers:
+        worker.start()
+    results = dict(queue.get(timeout=120) for _ in workers)
+    for worker in workers:
+        worker.join(timeout=60)
+        assert worker.exitcode == 0
+    whole = oracle_metrics.Metrics()
+    for predicted, target in _validation_items(count):
+        whole.update(*predicted, *target)
+    expected = whole()
+    for rank in range(2):
+        assert torch.equal(results[rank], results[0])
+        scalars = product_metrics.finish(results[rank][3].tolist())
+        assert list(scalars) == ['pitch', 'periodicity', 'ppg', 'loudness', 'loudness-loud', 'loudness-quiet']
+        for name, value in expected.items():
+            assert scalars[name] == pytest.approx(value, rel=1e-12), name

@@ -83,3 +83,56 @@ def test_two_rank_step_matches_single_gpu_full_batch(peer_optimizer):
         # gradients (different summation order across ranks) may move a few by that much
         assert largest <= 2 * 2e-4 * 1.01
         assert fraction < 2e-2
+
+
+def _validation_loader(items, frames):
+    from oracle import inputs
+    loader = []
+    for index in range(items):
+        loudness, pitch, periodicity, ppg, speakers, _, _ = inputs.synthesis(1, frames + index, seed=60 + index)
+        loader.append((
+            None, loudness, pitch, periodicity * .5, ppg, speakers, None, None, None,
+            torch.zeros(1, 1, (frames + index) * 256), None))
+    return loader
+
+
+def _validation_worker(rank, world, port, queue):
+    os.environ.update(
+        RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+        MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import promonet_b200
+    from promonet_b200 import parallel
+    from promonet_b200.model import init
+    from promonet_b200.train import evaluate
+    torch.cuda.set_device(rank)
+    device = torch.device('cuda', rank)
+    parallel.initialize('nccl', device)
+    generator = promonet_b200.model.Generator(device=device, state=init.hifigan_state(1234))
+    loader = _validation_loader(3, 20)
+    scalars, waveforms = evaluate(None, 1, generator, loader, rank)
+    alone, _ = evaluate(None, 1, generator, loader, rank, data_parallel=False)
+    queue.put((rank, scalars, alone, sorted(waveforms)))
+    parallel.barrier()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_rank_validation_equals_single_gpu_validation():
+    """Items dealt round-robin to two ranks + one all-reduce of the sums = the scalars one GPU
+    computes over the whole loader"""
+    context = mp.get_context('spawn')
+    queue = context.Queue()
+    port = _free_port()
+    workers = [
+        context.Process(target=_validation_worker, args=(rank, 2, port, queue)) for rank in range(2)]
+    for worker in workers:
+        worker.start()
+    results = {rank: rest for rank, *rest in (queue.get(timeout=600) for _ in workers)}
+    for worker in workers:
+        worker.join(timeout=120)
+        assert worker.exitcode == 0
+    assert results[0][0] == results[1][0]                       # same scalars on both ranks
+    assert results[0][1] == results[1][1]
+    for name, value in results[0][1].items():
+        assert results[0][0][name] == pytest.approx(value, rel=1e-9, nan_ok=True), name
+    assert len(results[0][2]) == 2 * 7 and len(results[1][2]) == 7    # items 0, 2 and item 1
