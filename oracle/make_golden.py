@@ -256,6 +256,46 @@ def train_flags():
     print('wrote train_flags.npz', result['losses'], result['logit_sizes'])
 
 
+def train_resolution():
+    """MULTI_RESOLUTION_DISCRIMINATOR (config/defaults.py:177) on: the three DiscriminatorR of the
+    unmodified reference (model/discriminator.py:96-141) — logits, feature-map checksums, the
+    gradient norms of the discriminator loss and of the generator-side losses"""
+    promonet = ref_shim.load()
+    promonet.MULTI_RESOLUTION_DISCRIMINATOR = True
+    torch.manual_seed(promonet.RANDOM_SEED)
+    discriminators = promonet.model.Discriminator()
+    promonet.MULTI_RESOLUTION_DISCRIMINATOR = False
+    assert len(discriminators.discriminators) == 9
+    generator = torch.Generator().manual_seed(TRAIN_SEED)
+    audio = .3 * torch.randn(2, 1, 8192, generator=generator)
+    generated = (.3 * torch.randn(2, 1, 8192, generator=generator)).requires_grad_()
+    real_logits, fake_logits, real_maps, fake_maps = discriminators(audio, generated)
+    discriminator_loss, _, _ = promonet.loss.discriminator(
+        [logit.float() for logit in real_logits], [logit.float() for logit in fake_logits])
+    names = sorted(k for k, _ in discriminators.named_parameters() if k.split('.')[1] in '567')
+    parameters = dict(discriminators.named_parameters())
+    d_grads = torch.autograd.grad(
+        discriminator_loss, [parameters[k] for k in names], retain_graph=True)
+    generator_loss = promonet.loss.feature_matching(real_maps, fake_maps) + \
+        promonet.loss.generator(fake_logits)[0]
+    g_grad, = torch.autograd.grad(generator_loss, generated)
+    state = discriminators.state_dict()
+    result = {
+        'audio': audio.numpy(), 'generated': generated.detach().numpy(),
+        'losses': np.array([float(discriminator_loss), float(generator_loss)]),
+        'names': np.array(names),
+        'grad_norms': np.array([float(g.double().norm()) for g in d_grads]),
+        'generated_grad': g_grad.numpy(),
+        'checksums': np.array([float(state[k].double().abs().sum()) for k in sorted(state)])}
+    for index in (5, 6, 7):
+        result[f'logits_real_{index}'] = real_logits[index].detach().numpy()
+        result[f'logits_fake_{index}'] = fake_logits[index].detach().numpy()
+        result[f'fmap_checksums_{index}'] = np.array(
+            [float(m.double().abs().sum()) for m in fake_maps[index]])
+    np.savez_compressed(GOLDEN / 'train_resolution.npz', **result)
+    print('wrote train_resolution.npz', result['losses'], [real_logits[i].shape for i in (5, 6, 7)])
+
+
 def metric_inputs(seed, frames, rows):
     """Seeded (loudness, pitch, periodicity, ppg) straddling the loudness and voicing thresholds"""
     generator = torch.Generator().manual_seed(seed)
@@ -313,6 +353,8 @@ if __name__ == '__main__':
     import sys
     if '--metrics' in sys.argv:
         metrics()
+    elif '--train-resolution' in sys.argv:
+        train_resolution()
     elif '--train-flags' in sys.argv:
         train_flags()
     elif '--fargan' in sys.argv:

@@ -99,19 +99,74 @@ def discriminator_s(state, prefix, x):
     return torch.flatten(x, 1, -1), fmaps
 
 
-def discriminator(state, y, y_hat):
-    """Discriminator.forward discriminator.py:36-49 (config/promonet.py: MPD x 5 + CMB; with
-    MULTI_SCALE_DISCRIMINATOR the DiscriminatorS sits between them, :18-28)"""
-    logits_real, logits_fake, fmaps_real, fmaps_fake = [], [], [], []
+MULTI_RESOLUTIONS = ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240))   # discriminator.py:23
+
+
+def resolution_spectrogram(x, resolution):
+    """DiscriminatorR.spectrogram discriminator.py:127-141: reflect pad (n_fft - hop) / 2, STFT
+    without a window (rectangular over win_length, centred in n_fft by torch.stft), magnitude"""
+    n_fft, hop_length, win_length = resolution
+    pad = int((n_fft - hop_length) / 2)
+    x = F.pad(x, (pad, pad), mode='reflect')
+    x = torch.stft(
+        x.squeeze(1), n_fft=n_fft, hop_length=hop_length, win_length=win_length,
+        window=torch.ones(win_length, dtype=x.dtype), center=False, return_complex=True)
+    return torch.norm(torch.view_as_real(x), p=2, dim=-1).unsqueeze(1)
+
+
+def discriminator_r(state, prefix, x, resolution):
+    """DiscriminatorR.forward discriminator.py:112-125 (MULTI_RESOLUTION_DISCRIMINATOR): note the
+    LeakyReLU slope 0.2 here (:121), not LRELU_SLOPE"""
+    x = resolution_spectrogram(x, resolution)
+    fmaps = []
+    for i in range(5):
+        kernel_w = 9 if i < 4 else 3
+        stride = (1, 2) if 1 <= i <= 3 else (1, 1)
+        x = F.conv2d(
+            x, weight(state, f'{prefix}.convs.{i}'), state[f'{prefix}.convs.{i}.bias'], stride,
+            (1, kernel_w // 2))
+        x = F.leaky_relu(x, 0.2)
+        fmaps.append(x)
+    x = F.conv2d(
+        x, weight(state, f'{prefix}.conv_post'), state[f'{prefix}.conv_post.bias'], 1, (1, 1))
+    fmaps.append(x)
+    return torch.flatten(x, 1, -1), fmaps
+
+
+def kinds(state):
+    """The sub-discriminators of a state dict in order (discriminator.py:15-34): 'p' x 5, then 's'
+    if MULTI_SCALE_DISCRIMINATOR, 'r' x 3 if MULTI_RESOLUTION_DISCRIMINATOR, then 'cmb'"""
+    result = []
     count = len({k.split('.')[1] for k in state if k.startswith('discriminators.')})
-    multi_scale = count == len(PERIODS) + 2
     for i in range(count):
         prefix = f'discriminators.{i}'
+        if f'{prefix}.band_convs.0.0.0.weight_v' in state:
+            result.append('cmb')
+        elif state[f'{prefix}.convs.0.weight_v'].ndim == 3:
+            result.append('s')
+        elif state[f'{prefix}.convs.0.weight_v'].shape[-1] == 9:
+            result.append('r')
+        else:
+            result.append('p')
+    return result
+
+
+def discriminator(state, y, y_hat):
+    """Discriminator.forward discriminator.py:36-49 (config/promonet.py: MPD x 5 + CMB; with
+    MULTI_SCALE_DISCRIMINATOR the DiscriminatorS and with MULTI_RESOLUTION_DISCRIMINATOR the three
+    DiscriminatorR sit between them, :18-28)"""
+    logits_real, logits_fake, fmaps_real, fmaps_fake = [], [], [], []
+    periods, resolutions = iter(PERIODS), iter(MULTI_RESOLUTIONS)
+    for i, kind in enumerate(kinds(state)):
+        prefix = f'discriminators.{i}'
+        argument = next(periods) if kind == 'p' else next(resolutions) if kind == 'r' else None
         for x, logits, fmaps in ((y, logits_real, fmaps_real), (y_hat, logits_fake, fmaps_fake)):
-            if i < len(PERIODS):
-                logit, fmap = discriminator_p(state, prefix, x, PERIODS[i])
-            elif multi_scale and i == len(PERIODS):
+            if kind == 'p':
+                logit, fmap = discriminator_p(state, prefix, x, argument)
+            elif kind == 's':
                 logit, fmap = discriminator_s(state, prefix, x)
+            elif kind == 'r':
+                logit, fmap = discriminator_r(state, prefix, x, argument)
             else:
                 logit, fmap = discriminator_cmb(state, prefix, x)
             logits.append(logit)

@@ -177,12 +177,17 @@ MULTI_SCALE_CONVS = (
     (256, 1024, 41, 4, 64, 20), (1024, 1024, 41, 4, 256, 20), (1024, 1024, 5, 1, 1, 2))
 
 
-def discriminator_state(seed=None, multi_scale=False):
+# DiscriminatorR, model/discriminator.py:23: (n_fft, hop_length, win_length)
+MULTI_RESOLUTIONS = ((1024, 120, 600), (2048, 240, 1200), (512, 50, 240))
+
+
+def discriminator_state(seed=None, multi_scale=False, multi_resolution=False):
     """State dict of a freshly constructed promonet.model.Discriminator()
     (promonet/model/discriminator.py:15-34,61-72,148-173): same keys and the same
     torch RNG draw order (Conv2d.reset_parameters per layer, in construction order).
     multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180): DiscriminatorS is
-    inserted after the period discriminators (:20-21)"""
+    inserted after the period discriminators (:20-21); multi_resolution =
+    MULTI_RESOLUTION_DISCRIMINATOR (:177): three DiscriminatorR after that (:22-25, :99-110)"""
     if seed is not None:
         torch.manual_seed(seed)
     state = OrderedDict()
@@ -202,6 +207,18 @@ def discriminator_state(seed=None, multi_scale=False):
             _weight_norm_conv(state, f'{prefix}.convs.{layer}', torch.nn.Conv1d(
                 c_in, c_out, kernel, stride, groups=groups, padding=padding))
         _weight_norm_conv(state, f'{prefix}.conv_post', torch.nn.Conv1d(1024, 1, 3, 1, padding=1))
+        index += 1
+    for _ in MULTI_RESOLUTIONS if multi_resolution else ():
+        prefix = f'discriminators.{index}'
+        for layer in range(5):
+            kernel = (3, 9) if layer < 4 else (3, 3)
+            stride = (1, 2) if 1 <= layer <= 3 else (1, 1)
+            _weight_norm_conv(
+                state, f'{prefix}.convs.{layer}',
+                torch.nn.Conv2d(1 if layer == 0 else 32, 32, kernel, stride,
+                                padding=(1, kernel[1] // 2)))
+        _weight_norm_conv(
+            state, f'{prefix}.conv_post', torch.nn.Conv2d(32, 1, (3, 3), padding=(1, 1)))
         index += 1
     prefix = f'discriminators.{index}'
     for band, _ in enumerate(config.CMB_BANDS):

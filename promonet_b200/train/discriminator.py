@@ -251,6 +251,11 @@ class Discriminator:
             else torch.device(device)
         state = init.discriminator_state(multi_scale=multi_scale) if state is None else state
         count = len({k.split('.')[1] for k in state})
+        if count not in (len(config.DISCRIMINATOR_PERIODS) + 1, len(config.DISCRIMINATOR_PERIODS) + 2):
+            raise NotImplementedError(
+                f'{count} sub-discriminators: only 5 x DiscriminatorP (+ DiscriminatorS) + '
+                'DiscriminatorCMB are built; MULTI_RESOLUTION_DISCRIMINATOR / FARGAN_DISCRIMINATOR '
+                'states (DESIGN.md section 7) are not')
         multi_scale = count == len(config.DISCRIMINATOR_PERIODS) + 2
         self.params = ParamSet(state, self.device, peer_group=peer_group)
         self.layers = Layers(self.params, math)

@@ -113,3 +113,44 @@ def test_oracle_with_multi_scale_and_spectral_convergence_matches_reference():
         names = [str(n) for n in golden[f'{kind}_names']]
         norms = np.array([float(grads[n].double().norm()) for n in names])
         np.testing.assert_allclose(norms, golden[f'{kind}_grad_norms'], rtol=1e-3)
+
+
+def test_multi_resolution_oracle_matches_reference_golden():
+    """tests/golden/train_resolution.npz: MULTI_RESOLUTION_DISCRIMINATOR on (the
+    oracle and the seeded state only — the CUDA path does not build DiscriminatorR yet)"""
+    golden = np.load(GOLDEN / 'train_resolution.npz')
+    plain = init.discriminator_state(1234, multi_resolution=True)
+    assert oracle_train.kinds(plain) == ['p'] * 5 + ['r'] * 3 + ['cmb']
+    np.testing.assert_allclose(
+        [float(plain[k].double().abs().sum()) for k in sorted(plain)], golden['checksums'], rtol=1e-12)
+    state = oracle_train.leaf_state(plain)
+    audio = torch.from_numpy(golden['audio'])
+    generated = torch.from_numpy(golden['generated']).requires_grad_()
+    real_logits, fake_logits, real_maps, fake_maps = oracle_train.discriminator(state, audio, generated)
+    for index in (5, 6, 7):
+        assert relative_error(real_logits[index], torch.from_numpy(golden[f'logits_real_{index}'])) < 1e-5
+        assert relative_error(fake_logits[index], torch.from_numpy(golden[f'logits_fake_{index}'])) < 1e-5
+        np.testing.assert_allclose(
+            [float(m.detach().double().abs().sum()) for m in fake_maps[index]],
+            golden[f'fmap_checksums_{index}'], rtol=1e-5)
+    discriminator_loss = oracle_train.discriminator_loss(real_logits, fake_logits)
+    generator_loss = oracle_train.feature_matching_loss(real_maps, fake_maps) + \
+        oracle_train.generator_loss(fake_logits)
+    np.testing.assert_allclose(
+        [float(discriminator_loss), float(generator_loss)], golden['losses'], rtol=1e-5)
+    names = [str(n) for n in golden['names']]
+    grads = torch.autograd.grad(discriminator_loss, [state[n] for n in names], retain_graph=True)
+    np.testing.assert_allclose(
+        [float(g.double().norm()) for g in grads], golden['grad_norms'], rtol=1e-3)
+    gradient, = torch.autograd.grad(generator_loss, generated)
+    assert relative_error(gradient, torch.from_numpy(golden['generated_grad'])) < 1e-3
+
+
+def test_unbuilt_discriminator_configurations_are_refused():
+    """The CUDA Discriminator refuses a state dict with sub-discriminators it does not build
+    (NotImplementedError, before any device work; without CUDA the no-CPU-path RuntimeError
+    comes first)"""
+    from promonet_b200.train.discriminator import Discriminator
+    state = init.discriminator_state(1234, multi_resolution=True)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        Discriminator(state)
