@@ -517,6 +517,22 @@ int pmn_grid_sample(
     const float* sequence, const float* grid, float* out, int items, int channels, int t_in,
     int t_out, int nearest, int renormalize, void* stream);
 
+/* ---- Multi-resolution spectrogram discriminator front end ----
+ * DiscriminatorR.spectrogram, promonet/model/discriminator.py:127-141.  STATUS: compiled and bound,
+ * not yet run on a GPU; not on the default training path.
+ * pmn_dft_basis_rect: the weight of the STFT-as-1-x-1-convolution (see pmn_dft_basis) for
+ * torch.stft(window=None, win_length <= n_fft): (2 bins, n_fft), a rectangular window of win_length
+ * samples centred in the frame. */
+int pmn_dft_basis_rect(float* out, int n_fft, int win_length, void* stream);
+/* spec (items, 2 bins, frames), real rows then imaginary rows -> magnitude (items, bins, frames)
+ * = sqrt(re^2 + im^2) (no epsilon: torch.norm, :141); backward: gspec (items, 2 bins, frames) =
+ * gmagnitude (re, im) / |X|, zero where |X| = 0 */
+int pmn_complex_magnitude(
+    const float* spec, float* magnitude, int items, int bins, int frames, void* stream);
+int pmn_complex_magnitude_backward(
+    const float* gmagnitude, const float* spec, float* gspec, int items, int bins, int frames,
+    void* stream);
+
 /* ---- In-training validation ----
  * promonet.evaluate.Metrics.update (promonet/evaluate/metrics.py:38-61) in one pass over
  * `items` utterances of `frames` frames: adds into sums[PMN_METRICS_SLOTS] (device doubles)

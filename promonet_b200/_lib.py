@@ -179,6 +179,11 @@ SIGNATURES = {
         c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pmn_frame_overlap_add': (
         c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    # ---- multi-resolution discriminator front end ----
+    'pmn_dft_basis_rect': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'pmn_complex_magnitude': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_complex_magnitude_backward': (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     # ---- in-training validation ----
     'pmn_metrics_update': (
         c_int,

@@ -30,7 +30,8 @@ class Trainer:
 
     def __init__(self, generator_state=None, discriminator_state=None, device=None,
                  process_group=None, math='tf32', multi_scale_discriminator=False,
-                 spectral_convergence_loss=False, peer_optimizer=True, data_parallel=True):
+                 spectral_convergence_loss=False, peer_optimizer=True, data_parallel=True,
+                 multi_resolution_discriminator=False):
         """math: 'tf32' runs the convolutions' forward and data gradients on the tensor
         cores (tf32 operands, fp32 accumulation; the reference trains under fp16 autocast,
         train/core.py:220); 'fp32' is the exact FMA path used for parity"""
@@ -49,7 +50,8 @@ class Trainer:
         # MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180) and SPECTRAL_CONVERGENCE_LOSS (:358)
         # are off in config/promonet.py; BASELINE.json's wording of the training config names both
         self.discriminators = Discriminator(
-            discriminator_state, self.generator.device, math, multi_scale_discriminator, peer_group)
+            discriminator_state, self.generator.device, math, multi_scale_discriminator, peer_group,
+            multi_resolution_discriminator)
         self.spectral_convergence = None
         if spectral_convergence_loss:
             from promonet_b200.train.losses import MultiResolutionSpectralConvergence

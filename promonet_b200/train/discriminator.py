@@ -1,5 +1,6 @@
 """Trainable discriminators: 5 x multi-period + complex multi-band
-(promonet/model/discriminator.py:13-93,146-208 under config/promonet.py).
+(promonet/model/discriminator.py:13-93,146-208 under config/promonet.py), optionally the
+multi-scale (:211-239) and the three multi-resolution (:96-141) ones.
 
 `forward(x)` runs every sub-discriminator on a batch whose first half is real
 audio and second half generated audio (the reference calls each sub-discriminator
@@ -133,6 +134,111 @@ class Scale:
                 ops.axpby(1., target.view(n, 1, -1), 1., gaudio)
 
 
+class Resolution:
+    """DiscriminatorR discriminator.py:96-141 (MULTI_RESOLUTION_DISCRIMINATOR, off by default).
+    The STFT (window=None, win_length < n_fft, hop not a divisor of n_fft) is a 1 x 1
+    convolution over the reflect-padded signal read in place as overlapping frames, with the
+    DFT basis as its weight: the same construction as the spectral-convergence loss
+    (train/losses.py), so its forward and backward are the conv kernels.
+
+    STATUS: composed from kernels that are individually tested, but this class itself has not
+    run on a GPU yet; its tests are gated behind PROMONET_B200_UNVERIFIED."""
+
+    SLOPE = 0.2     # discriminator.py:121 (not LRELU_SLOPE)
+
+    def __init__(self, layers, prefix, resolution, math):
+        self.n_fft, self.hop, self.win = resolution
+        self.math = math
+        self.convs = [layers.conv(f'{prefix}.convs.{i}') for i in range(5)]
+        self.post = layers.conv(f'{prefix}.conv_post')
+        self.basis = None
+
+    def _basis(self, device):
+        """(rows, forward operand, backward operand) of the DFT convolution, built once"""
+        if self.basis is None:
+            basis = ops.dft_basis_rect(self.n_fft, self.win, device)     # (2 bins, n_fft)
+            rows = basis.shape[0]
+            if self.math == 'tf32':
+                forward = ops.pack_weight_taps(
+                    basis, torch.empty(ops.packed_floats(rows, self.n_fft, 1), device=device),
+                    rows, self.n_fft, 1, False)
+                backward = ops.pack_weight_taps(
+                    basis, torch.empty(ops.packed_floats(self.n_fft, rows, 1), device=device),
+                    rows, self.n_fft, 1, True)
+            else:
+                forward = basis
+                backward = ops.transpose_weight(basis, torch.empty_like(basis), rows, self.n_fft, 1)
+            self.basis = (rows, forward, backward)
+        return self.basis
+
+    def _dft(self, geometry, a, weight, out):
+        if self.math == 'tf32':
+            return ops.conv_gemm_tc(geometry, False, a, weight, out)
+        return ops.conv_gemm(geometry, False, a, weight, out)
+
+    def forward(self, x):
+        """x (N, 1, T) -> record with maps[0] = |STFT| (N, 1, bins, frames), maps[1..6] = feature maps"""
+        n, _, t = x.shape
+        pad = (self.n_fft - self.hop) // 2                               # :129-132
+        padded = ops.reflect_pad(x.view(n, t), pad, pad)
+        length = t + 2 * pad
+        frames = 1 + (length - self.n_fft) // self.hop                   # center=False
+        rows, forward, _ = self._basis(x.device)
+        geometry = ops.geometry(
+            n, self.n_fft, rows, (frames, 1), (1, 1), strides=(1, self.hop, length))
+        spec = self._dft(geometry, padded, forward, torch.empty(n, rows, frames, device=x.device))
+        maps = [ops.complex_magnitude(spec)]
+        geometries = []
+        for i, conv in enumerate(self.convs + [self.post]):
+            kernel = (3, 9) if i < 4 else (3, 3)
+            stride = (1, 2) if 1 <= i <= 3 else (1, 1)
+            source = maps[-1]
+            geometry = ops.geometry(
+                n, conv.dim1, conv.dim0, source.shape[2:], kernel, stride, 1, (1, kernel[1] // 2))
+            out = torch.empty(n, conv.dim0, geometry.h_out, geometry.w_out, device=x.device)
+            conv.apply(geometry, False, source, out, bias=conv.bias,
+                       out_act=ops.OUT_LRELU if i < 5 else ops.OUT_NONE, out_slope=self.SLOPE)
+            maps.append(out)
+            geometries.append(geometry)
+        return {
+            'maps': maps, 'geometries': geometries, 'spec': spec, 'pad': pad, 'samples': t,
+            'frames': frames, 'length': length}
+
+    def backward(self, record, gmaps, lo, hi, weights, gaudio):
+        """As Period.backward; the gradient of maps[0] goes back through the magnitude, the DFT
+        convolution, the overlap-add of the frames and the reflect padding"""
+        layers = self.convs + [self.post]
+        n = hi - lo
+        for i in reversed(range(6)):
+            geometry = _with_batch(record['geometries'][i], n)
+            y, x = record['maps'][i + 1][lo:hi], record['maps'][i][lo:hi]
+            act = (ops.ACT_LRELU_MASK, self.SLOPE) if i < 5 else (ops.ACT_NONE, 1.)
+            g = gmaps[i]
+            if weights:
+                layers[i].wgrad(geometry, g, x, dy_companion=y, dy_act=act[0], dy_slope=act[1])
+            if i == 0 and gaudio is None:
+                break
+            target = gmaps[i - 1] if i > 0 else None
+            accumulate = target is not None
+            if target is None:
+                target = torch.empty_like(x)
+            layers[i].apply_transposed(
+                geometry, True, g, target, a_companion=y, a_act=act[0], a_slope=act[1],
+                accumulate=accumulate)
+            if i > 0:
+                gmaps[i - 1] = target
+                continue
+            frames, length, pad = record['frames'], record['length'], record['pad']
+            rows, _, backward = self._basis(target.device)
+            gspec = ops.complex_magnitude_backward(target, record['spec'][lo:hi])
+            geometry = ops.geometry(n, rows, self.n_fft, (frames, 1), (1, 1))
+            gframes = self._dft(
+                geometry, gspec, backward, torch.empty(n, self.n_fft, frames, device=target.device))
+            gpadded = torch.zeros(n, length, device=target.device)
+            ops.frame_overlap_add(gframes, gpadded, self.hop)
+            ops.reflect_pad_backward(gpadded, gaudio.view(n, -1), pad, pad, accumulate=True)
+
+
 class ComplexMultiBand:
     """DiscriminatorCMB discriminator.py:146-208"""
 
@@ -240,23 +346,52 @@ def _with_batch(geometry, batch):
     return copy
 
 
+def sub_discriminators(state):
+    """The sub-discriminators a state dict holds, in order (discriminator.py:15-34): 'p' x 5, 's' if
+    MULTI_SCALE_DISCRIMINATOR, 'r' x 3 if MULTI_RESOLUTION_DISCRIMINATOR, 'cmb'.  Anything else
+    (FARGAN_DISCRIMINATOR, a subset) is not built and raises."""
+    kinds = []
+    for index in range(len({k.split('.')[1] for k in state})):
+        prefix = f'discriminators.{index}'
+        first = state.get(f'{prefix}.convs.0.weight_v')
+        if f'{prefix}.band_convs.0.0.0.weight_v' in state:
+            kinds.append('cmb')
+        elif first is None:
+            kinds.append('?')
+        elif first.ndim == 3:
+            kinds.append('s')
+        elif tuple(first.shape[1:]) == (1, 3, 9):
+            kinds.append('r')
+        elif tuple(first.shape[1:]) == (1, 5, 1):
+            kinds.append('p')
+        else:
+            kinds.append('?')
+    periods = len(config.DISCRIMINATOR_PERIODS)
+    allowed = [
+        ['p'] * periods + scale + resolution + ['cmb']
+        for scale in ([], ['s']) for resolution in ([], ['r'] * len(init.MULTI_RESOLUTIONS))]
+    if kinds not in allowed:
+        raise NotImplementedError(
+            f'sub-discriminators {kinds}: only 5 x DiscriminatorP (+ DiscriminatorS) '
+            '(+ 3 x DiscriminatorR) + DiscriminatorCMB are built (DESIGN.md section 7)')
+    return kinds
+
+
 class Discriminator:
 
-    def __init__(self, state=None, device=None, math='tf32', multi_scale=False, peer_group=None):
-        """multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180; inferred from the
-        keys when a state dict is given)"""
+    def __init__(self, state=None, device=None, math='tf32', multi_scale=False, peer_group=None,
+                 multi_resolution=False):
+        """multi_scale = MULTI_SCALE_DISCRIMINATOR (config/defaults.py:180), multi_resolution =
+        MULTI_RESOLUTION_DISCRIMINATOR (:177); both are inferred from the keys when a state dict
+        is given"""
         if not torch.cuda.is_available():
             raise RuntimeError('promonet_b200.train needs a CUDA device (sm_100a); there is no CPU path')
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
-        state = init.discriminator_state(multi_scale=multi_scale) if state is None else state
-        count = len({k.split('.')[1] for k in state})
-        if count not in (len(config.DISCRIMINATOR_PERIODS) + 1, len(config.DISCRIMINATOR_PERIODS) + 2):
-            raise NotImplementedError(
-                f'{count} sub-discriminators: only 5 x DiscriminatorP (+ DiscriminatorS) + '
-                'DiscriminatorCMB are built; MULTI_RESOLUTION_DISCRIMINATOR / FARGAN_DISCRIMINATOR '
-                'states (DESIGN.md section 7) are not')
-        multi_scale = count == len(config.DISCRIMINATOR_PERIODS) + 2
+        if state is None:
+            state = init.discriminator_state(multi_scale=multi_scale, multi_resolution=multi_resolution)
+        kinds = sub_discriminators(state)
+        multi_scale = 's' in kinds
         self.params = ParamSet(state, self.device, peer_group=peer_group)
         self.layers = Layers(self.params, math)
         self.modules = [
@@ -264,6 +399,9 @@ class Discriminator:
             for i, period in enumerate(config.DISCRIMINATOR_PERIODS)]
         if multi_scale:
             self.modules.append(Scale(self.layers, f'discriminators.{len(self.modules)}'))
+        for resolution in init.MULTI_RESOLUTIONS if 'r' in kinds else ():
+            self.modules.append(Resolution(
+                self.layers, f'discriminators.{len(self.modules)}', resolution, math))
         self.cmb = ComplexMultiBand(self.layers, f'discriminators.{len(self.modules)}')
         self.layers.allocate()
 

@@ -314,3 +314,30 @@ def frame_overlap_add(gframes, gsignal, hop):
         _lib.ptr(gframes), _lib.ptr(gsignal), batch, n_fft, frames, hop, gsignal.shape[-1],
         _lib.stream()))
     return gsignal
+
+
+def dft_basis_rect(n_fft, win_length, device):
+    """(2 bins, n_fft) DFT weight with a centred rectangular window of win_length samples
+    (torch.stft(window=None, win_length=...), model/discriminator.py:134-140)"""
+    out = torch.empty(2 * (n_fft // 2 + 1), n_fft, device=device)
+    _check(_lib.library().pmn_dft_basis_rect(_lib.ptr(out), n_fft, win_length, _lib.stream()))
+    return out
+
+
+def complex_magnitude(spec):
+    """spec (N, 2 bins, frames) -> |X| as (N, 1, bins, frames) (discriminator.py:141)"""
+    items, rows, frames = spec.shape
+    out = torch.empty(items, 1, rows // 2, frames, device=spec.device)
+    _check(_lib.library().pmn_complex_magnitude(
+        _lib.ptr(spec), _lib.ptr(out), items, rows // 2, frames, _lib.stream()))
+    return out
+
+
+def complex_magnitude_backward(gmagnitude, spec):
+    """-> gradient of spec (N, 2 bins, frames)"""
+    items, rows, frames = spec.shape
+    gspec = torch.empty_like(spec)
+    _check(_lib.library().pmn_complex_magnitude_backward(
+        _lib.ptr(gmagnitude), _lib.ptr(spec), _lib.ptr(gspec), items, rows // 2, frames,
+        _lib.stream()))
+    return gspec

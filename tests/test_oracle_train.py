@@ -147,10 +147,17 @@ def test_multi_resolution_oracle_matches_reference_golden():
 
 
 def test_unbuilt_discriminator_configurations_are_refused():
-    """The CUDA Discriminator refuses a state dict with sub-discriminators it does not build
-    (NotImplementedError, before any device work; without CUDA the no-CPU-path RuntimeError
-    comes first)"""
-    from promonet_b200.train.discriminator import Discriminator
-    state = init.discriminator_state(1234, multi_resolution=True)
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        Discriminator(state)
+    """The CUDA Discriminator refuses a state dict whose sub-discriminators it does not build
+    (NotImplementedError from the key inspection, before any device work)"""
+    from promonet_b200.train.discriminator import sub_discriminators
+    assert sub_discriminators(init.discriminator_state(1234)) == ['p'] * 5 + ['cmb']
+    assert sub_discriminators(init.discriminator_state(1234, multi_scale=True)) == \
+        ['p'] * 5 + ['s', 'cmb']
+    state = init.discriminator_state(1234, multi_scale=True, multi_resolution=True)
+    assert sub_discriminators(state) == ['p'] * 5 + ['s'] + ['r'] * 3 + ['cmb']
+    without_cmb = {k: v for k, v in state.items() if not k.startswith('discriminators.9.')}
+    with pytest.raises(NotImplementedError):
+        sub_discriminators(without_cmb)
+    reordered = {k.replace('discriminators.0.', 'discriminators.10.'): v for k, v in state.items()}
+    with pytest.raises((NotImplementedError, KeyError)):
+        sub_discriminators(reordered)

@@ -83,3 +83,44 @@ def test_packed_weight_sizes():
     assert ops.packed_floats(1, 32, 7) == 32 * 7 * 32
     assert ops.packed_floats(100, 40, 3) == 128 * 3 * 64
     assert ops.channel_pad(113) == 128
+
+
+@pytest.mark.parametrize('flags,modules,convs', [
+    ({}, 5, 5 * 6 + 26), ({'multi_scale': True}, 6, 5 * 6 + 7 + 26),
+    ({'multi_resolution': True}, 8, 5 * 6 + 3 * 6 + 26),
+    ({'multi_scale': True, 'multi_resolution': True}, 9, 5 * 6 + 7 + 3 * 6 + 26)])
+def test_discriminator_module_graph_builds_for_every_flag(monkeypatch, flags, modules, convs):
+    """Construction only (flat storage, layer views, weight table: no kernel is launched), on the
+    CPU with the CUDA check bypassed: the default graph and the flagged ones stay wired"""
+    from promonet_b200.train import discriminator
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    state = init.discriminator_state(3, **flags)
+    for math in ('fp32', 'tf32'):
+        module = discriminator.Discriminator(state, 'cpu', math)
+        assert len(module.modules) == modules and len(module.layers.layers) == convs
+        assert module.cmb.post.prefix == f'discriminators.{modules}.conv_post'
+        kinds = [type(m).__name__ for m in module.modules]
+        assert kinds == ['Period'] * 5 + ['Scale'] * ('multi_scale' in flags) + \
+            ['Resolution'] * (3 * ('multi_resolution' in flags))
+        for layer in module.layers.layers:
+            assert layer.w is not None and layer.gw is not None
+            assert (layer.packed is not None) == (math == 'tf32')
+        restored = module.state_dict()
+        assert all(torch.equal(restored[k], state[k]) for k in state)
+    resolutions = [m for m in module.modules if isinstance(m, discriminator.Resolution)]
+    assert [(m.n_fft, m.hop, m.win) for m in resolutions] == (
+        [(1024, 120, 600), (2048, 240, 1200), (512, 50, 240)] if resolutions else [])
+
+
+def test_trainer_wiring_for_every_discriminator_flag(monkeypatch):
+    """Trainer construction on the CPU (CUDA check bypassed, no kernel launched): the flags reach
+    the discriminator, the default stays 5 x period + complex multi-band"""
+    from promonet_b200.train import Trainer
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    names = lambda trainer: [type(m).__name__ for m in trainer.discriminators.modules]
+    assert names(Trainer(device='cpu')) == ['Period'] * 5
+    flagged = Trainer(
+        device='cpu', math='fp32', multi_scale_discriminator=True,
+        multi_resolution_discriminator=True, spectral_convergence_loss=False)
+    assert names(flagged) == ['Period'] * 5 + ['Scale'] + ['Resolution'] * 3
+    assert flagged.world == 1 and flagged.generator.params.peers is None
