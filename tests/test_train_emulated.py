@@ -16,7 +16,7 @@ from promonet_b200 import config
 from promonet_b200.model import init
 
 
-def run(monkeypatch, state, samples=2048, count=2, seed=0):
+def run(monkeypatch, state, samples=2048, count=1, seed=0):
     """One discriminator step and one generator-side backward, emulated and by autograd"""
     from promonet_b200.train import ops
     from promonet_b200.train.discriminator import Discriminator
