@@ -103,17 +103,33 @@ def prepare_weights(table, layers, max_dim0):
     _, entries = _tables[table.data_ptr()]
     assert len(entries) == layers
     for entry in entries:
-        if entry.get('groups', 1) != 1:
-            raise NotImplementedError('the test double does not emulate grouped layers')
-        dim0, dim1, taps = entry['dim0'], entry['dim1'], entry['taps']
+        dim0, dim1, taps, groups = entry['dim0'], entry['dim1'], entry['taps'], entry.get('groups', 1)
         assert dim0 <= max_dim0
         weight = entry['v'].reshape(dim0, -1)
         if entry['g'] is not None:
             weight = entry['g'].reshape(dim0, 1) * weight / weight.norm(dim=1, keepdim=True)
             entry['w'].view(-1).copy_(weight.reshape(-1))
+        if groups > 1:
+            # block-diagonal dense form of a grouped weight (dim0, dim1 / groups, taps)
+            rows, cols = dim0 // groups, dim1 // groups
+            dense = torch.zeros(dim0, dim1, taps)
+            for group in range(groups):
+                dense[group * rows:(group + 1) * rows, group * cols:(group + 1) * cols] = \
+                    weight.reshape(dim0, cols, taps)[group * rows:(group + 1) * rows]
+            weight = dense
+            entry['dense'].view(-1).copy_(dense.reshape(-1))
         if entry.get('wt') is not None:
             transpose_weight(weight, entry['wt'], dim0, dim1, taps)
         assert entry.get('packed') is None and entry.get('packed_t') is None    # fp32 path only
+
+
+def extract_grouped(dense, gw, dim0, dim1, taps, groups):
+    rows, cols = dim0 // groups, dim1 // groups
+    dense = dense.reshape(dim0, dim1, taps)
+    blocks = [
+        dense[group * rows:(group + 1) * rows, group * cols:(group + 1) * cols]
+        for group in range(groups)]
+    return _store(gw, torch.cat(blocks), False)
 
 
 def transpose_weight(w, wt, dim0, dim1, taps):
@@ -220,6 +236,30 @@ def dft_basis_rect(n_fft, win_length, device):
     return torch.cat([window * torch.cos(phase), -window * torch.sin(phase)]).float()
 
 
+def dft_basis(n_fft, device):
+    """pmn_dft_basis: periodic hann window over the whole frame"""
+    bins = n_fft // 2 + 1
+    window = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+    k = torch.arange(bins, dtype=torch.float64)[:, None]
+    phase = 2 * torch.pi * ((k * torch.arange(n_fft, dtype=torch.float64)[None]) % n_fft) / n_fft
+    return torch.cat([window * torch.cos(phase), -window * torch.sin(phase)]).float()
+
+
+def spectral_convergence(spec, batch, weight, sums, loss, gspec=None):
+    """pmn_spectral_convergence (promonet/train/loss.py:61-122)"""
+    bins = spec.shape[1] // 2
+    root = lambda z: torch.sqrt(torch.clamp(torch.sqrt(z[:, :bins] ** 2 + z[:, bins:] ** 2), min=1e-7))
+    leaf = spec[batch:].detach().clone().requires_grad_()
+    target = root(spec[:batch])
+    difference, reference = (target - root(leaf)).abs().sum(), target.sum()
+    sums.copy_(torch.stack([difference.detach(), reference]))
+    if loss is not None:
+        loss.add_(weight * (difference / reference).detach())
+    if gspec is not None:
+        (weight * difference / reference).backward()
+        _store(gspec, leaf.grad, False)
+
+
 def complex_magnitude(spec):
     items, rows, frames = spec.shape
     bins = rows // 2
@@ -241,7 +281,65 @@ def frame_overlap_add(gframes, gsignal, hop):
     return gsignal
 
 
+def conv_transpose1d(x, weight, bias, stride, in_slope):
+    k = weight.shape[-1]
+    return F.conv_transpose1d(
+        F.leaky_relu(x, in_slope), weight, bias, stride=stride, padding=(k - stride) // 2)
+
+
+def features(loudness, pitch, periodicity, ppg, pitch_distribution, pitch_embedding, threshold):
+    from oracle import features as oracle_features
+    state = {
+        'ppg_threshold': torch.tensor(threshold), 'pitch_distribution': pitch_distribution,
+        'pitch_embedding.weight': pitch_embedding}
+    return oracle_features.prepare_features(state, loudness, pitch, periodicity, ppg).contiguous()
+
+
+def pitch_bins(pitch, edges, fmin, fmax):
+    return torch.clip(torch.searchsorted(edges, torch.clip(pitch, fmin, fmax)), 0, edges.numel() - 1)
+
+
+def global_features(speaker_embedding, speakers, sbr, lr):
+    return torch.cat([speaker_embedding[speakers], sbr[:, None], lr[:, None]], dim=1)
+
+
+def embedding_backward(gout, index, gtable, channel_offset=0):
+    channels = gtable.shape[1]
+    rows = gout[:, channel_offset:channel_offset + channels].permute(0, 2, 1).reshape(-1, channels)
+    gtable.index_put_((index.reshape(-1),), rows, accumulate=True)
+
+
+def row_sum(x, out, rows, cols, accumulate=False):
+    return _store(out, x.reshape(rows, cols).sum(dim=1), accumulate)
+
+
+def channel_sum(x, out, accumulate=False):
+    batch, channels = x.shape[:2]
+    return _store(out, x.reshape(batch, channels, -1).sum(dim=(0, 2)), accumulate)
+
+
+def _mel_basis():
+    from oracle import dsp
+    return torch.from_numpy(dsp.mel_basis()).float()
+
+
+def linear_to_mel(magnitude, floor=float('-inf')):
+    return torch.log(_mel_basis() @ magnitude).clamp_min(floor)
+
+
+def mel_loss(magnitude, target_mels, weight, loss, gmagnitude=None, grad_weight=None):
+    leaf = magnitude.detach().clone().requires_grad_()
+    value = (torch.log(_mel_basis() @ leaf) - target_mels).abs().mean()
+    if loss is not None:
+        loss.add_(weight * value.detach())
+    if gmagnitude is not None:
+        value.backward()
+        _store(gmagnitude, (weight if grad_weight is None else grad_weight) * leaf.grad, False)
+
+
 EMULATED = (
+    conv_transpose1d, features, pitch_bins, global_features, embedding_backward, row_sum,
+    channel_sum, linear_to_mel, mel_loss, extract_grouped, dft_basis, spectral_convergence,
     conv_gemm, conv_wgrad, weight_table, prepare_weights, transpose_weight, weight_norm_backward,
     reflect_pad, reflect_pad_backward, axpby, mse_to_target, l1_mean, stft_magnitude,
     stft_magnitude_backward, copy_columns, dft_basis_rect, complex_magnitude,

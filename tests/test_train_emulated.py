@@ -1,11 +1,13 @@
-"""Host logic of the trainable discriminators on the CPU: promonet_b200/train/discriminator.py
+"""Host logic of the training step on the CPU: promonet_b200/train/{core,generator,discriminator}.py
 run over tests/emulated_ops.py (a plain-torch double of the kernel launches, see its header)
 against oracle/train.py's autograd.
 
 1. The double is held to the oracle through the modules that ARE verified on the GPU (5 x
    multi-period + complex multi-band): if this passes, the double has the operators' semantics.
 2. The same double then checks the sequencing that has NOT run on a GPU yet (DiscriminatorR:
-   forward, weight gradients, gradient with respect to the audio)."""
+   forward, weight gradients, gradient with respect to the audio).
+3. One whole Trainer.step (generator forward, discriminator step, generator step: every loss and
+   every parameter gradient of both modules) as a CPU regression test of the step's sequencing."""
 import pytest
 import torch
 
@@ -89,3 +91,39 @@ def test_multi_resolution_sequencing_matches_autograd(monkeypatch):
     views and flags are checked here over the double"""
     D = run(monkeypatch, init.discriminator_state(1234, multi_resolution=True), seed=1)
     assert [type(m).__name__ for m in D.modules[5:]] == ['Resolution'] * 3
+
+
+@pytest.mark.parametrize('flags', [
+    {}, {'multi_scale': True, 'multi_resolution': True, 'spectral_convergence': True}],
+    ids=['config/promonet.py', 'every flag'])
+def test_whole_training_step_sequencing_matches_autograd(monkeypatch, flags):
+    """Trainer.step(update=False) over the double against oracle/train.py's step in fp64: the same
+    comparison tests/test_train_gpu.py makes on the GPU, here for the host logic alone; once for
+    the default configuration, once with MULTI_SCALE_DISCRIMINATOR, MULTI_RESOLUTION_DISCRIMINATOR
+    and SPECTRAL_CONVERGENCE_LOSS on"""
+    from promonet_b200.train import Trainer
+    emulated_ops.install(monkeypatch)
+    spectral = flags.get('spectral_convergence', False)
+    states = init.hifigan_state(1234), init.discriminator_state(
+        1234, flags.get('multi_scale', False), flags.get('multi_resolution', False))
+    batch = oracle_train.batch(2 if not flags else 1, 8, seed=21)
+    g_state = oracle_train.leaf_state(states[0], torch.float64)
+    d_state = oracle_train.leaf_state(states[1], torch.float64)
+    losses, g_grads, d_grads, generated = oracle_train.step(
+        g_state, d_state, [t.double() if t.is_floating_point() else t for t in batch],
+        spectral_convergence=spectral)
+    trainer = Trainer(*states, device='cpu', math='fp32', spectral_convergence_loss=spectral)
+    assert len(trainer.discriminators.modules) == 5 + (4 if flags else 0)
+    ours = trainer.step(*[t.contiguous() for t in batch], update=False)
+    assert relative_error(trainer.generated, generated) < 1e-4
+    names = ('discriminator', 'mel', 'feature_matching', 'adversarial', 'generator') + (
+        ('spectral_convergence',) if spectral else ())
+    for i, name in enumerate(names):
+        assert float(ours[i]) == pytest.approx(float(losses[name]), rel=1e-4), name
+    for module, expected in ((trainer.discriminators, d_grads), (trainer.generator, g_grads)):
+        gradients = module.params.gradients()
+        assert sorted(gradients) == sorted(expected)
+        errors = sorted((relative_error(gradients[n], g), n) for n, g in expected.items())
+        # sign / mask decisions at near-zero values may move a few tensors (see test_train_gpu.py)
+        assert errors[len(errors) // 2][0] < 4e-4 and errors[-1][0] < 5e-2, errors[-4:]
+        assert sum(e >= 2e-3 for e, _ in errors) <= 4, errors[-6:]
