@@ -518,8 +518,8 @@ int pmn_grid_sample(
     int t_out, int nearest, int renormalize, void* stream);
 
 /* ---- Multi-resolution spectrogram discriminator front end ----
- * DiscriminatorR.spectrogram, promonet/model/discriminator.py:127-141.  STATUS: compiled and bound,
- * not yet run on a GPU; not on the default training path.
+ * DiscriminatorR.spectrogram, promonet/model/discriminator.py:127-141 (MULTI_RESOLUTION_DISCRIMINATOR,
+ * off in config/promonet.py).
  * pmn_dft_basis_rect: the weight of the STFT-as-1-x-1-convolution (see pmn_dft_basis) for
  * torch.stft(window=None, win_length <= n_fft): (2 bins, n_fft), a rectangular window of win_length
  * samples centred in the frame. */

@@ -7,10 +7,8 @@
 // exactly like the spectral-convergence loss, train_spectral.cu); this file supplies the weight of
 // that convolution for torch.stft(window=None, win_length < n_fft) — a rectangular window of
 // win_length samples centred in the frame — and the magnitude between the STFT and the first
-// convolution, forward and backward.  HBM-bound, one pass each.
-//
-// STATUS: compiled and bound, not yet run on a GPU; nothing on the default
-// training path launches these kernels.
+// convolution, forward and backward.  HBM-bound, one pass each.  Nothing on the default training
+// path launches these kernels (the flag is off in config/promonet.py).
 #include "common.cuh"
 
 namespace pmn {

@@ -139,10 +139,7 @@ class Resolution:
     The STFT (window=None, win_length < n_fft, hop not a divisor of n_fft) is a 1 x 1
     convolution over the reflect-padded signal read in place as overlapping frames, with the
     DFT basis as its weight: the same construction as the spectral-convergence loss
-    (train/losses.py), so its forward and backward are the conv kernels.
-
-    STATUS: composed from kernels that are individually tested, but this class itself has not
-    run on a GPU yet; its tests are gated behind PROMONET_B200_UNVERIFIED."""
+    (train/losses.py), so its forward and backward are the conv kernels."""
 
     SLOPE = 0.2     # discriminator.py:121 (not LRELU_SLOPE)
 

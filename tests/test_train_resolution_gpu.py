@@ -1,12 +1,7 @@
 """MULTI_RESOLUTION_DISCRIMINATOR (promonet/model/discriminator.py:96-141) on the GPU against the
-oracle and tests/golden/train_resolution.npz (the reference module's own outputs and gradients).
-
-GATED: promonet_b200.train.discriminator.Resolution and csrc/train_resolution.cu were written after
-this round's GPU budget was spent and have not run on a GPU yet.  Until they
-have, these tests only run with PROMONET_B200_UNVERIFIED=1, so that the default `-m gpu` run holds
-verified code only; the flag is not part of any default path."""
-import os
-
+oracle and tests/golden/train_resolution.npz (the reference module's own outputs and gradients):
+the DFT basis and magnitude kernels, the three DiscriminatorR forward (fp32 and tf32), their weight
+gradients and the gradient with respect to the audio, and a whole training step with the flag on."""
 import numpy as np
 import pytest
 import torch
@@ -14,11 +9,7 @@ import torch
 from conftest import GOLDEN, relative_error
 from oracle import train as oracle_train
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(
-        os.environ.get('PROMONET_B200_UNVERIFIED') != '1',
-        reason='multi-resolution discriminator: not yet run on a GPU (set PROMONET_B200_UNVERIFIED=1)')]
+pytestmark = pytest.mark.gpu
 
 FORWARD_TOLERANCE = 1e-4
 GRADIENT_TOLERANCE = 2e-3
