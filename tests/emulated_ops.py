@@ -5,9 +5,9 @@ of libpromonet_b200 by plain-torch functions with the semantics include/promonet
 documents for them (math='fp32' path, ungrouped layers).  It exists to run the HOST logic of the
 trainable modules — which launches they make, on which views, with which flags, in which order —
 without a GPU: tests/test_train_emulated.py first holds the double to the oracle through the
-discriminators that are verified on the GPU (multi-period, complex multi-band), then uses it on
-the sequencing that is not (DiscriminatorR).  It says nothing about the CUDA kernels themselves
-and nothing under promonet_b200/ may import it."""
+multi-period and complex multi-band discriminators, then uses it on the other modules and on
+the whole Trainer.step (new sequencing can be developed against it before GPU time is spent).
+It says nothing about the CUDA kernels themselves and nothing under promonet_b200/ may import it."""
 import torch
 import torch.nn.functional as F
 

@@ -4,8 +4,9 @@ against oracle/train.py's autograd.
 
 1. The double is held to the oracle through the modules that ARE verified on the GPU (5 x
    multi-period + complex multi-band): if this passes, the double has the operators' semantics.
-2. The same double then checks the sequencing that has NOT run on a GPU yet (DiscriminatorR:
-   forward, weight gradients, gradient with respect to the audio).
+2. The same double then checks the sequencing of DiscriminatorR (forward, weight gradients,
+   gradient with respect to the audio): written when no GPU time was left, checked here first,
+   and green on the B200 at its first run afterwards.
 3. One whole Trainer.step (generator forward, discriminator step, generator step: every loss and
    every parameter gradient of both modules) as a CPU regression test of the step's sequencing."""
 import pytest
@@ -87,8 +88,8 @@ def test_double_agrees_with_the_oracle_on_the_gpu_verified_discriminators(monkey
 
 
 def test_multi_resolution_sequencing_matches_autograd(monkeypatch):
-    """DiscriminatorR (train/discriminator.py:Resolution): not yet run on a GPU; its launches,
-    views and flags are checked here over the double"""
+    """DiscriminatorR (train/discriminator.py:Resolution): its launches, views and flags over
+    the double (how it was developed before it first ran on a GPU)"""
     D = run(monkeypatch, init.discriminator_state(1234, multi_resolution=True), seed=1)
     assert [type(m).__name__ for m in D.modules[5:]] == ['Resolution'] * 3
 
