@@ -48,11 +48,16 @@ def mma_cycles(columns):
     return max(columns / 2, 64)
 
 
-def tensor_ms(channels, taps, t_len, columns_scale=1, rows=None):
-    """columns_scale = 2: the space-to-depth form (twice the channels over half the steps)"""
+def tensor_ms(channels, taps, t_len, columns_scale=1, rows=None, scheme='bf16x3'):
+    """columns_scale = 2: the space-to-depth form (twice the channels over half the steps);
+    scheme 'fp16+mxfp8x2': per 16 channels one fp16 MMA (N = C) and two halves of an fp8 MMA
+    (K = 32, twice the rate: N / 2 cycles per 32 channels, same 64-cycle A fetch)"""
     c = channels * columns_scale
-    wide = [2 * c] if 2 * c <= 256 else [c, c]
-    per_step = sum(mma_cycles(n) for n in wide) + mma_cycles(c)
+    if scheme == 'bf16x3':
+        wide = [2 * c] if 2 * c <= 256 else [c, c]
+        per_step = sum(mma_cycles(n) for n in wide) + mma_cycles(c)
+    else:
+        per_step = mma_cycles(c) + 2 * mma_cycles(c) / 2
     tiles = -(-(BATCH * (t_len // columns_scale if rows is None else rows)) // 128)
     cycles = -(-tiles // SMS) * taps * (c // 16) * per_step
     return cycles / (CLOCK_GHZ * 1e6) / tensor_efficiency()
@@ -90,11 +95,12 @@ def main():
     # The whole step: 3 dilations x (c1, c2) per kernel size per stage; k = 7 interpolated from the
     # model ratio of its neighbours
     print('\nWhole step (72 launches), model roofs and what the planned kernels change:')
-    header = ' C  | now: model  measured | fused c1+c2 pairs (12 B / element) | + space-to-depth for d = 1'
+    header = (' C  | now: model  measured | fused c1+c2 pairs (12 B / element) | + space-to-depth for d = 1'
+              ' | + fp16 main, 2 x mxfp8 corrections')
     print(header)
-    totals = [0., 0., 0., 0.]
+    totals = [0., 0., 0., 0., 0.]
     for channels, t_len in STAGES:
-        now = real = fused = s2d = 0.
+        now = real = fused = s2d = two = 0.
         for kernel in KERNELS:
             near = 3 if kernel == 3 else 11
             for dilation in DILATIONS:
@@ -120,10 +126,13 @@ def main():
                     first = deep if dilation == 1 else plain
                     best = min(best, max((first + deep) * halo, hbm_ms(channels, t_len, 12)))
                 s2d += best
-        print(f'{channels:3d} | {now:10.2f} {real:9.2f} | {fused:32.2f} | {s2d:27.2f}')
-        for i, value in enumerate((now, real, fused, s2d)):
+                # 2 MMA units per MAC instead of 3, on the fused pair
+                cheaper = 2 * tensor_ms(channels, kernel, t_len, scheme='fp16+mxfp8x2')
+                two += min(best, max(cheaper * halo, hbm_ms(channels, t_len, 12)))
+        print(f'{channels:3d} | {now:10.2f} {real:9.2f} | {fused:32.2f} | {s2d:27.2f} | {two:33.2f}')
+        for i, value in enumerate((now, real, fused, s2d, two)):
             totals[i] += value
-    print('sum | {:10.2f} {:9.2f} | {:32.2f} | {:27.2f}'.format(*totals))
+    print('sum | {:10.2f} {:9.2f} | {:32.2f} | {:27.2f} | {:33.2f}'.format(*totals))
     flops = 3 * 8.117e12           # three bf16 products per MAC of the 8.117 TFLOP of residual blocks
     print(f'\n(no A-fetch floor, no HBM roof: {flops / (peaks()[1] * 1e12) * 1e3:.1f} ms per step for the '
           'residual blocks at the sustained bf16 rate)')
