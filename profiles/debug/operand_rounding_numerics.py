@@ -5,6 +5,7 @@ way a scheme would round them (products and sums exact, as fp32 / int32 accumula
 precision); the error of the generated audio against the fp64 oracle is printed per scheme.
 
     python profiles/debug/operand_rounding_numerics.py [frames] [scheme ...]      (SEED=n for other inputs)
+    python profiles/debug/operand_rounding_numerics.py pitch                      (the pitch network)
 
 Schemes (MMA cost per MAC in units of one bf16 MMA; results in DESIGN.md section 7):
   bf16x3             the shipped one: x_hi w_hi + x_hi w_lo + x_lo w_hi on bf16 halves          3
@@ -149,5 +150,45 @@ def main():
             print(f'{scheme:21s} {error(audio):.2e}')
 
 
+
+
+def pitch_network(frames=24, schemes=('bf16x3', 'fp16+mxfp8x2')):
+    """The same question for the FCNF0++ pitch network of the preprocess chain (oracle/penn.py:
+    395 MFLOP per frame, every layer on conv1d_tc_kernel): error of the logits, bar 1e-4"""
+    from oracle import penn
+    state = penn.init_state(1234)
+    double = {k: v.double() for k, v in state.items()}
+    audio = inputs.audio(1, 256 * frames + 1024, seed=2)
+    with torch.no_grad():
+        x = penn.frames(audio, 22050, 256 / 22050).double()
+        exact = penn.infer(double, x)
+        error = lambda logits: float((logits.double() - exact).abs().max() / exact.abs().max())
+        print(f'pitch network, {x.shape[0]} frames: fp32 {error(penn.infer(state, x.float())):.2e}')
+        for scheme in schemes:
+            conv, _ = make(scheme)
+            # the first layer (1 input channel) is an im2col 1 x 1 conv in the product: also rounded
+            F.conv1d = lambda x, w, b=None, *a, **k: conv(x, w, b, *a, **k) if w.shape[1] >= 32 \
+                else sum(conv1d(p, q, None, *a, **k) for p, q in split_products(scheme, x, w)) + b[None, :, None]
+            try:
+                logits = penn.infer(double, x)
+            finally:
+                F.conv1d = conv1d
+            print(f'  {scheme:19s} {error(logits):.2e}')
+
+
+def split_products(scheme, x, w):
+    """The k = 32, one-channel first layer as the three (or 1 + 2) products of the scheme, with
+    the block scales taken along the taps (its reduction axis)"""
+    if scheme == 'bf16x3':
+        x_hi, x_lo = split_bf16(x)
+        w_hi, w_lo = split_bf16(w)
+        return (x_hi, w_hi), (x_hi, w_lo), (x_lo, w_hi)
+    x_hi, w_hi = x.float().half().double(), w.float().half().double()
+    return (x_hi, w_hi), (fp8(x_hi), fp8(w - w_hi)), (fp8(x - x_hi), fp8(w_hi))
+
+
 if __name__ == '__main__':
-    main()
+    if 'pitch' in sys.argv:
+        pitch_network()
+    else:
+        main()
