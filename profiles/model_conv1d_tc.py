@@ -27,6 +27,10 @@ ROOT = Path(__file__).resolve().parent.parent
 BATCH, SMS, CLOCK_GHZ = 32, 148, 1.86
 STAGES = ((256, 3440), (128, 27520), (64, 55040), (32, 110080))      # channels, time steps (5 s)
 KERNELS, DILATIONS = (3, 7, 11), (1, 3, 5)
+# A fused c1 -> c2 pair that reads the fp32 residual stream once (operand planes made in shared
+# memory by the kernel, the residual taken from the same tile) and writes it once: 4 + 4 bytes per
+# element.  Today: c1 planes in + out (8), c2 planes in + fp32 residual in + fp32 and planes out (16).
+PAIR_BYTES = 8
 
 
 def peaks():
@@ -95,7 +99,7 @@ def main():
     # The whole step: 3 dilations x (c1, c2) per kernel size per stage; k = 7 interpolated from the
     # model ratio of its neighbours
     print('\nWhole step (72 launches), model roofs and what the planned kernels change:')
-    header = (' C  | now: model  measured | fused c1+c2 pairs (12 B / element) | + space-to-depth for d = 1'
+    header = (' C  | now: model  measured | fused c1+c2 pairs (8 B / element)  | + space-to-depth for d = 1'
               ' | + fp16 main, 2 x mxfp8 corrections')
     print(header)
     totals = [0., 0., 0., 0., 0.]
@@ -112,9 +116,9 @@ def main():
                     max(tensor_ms(channels, near, t_len), hbm_ms(channels, t_len, 8)) +
                     max(tensor_ms(channels, near, t_len), hbm_ms(channels, t_len, 16)))
                 real += (c1 + c2) * ratio
-                # fused pair: a tile keeps 128 - (k - 1) of its rows, traffic 12 B / element
+                # fused pair: a tile keeps 128 - (k - 1) of its rows, traffic PAIR_BYTES / element
                 halo = 128 / (128 - (kernel - 1))
-                pair = max(pair_tensor * halo, hbm_ms(channels, t_len, 12))
+                pair = max(pair_tensor * halo, hbm_ms(channels, t_len, PAIR_BYTES))
                 # fuse only where it wins
                 fused += min(pair, c1 + c2)
                 # space-to-depth (c2 always, c1 when d = 1) for the narrow stages
@@ -124,11 +128,11 @@ def main():
                     deep = tensor_ms(channels, taps, t_len, columns_scale=2)
                     plain = tensor_ms(channels, kernel, t_len)
                     first = deep if dilation == 1 else plain
-                    best = min(best, max((first + deep) * halo, hbm_ms(channels, t_len, 12)))
+                    best = min(best, max((first + deep) * halo, hbm_ms(channels, t_len, PAIR_BYTES)))
                 s2d += best
                 # 2 MMA units per MAC instead of 3, on the fused pair
                 cheaper = 2 * tensor_ms(channels, kernel, t_len, scheme='fp16+mxfp8x2')
-                two += min(best, max(cheaper * halo, hbm_ms(channels, t_len, 12)))
+                two += min(best, max(cheaper * halo, hbm_ms(channels, t_len, PAIR_BYTES)))
         print(f'{channels:3d} | {now:10.2f} {real:9.2f} | {fused:32.2f} | {s2d:27.2f} | {two:33.2f}')
         for i, value in enumerate((now, real, fused, s2d, two)):
             totals[i] += value
