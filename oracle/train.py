@@ -297,10 +297,9 @@ def leaf_state(state, dtype=torch.float32):
 
 def batch(batch_size, frames, seed=1234):
     """Synthetic training batch with the shapes of data/collate.py:43-60"""
-    from oracle import inputs
-    loudness, pitch, periodicity, ppg, speakers, sbr, lr = inputs.synthesis(
-        batch_size, frames, seed=seed, loudness_rows=513)
-    audio = inputs.audio(batch_size, frames * 256, seed=seed + 1)[:, None]
+    from promonet_b200 import synthetic
+    loudness, pitch, periodicity, ppg, speakers, sbr, lr, audio = synthetic.training(
+        batch_size, frames, seed)
     with torch.no_grad():
         spectrograms = dsp.magnitude(audio)
     return loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio

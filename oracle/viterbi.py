@@ -6,6 +6,7 @@ C code on small cases.  Both follow torbi.from_probabilities as it is called at
 promonet/preprocess/harmonics.py:270-276.
 """
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
@@ -51,14 +52,26 @@ def decode(observation, batch_frames=None, transition=None, initial=None, log_pr
     lengths = None
     if batch_frames is not None:
         lengths = np.ascontiguousarray(batch_frames, dtype=np.int32)
-    status = library().viterbi_oracle(
-        observation.ctypes.data_as(ctypes.c_void_p),
-        lengths.ctypes.data_as(ctypes.c_void_p) if lengths is not None else None,
-        transition.ctypes.data_as(ctypes.c_void_p),
-        initial.ctypes.data_as(ctypes.c_void_p),
-        indices.ctypes.data_as(ctypes.c_void_p),
-        batch, frames, states)
-    if status:
+    # one call per utterance, spread over host threads (ctypes releases the GIL): only
+    # the wall time of the checker depends on this
+    function = library().viterbi_oracle
+
+    def one(b):
+        return function(
+            observation[b:b + 1].ctypes.data_as(ctypes.c_void_p),
+            lengths[b:b + 1].ctypes.data_as(ctypes.c_void_p) if lengths is not None else None,
+            transition.ctypes.data_as(ctypes.c_void_p),
+            initial.ctypes.data_as(ctypes.c_void_p),
+            indices[b:b + 1].ctypes.data_as(ctypes.c_void_p),
+            1, frames, states)
+
+    if batch > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(batch, os.cpu_count() or 1)) as pool:
+            statuses = list(pool.map(one, range(batch)))
+    else:
+        statuses = [one(b) for b in range(batch)]
+    if any(statuses):
         raise MemoryError('viterbi_oracle')
     return indices
 
