@@ -69,6 +69,13 @@ int pmn_generator_set_tensor(
  * and pack weights for the kernels.  Must be called after all tensors are set. */
 int pmn_generator_finalize(pmn_generator* g, int math, void* stream);
 
+/* Tensor-core math only: which residual blocks (Block.forward, hifigan.py:198-210) run
+ * their three c1 -> c2 pairs as fused pmn_conv_pair_tc-style launches.  Bit
+ * 3 * stage + block (block 0 / 1 / 2 = kernel 3 / 7 / 11); stage 0 (C = 256) is never
+ * fused.  The default is the measured-fastest selection; results are bit-identical
+ * for every mask. */
+int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask);
+
 size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames);
 
 /* Generator.forward generator.py:116-135.
@@ -242,6 +249,21 @@ int pmn_conv1d_tc(
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
     int batch, int channels, int t_len, int k, int dilation,
     float in_slope, float out_slope,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* One residual pair of Block.forward (promonet/model/hifigan.py:198-210),
+ *     y = x + c2(lrelu(c1(lrelu(x), dilation)))      c1, c2: Conv1d(C, C, k), "same",
+ * fused in one tcgen05 kernel that reads the fp32 stream once and writes it once
+ * (promonet_b200/csrc/conv_pair_tc.cu); C in {32, 64, 128}, odd k <= 11,
+ * (k - 1) * dilation <= 50.  weight1 / weight2 are folded fp32 (C, C, K) and are
+ * packed into `workspace` (pmn_conv_pair_tc_workspace_bytes) on every call: a
+ * parity entry point.  out and accum (same modes as pmn_conv1d) must not alias x.
+ * Bit-identical to pmn_conv1d_tc applied twice. */
+size_t pmn_conv_pair_tc_workspace_bytes(int channels, int k);
+int pmn_conv_pair_tc(
+    const float* x, const float* weight1, const float* bias1, const float* weight2,
+    const float* bias2, float* out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation, float slope,
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* General form: C_in -> C_out in {(256,256), (128,128), (64,64), (32,32), (256,32),

@@ -103,6 +103,11 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream) {
     return generator_finalize(g, math, (cudaStream_t)stream);
 }
 
+int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask) {
+    PMN_REQUIRE(g, "set_pair_mask: null generator");
+    return generator_set_pair_mask(g, mask);
+}
+
 size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames) {
     if (!g || batch <= 0 || frames <= 0) return 0;
     return generator_workspace_bytes(g, batch, frames);
@@ -392,6 +397,31 @@ int pmn_conv1d_tc_general(
     PMN_TRY(launch_conv1d_tc(a, stream));
     if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, c_out, t_out, stream));
     return PMN_OK;
+}
+
+size_t pmn_conv_pair_tc_workspace_bytes(int channels, int k) {
+    if (channels <= 0 || k <= 0) return 0;
+    return 2 * align_up(tc_weight_elements(channels, channels, k) * sizeof(__nv_bfloat16), 256);
+}
+
+int pmn_conv_pair_tc(
+    const float* x, const float* weight1, const float* bias1, const float* weight2,
+    const float* bias2, float* out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation, float slope,
+    void* workspace, size_t workspace_bytes, void* stream_) {
+    PMN_REQUIRE(x && weight1 && weight2 && workspace, "conv_pair_tc: null pointer");
+    PMN_REQUIRE(tc_pair_supported(channels, k, dilation), "conv_pair_tc: unsupported shape");
+    if (pmn_conv_pair_tc_workspace_bytes(channels, k) > workspace_bytes)
+        return fail(PMN_ERR_WORKSPACE, "conv_pair_tc: workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    auto* slabs1 = static_cast<__nv_bfloat16*>(workspace);
+    auto* slabs2 = reinterpret_cast<__nv_bfloat16*>(
+        static_cast<char*>(workspace) + pmn_conv_pair_tc_workspace_bytes(channels, k) / 2);
+    PMN_TRY(launch_pack_tc_weight(weight1, slabs1, channels, channels, k, false, stream));
+    PMN_TRY(launch_pack_tc_weight(weight2, slabs2, channels, channels, k, false, stream));
+    return launch_conv_pair_tc(
+        x, slabs1, bias1, slabs2, bias2, out, accum, accum_mode, accum_scale, batch, channels,
+        t_len, k, dilation, slope, stream);
 }
 
 int pmn_conv_transpose1d(

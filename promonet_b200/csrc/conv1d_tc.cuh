@@ -85,6 +85,16 @@ int launch_f32_from_planes(
 int launch_zero_plane_pads(
     __nv_bfloat16* planes, int batch, int channels, int t_len, cudaStream_t stream);
 
+// One residual pair y = x + c2(lrelu(c1(lrelu(x)))) (hifigan.py:198-210) in one kernel
+// (conv_pair_tc.cu): x, out, accum are fp32 (B, C, T); w1 / w2 are the slabs of
+// launch_pack_tc_weight; C in {32, 64, 128}, odd k <= 11, (k - 1) dilation <= 50.
+// out / accum must not alias x.  Bit-identical to the two launch_conv1d_tc calls.
+bool tc_pair_supported(int channels, int k, int dilation);
+int launch_conv_pair_tc(
+    const float* x, const __nv_bfloat16* w1, const float* bias1, const __nv_bfloat16* w2,
+    const float* bias2, float* out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation, float slope, cudaStream_t stream);
+
 // folded fp32 weight (C_out, C_in, K) -> hi/lo slabs
 int launch_pack_tc_weight(
     const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, bool frames, cudaStream_t stream);

@@ -28,6 +28,9 @@ constexpr int kUpRate[kStages] = {8, 8, 2, 2};      // :262
 constexpr int kResKernel[3] = {3, 7, 11};           // :250
 constexpr int kResDilation[3] = {1, 3, 5};          // :253
 constexpr float kSlope = 0.1f;                      // :216
+// Which residual blocks take the fused pair kernel by default: the HBM-bound ones
+// (profiles/r2_pair_selection.txt); bit 3 * stage + block, block = kernel 3 / 7 / 11
+constexpr unsigned kDefaultPairMask = 0xFF8u;       // stages 1-3 (C = 128, 64, 32), all kernels
 
 
 struct PackedConv {
@@ -46,6 +49,9 @@ struct pmn_generator {
     bool finalized = false;
     int math = PMN_MATH_FP32_SIMT;
     float ppg_threshold = 0.85f;
+    // bit (3 * stage + block): run that residual block's three c1 -> c2 pairs as fused
+    // conv_pair_tc_kernel launches (tensor-core math, C <= 128) instead of six conv1d_tc ones
+    unsigned pair_mask = pmn::kDefaultPairMask;
 
     pmn::PackedConv up[pmn::kStages];
     pmn::PackedConv conv1[pmn::kStages][3][3];
@@ -129,7 +135,7 @@ Workspace carve(void* base, int batch, int frames, int math) {
     w.x0 = take(stage);
     w.cur = take(stage);
     w.mrf = take(stage);
-    w.xt = nullptr;
+    w.xt = take(stage);
     w.a0 = w.at = w.ac = nullptr;
     if (math == PMN_MATH_BF16X3_TC) {
         // planes are (B, 2, C, t_pad) bf16; the widest is the last stage (C = 32)
@@ -144,8 +150,6 @@ Workspace carve(void* base, int batch, int frames, int math) {
         w.a0 = take_planes();
         w.at = take_planes();
         w.ac = take_planes();
-    } else {
-        w.xt = take(stage);
     }
     w.bytes = (size_t)(p - static_cast<char*>(base));
     return w;
@@ -235,6 +239,11 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
     return PMN_OK;
 }
 
+int generator_set_pair_mask(pmn_generator* g, unsigned mask) {
+    g->pair_mask = mask;
+    return PMN_OK;
+}
+
 size_t generator_workspace_bytes(const pmn_generator* g, int batch, int frames) {
     return carve(nullptr, batch, frames, g->math).bytes;
 }
@@ -300,12 +309,36 @@ int generator_forward(
         t_len *= kUpRate[s];
         const int channels = up.c_out;
         if (g->math == PMN_MATH_BF16X3_TC) {
-            // G5/G6 on tcgen05: activations travel between convs as bf16 hi/lo
-            // planes of lrelu(.), the residual stream stays fp32
-            PMN_TRY(launch_planes_from_f32(w.x0, w.a0, batch, channels, t_len, kSlope, stream));
-            PMN_TRY(launch_zero_plane_pads(w.at, batch, channels, t_len, stream));
-            PMN_TRY(launch_zero_plane_pads(w.ac, batch, channels, t_len, stream));
+            // G5/G6 on tcgen05.  Blocks selected by pair_mask run as three fused pair
+            // launches over the fp32 stream (x0 -> cur -> xt -> mean); the others as six
+            // launches with the activations travelling between them as bf16 hi/lo planes
+            // of lrelu(.) next to the fp32 residual stream
+            bool fused[3], any_planes = false;
             for (int j = 0; j < 3; ++j) {
+                fused[j] = ((g->pair_mask >> (3 * s + j)) & 1u) != 0 &&
+                           tc_pair_supported(channels, kResKernel[j], kResDilation[2]);
+                any_planes = any_planes || !fused[j];
+            }
+            if (any_planes) {
+                PMN_TRY(launch_planes_from_f32(w.x0, w.a0, batch, channels, t_len, kSlope, stream));
+                PMN_TRY(launch_zero_plane_pads(w.at, batch, channels, t_len, stream));
+                PMN_TRY(launch_zero_plane_pads(w.ac, batch, channels, t_len, stream));
+            }
+            for (int j = 0; j < 3; ++j) {
+                if (fused[j]) {
+                    const float* in = w.x0;
+                    for (int d = 0; d < 3; ++d) {
+                        const PackedConv& c1 = g->conv1[s][j][d];
+                        const PackedConv& c2 = g->conv2[s][j][d];
+                        float* out = d == 0 ? w.cur : d == 1 ? w.xt : nullptr;
+                        PMN_TRY(launch_conv_pair_tc(
+                            in, c1.slabs, c1.bias, c2.slabs, c2.bias, out,
+                            d == 2 ? w.mrf : nullptr, j == 0 ? 1 : 2, 1.f / 3.f,
+                            batch, channels, t_len, kResKernel[j], kResDilation[d], kSlope, stream));
+                        in = out;
+                    }
+                    continue;
+                }
                 for (int d = 0; d < 3; ++d) {
                     TcConvArgs a;
                     a.batch = batch; a.c_in = a.c_out = channels; a.t_len = t_len;

@@ -11,6 +11,7 @@ int generator_set_tensor(
     pmn_generator* g, const char* name, const float* data, const int64_t* shape, int ndim,
     cudaStream_t stream);
 int generator_finalize(pmn_generator* g, int math, cudaStream_t stream);
+int generator_set_pair_mask(pmn_generator* g, unsigned mask);
 size_t generator_workspace_bytes(const pmn_generator* g, int batch, int frames);
 int generator_features(
     pmn_generator* g, const float* loudness, int rows, const float* pitch,

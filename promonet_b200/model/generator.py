@@ -6,6 +6,8 @@ Mirrors the interface of promonet.model.Generator
 pairs), and calling it takes the same eight arguments and returns (B, 1, T).
 All arithmetic happens in the CUDA library; torch only owns the memory.
 """
+import os
+
 import torch
 
 from promonet_b200 import _lib, config
@@ -14,7 +16,11 @@ from promonet_b200.model import init
 
 class Generator:
 
-    def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None):
+    def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None, pair_mask=None):
+        """pair_mask: which residual blocks run as fused pair kernels
+        (pmn_generator_set_pair_mask); None = the library default, or the
+        PMN_PAIR_MASK environment variable (an experiment knob: the output bits
+        do not depend on it)"""
         if not torch.cuda.is_available():
             raise RuntimeError(
                 'promonet_b200.model.Generator needs a CUDA device (sm_100a); '
@@ -22,6 +28,9 @@ class Generator:
         self.device = torch.device(
             'cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.math = math
+        if pair_mask is None and os.environ.get('PMN_PAIR_MASK'):
+            pair_mask = int(os.environ['PMN_PAIR_MASK'], 0)
+        self.pair_mask = pair_mask
         self.handle = None
         self.default_previous_samples = torch.zeros(1, 1, 1, device=self.device)
         self._workspace = None
@@ -66,6 +75,8 @@ class Generator:
                     handle, name.encode(), value.data_ptr(), shape, value.ndim,
                     stream))
             _lib.check(lib.pmn_generator_finalize(handle, self.math, stream))
+            if self.pair_mask is not None:
+                _lib.check(lib.pmn_generator_set_pair_mask(handle, self.pair_mask))
             torch.cuda.current_stream().synchronize()
         self._state = {k: v.detach().cpu() for k, v in state.items()}
         return self
