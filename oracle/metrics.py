@@ -189,9 +189,10 @@ class Metrics:
 
 
 def grid_constant(frames, ratio):
-    """promonet.edit.grid.constant -> ppgs.edit.grid.constant (un-vendored): a uniform grid of
-    round((T + 1) / ratio) positions over [0, T - 1]"""
-    return features.grid_of_length(frames, round((frames + 1) / ratio))
+    """promonet.edit.grid.constant -> ppgs.edit.grid.constant (un-vendored, [RECALLED]): a uniform
+    grid of round(T / ratio + 1e-4) positions over [0, T - 1], the frame count of the reference's
+    own selective-stretch branch (promonet/edit/core.py:82)"""
+    return features.grid_of_length(frames, round(frames / ratio + 1e-4))
 
 
 def edit_from_features(loudness, pitch, periodicity, ppg, pitch_shift_cents=None,

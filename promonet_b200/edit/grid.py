@@ -35,6 +35,7 @@ def of_length(tensor, length):
 
 
 def constant(tensor, ratio):
-    """Grid for constant-ratio time-stretching (ppgs.edit.grid.constant: un-vendored, restated
-    as of_length with round((T + 1) / ratio) frames)"""
-    return of_length(tensor, round((tensor.shape[-1] + 1) / ratio))
+    """Grid for constant-ratio time-stretching (ppgs.edit.grid.constant: un-vendored, [RECALLED]
+    of_length with round(T / ratio + 1e-4) frames -- the frame count the reference's own
+    selective-stretch branch uses, promonet/edit/core.py:82)"""
+    return of_length(tensor, round(tensor.shape[-1] / ratio + 1e-4))

@@ -20,7 +20,8 @@ def from_audio(
     gpu: Optional[int] = None,
     features: list = ['loudness', 'pitch', 'periodicity'],
     loudness_bands: Optional[int] = config.LOUDNESS_BANDS,
-    max_harmonics=None
+    max_harmonics=None,
+    pitch_checkpoint=None
 ) -> Tuple:
     """Preprocess audio
 
@@ -33,6 +34,8 @@ def from_audio(
             wrap foreign pretrained models and are out of scope: asking for
             them raises.
         loudness_bands: The number of A-weighted loudness bands
+        pitch_checkpoint: FCNF0++ checkpoint for pitch / periodicity (penn's own or
+            ours; default $PROMONET_B200_PITCH_CHECKPOINT; none = random init + warning)
 
     Returns (in this order, those requested)
         loudness (bands, F), pitch (1, F), periodicity (1, F),
@@ -42,7 +45,7 @@ def from_audio(
         value[0] if name in ('loudness', 'spectrogram', 'mels') else value
         for name, value in zip(
             [f for f in SUPPORTED if f in features],
-            from_audio_batch(audio, sample_rate, gpu, features, loudness_bands)))
+            from_audio_batch(audio, sample_rate, gpu, features, loudness_bands, pitch_checkpoint)))
 
 
 def from_audio_batch(
@@ -50,7 +53,8 @@ def from_audio_batch(
     sample_rate: int = config.SAMPLE_RATE,
     gpu: Optional[int] = None,
     features: list = ['loudness', 'pitch', 'periodicity'],
-    loudness_bands: Optional[int] = config.LOUDNESS_BANDS
+    loudness_bands: Optional[int] = config.LOUDNESS_BANDS,
+    pitch_checkpoint=None
 ) -> Tuple:
     """Batched from_audio over equal-length utterances audio (B, T):
     loudness (B, bands, F), pitch (B, F), periodicity (B, F), spectrogram
@@ -72,7 +76,7 @@ def from_audio_batch(
         value = loudness.from_audio(audio, loudness_bands)
         result.append(value if value.ndim == 3 else value[None])
     if 'pitch' in features or 'periodicity' in features:
-        pitch, periodicity = _pitch_model(device)(
+        pitch, periodicity = _pitch_model(device, pitch_checkpoint)(
             audio, sample_rate, config.HOPSIZE / config.SAMPLE_RATE,
             config.FMIN, config.FMAX, 2048)
         if 'pitch' in features:
@@ -87,24 +91,28 @@ def from_audio_batch(
 
 
 def from_file(file, gpu=None, features=['loudness', 'pitch', 'periodicity'],
-              loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None) -> Tuple:
+              loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None,
+              pitch_checkpoint=None) -> Tuple:
     """Preprocess audio on disk (promonet/preprocess/core.py:129-166); 22.05 kHz PCM wav"""
     return from_audio(
-        load_audio(file), gpu=gpu, features=features, loudness_bands=loudness_bands)
+        load_audio(file), gpu=gpu, features=features, loudness_bands=loudness_bands,
+        pitch_checkpoint=pitch_checkpoint)
 
 
 def from_file_to_file(file, output_prefix=None, gpu=None,
                       features=['loudness', 'pitch', 'periodicity'],
-                      loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None) -> None:
+                      loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None,
+                      pitch_checkpoint=None) -> None:
     """Preprocess audio on disk and save (preprocess/core.py:169-224)"""
     from_files_to_files(
-        [file], None if output_prefix is None else [output_prefix], gpu, features, loudness_bands)
+        [file], None if output_prefix is None else [output_prefix], gpu, features, loudness_bands,
+        pitch_checkpoint=pitch_checkpoint)
 
 
 def from_files_to_files(files, output_prefixes=None, gpu=None,
                         features=['loudness', 'pitch', 'periodicity'],
                         loudness_bands=config.LOUDNESS_BANDS, max_harmonics=None,
-                        max_batch=32) -> None:
+                        max_batch=32, pitch_checkpoint=None) -> None:
     """Preprocess multiple audio files on disk and save (preprocess/core.py:227-319): writes
     `{prefix}-loudness.pt`, `{prefix}-viterbi-pitch.pt`, `{prefix}-viterbi-periodicity.pt` (the
     names of the reference under VITERBI_DECODE_PITCH, :262-268), `{prefix}-spectrogram.pt`,
@@ -127,7 +135,8 @@ def from_files_to_files(files, output_prefixes=None, gpu=None,
         for start in range(0, len(members), max_batch):
             chunk = members[start:start + max_batch]
             results = from_audio_batch(
-                torch.cat([audio[i] for i in chunk]), config.SAMPLE_RATE, gpu, features, loudness_bands)
+                torch.cat([audio[i] for i in chunk]), config.SAMPLE_RATE, gpu, features, loudness_bands,
+                pitch_checkpoint)
             for name, values in zip(order, results):
                 for i, value in zip(chunk, values.cpu()):
                     # pitch and periodicity are stored (1, F) like penn's outputs
@@ -149,9 +158,29 @@ def load_audio(file):
     return (data.float() / 32768.).reshape(-1, channels).mean(1)[None]
 
 
-def _pitch_model(device):
+PITCH_CHECKPOINT_VARIABLE = 'PROMONET_B200_PITCH_CHECKPOINT'
+
+
+def _pitch_model(device, checkpoint=None):
+    """The FCNF0++ network of `device`, loaded from `checkpoint` (or the file named by
+    $PROMONET_B200_PITCH_CHECKPOINT).  penn's pretrained weights are downloaded by the
+    reference and are not available offline: without a checkpoint the network is a seeded
+    random initialisation, whose pitch is meaningless outside tests and benchmarks -- say so."""
+    import os
+    import warnings
+    checkpoint = checkpoint or os.environ.get(PITCH_CHECKPOINT_VARIABLE) or None
     if not hasattr(_pitch_model, 'models'):
         _pitch_model.models = {}
-    if device not in _pitch_model.models:
-        _pitch_model.models[device] = penn.Model(device=device)
-    return _pitch_model.models[device]
+    key = (device, None if checkpoint is None else str(checkpoint))
+    if key not in _pitch_model.models:
+        if checkpoint is None:
+            warnings.warn(
+                'promonet_b200.preprocess: no FCNF0++ checkpoint given (pitch_checkpoint= or '
+                f'${PITCH_CHECKPOINT_VARIABLE}): pitch and periodicity come from a RANDOMLY '
+                'INITIALISED network (seed 1234) and are only good for tests and benchmarks',
+                RuntimeWarning, stacklevel=3)
+            state = None
+        else:
+            state = penn.load_checkpoint(checkpoint)
+        _pitch_model.models[key] = penn.Model(device=device, state=state)
+    return _pitch_model.models[key]

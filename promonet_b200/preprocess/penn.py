@@ -45,6 +45,52 @@ def init_state(seed=config.RANDOM_SEED):
     return state
 
 
+def convert_state(state):
+    """Checkpoint state dict -> this module's names.  Accepts our own names
+    (`layers.N.conv.weight`, ...) and the names of upstream penn's FCNF0++ as far
+    as they can be known offline (penn is not installed: [RECALLED] its model is a
+    Sequential of Sequential blocks, so keys look like `N.M.weight` with the Conv1d
+    at M = 0 and the LayerNorm after the ReLU / MaxPool, and the final Conv1d at
+    `6.weight`, possibly under a `model.` / `module.` prefix).  The mapping goes by
+    block index and tensor rank -- rank 3 = convolution, rank 2 = LayerNorm
+    (C, length) -- not by M, and every tensor must land on a slot of the right shape."""
+    import re
+    expected = init_state(0)
+    if all(name in state for name in expected):
+        return OrderedDict((name, state[name]) for name in expected)
+    out = OrderedDict()
+    for name, tensor in state.items():
+        if not torch.is_tensor(tensor):
+            continue
+        match = re.search(r'(?:^|\.)(\d+)\.(?:(\d+)\.)?(weight|bias)$', name)
+        if not match:
+            continue
+        block, kind = int(match.group(1)), match.group(3)
+        if block == 6:
+            target = f'layers.6.{kind}'
+        elif tensor.ndim == 3 or (kind == 'bias' and tensor.ndim == 1):
+            target = f'layers.{block}.conv.{kind}'
+        else:
+            target = f'layers.{block}.norm.{kind}'
+        out[target] = tensor
+    missing = [name for name in expected if name not in out]
+    wrong = [name for name in expected if name in out and out[name].shape != expected[name].shape]
+    if missing or wrong:
+        raise ValueError(
+            f'not an FCNF0++ checkpoint: missing {missing[:4]}, wrong shape {wrong[:4]} '
+            f'(keys seen: {list(state)[:6]})')
+    return OrderedDict((name, out[name]) for name in expected)
+
+
+def load_checkpoint(file):
+    """torchutil.checkpoint file ({'model': state_dict, ...}) or a bare state dict"""
+    state = torch.load(file, map_location='cpu')
+    for key in ('model', 'state_dict'):
+        if isinstance(state, dict) and key in state and isinstance(state[key], dict):
+            state = state[key]
+    return convert_state(state)
+
+
 def transition_matrix(hopsize_seconds):
     """Triangular-band pitch transition: max(0, max_bins_per_frame - |i - j|), rows normalised"""
     max_bins = MAX_OCTAVES_PER_SECOND * hopsize_seconds * (OCTAVE / CENTS_PER_BIN) + 1
@@ -174,10 +220,7 @@ def from_audio(
         from_audio.checkpoint != checkpoint or
         from_audio.device != device
     ):
-        state = None
-        if checkpoint is not None:
-            state = torch.load(checkpoint, map_location='cpu')
-            state = state.get('model', state)
+        state = None if checkpoint is None else load_checkpoint(checkpoint)
         from_audio.model = Model(device=device, state=state)
         from_audio.checkpoint = checkpoint
         from_audio.device = device

@@ -58,6 +58,7 @@ class Trainer:
             self.spectral_convergence = MultiResolutionSpectralConvergence(self.generator.device, math)
         self.device = self.generator.device
         self.step_count = 0
+        self.epoch = 0
 
     ###########################################################################
     # Data-parallel gradient exchange
@@ -223,8 +224,9 @@ class Trainer:
     # Checkpoints (torchutil.checkpoint layout: train/core.py:426-438)
     ###########################################################################
 
-    def save(self, directory, epoch=0):
+    def save(self, directory, epoch=None):
         directory = Path(directory)
+        epoch = self.epoch if epoch is None else epoch
         rank = torch.distributed.get_rank(self.process_group) if self.world > 1 else 0
         if rank == 0:
             directory.mkdir(parents=True, exist_ok=True)
@@ -245,32 +247,40 @@ class Trainer:
                 continue
             checkpoint = torch.load(files[-1], map_location='cpu')
             module.load_state_dict(checkpoint['model'])
-            optimizer = checkpoint.get('optimizer')
-            if isinstance(optimizer, dict) and 'exp_avg' in optimizer:
-                module.params.load_optimizer_state(optimizer)
+            if checkpoint.get('optimizer') is not None:
+                module.params.load_optimizer_state(checkpoint['optimizer'])
             self.step_count = int(checkpoint.get('step', 0))
+            self.epoch = int(checkpoint.get('epoch', 0))
 
 
 def train(directory, dataset='vctk', train_partition='train', valid_partition='valid',
-          adapt_from=None, gpu=None, loader=None, steps=None, valid_loader=None):
+          adapt_from=None, gpu=None, loader=None, steps=None, valid_loader=None,
+          peer_optimizer=True, pitch_checkpoint=None):
     """promonet.train (promonet/train/core.py:17-24).  The reference builds its loader
     from a preprocessed dataset on disk (promonet/data, out of scope here): pass `loader`,
     an iterable of batches laid out as data/collate.py:43-60
     (text, loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
     loudness_ratios, spectrograms, audio, stems).  With `valid_loader` (batch-1 batches of the same
     layout) the generator is evaluated every EVALUATION_INTERVAL steps like train/core.py:387-426
-    (promonet_b200.train.evaluate)"""
+    (promonet_b200.train.evaluate).  `steps` defaults to STEPS, or STEPS + ADAPTATION_STEPS when
+    adapting (:111-114); `peer_optimizer=False` selects the NCCL all-reduce exchange;
+    `pitch_checkpoint` is the FCNF0++ checkpoint the validation's pitch extraction uses."""
     if loader is None:
         raise ValueError(
             'promonet_b200.train needs `loader`: the dataset pipeline of the reference '
             '(promonet.data) is outside the accelerated path')
     device = torch.device('cuda', 0 if gpu is None else gpu)
     torch.cuda.set_device(device)
-    trainer = Trainer(device=device)
+    trainer = Trainer(device=device, peer_optimizer=peer_optimizer)
     trainer.load(adapt_from if adapt_from is not None else directory)
     trainer.broadcast_parameters()
-    steps = config.STEPS if steps is None else steps
+    if steps is None:
+        # :111-114: adaptation runs ADAPTATION_STEPS past the pretraining budget
+        steps = config.STEPS + (config.ADAPTATION_STEPS if adapt_from is not None else 0)
     while trainer.step_count < steps:
+        sampler = getattr(loader, 'batch_sampler', None)
+        if hasattr(sampler, 'set_epoch'):
+            sampler.set_epoch(trainer.epoch)             # :133
         for batch in loader:
             (_, loudness, pitch, periodicity, ppg, speakers, sbr, lr, spectrograms, audio, _) = batch
             if audio.shape[-1] < config.CHUNK_SIZE:   # :154
@@ -283,10 +293,11 @@ def train(directory, dataset='vctk', train_partition='train', valid_partition='v
                 from promonet_b200.train.evaluate import evaluate
                 evaluate(
                     directory, step, trainer.generator, valid_loader, device.index,
-                    config.DEFAULT_EVALUATION_STEPS)
+                    config.DEFAULT_EVALUATION_STEPS, pitch_checkpoint=pitch_checkpoint)
             if trainer.step_count % config.CHECKPOINT_INTERVAL == 0:
                 trainer.save(directory)
             if trainer.step_count >= steps:
                 break
+        trainer.epoch += 1                                # :382
     trainer.save(directory)
     return trainer

@@ -45,7 +45,7 @@ def inference_generator(generator, device):
 
 
 def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None, ppg_model=None,
-             process_group=None, data_parallel=True):
+             process_group=None, data_parallel=True, pitch_checkpoint=None):
     """Perform model evaluation (train/core.py:487-813)
 
     Arguments
@@ -56,6 +56,7 @@ def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None
         gpu: the GPU index (None = current CUDA device)
         evaluation_steps: stop after this many items (None = the whole loader)
         ppg_model: optional callable audio (B, T) -> ppg (B, 40, F)
+        pitch_checkpoint: FCNF0++ checkpoint of the pitch extraction (preprocess.from_audio)
         process_group, data_parallel: under torch.distributed the items are dealt round-robin to
             the ranks of `process_group` and the sums are all-reduced (data_parallel=False: every
             rank evaluates everything on its own)
@@ -83,7 +84,8 @@ def evaluate(directory, step, generator, loader, gpu=None, evaluation_steps=None
     def analyze(audio):
         """audio (B, 1, T) -> loudness (B, 8, F), pitch (B, F), periodicity (B, F), ppg | None"""
         audio = audio[:, 0]
-        loudness, pitch, periodicity = preprocess.from_audio_batch(audio, gpu=device.index)
+        loudness, pitch, periodicity = preprocess.from_audio_batch(
+            audio, gpu=device.index, pitch_checkpoint=pitch_checkpoint)
         return loudness, pitch, periodicity, None if ppg_model is None else ppg_model(audio)
 
     # without a PPG model for the generated audio there is no pronunciation metric

@@ -5,8 +5,9 @@ matching `grad`, `exp_avg` and `exp_avg_sq` buffers, so that the optimizer is on
 kernel launch (pmn_adamw) and the data-parallel gradient exchange is one NCCL
 all-reduce per module (train/core.py:255,338 are where the reference would
 need them).  Names and shapes are those of the reference state dict
-(promonet.model.Generator / Discriminator .state_dict()), so checkpoints
-interchange (torchutil.checkpoint format: train/core.py:426-438).
+(promonet.model.Generator / Discriminator .state_dict()) and the optimizer moments are
+saved and loaded in torch.optim.AdamW.state_dict() layout, so checkpoints interchange with
+the reference both ways (torchutil.checkpoint format: train/core.py:426-438).
 """
 from collections import OrderedDict
 
@@ -37,12 +38,31 @@ class ParamSet:
         self.peers = None
         if peer_group is not None:
             import torch.distributed as dist
-            import torch.distributed._symmetric_memory as symmetric
-            self.data = symmetric.empty(offset, dtype=torch.float32, device=self.device).zero_()
-            self.grad = symmetric.empty(offset, dtype=torch.float32, device=self.device).zero_()
+            # Symmetric memory needs NVLink peer access between every pair of ranks (and is a
+            # private torch API): when any rank cannot set it up, all ranks fall back together
+            # to plain buffers, i.e. to the NCCL all-reduce exchange (Trainer.optimize)
+            try:
+                import torch.distributed._symmetric_memory as symmetric
+                data = symmetric.empty(offset, dtype=torch.float32, device=self.device).zero_()
+                grad = symmetric.empty(offset, dtype=torch.float32, device=self.device).zero_()
+                handles = (symmetric.rendezvous(data, group=peer_group),
+                           symmetric.rendezvous(grad, group=peer_group))
+                failure = None
+            except Exception as error:               # noqa: BLE001 (any failure means "no peers")
+                failure = error
+            agreed = torch.tensor([0. if failure is None else 1.], device=self.device)
+            dist.all_reduce(agreed, group=peer_group)
+            if float(agreed) > 0:
+                import warnings
+                warnings.warn(
+                    'promonet_b200.train: peer-memory optimizer step unavailable '
+                    f'({failure!r}); using the NCCL all-reduce exchange', RuntimeWarning)
+                peer_group = None
+        if peer_group is not None:
+            self.data, self.grad = data, grad
             self.peers = {
-                'data': symmetric.rendezvous(self.data, group=peer_group),
-                'grad': symmetric.rendezvous(self.grad, group=peer_group),
+                'data': handles[0],
+                'grad': handles[1],
                 'group': peer_group,
                 'rank': dist.get_rank(peer_group), 'world': dist.get_world_size(peer_group)}
             # this rank's slice of the flat buffers (ZeRO-1: it keeps the moments of that slice)
@@ -113,15 +133,61 @@ class ParamSet:
         dist.all_gather_into_tensor(whole, mine, group=self.peers['group'])
         return whole[:self.numel]
 
-    def optimizer_state(self):
-        return {
-            'exp_avg': self._whole(self.exp_avg).cpu(), 'exp_avg_sq': self._whole(self.exp_avg_sq).cpu(),
-            'step': self.steps}
+    def optimizer_state(self, lr=None, betas=None, eps=None, weight_decay=None):
+        """torch.optim.AdamW.state_dict() of the optimizer the reference builds over
+        `module.parameters()` (promonet/train/core.py:62-63, saved by torchutil.checkpoint at
+        :426-438): per-parameter `exp_avg` / `exp_avg_sq` / `step` keyed by the parameter's
+        position, which is the order of the state dict; a reference run can resume from it"""
+        from promonet_b200 import config
+        exp_avg, exp_avg_sq = self._whole(self.exp_avg).cpu(), self._whole(self.exp_avg_sq).cpu()
+        state = {}
+        for position, name in enumerate(self.index):
+            state[position] = {
+                'step': torch.tensor(float(self.steps)),
+                'exp_avg': self._view(exp_avg, name).clone(),
+                'exp_avg_sq': self._view(exp_avg_sq, name).clone()}
+        group = {
+            'lr': config.LEARNING_RATE if lr is None else lr,
+            'betas': tuple(config.ADAM_BETAS if betas is None else betas),
+            'eps': config.ADAM_EPS if eps is None else eps,
+            'weight_decay': config.WEIGHT_DECAY if weight_decay is None else weight_decay,
+            'amsgrad': False, 'maximize': False, 'foreach': None, 'capturable': False,
+            'differentiable': False, 'fused': None, 'decoupled_weight_decay': True,
+            'params': list(range(len(self.index)))}
+        return {'state': state, 'param_groups': [group]}
 
     def load_optimizer_state(self, state):
-        self.exp_avg.copy_(state['exp_avg'])
-        self.exp_avg_sq.copy_(state['exp_avg_sq'])
-        self.steps = int(state['step'])
+        """Accepts torch.optim.AdamW.state_dict() (a reference checkpoint or ours) and the flat
+        layout of this library's first checkpoints; anything else raises instead of silently
+        restarting the moments and the bias-correction step"""
+        if 'exp_avg' in state and 'state' not in state:         # flat buffers (round-1 files)
+            self.exp_avg.copy_(state['exp_avg'])
+            self.exp_avg_sq.copy_(state['exp_avg_sq'])
+            self.steps = int(state['step'])
+        elif 'state' in state and 'param_groups' in state:
+            positions = state['param_groups'][0]['params']
+            names = list(self.index)
+            if len(positions) != len(names):
+                raise ValueError(
+                    f'optimizer state has {len(positions)} parameters, the module {len(names)}')
+            if not state['state']:
+                return                                          # an optimizer that never stepped
+            exp_avg, exp_avg_sq = torch.zeros(self.numel), torch.zeros(self.numel)
+            steps = 0
+            for position, name in zip(positions, names):
+                entry = state['state'][position]
+                if tuple(entry['exp_avg'].shape) != self.index[name][1]:
+                    raise ValueError(f'optimizer state of {name} has shape {tuple(entry["exp_avg"].shape)}')
+                self._view(exp_avg, name).copy_(entry['exp_avg'])
+                self._view(exp_avg_sq, name).copy_(entry['exp_avg_sq'])
+                steps = max(steps, int(entry['step']))
+            self.exp_avg.copy_(exp_avg)
+            self.exp_avg_sq.copy_(exp_avg_sq)
+            self.steps = steps
+        else:
+            raise ValueError(
+                'unrecognised optimizer state: expected torch.optim.AdamW.state_dict() '
+                f'(keys state / param_groups), got keys {sorted(state)[:6]}')
         self.steps_device.fill_(float(self.steps))
 
     def adamw_peer(self, lr, betas, eps, weight_decay):

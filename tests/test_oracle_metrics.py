@@ -51,8 +51,9 @@ def test_edit_oracle_matches_reference_golden(golden):
         for name, value in zip(EDIT_NAMES, outputs):
             assert torch.equal(value, g[f'edit_{index}_{name}']), (index, name)
     # the frame counts of the two evaluation ratios (config/defaults.py:204)
-    assert g['edit_0_pitch'].shape[-1] == round(58 / .717) == 81
-    assert g['edit_1_pitch'].shape[-1] == round(58 / 1.414) == 41
+    # round(T / ratio + 1e-4), the count of the reference's own branch at edit/core.py:82
+    assert g['edit_0_pitch'].shape[-1] == round(57 / .717 + 1e-4) == 79
+    assert g['edit_1_pitch'].shape[-1] == round(57 / 1.414 + 1e-4) == 40
 
 
 def test_metrics_special_cases():

@@ -252,3 +252,28 @@ def test_train_entry_point_runs_saves_and_resumes(tmp_path):
     # a batch shorter than CHUNK_SIZE is skipped like train/core.py:154
     short = [(None, *oracle_train.batch(1, 8, seed=64), None)] + list(loader())
     assert train(tmp_path, loader=short, steps=4).step_count == 4
+
+
+def test_adaptation_runs_past_the_pretraining_budget(tmp_path, monkeypatch):
+    """train/core.py:111-114: with adapt_from the run lasts STEPS + ADAPTATION_STEPS, so a
+    finished checkpoint (step == STEPS) still gets its adaptation steps; the epoch counter is
+    saved and restored (:89,462)"""
+    from promonet_b200 import config
+    from promonet_b200.train import train
+    monkeypatch.setattr(config, 'STEPS', 2)
+    monkeypatch.setattr(config, 'ADAPTATION_STEPS', 1)
+    batches = [(None, *oracle_train.batch(1, 64, seed=71), None)]
+    pretrained = train(tmp_path / 'base', loader=batches)
+    assert pretrained.step_count == 2 and pretrained.epoch == 2
+    before = pretrained.generator.params.data.clone()
+    adapted = train(tmp_path / 'adapted', loader=batches, adapt_from=tmp_path / 'base')
+    assert adapted.step_count == 3
+    assert adapted.epoch == 3
+    assert adapted.generator.params.steps == 3           # the moments were resumed, not restarted
+    assert not torch.equal(adapted.generator.params.data, before)
+    checkpoint = torch.load(tmp_path / 'adapted' / 'generator-00000003.pt')
+    assert checkpoint['epoch'] == 3 and set(checkpoint['optimizer']) == {'state', 'param_groups'}
+    # a reference-side torch.optim.AdamW accepts the saved optimizer state
+    leaves = [torch.nn.Parameter(v.clone()) for k, v in checkpoint['model'].items()
+              if k in adapted.generator.params.index]
+    torch.optim.AdamW(leaves).load_state_dict(checkpoint['optimizer'])

@@ -124,3 +124,63 @@ def test_trainer_wiring_for_every_discriminator_flag(monkeypatch):
         multi_resolution_discriminator=True, spectral_convergence_loss=False)
     assert names(flagged) == ['Period'] * 5 + ['Scale'] + ['Resolution'] * 3
     assert flagged.world == 1 and flagged.generator.params.peers is None
+
+
+def test_optimizer_state_interchanges_with_torch_adamw():
+    """Checkpoints carry torch.optim.AdamW.state_dict() (torchutil.checkpoint, train/core.py:426-438):
+    a reference optimizer's state loads into the flat buffers and ours loads into a reference optimizer"""
+    from promonet_b200 import config
+    torch.manual_seed(0)
+    state = {'a.weight': torch.randn(3, 5), 'a.bias': torch.randn(3), 'b.weight_g': torch.randn(7, 1, 1)}
+    params = ParamSet(state, 'cpu')
+    leaves = [torch.nn.Parameter(v.clone()) for v in state.values()]
+    reference = torch.optim.AdamW(
+        leaves, lr=config.LEARNING_RATE, betas=config.ADAM_BETAS, eps=config.ADAM_EPS,
+        weight_decay=config.WEIGHT_DECAY)
+    for _ in range(3):
+        for leaf in leaves:
+            leaf.grad = torch.randn_like(leaf)
+        reference.step()
+    params.load_optimizer_state(reference.state_dict())
+    assert params.steps == 3 and float(params.steps_device) == 3.
+    for leaf, name in zip(leaves, state):
+        assert torch.equal(params._view(params.exp_avg, name), reference.state[leaf]['exp_avg'])
+        assert torch.equal(params._view(params.exp_avg_sq, name), reference.state[leaf]['exp_avg_sq'])
+    exported = params.optimizer_state()
+    assert exported['param_groups'][0]['lr'] == config.LEARNING_RATE
+    fresh = torch.optim.AdamW([torch.nn.Parameter(v.clone()) for v in state.values()])
+    fresh.load_state_dict(exported)                     # what torchutil.checkpoint.load does
+    for position, leaf in enumerate(fresh.param_groups[0]['params']):
+        assert torch.equal(fresh.state[leaf]['exp_avg'], reference.state[leaves[position]]['exp_avg'])
+        assert float(fresh.state[leaf]['step']) == 3.
+    # the flat layout of the first checkpoints still loads; anything else is refused loudly
+    params.load_optimizer_state({'exp_avg': params.exp_avg.clone(), 'exp_avg_sq': params.exp_avg_sq.clone(), 'step': 5})
+    assert params.steps == 5
+    with pytest.raises(ValueError):
+        params.load_optimizer_state({'moments': 1})
+    with pytest.raises(ValueError):
+        params.load_optimizer_state({'state': {}, 'param_groups': [{'params': [0]}]})
+
+
+def test_pitch_checkpoint_key_mapping():
+    """FCNF0++ checkpoints: our names, and upstream penn's Sequential-of-Sequential names
+    ([RECALLED]: `N.0.weight` conv, `N.2|3.weight` LayerNorm, `6.weight` head), mapped by
+    block index and tensor rank; anything that does not cover the network is refused"""
+    from promonet_b200.preprocess import penn
+    ours = penn.init_state(3)
+    assert all(torch.equal(v, ours[k]) for k, v in penn.convert_state(ours).items())
+    upstream = {}
+    for i in range(6):
+        norm = 3 if i < 3 else 2                        # after Conv1d, ReLU (, MaxPool1d)
+        upstream[f'{i}.0.weight'] = ours[f'layers.{i}.conv.weight']
+        upstream[f'{i}.0.bias'] = ours[f'layers.{i}.conv.bias']
+        upstream[f'{i}.{norm}.weight'] = ours[f'layers.{i}.norm.weight']
+        upstream[f'{i}.{norm}.bias'] = ours[f'layers.{i}.norm.bias']
+    upstream['6.weight'], upstream['6.bias'] = ours['layers.6.weight'], ours['layers.6.bias']
+    for prefix in ('', 'module.'):
+        mapped = penn.convert_state({prefix + k: v for k, v in upstream.items()})
+        assert list(mapped) == list(ours)
+        assert all(torch.equal(mapped[k], ours[k]) for k in ours)
+    del upstream['4.2.bias']
+    with pytest.raises(ValueError):
+        penn.convert_state(upstream)
