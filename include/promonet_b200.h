@@ -260,6 +260,11 @@ int pmn_conv1d_tc(
  * parity entry point.  out and accum (same modes as pmn_conv1d) must not alias x.
  * Bit-identical to pmn_conv1d_tc applied twice. */
 size_t pmn_conv_pair_tc_workspace_bytes(int channels, int k);
+/* Profiling aid: while `counters` (device, 148 x 10 x 4 int64) is non-NULL every fused-pair
+ * launch stores per-warp-role cycle counters there; `variant` >= 0 selects a kernel variant
+ * (converter warps / mid-image buffers) for experiments, -1 the default.  Results do not
+ * depend on the variant. */
+void pmn_debug_pair_tc(void* counters, int variant);
 int pmn_conv_pair_tc(
     const float* x, const float* weight1, const float* bias1, const float* weight2,
     const float* bias2, float* out, float* accum, int accum_mode, float accum_scale,

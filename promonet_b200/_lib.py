@@ -100,6 +100,7 @@ SIGNATURES = {
          c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
          c_float, c_float, c_void_p, c_size_t, c_void_p]),
     'pmn_conv_pair_tc_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'pmn_debug_pair_tc': (None, [c_void_p, c_int]),
     'pmn_conv_pair_tc': (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,

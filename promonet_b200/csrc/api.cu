@@ -399,6 +399,10 @@ int pmn_conv1d_tc_general(
     return PMN_OK;
 }
 
+void pmn_debug_pair_tc(void* counters, int variant) {
+    tc_pair_set_debug(static_cast<long long*>(counters), variant);
+}
+
 size_t pmn_conv_pair_tc_workspace_bytes(int channels, int k) {
     if (channels <= 0 || k <= 0) return 0;
     return 2 * align_up(tc_weight_elements(channels, channels, k) * sizeof(__nv_bfloat16), 256);

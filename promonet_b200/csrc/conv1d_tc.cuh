@@ -95,6 +95,10 @@ int launch_conv_pair_tc(
     const float* bias2, float* out, float* accum, int accum_mode, float accum_scale,
     int batch, int channels, int t_len, int k, int dilation, float slope, cudaStream_t stream);
 
+// Profiling aid: per-CTA cycle counters of every following pair launch (null = off) and the
+// kernel variant to launch (-1 = default)
+void tc_pair_set_debug(long long* counters, int variant);
+
 // folded fp32 weight (C_out, C_in, K) -> hi/lo slabs
 int launch_pack_tc_weight(
     const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, bool frames, cudaStream_t stream);

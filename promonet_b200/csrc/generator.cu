@@ -28,9 +28,13 @@ constexpr int kUpRate[kStages] = {8, 8, 2, 2};      // :262
 constexpr int kResKernel[3] = {3, 7, 11};           // :250
 constexpr int kResDilation[3] = {1, 3, 5};          // :253
 constexpr float kSlope = 0.1f;                      // :216
-// Which residual blocks take the fused pair kernel by default: the HBM-bound ones
-// (profiles/r2_pair_selection.txt); bit 3 * stage + block, block = kernel 3 / 7 / 11
-constexpr unsigned kDefaultPairMask = 0xFF8u;       // stages 1-3 (C = 128, 64, 32), all kernels
+// Which residual blocks take the fused pair kernel by default; bit 3 * stage + block, block =
+// kernel 3 / 7 / 11.  Measured on B200 (profiles/r2_pair_breakdown.txt, r2_pair_selection*.txt):
+// these convolutions are bound by the tensor pipe's operand fetch from shared memory (105-145
+// cycles per M128 MMA), not by HBM, so keeping the pair on chip only pays where the two-launch
+// path is HBM-bound: the k = 3 block of stage 1 (C = 128), +1 % of the step.  Everything else
+// is faster as two launches (larger tiles, half the weight streaming, no converter traffic).
+constexpr unsigned kDefaultPairMask = 0x008u;
 
 
 struct PackedConv {
