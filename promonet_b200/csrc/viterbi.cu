@@ -37,7 +37,7 @@ __host__ __device__ inline int cluster_slice(int states) {
 // floats of shared memory the fast path needs for a given band width
 __host__ __device__ inline size_t cluster_floats(int states, int max_width) {
     const int slice = cluster_slice(states);
-    return (size_t)max_width * (slice | 1) + 2 * (size_t)slice + (size_t)kClusterSize * slice;
+    return (size_t)max_width * (slice | 1) + 2 * (size_t)kClusterSize * slice;
 }
 
 
@@ -195,8 +195,11 @@ viterbi_cluster_kernel(
 
     extern __shared__ float smem[];
     float* band_s = smem;                        // [max_width][pitch]
-    float* mine = band_s + (size_t)max_width * pitch;  // [2][slice] scores of my states
-    float* full = mine + 2 * slice;              // [kClusterSize * slice] gathered scores
+    // every CTA keeps the WHOLE score vector of the previous and of the current frame: a CTA
+    // publishes its slice of the new scores straight into all eight copies (distributed
+    // shared memory stores), so a frame costs one cluster barrier and no gather
+    const int whole = kClusterSize * slice;
+    float* full = band_s + (size_t)max_width * pitch;   // [2][whole]
 
     const int j0 = rank * slice;
     const int length = batch_frames ? min(batch_frames[b], frames) : frames;
@@ -210,35 +213,46 @@ viterbi_cluster_kernel(
     }
     const int jl = tid / kSplit, part = tid % kSplit;
     const int j = j0 + jl;
-    const bool owner = jl < slice && j < states;
+    const bool mine = jl < slice;                // this thread group holds a (possibly padded) state
+    const bool owner = mine && j < states;
     int first = 0, count = 0;
     if (owner) { first = lo[j]; count = width[j]; }
     const int chunk = (count + kSplit - 1) / kSplit;
     const int begin = min(part * chunk, count), end = min(begin + chunk, count);
+    // the kSplit threads of a state share the publishing: thread `part` writes the copies of
+    // CTAs part * (kClusterSize / kSplit) ...
+    constexpr int kPeersPerThread = kClusterSize / kSplit;
+    float* copies[kPeersPerThread];
+#pragma unroll
+    for (int i = 0; i < kPeersPerThread; ++i)
+        copies[i] = cluster.map_shared_rank(full, part * kPeersPerThread + i) + j0 + jl;
+    auto load_observation = [&](int t) {
+        if (!owner || t >= length) return 0.f;
+        const float o = obs[(size_t)t * states + j];
+        return log_probs ? o : logf(o);
+    };
 
-    if (owner && part == 0) {
-        const float o = log_probs ? obs[j] : logf(obs[j]);
-        const float p = log_probs ? initial[j] : logf(initial[j]);
-        mine[jl] = p + o;
-    } else if (jl < slice && part == 0) {
-        mine[jl] = -INFINITY;
+    if (mine) {
+        float score = -INFINITY;                 // padded states never win
+        if (owner) score = (log_probs ? initial[j] : logf(initial[j])) + load_observation(0);
+#pragma unroll
+        for (int i = 0; i < kPeersPerThread; ++i) {
+            copies[i][0] = score;
+            copies[i][whole] = -INFINITY;
+        }
     }
+    float next_observation = load_observation(1);    // one frame ahead of its use
     cluster.sync();
 
     int current = 0;
     for (int t = 1; t < max(length, 1); ++t) {
-        // gather the previous scores of every CTA of the cluster
-        for (int idx = tid; idx < kClusterSize * slice; idx += kClusterThreads) {
-            const int peer = idx / slice;
-            const float* remote = cluster.map_shared_rank(mine + current * slice, peer);
-            full[idx] = remote[idx % slice];
-        }
-        __syncthreads();
+        const float observed = next_observation;
+        next_observation = load_observation(t + 1);
         float best = -INFINITY;
         int arg = 0x7fffffff;
         if (owner) {
             const float* column = band_s + jl;
-            const float* source = full + first;
+            const float* source = full + current * whole + first;
             for (int k = begin; k < end; ++k) {
                 const float value = source[k] + column[k * pitch];
                 if (value > best) { best = value; arg = first + k; }
@@ -251,42 +265,35 @@ viterbi_cluster_kernel(
             const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
             if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
         }
-        if (owner && part == 0) {
-            const float o = log_probs ? obs[(size_t)t * states + j] : logf(obs[(size_t)t * states + j]);
-            mine[(current ^ 1) * slice + jl] = best + o;
-            back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
+        if (owner) {
+            const float score = best + observed;
+#pragma unroll
+            for (int i = 0; i < kPeersPerThread; ++i) copies[i][(current ^ 1) * whole] = score;
+            if (part == 0) back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
         }
         current ^= 1;
-        cluster.sync();  // new scores visible cluster-wide; everyone is done reading the old ones
+        // the new scores are visible in every copy; everyone is done reading the old ones, which
+        // the frame after this one overwrites
+        cluster.sync();
     }
 
-    // final argmax and backtrace on the first CTA of the cluster
+    // final argmax and backtrace on the first CTA of the cluster (it holds the whole vector)
     __threadfence();
     cluster.sync();
-    if (rank == 0) {
-        for (int idx = tid; idx < kClusterSize * slice; idx += kClusterThreads) {
-            const int peer = idx / slice;
-            const float* remote = cluster.map_shared_rank(mine + current * slice, peer);
-            full[idx] = (peer * slice + idx % slice) < states ? remote[idx % slice] : -INFINITY;
+    if (rank == 0 && tid == 0) {
+        const float* last = full + current * whole;
+        int state = 0;
+        float best = -INFINITY;
+        if (length > 0) {
+            for (int k = 0; k < whole; ++k)
+                if (k < states && last[k] > best) { best = last[k]; state = k; }
         }
-        __syncthreads();
-        if (tid == 0) {
-            int state = 0;
-            float best = -INFINITY;
-            if (length > 0) {
-                for (int k = 0; k < kClusterSize * slice; ++k) {
-                    const int global = (k / slice) * slice + k % slice;  // = k: slices are contiguous
-                    if (global < states && full[k] > best) { best = full[k]; state = global; }
-                }
-            }
-            for (int t = length - 1; t >= 0; --t) {
-                path[t] = state;
-                if (t > 0) state = back[(size_t)t * states + state];
-            }
-            for (int t = max(length, 0); t < frames; ++t) path[t] = 0;
+        for (int t = length - 1; t >= 0; --t) {
+            path[t] = state;
+            if (t > 0) state = back[(size_t)t * states + state];
         }
+        for (int t = max(length, 0); t < frames; ++t) path[t] = 0;
     }
-    cluster.sync();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 struct Workspace {
