@@ -364,10 +364,20 @@ def synthesis(ctx):
         ms = ctx.timed(resident, args.steps)
     launches = _lib.launch_count() - launches_before
 
-    # End to end: host buffers in, host audio out, copies inside the timed region
+    # End to end: host buffers in, host audio out, every step's copies inside the timed
+    # region.  stream_host pipelines them (the D2H of step i and the H2D of step i + 1 overlap
+    # the synthesis of step i + 1); forward_host is the same call made synchronously
+    def streamed():
+        for audio in model.stream_host(host for _ in range(args.steps)):
+            last = audio
+        return last
+
     for _ in range(2):
         end_to_end()
-    e2e_seconds = ctx.wall(end_to_end, args.steps)
+    for _ in model.stream_host(host for _ in range(3)):
+        pass
+    e2e_seconds = ctx.wall(streamed, 1)
+    e2e_synchronous_seconds = ctx.wall(end_to_end, args.steps)
 
     # Roofline of the dominant kernel: same steps again with per-launch CUDA events
     dominant = 'conv1d_kernel' if math == _lib.MATH_FP32_SIMT else 'conv1d_tc_kernel'
@@ -406,7 +416,10 @@ def synthesis(ctx):
             'value': total_samples / e2e_seconds, 'unit': UNIT,
             'h2d_bytes_per_step': sum(t.numel() * t.element_size() for t in host),
             'd2h_bytes_per_step': audio_host.numel() * 4,
-            'api': 'promonet_b200.model.Generator.forward_host -> pmn_generator_forward_host'},
+            'api': 'promonet_b200.model.Generator.stream_host (pinned host batches in, pinned host audio '
+                   'out; copies on their own streams overlap the next step\'s kernels)',
+            'synchronous_value': total_samples / e2e_synchronous_seconds,
+            'synchronous_api': 'promonet_b200.model.Generator.forward_host -> pmn_generator_forward_host'},
         'roofline': {
             'bound': 'tensor',
             'kernel': dominant + (' + conv_pair_tc_kernel (the residual-block convolutions)'
@@ -740,6 +753,40 @@ def gpu_eager_baseline(ctx):
         result['modes'][name] = {
             'ms_per_step': ms, 'value': BATCH * SAMPLES / (ms * 1e-3),
             'error_vs_fp32': relative_error(audio, exact)}
+    del model, batch
+    torch.cuda.empty_cache()
+    # the training step (configs[3]) the same way: the reference's loop body, its modules,
+    # losses and optimizers; fp16 autocast + GradScaler is how the reference trains
+    from promonet_b200 import synthetic
+    *inputs, audio = synthetic.training(TRAIN_BATCH, TRAIN_FRAMES, 1234)
+    audio = audio.to(ctx.device)
+    with torch.no_grad():
+        spectrograms = promonet.preprocess.spectrogram.from_audio(audio)
+    batch = [t.to(ctx.device) for t in inputs] + [spectrograms, audio]
+    result['train'] = {
+        'what': f'promonet/train/core.py:183-369 composed from the reference modules on cuda, '
+                f'{TRAIN_BATCH} items x 16 384 samples', 'unit': 'items/s', 'modes': {}}
+    for name, tf32, autocast in (('fp32', False, False), ('tf32', True, False), ('fp16_autocast', True, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            step = reference.TrainingStep(promonet, ctx.device, autocast)
+            for _ in range(2):
+                step(*batch)
+            torch.cuda.synchronize()
+            start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
+            start.record()
+            for _ in range(3):
+                loss = step(*batch)
+            stop.record()
+            torch.cuda.synchronize()
+            ms = start.elapsed_time(stop) / 3
+            result['train']['modes'][name] = {
+                'ms_per_step': ms, 'value': TRAIN_BATCH / (ms * 1e-3), 'generator_loss': float(loss)}
+            del step
+        except Exception as error:
+            result['train']['modes'][name] = {'error': repr(error)[:200]}
+        torch.cuda.empty_cache()
     return result
 
 

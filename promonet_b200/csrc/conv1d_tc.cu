@@ -607,6 +607,8 @@ bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
         {128, 256, false, {32, 256, false}}, {256, 512, true, {32, 256, false}},
         // block 0 as a 32-"channel" (tap) 1x1 conv over im2col rows; head 2048 -> 1440
         {32, 256, false, {32, 256, false}},  {2048, 1440, false, {64, 160, false}},
+        // penn block 1 folded by 4 in time (pitch.cu): 1024 -> 128, k = 9
+        {1024, 128, false, {64, 128, false}},
     };
     for (const Entry& entry : table) {
         if (entry.c_in == c_in && entry.c_out == c_out && entry.frames == frames) {
@@ -645,6 +647,7 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 128) return launch_variant<32, 128, 2, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
+    if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2>(a, 1, stream);
     return launch_variant<128, 256, 1, 32, 4, 2>(a, 1, stream);
 }
 

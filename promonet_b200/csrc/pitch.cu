@@ -13,6 +13,14 @@
 // straddle two frames are computed and dropped by the pooling / LayerNorm kernel.
 // The last block writes its (512, 4) activations transposed so that the final
 // layer is a dense 2048 -> 1440 product over all frames (conv1d with k = 1).
+//
+// Block 1 (256 -> 32 channels, k = 32: 60 % of the network's FLOPs) has only 32 output
+// columns, a quarter of what one M = 128 MMA needs to amortise its A-operand fetch.  On the
+// tensor-core path it runs "folded by 4" in time instead: four consecutive samples become
+// four channel groups (x4[t4, (p, c)] = x[4 t4 + p, c], 1024 channels) and four consecutive
+// outputs become four column groups (y4[t4, (q, o)] = y[4 t4 + q, o], 128 columns) of a
+// 9-tap convolution with the block-Toeplitz weight W4[(q, o), (p, c), J] = W[o, c, 4 J + p - q]
+// (zero outside 0..31): 12.5 % more multiply-adds, all of them at full tensor rate.
 #include <math.h>
 
 #include <map>
@@ -41,6 +49,15 @@ constexpr bool kPooled[kLayers] = {true, true, true, false, false, false};
 constexpr int kLength[kLayers + 1] = {993, 481, 225, 97, 66, 35, 4};  // per-frame length after block i
 constexpr float kCentsPerBin = 5.f, kFmin = 31.f, kOctave = 1200.f;
 constexpr int kLocalWindow = 19;
+constexpr int kFold = 4;                       // block 1 on the tensor cores: folded by 4 in time
+constexpr int kFoldTaps = 9;                   // ceil((32 + 3) / 4)
+constexpr int kFoldStride = 484;               // block 1's frame stride: a multiple of 4 >= 481
+// Block 0 on the tensor-core path takes its own operand buffer (im2col rows) and runs in
+// sub-chunks of at most kSubFrames frames.  Measured (profiles/r2_preprocess_history.txt):
+// sub-chunks small enough for the convolution output to stay in L2 (95 frames, 48 MB) make
+// the LayerNorm pass 20 % faster but cost more than that in per-launch overheads (296
+// instead of 14 launches of each kernel), so the sub-chunk is the whole default frame batch
+constexpr int kSubFrames = 2048;
 
 }  // namespace
 
@@ -58,6 +75,7 @@ struct pmn_pitch {
     float* head_weight = nullptr;            // packed (2048, 1, 1440)
     __nv_bfloat16* head_slabs = nullptr;     // tensor-core path
     const float* head_bias = nullptr;
+    const float* folded_bias = nullptr;      // block 1 folded by 4: bias of column (q, o)
     // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
     struct Resampler { float* table; int orig, fresh, width; };
     std::map<int, Resampler> resamplers;
@@ -173,19 +191,30 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(
 __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
-    int count, int t_pad, bool transposed, int stride_out) {
+    int count, int t_pad, bool transposed, int stride_out, bool fold_out, bool fold_in, int frame_base) {
     __shared__ double partial[2][8];
     __shared__ float stats[2];
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
     const int groups = channels / 8;
+    const int g_begin = 0, g_end = groups;
+    // fold_out: the operand of a convolution folded by 4 in time: sample t of channel group g
+    // is row t / 4 of group (t % 4) * groups + g, and a frame has stride_out / 4 rows
+    const int plane_groups = fold_out ? 4 * groups : groups;
     uint4* hi_plane = reinterpret_cast<uint4*>(planes);
-    uint4* lo_plane = hi_plane + (size_t)groups * t_pad;
+    uint4* lo_plane = hi_plane + (size_t)plane_groups * t_pad;
+    // frame f of this launch is frame frame_base + f of the operand being written
+    auto plane_row = [&](int g, int t) {
+        const size_t frame = (size_t)(frame_base + f);
+        if (fold_out)
+            return (size_t)((t & 3) * groups + g) * t_pad + kTcPad + frame * (stride_out >> 2) + (t >> 2);
+        return (size_t)g * t_pad + kTcPad + frame * stride_out + t;
+    };
     // rows [l_out, stride_out) of a frame and whole frames >= count are zero padding
-    for (int idx = tid; idx < groups * stride_out; idx += blockDim.x) {
+    for (int idx = tid; idx < (g_end - g_begin) * stride_out; idx += blockDim.x) {
         const int t = idx % stride_out;
         if (!transposed && (f >= count || t >= l_out)) {
-            const size_t row = (size_t)(idx / stride_out) * t_pad + kTcPad + (size_t)f * stride_out + t;
+            const size_t row = plane_row(g_begin + idx / stride_out, t);
             hi_plane[row] = make_uint4(0, 0, 0, 0);
             lo_plane[row] = make_uint4(0, 0, 0, 0);
         }
@@ -194,6 +223,12 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const int total = channels * l_out;
     const float* base = in + (size_t)f * l_in;
     auto value = [&](int c, int t) {
+        if (fold_in) {
+            // output of a folded convolution, not yet pooled: sample 4 t4 + q of channel c is
+            // row t4 of column q * channels + c; MaxPool(2) pairs q = 0 | 1 and q = 2 | 3
+            const float* row = base + (size_t)((t & 1) * 2 * channels + c) * in_row + (t >> 1);
+            return fmaxf(row[0], row[(size_t)channels * in_row]);
+        }
         const float* row = base + (size_t)c * in_row;
         return pooled ? fmaxf(row[2 * t], row[2 * t + 1]) : row[t];
     };
@@ -256,30 +291,46 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
         }
         return;
     }
-    for (int g = warp; g < groups; g += 8) {
-        for (int t = lane; t < l_out; t += 32) {
-            float y[8];
+    for (int idx = tid; idx < (g_end - g_begin) * l_out; idx += blockDim.x) {
+        const int g = g_begin + idx / l_out, t = idx % l_out;
+        float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = value(g * 8 + e, t);   // 8 independent loads
-            unsigned int hi[4], lo[4];
+        for (int e = 0; e < 8; ++e) y[e] = value(g * 8 + e, t);   // 8 independent loads
+        unsigned int hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float z[2];
+        for (int e = 0; e < 4; ++e) {
+            float z[2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = g * 8 + 2 * e + h;
-                    z[h] = (y[2 * e + h] - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
-                }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
-                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            for (int h = 0; h < 2; ++h) {
+                const int c = g * 8 + 2 * e + h;
+                z[h] = (y[2 * e + h] - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
             }
-            const size_t row = (size_t)g * t_pad + kTcPad + (size_t)f * stride_out + t;
-            hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
+            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
         }
+        const size_t row = plane_row(g, t);
+        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// Block 1's weight (32, 256, 32) as the weight (128, 1024, 9) of the convolution folded by 4
+// in time: W4[(q, o), (p, c), J] = W[o, c, 4 J + p - q], zero where that tap does not exist
+__global__ void fold_weight_kernel(const float* __restrict__ w, float* __restrict__ folded) {
+    constexpr int kOut = 32, kIn = 256, kFold = 4, kTaps = (kKernel + kFold - 1) / kFold + 1;
+    const int total = kFold * kOut * kFold * kIn * kTaps;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int rest = idx;
+        const int J = rest % kTaps; rest /= kTaps;
+        const int c = rest % kIn; rest /= kIn;
+        const int pp = rest % kFold; rest /= kFold;
+        const int o = rest % kOut; rest /= kOut;
+        const int q = rest;
+        const int j = kFold * J + pp - q;
+        folded[idx] = (j >= 0 && j < kKernel) ? w[((size_t)o * kIn + c) * kKernel + j] : 0.f;
     }
 }
 
@@ -456,7 +507,7 @@ int resampler(pmn_pitch* p, int sample_rate, const pmn_pitch::Resampler** out) {
 
 struct Workspace {
     float *resampled, *conv, *act, *logits_t, *masked, *distribution;
-    __nv_bfloat16* planes;
+    __nv_bfloat16 *planes, *planes0;
     int* bins;
     void* viterbi;
     size_t viterbi_bytes, bytes;
@@ -476,7 +527,12 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     w.conv = (float*)take(fb * 256 * (kCropped + 1) * 4);                 // largest conv output (layer 0)
     w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
     // tensor-core operand planes: the widest is block 0's output (256 channels x 481 rows per frame)
-    w.planes = (__nv_bfloat16*)take(tc_planes_elements(1, 256, (int)(fb + 16) * 482) * 2);
+    w.planes = (__nv_bfloat16*)take(std::max(
+        tc_planes_elements(1, 256, (int)(fb + 16) * 482),
+        tc_planes_elements(1, kFold * 256, (int)(fb + 16) * (kFoldStride / kFold))) * 2);
+    // block 0's own operand (im2col rows of a sub-chunk of frames, 32 "channels")
+    w.planes0 = (__nv_bfloat16*)take(
+        tc_planes_elements(1, kKernel, (int)std::min<size_t>(kSubFrames, fb) * (kCropped + 1)) * 2);
     w.logits_t = (float*)take(fb * kBins * 4);
     w.masked = (float*)take(total * kBins * 4);
     w.distribution = (float*)take(total * kBins * 4);
@@ -517,6 +573,33 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
             float* slabs;  // bf16 hi + lo = the bytes of the fp32 tensor
             PMN_TRY(alloc(p, w->numel(), &slabs));
             p->conv_slabs[i] = reinterpret_cast<__nv_bfloat16*>(slabs);
+            if (i == 1) {
+                // folded by 4: (32, 256, 32) -> (128, 1024, 9), 12.5 % zeros
+                const size_t folded_numel = (size_t)kFold * 32 * kFold * 256 * kFoldTaps;
+                float *folded, *folded_slabs;
+                PMN_TRY(alloc(p, folded_numel, &folded));
+                PMN_TRY(alloc(p, folded_numel, &folded_slabs));
+                {
+                    LaunchScope scope("fold_weight_kernel", stream);
+                    fold_weight_kernel<<<1024, 256, 0, stream>>>(w->data, folded);
+                    PMN_TRY(launched("fold_weight_kernel"));
+                }
+                p->conv_slabs[i] = reinterpret_cast<__nv_bfloat16*>(folded_slabs);
+                PMN_TRY(launch_pack_tc_weight(
+                    folded, p->conv_slabs[i], kFold * 32, kFold * 256, kFoldTaps, false, stream));
+                // the bias of column (q, o) is the bias of channel o
+                float* bias4;
+                PMN_TRY(alloc(p, kFold * 32, &bias4));
+                for (int q = 0; q < kFold; ++q)
+                    PMN_TRY(check_cuda(
+                        cudaMemcpyAsync(bias4 + q * 32, b->data, 32 * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, stream), "fold bias"));
+                p->folded_bias = bias4;
+                p->conv_bias[i] = b->data;
+                p->norm_weight[i] = nw->data;
+                p->norm_bias[i] = nb->data;
+                continue;
+            }
             // block 0: (256, 1, 32) is read as a (256, 32, 1) 1x1 conv over the 32 taps
             PMN_TRY(launch_pack_tc_weight(
                 w->data, p->conv_slabs[i], kChannels[i + 1], i == 0 ? kKernel : kChannels[i],
@@ -608,36 +691,74 @@ int pitch_forward(
         const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
         // Tensor-core path: frame strides are even where a MaxPool follows, so pooling
         // pairs never straddle two frames and the conv epilogue can pool adjacent lanes
-        auto stride_of = [&](int i) { return tensor_cores && i < 3 ? kLength[i] + 1 : kLength[i]; };
-        {
+        auto stride_of = [&](int i) {
+            if (tensor_cores && i == 1) return kFoldStride;
+            return tensor_cores && i < 3 ? kLength[i] + 1 : kLength[i];
+        };
+        if (!tensor_cores) {
             const int stride = stride_of(0);
             dim3 grid(ceil_div(stride, 256), count);
             LaunchScope scope("frames_kernel", stream);
             frames_kernel<<<grid, 256, 0, stream>>>(
                 audio8k, w.act, out_samples, frames, first, count, hop, padding, stride);
             PMN_TRY(launched("frames_kernel"));
+        } else {
+            // Block 0, a sub-chunk of frames at a time (kSubFrames): frames -> im2col operand ->
+            // 1x1 convolution over the 32 taps (ReLU + MaxPool in its epilogue) -> LayerNorm ->
+            // block 1's folded operand, at the sub-chunk's place in the chunk's operand
+            const int stride = stride_of(0), stride_next = stride_of(1);
+            const int t_next = count * (stride_next / kFold);
+            PMN_TRY(launch_zero_plane_pads(w.planes, 1, kFold * kChannels[1], t_next, stream));
+            for (int sub = 0; sub < count; sub += kSubFrames) {
+                const int n = std::min(kSubFrames, count - sub);
+                {
+                    dim3 grid(ceil_div(stride, 256), n);
+                    LaunchScope scope("frames_kernel", stream);
+                    frames_kernel<<<grid, 256, 0, stream>>>(
+                        audio8k, w.act, out_samples, frames, first + sub, n, hop, padding, stride);
+                    PMN_TRY(launched("frames_kernel"));
+                }
+                const size_t conv_rows = (size_t)n * stride - (kKernel - 1);
+                const int t_pad = tc_padded_length((int)conv_rows);
+                {
+                    dim3 grid(ceil_div(t_pad, 128), 4);
+                    LaunchScope scope("im2col_planes_kernel", stream);
+                    im2col_planes_kernel<<<grid, 128, 0, stream>>>(
+                        w.act, w.planes0, n * stride, (int)conv_rows, t_pad);
+                    PMN_TRY(launched("im2col_planes_kernel"));
+                }
+                TcConvArgs a;
+                a.x_planes = w.planes0; a.w_slabs = p->conv_slabs[0]; a.bias = p->conv_bias[0];
+                a.out = w.conv; a.batch = 1; a.c_in = kKernel; a.c_out = kChannels[1]; a.k = 1;
+                a.t_len = (int)conv_rows; a.valid = true; a.relu = true; a.pool = true;
+                a.out_row = (int)(conv_rows / 2);
+                PMN_TRY(launch_conv1d_tc(a, stream));
+                LaunchScope scope("pool_norm_planes_kernel", stream);
+                pool_norm_planes_kernel<<<n, 256, 0, stream>>>(
+                    w.conv, p->norm_weight[0], p->norm_bias[0], w.planes, kChannels[1], stride / 2,
+                    kLength[1], false, conv_rows / 2, n, tc_padded_length(t_next), false, stride_next,
+                    true, false, sub);
+                PMN_TRY(launched("pool_norm_planes_kernel"));
+            }
         }
         const int padded = (count + 15) / 16 * 16;  // frame-mode tiles cover 16 frames
-        for (int i = 0; i < kLayers; ++i) {
+        for (int i = tensor_cores ? 1 : 0; i < kLayers; ++i) {
             const int l_in = stride_of(i);                       // frame stride of the input rows
-            const size_t conv_rows = (size_t)count * l_in - (kKernel - 1);
-            const bool pool_in_conv = tensor_cores && kPooled[i];
+            const bool folded = tensor_cores && i == 1;          // block 1: folded by 4 in time
+            const size_t conv_rows = folded ? (size_t)count * (l_in / kFold) - (kFoldTaps - 1)
+                                            : (size_t)count * l_in - (kKernel - 1);
+            const bool pool_in_conv = tensor_cores && kPooled[i] && !folded;
             const size_t row = pool_in_conv ? conv_rows / 2 : conv_rows;  // row length of w.conv
-            const int l_conv = pool_in_conv ? l_in / 2 : l_in;   // frame stride inside w.conv
+            // frame stride inside w.conv
+            const int l_conv = folded ? l_in / kFold : pool_in_conv ? l_in / 2 : l_in;
             if (tensor_cores) {
                 TcConvArgs a;
                 a.x_planes = w.planes; a.w_slabs = p->conv_slabs[i]; a.bias = p->conv_bias[i];
                 a.out = w.conv; a.batch = 1; a.c_out = kChannels[i + 1];
                 a.valid = true; a.relu = true; a.pool = pool_in_conv; a.out_row = (int)row;
-                if (i == 0) {
-                    // 32 taps as 32 channels of a 1x1 conv over im2col rows of the frame buffer
-                    const int t_pad = tc_padded_length((int)conv_rows);
-                    dim3 grid(ceil_div(t_pad, 128), 4);
-                    LaunchScope scope("im2col_planes_kernel", stream);
-                    im2col_planes_kernel<<<grid, 128, 0, stream>>>(
-                        w.act, w.planes, count * l_in, (int)conv_rows, t_pad);
-                    PMN_TRY(launched("im2col_planes_kernel"));
-                    a.c_in = kKernel; a.k = 1; a.t_len = (int)conv_rows;
+                if (folded) {
+                    a.c_in = kFold * kChannels[i]; a.c_out = kFold * kChannels[i + 1];
+                    a.k = kFoldTaps; a.t_len = count * (l_in / kFold); a.bias = p->folded_bias;
                 } else {
                     a.c_in = kChannels[i]; a.k = kKernel; a.t_len = count * l_in;
                 }
@@ -658,12 +779,15 @@ int pitch_forward(
                 // the next block runs on the tensor cores: write its operand planes
                 const int stride_next = stride_of(i + 1);
                 const int frames_out = i + 1 == kLayers - 1 ? padded : count;
-                const int t_next = frames_out * stride_next;
-                PMN_TRY(launch_zero_plane_pads(w.planes, 1, kChannels[i + 1], t_next, stream));
+                const bool fold_next = i + 1 == 1;           // the next block reads the folded layout
+                const int t_next = fold_next ? frames_out * (stride_next / kFold) : frames_out * stride_next;
+                PMN_TRY(launch_zero_plane_pads(
+                    w.planes, 1, fold_next ? kFold * kChannels[i + 1] : kChannels[i + 1], t_next, stream));
                 LaunchScope scope("pool_norm_planes_kernel", stream);
                 pool_norm_planes_kernel<<<frames_out, 256, 0, stream>>>(
                     w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_conv,
-                    kLength[i + 1], false, row, count, tc_padded_length(t_next), false, stride_next);
+                    kLength[i + 1], false, row, count, tc_padded_length(t_next), false, stride_next,
+                    fold_next, folded, 0);
                 PMN_TRY(launched("pool_norm_planes_kernel"));
             } else if (tensor_cores) {
                 // last block: (512, 4) per frame becomes one 2048-channel row of the head's operand
@@ -671,7 +795,8 @@ int pitch_forward(
                 LaunchScope scope("pool_norm_planes_kernel", stream);
                 pool_norm_planes_kernel<<<count, 256, 0, stream>>>(
                     w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_conv,
-                    kLength[i + 1], false, row, count, tc_padded_length(count), true, kLength[i + 1]);
+                    kLength[i + 1], false, row, count, tc_padded_length(count), true, kLength[i + 1],
+                    false, false, 0);
                 PMN_TRY(launched("pool_norm_planes_kernel"));
             } else {
                 LaunchScope scope("pool_norm_kernel", stream);

@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 
 #include "spectral.cuh"
+#include "tc_ptx.cuh"
 
 namespace pmn {
 
@@ -195,11 +196,17 @@ viterbi_cluster_kernel(
 
     extern __shared__ float smem[];
     float* band_s = smem;                        // [max_width][pitch]
-    // every CTA keeps the WHOLE score vector of the previous and of the current frame: a CTA
-    // publishes its slice of the new scores straight into all eight copies (distributed
-    // shared memory stores), so a frame costs one cluster barrier and no gather
+    // every CTA keeps the WHOLE score vector of the previous and of the current frame.  A CTA
+    // publishes each new score straight into all eight copies with st.async (a remote
+    // shared-memory store that reports its bytes to an mbarrier of the destination CTA), so a
+    // frame needs no cluster barrier and no fence: a CTA starts frame t + 1 as soon as the
+    // transaction barrier of frame t has counted the bytes of all `states` scores.  The two
+    // buffers cannot be overwritten early: nobody can finish frame t + 1 (and write into the
+    // buffer frame t was computed from) before every CTA has sent all its frame-t scores,
+    // i.e. has finished reading that buffer.
     const int whole = kClusterSize * slice;
     float* full = band_s + (size_t)max_width * pitch;   // [2][whole]
+    __shared__ uint64_t landed[2];                      // landed[p]: scores of a frame of parity p
 
     const int j0 = rank * slice;
     const int length = batch_frames ? min(batch_frames[b], frames) : frames;
@@ -211,10 +218,15 @@ viterbi_cluster_kernel(
         const int k = idx / slice, jl = idx % slice;
         band_s[k * pitch + jl] = j0 + jl < states ? band[(size_t)k * states + j0 + jl] : -INFINITY;
     }
+    for (int idx = tid; idx < 2 * whole; idx += kClusterThreads) full[idx] = -INFINITY;  // padded states
+    if (tid == 0) {
+        tc::mbar_init(landed, 1);
+        tc::mbar_init(landed + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int jl = tid / kSplit, part = tid % kSplit;
     const int j = j0 + jl;
-    const bool mine = jl < slice;                // this thread group holds a (possibly padded) state
-    const bool owner = mine && j < states;
+    const bool owner = jl < slice && j < states;
     int first = 0, count = 0;
     if (owner) { first = lo[j]; count = width[j]; }
     const int chunk = (count + kSplit - 1) / kSplit;
@@ -222,27 +234,41 @@ viterbi_cluster_kernel(
     // the kSplit threads of a state share the publishing: thread `part` writes the copies of
     // CTAs part * (kClusterSize / kSplit) ...
     constexpr int kPeersPerThread = kClusterSize / kSplit;
-    float* copies[kPeersPerThread];
+    uint32_t copies[kPeersPerThread], barriers[kPeersPerThread];   // shared::cluster addresses
 #pragma unroll
-    for (int i = 0; i < kPeersPerThread; ++i)
-        copies[i] = cluster.map_shared_rank(full, part * kPeersPerThread + i) + j0 + jl;
+    for (int i = 0; i < kPeersPerThread; ++i) {
+        const uint32_t peer = part * kPeersPerThread + i;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(copies[i]) : "r"(tc::smem_u32(full + j0 + jl)), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(barriers[i]) : "r"(tc::smem_u32(landed)), "r"(peer));
+    }
+    // score of frame t (parity t & 1) into every copy
+    auto publish = [&](float score, int parity) {
+#pragma unroll
+        for (int i = 0; i < kPeersPerThread; ++i)
+            asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+                         ::"r"(copies[i] + (uint32_t)(parity * whole) * 4u), "r"(__float_as_uint(score)),
+                           "r"(barriers[i] + (uint32_t)parity * 8u) : "memory");
+    };
+    // all `states` scores of frame t have landed in this CTA's copy.  Only the threads that
+    // read the scores wait (a thread that reads nothing could otherwise still be polling for
+    // frame t when the same barrier completes frame t + 2; a reader cannot lag that far,
+    // because frame t + 2 cannot complete anywhere without its frame t + 1 score)
+    auto await = [&](int t) {
+        if (tid == 0) tc::mbar_expect_tx(landed + (t & 1), (uint32_t)states * 4u);
+        if (owner || tid == 0) tc::mbar_wait(landed + (t & 1), (t >> 1) & 1);
+    };
     auto load_observation = [&](int t) {
         if (!owner || t >= length) return 0.f;
         const float o = obs[(size_t)t * states + j];
         return log_probs ? o : logf(o);
     };
 
-    if (mine) {
-        float score = -INFINITY;                 // padded states never win
-        if (owner) score = (log_probs ? initial[j] : logf(initial[j])) + load_observation(0);
-#pragma unroll
-        for (int i = 0; i < kPeersPerThread; ++i) {
-            copies[i][0] = score;
-            copies[i][whole] = -INFINITY;
-        }
-    }
+    cluster.sync();      // every copy is initialised and every barrier exists before the first store
+    if (owner) publish((log_probs ? initial[j] : logf(initial[j])) + load_observation(0), 0);
     float next_observation = load_observation(1);    // one frame ahead of its use
-    cluster.sync();
+    await(0);
 
     int current = 0;
     for (int t = 1; t < max(length, 1); ++t) {
@@ -266,21 +292,23 @@ viterbi_cluster_kernel(
             if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
         }
         if (owner) {
-            const float score = best + observed;
-#pragma unroll
-            for (int i = 0; i < kPeersPerThread; ++i) copies[i][(current ^ 1) * whole] = score;
+            publish(best + observed, t & 1);
             if (part == 0) back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
         }
         current ^= 1;
-        // the new scores are visible in every copy; everyone is done reading the old ones, which
-        // the frame after this one overwrites
-        cluster.sync();
+        await(t);
     }
 
     // final argmax and backtrace on the first CTA of the cluster (it holds the whole vector)
     __threadfence();
     cluster.sync();
-    if (rank == 0 && tid == 0) {
+    if (rank != 0) return;
+    // The backtrace is a chain of `length` dependent loads.  Followed through global memory
+    // by one thread it costs an L2 round trip per frame; instead all threads stage the
+    // back-pointers of a block of frames in the shared memory the band no longer needs, and
+    // the walker steps through them there.
+    __shared__ int walker_state;
+    if (tid == 0) {
         const float* last = full + current * whole;
         int state = 0;
         float best = -INFINITY;
@@ -288,11 +316,26 @@ viterbi_cluster_kernel(
             for (int k = 0; k < whole; ++k)
                 if (k < states && last[k] > best) { best = last[k]; state = k; }
         }
-        for (int t = length - 1; t >= 0; --t) {
-            path[t] = state;
-            if (t > 0) state = back[(size_t)t * states + state];
-        }
+        walker_state = state;
         for (int t = max(length, 0); t < frames; ++t) path[t] = 0;
+    }
+    short* staged = reinterpret_cast<short*>(band_s);
+    const int block_frames = max(1, (int)(((size_t)max_width * pitch * sizeof(float)) / ((size_t)states * sizeof(short))));
+    for (int hi = length - 1; hi >= 0; hi -= block_frames) {
+        const int lo_frame = max(hi - block_frames + 1, 0);
+        __syncthreads();                                  // the walker is done with the last block
+        const size_t offset = (size_t)lo_frame * states;
+        const int shorts = (hi - lo_frame + 1) * states;
+        for (int idx = tid; idx < shorts; idx += kClusterThreads) staged[idx] = __ldcg(back + offset + idx);
+        __syncthreads();
+        if (tid == 0) {
+            int state = walker_state;
+            for (int t = hi; t >= lo_frame; --t) {
+                path[t] = state;
+                if (t > 0) state = staged[(size_t)(t - lo_frame) * states + state];
+            }
+            walker_state = state;
+        }
     }
 }
 

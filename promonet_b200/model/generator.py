@@ -35,6 +35,7 @@ class Generator:
         self.default_previous_samples = torch.zeros(1, 1, 1, device=self.device)
         self._workspace = None
         self._staging = None
+        self._streaming = None
         self._state = None
         self.load_state_dict(init.hifigan_state() if state is None else state)
 
@@ -88,7 +89,7 @@ class Generator:
         if device != self.device:
             self.device = device
             self.default_previous_samples = self.default_previous_samples.to(device)
-            self._workspace = self._staging = None
+            self._workspace = self._staging = self._streaming = None
             self.load_state_dict(self._state)
         return self
 
@@ -133,9 +134,11 @@ class Generator:
         speakers,
         spectral_balance_ratios,
         loudness_ratios,
-        previous_samples=None
+        previous_samples=None,
+        out=None
     ):
-        """Generator.forward (generator.py:116-135) on device tensors"""
+        """Generator.forward (generator.py:116-135) on device tensors; `out` (B, 1, 256 F)
+        receives the audio when given"""
         batch, frames = self._check_inputs(
             loudness, pitch, periodicity, ppg, speakers,
             spectral_balance_ratios, loudness_ratios)
@@ -148,7 +151,11 @@ class Generator:
         sbr = spectral_balance_ratios.to(**f32).contiguous()
         lr = loudness_ratios.to(**f32).contiguous()
         audio = torch.empty(
-            batch, 1, frames * config.HOPSIZE, **f32)
+            batch, 1, frames * config.HOPSIZE, **f32) if out is None else out
+        if out is not None and (
+                out.shape != (batch, 1, frames * config.HOPSIZE) or out.dtype != torch.float32 or
+                out.device != self.device or not out.is_contiguous()):
+            raise ValueError('out must be a contiguous float32 (B, 1, 256 F) tensor on the model device')
         if batch == 0 or frames == 0:
             return audio
         with torch.cuda.device(self.device):
@@ -209,6 +216,67 @@ class Generator:
                 workspace.data_ptr(), workspace.numel(), _lib.stream()))
             torch.cuda.current_stream().synchronize()
         return out
+
+    def stream_host(self, batches, depth=2):
+        """Synthesize a stream of HOST batches (tuples of the seven pinned host tensors that
+        forward_host takes), yielding one pinned host audio tensor (B, 1, 256 F) per batch, in
+        order.  Copies run on their own streams: the device-to-host copy of batch i and the
+        host-to-device copy of batch i + 1 overlap the synthesis of batch i + 1 / i + 2, so the
+        GPU never waits for PCIe.  A yielded tensor is reused `depth` batches later: consume
+        (or copy) it before advancing the generator that far."""
+        if depth < 2:
+            raise ValueError('depth must be at least 2')
+        compute = torch.cuda.current_stream(self.device)
+        # streams and the slots' device / pinned buffers live with the model: allocating pinned
+        # memory is slow and synchronizes the device, so a second stream of batches reuses them
+        if getattr(self, '_streaming', None) is None or len(self._streaming['slots']) != depth:
+            self._streaming = dict(
+                copy_in=torch.cuda.Stream(self.device), copy_out=torch.cuda.Stream(self.device),
+                slots=[dict(inputs=None, audio=None, host=None, done=None) for _ in range(depth)])
+        copy_in, copy_out = self._streaming['copy_in'], self._streaming['copy_out']
+        slots = self._streaming['slots']
+        for slot in slots:
+            if slot['done'] is not None:
+                slot['done'].synchronize()
+        pending = []
+        for index, batch in enumerate(batches):
+            slot = slots[index % depth]
+            if slot['done'] is not None:
+                # its previous audio has been yielded (depth >= 2) and its copy has finished
+                slot['done'].synchronize()
+            batch_size, frames = self._check_inputs(*batch)
+            with torch.cuda.stream(copy_in):
+                # the slot's device inputs were last read by a forward that has been waited for
+                slot['inputs'] = [
+                    t.to(self.device, torch.int64 if t.dtype in (torch.int32, torch.int64) else torch.float32,
+                         non_blocking=True) for t in batch]
+                ready = torch.cuda.Event()
+                ready.record(copy_in)
+            shape = (batch_size, 1, frames * config.HOPSIZE)
+            if slot['audio'] is None or slot['audio'].shape != shape:
+                slot['audio'] = torch.empty(shape, device=self.device)
+                slot['host'] = torch.empty(shape, pin_memory=True)
+            compute.wait_event(ready)
+            self(*slot['inputs'], out=slot['audio'])
+            for tensor in slot['inputs']:
+                tensor.record_stream(compute)
+            computed = torch.cuda.Event()
+            computed.record(compute)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(computed)
+                slot['host'].copy_(slot['audio'], non_blocking=True)
+                slot['done'] = torch.cuda.Event()
+                slot['done'].record(copy_out)
+            # the next forward may not overwrite this slot's audio before its copy out: with
+            # depth slots that is guaranteed by the synchronize at the top of the loop
+            pending.append(slot)
+            if len(pending) == depth:
+                first = pending.pop(0)
+                first['done'].synchronize()
+                yield first['host']
+        for slot in pending:
+            slot['done'].synchronize()
+            yield slot['host']
 
     def features(self, loudness, pitch, periodicity, ppg):
         """Generator.prepare_features (generator.py:137-197) -> (B, 113, F)"""

@@ -199,6 +199,23 @@ def test_forward_host_equals_device_forward(model):
     assert torch.equal(host, device)
 
 
+def test_stream_host_yields_every_batch_in_order(model):
+    """The pipelined host entry (copies on their own streams) returns what the synchronous
+    device forward returns, for batches of different shapes and more batches than slots"""
+    batches = [
+        [a.pin_memory() for a in inputs.synthesis(batch, frames, seed=20 + i)]
+        for i, (batch, frames) in enumerate([(2, 33), (2, 33), (1, 50), (3, 17), (2, 33)])]
+    expected = [model(*[a.cuda() for a in batch]).cpu() for batch in batches]
+    count = 0
+    for audio, reference in zip(model.stream_host(iter(batches)), expected):
+        assert audio.is_pinned() and torch.equal(audio, reference)
+        count += 1
+    assert count == len(batches)
+    assert list(model.stream_host(iter([]))) == []
+    with pytest.raises(ValueError):
+        list(model.stream_host(iter(batches), depth=1))
+
+
 def test_from_features_signature_and_parity(state):
     """promonet.synthesize.from_features (synthesize/core.py:18-59)"""
     import promonet_b200
