@@ -26,7 +26,8 @@ KERNELS = (
     'stft_kernel', 'loudness_finish_kernel', 'resample_kernel', 'frames_kernel', 'conv1d_kernel',
     'conv1d_tc_kernel', 'im2col_planes_kernel', 'pool_norm_kernel', 'pool_norm_planes_kernel',
     'zero_plane_pads_kernel', 'posterior_kernel', 'band_fill_kernel', 'viterbi_kernel',
-    'viterbi_cluster_kernel', 'pitch_kernel')
+    'viterbi_cluster_kernel', 'pitch_kernel', 'padded_kernel', 'column_sums_kernel',
+    'frame_stats_kernel', 'shared_norm_planes_kernel')
 
 
 def main():

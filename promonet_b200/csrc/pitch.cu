@@ -58,6 +58,14 @@ constexpr int kFoldStride = 484;               // block 1's frame stride: a mult
 // the LayerNorm pass 20 % faster but cost more than that in per-launch overheads (296
 // instead of 14 launches of each kernel), so the sub-chunk is the whole default frame batch
 constexpr int kSubFrames = 2048;
+// Block 0 shared between frames (hop even): consecutive frames overlap by 1 - hop / 1024 (91 % at
+// the default hop of 92 samples) and block 0's convolution, ReLU and MaxPool do not depend on the
+// frame, only its LayerNorm does.  The convolution therefore runs ONCE over each reflect-padded
+// utterance (10.7 x fewer multiply-adds than frame by frame at the default hop) and the LayerNorm
+// kernel reads frame f's 481 pooled rows at offset (hop f + 16) / 2 of that shared output.
+// Utterances are processed in groups whose pooled output stays below this many rows (x 256
+// channels x 4 bytes = 2 GiB).
+constexpr int kPooledRowsCap = 1 << 21;
 
 }  // namespace
 
@@ -133,6 +141,25 @@ __global__ void __launch_bounds__(256) frames_kernel(
     out[(size_t)local * stride + n] = value;
 }
 
+// Reflect-padded utterances laid end to end: out[u * stride + s] = padded[first_item + u][s],
+// the signal frames_kernel cuts its frames from (frame f is padded[hop f : hop f + 1024])
+__global__ void __launch_bounds__(256) padded_kernel(
+    const float* __restrict__ audio, float* __restrict__ out, int samples, int first_item,
+    int padding, int stride) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= stride) return;
+    const int b = first_item + blockIdx.y;
+    int i = s - padding;
+    float value = 0.f;
+    if (i < 0) i = -i;
+    if (i >= samples) {
+        const int beyond = i - (samples - 1);
+        i = beyond <= padding ? samples - 1 - beyond : -1;
+    }
+    if (i >= 0 && i < samples) value = audio[(size_t)b * samples + i];
+    out[(size_t)blockIdx.y * stride + s] = value;
+}
+
 // MaxPool(2) (optional) + LayerNorm over (C, L) with elementwise affine, per frame.
 // in: [C][in_row] with frame f at columns f * l_in .. f * l_in + l_conv (already ReLU'd)
 // out: [C][count * l_out] or, transposed, [(c * l_out + t)][count]
@@ -191,7 +218,8 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(
 __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
-    int count, int t_pad, bool transposed, int stride_out, bool fold_out, bool fold_in, int frame_base) {
+    int count, int t_pad, bool transposed, int stride_out, bool fold_out, bool fold_in, int frame_base,
+    int frames_per_item = 0, int item_stride = 0, int first_frame = 0) {
     __shared__ double partial[2][8];
     __shared__ float stats[2];
     const int f = blockIdx.x;
@@ -221,7 +249,13 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     }
     if (f >= count) return;
     const int total = channels * l_out;
-    const float* base = in + (size_t)f * l_in;
+    // frames_per_item > 0: `in` is shared by overlapping frames (block 0): frame first_frame + f
+    // is frame (.) % frames_per_item of item (.) / frames_per_item, items item_stride columns
+    // apart, frames l_in columns apart
+    const float* base = frames_per_item > 0
+        ? in + (size_t)((first_frame + f) / frames_per_item) * item_stride +
+              (size_t)((first_frame + f) % frames_per_item) * l_in
+        : in + (size_t)f * l_in;
     auto value = [&](int c, int t) {
         if (fold_in) {
             // output of a folded convolution, not yet pooled: sample 4 t4 + q of channel c is
@@ -312,6 +346,123 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
             lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
         }
         const size_t row = plane_row(g, t);
+        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---- block 0 shared between frames: LayerNorm of frame windows of one pooled convolution ----
+
+// sums[0][u] = sum_c in[c][u], sums[1][u] = sum_c in[c][u]^2 (one pass over the shared output)
+__global__ void __launch_bounds__(256) column_sums_kernel(
+    const float* __restrict__ in, float* __restrict__ sums, int channels, size_t in_row) {
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= in_row) return;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, squares[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < channels; c += 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = in[(size_t)(c + i) * in_row + u];
+            sum[i] += v;
+            squares[i] = fmaf(v, v, squares[i]);
+        }
+    }
+    sums[u] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    sums[in_row + u] = (squares[0] + squares[1]) + (squares[2] + squares[3]);
+}
+
+// column offset of frame `frame` (counted from the first frame of the group) in the shared output
+__device__ __forceinline__ size_t shared_frame_offset(int frame, int frames_per_item, int item_stride, int l_in) {
+    return (size_t)(frame / frames_per_item) * item_stride + (size_t)(frame % frames_per_item) * l_in;
+}
+
+// mean and 1 / std of every frame's (channels x l_out) window, one warp per frame
+__global__ void __launch_bounds__(256) frame_stats_kernel(
+    const float* __restrict__ sums, size_t in_row, float2* __restrict__ stats, int count,
+    int frames_per_item, int item_stride, int l_in, int l_out, int first_frame, int channels) {
+    const int f = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= count) return;
+    const float* column = sums + shared_frame_offset(first_frame + f, frames_per_item, item_stride, l_in);
+    double sum = 0., squares = 0.;
+    for (int t = lane; t < l_out; t += 32) {
+        sum += column[t];
+        squares += column[in_row + t];
+    }
+    for (int offset = 16; offset > 0; offset >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, offset);
+        squares += __shfl_xor_sync(0xffffffffu, squares, offset);
+    }
+    if (lane == 0) {
+        const double total = (double)channels * l_out;
+        const double mean = sum / total;
+        const double variance = fmax(squares / total - mean * mean, 0.);
+        stats[f] = make_float2((float)mean, (float)(1. / sqrt(variance + 1e-5)));
+    }
+}
+
+// (x - mean_f) rstd_f weight[c, t] + bias[c, t] of kSharedFrames consecutive frames x 8 channels
+// per CTA, written as the hi / lo planes of block 1's operand folded by 4 in time.  The frames'
+// windows overlap (l_in = hop / 2 columns apart, l_out wide), so the CTA stages their union and
+// the 8 channels' affine parameters in shared memory once: 0.46 instead of 3 loads per output.
+constexpr int kSharedFrames = 8;
+__global__ void __launch_bounds__(256) shared_norm_planes_kernel(
+    const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
+    const float2* __restrict__ stats, __nv_bfloat16* __restrict__ planes, int channels, int l_in,
+    int l_out, size_t in_row, int count, int t_pad, int stride_out, int frames_per_item,
+    int item_stride, int first_frame) {
+    extern __shared__ float shared_norm_smem[];
+    const int width = l_out + (kSharedFrames - 1) * l_in;
+    float* tile = shared_norm_smem;               // [8][width]
+    float* gamma = tile + 8 * width;              // [8][l_out]
+    float* beta = gamma + 8 * l_out;              // [8][l_out]
+    const int f0 = blockIdx.x * kSharedFrames, g = blockIdx.y;
+    const int groups = channels / 8;
+    const int n_frames = min(kSharedFrames, count - f0);
+    const int item0 = (first_frame + f0) / frames_per_item;
+    // frames of this CTA that lie in the first frame's utterance share the staged window
+    int same = 1;
+    while (same < n_frames && (first_frame + f0 + same) / frames_per_item == item0) ++same;
+    const size_t offset0 = shared_frame_offset(first_frame + f0, frames_per_item, item_stride, l_in);
+    const int needed = (same - 1) * l_in + l_out;
+    for (int idx = threadIdx.x; idx < 8 * needed; idx += blockDim.x) {
+        const int c = idx / needed, pos = idx % needed;
+        tile[c * width + pos] = in[(size_t)(g * 8 + c) * in_row + offset0 + pos];
+    }
+    for (int idx = threadIdx.x; idx < 8 * l_out; idx += blockDim.x) {
+        gamma[idx] = weight[(size_t)g * 8 * l_out + idx];
+        beta[idx] = bias[(size_t)g * 8 * l_out + idx];
+    }
+    __syncthreads();
+    uint4* hi_plane = reinterpret_cast<uint4*>(planes);
+    uint4* lo_plane = hi_plane + (size_t)4 * groups * t_pad;
+    for (int idx = threadIdx.x; idx < n_frames * stride_out; idx += blockDim.x) {
+        const int j = idx / stride_out, t = idx % stride_out;
+        unsigned int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+        if (t < l_out) {
+            const float2 st = stats[f0 + j];
+            const float* global = nullptr;
+            if (j >= same)
+                global = in + (size_t)(g * 8) * in_row +
+                         shared_frame_offset(first_frame + f0 + j, frames_per_item, item_stride, l_in) + t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float z[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = 2 * e + h;
+                    const float x = global ? global[(size_t)c * in_row] : tile[c * width + j * l_in + t];
+                    z[h] = (x - st.x) * st.y * gamma[c * l_out + t] + beta[c * l_out + t];
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
+                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
+                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            }
+        }
+        // sample t of channel group g is row t / 4 of group (t % 4) * groups + g (pool_norm_planes_kernel)
+        const size_t row = (size_t)((t & 3) * groups + g) * t_pad + kTcPad +
+                           (size_t)(f0 + j) * (stride_out >> 2) + (t >> 2);
         hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -506,14 +657,26 @@ int resampler(pmn_pitch* p, int sample_rate, const pmn_pitch::Resampler** out) {
 }
 
 struct Workspace {
-    float *resampled, *conv, *act, *logits_t, *masked, *distribution;
+    float *resampled, *conv, *act, *logits_t, *masked, *distribution, *pooled, *sums, *padded;
+    float2* stats;
     __nv_bfloat16 *planes, *planes0;
     int* bins;
     void* viterbi;
     size_t viterbi_bytes, bytes;
 };
 
-Workspace carve(void* base, int batch, int out_samples, int frames, int frame_batch) {
+// Rows of one reflect-padded utterance on the shared block-0 time axis (even, so MaxPool pairs
+// never straddle two utterances) and utterances per group; 0 when the hop is odd (frame starts
+// then fall on both parities of the pooling grid and block 0 runs frame by frame)
+int shared_item_rows(int frames, int hop) {
+    if (hop % 2) return 0;
+    return (hop * (frames - 1) + kCropStart + kCropped + 1) / 2 * 2;
+}
+int shared_group(int batch, int item_rows) {
+    return std::max(1, std::min(batch, 2 * kPooledRowsCap / item_rows));
+}
+
+Workspace carve(void* base, int batch, int out_samples, int frames, int frame_batch, int hop) {
     Workspace w;
     char* p = static_cast<char*>(base);
     auto take = [&](size_t bytes) {
@@ -531,8 +694,16 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
         tc_planes_elements(1, 256, (int)(fb + 16) * 482),
         tc_planes_elements(1, kFold * 256, (int)(fb + 16) * (kFoldStride / kFold))) * 2);
     // block 0's own operand (im2col rows of a sub-chunk of frames, 32 "channels")
-    w.planes0 = (__nv_bfloat16*)take(
-        tc_planes_elements(1, kKernel, (int)std::min<size_t>(kSubFrames, fb) * (kCropped + 1)) * 2);
+    const int item_rows = shared_item_rows(frames, hop);
+    const size_t shared_rows = item_rows ? (size_t)shared_group(batch, item_rows) * item_rows : 0;
+    w.planes0 = (__nv_bfloat16*)take(std::max(
+        tc_planes_elements(1, kKernel, (int)std::min<size_t>(kSubFrames, fb) * (kCropped + 1)),
+        tc_planes_elements(1, kKernel, (int)shared_rows)) * 2);
+    // block 0's pooled output over whole utterances (shared by their frames), plus the padded signal
+    w.pooled = (float*)take((shared_rows / 2 + 64) * 256 * 4);
+    w.padded = (float*)take(shared_rows * 4);
+    w.sums = (float*)take(shared_rows * 4);          // 2 x (shared_rows / 2) column sums
+    w.stats = (float2*)take(fb * sizeof(float2));    // mean, 1 / std per frame of a chunk
     w.logits_t = (float*)take(fb * kBins * 4);
     w.masked = (float*)take(total * kBins * 4);
     w.distribution = (float*)take(total * kBins * 4);
@@ -646,7 +817,8 @@ static int resampled_length(int samples, int sample_rate) {
 
 size_t pitch_workspace_bytes(int batch, int samples, int sample_rate, double hopsize_seconds, int frame_batch) {
     return carve(nullptr, batch, resampled_length(samples, sample_rate),
-                 pitch_frames(samples, sample_rate, hopsize_seconds), frame_batch).bytes;
+                 pitch_frames(samples, sample_rate, hopsize_seconds), frame_batch,
+                 (int)(hopsize_seconds * kRate)).bytes;
 }
 
 int pitch_forward(
@@ -665,7 +837,7 @@ int pitch_forward(
     PMN_REQUIRE(out_samples > padding, "pitch: audio shorter than the reflect padding");
     const int frames = pitch_frames(samples, sample_rate, hopsize_seconds);
     const int total = batch * frames;
-    Workspace w = carve(workspace, batch, out_samples, frames, frame_batch);
+    Workspace w = carve(workspace, batch, out_samples, frames, frame_batch, hop);
     if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "pitch: workspace too small");
 
     // 1. resample to 8 kHz
@@ -685,10 +857,49 @@ int pitch_forward(
     const int min_bin = std::max(0, (int)floor(kOctave * log2((double)fmin / kFmin) / kCentsPerBin));
     const int max_bin = std::min(kBins, (int)ceil(kOctave * log2((double)fmax / kFmin) / kCentsPerBin));
 
-    // 2. network, frame_batch frames at a time
-    for (int first = 0; first < total; first += frame_batch) {
-        const int count = std::min(frame_batch, total - first);
-        const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
+    // 2. network, frame_batch frames at a time; on the tensor-core path with an even hop block 0's
+    // convolution runs once per group of utterances before the group's frames (kPooledRowsCap)
+    const bool tensor_cores = p->math == PMN_MATH_BF16X3_TC;
+    const int item_rows = tensor_cores ? shared_item_rows(frames, hop) : 0;
+    const bool shared0 = item_rows > 0;
+    const int group = shared0 ? shared_group(batch, item_rows) : batch;
+    size_t pooled_row = 0;     // row length of w.pooled
+    for (int item0 = 0; item0 < batch; item0 += group) {
+    const int items = std::min(group, batch - item0);
+    if (shared0) {
+        float* padded = w.padded;
+        {
+            dim3 grid(ceil_div(item_rows, 256), items);
+            LaunchScope scope("padded_kernel", stream);
+            padded_kernel<<<grid, 256, 0, stream>>>(
+                audio8k, padded, out_samples, item0, padding, item_rows);
+            PMN_TRY(launched("padded_kernel"));
+        }
+        const size_t rows_in = (size_t)items * item_rows;
+        const size_t conv_rows = rows_in - (kKernel - 1);
+        const int t_pad = tc_padded_length((int)conv_rows);
+        {
+            dim3 grid(ceil_div(t_pad, 128), 4);
+            LaunchScope scope("im2col_planes_kernel", stream);
+            im2col_planes_kernel<<<grid, 128, 0, stream>>>(
+                padded, w.planes0, (int)rows_in, (int)conv_rows, t_pad);
+            PMN_TRY(launched("im2col_planes_kernel"));
+        }
+        pooled_row = conv_rows / 2;
+        TcConvArgs a;
+        a.x_planes = w.planes0; a.w_slabs = p->conv_slabs[0]; a.bias = p->conv_bias[0];
+        a.out = w.pooled; a.batch = 1; a.c_in = kKernel; a.c_out = kChannels[1]; a.k = 1;
+        a.t_len = (int)conv_rows; a.valid = true; a.relu = true; a.pool = true;
+        a.out_row = (int)pooled_row;
+        PMN_TRY(launch_conv1d_tc(a, stream));
+        LaunchScope scope("column_sums_kernel", stream);
+        column_sums_kernel<<<(unsigned)((pooled_row + 255) / 256), 256, 0, stream>>>(
+            w.pooled, w.sums, kChannels[1], pooled_row);
+        PMN_TRY(launched("column_sums_kernel"));
+    }
+    const int group_end = (item0 + items) * frames;
+    for (int first = item0 * frames; first < group_end; first += frame_batch) {
+        const int count = std::min(frame_batch, group_end - first);
         // Tensor-core path: frame strides are even where a MaxPool follows, so pooling
         // pairs never straddle two frames and the conv epilogue can pool adjacent lanes
         auto stride_of = [&](int i) {
@@ -702,6 +913,38 @@ int pitch_forward(
             frames_kernel<<<grid, 256, 0, stream>>>(
                 audio8k, w.act, out_samples, frames, first, count, hop, padding, stride);
             PMN_TRY(launched("frames_kernel"));
+        } else if (shared0) {
+            // Block 0: LayerNorm of every frame's window of the shared pooled convolution ->
+            // block 1's folded operand
+            const int stride_next = stride_of(1);
+            const int t_next = count * (stride_next / kFold);
+            PMN_TRY(launch_zero_plane_pads(w.planes, 1, kFold * kChannels[1], t_next, stream));
+            const int first_frame = first - item0 * frames;
+            {
+                LaunchScope scope("frame_stats_kernel", stream);
+                frame_stats_kernel<<<ceil_div(count, 8), 256, 0, stream>>>(
+                    w.sums + kCropStart / 2, pooled_row, w.stats, count, frames, item_rows / 2,
+                    hop / 2, kLength[1], first_frame, kChannels[1]);
+                PMN_TRY(launched("frame_stats_kernel"));
+            }
+            const int width = kLength[1] + (kSharedFrames - 1) * (hop / 2);
+            const int smem = (8 * width + 16 * kLength[1]) * (int)sizeof(float);
+            PMN_REQUIRE(smem <= 200 * 1024, "pitch: hop too long for the shared block 0");
+            static bool configured = false;
+            if (!configured) {
+                PMN_TRY(check_cuda(
+                    cudaFuncSetAttribute(shared_norm_planes_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                    "shared_norm_planes smem attribute"));
+                configured = true;
+            }
+            dim3 grid(ceil_div(count, kSharedFrames), kChannels[1] / 8);
+            LaunchScope scope("shared_norm_planes_kernel", stream);
+            shared_norm_planes_kernel<<<grid, 256, smem, stream>>>(
+                w.pooled + kCropStart / 2, p->norm_weight[0], p->norm_bias[0], w.stats, w.planes,
+                kChannels[1], hop / 2, kLength[1], pooled_row, count, tc_padded_length(t_next),
+                stride_next, frames, item_rows / 2, first_frame);
+            PMN_TRY(launched("shared_norm_planes_kernel"));
         } else {
             // Block 0, a sub-chunk of frames at a time (kSubFrames): frames -> im2col operand ->
             // 1x1 convolution over the 32 taps (ReLU + MaxPool in its epilogue) -> LayerNorm ->
@@ -824,6 +1067,7 @@ int pitch_forward(
                 w.distribution + (size_t)first * kBins, periodicity + first);
             PMN_TRY(launched("posterior_kernel"));
         }
+    }
     }
 
     // 3. Viterbi over the posteriors, 4. local expected value

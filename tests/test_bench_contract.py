@@ -29,7 +29,9 @@ def test_reference_arm_prints_the_contract_line():
     assert 'workload' in line['config'] and 'model' not in line['config']
     assert line['value'] > 0 and line['ms_per_step'] > 0
     cpu = line['cpu_baseline']
-    assert cpu['kind'] == 'port' and cpu['cores'] == os.cpu_count() and cpu['value'] == line['value']
+    # the unmodified reference (oracle/_ref, vendored by build()) when present, else the oracle port
+    kind = 'reference' if (ROOT / 'oracle' / '_ref' / 'promonet').exists() else 'port'
+    assert cpu['kind'] == kind and cpu['cores'] == os.cpu_count() and cpu['value'] == line['value']
     assert cpu['unit'] == line['unit'] and 'utterances' in cpu['sample']
     assert line['e2e'] == {
         'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}

@@ -20,7 +20,7 @@ def write_wav(file, samples, value):
 def test_preprocess_files_are_bucketed_by_length_and_saved_under_the_reference_names(tmp_path, monkeypatch):
     calls = []
 
-    def double(audio, sample_rate, gpu, features, loudness_bands):
+    def double(audio, sample_rate, gpu, features, loudness_bands, pitch_checkpoint=None):
         """Stands in for from_audio_batch: every feature is the utterance's first sample"""
         calls.append(tuple(audio.shape))
         batch, frames = audio.shape[0], audio.shape[1] // 256
