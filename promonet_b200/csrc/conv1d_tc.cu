@@ -394,15 +394,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         for (int g = 0; g < kW / 8; ++g) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float y0 = leaky(v[g * 8 + 2 * e], a.out_slope);
-                                const float y1 = leaky(v[g * 8 + 2 * e + 1], a.out_slope);
-                                const __nv_bfloat16 h0 = __float2bfloat16_rn(y0);
-                                const __nv_bfloat16 h1 = __float2bfloat16_rn(y1);
-                                hi[e] = pack_bf16(h0, h1);
-                                lo[e] = pack_bf16(__float2bfloat16_rn(y0 - __bfloat162float(h0)),
-                                                  __float2bfloat16_rn(y1 - __bfloat162float(h1)));
-                            }
+                            for (int e = 0; e < 4; ++e)
+                                split_pair(leaky(v[g * 8 + 2 * e], a.out_slope),
+                                           leaky(v[g * 8 + 2 * e + 1], a.out_slope), hi[e], lo[e]);
                             const size_t row_hi =
                                 ((size_t)(b * 2) * groups_out + (c_first / 8 + g)) * out_pad + kTcPad + t;
                             const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
@@ -447,12 +441,8 @@ __global__ void __launch_bounds__(128) planes_from_f32_kernel(
         const float* src = x + ((size_t)b * channels + g * 8) * t_len + t;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float y0 = leaky(__ldg(src + (size_t)(2 * e) * t_len), slope);
-            const float y1 = leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope);
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-            hi[e] = pack_bf16(h0, h1);
-            lo[e] = pack_bf16(__float2bfloat16_rn(y0 - __bfloat162float(h0)),
-                              __float2bfloat16_rn(y1 - __bfloat162float(h1)));
+            split_pair(leaky(__ldg(src + (size_t)(2 * e) * t_len), slope),
+                       leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope), hi[e], lo[e]);
         }
     }
     const size_t row_hi = ((size_t)(b * 2) * groups + g) * t_pad + row;

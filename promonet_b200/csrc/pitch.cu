@@ -31,6 +31,7 @@
 #include "conv1d_tc.cuh"
 #include "pitch.cuh"
 #include "spectral.cuh"
+#include "tc_ptx.cuh"
 #include "tensor_store.cuh"
 
 namespace pmn {
@@ -266,18 +267,27 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
         const float* row = base + (size_t)c * in_row;
         return pooled ? fmaxf(row[2 * t], row[2 * t + 1]) : row[t];
     };
-    // statistics: one warp per channel row, 4 independent loads in flight per lane
-    const int warp = tid >> 5, lane = tid & 31;
+    // statistics: the frame's (channel, sample) pairs flat over the threads, 8 independent loads in
+    // flight per thread (a warp per channel row left 48 - 64 dependent load latencies in a row on
+    // the short rows of blocks 3 - 5: 66, 35 and 4 samples)
     float sum = 0.f, squares = 0.f;
-    for (int c = warp; c < channels; c += 8) {
-        int t = lane;
-        for (; t + 96 < l_out; t += 128) {
-            const float v0 = value(c, t), v1 = value(c, t + 32), v2 = value(c, t + 64), v3 = value(c, t + 96);
-            sum += (v0 + v1) + (v2 + v3);
-            squares = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, squares))));
+    {
+        int idx = tid;
+        for (; idx + 7 * 256 < total; idx += 8 * 256) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int flat = idx + i * 256;
+                v[i] = value(flat / l_out, flat % l_out);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sum += v[i];
+                squares = fmaf(v[i], v[i], squares);
+            }
         }
-        for (; t < l_out; t += 32) {
-            const float v = value(c, t);
+        for (; idx < total; idx += 256) {
+            const float v = value(idx / l_out, idx % l_out);
             sum += v;
             squares = fmaf(v, v, squares);
         }
@@ -314,11 +324,7 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
                     const int flat = g * 8 + 2 * e + h;
                     y[h] = (value(flat / l_out, flat % l_out) - mean) * rstd * weight[flat] + bias[flat];
                 }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
-                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+                tc::split_pair(y[0], y[1], hi[e], lo[e]);
             }
             hi_wide[(size_t)g * t_pad + kTcPad + f] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             lo_wide[(size_t)g * t_pad + kTcPad + f] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -339,11 +345,7 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
                 const int c = g * 8 + 2 * e + h;
                 z[h] = (y[2 * e + h] - mean) * rstd * weight[c * l_out + t] + bias[c * l_out + t];
             }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
-            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            tc::split_pair(z[0], z[1], hi[e], lo[e]);
         }
         const size_t row = plane_row(g, t);
         hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -413,8 +415,7 @@ __global__ void __launch_bounds__(256) shared_norm_planes_kernel(
     extern __shared__ float shared_norm_smem[];
     const int width = l_out + (kSharedFrames - 1) * l_in;
     float* tile = shared_norm_smem;               // [8][width]
-    float* gamma = tile + 8 * width;              // [8][l_out]
-    float* beta = gamma + 8 * l_out;              // [8][l_out]
+    __shared__ float2 frame_stats[kSharedFrames];
     const int f0 = blockIdx.x * kSharedFrames, g = blockIdx.y;
     const int groups = channels / 8;
     const int n_frames = min(kSharedFrames, count - f0);
@@ -424,47 +425,55 @@ __global__ void __launch_bounds__(256) shared_norm_planes_kernel(
     while (same < n_frames && (first_frame + f0 + same) / frames_per_item == item0) ++same;
     const size_t offset0 = shared_frame_offset(first_frame + f0, frames_per_item, item_stride, l_in);
     const int needed = (same - 1) * l_in + l_out;
-    for (int idx = threadIdx.x; idx < 8 * needed; idx += blockDim.x) {
-        const int c = idx / needed, pos = idx % needed;
-        tile[c * width + pos] = in[(size_t)(g * 8 + c) * in_row + offset0 + pos];
-    }
-    for (int idx = threadIdx.x; idx < 8 * l_out; idx += blockDim.x) {
-        gamma[idx] = weight[(size_t)g * 8 * l_out + idx];
-        beta[idx] = bias[(size_t)g * 8 * l_out + idx];
-    }
+    const float* source = in + (size_t)(g * 8) * in_row + offset0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        for (int pos = threadIdx.x; pos < needed; pos += blockDim.x)
+            tile[c * width + pos] = source[(size_t)c * in_row + pos];
+    if (threadIdx.x < n_frames) frame_stats[threadIdx.x] = stats[f0 + threadIdx.x];
     __syncthreads();
     uint4* hi_plane = reinterpret_cast<uint4*>(planes);
     uint4* lo_plane = hi_plane + (size_t)4 * groups * t_pad;
-    for (int idx = threadIdx.x; idx < n_frames * stride_out; idx += blockDim.x) {
-        const int j = idx / stride_out, t = idx % stride_out;
-        unsigned int hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-        if (t < l_out) {
-            const float2 st = stats[f0 + j];
-            const float* global = nullptr;
-            if (j >= same)
-                global = in + (size_t)(g * 8) * in_row +
-                         shared_frame_offset(first_frame + f0 + j, frames_per_item, item_stride, l_in) + t;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float z[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = 2 * e + h;
-                    const float x = global ? global[(size_t)c * in_row] : tile[c * width + j * l_in + t];
-                    z[h] = (x - st.x) * st.y * gamma[c * l_out + t] + beta[c * l_out + t];
-                }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(z[0]), h1 = __float2bfloat16_rn(z[1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(z[0] - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(z[1] - __bfloat162float(h1));
-                hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-                lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
-            }
-        }
+    // a thread owns sample t of every frame: the affine parameters of (8 channels, t) stay in registers
+    for (int t = threadIdx.x; t < stride_out; t += blockDim.x) {
         // sample t of channel group g is row t / 4 of group (t % 4) * groups + g (pool_norm_planes_kernel)
-        const size_t row = (size_t)((t & 3) * groups + g) * t_pad + kTcPad +
-                           (size_t)(f0 + j) * (stride_out >> 2) + (t >> 2);
-        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        const size_t row0 = (size_t)((t & 3) * groups + g) * t_pad + kTcPad +
+                            (size_t)f0 * (stride_out >> 2) + (t >> 2);
+        if (t >= l_out) {
+            for (int j = 0; j < n_frames; ++j) {
+                hi_plane[row0 + (size_t)j * (stride_out >> 2)] = make_uint4(0, 0, 0, 0);
+                lo_plane[row0 + (size_t)j * (stride_out >> 2)] = make_uint4(0, 0, 0, 0);
+            }
+            continue;
+        }
+        float gamma[8], beta[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            gamma[c] = weight[(size_t)(g * 8 + c) * l_out + t];
+            beta[c] = bias[(size_t)(g * 8 + c) * l_out + t];
+        }
+        for (int j = 0; j < n_frames; ++j) {
+            const float2 st = frame_stats[j];
+            float x[8];
+            if (j < same) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = tile[c * width + j * l_in + t];
+            } else {
+                const float* global = in + (size_t)(g * 8) * in_row + t +
+                    shared_frame_offset(first_frame + f0 + j, frames_per_item, item_stride, l_in);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = global[(size_t)c * in_row];
+            }
+            unsigned int hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                tc::split_pair((x[2 * e] - st.x) * st.y * gamma[2 * e] + beta[2 * e],
+                               (x[2 * e + 1] - st.x) * st.y * gamma[2 * e + 1] + beta[2 * e + 1],
+                               hi[e], lo[e]);
+            const size_t row = row0 + (size_t)j * (stride_out >> 2);
+            hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
@@ -504,11 +513,7 @@ __global__ void __launch_bounds__(128) im2col_planes_kernel(
                 const int i = r + g * 8 + 2 * e + h;
                 y[h] = i < samples ? x[i] : 0.f;
             }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[0]), h1 = __float2bfloat16_rn(y[1]);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(y[0] - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(y[1] - __bfloat162float(h1));
-            hi[e] = (unsigned int)__bfloat16_as_ushort(h0) | ((unsigned int)__bfloat16_as_ushort(h1) << 16);
-            lo[e] = (unsigned int)__bfloat16_as_ushort(l0) | ((unsigned int)__bfloat16_as_ushort(l1) << 16);
+            tc::split_pair(y[0], y[1], hi[e], lo[e]);
         }
     }
     uint4* hi_plane = reinterpret_cast<uint4*>(planes);
@@ -928,7 +933,7 @@ int pitch_forward(
                 PMN_TRY(launched("frame_stats_kernel"));
             }
             const int width = kLength[1] + (kSharedFrames - 1) * (hop / 2);
-            const int smem = (8 * width + 16 * kLength[1]) * (int)sizeof(float);
+            const int smem = 8 * width * (int)sizeof(float);
             PMN_REQUIRE(smem <= 200 * 1024, "pitch: hop too long for the shared block 0");
             static bool configured = false;
             if (!configured) {

@@ -103,12 +103,15 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// bf16 hi / lo halves of y (y ~ hi + lo to 16 mantissa bits), two values per word
+// bf16 hi / lo halves of y (y ~ hi + lo to 16 mantissa bits), two values per word.  The packed
+// convert (cvt.rn.bf16x2.f32 -> F2FP.BF16.F32.PACK_AB) rounds like two scalar converts but is one
+// instruction on the ALU pipe instead of two quarter-rate F2F plus a PRMT
 __device__ __forceinline__ void split_pair(float y0, float y1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-    hi = pack_bf16(h0, h1);
-    lo = pack_bf16(__float2bfloat16_rn(y0 - __bfloat162float(h0)),
-                   __float2bfloat16_rn(y1 - __bfloat162float(h1)));
+    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(
+        y0 - __uint_as_float(hi << 16), y1 - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 }  // namespace tc

@@ -29,8 +29,15 @@ constexpr int kThreads = 1024;
 // Banded fast path (viterbi_cluster_kernel below)
 constexpr int kClusterSize = 8;
 constexpr int kSplit = 4;                       // threads per state
-constexpr int kClusterThreads = 768;
+constexpr int kClusterThreads = 736;      // 23 warps: 4 threads x 180 states, 88 registers each
 constexpr int kClusterSmem = 200 * 1024;
+// Bands of at most kSplit * kRegisterBand rows (penn's pitch transition: 181) stay in REGISTERS:
+// thread (state, part) keeps rows part, part + kSplit, ... of its column for the whole utterance,
+// so a band entry costs one conflict-free shared-memory load (the scores) instead of two loads
+// with two-way bank conflicts.  Measured before: 5.7 of the 7.4 kcycles of a frame were this scan.
+constexpr int kRegisterBand = 46;
+// one bulk copy of the slice per peer instead of 4-byte st.async per score: measured 7 % slower
+constexpr bool kBulkPublish = false;
 
 __host__ __device__ inline int cluster_slice(int states) {
     return (states + kClusterSize - 1) / kClusterSize;
@@ -38,7 +45,7 @@ __host__ __device__ inline int cluster_slice(int states) {
 // floats of shared memory the fast path needs for a given band width
 __host__ __device__ inline size_t cluster_floats(int states, int max_width) {
     const int slice = cluster_slice(states);
-    return (size_t)max_width * (slice | 1) + 2 * (size_t)kClusterSize * slice;
+    return (((size_t)max_width * (slice | 1) + 3) & ~(size_t)3) + 2 * (size_t)kClusterSize * slice + 16;
 }
 
 
@@ -205,7 +212,7 @@ viterbi_cluster_kernel(
     // buffer frame t was computed from) before every CTA has sent all its frame-t scores,
     // i.e. has finished reading that buffer.
     const int whole = kClusterSize * slice;
-    float* full = band_s + (size_t)max_width * pitch;   // [2][whole]
+    float* full = band_s + (((size_t)max_width * pitch + 3) & ~(size_t)3);   // [2][whole], 16 B aligned
     __shared__ uint64_t landed[2];                      // landed[p]: scores of a frame of parity p
 
     const int j0 = rank * slice;
@@ -214,11 +221,14 @@ viterbi_cluster_kernel(
     short* back = psi + (size_t)b * frames * states;
     int* path = indices + (size_t)b * frames;
 
-    for (int idx = tid; idx < max_width * slice; idx += kClusterThreads) {
-        const int k = idx / slice, jl = idx % slice;
-        band_s[k * pitch + jl] = j0 + jl < states ? band[(size_t)k * states + j0 + jl] : -INFINITY;
+    const bool in_registers = max_width <= kSplit * kRegisterBand;
+    if (!in_registers) {
+        for (int idx = tid; idx < max_width * slice; idx += kClusterThreads) {
+            const int k = idx / slice, jl = idx % slice;
+            band_s[k * pitch + jl] = j0 + jl < states ? band[(size_t)k * states + j0 + jl] : -INFINITY;
+        }
     }
-    for (int idx = tid; idx < 2 * whole; idx += kClusterThreads) full[idx] = -INFINITY;  // padded states
+    for (int idx = tid; idx < 2 * whole + 16; idx += kClusterThreads) full[idx] = -INFINITY;  // padded states
     if (tid == 0) {
         tc::mbar_init(landed, 1);
         tc::mbar_init(landed + 1, 1);
@@ -231,32 +241,68 @@ viterbi_cluster_kernel(
     if (owner) { first = lo[j]; count = width[j]; }
     const int chunk = (count + kSplit - 1) / kSplit;
     const int begin = min(part * chunk, count), end = min(begin + chunk, count);
-    // the kSplit threads of a state share the publishing: thread `part` writes the copies of
-    // CTAs part * (kClusterSize / kSplit) ...
+    float band_r[kRegisterBand];
+    if (in_registers) {
+#pragma unroll
+        for (int i = 0; i < kRegisterBand; ++i) {
+            const int k = kSplit * i + part;
+            band_r[i] = (owner && k < count) ? band[(size_t)k * states + j] : -INFINITY;
+        }
+    }
+    // Publishing.  Measured: the frame is bounded by the number of remote-store packets, not by
+    // their bytes (four states per 16-byte st.async doubled the packets of a warp and made the
+    // frame 33 % slower).  When the slice is a multiple of 4 states every thread therefore
+    // writes its state's score into the CTA's OWN copy, and after one CTA barrier seven threads
+    // each send the whole slice to one peer as a single bulk copy (cp.async.bulk shared::cta ->
+    // shared::cluster, bytes reported to the peer's transaction barrier).  Otherwise every
+    // thread sends its score to kClusterSize / kSplit destinations with 4-byte st.async.
+    const bool bulk = kBulkPublish && slice % 4 == 0;
     constexpr int kPeersPerThread = kClusterSize / kSplit;
     uint32_t copies[kPeersPerThread], barriers[kPeersPerThread];   // shared::cluster addresses
+    if (bulk) {
+        const uint32_t peer = tid < kClusterSize ? tid : 0;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(copies[0]) : "r"(tc::smem_u32(full + j0)), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(barriers[0]) : "r"(tc::smem_u32(landed)), "r"(peer));
+    } else {
 #pragma unroll
-    for (int i = 0; i < kPeersPerThread; ++i) {
-        const uint32_t peer = part * kPeersPerThread + i;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(copies[i]) : "r"(tc::smem_u32(full + j0 + jl)), "r"(peer));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(barriers[i]) : "r"(tc::smem_u32(landed)), "r"(peer));
+        for (int i = 0; i < kPeersPerThread; ++i) {
+            const uint32_t peer = part * kPeersPerThread + i;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                         : "=r"(copies[i]) : "r"(tc::smem_u32(full + j0 + jl)), "r"(peer));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                         : "=r"(barriers[i]) : "r"(tc::smem_u32(landed)), "r"(peer));
+        }
     }
-    // score of frame t (parity t & 1) into every copy
+    // score of frame t (parity t & 1) into every copy; called by every thread of the CTA
     auto publish = [&](float score, int parity) {
+        if (bulk) {
+            if (owner && part == 0) full[parity * whole + j0 + jl] = score;
+            tc::fence_proxy_async();
+            __syncthreads();
+            if (tid < kClusterSize && tid != rank)
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                    ::"r"(copies[0] + (uint32_t)(parity * whole) * 4u),
+                      "r"(tc::smem_u32(full + parity * whole + j0)), "r"((uint32_t)slice * 4u),
+                      "r"(barriers[0] + (uint32_t)parity * 8u) : "memory");
+            return;
+        }
+        if (!owner) return;
 #pragma unroll
         for (int i = 0; i < kPeersPerThread; ++i)
             asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
                          ::"r"(copies[i] + (uint32_t)(parity * whole) * 4u), "r"(__float_as_uint(score)),
                            "r"(barriers[i] + (uint32_t)parity * 8u) : "memory");
     };
-    // all `states` scores of frame t have landed in this CTA's copy.  Only the threads that
+    // all scores of frame t have landed in this CTA's copy.  Only the threads that
     // read the scores wait (a thread that reads nothing could otherwise still be polling for
     // frame t when the same barrier completes frame t + 2; a reader cannot lag that far,
     // because frame t + 2 cannot complete anywhere without its frame t + 1 score)
+    const uint32_t frame_bytes = (uint32_t)(bulk ? (kClusterSize - 1) * slice : states) * 4u;
     auto await = [&](int t) {
-        if (tid == 0) tc::mbar_expect_tx(landed + (t & 1), (uint32_t)states * 4u);
+        if (tid == 0) tc::mbar_expect_tx(landed + (t & 1), frame_bytes);
         if (owner || tid == 0) tc::mbar_wait(landed + (t & 1), (t >> 1) & 1);
     };
     auto load_observation = [&](int t) {
@@ -266,7 +312,7 @@ viterbi_cluster_kernel(
     };
 
     cluster.sync();      // every copy is initialised and every barrier exists before the first store
-    if (owner) publish((log_probs ? initial[j] : logf(initial[j])) + load_observation(0), 0);
+    publish(owner ? (log_probs ? initial[j] : logf(initial[j])) + load_observation(0) : -INFINITY, 0);
     float next_observation = load_observation(1);    // one frame ahead of its use
     await(0);
 
@@ -276,7 +322,28 @@ viterbi_cluster_kernel(
         next_observation = load_observation(t + 1);
         float best = -INFINITY;
         int arg = 0x7fffffff;
-        if (owner) {
+        if (in_registers) {
+            // rows part, part + kSplit, ...: the lanes of a warp read 11 consecutive scores per
+            // step (conflict-free); rows past the band carry -inf and never win
+            const float* source = full + current * whole + first + part;
+            int winner = -1;
+            constexpr int kGroup = 8;     // loads issued together, ahead of their compare chain
+            float scores[kGroup];
+#pragma unroll
+            for (int i0 = 0; i0 < kRegisterBand; i0 += kGroup) {
+#pragma unroll
+                for (int i = 0; i < kGroup; ++i)
+                    if (i0 + i < kRegisterBand) scores[i] = source[kSplit * (i0 + i)];
+#pragma unroll
+                for (int i = 0; i < kGroup; ++i) {
+                    if (i0 + i < kRegisterBand) {
+                        const float value = scores[i] + band_r[i0 + i];
+                        if (value > best) { best = value; winner = i0 + i; }
+                    }
+                }
+            }
+            if (winner >= 0) arg = first + kSplit * winner + part;
+        } else if (owner) {
             const float* column = band_s + jl;
             const float* source = full + current * whole + first;
             for (int k = begin; k < end; ++k) {
@@ -291,10 +358,8 @@ viterbi_cluster_kernel(
             const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
             if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
         }
-        if (owner) {
-            publish(best + observed, t & 1);
-            if (part == 0) back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
-        }
+        publish(best + observed, t & 1);
+        if (owner && part == 0) back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
         current ^= 1;
         await(t);
     }
