@@ -520,7 +520,8 @@ def preprocess(ctx):
         'conv1d_kernel', 'conv1d_tc_kernel', 'im2col_planes_kernel', 'pool_norm_kernel',
         'pool_norm_planes_kernel', 'zero_plane_pads_kernel', 'posterior_kernel', 'band_fill_kernel',
         'viterbi_kernel', 'viterbi_cluster_kernel', 'viterbi_toeplitz_kernel', 'pitch_kernel', 'padded_kernel',
-        'column_sums_kernel', 'frame_stats_kernel', 'shared_norm_planes_kernel')
+        'column_sums_kernel', 'frame_stats_kernel', 'shared_norm_planes_kernel', 'frame_major_stats_kernel',
+    'frame_major_norm_planes_kernel')
     kernels = ctx.kernels(step, names)
     frames = PRE_BATCH * PRE_FRAMES
     cnn_ms = sum(kernels.get(n, {'ms_per_step': 0.})['ms_per_step'] for n in ('conv1d_kernel', 'conv1d_tc_kernel'))

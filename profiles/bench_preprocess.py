@@ -27,7 +27,8 @@ KERNELS = (
     'conv1d_tc_kernel', 'im2col_planes_kernel', 'pool_norm_kernel', 'pool_norm_planes_kernel',
     'zero_plane_pads_kernel', 'posterior_kernel', 'band_fill_kernel', 'viterbi_kernel',
     'viterbi_cluster_kernel', 'pitch_kernel', 'padded_kernel', 'column_sums_kernel',
-    'frame_stats_kernel', 'shared_norm_planes_kernel')
+    'frame_stats_kernel', 'shared_norm_planes_kernel', 'frame_major_stats_kernel',
+    'frame_major_norm_planes_kernel')
 
 
 def main():

@@ -58,7 +58,10 @@ constexpr int kMaxFrameLength = 35;
 // come out of ONE MMA (columns [0, N) and [N, 2 N)) and a_lo w_hi of a second one
 // that accumulates into [0, N): two reads of the 128-row A operand per K chunk
 // instead of three, which is what bounds the narrow (N <= 64) layers.
-template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT>
+// XS activation-slab stages: 2 everywhere except the k = 1 layers with a long K (frame-major pitch
+// blocks 4 and 5), where a 32-channel slab is only 768 cycles of MMAs and two stages do not cover
+// the L2 latency of the next slab.
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT, int XS = 2>
 struct TcConfig {
     static constexpr int kTile = S * 128;
     static constexpr int kRowsMax =
@@ -67,7 +70,7 @@ struct TcConfig {
     static constexpr int kBlocks = C_IN / KB;
     static constexpr int kXSlab = 2 * kGroups * kRowsMax * 16;  // bytes, both planes
     static constexpr int kWSlab = KB * N * 4;                   // bytes, both planes
-    static constexpr int kXStages = 2;
+    static constexpr int kXStages = XS;
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
     static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 6144;
     static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
@@ -80,10 +83,10 @@ struct TcConfig {
     static_assert(MODE != kFrames || S == 1, "frame mode computes one 128-row tile");
 };
 
-template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, int UP, bool CONCAT>
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, int UP, bool CONCAT, int XS>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     TcConvArgs a, int t_pad, int tiles_per_item, int n_tiles, int num_tiles) {
-    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT>;
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* x_slabs = smem;
@@ -131,6 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             uint32_t xcount = 0, wcount = 0;
             long long wait_x = 0, wait_w = 0, begin = a.debug ? clock64() : 0, mark = 0;
             const uint32_t x_bytes = 2 * Cfg::kGroups * rows * 16;
+            const int plane_groups = a.plane_groups > 0 ? a.plane_groups : C_IN / 8;
+            const int item_groups = a.item_groups > 0 ? a.item_groups : 2 * (C_IN / 8);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int nt = tile % n_tiles, rest = tile / n_tiles;
                 const int b = rest / tiles_per_item;
@@ -148,8 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll 1
                         for (int g = 0; g < Cfg::kGroups; ++g) {
                             const size_t row0 =
-                                ((size_t)(b * 2 + p) * (C_IN / 8) + kb * Cfg::kGroups + g) * t_pad +
-                                kTcPad + t0 - left;
+                                ((size_t)b * item_groups + (size_t)p * plane_groups + kb * Cfg::kGroups + g) *
+                                    t_pad + kTcPad + t0 - left;
                             bulk_copy(dst + (p * Cfg::kGroups + g) * rows * 16,
                                       a.x_planes + row0 * 8, rows * 16, x_full + xs);
                         }
@@ -557,10 +562,11 @@ int sm_count() {
     return count;
 }
 
-template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE = kConv, int UP = 0, bool CONCAT = false>
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE = kConv, int UP = 0, bool CONCAT = false,
+          int XS = 2>
 int launch_variant(const TcConvArgs& a, int n_tiles, cudaStream_t stream) {
-    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT>;
-    auto kernel = conv1d_tc_kernel<C_IN, N, S, KB, NW, AS, MODE, UP, CONCAT>;
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS>;
+    auto kernel = conv1d_tc_kernel<C_IN, N, S, KB, NW, AS, MODE, UP, CONCAT, XS>;
     static bool configured = false;
     if (!configured) {
         PMN_TRY(check_cuda(
@@ -597,8 +603,10 @@ bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
         {128, 256, false, {32, 256, false}}, {256, 512, true, {32, 256, false}},
         // block 0 as a 32-"channel" (tap) 1x1 conv over im2col rows; head 2048 -> 1440
         {32, 256, false, {32, 256, false}},  {2048, 1440, false, {64, 160, false}},
-        // penn block 1 folded by 4 in time (pitch.cu): 1024 -> 128, k = 9
+        // penn block 1 folded by 4 in time (pitch.cu): 1024 -> 128, k = 9; also block 3 frame-major
         {1024, 128, false, {64, 128, false}},
+        // penn blocks 4 and 5 frame-major (pitch.cu): K = 32 taps x C_in, k = 1
+        {4096, 256, false, {32, 256, false}}, {8192, 512, false, {32, 256, false}},
     };
     for (const Entry& entry : table) {
         if (entry.c_in == c_in && entry.c_out == c_out && entry.frames == frames) {
@@ -638,6 +646,8 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
     if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2>(a, 1, stream);
+    if (a.c_in == 4096) return launch_variant<4096, 256, 1, 32, 3, 2, kConv, 0, false, 4>(a, 1, stream);
+    if (a.c_in == 8192) return launch_variant<8192, 256, 1, 32, 3, 2, kConv, 0, false, 4>(a, 2, stream);
     return launch_variant<128, 256, 1, 32, 4, 2>(a, 1, stream);
 }
 

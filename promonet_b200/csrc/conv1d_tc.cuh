@@ -55,6 +55,11 @@ struct TcConvArgs {
     // frame): frames of frame_length rows each, the first frame_valid outputs kept
     int frames = 0, frame_length = 0, frame_valid = 0;
     float out_slope = 1.f;
+    // Operand addressing in 8-channel groups (0 = the default planes[b][plane][c / 8] layout):
+    // item b starts item_groups groups after item b - 1 and the lo plane plane_groups groups after
+    // the hi plane.  The frame-major pitch layers (pitch.cu) read planes[plane][position][c / 8]
+    // with the batch index as the position: item_groups = C / 8, plane_groups = positions C / 8
+    int item_groups = 0, plane_groups = 0;
     // Optional (gridDim.x, 10 warps, 4) cycle counters: [0] total, [1..3] barrier waits
     long long* debug = nullptr;
 };

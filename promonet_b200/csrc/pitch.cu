@@ -53,6 +53,7 @@ constexpr int kLocalWindow = 19;
 constexpr int kFold = 4;                       // block 1 on the tensor cores: folded by 4 in time
 constexpr int kFoldTaps = 9;                   // ceil((32 + 3) / 4)
 constexpr int kFoldStride = 484;               // block 1's frame stride: a multiple of 4 >= 481
+constexpr int kFrameMajorFirst = 3;            // blocks 3, 4, 5 and the head run frame-major (below)
 // Block 0 on the tensor-core path takes its own operand buffer (im2col rows) and runs in
 // sub-chunks of at most kSubFrames frames.  Measured (profiles/r2_preprocess_history.txt):
 // sub-chunks small enough for the convolution output to stay in L2 (95 frames, 48 MB) make
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     __nv_bfloat16* __restrict__ planes, int channels, int l_in, int l_out, bool pooled, size_t in_row,
     int count, int t_pad, bool transposed, int stride_out, bool fold_out, bool fold_in, int frame_base,
-    int frames_per_item = 0, int item_stride = 0, int first_frame = 0) {
+    int frames_per_item = 0, int item_stride = 0, int first_frame = 0, bool frame_major = false) {
     __shared__ double partial[2][8];
     __shared__ float stats[2];
     const int f = blockIdx.x;
@@ -229,12 +230,14 @@ __global__ void __launch_bounds__(256) pool_norm_planes_kernel(
     const int g_begin = 0, g_end = groups;
     // fold_out: the operand of a convolution folded by 4 in time: sample t of channel group g
     // is row t / 4 of group (t % 4) * groups + g, and a frame has stride_out / 4 rows
-    const int plane_groups = fold_out ? 4 * groups : groups;
+    // frame_major: the operand of a frame-major layer, planes[plane][t groups + g][kTcPad + f][8]
+    const int plane_groups = frame_major ? l_out * groups : fold_out ? 4 * groups : groups;
     uint4* hi_plane = reinterpret_cast<uint4*>(planes);
     uint4* lo_plane = hi_plane + (size_t)plane_groups * t_pad;
     // frame f of this launch is frame frame_base + f of the operand being written
     auto plane_row = [&](int g, int t) {
         const size_t frame = (size_t)(frame_base + f);
+        if (frame_major) return ((size_t)t * groups + g) * t_pad + kTcPad + frame;
         if (fold_out)
             return (size_t)((t & 3) * groups + g) * t_pad + kTcPad + frame * (stride_out >> 2) + (t >> 2);
         return (size_t)g * t_pad + kTcPad + frame * stride_out + t;
@@ -477,6 +480,110 @@ __global__ void __launch_bounds__(256) shared_norm_planes_kernel(
     }
 }
 
+// ---- frame-major layers (blocks 3 - 5 and the head on the tensor-core path) ----
+//
+// Laid end to end on one time axis, a frame of L rows yields L - 31 valid outputs of a k = 32
+// convolution and 31 that straddle two frames: 32 % of block 3's rows, 47 % of block 4's and (in
+// its 16 frames x 8 rows tiles) 50 % of block 5's were computed and dropped.  These layers
+// therefore keep their activations FRAME-MAJOR, planes[plane][position][c / 8][frame][8]: output
+// position t of every frame is then one dense product over K = (tap j, channel c) whose operand,
+// position t + j, is the contiguous group range [t C / 8, (t + 32) C / 8) -- a k = 1 launch of
+// conv1d_tc_kernel with the batch index as the position (TcConvArgs::item_groups) and frames as
+// rows, no row wasted.
+
+// (C_out, C_in, K) -> (C_out, K C_in), column j C_in + c
+__global__ void tap_major_weight_kernel(
+    const float* __restrict__ w, float* __restrict__ out, int c_out, int c_in, int k) {
+    const size_t total = (size_t)c_out * c_in * k;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / ((size_t)c_in * k));
+        const int rest = (int)(idx % ((size_t)c_in * k));
+        const int j = rest / c_in, c = rest % c_in;
+        out[idx] = w[((size_t)o * c_in + c) * k + j];
+    }
+}
+
+constexpr int kStatSlices = 16;
+
+// in: (positions, channels, frames) = `rows` rows of in_row floats.  partial[(slice count + f) 2 + i]:
+// sum (i = 0) and sum of squares (i = 1) of frame f over the rows slice, slice + 16, ...
+__global__ void __launch_bounds__(256) frame_major_stats_kernel(
+    const float* __restrict__ in, double* __restrict__ partial, int rows, size_t in_row, int count) {
+    __shared__ float shared[2][8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 32 + lane, slice = blockIdx.y;
+    const bool live = f < count;
+    const int step = kStatSlices * 8;
+    float sum[4] = {0.f, 0.f, 0.f, 0.f}, squares[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = slice + kStatSlices * warp;
+    const float* column = in + (live ? f : 0);
+    for (; r + 3 * step < rows; r += 4 * step) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = column[(size_t)(r + i * step) * in_row];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sum[i] += v[i]; squares[i] = fmaf(v[i], v[i], squares[i]); }
+    }
+    for (; r < rows; r += step) {
+        const float v = column[(size_t)r * in_row];
+        sum[0] += v;
+        squares[0] = fmaf(v, v, squares[0]);
+    }
+    shared[0][warp][lane] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+    shared[1][warp][lane] = (squares[0] + squares[1]) + (squares[2] + squares[3]);
+    __syncthreads();
+    if (warp < 2 && live) {
+        double total = 0.;
+        for (int w = 0; w < 8; ++w) total += shared[warp][w][lane];
+        partial[((size_t)slice * count + f) * 2 + warp] = total;
+    }
+}
+
+// LayerNorm over (channels, positions) of every frame, written as the next layer's frame-major
+// operand planes[plane][t groups + g][kTcPad + f][8]; lanes are frames: every load and store of a
+// warp is one contiguous run
+__global__ void __launch_bounds__(256) frame_major_norm_planes_kernel(
+    const float* __restrict__ in, const double* __restrict__ partial, const float* __restrict__ weight,
+    const float* __restrict__ bias, __nv_bfloat16* __restrict__ planes, int channels, int positions,
+    size_t in_row, int count, int t_pad) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 32 + lane;
+    if (f >= count) return;
+    double sum = 0., squares = 0.;
+    for (int slice = 0; slice < kStatSlices; ++slice) {
+        sum += partial[((size_t)slice * count + f) * 2];
+        squares += partial[((size_t)slice * count + f) * 2 + 1];
+    }
+    const double total = (double)channels * positions;
+    const double mean_d = sum / total;
+    const float mean = (float)mean_d;
+    const float rstd = (float)(1. / sqrt(fmax(squares / total - mean_d * mean_d, 0.) + 1e-5));
+    const int groups = channels / 8, work = positions * groups;
+    uint4* hi_plane = reinterpret_cast<uint4*>(planes);
+    uint4* lo_plane = hi_plane + (size_t)work * t_pad;
+    for (int idx = blockIdx.y * 8 + warp; idx < work; idx += gridDim.y * 8) {
+        const int t = idx / groups, g = idx % groups;
+        const float* source = in + ((size_t)t * channels + g * 8) * in_row + f;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = source[(size_t)e * in_row];
+        unsigned int hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = g * 8 + 2 * e;
+            tc::split_pair(
+                (x[2 * e] - mean) * rstd * weight[(size_t)c * positions + t] + bias[(size_t)c * positions + t],
+                (x[2 * e + 1] - mean) * rstd * weight[(size_t)(c + 1) * positions + t] +
+                    bias[(size_t)(c + 1) * positions + t],
+                hi[e], lo[e]);
+        }
+        const size_t row = (size_t)idx * t_pad + kTcPad + f;
+        hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // Block 1's weight (32, 256, 32) as the weight (128, 1024, 9) of the convolution folded by 4
 // in time: W4[(q, o), (p, c), J] = W[o, c, 4 J + p - q], zero where that tap does not exist
 __global__ void fold_weight_kernel(const float* __restrict__ w, float* __restrict__ folded) {
@@ -664,6 +771,7 @@ int resampler(pmn_pitch* p, int sample_rate, const pmn_pitch::Resampler** out) {
 struct Workspace {
     float *resampled, *conv, *act, *logits_t, *masked, *distribution, *pooled, *sums, *padded;
     float2* stats;
+    double* partial;
     __nv_bfloat16 *planes, *planes0;
     int* bins;
     void* viterbi;
@@ -695,9 +803,12 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     w.conv = (float*)take(fb * 256 * (kCropped + 1) * 4);                 // largest conv output (layer 0)
     w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
     // tensor-core operand planes: the widest is block 0's output (256 channels x 481 rows per frame)
-    w.planes = (__nv_bfloat16*)take(std::max(
+    // (the frame-major layers' operands have one row per frame, padded to the tile, per
+    // (position, channel group): block 5's 35 x 256 channels are the most)
+    w.planes = (__nv_bfloat16*)take(std::max(std::max(
         tc_planes_elements(1, 256, (int)(fb + 16) * 482),
-        tc_planes_elements(1, kFold * 256, (int)(fb + 16) * (kFoldStride / kFold))) * 2);
+        tc_planes_elements(1, kFold * 256, (int)(fb + 16) * (kFoldStride / kFold))),
+        tc_planes_elements(1, kLength[5] * kChannels[5], (int)fb)) * 2);
     // block 0's own operand (im2col rows of a sub-chunk of frames, 32 "channels")
     const int item_rows = shared_item_rows(frames, hop);
     const size_t shared_rows = item_rows ? (size_t)shared_group(batch, item_rows) * item_rows : 0;
@@ -709,6 +820,7 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     w.padded = (float*)take(shared_rows * 4);
     w.sums = (float*)take(shared_rows * 4);          // 2 x (shared_rows / 2) column sums
     w.stats = (float2*)take(fb * sizeof(float2));    // mean, 1 / std per frame of a chunk
+    w.partial = (double*)take(fb * kStatSlices * 2 * sizeof(double));   // frame-major LayerNorm sums
     w.logits_t = (float*)take(fb * kBins * 4);
     w.masked = (float*)take(total * kBins * 4);
     w.distribution = (float*)take(total * kBins * 4);
@@ -776,6 +888,23 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
                 p->norm_bias[i] = nb->data;
                 continue;
             }
+            if (i >= kFrameMajorFirst) {
+                // frame-major layer: (C_out, C_in, 32) -> (C_out, 32 C_in) with K = (tap, channel)
+                float* tap_major;
+                PMN_TRY(alloc(p, w->numel(), &tap_major));
+                {
+                    LaunchScope scope("tap_major_weight_kernel", stream);
+                    tap_major_weight_kernel<<<1024, 256, 0, stream>>>(
+                        w->data, tap_major, kChannels[i + 1], kChannels[i], kKernel);
+                    PMN_TRY(launched("tap_major_weight_kernel"));
+                }
+                PMN_TRY(launch_pack_tc_weight(
+                    tap_major, p->conv_slabs[i], kChannels[i + 1], kKernel * kChannels[i], 1, false, stream));
+                p->conv_bias[i] = b->data;
+                p->norm_weight[i] = nw->data;
+                p->norm_bias[i] = nb->data;
+                continue;
+            }
             // block 0: (256, 1, 32) is read as a (256, 32, 1) 1x1 conv over the 32 taps
             PMN_TRY(launch_pack_tc_weight(
                 w->data, p->conv_slabs[i], kChannels[i + 1], i == 0 ? kKernel : kChannels[i],
@@ -798,7 +927,15 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
         float* slabs;
         PMN_TRY(alloc(p, w->numel(), &slabs));
         p->head_slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
-        PMN_TRY(launch_pack_tc_weight(w->data, p->head_slabs, kBins, 2048, 1, false, stream));
+        // the head reads block 5's frame-major output: K = (position t, channel c)
+        float* tap_major;
+        PMN_TRY(alloc(p, w->numel(), &tap_major));
+        {
+            LaunchScope scope("tap_major_weight_kernel", stream);
+            tap_major_weight_kernel<<<1024, 256, 0, stream>>>(w->data, tap_major, kBins, 512, 4);
+            PMN_TRY(launched("tap_major_weight_kernel"));
+        }
+        PMN_TRY(launch_pack_tc_weight(tap_major, p->head_slabs, kBins, 2048, 1, false, stream));
     } else {
         PMN_TRY(alloc(p, w->numel(), &p->head_weight));
         PMN_TRY(launch_pack_conv1d_weight(w->data, p->head_weight, kBins, 2048, 1, stream));
@@ -991,6 +1128,32 @@ int pitch_forward(
         }
         const int padded = (count + 15) / 16 * 16;  // frame-mode tiles cover 16 frames
         for (int i = tensor_cores ? 1 : 0; i < kLayers; ++i) {
+            if (tensor_cores && i >= kFrameMajorFirst) {
+                // frame-major layer: one dense product per output position, rows = frames
+                const int c_in = kChannels[i], c_out = kChannels[i + 1];
+                const int positions_in = kLength[i], positions_out = kLength[i + 1];
+                const int t_pad = tc_padded_length(count);
+                TcConvArgs a;
+                a.x_planes = w.planes; a.w_slabs = p->conv_slabs[i]; a.bias = p->conv_bias[i];
+                a.out = w.conv; a.batch = positions_out; a.c_in = kKernel * c_in; a.c_out = c_out;
+                a.k = 1; a.t_len = count; a.valid = true; a.relu = true; a.out_row = count;
+                a.item_groups = c_in / 8; a.plane_groups = positions_in * (c_in / 8);
+                PMN_TRY(launch_conv1d_tc(a, stream));
+                {
+                    dim3 grid(ceil_div(count, 32), kStatSlices);
+                    LaunchScope scope("frame_major_stats_kernel", stream);
+                    frame_major_stats_kernel<<<grid, 256, 0, stream>>>(
+                        w.conv, w.partial, positions_out * c_out, count, count);
+                    PMN_TRY(launched("frame_major_stats_kernel"));
+                }
+                dim3 grid(ceil_div(count, 32), 16);
+                LaunchScope scope("frame_major_norm_planes_kernel", stream);
+                frame_major_norm_planes_kernel<<<grid, 256, 0, stream>>>(
+                    w.conv, w.partial, p->norm_weight[i], p->norm_bias[i], w.planes, c_out,
+                    positions_out, count, count, t_pad);
+                PMN_TRY(launched("frame_major_norm_planes_kernel"));
+                continue;
+            }
             const int l_in = stride_of(i);                       // frame stride of the input rows
             const bool folded = tensor_cores && i == 1;          // block 1: folded by 4 in time
             const size_t conv_rows = folded ? (size_t)count * (l_in / kFold) - (kFoldTaps - 1)
@@ -1023,7 +1186,15 @@ int pitch_forward(
                 a.t_in = count * l_in; a.t_out = (int)row; a.k = kKernel; a.out_act = 2;
                 PMN_TRY(launch_conv1d(a, stream));
             }
-            if (tensor_cores && i < kLayers - 1) {
+            if (tensor_cores && i + 1 == kFrameMajorFirst) {
+                // the next block is frame-major: planes[plane][t groups + g][kTcPad + f][8]
+                LaunchScope scope("pool_norm_planes_kernel", stream);
+                pool_norm_planes_kernel<<<count, 256, 0, stream>>>(
+                    w.conv, p->norm_weight[i], p->norm_bias[i], w.planes, kChannels[i + 1], l_conv,
+                    kLength[i + 1], false, row, count, tc_padded_length(count), false, kLength[i + 1],
+                    false, folded, 0, 0, 0, 0, true);
+                PMN_TRY(launched("pool_norm_planes_kernel"));
+            } else if (tensor_cores && i < kLayers - 1) {
                 // the next block runs on the tensor cores: write its operand planes
                 const int stride_next = stride_of(i + 1);
                 const int frames_out = i + 1 == kLayers - 1 ? padded : count;
