@@ -646,8 +646,11 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
     if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2>(a, 1, stream);
-    if (a.c_in == 4096) return launch_variant<4096, 256, 1, 32, 3, 2, kConv, 0, false, 4>(a, 1, stream);
-    if (a.c_in == 8192) return launch_variant<8192, 256, 1, 32, 3, 2, kConv, 0, false, 4>(a, 2, stream);
+    // K = 4096 / 8192 with 256 columns: a 128-row tile streams its whole 4 MB weight from L2 in 98 k
+    // MMA cycles (43 B per cycle and SM: the L2 limit), so a tile takes 256 rows (two subtiles per
+    // weight slab) and a single accumulator stage -- the exposed epilogue is 2 % of such a tile
+    if (a.c_in == 4096) return launch_variant<4096, 256, 2, 32, 3, 1>(a, 1, stream);
+    if (a.c_in == 8192) return launch_variant<8192, 256, 2, 32, 3, 1>(a, 2, stream);
     return launch_variant<128, 256, 1, 32, 4, 2>(a, 1, stream);
 }
 

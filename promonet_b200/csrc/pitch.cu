@@ -799,9 +799,13 @@ Workspace carve(void* base, int batch, int out_samples, int frames, int frame_ba
     };
     const size_t total = (size_t)batch * frames;
     const size_t fb = (size_t)std::min<size_t>(frame_batch, total);
+    // block 0 frame by frame (the fp32 path, and the tensor-core path when the hop is odd) never
+    // takes more than kSubFrames frames at a time, whatever the frame batch
+    const size_t fb0 = std::min<size_t>(fb, kSubFrames);
     w.resampled = (float*)take((size_t)batch * out_samples * 4);
-    w.conv = (float*)take(fb * 256 * (kCropped + 1) * 4);                 // largest conv output (layer 0)
-    w.act = (float*)take(fb * 256 * 481 * 4);                        // largest block output / input
+    // largest conv output: block 0 frame by frame, else block 1 (128 columns x 121 rows per frame)
+    w.conv = (float*)take(std::max(fb0 * 256 * (kCropped + 1), fb * 128 * (kFoldStride / kFold)) * 4);
+    w.act = (float*)take(fb0 * 256 * 481 * 4);                       // largest block output / input (fp32 path)
     // tensor-core operand planes: the widest is block 0's output (256 channels x 481 rows per frame)
     // (the frame-major layers' operands have one row per frame, padded to the tile, per
     // (position, channel group): block 5's 35 x 256 channels are the most)
@@ -1040,8 +1044,9 @@ int pitch_forward(
         PMN_TRY(launched("column_sums_kernel"));
     }
     const int group_end = (item0 + items) * frames;
-    for (int first = item0 * frames; first < group_end; first += frame_batch) {
-        const int count = std::min(frame_batch, group_end - first);
+    const int chunk = tensor_cores ? frame_batch : std::min(frame_batch, kSubFrames);
+    for (int first = item0 * frames; first < group_end; first += chunk) {
+        const int count = std::min(chunk, group_end - first);
         // Tensor-core path: frame strides are even where a MaxPool follows, so pooling
         // pairs never straddle two frames and the conv epilogue can pool adjacent lanes
         auto stride_of = [&](int i) {

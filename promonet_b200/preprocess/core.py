@@ -13,6 +13,12 @@ __all__ = ['from_audio', 'from_audio_batch', 'from_file', 'from_file_to_file', '
 
 SUPPORTED = ('loudness', 'pitch', 'periodicity', 'spectrogram', 'mels')
 
+# Frames per pass of the pitch network.  The reference hands penn batch_size=2048
+# (preprocess/core.py:77), a memory bound of its frame-by-frame network; no result depends on
+# it.  Here a pass costs 0.6 MB of workspace per frame and larger passes fill the 148 SMs better
+# (the last two blocks have 4 and 35 output positions per frame to spread over them).
+FRAME_BATCH = 8192
+
 
 def from_audio(
     audio: torch.Tensor,
@@ -78,7 +84,7 @@ def from_audio_batch(
     if 'pitch' in features or 'periodicity' in features:
         pitch, periodicity = _pitch_model(device, pitch_checkpoint)(
             audio, sample_rate, config.HOPSIZE / config.SAMPLE_RATE,
-            config.FMIN, config.FMAX, 2048)
+            config.FMIN, config.FMAX, FRAME_BATCH)
         if 'pitch' in features:
             result.append(pitch)
         if 'periodicity' in features:
