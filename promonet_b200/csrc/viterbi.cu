@@ -15,6 +15,10 @@
 // are bit-exact against the CPU recurrence on the same log inputs.
 #include <math.h>
 
+#include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <cooperative_groups.h>
 
 #include "spectral.cuh"
@@ -31,6 +35,7 @@ constexpr int kClusterSize = 8;
 constexpr int kSplit = 4;                       // threads per state
 constexpr int kClusterThreads = 736;      // 23 warps: 4 threads x 180 states, 88 registers each
 constexpr int kClusterSmem = 200 * 1024;
+constexpr int kPair = 4;                        // utterances a cluster decodes at once, at most (below)
 // Bands of at most kSplit * kRegisterBand rows (penn's pitch transition: 181) stay in REGISTERS:
 // thread (state, part) keeps rows part, part + kSplit, ... of its column for the whole utterance,
 // so a band entry costs one conflict-free shared-memory load (the scores) instead of two loads
@@ -45,7 +50,7 @@ __host__ __device__ inline int cluster_slice(int states) {
 // floats of shared memory the fast path needs for a given band width
 __host__ __device__ inline size_t cluster_floats(int states, int max_width) {
     const int slice = cluster_slice(states);
-    return (((size_t)max_width * (slice | 1) + 3) & ~(size_t)3) + 2 * (size_t)kClusterSize * slice + 16;
+    return (((size_t)max_width * (slice | 1) + 3) & ~(size_t)3) + 2 * kPair * (size_t)kClusterSize * slice + 16;
 }
 
 
@@ -182,14 +187,24 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(
 // (dense transition matrices): viterbi_kernel then does the work.
 // ---------------------------------------------------------------------------
 
+// A B200 runs 15 clusters of 8 CTAs at once at one CTA per SM (cudaOccupancyMaxActiveClusters;
+// profiles/debug/cluster_probe.cu), so a batch of 32 utterances at one per cluster takes three
+// waves, the last with two clusters.  A cluster therefore decodes up to kPair utterances at once,
+// as many as it takes to fit the batch into one wave (launch_viterbi): their recurrences are
+// independent, the frame of one is scanned while the scores of another travel, and the band
+// registers serve all of them (measured per frame and utterance: 5.1 kcycles alone, 4.0 in pairs).
+
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClusterThreads, 1)
 viterbi_cluster_kernel(
     const float* __restrict__ observation, const int* __restrict__ batch_frames,
     const float* __restrict__ initial, bool log_probs,
     const float* __restrict__ band, const int* __restrict__ lo, const int* __restrict__ width,
     const int* __restrict__ max_width_ptr,
-    short* __restrict__ psi, int* __restrict__ indices, int frames, int states) {
+    short* __restrict__ psi, int* __restrict__ indices, int frames, int states, int batch, int per_cluster,
+    long long* __restrict__ debug) {
     namespace cg = cooperative_groups;
+    long long stamps[4];
+    if (debug) stamps[0] = clock64();
     const int max_width = *max_width_ptr;
     const int slice = cluster_slice(states);
     if (cluster_floats(states, max_width) * sizeof(float) > (size_t)kClusterSmem ||
@@ -197,30 +212,26 @@ viterbi_cluster_kernel(
         return;  // uniform across the grid: the general kernel handles it
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int b = blockIdx.x / kClusterSize;
+    const int b0 = (blockIdx.x / kClusterSize) * per_cluster;      // first utterance of this cluster
+    const int items = min(per_cluster, batch - b0);
     const int tid = threadIdx.x;
     const int pitch = slice | 1;                 // odd row pitch: conflict-free column reads
 
     extern __shared__ float smem[];
     float* band_s = smem;                        // [max_width][pitch]
-    // every CTA keeps the WHOLE score vector of the previous and of the current frame.  A CTA
-    // publishes each new score straight into all eight copies with st.async (a remote
-    // shared-memory store that reports its bytes to an mbarrier of the destination CTA), so a
-    // frame needs no cluster barrier and no fence: a CTA starts frame t + 1 as soon as the
+    // every CTA keeps the WHOLE score vector of the previous and of the current frame of each of
+    // its utterances.  A CTA publishes each new score straight into all eight copies with st.async
+    // (a remote shared-memory store that reports its bytes to an mbarrier of the destination CTA),
+    // so a frame needs no cluster barrier and no fence: a CTA starts frame t + 1 as soon as the
     // transaction barrier of frame t has counted the bytes of all `states` scores.  The two
     // buffers cannot be overwritten early: nobody can finish frame t + 1 (and write into the
     // buffer frame t was computed from) before every CTA has sent all its frame-t scores,
     // i.e. has finished reading that buffer.
     const int whole = kClusterSize * slice;
-    float* full = band_s + (((size_t)max_width * pitch + 3) & ~(size_t)3);   // [2][whole], 16 B aligned
-    __shared__ uint64_t landed[2];                      // landed[p]: scores of a frame of parity p
+    float* full = band_s + (((size_t)max_width * pitch + 3) & ~(size_t)3);   // [kPair][2][whole] (+ 16)
+    __shared__ uint64_t landed[kPair][2];               // landed[u][p]: scores of a frame of parity p
 
     const int j0 = rank * slice;
-    const int length = batch_frames ? min(batch_frames[b], frames) : frames;
-    const float* obs = observation + (size_t)b * frames * states;
-    short* back = psi + (size_t)b * frames * states;
-    int* path = indices + (size_t)b * frames;
-
     const bool in_registers = max_width <= kSplit * kRegisterBand;
     if (!in_registers) {
         for (int idx = tid; idx < max_width * slice; idx += kClusterThreads) {
@@ -228,10 +239,9 @@ viterbi_cluster_kernel(
             band_s[k * pitch + jl] = j0 + jl < states ? band[(size_t)k * states + j0 + jl] : -INFINITY;
         }
     }
-    for (int idx = tid; idx < 2 * whole + 16; idx += kClusterThreads) full[idx] = -INFINITY;  // padded states
+    for (int idx = tid; idx < kPair * 2 * whole + 16; idx += kClusterThreads) full[idx] = -INFINITY;  // padded states
     if (tid == 0) {
-        tc::mbar_init(landed, 1);
-        tc::mbar_init(landed + 1, 1);
+        for (int i = 0; i < kPair * 2; ++i) tc::mbar_init(&landed[0][0] + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int jl = tid / kSplit, part = tid % kSplit;
@@ -249,149 +259,163 @@ viterbi_cluster_kernel(
             band_r[i] = (owner && k < count) ? band[(size_t)k * states + j] : -INFINITY;
         }
     }
-    // Publishing.  Measured: the frame is bounded by the number of remote-store packets, not by
-    // their bytes (four states per 16-byte st.async doubled the packets of a warp and made the
-    // frame 33 % slower).  When the slice is a multiple of 4 states every thread therefore
-    // writes its state's score into the CTA's OWN copy, and after one CTA barrier seven threads
-    // each send the whole slice to one peer as a single bulk copy (cp.async.bulk shared::cta ->
-    // shared::cluster, bytes reported to the peer's transaction barrier).  Otherwise every
-    // thread sends its score to kClusterSize / kSplit destinations with 4-byte st.async.
-    const bool bulk = kBulkPublish && slice % 4 == 0;
+    // the kSplit threads of a state share the publishing: thread `part` writes the copies of
+    // CTAs part * (kClusterSize / kSplit) ...  (Measured alternatives, profiles/
+    // r2_viterbi_breakdown.txt: four states per 16-byte st.async double the remote packets of a
+    // warp, +33 %; one bulk copy of the slice per peer after a CTA barrier, +7 %.)
     constexpr int kPeersPerThread = kClusterSize / kSplit;
     uint32_t copies[kPeersPerThread], barriers[kPeersPerThread];   // shared::cluster addresses
-    if (bulk) {
-        const uint32_t peer = tid < kClusterSize ? tid : 0;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(copies[0]) : "r"(tc::smem_u32(full + j0)), "r"(peer));
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                     : "=r"(barriers[0]) : "r"(tc::smem_u32(landed)), "r"(peer));
-    } else {
 #pragma unroll
-        for (int i = 0; i < kPeersPerThread; ++i) {
-            const uint32_t peer = part * kPeersPerThread + i;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                         : "=r"(copies[i]) : "r"(tc::smem_u32(full + j0 + jl)), "r"(peer));
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-                         : "=r"(barriers[i]) : "r"(tc::smem_u32(landed)), "r"(peer));
-        }
+    for (int i = 0; i < kPeersPerThread; ++i) {
+        const uint32_t peer = part * kPeersPerThread + i;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(copies[i]) : "r"(tc::smem_u32(full + j0 + jl)), "r"(peer));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                     : "=r"(barriers[i]) : "r"(tc::smem_u32(&landed[0][0])), "r"(peer));
     }
-    // score of frame t (parity t & 1) into every copy; called by every thread of the CTA
-    auto publish = [&](float score, int parity) {
-        if (bulk) {
-            if (owner && part == 0) full[parity * whole + j0 + jl] = score;
-            tc::fence_proxy_async();
-            __syncthreads();
-            if (tid < kClusterSize && tid != rank)
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                    ::"r"(copies[0] + (uint32_t)(parity * whole) * 4u),
-                      "r"(tc::smem_u32(full + parity * whole + j0)), "r"((uint32_t)slice * 4u),
-                      "r"(barriers[0] + (uint32_t)parity * 8u) : "memory");
-            return;
-        }
-        if (!owner) return;
+    // score of frame t (parity t & 1) of utterance u into every copy
+    auto publish = [&](int u, float score, int parity) {
 #pragma unroll
         for (int i = 0; i < kPeersPerThread; ++i)
             asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
-                         ::"r"(copies[i] + (uint32_t)(parity * whole) * 4u), "r"(__float_as_uint(score)),
-                           "r"(barriers[i] + (uint32_t)parity * 8u) : "memory");
+                         ::"r"(copies[i] + (uint32_t)((u * 2 + parity) * whole) * 4u), "r"(__float_as_uint(score)),
+                           "r"(barriers[i] + (uint32_t)(u * 2 + parity) * 8u) : "memory");
     };
-    // all scores of frame t have landed in this CTA's copy.  Only the threads that
-    // read the scores wait (a thread that reads nothing could otherwise still be polling for
-    // frame t when the same barrier completes frame t + 2; a reader cannot lag that far,
-    // because frame t + 2 cannot complete anywhere without its frame t + 1 score)
-    const uint32_t frame_bytes = (uint32_t)(bulk ? (kClusterSize - 1) * slice : states) * 4u;
-    auto await = [&](int t) {
-        if (tid == 0) tc::mbar_expect_tx(landed + (t & 1), frame_bytes);
-        if (owner || tid == 0) tc::mbar_wait(landed + (t & 1), (t >> 1) & 1);
+    // all `states` scores of frame t of utterance u have landed in this CTA's copy.  Only the
+    // threads that read the scores wait (a thread that reads nothing could otherwise still be
+    // polling for frame t when the same barrier completes frame t + 2; a reader cannot lag that
+    // far, because frame t + 2 cannot complete anywhere without its frame t + 1 score)
+    auto await = [&](int u, int t) {
+        if (tid == 0) tc::mbar_expect_tx(&landed[u][t & 1], (uint32_t)states * 4u);
+        if (owner || tid == 0) tc::mbar_wait(&landed[u][t & 1], (t >> 1) & 1);
     };
-    auto load_observation = [&](int t) {
-        if (!owner || t >= length) return 0.f;
-        const float o = obs[(size_t)t * states + j];
+    __shared__ int length[kPair];          // uniform per CTA: kept out of the registers
+    __shared__ const float* obs[kPair];
+    __shared__ short* back[kPair];
+    float next_observation[kPair];
+    if (tid < kPair) {
+        const int u = tid, b = b0 + u;
+        length[u] = u < items ? (batch_frames ? min(batch_frames[b], frames) : frames) : 0;
+        obs[u] = observation + (size_t)(u < items ? b : b0) * frames * states;
+        back[u] = psi + (size_t)(u < items ? b : b0) * frames * states;
+    }
+    __syncthreads();
+    int longest = 0;
+#pragma unroll
+    for (int u = 0; u < kPair; ++u) longest = max(longest, length[u]);
+    auto load_observation = [&](int u, int t) {
+        if (!owner || t >= length[u]) return 0.f;
+        const float o = obs[u][(size_t)t * states + j];
         return log_probs ? o : logf(o);
     };
 
     cluster.sync();      // every copy is initialised and every barrier exists before the first store
-    publish(owner ? (log_probs ? initial[j] : logf(initial[j])) + load_observation(0) : -INFINITY, 0);
-    float next_observation = load_observation(1);    // one frame ahead of its use
-    await(0);
-
-    int current = 0;
-    for (int t = 1; t < max(length, 1); ++t) {
-        const float observed = next_observation;
-        next_observation = load_observation(t + 1);
-        float best = -INFINITY;
-        int arg = 0x7fffffff;
-        if (in_registers) {
-            // rows part, part + kSplit, ...: the lanes of a warp read 11 consecutive scores per
-            // step (conflict-free); rows past the band carry -inf and never win
-            const float* source = full + current * whole + first + part;
-            int winner = -1;
-            constexpr int kGroup = 8;     // loads issued together, ahead of their compare chain
-            float scores[kGroup];
+    if (debug) stamps[1] = clock64();
 #pragma unroll
-            for (int i0 = 0; i0 < kRegisterBand; i0 += kGroup) {
-#pragma unroll
-                for (int i = 0; i < kGroup; ++i)
-                    if (i0 + i < kRegisterBand) scores[i] = source[kSplit * (i0 + i)];
-#pragma unroll
-                for (int i = 0; i < kGroup; ++i) {
-                    if (i0 + i < kRegisterBand) {
-                        const float value = scores[i] + band_r[i0 + i];
-                        if (value > best) { best = value; winner = i0 + i; }
-                    }
-                }
-            }
-            if (winner >= 0) arg = first + kSplit * winner + part;
-        } else if (owner) {
-            const float* column = band_s + jl;
-            const float* source = full + current * whole + first;
-            for (int k = begin; k < end; ++k) {
-                const float value = source[k] + column[k * pitch];
-                if (value > best) { best = value; arg = first + k; }
-            }
-        }
-        // combine the kSplit parts of a state (adjacent lanes), lowest index on ties
-#pragma unroll
-        for (int offset = 1; offset < kSplit; offset <<= 1) {
-            const float other = __shfl_xor_sync(0xffffffffu, best, offset);
-            const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
-            if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
-        }
-        publish(best + observed, t & 1);
-        if (owner && part == 0) back[(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
-        current ^= 1;
-        await(t);
+    for (int u = 0; u < kPair; ++u) {
+        if (length[u] > 0 && owner)
+            publish(u, (log_probs ? initial[j] : logf(initial[j])) + load_observation(u, 0), 0);
+        next_observation[u] = load_observation(u, 1);    // one frame ahead of its use
     }
 
-    // final argmax and backtrace on the first CTA of the cluster (it holds the whole vector)
+    for (int t = 1; t < longest; ++t) {
+#pragma unroll
+        for (int u = 0; u < kPair; ++u) {
+            if (t >= length[u]) continue;                // uniform across the cluster
+            await(u, t - 1);
+            const float observed = next_observation[u];
+            next_observation[u] = load_observation(u, t + 1);
+            const float* previous = full + (size_t)(u * 2 + ((t - 1) & 1)) * whole;
+            float best = -INFINITY;
+            int arg = 0x7fffffff;
+            if (in_registers) {
+                // rows part, part + kSplit, ...: the lanes of a warp read 11 consecutive scores per
+                // step (conflict-free); rows past the band carry -inf and never win
+                const float* source = previous + first + part;
+                int winner = -1;
+                constexpr int kGroup = 8;     // loads issued together, ahead of their compare chain
+                float scores[kGroup];
+#pragma unroll
+                for (int i0 = 0; i0 < kRegisterBand; i0 += kGroup) {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i)
+                        if (i0 + i < kRegisterBand) scores[i] = source[kSplit * (i0 + i)];
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        if (i0 + i < kRegisterBand) {
+                            const float value = scores[i] + band_r[i0 + i];
+                            if (value > best) { best = value; winner = i0 + i; }
+                        }
+                    }
+                }
+                if (winner >= 0) arg = first + kSplit * winner + part;
+            } else if (owner) {
+                const float* column = band_s + jl;
+                const float* source = previous + first;
+                for (int k = begin; k < end; ++k) {
+                    const float value = source[k] + column[k * pitch];
+                    if (value > best) { best = value; arg = first + k; }
+                }
+            }
+            // combine the kSplit parts of a state (adjacent lanes), lowest index on ties
+#pragma unroll
+            for (int offset = 1; offset < kSplit; offset <<= 1) {
+                const float other = __shfl_xor_sync(0xffffffffu, best, offset);
+                const int other_arg = __shfl_xor_sync(0xffffffffu, arg, offset);
+                if (other > best || (other == best && other_arg < arg)) { best = other; arg = other_arg; }
+            }
+            if (owner) {
+                publish(u, best + observed, t & 1);
+                if (part == 0) back[u][(size_t)t * states + j] = (short)(arg == 0x7fffffff ? 0 : arg);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kPair; ++u)
+        if (length[u] > 0) await(u, length[u] - 1);
+
+    // final argmax and backtrace of utterance u on CTA u of the cluster (every CTA holds the whole
+    // vector)
+    if (debug) stamps[2] = clock64();
     __threadfence();
     cluster.sync();
-    if (rank != 0) return;
+    if (rank >= items) return;
+    const int mine = rank;
+    const int my_length = length[mine];
+    int* path = indices + (size_t)(b0 + mine) * frames;
     // The backtrace is a chain of `length` dependent loads.  Followed through global memory
     // by one thread it costs an L2 round trip per frame; instead all threads stage the
     // back-pointers of a block of frames in the shared memory the band no longer needs, and
     // the walker steps through them there.
     __shared__ int walker_state;
     if (tid == 0) {
-        const float* last = full + current * whole;
+        const float* last = full + (size_t)(mine * 2 + ((my_length - 1) & 1)) * whole;
         int state = 0;
         float best = -INFINITY;
-        if (length > 0) {
+        if (my_length > 0) {
             for (int k = 0; k < whole; ++k)
                 if (k < states && last[k] > best) { best = last[k]; state = k; }
         }
         walker_state = state;
-        for (int t = max(length, 0); t < frames; ++t) path[t] = 0;
+        for (int t = max(my_length, 0); t < frames; ++t) path[t] = 0;
     }
     short* staged = reinterpret_cast<short*>(band_s);
+    const short* mine_back = back[mine];
     const int block_frames = max(1, (int)(((size_t)max_width * pitch * sizeof(float)) / ((size_t)states * sizeof(short))));
-    for (int hi = length - 1; hi >= 0; hi -= block_frames) {
+    const bool wide = ((size_t)states * sizeof(short)) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(mine_back) & 15) == 0;   // 16-byte loads
+    for (int hi = my_length - 1; hi >= 0; hi -= block_frames) {
         const int lo_frame = max(hi - block_frames + 1, 0);
         __syncthreads();                                  // the walker is done with the last block
         const size_t offset = (size_t)lo_frame * states;
         const int shorts = (hi - lo_frame + 1) * states;
-        for (int idx = tid; idx < shorts; idx += kClusterThreads) staged[idx] = __ldcg(back + offset + idx);
+        if (wide) {
+            const uint4* source = reinterpret_cast<const uint4*>(mine_back + offset);
+            uint4* target = reinterpret_cast<uint4*>(staged);
+            for (int idx = tid; idx < shorts / 8; idx += kClusterThreads) target[idx] = __ldcg(source + idx);
+        } else {
+            for (int idx = tid; idx < shorts; idx += kClusterThreads) staged[idx] = __ldcg(mine_back + offset + idx);
+        }
         __syncthreads();
         if (tid == 0) {
             int state = walker_state;
@@ -401,6 +425,10 @@ viterbi_cluster_kernel(
             }
             walker_state = state;
         }
+    }
+    if (debug && blockIdx.x == 0 && tid == 0) {
+        stamps[3] = clock64();
+        for (int i = 0; i < 4; ++i) debug[i] = stamps[i] - stamps[0];
     }
 }
 
@@ -477,10 +505,49 @@ int launch_viterbi(
     {
         // banded fast path (returns at once if the band does not fit in shared memory)
         LaunchScope scope("viterbi_cluster_kernel", stream);
-        viterbi_cluster_kernel<<<batch * kClusterSize, kClusterThreads, kClusterSmem, stream>>>(
+        // more utterances than clusters that run at once (8 GPCs x 2 clusters of 8 SMs): two per cluster
+        static long long* debug = nullptr;
+        static bool debug_checked = false;
+        if (!debug_checked) {
+            debug_checked = true;
+            const char* flag = getenv("PMN_VITERBI_DEBUG");
+            if (flag && flag[0] == '1') cudaMalloc(&debug, 4 * sizeof(long long));
+        }
+        // as many utterances per cluster as it takes to run the batch in one wave of clusters
+        static int wave = 0;
+        if (!wave) {
+            cudaLaunchConfig_t config = {};
+            config.gridDim = dim3(kClusterSize);
+            config.blockDim = dim3(kClusterThreads);
+            config.dynamicSmemBytes = kClusterSmem;
+            cudaLaunchAttribute attribute;
+            attribute.id = cudaLaunchAttributeClusterDimension;
+            attribute.val.clusterDim.x = kClusterSize;
+            attribute.val.clusterDim.y = attribute.val.clusterDim.z = 1;
+            config.attrs = &attribute;
+            config.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&wave, viterbi_cluster_kernel, &config) != cudaSuccess || wave < 1) {
+                cudaGetLastError();
+                wave = 15;      // measured on a B200
+            }
+        }
+        const char* pair_flag = getenv("PMN_VITERBI_PAIR");   // profiling aid: force the count
+        const int per_cluster = pair_flag ? std::max(1, std::min(kPair, atoi(pair_flag)))
+                                          : std::max(1, std::min(kPair, (batch + wave - 1) / wave));
+        const int clusters = (batch + per_cluster - 1) / per_cluster;
+        viterbi_cluster_kernel<<<clusters * kClusterSize, kClusterThreads, kClusterSmem, stream>>>(
             observation, batch_frames, initial, log_probs, w.band, w.lo, w.width, w.max_width,
-            w.psi, indices, frames, states);
+            w.psi, indices, frames, states, batch, per_cluster, debug);
         PMN_TRY(launched("viterbi_cluster_kernel"));
+        if (debug) {
+            // profiling aid (PMN_VITERBI_DEBUG=1): cycles of CTA 0 at the start of the frame loop,
+            // at its end and at the end of the backtrace
+            long long host[4];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(host, debug, sizeof(host), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "viterbi CTA 0: frame loop starts at %lld, ends at %lld, kernel ends at %lld cycles\n",
+                    host[1], host[2], host[3]);
+        }
     }
     LaunchScope scope("viterbi_kernel", stream);
     viterbi_kernel<<<batch, kThreads, smem, stream>>>(

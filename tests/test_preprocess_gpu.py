@@ -92,7 +92,11 @@ def viterbi_inputs(batch, frames, states, band=None, seed=0):
 
 
 @pytest.mark.parametrize('batch,frames,states,band', [
-    (1, 1, 7, None), (3, 50, 40, None), (2, 200, 333, 12), (4, 64, 1440, 90), (1, 30, 1025, 0)])
+    (1, 1, 7, None), (3, 50, 40, None), (2, 200, 333, 12), (4, 64, 1440, 90), (1, 30, 1025, 0),
+    # more than 16 utterances: two per cluster, interleaved (odd batch: the last cluster holds one);
+    # band 100 is wider than the register-resident band and takes the shared-memory scan;
+    # 40 utterances: three per cluster
+    (19, 40, 1440, 90), (18, 33, 1440, 100), (40, 12, 1440, 90)])
 def test_viterbi_bit_exact_on_log_inputs(pb, batch, frames, states, band):
     observation, transition, initial = viterbi_inputs(batch, frames, states, band, seed=frames)
     with np.errstate(divide='ignore'):
