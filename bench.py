@@ -381,14 +381,15 @@ def synthesis(ctx):
 
     # Roofline of the dominant kernel: same steps again with per-launch CUDA events
     dominant = 'conv1d_kernel' if math == _lib.MATH_FP32_SIMT else 'conv1d_tc_kernel'
-    names = ('conv1d_kernel', 'conv1d_tc_kernel', 'conv_pair_tc_kernel', 'conv_transpose1d_kernel',
+    names = ('conv1d_kernel', 'conv1d_tc_kernel', 'conv1d_tcw_kernel', 'conv_pair_tc_kernel', 'conv_transpose1d_kernel',
              'conv_transpose1d_tc_kernel', 'planes_from_f32_kernel', 'zero_plane_pads_kernel',
              'head_kernel', 'features_kernel', 'speaker_bias_kernel')
     shares = ctx.kernels(resident, names, args.steps)
-    tensor_ms = sum(shares.get(n, {'ms_per_step': 0.})['ms_per_step']
-                    for n in ('conv1d_tc_kernel', 'conv_pair_tc_kernel'))
-    tensor_launches = sum(shares.get(n, {'launches_per_step': 0})['launches_per_step']
-                          for n in ('conv1d_tc_kernel', 'conv_pair_tc_kernel'))
+    # the 72 residual-block convolutions run on three kernels (conv1d_tc_kernel: time on the M side;
+    # conv1d_tcw_kernel: weights on the M side, the narrow layers; conv_pair_tc_kernel: a fused pair)
+    resblock_kernels = ('conv1d_tc_kernel', 'conv1d_tcw_kernel', 'conv_pair_tc_kernel')
+    tensor_ms = sum(shares.get(n, {'ms_per_step': 0.})['ms_per_step'] for n in resblock_kernels)
+    tensor_launches = sum(shares.get(n, {'launches_per_step': 0})['launches_per_step'] for n in resblock_kernels)
     if math == _lib.MATH_FP32_SIMT:
         tensor_ms = shares[dominant]['ms_per_step']
         tensor_launches = shares[dominant]['launches_per_step']
@@ -422,8 +423,8 @@ def synthesis(ctx):
             'synchronous_api': 'promonet_b200.model.Generator.forward_host -> pmn_generator_forward_host'},
         'roofline': {
             'bound': 'tensor',
-            'kernel': dominant + (' + conv_pair_tc_kernel (the residual-block convolutions)'
-                                  if 'conv_pair_tc_kernel' in shares else ''),
+            'kernel': dominant + (' + conv1d_tcw_kernel + conv_pair_tc_kernel (the residual-block convolutions)'
+                                  if 'conv_pair_tc_kernel' in shares or 'conv1d_tcw_kernel' in shares else ''),
             'achieved': achieved, 'peak': peak['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
             'frac': achieved / peak['bf16_tflops_sustained'] if achieved else None,
             'peak_source': f"{peak['source']} sustained bf16 cuBLAS (kernel timed inside a long step)",

@@ -25,6 +25,8 @@
 //             fp32 and/or hi/lo-plane stores, MRF accumulate (hifigan.py:141-145)
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps
 // the MMAs of tile i + 1.
+#include <stdlib.h>
+
 #include "conv1d_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -622,8 +624,22 @@ bool tc_supported(int c_in, int c_out, int k, int dilation) {
            (k - 1) * dilation <= 2 * kMaxHalo;
 }
 
+namespace {
+// PMN_TCW: 0 never, 1 (default) where it is the faster kernel, 2 wherever it applies
+int tcw_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* flag = getenv("PMN_TCW");
+        mode = flag && flag[0] >= '0' && flag[0] <= '2' ? flag[0] - '0' : 1;
+    }
+    return mode;
+}
+}  // namespace
+
 int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     PMN_REQUIRE(a.x_planes && a.w_slabs, "conv1d_tc: null input");
+    if (tcw_mode() && tcw_applies(a) && (tcw_mode() == 2 || tcw_preferred(a)))
+        return launch_conv1d_tcw(a, a.w_slabs + tc_plain_weight_elements(a.c_out, a.c_in, a.k), stream);
     PMN_REQUIRE(a.out || a.out_planes || (a.accum && a.accum_mode), "conv1d_tc: no output");
     PMN_REQUIRE(a.batch > 0 && a.t_len > 0, "conv1d_tc: empty input");
     PMN_REQUIRE(a.k >= 1 && a.k <= 32 && (a.k - 1) * a.dilation <= 2 * kMaxHalo,
@@ -732,6 +748,8 @@ int launch_pack_tc_weight(
     const float* w, __nv_bfloat16* slabs, int c_out, int c_in, int k, bool frames, cudaStream_t stream) {
     TcPlan plan;
     PMN_REQUIRE(w && slabs && tc_conv_plan(c_in, c_out, frames, &plan), "pack_tc_weight: bad argument");
+    if (!frames && tcw_shape_supported(c_in, c_out, k))
+        PMN_TRY(launch_pack_tcw_weight(w, slabs + tc_plain_weight_elements(c_out, c_in, k), c_in, k, stream));
     const size_t total = (size_t)c_out * c_in * k;
     const int blocks = (int)min((size_t)2048, (total + 255) / 256);
     LaunchScope scope("pack_tc_weight_kernel", stream);

@@ -23,7 +23,7 @@ __device__ __forceinline__ int tc_padded_length_device(int t_len) {
     return kTcPad + (t_len + kTcTimeAlign - 1) / kTcTimeAlign * kTcTimeAlign + kTcPad;
 }
 inline size_t tc_planes_elements(int batch, int channels, int t_len) {
-    return (size_t)batch * 2 * channels * tc_padded_length(t_len);
+    return (size_t)batch * 2 * channels * tc_padded_length(t_len) + 8192;   // + kTcPlanesSlack
 }
 // Weight slabs (bf16 hi + lo = the bytes of the fp32 tensor): see pack_tc_weight_kernel
 struct TcPlan {
@@ -32,7 +32,15 @@ struct TcPlan {
     bool concat;   // hi and lo rows interleaved per K group (one wide MMA for a_hi)
 };
 bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan);
-inline size_t tc_weight_elements(int c_out, int c_in, int k) { return (size_t)2 * c_out * c_in * k; }
+// Narrow square layers (C = 32 / 64, odd k <= 11) also run with the weights on the M side of the
+// MMAs (conv1d_tcw.cu); their slabs in that kernel's format follow the plain ones in the buffer
+bool tcw_shape_supported(int c_in, int c_out, int k);
+size_t tcw_weight_elements(int channels, int k);
+inline size_t tc_plain_weight_elements(int c_out, int c_in, int k) { return (size_t)2 * c_out * c_in * k; }
+inline size_t tc_weight_elements(int c_out, int c_in, int k) {
+    return tc_plain_weight_elements(c_out, c_in, k) +
+           (tcw_shape_supported(c_in, c_out, k) ? tcw_weight_elements(c_in, k) : 0);
+}
 bool tc_supported(int c_in, int c_out, int k, int dilation);
 
 struct TcConvArgs {
@@ -65,6 +73,15 @@ struct TcConvArgs {
 };
 
 int launch_conv1d_tc(const TcConvArgs& args, cudaStream_t stream);
+// conv1d_tcw.cu: the same convolution for the narrow square layers (launch_conv1d_tc dispatches to
+// it when tcw_applies; PMN_TCW=0 in the environment keeps everything on conv1d_tc_kernel)
+bool tcw_applies(const TcConvArgs& args);     // the kernel can run it
+bool tcw_preferred(const TcConvArgs& args);   // ... and is the faster one (PMN_TCW=2: whenever it applies)
+int launch_conv1d_tcw(const TcConvArgs& args, const __nv_bfloat16* slabs, cudaStream_t stream);
+int launch_pack_tcw_weight(const float* w, __nv_bfloat16* slabs, int channels, int k, cudaStream_t stream);
+// rows a kernel may read past the end of a planes buffer (conv1d_tcw's window of the last tile):
+// every planes allocation ends with this many spare elements
+constexpr size_t kTcPlanesSlack = 8192;
 // Every following launch writes its cycle counters to `counters` (device, SMs x 40 int64); null = off
 void tc_set_debug_counters(long long* counters);
 

@@ -109,8 +109,8 @@ int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int 
     conv->k = k;
     conv->bias = bias->data;
     if (g->math == PMN_MATH_BF16X3_TC) {
-        float* slabs;  // two bf16 planes = the bytes of one fp32 tensor
-        PMN_TRY(alloc(g, shape->numel(), &slabs));
+        float* slabs;  // two bf16 planes = the bytes of one fp32 tensor (+ the narrow layers' second format)
+        PMN_TRY(alloc(g, (tc_weight_elements(channels, channels, k) + 1) / 2, &slabs));
         conv->slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
         return launch_pack_tc_weight(w, conv->slabs, channels, channels, k, false, stream);
     }
