@@ -25,6 +25,8 @@
 //             fp32 and/or hi/lo-plane stores, MRF accumulate (hifigan.py:141-145)
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps
 // the MMAs of tile i + 1.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdlib.h>
 
 #include "conv1d_tc.cuh"
@@ -63,7 +65,8 @@ constexpr int kMaxFrameLength = 35;
 // XS activation-slab stages: 2 everywhere except the k = 1 layers with a long K (frame-major pitch
 // blocks 4 and 5), where a 32-channel slab is only 768 cycles of MMAs and two stages do not cover
 // the L2 latency of the next slab.
-template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT, int XS = 2>
+// F8: "fp16 + 2 x fp8" operands (conv1d_tc.cuh); a second accumulator holds the fp8 corrections.
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT, int XS = 2, bool F8 = false>
 struct TcConfig {
     static constexpr int kTile = S * 128;
     static constexpr int kRowsMax =
@@ -76,19 +79,21 @@ struct TcConfig {
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
     static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 6144;
     static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
-    static constexpr int kColumns = AS * S * kCols;
+    static constexpr int kStageCols = (F8 ? 2 : 1) * S * kCols;   // TMEM columns of one accumulator stage
+    static constexpr int kColumns = AS * kStageCols;
     static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
                                   : kColumns <= 256 ? 256 : 512;
     static_assert(kColumns <= 512, "accumulators exceed TMEM");
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
     static_assert(C_IN % KB == 0 && KB % 16 == 0 && N % 32 == 0 && kCols <= 256, "shape");
     static_assert(MODE != kFrames || S == 1, "frame mode computes one 128-row tile");
+    static_assert(!F8 || (MODE == kConv && !CONCAT && KB % 32 == 0), "fp8 corrections: plain convolutions only");
 };
 
-template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, int UP, bool CONCAT, int XS>
+template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, int UP, bool CONCAT, int XS, bool F8>
 __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     TcConvArgs a, int t_pad, int tiles_per_item, int n_tiles, int num_tiles) {
-    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS>;
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS, F8>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* x_slabs = smem;
@@ -150,6 +155,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     if (a.debug) wait_x += clock64() - mark;
                     mbar_expect_tx(x_full + xs, x_bytes);
                     uint8_t* dst = x_slabs + xs * Cfg::kXSlab;
+                    if constexpr (F8) {
+                        // fp16 section: kGroups row groups of this K block; the two e4m3 sections:
+                        // kGroups / 2 row groups (16 channels a row) each
+#pragma unroll 1
+                        for (int g = 0; g < 2 * Cfg::kGroups; ++g) {
+                            const int section = g < Cfg::kGroups ? 0 : 1 + (g - Cfg::kGroups) / (Cfg::kGroups / 2);
+                            const int within = g < Cfg::kGroups ? g : (g - Cfg::kGroups) % (Cfg::kGroups / 2);
+                            const size_t group =
+                                (size_t)b * item_groups +
+                                (section == 0 ? kb * Cfg::kGroups
+                                              : C_IN / 8 + (section - 1) * (C_IN / 16) + kb * (Cfg::kGroups / 2)) + within;
+                            bulk_copy(dst + g * rows * 16, a.x_planes + (group * t_pad + kTcPad + t0 - left) * 8,
+                                      rows * 16, x_full + xs);
+                        }
+                    } else {
 #pragma unroll 1
                     for (int p = 0; p < 2; ++p) {
 #pragma unroll 1
@@ -160,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             bulk_copy(dst + (p * Cfg::kGroups + g) * rows * 16,
                                       a.x_planes + row0 * 8, rows * 16, x_full + xs);
                         }
+                    }
                     }
                     for (int tap = 0; tap < a.k; ++tap) {
                         const uint32_t ws = wcount % NW, wphase = (wcount / NW) & 1;
@@ -197,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 mbar_wait(acc_empty + as, aphase ^ 1);
                 if (a.debug) wait_acc += clock64() - mark;
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + as * (S * Cfg::kCols);
+                const uint32_t d_base = tmem_base + as * Cfg::kStageCols;
                 for (int kb = 0; kb < Cfg::kBlocks; ++kb) {
                     const uint32_t xs = xcount % Cfg::kXStages, xphase = (xcount / Cfg::kXStages) & 1;
                     ++xcount;
@@ -218,6 +239,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         for (int s = 0; s < S; ++s) {
                             const uint32_t row = s * 128 + tap * a.dilation;
                             const uint32_t d = d_base + s * Cfg::kCols;
+                            if constexpr (F8) {
+                                constexpr uint32_t idesc0 = instr_desc_format0(128, N);
+                                const uint32_t d_low = d + S * Cfg::kCols;      // the corrections' accumulator
+                                const uint32_t x8 = x_addr + Cfg::kGroups * rows * 16;
+                                const uint32_t w8 = w_addr + Cfg::kGroups * N * 16;
+#pragma unroll
+                                for (int kk = 0; kk < KB / 32; ++kk) {
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        // fp16 x fp16: channels 32 kk + 16 h .. + 15 (two 8-channel row groups)
+                                        const uint64_t a16 = smem_desc(
+                                            x_addr + ((4 * kk + 2 * h) * rows + row) * 16, rows * 16, a_sbo);
+                                        const uint64_t b16 = smem_desc(w_addr + (4 * kk + 2 * h) * N * 16, N * 16, 128);
+                                        tc_mma(d, a16, b16, idesc0, !(first && kk == 0 && h == 0));
+                                    }
+                                    // e4m3(x) e4m3(w low) + e4m3(x low) e4m3(w): channels 32 kk .. + 31
+                                    const uint32_t xa8 = x8 + (2 * kk * rows + row) * 16;
+                                    const uint32_t wa8 = w8 + 2 * kk * N * 16;
+                                    constexpr uint32_t w_half = (Cfg::kGroups / 2) * N * 16;
+                                    const uint32_t x_half = (Cfg::kGroups / 2) * rows * 16;
+                                    tc_mma_f8(d_low, smem_desc(xa8, rows * 16, a_sbo), smem_desc(wa8, N * 16, 128),
+                                              idesc0, !(first && kk == 0));
+                                    tc_mma_f8(d_low, smem_desc(xa8 + x_half, rows * 16, a_sbo),
+                                              smem_desc(wa8 + w_half, N * 16, 128), idesc0, 1);
+                                }
+                                continue;
+                            }
 #pragma unroll
                             for (int kk = 0; kk < KB / 16; ++kk) {
                                 const uint32_t xa = x_addr + (2 * kk * rows + row) * 16;
@@ -286,8 +334,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             };
             auto load = [&](int s, int c0, uint32_t (&raw)[kW]) {
                 const uint32_t address =
-                    tmem_base + ((uint32_t)(quad * 32) << 16) + as * (S * Cfg::kCols) + s * Cfg::kCols + c0;
+                    tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::kStageCols + s * Cfg::kCols + c0;
                 tc_load16(address, raw);
+                if constexpr (F8) {
+                    uint32_t low[kW];
+                    tc_load16(address + S * Cfg::kCols, low);
+#pragma unroll
+                    for (int i = 0; i < kW; ++i)
+                        raw[i] = __float_as_uint(fmaf(__uint_as_float(low[i]), a.correction_scale, __uint_as_float(raw[i])));
+                }
                 if constexpr (CONCAT) {
                     uint32_t other[kW];
                     tc_load16(address + N, other);
@@ -515,6 +570,36 @@ __global__ void pack_tc_weight_kernel(
     }
 }
 
+// Conv1d weight (C_out, C_in, K) fp32 -> "fp16 + 2 x fp8" slabs (conv1d_tc.cuh):
+// [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16 | [KB / 16][N][16] e4m3((w - fp16 w) s_low) | e4m3(w s) }
+__global__ void pack_tc_weight_f8_kernel(
+    const float* __restrict__ w, uint8_t* __restrict__ slabs, int c_out, int c_in, int k, int kb_size,
+    int n_tile, float scale, float scale_low) {
+    const size_t total = (size_t)c_out * c_in * k;
+    const int blocks = c_in / kb_size;
+    const size_t slab_bytes = (size_t)kb_size * n_tile * 4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t rest = idx;
+        const int cl = rest % kb_size; rest /= kb_size;      // channel within the K block
+        const int col = rest % n_tile; rest /= n_tile;
+        const int kb = rest % blocks; rest /= blocks;
+        const int tap = rest % k; rest /= k;
+        const int nt = (int)rest;
+        const int c = kb * kb_size + cl, o = nt * n_tile + col;
+        const float value = w[((size_t)o * c_in + c) * k + tap];
+        const __half high = __float2half_rn(value);
+        const float low = value - __half2float(high);
+        uint8_t* slab = slabs + ((size_t)(nt * k + tap) * blocks + kb) * slab_bytes;
+        reinterpret_cast<__half*>(slab)[((size_t)(cl / 8) * n_tile + col) * 8 + cl % 8] = high;
+        uint8_t* low_section = slab + (size_t)kb_size * n_tile * 2;
+        uint8_t* high_section = low_section + (size_t)kb_size * n_tile;
+        const size_t at = ((size_t)(cl / 16) * n_tile + col) * 16 + cl % 16;
+        low_section[at] = (uint8_t)__nv_cvt_float_to_fp8(low * scale_low, __NV_SATFINITE, __NV_E4M3);
+        high_section[at] = (uint8_t)__nv_cvt_float_to_fp8(value * scale, __NV_SATFINITE, __NV_E4M3);
+    }
+}
+
 // ConvTranspose1d weight (C_in, C_out, 2 UP), already folded ->
 // [n tile][tap 0..2][c_in / KB][plane][KB / 8][N_TILE][8] bf16 with column
 // n = o * UP + q and taps x[i-1], x[i], x[i+1] (conv_transpose1d.cu has the algebra):
@@ -565,10 +650,10 @@ int sm_count() {
 }
 
 template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE = kConv, int UP = 0, bool CONCAT = false,
-          int XS = 2>
+          int XS = 2, bool F8 = false>
 int launch_variant(const TcConvArgs& a, int n_tiles, cudaStream_t stream) {
-    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS>;
-    auto kernel = conv1d_tc_kernel<C_IN, N, S, KB, NW, AS, MODE, UP, CONCAT, XS>;
+    using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS, F8>;
+    auto kernel = conv1d_tc_kernel<C_IN, N, S, KB, NW, AS, MODE, UP, CONCAT, XS, F8>;
     static bool configured = false;
     if (!configured) {
         PMN_TRY(check_cuda(
@@ -661,6 +746,9 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 128) return launch_variant<32, 128, 2, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
+    PMN_REQUIRE(!a.f8x2 || (a.c_in == 1024 && a.c_out == 128 && !frames), "conv1d_tc: fp8 corrections are built for 1024 -> 128");
+    if (a.c_in == 1024 && a.f8x2)
+        return launch_variant<1024, 128, 2, 64, 2, 1, kConv, 0, false, 2, true>(a, 1, stream);
     if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2>(a, 1, stream);
     // K = 4096 / 8192 with 256 columns: a 128-row tile streams its whole 4 MB weight from L2 in 98 k
     // MMA cycles (43 B per cycle and SM: the L2 limit), so a tile takes 256 rows (two subtiles per
@@ -742,6 +830,23 @@ int launch_zero_plane_pads(
     zero_plane_pads_kernel<<<batch * 2 * (channels / 8), 128, 0, stream>>>(
         planes, t_len, tc_padded_length(t_len));
     return launched("zero_plane_pads_kernel");
+}
+
+int launch_pack_tc_weight_f8(
+    const float* w, void* slabs, int c_out, int c_in, int k, int weight_shift, cudaStream_t stream) {
+    TcPlan plan;
+    PMN_REQUIRE(w && slabs && tc_conv_plan(c_in, c_out, false, &plan) && !plan.concat && plan.k_block % 32 == 0,
+                "pack_tc_weight_f8: bad argument");
+    PMN_REQUIRE(weight_shift >= 0 && weight_shift <= 16, "pack_tc_weight_f8: bad weight scale");
+    const size_t total = (size_t)c_out * c_in * k;
+    const int blocks = (int)min((size_t)2048, (total + 255) / 256);
+    // s_x s_wl = s_xl s_w: s_wl = s_w s_xl / s_x
+    const float scale = (float)(1 << weight_shift);
+    LaunchScope scope("pack_tc_weight_f8_kernel", stream);
+    pack_tc_weight_f8_kernel<<<blocks, 256, 0, stream>>>(
+        w, static_cast<uint8_t*>(slabs), c_out, c_in, k, plan.k_block, plan.n_tile, scale,
+        scale * kF8ScaleXLow / kF8ScaleX);
+    return launched("pack_tc_weight_f8_kernel");
 }
 
 int launch_pack_tc_weight(

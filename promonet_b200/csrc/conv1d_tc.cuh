@@ -68,6 +68,10 @@ struct TcConvArgs {
     // the hi plane.  The frame-major pitch layers (pitch.cu) read planes[plane][position][c / 8]
     // with the batch index as the position: item_groups = C / 8, plane_groups = positions C / 8
     int item_groups = 0, plane_groups = 0;
+    // "fp16 + 2 x fp8" operands (tc_f8_* below): x_planes / w_slabs are in the three-section format
+    // and the fp8 correction products, accumulated apart, are added with this power-of-two factor
+    bool f8x2 = false;
+    float correction_scale = 1.f;
     // Optional (gridDim.x, 10 warps, 4) cycle counters: [0] total, [1..3] barrier waits
     long long* debug = nullptr;
 };
@@ -120,6 +124,23 @@ int launch_conv_pair_tc(
 // Profiling aid: per-CTA cycle counters of every following pair launch (null = off) and the
 // kernel variant to launch (-1 = default)
 void tc_pair_set_debug(long long* counters, int variant);
+
+// fp32-grade products at two thirds of the tensor cycles, for operands of a KNOWN range (the
+// LayerNorm outputs of the pitch network): x w ~ fp16(x) fp16(w)  [kind::f16]
+//   + e4m3(x s_x) e4m3((w - fp16(w)) s_wl) + e4m3((x - fp16(x)) s_xl) e4m3(w s_w)   [kind::f8f6f4, K = 32]
+// with power-of-two scales, s_x s_wl = s_xl s_w, the two corrections (2^-11 of the main term: three
+// mantissa bits are enough for them) summed in a second accumulator and added in the epilogue.
+// Operand format, in 16-byte rows like the planes: [C / 8 groups][t_pad][8] fp16, then
+// [C / 16][t_pad][16] e4m3 of x s_x, then the same of (x - fp16(x)) s_xl.
+constexpr float kF8ScaleX = 8.f;            // |x| <= 56 before the e4m3 of x saturates
+constexpr float kF8ScaleXLow = 16384.f;     // 2^14: (x - fp16(x)) <= 2^-11 |x|
+// weight slabs [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16 | [KB / 16][N][16] e4m3 low | e4m3 high };
+// weight_shift: w 2^shift <= 256 (launch_pack_tc_weight_f8 derives the other scale)
+int launch_pack_tc_weight_f8(
+    const float* w, void* slabs, int c_out, int c_in, int k, int weight_shift, cudaStream_t stream);
+inline float tc_f8_correction_scale(int weight_shift) {
+    return 1.f / (kF8ScaleXLow * (float)(1 << weight_shift));
+}
 
 // folded fp32 weight (C_out, C_in, K) -> hi/lo slabs
 int launch_pack_tc_weight(

@@ -21,7 +21,10 @@
 // outputs become four column groups (y4[t4, (q, o)] = y[4 t4 + q, o], 128 columns) of a
 // 9-tap convolution with the block-Toeplitz weight W4[(q, o), (p, c), J] = W[o, c, 4 J + p - q]
 // (zero outside 0..31): 12.5 % more multiply-adds, all of them at full tensor rate.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <new>
@@ -86,6 +89,10 @@ struct pmn_pitch {
     __nv_bfloat16* head_slabs = nullptr;     // tensor-core path
     const float* head_bias = nullptr;
     const float* folded_bias = nullptr;      // block 1 folded by 4: bias of column (q, o)
+    // block 1 with "fp16 + 2 x fp8" operands (conv1d_tc.cuh): its slabs and the weights' power-of-two
+    // scale; -1: bf16 x 3 (PMN_PITCH_F8=0, or a hop that keeps block 0 frame by frame)
+    void* block1_f8_slabs = nullptr;
+    int block1_shift = -1;
     // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
     struct Resampler { float* table; int orig, fresh, width; };
     std::map<int, Resampler> resamplers;
@@ -410,14 +417,20 @@ __global__ void __launch_bounds__(256) frame_stats_kernel(
 // windows overlap (l_in = hop / 2 columns apart, l_out wide), so the CTA stages their union and
 // the 8 channels' affine parameters in shared memory once: 0.46 instead of 3 loads per output.
 constexpr int kSharedFrames = 8;
-__global__ void __launch_bounds__(256) shared_norm_planes_kernel(
+// F8: the operand in the "fp16 + 2 x fp8" format (conv1d_tc.cuh), 16 channels per CTA: per sample
+// two fp16 rows (8 channels each), one e4m3 row of z s_x and one of (z - fp16 z) s_xl.  With twice the
+// shared memory per CTA it runs 512 threads, two per sample on alternate frames, so that as many
+// threads stay resident (at 256 it was 1.6 x slower; 8 channels per thread writing half e4m3 rows 2 x)
+template <bool F8>
+__global__ void __launch_bounds__(F8 ? 512 : 256) shared_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     const float2* __restrict__ stats, __nv_bfloat16* __restrict__ planes, int channels, int l_in,
     int l_out, size_t in_row, int count, int t_pad, int stride_out, int frames_per_item,
     int item_stride, int first_frame) {
+    constexpr int kC = F8 ? 16 : 8;               // channels per CTA
     extern __shared__ float shared_norm_smem[];
     const int width = l_out + (kSharedFrames - 1) * l_in;
-    float* tile = shared_norm_smem;               // [8][width]
+    float* tile = shared_norm_smem;               // [kC][width]
     __shared__ float2 frame_stats[kSharedFrames];
     const int f0 = blockIdx.x * kSharedFrames, g = blockIdx.y;
     const int groups = channels / 8;
@@ -428,54 +441,92 @@ __global__ void __launch_bounds__(256) shared_norm_planes_kernel(
     while (same < n_frames && (first_frame + f0 + same) / frames_per_item == item0) ++same;
     const size_t offset0 = shared_frame_offset(first_frame + f0, frames_per_item, item_stride, l_in);
     const int needed = (same - 1) * l_in + l_out;
-    const float* source = in + (size_t)(g * 8) * in_row + offset0;
+    const float* source = in + (size_t)(g * kC) * in_row + offset0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
+    for (int c = 0; c < kC; ++c)
         for (int pos = threadIdx.x; pos < needed; pos += blockDim.x)
             tile[c * width + pos] = source[(size_t)c * in_row + pos];
     if (threadIdx.x < n_frames) frame_stats[threadIdx.x] = stats[f0 + threadIdx.x];
     __syncthreads();
-    uint4* hi_plane = reinterpret_cast<uint4*>(planes);
-    uint4* lo_plane = hi_plane + (size_t)4 * groups * t_pad;
-    // a thread owns sample t of every frame: the affine parameters of (8 channels, t) stay in registers
-    for (int t = threadIdx.x; t < stride_out; t += blockDim.x) {
-        // sample t of channel group g is row t / 4 of group (t % 4) * groups + g (pool_norm_planes_kernel)
-        const size_t row0 = (size_t)((t & 3) * groups + g) * t_pad + kTcPad +
-                            (size_t)f0 * (stride_out >> 2) + (t >> 2);
+    uint4* rows16 = reinterpret_cast<uint4*>(planes);
+    const int step = stride_out >> 2;             // rows between consecutive frames
+    // a thread owns sample t of every (F8: every second) frame: the affine parameters of
+    // (kC channels, t) stay in registers
+    const int j_first = threadIdx.x / 256, j_step = blockDim.x / 256;
+    for (int t = threadIdx.x % 256; t < stride_out; t += 256) {
+        // sample t of an 8-channel group g8 is row t / 4 of group (t % 4) * groups + g8 (pool_norm_planes_kernel);
+        // row groups of this thread's rows: bf16: hi, lo; F8: fp16 a, fp16 b, e4m3 z, e4m3 low
+        size_t group[4];
+        if (F8) {
+            group[0] = (size_t)(t & 3) * groups + 2 * g;
+            group[1] = group[0] + 1;
+            group[2] = (size_t)4 * groups + (size_t)(t & 3) * (groups / 2) + g;
+            group[3] = group[2] + (size_t)4 * (groups / 2);
+        } else {
+            group[0] = (size_t)(t & 3) * groups + g;
+            group[1] = group[0] + (size_t)4 * groups;
+            group[2] = group[3] = 0;
+        }
+        const size_t within = kTcPad + (size_t)f0 * step + (t >> 2);
+        uint4* target[4];                             // this thread's rows of frame f0
+#pragma unroll
+        for (int r = 0; r < 4; ++r) target[r] = rows16 + group[r] * t_pad + within;
         if (t >= l_out) {
-            for (int j = 0; j < n_frames; ++j) {
-                hi_plane[row0 + (size_t)j * (stride_out >> 2)] = make_uint4(0, 0, 0, 0);
-                lo_plane[row0 + (size_t)j * (stride_out >> 2)] = make_uint4(0, 0, 0, 0);
-            }
+            for (int j = j_first; j < n_frames; j += j_step)
+                for (int r = 0; r < (F8 ? 4 : 2); ++r) target[r][j * step] = make_uint4(0, 0, 0, 0);
             continue;
         }
-        float gamma[8], beta[8];
+        float gamma[kC], beta[kC];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            gamma[c] = weight[(size_t)(g * 8 + c) * l_out + t];
-            beta[c] = bias[(size_t)(g * 8 + c) * l_out + t];
+        for (int c = 0; c < kC; ++c) {
+            gamma[c] = weight[(size_t)(g * kC + c) * l_out + t];
+            beta[c] = bias[(size_t)(g * kC + c) * l_out + t];
         }
-        for (int j = 0; j < n_frames; ++j) {
+        for (int j = j_first; j < n_frames; j += j_step) {
             const float2 st = frame_stats[j];
-            float x[8];
+            float x[kC];
             if (j < same) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) x[c] = tile[c * width + j * l_in + t];
+                for (int c = 0; c < kC; ++c) x[c] = tile[c * width + j * l_in + t];
             } else {
-                const float* global = in + (size_t)(g * 8) * in_row + t +
+                const float* global = in + (size_t)(g * kC) * in_row + t +
                     shared_frame_offset(first_frame + f0 + j, frames_per_item, item_stride, l_in);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) x[c] = global[(size_t)c * in_row];
+                for (int c = 0; c < kC; ++c) x[c] = global[(size_t)c * in_row];
             }
-            unsigned int hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                tc::split_pair((x[2 * e] - st.x) * st.y * gamma[2 * e] + beta[2 * e],
-                               (x[2 * e + 1] - st.x) * st.y * gamma[2 * e + 1] + beta[2 * e + 1],
-                               hi[e], lo[e]);
-            const size_t row = row0 + (size_t)j * (stride_out >> 2);
-            hi_plane[row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            lo_plane[row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int c = 0; c < kC; ++c) x[c] = (x[c] - st.x) * st.y * gamma[c] + beta[c];
+            const int row = j * step;
+            if (F8) {
+                unsigned int half_words[8], z8[4], low8[4];
+                const __half2 scale_x = __float2half2_rn(kF8ScaleX);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                    half_words[e] = *reinterpret_cast<const unsigned int*>(&h);
+                    const float2 back = __half22float2(h);
+                    // e4m3 of the fp16 value (not of x: the difference is 2^-11 of a term that is
+                    // itself 2^-11 of the product), straight from the packed halves
+                    const __half2 scaled = __hmul2(h, scale_x);
+                    const unsigned int z = __nv_cvt_halfraw2_to_fp8x2(
+                        *reinterpret_cast<const __half2_raw*>(&scaled), __NV_SATFINITE, __NV_E4M3);
+                    const unsigned int low = __nv_cvt_float2_to_fp8x2(
+                        make_float2((x[2 * e] - back.x) * kF8ScaleXLow, (x[2 * e + 1] - back.y) * kF8ScaleXLow),
+                        __NV_SATFINITE, __NV_E4M3);
+                    if (e % 2 == 0) { z8[e / 2] = z; low8[e / 2] = low; }
+                    else { z8[e / 2] |= z << 16; low8[e / 2] |= low << 16; }
+                }
+                target[0][row] = make_uint4(half_words[0], half_words[1], half_words[2], half_words[3]);
+                target[1][row] = make_uint4(half_words[4], half_words[5], half_words[6], half_words[7]);
+                target[2][row] = make_uint4(z8[0], z8[1], z8[2], z8[3]);
+                target[3][row] = make_uint4(low8[0], low8[1], low8[2], low8[3]);
+            } else {
+                unsigned int hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tc::split_pair(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+                target[0][row] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                target[1][row] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
 }
@@ -879,6 +930,28 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
                 p->conv_slabs[i] = reinterpret_cast<__nv_bfloat16*>(folded_slabs);
                 PMN_TRY(launch_pack_tc_weight(
                     folded, p->conv_slabs[i], kFold * 32, kFold * 256, kFoldTaps, false, stream));
+                {
+                    // "fp16 + 2 x fp8": block 1's input is a LayerNorm output (|x| of a few units), its
+                    // weights are scaled by the power of two that brings the largest to (128, 256]
+                    const char* flag = getenv("PMN_PITCH_F8");
+                    if (!(flag && flag[0] == '0')) {
+                        std::vector<float> host(w->numel());
+                        PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
+                        PMN_TRY(check_cuda(
+                            cudaMemcpy(host.data(), w->data, host.size() * sizeof(float), cudaMemcpyDeviceToHost),
+                            "read block 1 weight"));
+                        float largest = 0.f;
+                        for (float value : host) largest = std::max(largest, fabsf(value));
+                        int shift = 0;
+                        while (shift < 16 && largest * (float)(2 << shift) <= 256.f) ++shift;
+                        float* f8_slabs;
+                        PMN_TRY(alloc(p, folded_numel, &f8_slabs));
+                        PMN_TRY(launch_pack_tc_weight_f8(
+                            folded, f8_slabs, kFold * 32, kFold * 256, kFoldTaps, shift, stream));
+                        p->block1_f8_slabs = f8_slabs;
+                        p->block1_shift = shift;
+                    }
+                }
                 // the bias of column (q, o) is the bias of channel o
                 float* bias4;
                 PMN_TRY(alloc(p, kFold * 32, &bias4));
@@ -1075,19 +1148,25 @@ int pitch_forward(
                 PMN_TRY(launched("frame_stats_kernel"));
             }
             const int width = kLength[1] + (kSharedFrames - 1) * (hop / 2);
-            const int smem = 8 * width * (int)sizeof(float);
+            const bool f8 = p->block1_shift >= 0;        // block 1 takes "fp16 + 2 x fp8" operands
+            const int smem = (f8 ? 16 : 8) * width * (int)sizeof(float);
             PMN_REQUIRE(smem <= 200 * 1024, "pitch: hop too long for the shared block 0");
             static bool configured = false;
             if (!configured) {
                 PMN_TRY(check_cuda(
-                    cudaFuncSetAttribute(shared_norm_planes_kernel,
+                    cudaFuncSetAttribute(shared_norm_planes_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                    "shared_norm_planes smem attribute"));
+                PMN_TRY(check_cuda(
+                    cudaFuncSetAttribute(shared_norm_planes_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                     "shared_norm_planes smem attribute"));
                 configured = true;
             }
-            dim3 grid(ceil_div(count, kSharedFrames), kChannels[1] / 8);
+            dim3 grid(ceil_div(count, kSharedFrames), kChannels[1] / (f8 ? 16 : 8));
             LaunchScope scope("shared_norm_planes_kernel", stream);
-            shared_norm_planes_kernel<<<grid, 256, smem, stream>>>(
+            auto kernel = f8 ? shared_norm_planes_kernel<true> : shared_norm_planes_kernel<false>;
+            kernel<<<grid, f8 ? 512 : 256, smem, stream>>>(
                 w.pooled + kCropStart / 2, p->norm_weight[0], p->norm_bias[0], w.stats, w.planes,
                 kChannels[1], hop / 2, kLength[1], pooled_row, count, tc_padded_length(t_next),
                 stride_next, frames, item_rows / 2, first_frame);
@@ -1175,6 +1254,11 @@ int pitch_forward(
                 if (folded) {
                     a.c_in = kFold * kChannels[i]; a.c_out = kFold * kChannels[i + 1];
                     a.k = kFoldTaps; a.t_len = count * (l_in / kFold); a.bias = p->folded_bias;
+                    if (shared0 && p->block1_shift >= 0) {
+                        a.f8x2 = true;
+                        a.w_slabs = static_cast<const __nv_bfloat16*>(p->block1_f8_slabs);
+                        a.correction_scale = tc_f8_correction_scale(p->block1_shift);
+                    }
                 } else {
                     a.c_in = kChannels[i]; a.k = kKernel; a.t_len = count * l_in;
                 }
