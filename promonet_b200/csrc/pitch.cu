@@ -90,7 +90,7 @@ struct pmn_pitch {
     const float* head_bias = nullptr;
     const float* folded_bias = nullptr;      // block 1 folded by 4: bias of column (q, o)
     // block 1 with "fp16 + 2 x fp8" operands (conv1d_tc.cuh): its slabs and the weights' power-of-two
-    // scale; -1: bf16 x 3 (PMN_PITCH_F8=0, or a hop that keeps block 0 frame by frame)
+    // scale; -1: bf16 x 3 (the default; PMN_PITCH_F8=1 at model construction selects the fp8 form)
     void* block1_f8_slabs = nullptr;
     int block1_shift = -1;
     // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
@@ -933,8 +933,11 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
                 {
                     // "fp16 + 2 x fp8": block 1's input is a LayerNorm output (|x| of a few units), its
                     // weights are scaled by the power of two that brings the largest to (128, 256]
+                    // Opt-in (PMN_PITCH_F8=1): measured on 32 x 10 s the convolution gains 2.8 ms
+                    // (15.3 -> 12.5) and the kernel that writes its four-stream operand loses 2.4
+                    // (3.7 -> 6.3), profiles/r2_preprocess_history.txt
                     const char* flag = getenv("PMN_PITCH_F8");
-                    if (!(flag && flag[0] == '0')) {
+                    if (flag && flag[0] == '1') {
                         std::vector<float> host(w->numel());
                         PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
                         PMN_TRY(check_cuda(

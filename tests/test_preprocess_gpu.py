@@ -208,6 +208,20 @@ def test_pitch_pipeline_stages_match_oracle(pitch_model, pitch_state, batch, sam
     assert min(agreement) > 0.95, agreement
 
 
+def test_pitch_block1_with_fp8_corrections_matches_oracle(pb, pitch_state, monkeypatch):
+    """PMN_PITCH_F8=1: block 1 as fp16 x fp16 + two e4m3 correction products (conv1d_tc.cuh); same bar"""
+    monkeypatch.setenv('PMN_PITCH_F8', '1')
+    model = pb.preprocess.penn.Model(state=pitch_state, math=pb._lib.MATH_BF16X3_TC)
+    audio = inputs.audio(2, 33000, seed=5)
+    _, periodicity, logits, _ = model(audio, batch_size=64, return_intermediates=True)
+    for b in range(2):
+        _, expected_periodicity, aux = oracle_penn.from_audio(pitch_state, audio[b:b + 1])
+        expected_logits, _, _ = oracle_penn.postprocess(aux['logits'])
+        live = torch.isfinite(expected_logits)
+        assert relative_error(logits[b].cpu()[live], expected_logits[live]) < TOLERANCE
+        assert (periodicity[b].cpu() - expected_periodicity[0]).abs().max() < TOLERANCE
+
+
 def test_preprocess_from_audio_signature(pb):
     """promonet.preprocess.from_audio (preprocess/core.py:17-126)"""
     audio = inputs.audio(1, 22050, seed=1)
