@@ -12,8 +12,16 @@
 //    CTAs that never talk to another group.  Every CTA keeps its slice of every
 //    layer's weights (4 output units per layer, 140 KB) resident in shared
 //    memory for the whole utterance; activations (16 utterances x <= 1152
-//    values) are exchanged through L2 in a [k][utterance] layout and the 64
-//    CTAs of a group meet at a release/acquire counter barrier after each layer;
+//    values) are exchanged through L2 in a [k][utterance] layout.  There is no
+//    barrier between the 11 layers of a subframe: every exchanged value is its
+//    own flag.  A buffer holds a NaN sentinel until its producer stores the
+//    value, consumers spin on the loads that fetch their operands anyway (one
+//    L2 round trip per layer instead of an atomic, a polled counter and the
+//    operand loads: 48.7 -> 25.6 us per subframe on 32 x 5 s).  Buffers rotate
+//    over three slots by subframe and every CTA re-arms its slice of the slot
+//    of subframe n + 1 during subframe n, after it has seen the first layer of
+//    subframe n complete everywhere (so nobody still reads that slot) and a
+//    whole subframe before anybody polls it again;
 //  * the subframe input (conditioning slice, previous subframe, pitch lookback)
 //    is rebuilt by every CTA from the sample history, so the "previous input"
 //    state of FramewiseConv (fargan.py:349-364) never leaves shared memory.
@@ -63,17 +71,43 @@ constexpr int kSmemFloats = kWeights + 2 * kInput * kGroupItems + kStage + kScra
 constexpr int kSmemBytes = kSmemFloats * 4 + 64;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-// Activations of one group in global memory, all [k][16]
+// Activations of one group in global memory, all [k][16]; three slots each (slot n % 3 is
+// written and read in subframe n, h also read in n + 1)
+constexpr int kSlots = 3;
 struct GroupState {
-    float* fw;        // tanh(fwconv)            256
-    float* fwg;       // after GLU               256
-    float* h[3][2];   // GRU states, double-buffered
-    float* g[3];      // GRU GLU outputs         256 each
-    float* skip;      // tanh(skip dense)        256
-    float* skipg;     // after GLU               256
-    float* history;   // (512 + T) samples
-    unsigned int* barrier;
+    float* fw[kSlots];        // tanh(fwconv)            256
+    float* fwg[kSlots];       // after GLU               256
+    float* h[3][kSlots];      // GRU states
+    float* g[3][kSlots];      // GRU GLU outputs         256 each
+    float* skip[kSlots];      // tanh(skip dense)        256
+    float* skipg[kSlots];     // after GLU               256
+    float* history;           // (512 + T) samples; sentinel until produced
+    unsigned int* barrier;    // start-up only
 };
+constexpr int kExchanged = 2 + 3 + 3 + 2;         // buffers per slot
+constexpr unsigned int kSentinel = 0x7fc0dead;    // a quiet NaN no computation produces
+
+__device__ __forceinline__ float sentinel() { return __uint_as_float(kSentinel); }
+__device__ __forceinline__ bool pending(float v) { return __float_as_uint(v) == kSentinel; }
+
+// L2 load that the compiler may not hoist out of a polling loop
+__device__ __forceinline__ float4 load_l2(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float load_l2(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// one value, waiting for its producer
+__device__ __forceinline__ float wait_value(const float* p) {
+    float v = load_l2(p);
+    while (pending(v)) v = load_l2(p);
+    return v;
+}
 
 __device__ __forceinline__ float sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -93,11 +127,58 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
     __syncthreads();
 }
 
-// Copy rows [0, rows) of a [k][16] activation from L2 (never L1: other CTAs wrote it)
+// Copy a [256][16] activation from L2 (never L1: other CTAs wrote it) into shared memory, waiting
+// for every value to be produced.  A thread's four loads are issued together and only the ones
+// that came back with the sentinel are repeated: one L2 round trip when the producers are done
+// (a loop that waited on each load in turn cost four).
 __device__ __forceinline__ void stage(float* dst, const float* src, int rows) {
-    const float4* s = reinterpret_cast<const float4*>(src);
-    float4* d = reinterpret_cast<float4*>(dst);
-    for (int i = threadIdx.x; i < rows * kGroupItems / 4; i += kThreads) d[i] = __ldcg(s + i);
+    constexpr int kPer = kHop * kGroupItems / 4 / kThreads;   // 4
+    const float4* s = reinterpret_cast<const float4*>(src) + threadIdx.x;
+    float4* d = reinterpret_cast<float4*>(dst) + threadIdx.x;
+    float4 v[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) v[j] = load_l2(s + j * kThreads);
+    bool again;
+    do {
+        again = false;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            if (pending(v[j].x) || pending(v[j].y) || pending(v[j].z) || pending(v[j].w)) {
+                v[j] = load_l2(s + j * kThreads);
+                again = true;
+            }
+        }
+    } while (again);
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) d[j * kThreads] = v[j];
+}
+// two activations at once (eight loads in flight)
+__device__ __forceinline__ void stage2(float* dst0, const float* src0, float* dst1, const float* src1) {
+    constexpr int kPer = kHop * kGroupItems / 4 / kThreads;   // 4
+    const float4* s[2] = {reinterpret_cast<const float4*>(src0) + threadIdx.x,
+                          reinterpret_cast<const float4*>(src1) + threadIdx.x};
+    float4 v[2][kPer];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) v[a][j] = load_l2(s[a] + j * kThreads);
+    bool again;
+    do {
+        again = false;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                if (pending(v[a][j].x) || pending(v[a][j].y) || pending(v[a][j].z) || pending(v[a][j].w)) {
+                    v[a][j] = load_l2(s[a] + j * kThreads);
+                    again = true;
+                }
+            }
+    } while (again);
+    float4* d0 = reinterpret_cast<float4*>(dst0) + threadIdx.x;
+    float4* d1 = reinterpret_cast<float4*>(dst1) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { d0[j * kThreads] = v[0][j]; d1[j * kThreads] = v[1][j]; }
 }
 
 // acc[r] += sum_k w[k][r] * x[k][b] over this thread's K partition
@@ -156,45 +237,84 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
 
     for (int i = tid; i < kWeights; i += kThreads) w[i] = weights[(size_t)cta * kWeights + i];
     for (int i = tid; i < 2 * kInput * kGroupItems; i += kThreads) input[0][i] = 0.f;  // state3 = 0
-    // history[0:512] = previous samples; GRU states start at zero (fargan.py:406-415)
-    if (cta == 0) {
-        for (int i = tid; i < kHistory * kGroupItems; i += kThreads) {
-            const int k = i / kGroupItems, col = i % kGroupItems;
-            const int it = group * kGroupItems + col;
-            gs.history[i] = (previous && it < batch) ? previous[(size_t)it * kHistory + k] : 0.f;
+    // Start-up: every exchanged slot holds the sentinel, except the GRU states "of subframe -1"
+    // (slot 2), which start at zero (fargan.py:406-415); history[0:512] = previous samples, the rest
+    // sentinel.  The 64 CTAs share the fill and meet once at a barrier.
+    {
+        float* const* all = &gs.fw[0];     // the 10 x 3 buffer pointers are contiguous in GroupState
+        for (int buffer = 0; buffer < kExchanged * kSlots; ++buffer) {
+            // h[s][2] are buffers 2 * kSlots + s * kSlots + 2
+            const bool zero = buffer >= 2 * kSlots && buffer < 5 * kSlots && (buffer - 2 * kSlots) % kSlots == 2;
+            for (int i = cta * kThreads + tid; i < kHop * kGroupItems; i += kGroupCtas * kThreads)
+                all[buffer][i] = zero ? 0.f : sentinel();
         }
-        for (int s = 0; s < 3; ++s)
-            for (int i = tid; i < kHop * kGroupItems; i += kThreads) gs.h[s][0][i] = 0.f;
+        const size_t total = (size_t)(kHistory + samples) * kGroupItems;
+        for (size_t i = (size_t)cta * kThreads + tid; i < total; i += (size_t)kGroupCtas * kThreads) {
+            float v = sentinel();
+            if (i < (size_t)kHistory * kGroupItems) {
+                const int k = (int)(i / kGroupItems), col = (int)(i % kGroupItems);
+                const int it = group * kGroupItems + col;
+                v = (previous && it < batch) ? previous[(size_t)it * kHistory + k] : 0.f;
+                if (pending(v)) v = __uint_as_float(0x7fc00000u);   // a caller's NaN must not look unproduced
+            }
+            gs.history[i] = v;
+        }
     }
     group_barrier(gs.barrier, target);
 
     int current = 0;  // input[current] = this subframe's features, input[current ^ 1] = previous
     for (int n = 0; n < frames * kSubframes; ++n) {
         const int f = n / kSubframes, sub = n % kSubframes;
-        const int parity = n & 1;  // GRU state buffer read this subframe
+        const int slot = n % kSlots, before = (n + kSlots - 1) % kSlots, after = (n + 1) % kSlots;
         float* in = input[current];
         const float* state3 = input[current ^ 1];
         const float* hist = gs.history + (size_t)n * kSub * kGroupItems;  // 512-sample window
 
         // ---- subframe input: cond[:, sub::4] (fargan.py:109-113), previous 64, lookback 68 ----
-        for (int idx = tid; idx < kInput * kGroupItems; idx += kThreads) {
-            const int k = idx / kGroupItems, col = idx % kGroupItems;
-            const int it = group * kGroupItems + col;
-            float v = 0.f;
-            if (it < batch) {
+        {
+            // a thread's history samples are loaded together; the ones still pending (the previous
+            // subframe's, just being produced) are loaded again until they arrive
+            constexpr int kMine = (kInput * kGroupItems + kThreads - 1) / kThreads;   // 17
+            const float* address[kMine];
+            float value[kMine];
+#pragma unroll
+            for (int j = 0; j < kMine; ++j) {
+                const int idx = tid + j * kThreads;
+                address[j] = nullptr;
+                value[j] = 0.f;
+                if (idx >= kInput * kGroupItems) continue;
+                const int k = idx / kGroupItems, col = idx % kGroupItems;
+                const int it = group * kGroupItems + col;
+                if (it >= batch) continue;
                 if (k < 2 * kSub) {
-                    v = __ldg(cond + ((size_t)it * kCond + 4 * k + sub) * frames + f);
+                    value[j] = __ldg(cond + ((size_t)it * kCond + 4 * k + sub) * frames + f);
                 } else if (k < 3 * kSub) {
-                    v = __ldcg(hist + (size_t)(kHistory - kSub + (k - 2 * kSub)) * kGroupItems + col);
+                    address[j] = hist + (size_t)(kHistory - kSub + (k - 2 * kSub)) * kGroupItems + col;
                 } else {
                     const int period = (int)rintf(__ldg(features + ((size_t)it * 114 + 113) * frames + f));
                     int index = kHistory - period + (k - 3 * kSub) - 2;   // fargan.py:233-239
                     if (index >= kHistory) index -= period;
                     index = max(index, 0);
-                    v = __ldcg(hist + (size_t)index * kGroupItems + col);
+                    address[j] = hist + (size_t)index * kGroupItems + col;
                 }
+                if (address[j]) value[j] = load_l2(address[j]);
             }
-            in[idx] = v;
+            bool again;
+            do {
+                again = false;
+#pragma unroll
+                for (int j = 0; j < kMine; ++j) {
+                    if (address[j] && pending(value[j])) {
+                        value[j] = load_l2(address[j]);
+                        again = true;
+                    }
+                }
+            } while (again);
+#pragma unroll
+            for (int j = 0; j < kMine; ++j) {
+                const int idx = tid + j * kThreads;
+                if (idx < kInput * kGroupItems) in[idx] = value[j];
+            }
         }
         __syncthreads();
 
@@ -205,10 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             dot<kUnits>(acc, w + kWFw + kInput * kUnits, state3, kInput, part, b);
             reduce<kUnits>(acc, scratch, part, b);
             if (tid < kUnits * kGroupItems)
-                gs.fw[(size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems)] =
-                    tanhf(scratch[tid]);
+                __stcg(gs.fw[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
+                       tanhf(scratch[tid]));
         }
-        group_barrier(gs.barrier, target);
 
         // GLU: x * sigmoid(W x) for this CTA's 4 units (fargan.py:375-388)
         auto glu = [&](const float* wg, const float* x_global, float* out_global) {
@@ -220,12 +339,22 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             if (tid < kUnits * kGroupItems) {
                 const int unit = cta * kUnits + tid / kGroupItems, col = tid % kGroupItems;
                 const float x = staged[unit * kGroupItems + col];
-                out_global[(size_t)unit * kGroupItems + col] = x * sigmoid(scratch[tid]);
+                __stcg(out_global + (size_t)unit * kGroupItems + col, x * sigmoid(scratch[tid]));
             }
         };
 
-        glu(w + kWFwGlu, gs.fw, gs.fwg);
-        group_barrier(gs.barrier, target);
+        glu(w + kWFwGlu, gs.fw[slot], gs.fwg[slot]);
+        // fw of this subframe is complete everywhere (glu staged all of it): every CTA has finished
+        // subframe n - 1, so nobody reads the slot of subframe n + 1 any more (last written in
+        // n - 2, last read in n - 1): re-arm this CTA's slice of it, a whole subframe ahead of its
+        // next readers
+        if (tid < kUnits * kGroupItems) {
+            float* const* all = &gs.fw[0];
+            const size_t at = (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems);
+#pragma unroll
+            for (int buffer = 0; buffer < kExchanged; ++buffer) __stcg(all[buffer * kSlots + after] + at, sentinel());
+            __threadfence();
+        }
 
         // ---- three GRU cells + GLUs (fargan.py:267-309) ----
         const float* lookback = in + (3 * kSub + 2) * kGroupItems;  // pitch_lookback[:, 2:-2]
@@ -233,9 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         for (int s = 0; s < 3; ++s) {
             const float* wih = w + kWGru + s * (kGruIh + kGruHh);
             const float* whh = wih + kGruIh;
-            const float* x_global = s == 0 ? gs.fwg : gs.g[s - 1];
-            stage(staged, x_global, kHop);
-            stage(staged + kHop * kGroupItems, gs.h[s][parity], kHop);
+            const float* x_global = s == 0 ? gs.fwg[slot] : gs.g[s - 1][slot];
+            stage2(staged, x_global, staged + kHop * kGroupItems, gs.h[s][before]);
             __syncthreads();
             float gi[3 * kUnits] = {}, gh[3 * kUnits] = {};
             dot<3 * kUnits>(gi, wih, staged, kHop, part, b);
@@ -254,51 +382,45 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                 const float z = sigmoid(at(3 * u + 1) + at(3 * kUnits + 3 * u + 1));
                 const float c = tanhf(at(3 * u + 2) + r * at(3 * kUnits + 3 * u + 2));
                 const float h = staged[(kHop + unit) * kGroupItems + col];
-                gs.h[s][parity ^ 1][(size_t)unit * kGroupItems + col] = (1.f - z) * c + z * h;
+                __stcg(gs.h[s][slot] + (size_t)unit * kGroupItems + col, (1.f - z) * c + z * h);
             }
-            group_barrier(gs.barrier, target);
-            glu(w + kWGlu + s * kHop * kUnits, gs.h[s][parity ^ 1], gs.g[s]);
-            group_barrier(gs.barrier, target);
+            glu(w + kWGlu + s * kHop * kUnits, gs.h[s][slot], gs.g[s][slot]);
         }
 
         // ---- skip: tanh(W [g1, g2, g3, fw, lookback, previous]) then GLU (fargan.py:311-325) ----
         {
             float acc[kUnits] = {};
-            stage(staged, gs.g[0], kHop);
-            stage(staged + kHop * kGroupItems, gs.g[1], kHop);
+            stage2(staged, gs.g[0][slot], staged + kHop * kGroupItems, gs.g[1][slot]);
             __syncthreads();
             dot<kUnits>(acc, w + kWSkip, staged, 2 * kHop, part, b);
             __syncthreads();
-            stage(staged, gs.g[2], kHop);
-            stage(staged + kHop * kGroupItems, gs.fwg, kHop);
+            stage2(staged, gs.g[2][slot], staged + kHop * kGroupItems, gs.fwg[slot]);
             __syncthreads();
             dot<kUnits>(acc, w + kWSkip + 2 * kHop * kUnits, staged, 2 * kHop, part, b);
             dot<kUnits>(acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
             dot<kUnits>(acc, w + kWSkip + (4 * kHop + kSub) * kUnits, last, kSub, part, b);
             reduce<kUnits>(acc, scratch, part, b);
             if (tid < kUnits * kGroupItems)
-                gs.skip[(size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems)] =
-                    tanhf(scratch[tid]);
+                __stcg(gs.skip[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
+                       tanhf(scratch[tid]));
         }
-        group_barrier(gs.barrier, target);
-        glu(w + kWSkipGlu, gs.skip, gs.skipg);
-        group_barrier(gs.barrier, target);
+        glu(w + kWSkipGlu, gs.skip[slot], gs.skipg[slot]);
 
         // ---- output: tanh(W skip), one of the 64 samples per CTA (fargan.py:327-329) ----
         {
-            stage(staged, gs.skipg, kHop);
+            stage(staged, gs.skipg[slot], kHop);
             __syncthreads();
             float acc[1] = {};
             dot<1>(acc, w + kWOut, staged, kHop, part, b);
             reduce<1>(acc, scratch, part, b);
             if (tid < kGroupItems) {
                 const float y = tanhf(scratch[tid]);
-                gs.history[(size_t)(kHistory + n * kSub + cta) * kGroupItems + tid] = y;
+                __stcg(gs.history + (size_t)(kHistory + n * kSub + cta) * kGroupItems + tid, y);
                 const int it = group * kGroupItems + tid;
                 if (it < batch) audio[(size_t)it * samples + n * kSub + cta] = y;
             }
         }
-        group_barrier(gs.barrier, target);
+        __syncthreads();   // `staged`, `scratch` and `in` are rewritten by the next subframe
         current ^= 1;
     }
 }
@@ -393,8 +515,9 @@ Workspace carve(void* base, int batch, int frames) {
     w.cond_in = (float*)take((size_t)batch * kCondIn * frames * 4);
     w.cond_a = (float*)take((size_t)batch * kCond * frames * 4);
     w.cond_b = (float*)take((size_t)batch * kCond * frames * 4);
-    // per group: fw, fwg, 6 h, 3 g, skip, skipg = 13 x 256 x 16, history (512 + T) x 16
-    w.group_floats = (size_t)13 * kHop * kGroupItems + (size_t)(kHistory + frames * kHop) * kGroupItems;
+    // per group: (fw, fwg, 3 h, 3 g, skip, skipg) x 3 slots x 256 x 16, history (512 + T) x 16
+    w.group_floats = (size_t)kExchanged * kSlots * kHop * kGroupItems +
+                     (size_t)(kHistory + frames * kHop) * kGroupItems;
     w.state = (float*)take((size_t)groups * w.group_floats * 4);
     w.groups = (GroupState*)take((size_t)groups * sizeof(GroupState));
     w.barriers = (unsigned int*)take((size_t)groups * 128);
@@ -543,11 +666,10 @@ int fargan_forward(
         float* p = w.state + (size_t)i * w.group_floats;
         const size_t unit = (size_t)kHop * kGroupItems;
         GroupState& s = host[i];
-        s.fw = p; s.fwg = p + unit;
-        for (int j = 0; j < 3; ++j) { s.h[j][0] = p + (2 + 2 * j) * unit; s.h[j][1] = p + (3 + 2 * j) * unit; }
-        for (int j = 0; j < 3; ++j) s.g[j] = p + (8 + j) * unit;
-        s.skip = p + 11 * unit; s.skipg = p + 12 * unit;
-        s.history = p + 13 * unit;
+        // buffer order = member order of GroupState (the kernel walks &fw[0] as 30 pointers)
+        float** all = &s.fw[0];
+        for (int buffer = 0; buffer < kExchanged * kSlots; ++buffer) all[buffer] = p + buffer * unit;
+        s.history = p + (size_t)kExchanged * kSlots * unit;
         s.barrier = w.barriers + (size_t)i * 32;
     }
     PMN_TRY(check_cuda(
