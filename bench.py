@@ -709,7 +709,7 @@ def train(ctx):
             'value': 1 / seconds, 'unit': 'items/s', 'cores': os.cpu_count(), 'kind': 'port',
             'sample': '1 item through oracle/train.py (torch autograd fp32 + AdamW; pinned to the '
                       'reference step by tests/golden/train.npz), one step'}
-    ctx.symmetric_memory = ctx.symmetric_memory or trainer.generator.params.peers is not None
+    ctx.trainers.append(trainer)
     return result
 
 
@@ -795,7 +795,7 @@ def gpu_eager_baseline(ctx):
 
 def run_b200(args):
     ctx = Context(args)
-    ctx.symmetric_memory = False
+    ctx.trainers = []
     result = synthesis(ctx)
     wanted = None if args.only is None else set(args.only.split(','))
     secondary = {}
@@ -821,14 +821,10 @@ def run_b200(args):
     if ctx.rank == 0:
         print(json.dumps(result), flush=True)
     if ctx.world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        ctx.torch.cuda.synchronize()
-        if ctx.symmetric_memory:
-            # live symmetric-memory mappings make destroy_process_group wait on the peers
-            sys.stdout.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        # closes the trainers' peer-memory mappings first (a teardown with live mappings has been
+        # seen to wait on the peers; the helper ends the process if it still does)
+        from promonet_b200 import parallel
+        parallel.shutdown(*ctx.trainers)
 
 
 def main():

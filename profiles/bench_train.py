@@ -117,8 +117,8 @@ def main():
                 'sample': '1 item through oracle/train.py (torch autograd fp32 + AdamW), one step'}
         print(json.dumps(result))
     if world > 1:
-        torch.distributed.barrier()
-        os._exit(0)   # symmetric-memory mappings make an orderly teardown block on the peers
+        from promonet_b200 import parallel
+        parallel.shutdown(trainer)
 
 
 if __name__ == '__main__':

@@ -114,3 +114,30 @@ def _all_gather_ragged(pieces, local, rank, world):
         if source == rank:
             pieces[source].copy_(local)
         dist.broadcast(pieces[source], src=source)
+
+
+def shutdown(*trainers, grace=30.):
+    """Orderly end of a multi-rank job: close the trainers (their peer-memory mappings), meet at a
+    barrier and destroy the process group.  torch's teardown has been seen to wait on the peers
+    with live symmetric-memory mappings; should it still be stuck after `grace` seconds, a watchdog
+    ends the process (everything has been printed and synchronised by then)."""
+    import sys
+    import threading
+    import time
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return
+    for trainer in trainers:
+        trainer.close()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    torch.distributed.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+
+    def watchdog():
+        time.sleep(grace)
+        sys.stderr.write('promonet_b200.parallel.shutdown: destroy_process_group did not return; exiting\n')
+        sys.stderr.flush()
+        os._exit(0)
+    threading.Thread(target=watchdog, daemon=True).start()
+    torch.distributed.destroy_process_group()

@@ -75,6 +75,15 @@ class Trainer:
                 parallel.all_reduce_sum(params.grad, self.process_group)   # NCCL over NVLink
             params.adamw(*settings, grad_scale=1. / self.world)
 
+    def close(self):
+        """Give up the peer-memory optimizer before tearing the process group down: with live
+        symmetric-memory mappings torch.distributed.destroy_process_group() can wait on the peers.
+        Call on every rank; parameters stay readable (state_dict), the trainer does not step again."""
+        torch.cuda.synchronize(self.device)
+        for module in (self.generator, self.discriminators):
+            module.params.release_peers()
+        self.closed = True
+
     def broadcast_parameters(self, source=0):
         if self.world > 1:
             for params in (self.generator.params, self.discriminators.params):
@@ -88,6 +97,8 @@ class Trainer:
              loudness_ratios, spectrograms, audio, update=True):
         """Batch tensors as collated by the reference (data/collate.py:43-60), on the device.
         Returns the five losses as a device tensor ordered like LOSSES (no host sync)."""
+        if getattr(self, 'closed', False):
+            raise RuntimeError('Trainer.step after Trainer.close()')
         batch = (loudness, pitch, periodicity, ppg, speakers, spectral_balance_ratios,
                  loudness_ratios, spectrograms, audio)
         self._discriminator_phase(batch)

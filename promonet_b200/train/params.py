@@ -190,6 +190,17 @@ class ParamSet:
                 f'(keys state / param_groups), got keys {sorted(state)[:6]}')
         self.steps_device.fill_(float(self.steps))
 
+    def release_peers(self):
+        """Drop the symmetric-memory mappings (before torch.distributed.destroy_process_group, which
+        can otherwise wait on the peers): the parameters and gradients move to plain device buffers
+        and the module falls back to the NCCL exchange"""
+        if self.peers is None:
+            return
+        data, grad = self.data.clone(), self.grad.clone()
+        torch.cuda.synchronize(self.device)
+        self.peers = None
+        self.data, self.grad = data, grad
+
     def adamw_peer(self, lr, betas, eps, weight_decay):
         """The data-parallel step in one kernel over NVLink peer memory: this rank averages its
         slice of every rank's gradients, applies AdamW to it and writes the new parameters into

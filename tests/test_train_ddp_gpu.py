@@ -55,10 +55,9 @@ def _worker(rank, world, port, queue, peer_optimizer):
     else:
         torch.distributed.barrier()
     queue.put((rank, result))
-    parallel.barrier()
-    # leave without tearing the process group down: with live symmetric-memory mappings the
-    # teardown can block on the other rank, and the parent only needs the exit code
-    os._exit(0)
+    # orderly teardown: peer mappings released, barrier, destroy_process_group (the helper ends
+    # the process should torch's teardown still wait on the peer)
+    parallel.shutdown(trainer)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
@@ -112,8 +111,7 @@ def _validation_worker(rank, world, port, queue):
     scalars, waveforms = evaluate(None, 1, generator, loader, rank)
     alone, _ = evaluate(None, 1, generator, loader, rank, data_parallel=False)
     queue.put((rank, scalars, alone, sorted(waveforms)))
-    parallel.barrier()
-    os._exit(0)
+    parallel.shutdown()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
