@@ -26,6 +26,8 @@
 //    is rebuilt by every CTA from the sample history, so the "previous input"
 //    state of FramewiseConv (fargan.py:349-364) never leaves shared memory.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <map>
 #include <new>
@@ -50,8 +52,9 @@ constexpr int kCond = 2 * kHop;     // 512
 constexpr int kGroupItems = 16;     // utterances per CTA group
 constexpr int kGroupCtas = 64;
 constexpr int kUnits = kHop / kGroupCtas;  // 4 output units per CTA per layer
-constexpr int kThreads = 256;
-constexpr int kParts = kThreads / kGroupItems;  // 16 K-partitions
+constexpr int kThreads = 512;            // 256: two warps per scheduler left the dot products latency-bound (gpurun call AR:
+                                      // 70 % of a subframe was local work, 30 % waiting for operands)
+constexpr int kParts = kThreads / kGroupItems;  // 32 K-partitions
 
 // Per-CTA weight image (floats), every block stored [k][rows]
 constexpr int kWFw = 0;                                   // 520 x 4
@@ -64,6 +67,9 @@ constexpr int kWSkip = kWGlu + 3 * kHop * kUnits;         // 1152 x 4
 constexpr int kWSkipGlu = kWSkip + (4 * kHop + 2 * kSub) * kUnits;
 constexpr int kWOut = kWSkipGlu + kHop * kUnits;          // 256 x 1
 constexpr int kWeights = kWOut + kHop;                    // 35104
+static_assert(kWFwGlu % 4 == 0 && kWGru % 4 == 0 && kGruIh % 4 == 0 && kGruHh % 4 == 0 && kWGlu % 4 == 0 &&
+              kWSkip % 4 == 0 && kWSkipGlu % 4 == 0 && kWOut % 4 == 0 && (kInput * kUnits) % 4 == 0 &&
+              (kSub * kUnits) % 4 == 0, "weight blocks are read with 16-byte loads");
 
 constexpr int kStage = 2 * kHop * kGroupItems;            // staged activations: 512 x 16 floats
 constexpr int kScratch = (kParts / 2) * 24 * kGroupItems; // K-partition partial sums
@@ -181,16 +187,35 @@ __device__ __forceinline__ void stage2(float* dst0, const float* src0, float* ds
     for (int j = 0; j < kPer; ++j) { d0[j * kThreads] = v[0][j]; d1[j * kThreads] = v[1][j]; }
 }
 
-// acc[r] += sum_k w[k][r] * x[k][b] over this thread's K partition
+// acc[r] += sum_k w[k][r] * x[k][b] over this thread's K partition.  The ROWS weights of a k are
+// contiguous and 16-byte aligned (every block of the image starts at a multiple of 4 floats):
+// they are read as ROWS / 4 vector loads -- with scalar loads the dot products were bound by the
+// issue of shared-memory loads (one per multiply-add: 480 per thread and GRU cell)
 template <int ROWS>
 __device__ __forceinline__ void dot(
     float (&acc)[ROWS], const float* __restrict__ w, const float* __restrict__ x, int k_count,
     int part, int b) {
-    for (int k = part; k < k_count; k += kParts) {
-        const float a = x[k * kGroupItems + b];
-        const float* row = w + k * ROWS;
+    if constexpr (ROWS % 4 == 0) {
+#pragma unroll 4
+        for (int k = part; k < k_count; k += kParts) {
+            const float a = x[k * kGroupItems + b];
+            const float4* row = reinterpret_cast<const float4*>(w + k * ROWS);
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(row[r], a, acc[r]);
+            for (int q = 0; q < ROWS / 4; ++q) {
+                const float4 v = row[q];
+                acc[4 * q] = fmaf(v.x, a, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(v.y, a, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(v.z, a, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(v.w, a, acc[4 * q + 3]);
+            }
+        }
+    } else {
+        for (int k = part; k < k_count; k += kParts) {
+            const float a = x[k * kGroupItems + b];
+            const float* row = w + k * ROWS;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(row[r], a, acc[r]);
+        }
     }
 }
 
@@ -214,12 +239,16 @@ __device__ __forceinline__ void reduce(float (&acc)[ROWS], float* scratch, int p
     __syncthreads();
 }
 
+// profiling aid (PMN_FARGAN_DEBUG=1): cycles thread 0 of CTA 0 spends waiting for operands
+// (subframe input, every stage call) against the whole frame loop
+__device__ long long g_fargan_cycles[8];
+
 __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     const float* __restrict__ weights,   // (64, kWeights) per-CTA images
     const float* __restrict__ cond,      // (B, 512, F) tanh conditioning
     const float* __restrict__ features,  // (B, 114, F): row 113 = pitch period
     const float* __restrict__ previous,  // (B, 512) or null (zeros)
-    GroupState* __restrict__ groups, float* __restrict__ audio, int batch, int frames) {
+    GroupState* __restrict__ groups, float* __restrict__ audio, int batch, int frames, int debug) {
     extern __shared__ __align__(16) float smem[];
     float* w = smem;
     float* input[2] = {smem + kWeights, smem + kWeights + kInput * kGroupItems};
@@ -263,6 +292,13 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     group_barrier(gs.barrier, target);
 
     int current = 0;  // input[current] = this subframe's features, input[current ^ 1] = previous
+    const bool timing = debug && blockIdx.x == 0 && tid == 0;
+    long long wait_input = 0, wait_stage = 0, t_dot = 0, t_reduce = 0, t_input = 0, mark = 0, mark2 = 0;
+    auto tick2 = [&]() { if (timing) mark2 = clock64(); };
+    auto tock2 = [&](long long& sum) { if (timing) sum += clock64() - mark2; };
+    const long long loop_start = timing ? clock64() : 0;
+    auto tick = [&]() { if (timing) mark = clock64(); };
+    auto tock = [&](long long& sum) { if (timing) sum += clock64() - mark; };
     for (int n = 0; n < frames * kSubframes; ++n) {
         const int f = n / kSubframes, sub = n % kSubframes;
         const int slot = n % kSlots, before = (n + kSlots - 1) % kSlots, after = (n + 1) % kSlots;
@@ -271,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         const float* hist = gs.history + (size_t)n * kSub * kGroupItems;  // 512-sample window
 
         // ---- subframe input: cond[:, sub::4] (fargan.py:109-113), previous 64, lookback 68 ----
+        tick2();
         {
             // a thread's history samples are loaded together; the ones still pending (the previous
             // subframe's, just being produced) are loaded again until they arrive
@@ -300,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                 if (address[j]) value[j] = load_l2(address[j]);
             }
             bool again;
+            tick();
             do {
                 again = false;
 #pragma unroll
@@ -310,6 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                     }
                 }
             } while (again);
+            tock(wait_input);
 #pragma unroll
             for (int j = 0; j < kMine; ++j) {
                 const int idx = tid + j * kThreads;
@@ -318,12 +357,19 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         }
         __syncthreads();
 
+        tock2(t_input);
         // ---- framewise conv: tanh(W [in; state3]) (fargan.py:349-364) ----
         {
             float acc[kUnits] = {};
+            tick2();
             dot<kUnits>(acc, w + kWFw, in, kInput, part, b);
+            tock2(t_dot);
+            tick2();
             dot<kUnits>(acc, w + kWFw + kInput * kUnits, state3, kInput, part, b);
+            tock2(t_dot);
+            tick2();
             reduce<kUnits>(acc, scratch, part, b);
+            tock2(t_reduce);
             if (tid < kUnits * kGroupItems)
                 __stcg(gs.fw[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
                        tanhf(scratch[tid]));
@@ -331,11 +377,17 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
 
         // GLU: x * sigmoid(W x) for this CTA's 4 units (fargan.py:375-388)
         auto glu = [&](const float* wg, const float* x_global, float* out_global) {
+            tick();
             stage(staged, x_global, kHop);
             __syncthreads();
+            tock(wait_stage);
             float acc[kUnits] = {};
+            tick2();
             dot<kUnits>(acc, wg, staged, kHop, part, b);
+            tock2(t_dot);
+            tick2();
             reduce<kUnits>(acc, scratch, part, b);
+            tock2(t_reduce);
             if (tid < kUnits * kGroupItems) {
                 const int unit = cta * kUnits + tid / kGroupItems, col = tid % kGroupItems;
                 const float x = staged[unit * kGroupItems + col];
@@ -363,17 +415,29 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             const float* wih = w + kWGru + s * (kGruIh + kGruHh);
             const float* whh = wih + kGruIh;
             const float* x_global = s == 0 ? gs.fwg[slot] : gs.g[s - 1][slot];
+            tick();
             stage2(staged, x_global, staged + kHop * kGroupItems, gs.h[s][before]);
             __syncthreads();
+            tock(wait_stage);
             float gi[3 * kUnits] = {}, gh[3 * kUnits] = {};
+            tick2();
             dot<3 * kUnits>(gi, wih, staged, kHop, part, b);
+            tock2(t_dot);
+            tick2();
             dot<3 * kUnits>(gi, wih + kHop * 3 * kUnits, lookback, kSub, part, b);
+            tock2(t_dot);
+            tick2();
             dot<3 * kUnits>(gi, wih + (kHop + kSub) * 3 * kUnits, last, kSub, part, b);
+            tock2(t_dot);
+            tick2();
             dot<3 * kUnits>(gh, whh, staged + kHop * kGroupItems, kHop, part, b);
+            tock2(t_dot);
             float both[6 * kUnits];
 #pragma unroll
             for (int r = 0; r < 3 * kUnits; ++r) { both[r] = gi[r]; both[3 * kUnits + r] = gh[r]; }
+            tick2();
             reduce<6 * kUnits>(both, scratch, part, b);
+            tock2(t_reduce);
             if (tid < kUnits * kGroupItems) {
                 const int u = tid / kGroupItems, col = tid % kGroupItems;
                 const int unit = cta * kUnits + u;
@@ -390,16 +454,30 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         // ---- skip: tanh(W [g1, g2, g3, fw, lookback, previous]) then GLU (fargan.py:311-325) ----
         {
             float acc[kUnits] = {};
+            tick();
             stage2(staged, gs.g[0][slot], staged + kHop * kGroupItems, gs.g[1][slot]);
             __syncthreads();
+            tock(wait_stage);
+            tick2();
             dot<kUnits>(acc, w + kWSkip, staged, 2 * kHop, part, b);
+            tock2(t_dot);
             __syncthreads();
+            tick();
             stage2(staged, gs.g[2][slot], staged + kHop * kGroupItems, gs.fwg[slot]);
             __syncthreads();
+            tock(wait_stage);
+            tick2();
             dot<kUnits>(acc, w + kWSkip + 2 * kHop * kUnits, staged, 2 * kHop, part, b);
+            tock2(t_dot);
+            tick2();
             dot<kUnits>(acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
+            tock2(t_dot);
+            tick2();
             dot<kUnits>(acc, w + kWSkip + (4 * kHop + kSub) * kUnits, last, kSub, part, b);
+            tock2(t_dot);
+            tick2();
             reduce<kUnits>(acc, scratch, part, b);
+            tock2(t_reduce);
             if (tid < kUnits * kGroupItems)
                 __stcg(gs.skip[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
                        tanhf(scratch[tid]));
@@ -408,11 +486,17 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
 
         // ---- output: tanh(W skip), one of the 64 samples per CTA (fargan.py:327-329) ----
         {
+            tick();
             stage(staged, gs.skipg[slot], kHop);
             __syncthreads();
+            tock(wait_stage);
             float acc[1] = {};
+            tick2();
             dot<1>(acc, w + kWOut, staged, kHop, part, b);
+            tock2(t_dot);
+            tick2();
             reduce<1>(acc, scratch, part, b);
+            tock2(t_reduce);
             if (tid < kGroupItems) {
                 const float y = tanhf(scratch[tid]);
                 __stcg(gs.history + (size_t)(kHistory + n * kSub + cta) * kGroupItems + tid, y);
@@ -422,6 +506,13 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         }
         __syncthreads();   // `staged`, `scratch` and `in` are rewritten by the next subframe
         current ^= 1;
+    }
+    if (timing) {
+        g_fargan_cycles[0] = clock64() - loop_start;
+        g_fargan_cycles[1] = wait_input;
+        g_fargan_cycles[2] = wait_stage;
+        g_fargan_cycles[3] = frames * kSubframes;
+        g_fargan_cycles[4] = t_dot; g_fargan_cycles[5] = t_reduce; g_fargan_cycles[6] = t_input;
     }
 }
 
@@ -699,12 +790,26 @@ int fargan_forward(
         cond += (size_t)first * kGroupItems * kCond * frames;
         feats += (size_t)first * kGroupItems * 114 * frames;
         int frames_arg = frames;
-        void* args[] = {&weights, &cond, &feats, &prev, &gs, &out, &items, &frames_arg};
+        static int debug = -1;
+        if (debug < 0) {
+            const char* flag = getenv("PMN_FARGAN_DEBUG");
+            debug = flag && flag[0] == '1';
+        }
+        void* args[] = {&weights, &cond, &feats, &prev, &gs, &out, &items, &frames_arg, &debug};
         LaunchScope scope("fargan_kernel", stream);
         PMN_TRY(check_cuda(
             cudaLaunchCooperativeKernel(
                 (void*)fargan_kernel, dim3(count * kGroupCtas), dim3(kThreads), args, kSmemBytes, stream),
             "fargan cooperative launch"));
+        if (debug) {
+            long long host[8];
+            cudaStreamSynchronize(stream);
+            cudaMemcpyFromSymbol(host, g_fargan_cycles, sizeof(host));
+            fprintf(stderr, "fargan CTA 0: %lld subframes, %lld cycles each: %lld building the subframe input (%lld of "
+                            "them waiting), %lld waiting in the stage calls, %lld in dot products, %lld in reductions\n",
+                    host[3], host[0] / host[3], host[6] / host[3], host[1] / host[3], host[2] / host[3],
+                    host[4] / host[3], host[5] / host[3]);
+        }
     }
     return PMN_OK;
 }
