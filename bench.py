@@ -790,6 +790,17 @@ def gpu_eager_baseline(ctx):
         except Exception as error:
             result['train']['modes'][name] = {'error': repr(error)[:200]}
         torch.cuda.empty_cache()
+    # FARGAN (configs[4]) the same way, in a process of its own: the reference freezes its
+    # configuration at import.  A Python loop of 4 subframes x frames, ~60 launches each.
+    try:
+        import subprocess
+        done = subprocess.run(
+            [sys.executable, '-m', 'oracle.reference', '--fargan-eager', str(BATCH), str(FRAMES)],
+            cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+        lines = [line for line in done.stdout.splitlines() if line.startswith('{')]
+        result['fargan'] = json.loads(lines[-1]) if lines else {'error': done.stderr[-300:]}
+    except Exception as error:
+        result['fargan'] = {'error': repr(error)[:200]}
     return result
 
 

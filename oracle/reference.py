@@ -89,3 +89,46 @@ class TrainingStep:
         self.scaler.step(self.generator_optimizer)
         self.scaler.update()
         return generator_losses
+
+
+def fargan_eager(batch, frames, seed=1234):
+    """The reference FARGAN generator (config/fargan.py) run eagerly by PyTorch on cuda:0, one
+    forward of `batch` utterances x `frames` frames after a short warm-up: ms and samples / s.
+    Run in its own process (`python -m oracle.reference --fargan-eager B F`): the reference
+    freezes its configuration at import."""
+    import json
+    import time
+    import torch
+    where = root()
+    promonet = load(os.path.join(where, 'config', 'fargan.py')) if where else None
+    if promonet is None:
+        return {'unavailable': 'the reference tree (oracle/_ref) did not travel to this box'}
+    from promonet_b200 import synthetic
+    device = torch.device('cuda', 0)
+    model = generator(promonet, seed).to(device)
+    inputs = [t.to(device) for t in synthetic.synthesis(batch, frames, seed=seed)]
+    previous = torch.zeros(batch, 1, promonet.NUM_PREVIOUS_SAMPLES, device=device)
+
+    def forward(count):
+        args = [t[..., :count] if t.ndim > 1 else t for t in inputs]
+        with torch.inference_mode():
+            return model(*args, previous)
+    forward(min(frames, 4))          # warm-up: kernels loaded, cuBLAS handles made
+    torch.cuda.synchronize()
+    begin = time.perf_counter()
+    audio = forward(frames)
+    torch.cuda.synchronize()
+    seconds = time.perf_counter() - begin
+    return {
+        'what': f'promonet.model.Generator (config/fargan.py) forward on cuda, {batch} x {frames} frames, '
+                f'torch {torch.__version__} eager fp32 (TF32 off), one forward after a 4-frame warm-up',
+        'unit': 'samples/s', 'ms_per_step': seconds * 1e3,
+        'value': audio.shape[0] * audio.shape[-1] / seconds,
+        'finite': bool(torch.isfinite(audio).all())}
+
+
+if __name__ == '__main__':
+    import json
+    import sys
+    if len(sys.argv) == 4 and sys.argv[1] == '--fargan-eager':
+        print(json.dumps(fargan_eager(int(sys.argv[2]), int(sys.argv[3]))))

@@ -194,3 +194,41 @@ def test_two_rank_validation_sums_equal_the_single_process_metrics():
         assert list(scalars) == ['pitch', 'periodicity', 'ppg', 'loudness', 'loudness-loud', 'loudness-quiet']
         for name, value in expected.items():
             assert scalars[name] == pytest.approx(value, rel=1e-12), name
+
+
+class _Closable:
+    """Stands in for a Trainer: shutdown must close it before the process group goes away"""
+
+    def __init__(self):
+        self.closed_while_initialized = None
+
+    def close(self):
+        self.closed_while_initialized = torch.distributed.is_initialized()
+
+
+def _shutdown_worker(rank, world, port, queue):
+    os.environ.update(
+        RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+        MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    parallel.initialize('gloo')
+    trainer = _Closable()
+    parallel.shutdown(trainer, grace=60.)
+    queue.put((rank, trainer.closed_while_initialized, torch.distributed.is_initialized()))
+
+
+def test_shutdown_closes_trainers_then_destroys_the_process_group():
+    """parallel.shutdown: close, barrier, destroy_process_group (the multi-GPU benchmark and the
+    data-parallel tests end through it); a no-op without a process group"""
+    parallel.shutdown()
+    context = mp.get_context('spawn')
+    queue = context.Queue()
+    port = _free_port()
+    workers = [
+        context.Process(target=_shutdown_worker, args=(rank, 2, port, queue)) for rank in range(2)]
+    for worker in workers:
+        worker.start()
+    results = sorted(queue.get(timeout=120) for _ in workers)
+    for worker in workers:
+        worker.join(timeout=60)
+        assert worker.exitcode == 0
+    assert results == [(0, True, False), (1, True, False)]
