@@ -114,7 +114,8 @@ int launch_zero_plane_pads(
 // One residual pair y = x + c2(lrelu(c1(lrelu(x)))) (hifigan.py:198-210) in one kernel
 // (conv_pair_tc.cu): x, out, accum are fp32 (B, C, T); w1 / w2 are the slabs of
 // launch_pack_tc_weight; C in {32, 64, 128}, odd k <= 11, (k - 1) dilation <= 50.
-// out / accum must not alias x.  Bit-identical to the two launch_conv1d_tc calls.
+// out / accum must not alias x.  Bit-identical to two conv1d_tc_kernel launches (where launch_conv1d_tc
+// takes conv1d_tcw_kernel instead, the two agree to fp32 rounding: another order of the tap sum).
 bool tc_pair_supported(int channels, int k, int dilation);
 int launch_conv_pair_tc(
     const float* x, const __nv_bfloat16* w1, const float* bias1, const __nv_bfloat16* w2,
