@@ -40,7 +40,11 @@ def reference(x, w, bias, dilation, in_slope):
 @pytest.mark.parametrize('channels,k,dilation,t_len,batch', [
     (32, 3, 1, 512, 1), (32, 11, 5, 1500, 2), (64, 7, 3, 700, 3), (64, 3, 1, 256, 1),
     (128, 11, 1, 300, 2), (128, 11, 5, 1111, 1), (128, 7, 1, 256, 1),
-    (256, 3, 5, 129, 2), (256, 11, 3, 1000, 1), (256, 7, 1, 128, 1)])
+    (256, 3, 5, 129, 2), (256, 11, 3, 1000, 1), (256, 7, 1, 128, 1),
+    # the narrow layers' kernel (weights on the M side, 224-step tiles): shorter than the halo, one
+    # tile exactly, one step into the next tile, the widest tap shifts, many tiles per CTA
+    (64, 11, 5, 30, 2), (64, 11, 1, 224, 1), (32, 11, 5, 225, 3), (64, 7, 5, 449, 2),
+    (32, 11, 1, 100, 1), (64, 3, 5, 2000, 1), (32, 11, 3, 224 * 160 + 7, 1)])
 def test_conv1d_tc_matches_fp64(channels, k, dilation, t_len, batch):
     torch.manual_seed(channels + k + dilation)
     x = torch.randn(batch, channels, t_len)
@@ -62,20 +66,22 @@ def test_conv1d_tc_many_tiles_per_cta():
     assert relative_error(out, expected) < 1e-4
 
 
-def test_conv1d_tc_epilogue():
+@pytest.mark.parametrize('channels', [64, 32, 128])
+def test_conv1d_tc_epilogue(channels):
+    """64: conv1d_tcw_kernel; 32 (k = 7 with a residual): conv1d_tc_kernel, CONCAT; 128: plain"""
     torch.manual_seed(2)
-    x = torch.randn(2, 64, 600)
-    w = torch.randn(64, 64, 7) / (64 * 7) ** .5
-    bias, residual = torch.randn(64), torch.randn(2, 64, 600)
+    x = torch.randn(2, channels, 600)
+    w = torch.randn(channels, channels, 7) / (channels * 7) ** .5
+    bias, residual = torch.randn(channels), torch.randn(2, channels, 600)
     y = reference(x, w, bias, 3, 0.1) + residual.double()
-    accum = torch.ones(2, 64, 600, device='cuda')
+    accum = torch.ones(2, channels, 600, device='cuda')
     out, planes = conv1d_tc(
         x, w, bias, residual, dilation=3, in_slope=0.1, out_slope=0.1, want_planes=True,
         accum=accum, accum_mode=2, accum_scale=1 / 3)
     assert relative_error(out, y) < 1e-4
     assert relative_error(planes, torch.nn.functional.leaky_relu(y, 0.1)) < 1e-4
     assert relative_error(accum, 1. + y / 3) < 1e-4
-    accum = torch.empty(2, 64, 600, device='cuda')
+    accum = torch.empty(2, channels, 600, device='cuda')
     out, _ = conv1d_tc(x, w, bias, dilation=3, in_slope=0.1, accum=accum, accum_mode=1,
                        accum_scale=0.5, want_out=False)
     assert out is None
