@@ -264,8 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                                     tc_mma_f8(d_low, smem_desc(xa8 + x_half, rows * 16, a_sbo),
                                               smem_desc(wa8 + w_half, N * 16, 128), idesc0, 1);
                                 }
-                                continue;
-                            }
+                            } else {
 #pragma unroll
                             for (int kk = 0; kk < KB / 16; ++kk) {
                                 const uint32_t xa = x_addr + (2 * kk * rows + row) * 16;
@@ -287,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                                     tc_mma(d, a_lo, b_hi, idesc, 1);
                                     tc_mma(d, a_hi, b_lo, idesc, 1);
                                 }
+                            }
                             }
                         }
                         tc_commit(w_empty + ws);

@@ -52,9 +52,9 @@ constexpr int kCond = 2 * kHop;     // 512
 constexpr int kGroupItems = 16;     // utterances per CTA group
 constexpr int kGroupCtas = 64;
 constexpr int kUnits = kHop / kGroupCtas;  // 4 output units per CTA per layer
-constexpr int kThreads = 512;            // 256: two warps per scheduler left the dot products latency-bound (gpurun call AR:
-                                      // 70 % of a subframe was local work, 30 % waiting for operands)
-constexpr int kParts = kThreads / kGroupItems;  // 32 K-partitions
+constexpr int kThreads = 256;            // 512 measured the same (profiles/r2_fargan_breakdown.txt); the side
+                                      // sums below want the registers
+constexpr int kParts = kThreads / kGroupItems;  // 16 K-partitions
 
 // Per-CTA weight image (floats), every block stored [k][rows]
 constexpr int kWFw = 0;                                   // 520 x 4
@@ -108,12 +108,6 @@ __device__ __forceinline__ float load_l2(const float* p) {
     asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
-// one value, waiting for its producer
-__device__ __forceinline__ float wait_value(const float* p) {
-    float v = load_l2(p);
-    while (pending(v)) v = load_l2(p);
-    return v;
-}
 
 __device__ __forceinline__ float sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -158,35 +152,6 @@ __device__ __forceinline__ void stage(float* dst, const float* src, int rows) {
 #pragma unroll
     for (int j = 0; j < kPer; ++j) d[j * kThreads] = v[j];
 }
-// two activations at once (eight loads in flight)
-__device__ __forceinline__ void stage2(float* dst0, const float* src0, float* dst1, const float* src1) {
-    constexpr int kPer = kHop * kGroupItems / 4 / kThreads;   // 4
-    const float4* s[2] = {reinterpret_cast<const float4*>(src0) + threadIdx.x,
-                          reinterpret_cast<const float4*>(src1) + threadIdx.x};
-    float4 v[2][kPer];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) v[a][j] = load_l2(s[a] + j * kThreads);
-    bool again;
-    do {
-        again = false;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int j = 0; j < kPer; ++j) {
-                if (pending(v[a][j].x) || pending(v[a][j].y) || pending(v[a][j].z) || pending(v[a][j].w)) {
-                    v[a][j] = load_l2(s[a] + j * kThreads);
-                    again = true;
-                }
-            }
-    } while (again);
-    float4* d0 = reinterpret_cast<float4*>(dst0) + threadIdx.x;
-    float4* d1 = reinterpret_cast<float4*>(dst1) + threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) { d0[j * kThreads] = v[0][j]; d1[j * kThreads] = v[1][j]; }
-}
-
 // acc[r] += sum_k w[k][r] * x[k][b] over this thread's K partition.  The ROWS weights of a k are
 // contiguous and 16-byte aligned (every block of the image starts at a multiple of 4 floats):
 // they are read as ROWS / 4 vector loads -- with scalar loads the dot products were bound by the
@@ -215,6 +180,30 @@ __device__ __forceinline__ void dot(
             const float* row = w + k * ROWS;
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(row[r], a, acc[r]);
+        }
+    }
+}
+
+// The same with the activation read straight from L2 (values a subframe old: complete, no polling);
+// all of a thread's loads are independent, so the product costs one L2 latency -- spent in the
+// shadow of an exchange the CTA is waiting for anyway
+template <int ROWS>
+__device__ __forceinline__ void dot_global(
+    float (&acc)[ROWS], const float* __restrict__ w, const float* __restrict__ x, int part, int b) {
+    constexpr int kSteps = kHop / kParts;
+    float a[kSteps];
+#pragma unroll
+    for (int i = 0; i < kSteps; ++i) a[i] = __ldcg(x + (part + i * kParts) * kGroupItems + b);
+#pragma unroll
+    for (int i = 0; i < kSteps; ++i) {
+        const float4* row = reinterpret_cast<const float4*>(w + (part + i * kParts) * ROWS);
+#pragma unroll
+        for (int q = 0; q < ROWS / 4; ++q) {
+            const float4 v = row[q];
+            acc[4 * q] = fmaf(v.x, a[i], acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v.y, a[i], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v.z, a[i], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v.w, a[i], acc[4 * q + 3]);
         }
     }
 }
@@ -375,6 +364,29 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                        tanhf(scratch[tid]));
         }
 
+        // Side sums: everything of the GRU cells and of the skip layer that does not depend on this
+        // subframe's exchanges -- the recurrent halves W_hh h of the three cells (h of the previous
+        // subframe, read straight from L2), the lookback / previous-subframe columns of their input
+        // halves and of the skip layer -- is computed here, while the other CTAs' framewise outputs
+        // travel, instead of on the critical path of the later layers
+        const float* lookback = in + (3 * kSub + 2) * kGroupItems;  // pitch_lookback[:, 2:-2]
+        const float* last = in + 2 * kSub * kGroupItems;             // previous subframe
+        float gh[3][3 * kUnits] = {}, gi_side[3][3 * kUnits] = {}, skip_acc[kUnits] = {}, h_previous[3] = {};
+        tick2();
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const float* wih = w + kWGru + s * (kGruIh + kGruHh);
+            dot_global<3 * kUnits>(gh[s], wih + kGruIh, gs.h[s][before], part, b);
+            dot<3 * kUnits>(gi_side[s], wih + kHop * 3 * kUnits, lookback, kSub, part, b);
+            dot<3 * kUnits>(gi_side[s], wih + (kHop + kSub) * 3 * kUnits, last, kSub, part, b);
+            if (tid < kUnits * kGroupItems)
+                h_previous[s] = __ldcg(gs.h[s][before] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems +
+                                       (tid % kGroupItems));
+        }
+        dot<kUnits>(skip_acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
+        dot<kUnits>(skip_acc, w + kWSkip + (4 * kHop + kSub) * kUnits, last, kSub, part, b);
+        tock2(t_dot);
+
         // GLU: x * sigmoid(W x) for this CTA's 4 units (fargan.py:375-388)
         auto glu = [&](const float* wg, const float* x_global, float* out_global) {
             tick();
@@ -409,32 +421,23 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
         }
 
         // ---- three GRU cells + GLUs (fargan.py:267-309) ----
-        const float* lookback = in + (3 * kSub + 2) * kGroupItems;  // pitch_lookback[:, 2:-2]
-        const float* last = in + 2 * kSub * kGroupItems;             // previous subframe
+        // The input of cell s (fwg, g1, g2) is also a column block of the skip layer (blocks 3, 0, 1 of
+        // [g1, g2, g3, fw | lookback, previous]): its share of the skip sum is taken while it is staged
+#pragma unroll
         for (int s = 0; s < 3; ++s) {
             const float* wih = w + kWGru + s * (kGruIh + kGruHh);
-            const float* whh = wih + kGruIh;
             const float* x_global = s == 0 ? gs.fwg[slot] : gs.g[s - 1][slot];
             tick();
-            stage2(staged, x_global, staged + kHop * kGroupItems, gs.h[s][before]);
+            stage(staged, x_global, kHop);
             __syncthreads();
             tock(wait_stage);
-            float gi[3 * kUnits] = {}, gh[3 * kUnits] = {};
             tick2();
-            dot<3 * kUnits>(gi, wih, staged, kHop, part, b);
-            tock2(t_dot);
-            tick2();
-            dot<3 * kUnits>(gi, wih + kHop * 3 * kUnits, lookback, kSub, part, b);
-            tock2(t_dot);
-            tick2();
-            dot<3 * kUnits>(gi, wih + (kHop + kSub) * 3 * kUnits, last, kSub, part, b);
-            tock2(t_dot);
-            tick2();
-            dot<3 * kUnits>(gh, whh, staged + kHop * kGroupItems, kHop, part, b);
+            dot<3 * kUnits>(gi_side[s], wih, staged, kHop, part, b);
+            dot<kUnits>(skip_acc, w + kWSkip + (s == 0 ? 3 : s - 1) * kHop * kUnits, staged, kHop, part, b);
             tock2(t_dot);
             float both[6 * kUnits];
 #pragma unroll
-            for (int r = 0; r < 3 * kUnits; ++r) { both[r] = gi[r]; both[3 * kUnits + r] = gh[r]; }
+            for (int r = 0; r < 3 * kUnits; ++r) { both[r] = gi_side[s][r]; both[3 * kUnits + r] = gh[s][r]; }
             tick2();
             reduce<6 * kUnits>(both, scratch, part, b);
             tock2(t_reduce);
@@ -445,38 +448,22 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                 const float r = sigmoid(at(3 * u) + at(3 * kUnits + 3 * u));
                 const float z = sigmoid(at(3 * u + 1) + at(3 * kUnits + 3 * u + 1));
                 const float c = tanhf(at(3 * u + 2) + r * at(3 * kUnits + 3 * u + 2));
-                const float h = staged[(kHop + unit) * kGroupItems + col];
-                __stcg(gs.h[s][slot] + (size_t)unit * kGroupItems + col, (1.f - z) * c + z * h);
+                __stcg(gs.h[s][slot] + (size_t)unit * kGroupItems + col, (1.f - z) * c + z * h_previous[s]);
             }
             glu(w + kWGlu + s * kHop * kUnits, gs.h[s][slot], gs.g[s][slot]);
         }
 
         // ---- skip: tanh(W [g1, g2, g3, fw, lookback, previous]) then GLU (fargan.py:311-325) ----
         {
-            float acc[kUnits] = {};
             tick();
-            stage2(staged, gs.g[0][slot], staged + kHop * kGroupItems, gs.g[1][slot]);
+            stage(staged, gs.g[2][slot], kHop);
             __syncthreads();
             tock(wait_stage);
             tick2();
-            dot<kUnits>(acc, w + kWSkip, staged, 2 * kHop, part, b);
-            tock2(t_dot);
-            __syncthreads();
-            tick();
-            stage2(staged, gs.g[2][slot], staged + kHop * kGroupItems, gs.fwg[slot]);
-            __syncthreads();
-            tock(wait_stage);
-            tick2();
-            dot<kUnits>(acc, w + kWSkip + 2 * kHop * kUnits, staged, 2 * kHop, part, b);
+            dot<kUnits>(skip_acc, w + kWSkip + 2 * kHop * kUnits, staged, kHop, part, b);
             tock2(t_dot);
             tick2();
-            dot<kUnits>(acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
-            tock2(t_dot);
-            tick2();
-            dot<kUnits>(acc, w + kWSkip + (4 * kHop + kSub) * kUnits, last, kSub, part, b);
-            tock2(t_dot);
-            tick2();
-            reduce<kUnits>(acc, scratch, part, b);
+            reduce<kUnits>(skip_acc, scratch, part, b);
             tock2(t_reduce);
             if (tid < kUnits * kGroupItems)
                 __stcg(gs.skip[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),

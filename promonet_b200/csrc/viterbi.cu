@@ -41,8 +41,6 @@ constexpr int kPair = 4;                        // utterances a cluster decodes 
 // so a band entry costs one conflict-free shared-memory load (the scores) instead of two loads
 // with two-way bank conflicts.  Measured before: 5.7 of the 7.4 kcycles of a frame were this scan.
 constexpr int kRegisterBand = 46;
-// one bulk copy of the slice per peer instead of 4-byte st.async per score: measured 7 % slower
-constexpr bool kBulkPublish = false;
 
 __host__ __device__ inline int cluster_slice(int states) {
     return (states + kClusterSize - 1) / kClusterSize;
