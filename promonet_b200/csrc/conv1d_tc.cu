@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll
                 for (int i = 0; i < kW; ++i) {
                     float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
+                    if (a.bias_batch) y += a.bias_batch[(size_t)b * a.c_out + c_first + i];
                     if (a.relu) y = fmaxf(y, 0.f);
                     v[i] = y;
                 }
@@ -447,8 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     }
                     if (a.accum_mode) {
 #pragma unroll
-                        for (int i = 0; i < kW; ++i)
-                            a.accum[idx + (size_t)i * out_row] = fmaf(v[i], a.accum_scale, acc[i]);
+                        for (int i = 0; i < kW; ++i) {
+                            const float total = fmaf(v[i], a.accum_scale, acc[i]);
+                            a.accum[idx + (size_t)i * out_row] = total;
+                            if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
+                        }
                     }
                     if (a.out_planes) {
                         const int out_pad = tc_padded_length_device(t_out);
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 // fp32 (B, C, T) -> hi/lo planes of lrelu(x); rows outside [0, T) are zeroed
 __global__ void __launch_bounds__(128) planes_from_f32_kernel(
     const float* __restrict__ x, __nv_bfloat16* __restrict__ planes,
-    int channels, int t_len, int t_pad, float slope) {
+    int channels, int t_len, int t_pad, float slope, int source_channels) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= t_pad) return;
     const int g = blockIdx.y, b = blockIdx.z;
@@ -500,11 +504,13 @@ __global__ void __launch_bounds__(128) planes_from_f32_kernel(
     const int t = row - kTcPad;
     uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
     if (t >= 0 && t < t_len) {
-        const float* src = x + ((size_t)b * channels + g * 8) * t_len + t;
+        const float* src = x + ((size_t)b * source_channels + g * 8) * t_len + t;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            split_pair(leaky(__ldg(src + (size_t)(2 * e) * t_len), slope),
-                       leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope), hi[e], lo[e]);
+            const int c = g * 8 + 2 * e;       // channels past the source's are zero
+            const float y0 = c < source_channels ? __ldg(src + (size_t)(2 * e) * t_len) : 0.f;
+            const float y1 = c + 1 < source_channels ? __ldg(src + (size_t)(2 * e + 1) * t_len) : 0.f;
+            split_pair(leaky(y0, slope), leaky(y1, slope), hi[e], lo[e]);
         }
     }
     const size_t row_hi = ((size_t)(b * 2) * groups + g) * t_pad + row;
@@ -684,6 +690,8 @@ bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
     struct Entry { int c_in, c_out; bool frames; TcPlan plan; };
     static const Entry table[] = {
         {256, 256, false, {32, 256, false}}, {128, 128, false, {64, 128, false}},
+        // HiFi-GAN's input convolution (113 -> 512, k = 7) with its input channels padded to 128
+        {128, 512, false, {32, 256, false}},
         {64, 64, false, {64, 64, true}},     {32, 32, false, {32, 32, true}},
         // penn FCNF0++ blocks 1..5 (valid convolutions, k = 32)
         {256, 32, false, {64, 32, true}},    {32, 128, false, {32, 128, false}},
@@ -740,6 +748,7 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     }
     if (a.c_in == 256 && a.c_out == 256) return launch_variant<256, 256, 1, 32, 3, 2>(a, 1, stream);
     if (a.c_in == 128 && a.c_out == 128) return launch_variant<128, 128, 2, 64, 2, 2>(a, 1, stream);
+    if (a.c_in == 128 && a.c_out == 512) return launch_variant<128, 256, 1, 32, 4, 2>(a, 2, stream);
     if (a.c_in == 64 && a.c_out == 64) return launch_variant<64, 64, 2, 64, 4, 2, kConv, 0, true>(a, 1, stream);
     if (a.c_in == 32 && a.c_out == 32) return launch_variant<32, 32, 4, 32, 8, 2, kConv, 0, true>(a, 1, stream);
     if (a.c_in == 256 && a.c_out == 32) return launch_variant<256, 32, 2, 64, 8, 2, kConv, 0, true>(a, 1, stream);
@@ -805,12 +814,14 @@ int launch_pack_tc_transpose_weight(
 
 int launch_planes_from_f32(
     const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
-    cudaStream_t stream) {
+    cudaStream_t stream, int source_channels) {
     PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "planes_from_f32: bad argument");
+    PMN_REQUIRE(source_channels >= 0 && source_channels <= channels, "planes_from_f32: bad channel count");
     const int t_pad = tc_padded_length(t_len);
     dim3 grid(ceil_div(t_pad, 128), channels / 8, batch);
     LaunchScope scope("planes_from_f32_kernel", stream);
-    planes_from_f32_kernel<<<grid, 128, 0, stream>>>(x, planes, channels, t_len, t_pad, slope);
+    planes_from_f32_kernel<<<grid, 128, 0, stream>>>(
+        x, planes, channels, t_len, t_pad, slope, source_channels ? source_channels : channels);
     return launched("planes_from_f32_kernel");
 }
 

@@ -47,12 +47,14 @@ struct TcConvArgs {
     const __nv_bfloat16* x_planes = nullptr;  // lrelu already applied by the producer
     const __nv_bfloat16* w_slabs = nullptr;
     const float* bias = nullptr;              // (C_out) or null
+    const float* bias_batch = nullptr;        // (B, C_out) added per item, or null (conv1d_tc_kernel only)
     const float* residual = nullptr;          // (B, C_out, T) fp32 or null
     float* out = nullptr;                     // (B, C_out, T) fp32 or null
     __nv_bfloat16* out_planes = nullptr;      // planes of lrelu(y, out_slope) or null
     float* accum = nullptr;                   // (B, C_out, T) fp32 or null
     int accum_mode = 0;                       // 0 unused, 1 store, 2 add
     float accum_scale = 1.f;
+    bool planes_from_accum = false;           // out_planes = planes of lrelu(the value stored to accum)
     int batch = 0, c_in = 0, c_out = 0, t_len = 0;
     int k = 1, dilation = 1;
     bool valid = false;                       // false: "same" padding (odd k); true: no padding
@@ -98,10 +100,12 @@ int launch_conv_transpose1d_tc(const TcConvArgs& args, int stride, cudaStream_t 
 int launch_pack_tc_transpose_weight(
     const float* w, __nv_bfloat16* slabs, int c_in, int c_out, int stride, cudaStream_t stream);
 
-// fp32 (B, C, T) -> planes of lrelu(x, slope); also writes the zero pad rows
+// fp32 (B, C, T) -> planes of lrelu(x, slope); also writes the zero pad rows.  source_channels
+// (0 = channels): channels of x; the planes' channels beyond them are zero (an operand padded
+// to a multiple of the kernel's K block)
 int launch_planes_from_f32(
     const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
-    cudaStream_t stream);
+    cudaStream_t stream, int source_channels = 0);
 
 // planes -> fp32 (hi + lo), for tests
 int launch_f32_from_planes(

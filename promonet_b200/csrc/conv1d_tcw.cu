@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(64 + SETS * 128, 1) conv1d_tcw_kernel(
 #pragma unroll
                         for (int i = 0; i < kPerThread; ++i) a.out[idx + (size_t)i * a.t_len] = v[i];
                     }
-                    if (a.accum_mode == 1) {
+                    if (a.accum_mode) {
 #pragma unroll
-                        for (int i = 0; i < kPerThread; ++i) a.accum[idx + (size_t)i * a.t_len] = v[i] * a.accum_scale;
-                    } else if (accumulate) {
-#pragma unroll
-                        for (int i = 0; i < kPerThread; ++i)
-                            a.accum[idx + (size_t)i * a.t_len] = fmaf(v[i], a.accum_scale, previous[i]);
+                        for (int i = 0; i < kPerThread; ++i) {
+                            const float total = accumulate ? fmaf(v[i], a.accum_scale, previous[i]) : v[i] * a.accum_scale;
+                            a.accum[idx + (size_t)i * a.t_len] = total;
+                            if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
+                        }
                     }
                     if (a.out_planes) {
 #pragma unroll
@@ -389,7 +389,8 @@ bool tcw_preferred(const TcConvArgs& a) {
 bool tcw_applies(const TcConvArgs& a) {
     if (!tcw_shape_supported(a.c_in, a.c_out, a.k)) return false;
     const int stack = 128 / a.c_in;
-    return !a.valid && !a.relu && !a.pool && a.frame_length == 0 && a.item_groups == 0 && a.plane_groups == 0 &&
+    return !a.valid && !a.relu && !a.pool && !a.f8x2 && a.bias_batch == nullptr && a.frame_length == 0 &&
+           a.item_groups == 0 && a.plane_groups == 0 &&
            a.out_row == 0 && a.debug == nullptr && a.dilation >= 1 && (stack - 1) * a.dilation <= kShiftMax &&
            (a.k - 1) / 2 * a.dilation <= kTcPad &&
            (((a.k + stack - 1) / stack) - 1) * stack * a.dilation <= kRowsMax - kColumns;

@@ -18,6 +18,7 @@ namespace pmn {
 namespace {
 
 constexpr int kNumFeatures = 113;   // config/static.py:47-52
+constexpr int kPaddedFeatures = 128;  // the input convolution's K on the tensor cores
 constexpr int kSpeakerChannels = 256;
 constexpr int kGlobalChannels = 258;  // static.py:40-43
 constexpr int kNumSpeakers = 109;     // static.py:58-59 (vctk)
@@ -61,6 +62,7 @@ struct pmn_generator {
     pmn::PackedConv conv1[pmn::kStages][3][3];
     pmn::PackedConv conv2[pmn::kStages][3][3];
     float* input_weight = nullptr;  // packed (113, 7, 512)
+    __nv_bfloat16* input_slabs = nullptr;   // tensor-core path: the same convolution with 128 input channels
 };
 
 namespace pmn {
@@ -183,6 +185,21 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
         return fail(PMN_ERR_STATE, "unexpected input_feature_conv shape");
     PMN_TRY(alloc(g, t->numel(), &g->input_weight));
     PMN_TRY(launch_pack_conv1d_weight(t->data, g->input_weight, kInitial, kNumFeatures, 7, stream));
+    if (math == PMN_MATH_BF16X3_TC) {
+        // (512, 113, 7) -> (512, 128, 7) with zero channels, then the tensor-core slabs
+        float *padded, *slabs;
+        const size_t padded_numel = (size_t)kInitial * kPaddedFeatures * 7;
+        PMN_TRY(alloc(g, padded_numel, &padded));
+        PMN_TRY(check_cuda(cudaMemsetAsync(padded, 0, padded_numel * sizeof(float), stream), "memset"));
+        PMN_TRY(check_cuda(
+            cudaMemcpy2DAsync(padded, (size_t)kPaddedFeatures * 7 * sizeof(float), t->data,
+                              (size_t)kNumFeatures * 7 * sizeof(float), (size_t)kNumFeatures * 7 * sizeof(float),
+                              kInitial, cudaMemcpyDeviceToDevice, stream),
+            "pad input weight"));
+        PMN_TRY(alloc(g, (tc_weight_elements(kInitial, kPaddedFeatures, 7) + 1) / 2, &slabs));
+        g->input_slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
+        PMN_TRY(launch_pack_tc_weight(padded, g->input_slabs, kInitial, kPaddedFeatures, 7, false, stream));
+    }
     PMN_TRY(find(g, "model.input_feature_conv.bias", &t));
     PMN_TRY(find(g, "model.input_speaker_conv.weight", &t));
     if (t->numel() != (size_t)kInitial * kGlobalChannels)
@@ -282,8 +299,21 @@ int generator_forward(
         g->store.data("model.input_speaker_conv.weight"),
         g->store.data("model.input_speaker_conv.bias"),
         w.speaker_bias, batch, kSpeakerChannels, kInitial, kNumSpeakers, stream));
-    // G3: input conv k7 + speaker bias
-    {
+    // G3: input conv k7 + speaker bias.  Tensor-core path: the 113 feature channels padded to 128,
+    // the speaker projection as a per-item bias, and the epilogue writes the LeakyReLU'd planes the
+    // first ConvTranspose1d reads (the fp32 tensor is not needed)
+    const bool input_on_tensor_cores = g->math == PMN_MATH_BF16X3_TC;
+    if (input_on_tensor_cores) {
+        PMN_TRY(launch_planes_from_f32(
+            w.features, w.a0, batch, kPaddedFeatures, frames, 1.f, stream, kNumFeatures));
+        PMN_TRY(launch_zero_plane_pads(w.at, batch, kInitial, frames, stream));
+        TcConvArgs a;
+        a.x_planes = w.a0; a.w_slabs = g->input_slabs;
+        a.bias = g->store.data("model.input_feature_conv.bias"); a.bias_batch = w.speaker_bias;
+        a.out_planes = w.at; a.out_slope = kSlope;
+        a.batch = batch; a.c_in = kPaddedFeatures; a.c_out = kInitial; a.t_len = frames; a.k = 7;
+        PMN_TRY(launch_conv1d_tc(a, stream));
+    } else {
         Conv1dArgs a;
         a.x = w.features; a.weight = g->input_weight;
         a.bias = g->store.data("model.input_feature_conv.bias");
@@ -296,13 +326,21 @@ int generator_forward(
 
     const float* stage_in = w.x_in;
     int t_len = frames;
+    bool planes_ready = false;   // w.a0 holds the planes of lrelu(stage_in)
     for (int s = 0; s < kStages; ++s) {
         // G4: LeakyReLU + ConvTranspose1d
         const PackedConv& up = g->up[s];
         if (g->math == PMN_MATH_BF16X3_TC) {
-            PMN_TRY(launch_planes_from_f32(stage_in, w.at, batch, up.c_in, t_len, kSlope, stream));
+            // the planes of lrelu(stage input) come from the epilogue that produced it: the input
+            // convolution (stage 0, in w.at) or the last residual-block launch of the stage before
+            // (in w.a0), unless that one ran as a fused pair
+            const __nv_bfloat16* up_planes = s == 0 ? w.at : w.a0;
+            if (!(s == 0 ? input_on_tensor_cores : planes_ready)) {
+                PMN_TRY(launch_planes_from_f32(stage_in, w.at, batch, up.c_in, t_len, kSlope, stream));
+                up_planes = w.at;
+            }
             TcConvArgs a;
-            a.x_planes = w.at; a.w_slabs = up.slabs; a.bias = up.bias; a.out = w.x0;
+            a.x_planes = up_planes; a.w_slabs = up.slabs; a.bias = up.bias; a.out = w.x0;
             a.batch = batch; a.c_in = up.c_in; a.c_out = up.c_out; a.t_len = t_len;
             PMN_TRY(launch_conv_transpose1d_tc(a, kUpRate[s], stream));
         } else {
@@ -364,11 +402,19 @@ int generator_forward(
                         a.accum = w.mrf;
                         a.accum_mode = j == 0 ? 1 : 2;
                         a.accum_scale = 1.f / 3.f;
+                        if (j == 2 && s + 1 < kStages) {
+                            // the stage's output is complete with this launch: its LeakyReLU'd planes,
+                            // the next stage's ConvTranspose1d operand, go to w.a0 (last read by this
+                            // block's first convolution)
+                            a.out_planes = w.a0;
+                            a.planes_from_accum = true;
+                        }
                     }
                     PMN_TRY(launch_conv1d_tc(a, stream));
                 }
             }
             stage_in = w.mrf;
+            planes_ready = !fused[2] && s + 1 < kStages;
             continue;
         }
         // G5/G6: three Blocks, mean folded into the last conv of each
