@@ -357,33 +357,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 mbar_wait(acc_full + as, aphase);
                 tc_fence_after();
                 const int t_up = UP * a.t_len;
+                // chunks are taken in runs that cover 8 output channels (8 / (16 / UP) chunks), so that
+                // the run's thread also holds what a 16-byte row of the output's planes needs
+                constexpr int kRun = UP >= 8 ? 8 * UP / kW : 1;
+                static_assert(kChunks % (2 * kRun) == 0, "chunk runs are split between two warp sets");
+                const int out_pad = tc_padded_length_device(t_up);
+                const int groups_out = a.c_out / 8;
 #pragma unroll 1
-                for (int chunk = half; chunk < kChunks; chunk += 2) {
-                    const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
+                for (int run = half; run < kChunks / kRun; run += 2) {
+                    float values[kRun * kW];     // [channel within the run][phase]
+                    const int s = run * kRun / kPerSub, c_run = (run * kRun % kPerSub) * kW;
                     const int i = row_of(s);
-                    uint32_t raw[kW];
-                    load(s, c0, raw);
-                    if (i >= 0) {
+                    const int o_run = (nt * N + c_run) / UP;
+#pragma unroll
+                    for (int part = 0; part < kRun; ++part) {
+                        const int c0 = c_run + part * kW;
+                        uint32_t raw[kW];
+                        load(s, c0, raw);
                         const int o0 = (nt * N + c0) / UP;
 #pragma unroll
                         for (int j = 0; j < kW / UP; ++j) {
                             const float bias = bias_smem[o0 + j];
-                            float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_up + (size_t)UP * i;
-                            if constexpr (UP % 4 == 0) {
 #pragma unroll
-                                for (int q = 0; q < UP; q += 4)
-                                    *reinterpret_cast<float4*>(dst + q) = make_float4(
-                                        __uint_as_float(raw[j * UP + q]) + bias,
-                                        __uint_as_float(raw[j * UP + q + 1]) + bias,
-                                        __uint_as_float(raw[j * UP + q + 2]) + bias,
-                                        __uint_as_float(raw[j * UP + q + 3]) + bias);
-                            } else {
+                            for (int q = 0; q < UP; ++q)
+                                values[part * kW + j * UP + q] = __uint_as_float(raw[j * UP + q]) + bias;
+                            if (i >= 0) {
+                                float* dst = a.out + ((size_t)b * a.c_out + o0 + j) * t_up + (size_t)UP * i;
+                                const float* v = values + part * kW + j * UP;
+                                if constexpr (UP % 4 == 0) {
 #pragma unroll
-                                for (int q = 0; q < UP; q += 2)
-                                    *reinterpret_cast<float2*>(dst + q) = make_float2(
-                                        __uint_as_float(raw[j * UP + q]) + bias,
-                                        __uint_as_float(raw[j * UP + q + 1]) + bias);
+                                    for (int q = 0; q < UP; q += 4)
+                                        *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < UP; q += 2)
+                                        *reinterpret_cast<float2*>(dst + q) = make_float2(v[q], v[q + 1]);
+                                }
                             }
+                        }
+                    }
+                    if (a.out_planes && i >= 0) {
+                        // planes of lrelu(y): per 8 channels and output sample one 16-byte row per plane
+                        constexpr int kChannels = kRun * kW / UP;        // 8 (UP = 8: one run) or 8 (UP = 2: one chunk)
+                        static_assert(kChannels == 8, "a run holds 8 output channels");
+#pragma unroll
+                        for (int q = 0; q < UP; ++q) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                split_pair(leaky(values[(2 * e) * UP + q], a.out_slope),
+                                           leaky(values[(2 * e + 1) * UP + q], a.out_slope), hi[e], lo[e]);
+                            const size_t row_hi =
+                                ((size_t)(b * 2) * groups_out + o_run / 8) * out_pad + kTcPad + (size_t)UP * i + q;
+                            const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
+                            *reinterpret_cast<uint4*>(a.out_planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(a.out_planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 }
@@ -790,7 +818,7 @@ int launch_conv_transpose1d_tc(const TcConvArgs& args, int stride, cudaStream_t 
     a.k = 3;
     a.dilation = 1;
     a.valid = false;
-    a.residual = nullptr; a.accum = nullptr; a.accum_mode = 0; a.out_planes = nullptr;
+    a.residual = nullptr; a.accum = nullptr; a.accum_mode = 0;   // out_planes: planes of lrelu(out, out_slope) or null
     const int n_tiles = stride * a.c_out / transpose_n_tile(a.c_in);
     switch (a.c_in) {
         case 512: return launch_variant<512, 256, 1, 32, 4, 2, kTranspose, 8>(a, n_tiles, stream);

@@ -326,15 +326,15 @@ int generator_forward(
 
     const float* stage_in = w.x_in;
     int t_len = frames;
-    bool planes_ready = false;   // w.a0 holds the planes of lrelu(stage_in)
+    bool planes_ready = false;   // w.ac holds the planes of lrelu(stage_in)
     for (int s = 0; s < kStages; ++s) {
         // G4: LeakyReLU + ConvTranspose1d
         const PackedConv& up = g->up[s];
         if (g->math == PMN_MATH_BF16X3_TC) {
             // the planes of lrelu(stage input) come from the epilogue that produced it: the input
             // convolution (stage 0, in w.at) or the last residual-block launch of the stage before
-            // (in w.a0), unless that one ran as a fused pair
-            const __nv_bfloat16* up_planes = s == 0 ? w.at : w.a0;
+            // (in w.ac), unless that one ran as a fused pair
+            const __nv_bfloat16* up_planes = s == 0 ? w.at : w.ac;
             if (!(s == 0 ? input_on_tensor_cores : planes_ready)) {
                 PMN_TRY(launch_planes_from_f32(stage_in, w.at, batch, up.c_in, t_len, kSlope, stream));
                 up_planes = w.at;
@@ -342,6 +342,9 @@ int generator_forward(
             TcConvArgs a;
             a.x_planes = up_planes; a.w_slabs = up.slabs; a.bias = up.bias; a.out = w.x0;
             a.batch = batch; a.c_in = up.c_in; a.c_out = up.c_out; a.t_len = t_len;
+            // ... and writes the planes of lrelu(its output), the residual blocks' first operand
+            PMN_TRY(launch_zero_plane_pads(w.a0, batch, up.c_out, t_len * kUpRate[s], stream));
+            a.out_planes = w.a0; a.out_slope = kSlope;
             PMN_TRY(launch_conv_transpose1d_tc(a, kUpRate[s], stream));
         } else {
             PMN_TRY(launch_conv_transpose1d(
@@ -362,7 +365,6 @@ int generator_forward(
                 any_planes = any_planes || !fused[j];
             }
             if (any_planes) {
-                PMN_TRY(launch_planes_from_f32(w.x0, w.a0, batch, channels, t_len, kSlope, stream));
                 PMN_TRY(launch_zero_plane_pads(w.at, batch, channels, t_len, stream));
                 PMN_TRY(launch_zero_plane_pads(w.ac, batch, channels, t_len, stream));
             }
@@ -404,9 +406,9 @@ int generator_forward(
                         a.accum_scale = 1.f / 3.f;
                         if (j == 2 && s + 1 < kStages) {
                             // the stage's output is complete with this launch: its LeakyReLU'd planes,
-                            // the next stage's ConvTranspose1d operand, go to w.a0 (last read by this
-                            // block's first convolution)
-                            a.out_planes = w.a0;
+                            // the next stage's ConvTranspose1d operand, go to w.ac (last read by this
+                            // pair's first convolution)
+                            a.out_planes = w.ac;
                             a.planes_from_accum = true;
                         }
                     }
