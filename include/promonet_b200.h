@@ -76,6 +76,12 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream);
  * for every mask. */
 int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask);
 
+/* Tensor-core math only: run the residual blocks of the C = 256 and C = 128 stages (62 % of the
+ * generator's FLOPs) with "fp16 + 2 x fp8" operands (pmn_conv1d_tc_f8): two thirds of the tensor
+ * cycles of the bf16 x 3 form, output within the same 1e-4 bar but closer to it (measured at
+ * B = 32 x 430 frames: DESIGN.md section 8).  Call after pmn_generator_finalize. */
+int pmn_generator_set_f8(pmn_generator* g, int enabled);
+
 size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames);
 
 /* Generator.forward generator.py:116-135.
@@ -245,6 +251,18 @@ size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k);
  * ([0] total, [1..3] cycles spent waiting on the pipeline barriers). */
 void pmn_debug_tc_counters(void* counters);
 int pmn_conv1d_tc(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation,
+    float in_slope, float out_slope,
+    void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same entry with "fp16 + 2 x fp8" operands (channels in {128, 256}): x and the weights are
+ * converted to fp16 of the scaled value plus two e4m3 sections (the value and its fp16 rounding
+ * error), products x_m w_m [kind::f16] + two fp8 correction products [kind::f8f6f4] accumulate in
+ * one TMEM accumulator at two thirds of the bf16 x 3 tensor cycles (conv1d_tc.cuh).  planes_out
+ * receives what the next convolution's operand holds of lrelu(y, out_slope): fp16 part + low part. */
+int pmn_conv1d_tc_f8(
     const float* x, const float* weight, const float* bias, const float* residual,
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
     int batch, int channels, int t_len, int k, int dilation,

@@ -29,6 +29,7 @@ SIGNATURES = {
         c_int, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
     'pmn_generator_finalize': (c_int, [c_void_p, c_int, c_void_p]),
     'pmn_generator_set_pair_mask': (c_int, [c_void_p, ctypes.c_uint]),
+    'pmn_generator_set_f8': (c_int, [c_void_p, c_int]),
     'pmn_generator_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int]),
     'pmn_generator_forward': (
         c_int,
@@ -90,6 +91,11 @@ SIGNATURES = {
     'pmn_debug_tc_counters': (None, [c_void_p]),
     'pmn_conv1d_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'pmn_conv1d_tc': (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+         c_void_p, c_size_t, c_void_p]),
+    'pmn_conv1d_tc_f8': (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_float, c_float,

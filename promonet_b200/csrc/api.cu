@@ -103,6 +103,11 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream) {
     return generator_finalize(g, math, (cudaStream_t)stream);
 }
 
+int pmn_generator_set_f8(pmn_generator* g, int enabled) {
+    PMN_REQUIRE(g, "set_f8: null generator");
+    return generator_set_f8(g, enabled != 0);
+}
+
 int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask) {
     PMN_REQUIRE(g, "set_pair_mask: null generator");
     return generator_set_pair_mask(g, mask);
@@ -357,6 +362,48 @@ size_t pmn_conv1d_tc_workspace_bytes(int batch, int channels, int t_len, int k) 
     return carve_tc_op(nullptr, batch, channels, t_len, k, 512).bytes;
 }
 
+namespace {
+int conv1d_tc_entry(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int c_in, int c_out, int t_len, int k, int dilation, int valid, int relu,
+    float in_slope, float out_slope, bool f8, void* workspace, size_t workspace_bytes, void* stream_) {
+    PMN_REQUIRE(x && weight && workspace, "conv1d_tc: null pointer");
+    PMN_REQUIRE(batch > 0 && t_len > 0, "conv1d_tc: empty input");
+    PMN_REQUIRE(tc_supported(c_in, c_out, k, dilation), "conv1d_tc: unsupported shape");
+    PMN_REQUIRE(c_out <= 512, "conv1d_tc: more than 512 output channels");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TcOpWorkspace w = carve_tc_op(workspace, batch, c_in, t_len, k, c_out);
+    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "conv1d_tc: workspace too small");
+    PMN_TRY(launch_planes_from_f32(x, w.x_planes, batch, c_in, t_len, in_slope, stream, 0, f8));
+    TcConvArgs a;
+    if (f8) {
+        // "fp16 + 2 x fp8" operands in and out (conv1d_tc.cuh)
+        int shift;
+        PMN_TRY(tc_f8_weight_shift_of(weight, (size_t)c_out * c_in * k, stream, &shift));
+        PMN_TRY(launch_pack_tc_weight_f8(weight, w.slabs, c_out, c_in, k, shift, stream));
+        a.f8x2 = a.out_f8 = true;
+        a.f8_unscale = tc_f8_unscale(shift);
+    } else {
+        PMN_TRY(launch_pack_tc_weight(weight, w.slabs, c_out, c_in, k, false, stream));
+    }
+    a.x_planes = w.x_planes; a.w_slabs = w.slabs; a.bias = bias; a.residual = residual;
+    a.out = out; a.accum = accum; a.accum_mode = accum_mode; a.accum_scale = accum_scale;
+    a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_len = t_len; a.k = k; a.dilation = dilation;
+    a.valid = valid != 0; a.relu = relu != 0;
+    a.out_slope = out_slope;
+    const int t_out = valid ? t_len - (k - 1) * dilation : t_len;
+    PMN_REQUIRE(t_out > 0, "conv1d_tc: input shorter than the kernel");
+    if (planes_out) {
+        a.out_planes = w.y_planes;
+        PMN_TRY(launch_zero_plane_pads(w.y_planes, batch, c_out, t_out, stream));
+    }
+    PMN_TRY(launch_conv1d_tc(a, stream));
+    if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, c_out, t_out, stream, f8));
+    return PMN_OK;
+}
+}  // namespace
+
 int pmn_conv1d_tc(
     const float* x, const float* weight, const float* bias, const float* residual,
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
@@ -373,30 +420,20 @@ int pmn_conv1d_tc_general(
     float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
     int batch, int c_in, int c_out, int t_len, int k, int dilation, int valid, int relu,
     float in_slope, float out_slope, void* workspace, size_t workspace_bytes, void* stream_) {
-    PMN_REQUIRE(x && weight && workspace, "conv1d_tc: null pointer");
-    PMN_REQUIRE(batch > 0 && t_len > 0, "conv1d_tc: empty input");
-    PMN_REQUIRE(tc_supported(c_in, c_out, k, dilation), "conv1d_tc: unsupported shape");
-    PMN_REQUIRE(c_out <= 512, "conv1d_tc: more than 512 output channels");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    TcOpWorkspace w = carve_tc_op(workspace, batch, c_in, t_len, k, c_out);
-    if (w.bytes > workspace_bytes) return fail(PMN_ERR_WORKSPACE, "conv1d_tc: workspace too small");
-    PMN_TRY(launch_planes_from_f32(x, w.x_planes, batch, c_in, t_len, in_slope, stream));
-    PMN_TRY(launch_pack_tc_weight(weight, w.slabs, c_out, c_in, k, false, stream));
-    TcConvArgs a;
-    a.x_planes = w.x_planes; a.w_slabs = w.slabs; a.bias = bias; a.residual = residual;
-    a.out = out; a.accum = accum; a.accum_mode = accum_mode; a.accum_scale = accum_scale;
-    a.batch = batch; a.c_in = c_in; a.c_out = c_out; a.t_len = t_len; a.k = k; a.dilation = dilation;
-    a.valid = valid != 0; a.relu = relu != 0;
-    a.out_slope = out_slope;
-    const int t_out = valid ? t_len - (k - 1) * dilation : t_len;
-    PMN_REQUIRE(t_out > 0, "conv1d_tc: input shorter than the kernel");
-    if (planes_out) {
-        a.out_planes = w.y_planes;
-        PMN_TRY(launch_zero_plane_pads(w.y_planes, batch, c_out, t_out, stream));
-    }
-    PMN_TRY(launch_conv1d_tc(a, stream));
-    if (planes_out) PMN_TRY(launch_f32_from_planes(w.y_planes, planes_out, batch, c_out, t_out, stream));
-    return PMN_OK;
+    return conv1d_tc_entry(
+        x, weight, bias, residual, out, planes_out, accum, accum_mode, accum_scale, batch, c_in, c_out,
+        t_len, k, dilation, valid, relu, in_slope, out_slope, false, workspace, workspace_bytes, stream_);
+}
+
+int pmn_conv1d_tc_f8(
+    const float* x, const float* weight, const float* bias, const float* residual,
+    float* out, float* planes_out, float* accum, int accum_mode, float accum_scale,
+    int batch, int channels, int t_len, int k, int dilation, float in_slope, float out_slope,
+    void* workspace, size_t workspace_bytes, void* stream_) {
+    PMN_REQUIRE(tc_f8_plan(channels, channels, nullptr), "conv1d_tc_f8: 128 or 256 channels");
+    return conv1d_tc_entry(
+        x, weight, bias, residual, out, planes_out, accum, accum_mode, accum_scale, batch, channels,
+        channels, t_len, k, dilation, 0, 0, in_slope, out_slope, true, workspace, workspace_bytes, stream_);
 }
 
 void pmn_debug_pair_tc(void* counters, int variant) {

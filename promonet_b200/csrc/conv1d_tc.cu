@@ -29,6 +29,8 @@
 #include <cuda_fp8.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "conv1d_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -65,7 +67,8 @@ constexpr int kMaxFrameLength = 35;
 // XS activation-slab stages: 2 everywhere except the k = 1 layers with a long K (frame-major pitch
 // blocks 4 and 5), where a 32-channel slab is only 768 cycles of MMAs and two stages do not cover
 // the L2 latency of the next slab.
-// F8: "fp16 + 2 x fp8" operands (conv1d_tc.cuh); a second accumulator holds the fp8 corrections.
+// F8: "fp16 + 2 x fp8" operands (conv1d_tc.cuh): two kind::f16 and two kind::f8f6f4 MMAs per 32 input
+// channels instead of six bf16 ones, all into the same accumulator.
 template <int C_IN, int N, int S, int KB, int NW, int AS, int MODE, bool CONCAT, int XS = 2, bool F8 = false>
 struct TcConfig {
     static constexpr int kTile = S * 128;
@@ -79,7 +82,7 @@ struct TcConfig {
     static constexpr int kBarriers = 2 * kXStages + 2 * NW + 2 * AS;
     static constexpr int kSmem = kXStages * kXSlab + NW * kWSlab + kBarriers * 8 + 16 + 128 + 6144;
     static constexpr int kCols = CONCAT ? 2 * N : N;            // TMEM columns per 128 rows
-    static constexpr int kStageCols = (F8 ? 2 : 1) * S * kCols;   // TMEM columns of one accumulator stage
+    static constexpr int kStageCols = S * kCols;                // TMEM columns of one accumulator stage
     static constexpr int kColumns = AS * kStageCols;
     static constexpr int kAlloc = kColumns <= 32 ? 32 : kColumns <= 64 ? 64 : kColumns <= 128 ? 128
                                   : kColumns <= 256 ? 256 : 512;
@@ -241,7 +244,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             const uint32_t d = d_base + s * Cfg::kCols;
                             if constexpr (F8) {
                                 constexpr uint32_t idesc0 = instr_desc_format0(128, N);
-                                const uint32_t d_low = d + S * Cfg::kCols;      // the corrections' accumulator
                                 const uint32_t x8 = x_addr + Cfg::kGroups * rows * 16;
                                 const uint32_t w8 = w_addr + Cfg::kGroups * N * 16;
 #pragma unroll
@@ -259,9 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                                     const uint32_t wa8 = w8 + 2 * kk * N * 16;
                                     constexpr uint32_t w_half = (Cfg::kGroups / 2) * N * 16;
                                     const uint32_t x_half = (Cfg::kGroups / 2) * rows * 16;
-                                    tc_mma_f8(d_low, smem_desc(xa8, rows * 16, a_sbo), smem_desc(wa8, N * 16, 128),
-                                              idesc0, !(first && kk == 0));
-                                    tc_mma_f8(d_low, smem_desc(xa8 + x_half, rows * 16, a_sbo),
+                                    tc_mma_f8(d, smem_desc(xa8, rows * 16, a_sbo), smem_desc(wa8, N * 16, 128), idesc0, 1);
+                                    tc_mma_f8(d, smem_desc(xa8 + x_half, rows * 16, a_sbo),
                                               smem_desc(wa8 + w_half, N * 16, 128), idesc0, 1);
                                 }
                             } else {
@@ -337,11 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::kStageCols + s * Cfg::kCols + c0;
                 tc_load16(address, raw);
                 if constexpr (F8) {
-                    uint32_t low[kW];
-                    tc_load16(address + S * Cfg::kCols, low);
 #pragma unroll
-                    for (int i = 0; i < kW; ++i)
-                        raw[i] = __float_as_uint(fmaf(__uint_as_float(low[i]), a.correction_scale, __uint_as_float(raw[i])));
+                    for (int i = 0; i < kW; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * a.f8_unscale);
                 }
                 if constexpr (CONCAT) {
                     uint32_t other[kW];
@@ -396,7 +394,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             }
                         }
                     }
-                    if (a.out_planes && i >= 0) {
+                    if (a.out_planes && a.out_f8 && i >= 0) {
+                        // the run's 8 channels: one fp16 row and half a row of each e4m3 section per sample
+                        const size_t item = (size_t)b * (groups_out * 2);
+                        const int half_row = (o_run / 8) & 1;
+#pragma unroll
+                        for (int q = 0; q < UP; ++q) {
+                            uint32_t main[4], coarse[2], low[2];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                uint32_t z, l;
+                                split_pair_f8(leaky(values[(2 * e) * UP + q], a.out_slope),
+                                              leaky(values[(2 * e + 1) * UP + q], a.out_slope), main[e], z, l);
+                                if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
+                                else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
+                            }
+                            const size_t at = kTcPad + (size_t)UP * i + q;
+                            uint4* rows = reinterpret_cast<uint4*>(a.out_planes);
+                            rows[(item + o_run / 8) * out_pad + at] = make_uint4(main[0], main[1], main[2], main[3]);
+                            uint2* coarse_row = reinterpret_cast<uint2*>(rows + (item + groups_out + o_run / 16) * out_pad + at);
+                            uint2* low_row = reinterpret_cast<uint2*>(
+                                rows + (item + groups_out + groups_out / 2 + o_run / 16) * out_pad + at);
+                            coarse_row[half_row] = make_uint2(coarse[0], coarse[1]);
+                            low_row[half_row] = make_uint2(low[0], low[1]);
+                        }
+                    } else if (a.out_planes && i >= 0) {
                         // planes of lrelu(y): per 8 channels and output sample one 16-byte row per plane
                         constexpr int kChannels = kRun * kW / UP;        // 8 (UP = 8: one run) or 8 (UP = 2: one chunk)
                         static_assert(kChannels == 8, "a run holds 8 output channels");
@@ -482,7 +504,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }
                     }
-                    if (a.out_planes) {
+                    if (a.out_planes && a.out_f8) {
+                        // [C / 8 fp16 rows | C / 16 coarse rows | C / 16 low rows] per item
+                        const int out_pad = tc_padded_length_device(t_out);
+                        uint32_t main[8], coarse[4], low[4];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            uint32_t z, l;
+                            split_pair_f8(leaky(v[2 * e], a.out_slope), leaky(v[2 * e + 1], a.out_slope), main[e], z, l);
+                            if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
+                            else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
+                        }
+                        const size_t item = (size_t)b * (groups_out * 2);
+                        uint4* rows = reinterpret_cast<uint4*>(a.out_planes);
+                        rows[(item + c_first / 8) * out_pad + kTcPad + t] = make_uint4(main[0], main[1], main[2], main[3]);
+                        rows[(item + c_first / 8 + 1) * out_pad + kTcPad + t] = make_uint4(main[4], main[5], main[6], main[7]);
+                        rows[(item + groups_out + c_first / 16) * out_pad + kTcPad + t] =
+                            make_uint4(coarse[0], coarse[1], coarse[2], coarse[3]);
+                        rows[(item + groups_out + groups_out / 2 + c_first / 16) * out_pad + kTcPad + t] =
+                            make_uint4(low[0], low[1], low[2], low[3]);
+                    } else if (a.out_planes) {
                         const int out_pad = tc_padded_length_device(t_out);
 #pragma unroll
                         for (int g = 0; g < kW / 8; ++g) {
@@ -547,6 +588,52 @@ __global__ void __launch_bounds__(128) planes_from_f32_kernel(
     *reinterpret_cast<uint4*>(planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// fp32 (B, C, T) -> the "fp16 + 2 x fp8" operand of lrelu(x) (conv1d_tc.cuh); one thread per row and
+// 16 channels; rows outside [0, T) are zeroed
+__global__ void __launch_bounds__(128) planes_f8_from_f32_kernel(
+    const float* __restrict__ x, uint4* __restrict__ rows, int channels, int t_len, int t_pad, float slope) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= t_pad) return;
+    const int g = blockIdx.y, b = blockIdx.z;       // g: 16-channel group
+    const int groups = channels / 8;
+    const int t = row - kTcPad;
+    uint32_t main[8] = {0, 0, 0, 0, 0, 0, 0, 0}, coarse[4] = {0, 0, 0, 0}, low[4] = {0, 0, 0, 0};
+    if (t >= 0 && t < t_len) {
+        const float* src = x + ((size_t)b * channels + g * 16) * t_len + t;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            uint32_t z, l;
+            split_pair_f8(leaky(__ldg(src + (size_t)(2 * e) * t_len), slope),
+                          leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope), main[e], z, l);
+            if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
+            else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
+        }
+    }
+    const size_t item = (size_t)b * (groups * 2);
+    rows[(item + 2 * g) * t_pad + row] = make_uint4(main[0], main[1], main[2], main[3]);
+    rows[(item + 2 * g + 1) * t_pad + row] = make_uint4(main[4], main[5], main[6], main[7]);
+    rows[(item + groups + g) * t_pad + row] = make_uint4(coarse[0], coarse[1], coarse[2], coarse[3]);
+    rows[(item + groups + groups / 2 + g) * t_pad + row] = make_uint4(low[0], low[1], low[2], low[3]);
+}
+
+// the same operand -> fp32 (B, C, T): main / s_m + low / s_xl (tests)
+__global__ void __launch_bounds__(128) f32_from_planes_f8_kernel(
+    const uint8_t* __restrict__ planes, float* __restrict__ x, int channels, int t_len, int t_pad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_len) return;
+    const int g = blockIdx.y, b = blockIdx.z;       // g: 8-channel group
+    const int groups = channels / 8;
+    const size_t item = (size_t)b * (groups * 2);
+    const __half* main = reinterpret_cast<const __half*>(planes + ((item + g) * t_pad + kTcPad + t) * 16);
+    const uint8_t* low = planes + ((item + groups + groups / 2 + g / 2) * t_pad + kTcPad + t) * 16 + (g % 2) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const __half_raw raw = __nv_cvt_fp8_to_halfraw(low[e], __NV_E4M3);
+        x[((size_t)b * channels + g * 8 + e) * t_len + t] =
+            __half2float(main[e]) / kF8ScaleMain + __half2float(__half(raw)) / kF8ScaleXLow;
+    }
+}
+
 // planes -> fp32 (B, C, T): hi + lo (tests / debugging)
 __global__ void __launch_bounds__(128) f32_from_planes_kernel(
     const __nv_bfloat16* __restrict__ planes, float* __restrict__ x,
@@ -605,10 +692,10 @@ __global__ void pack_tc_weight_kernel(
 }
 
 // Conv1d weight (C_out, C_in, K) fp32 -> "fp16 + 2 x fp8" slabs (conv1d_tc.cuh):
-// [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16 | [KB / 16][N][16] e4m3((w - fp16 w) s_low) | e4m3(w s) }
+// [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16(w s_main) | [KB / 16][N][16] e4m3((w s_main - fp16) s_low) | e4m3(w s) }
 __global__ void pack_tc_weight_f8_kernel(
     const float* __restrict__ w, uint8_t* __restrict__ slabs, int c_out, int c_in, int k, int kb_size,
-    int n_tile, float scale, float scale_low) {
+    int n_tile, float scale, float scale_main, float scale_low) {
     const size_t total = (size_t)c_out * c_in * k;
     const int blocks = c_in / kb_size;
     const size_t slab_bytes = (size_t)kb_size * n_tile * 4;
@@ -622,8 +709,9 @@ __global__ void pack_tc_weight_f8_kernel(
         const int nt = (int)rest;
         const int c = kb * kb_size + cl, o = nt * n_tile + col;
         const float value = w[((size_t)o * c_in + c) * k + tap];
-        const __half high = __float2half_rn(value);
-        const float low = value - __half2float(high);
+        const float main = value * scale_main;
+        const __half high = __float2half_rn(main);
+        const float low = main - __half2float(high);
         uint8_t* slab = slabs + ((size_t)(nt * k + tap) * blocks + kb) * slab_bytes;
         reinterpret_cast<__half*>(slab)[((size_t)(cl / 8) * n_tile + col) * 8 + cl % 8] = high;
         uint8_t* low_section = slab + (size_t)kb_size * n_tile * 2;
@@ -740,6 +828,19 @@ bool tc_conv_plan(int c_in, int c_out, bool frames, TcPlan* plan) {
     return false;
 }
 
+// "fp16 + 2 x fp8" variants: the pitch network's folded block 1 and the generator's C = 256 / 128
+// residual blocks.  C = 256 takes 128 columns x 256 rows per tile (two tiles per time window): with 256
+// columns x 128 rows a weight slab would serve 512 MMA cycles, 64 B per cycle and SM from L2
+bool tc_f8_plan(int c_in, int c_out, TcPlan* plan) {
+    TcPlan found;
+    if (c_in == 1024 && c_out == 128) found = {64, 128, false};
+    else if (c_in == 256 && c_out == 256) found = {32, 128, false};
+    else if (c_in == 128 && c_out == 128) found = {64, 128, false};
+    else return false;
+    if (plan) *plan = found;
+    return true;
+}
+
 bool tc_supported(int c_in, int c_out, int k, int dilation) {
     return tc_conv_plan(c_in, c_out, false, nullptr) && k >= 1 && k <= 32 &&
            (k - 1) * dilation <= 2 * kMaxHalo;
@@ -759,6 +860,18 @@ int tcw_mode() {
 
 int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     PMN_REQUIRE(a.x_planes && a.w_slabs, "conv1d_tc: null input");
+    PMN_REQUIRE(!a.f8x2 || (tc_f8_plan(a.c_in, a.c_out, nullptr) && a.frame_length == 0),
+                "conv1d_tc: no fp8 form for these channel counts");
+    if (a.f8x2) {
+        PMN_REQUIRE(a.out || a.out_planes || (a.accum && a.accum_mode), "conv1d_tc: no output");
+        PMN_REQUIRE(a.batch > 0 && a.t_len > 0, "conv1d_tc: empty input");
+        PMN_REQUIRE(a.k >= 1 && a.k <= 32 && (a.k - 1) * a.dilation <= 2 * kMaxHalo,
+                    "conv1d_tc: receptive field too wide");
+        PMN_REQUIRE(a.valid || a.k % 2 == 1, "conv1d_tc: same padding needs an odd kernel");
+        if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2, kConv, 0, false, 2, true>(a, 1, stream);
+        if (a.c_in == 256) return launch_variant<256, 128, 2, 32, 4, 2, kConv, 0, false, 2, true>(a, 2, stream);
+        return launch_variant<128, 128, 2, 64, 2, 2, kConv, 0, false, 2, true>(a, 1, stream);
+    }
     if (tcw_mode() && tcw_applies(a) && (tcw_mode() == 2 || tcw_preferred(a)))
         return launch_conv1d_tcw(a, a.w_slabs + tc_plain_weight_elements(a.c_out, a.c_in, a.k), stream);
     PMN_REQUIRE(a.out || a.out_planes || (a.accum && a.accum_mode), "conv1d_tc: no output");
@@ -783,9 +896,6 @@ int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     if (a.c_in == 32 && a.c_out == 128) return launch_variant<32, 128, 2, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 32 && a.c_out == 256) return launch_variant<32, 256, 1, 32, 4, 2>(a, 1, stream);
     if (a.c_in == 2048) return launch_variant<2048, 160, 1, 64, 3, 2>(a, 9, stream);
-    PMN_REQUIRE(!a.f8x2 || (a.c_in == 1024 && a.c_out == 128 && !frames), "conv1d_tc: fp8 corrections are built for 1024 -> 128");
-    if (a.c_in == 1024 && a.f8x2)
-        return launch_variant<1024, 128, 2, 64, 2, 1, kConv, 0, false, 2, true>(a, 1, stream);
     if (a.c_in == 1024) return launch_variant<1024, 128, 2, 64, 2, 2>(a, 1, stream);
     // K = 4096 / 8192 with 256 columns: a 128-row tile streams its whole 4 MB weight from L2 in 98 k
     // MMA cycles (43 B per cycle and SM: the L2 limit), so a tile takes 256 rows (two subtiles per
@@ -842,10 +952,19 @@ int launch_pack_tc_transpose_weight(
 
 int launch_planes_from_f32(
     const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
-    cudaStream_t stream, int source_channels) {
+    cudaStream_t stream, int source_channels, bool f8) {
     PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "planes_from_f32: bad argument");
     PMN_REQUIRE(source_channels >= 0 && source_channels <= channels, "planes_from_f32: bad channel count");
     const int t_pad = tc_padded_length(t_len);
+    if (f8) {
+        PMN_REQUIRE(channels % 16 == 0 && (source_channels == 0 || source_channels == channels),
+                    "planes_from_f32: the fp8 form takes whole 16-channel groups");
+        dim3 grid(ceil_div(t_pad, 128), channels / 16, batch);
+        LaunchScope scope("planes_f8_from_f32_kernel", stream);
+        planes_f8_from_f32_kernel<<<grid, 128, 0, stream>>>(
+            x, reinterpret_cast<uint4*>(planes), channels, t_len, t_pad, slope);
+        return launched("planes_f8_from_f32_kernel");
+    }
     dim3 grid(ceil_div(t_pad, 128), channels / 8, batch);
     LaunchScope scope("planes_from_f32_kernel", stream);
     planes_from_f32_kernel<<<grid, 128, 0, stream>>>(
@@ -854,9 +973,16 @@ int launch_planes_from_f32(
 }
 
 int launch_f32_from_planes(
-    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream) {
+    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream, bool f8) {
     PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "f32_from_planes: bad argument");
     dim3 grid(ceil_div(t_len, 128), channels / 8, batch);
+    if (f8) {
+        PMN_REQUIRE(channels % 16 == 0, "f32_from_planes: the fp8 form takes whole 16-channel groups");
+        LaunchScope scope("f32_from_planes_f8_kernel", stream);
+        f32_from_planes_f8_kernel<<<grid, 128, 0, stream>>>(
+            reinterpret_cast<const uint8_t*>(planes), x, channels, t_len, tc_padded_length(t_len));
+        return launched("f32_from_planes_f8_kernel");
+    }
     LaunchScope scope("f32_from_planes_kernel", stream);
     f32_from_planes_kernel<<<grid, 128, 0, stream>>>(planes, x, channels, t_len, tc_padded_length(t_len));
     return launched("f32_from_planes_kernel");
@@ -871,20 +997,31 @@ int launch_zero_plane_pads(
     return launched("zero_plane_pads_kernel");
 }
 
+int tc_f8_weight_shift_of(const float* w, size_t numel, cudaStream_t stream, int* shift) {
+    PMN_REQUIRE(w && shift && numel > 0, "tc_f8_weight_shift_of: bad argument");
+    std::vector<float> host(numel);
+    PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
+    PMN_TRY(check_cuda(cudaMemcpy(host.data(), w, numel * sizeof(float), cudaMemcpyDeviceToHost), "read weight"));
+    float largest = 0.f;
+    for (float value : host) largest = fmaxf(largest, fabsf(value));
+    *shift = tc_f8_weight_shift(largest);
+    return PMN_OK;
+}
+
 int launch_pack_tc_weight_f8(
     const float* w, void* slabs, int c_out, int c_in, int k, int weight_shift, cudaStream_t stream) {
     TcPlan plan;
-    PMN_REQUIRE(w && slabs && tc_conv_plan(c_in, c_out, false, &plan) && !plan.concat && plan.k_block % 32 == 0,
-                "pack_tc_weight_f8: bad argument");
+    PMN_REQUIRE(w && slabs && tc_f8_plan(c_in, c_out, &plan), "pack_tc_weight_f8: bad argument");
     PMN_REQUIRE(weight_shift >= 0 && weight_shift <= 16, "pack_tc_weight_f8: bad weight scale");
     const size_t total = (size_t)c_out * c_in * k;
     const int blocks = (int)min((size_t)2048, (total + 255) / 256);
-    // s_x s_wl = s_xl s_w: s_wl = s_w s_xl / s_x
+    // one factor for the three products: s_m s_wm = s_x s_wl' = s_xl s_w, hence s_wm = s_w s_xl / s_m
+    // and, per unit of the scaled weight, s_wl = s_wl' / s_wm = s_m / s_x
     const float scale = (float)(1 << weight_shift);
     LaunchScope scope("pack_tc_weight_f8_kernel", stream);
     pack_tc_weight_f8_kernel<<<blocks, 256, 0, stream>>>(
         w, static_cast<uint8_t*>(slabs), c_out, c_in, k, plan.k_block, plan.n_tile, scale,
-        scale * kF8ScaleXLow / kF8ScaleX);
+        scale * kF8ScaleXLow / kF8ScaleMain, kF8ScaleMain / kF8ScaleX);
     return launched("pack_tc_weight_f8_kernel");
 }
 

@@ -70,10 +70,11 @@ struct TcConvArgs {
     // the hi plane.  The frame-major pitch layers (pitch.cu) read planes[plane][position][c / 8]
     // with the batch index as the position: item_groups = C / 8, plane_groups = positions C / 8
     int item_groups = 0, plane_groups = 0;
-    // "fp16 + 2 x fp8" operands (tc_f8_* below): x_planes / w_slabs are in the three-section format
-    // and the fp8 correction products, accumulated apart, are added with this power-of-two factor
+    // "fp16 + 2 x fp8" operands (tc_f8_* below): x_planes / w_slabs are in the three-section format;
+    // all three products carry the same power-of-two scale, which the epilogue takes out again
     bool f8x2 = false;
-    float correction_scale = 1.f;
+    float f8_unscale = 1.f;                   // tc_f8_unscale(weight_shift)
+    bool out_f8 = false;                      // out_planes in the three-section format (any kernel mode)
     // Optional (gridDim.x, 10 warps, 4) cycle counters: [0] total, [1..3] barrier waits
     long long* debug = nullptr;
 };
@@ -105,11 +106,12 @@ int launch_pack_tc_transpose_weight(
 // to a multiple of the kernel's K block)
 int launch_planes_from_f32(
     const float* x, __nv_bfloat16* planes, int batch, int channels, int t_len, float slope,
-    cudaStream_t stream, int source_channels = 0);
+    cudaStream_t stream, int source_channels = 0, bool f8 = false);
 
-// planes -> fp32 (hi + lo), for tests
+// planes -> fp32 (hi + lo; f8: the fp16 section + the low section, both unscaled), for tests
 int launch_f32_from_planes(
-    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream);
+    const __nv_bfloat16* planes, float* x, int batch, int channels, int t_len, cudaStream_t stream,
+    bool f8 = false);
 
 // Zero only the pad rows of a planes buffer (the kernels never write them)
 int launch_zero_plane_pads(
@@ -130,21 +132,36 @@ int launch_conv_pair_tc(
 // kernel variant to launch (-1 = default)
 void tc_pair_set_debug(long long* counters, int variant);
 
-// fp32-grade products at two thirds of the tensor cycles, for operands of a KNOWN range (the
-// LayerNorm outputs of the pitch network): x w ~ fp16(x) fp16(w)  [kind::f16]
-//   + e4m3(x s_x) e4m3((w - fp16(w)) s_wl) + e4m3((x - fp16(x)) s_xl) e4m3(w s_w)   [kind::f8f6f4, K = 32]
-// with power-of-two scales, s_x s_wl = s_xl s_w, the two corrections (2^-11 of the main term: three
-// mantissa bits are enough for them) summed in a second accumulator and added in the epilogue.
-// Operand format, in 16-byte rows like the planes: [C / 8 groups][t_pad][8] fp16, then
-// [C / 16][t_pad][16] e4m3 of x s_x, then the same of (x - fp16(x)) s_xl.
-constexpr float kF8ScaleX = 8.f;            // |x| <= 56 before the e4m3 of x saturates
-constexpr float kF8ScaleXLow = 16384.f;     // 2^14: (x - fp16(x)) <= 2^-11 |x|
-// weight slabs [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16 | [KB / 16][N][16] e4m3 low | e4m3 high };
-// weight_shift: w 2^shift <= 256 (launch_pack_tc_weight_f8 derives the other scale)
+// fp32-grade products at two thirds of the tensor cycles, for operands of a bounded range (|x| < 56:
+// LayerNorm outputs of the pitch network, LeakyReLU'd activations of the generator), with
+// x_m = fp16(x s_m), w_m = fp16(w s_wm):
+//   x w s ~ x_m w_m  [kind::f16]  + e4m3(x s_x) e4m3((w s_wm - w_m) s_wl)
+//                                 + e4m3((x s_m - x_m) s_xl) e4m3(w s_w)   [kind::f8f6f4, K = 32]
+// All scales are powers of two chosen so that the three products carry the SAME factor
+// s = s_m s_wm = s_x s_wl' = s_xl' s_w (primes: per unit of x / w), so they accumulate in one TMEM
+// accumulator and the epilogue multiplies by 1 / s (exact).  The two corrections are 2^-11 of the
+// main term: the three mantissa bits of e4m3 are enough for them.
+// Operand format, in 16-byte rows like the planes: [C / 8 groups][t_pad][8] fp16 of x s_m, then
+// [C / 16][t_pad][16] e4m3 of x s_x, then the same of (x - x_m / s_m) s_xl
+// (device side: tc::split_pair_f8, whose constants mirror these).
+constexpr float kF8ScaleMain = 128.f;       // s_m: |x| < 512 in fp16 (saturating)
+constexpr float kF8ScaleX = 8.f;            // s_x: |x| <= 56 before the e4m3 of x saturates
+constexpr float kF8ScaleXLow = 16384.f;     // s_xl = 2^14: (x - x_m / s_m) <= 2^-11 |x|
+// weight slabs [n tile][tap][c_in / KB] x { [KB / 8][N][8] fp16 | [KB / 16][N][16] e4m3 low | e4m3 high }
+// with s_w = 2^weight_shift (|w| s_w <= 256), s_wm = s_w s_xl / s_m, s_wl' = s_w s_xl / s_x
+bool tc_f8_plan(int c_in, int c_out, TcPlan* plan);     // shapes the fp8 form is built for, their tiling
 int launch_pack_tc_weight_f8(
     const float* w, void* slabs, int c_out, int c_in, int k, int weight_shift, cudaStream_t stream);
-inline float tc_f8_correction_scale(int weight_shift) {
+inline float tc_f8_unscale(int weight_shift) {
     return 1.f / (kF8ScaleXLow * (float)(1 << weight_shift));
+}
+// ... for a weight tensor on the device (synchronises the stream: model set-up and parity entries only)
+int tc_f8_weight_shift_of(const float* w, size_t numel, cudaStream_t stream, int* shift);
+// the largest shift with max |w| 2^shift <= 256
+inline int tc_f8_weight_shift(float largest) {
+    int shift = 0;
+    while (shift < 16 && largest * (float)(2 << shift) <= 256.f) ++shift;
+    return shift;
 }
 
 // folded fp32 weight (C_out, C_in, K) -> hi/lo slabs

@@ -43,6 +43,9 @@ struct PackedConv {
     __nv_bfloat16* slabs = nullptr;  // tensor-core path: hi/lo weight slabs (conv1d_tc.cuh)
     const float* bias = nullptr;
     int c_in = 0, c_out = 0, k = 0;
+    // C >= 128: the same weights as "fp16 + 2 x fp8" slabs (conv1d_tc.cuh) and their power-of-two scale
+    void* f8_slabs = nullptr;
+    int f8_shift = 0;
 };
 
 }  // namespace
@@ -57,6 +60,9 @@ struct pmn_generator {
     // bit (3 * stage + block): run that residual block's three c1 -> c2 pairs as fused
     // conv_pair_tc_kernel launches (tensor-core math, C <= 128) instead of six conv1d_tc ones
     unsigned pair_mask = pmn::kDefaultPairMask;
+    // residual blocks of the C = 256 / 128 stages with "fp16 + 2 x fp8" operands (two thirds of the
+    // tensor cycles of bf16 x 3; pmn_generator_set_f8)
+    bool f8 = false;
 
     pmn::PackedConv up[pmn::kStages];
     pmn::PackedConv conv1[pmn::kStages][3][3];
@@ -114,6 +120,13 @@ int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int 
         float* slabs;  // two bf16 planes = the bytes of one fp32 tensor (+ the narrow layers' second format)
         PMN_TRY(alloc(g, (tc_weight_elements(channels, channels, k) + 1) / 2, &slabs));
         conv->slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
+        if (tc_f8_plan(channels, channels, nullptr)) {
+            float* f8_slabs;
+            PMN_TRY(alloc(g, shape->numel(), &f8_slabs));
+            PMN_TRY(tc_f8_weight_shift_of(w, shape->numel(), stream, &conv->f8_shift));
+            PMN_TRY(launch_pack_tc_weight_f8(w, f8_slabs, channels, channels, k, conv->f8_shift, stream));
+            conv->f8_slabs = f8_slabs;
+        }
         return launch_pack_tc_weight(w, conv->slabs, channels, channels, k, false, stream);
     }
     PMN_TRY(alloc(g, shape->numel(), &conv->weight));
@@ -260,6 +273,13 @@ int generator_finalize(pmn_generator* g, int math, cudaStream_t stream) {
     return PMN_OK;
 }
 
+int generator_set_f8(pmn_generator* g, bool enabled) {
+    if (enabled && g->finalized && g->math != PMN_MATH_BF16X3_TC)
+        return fail(PMN_ERR_STATE, "generator: the fp8 form belongs to the tensor-core math mode");
+    g->f8 = enabled;
+    return PMN_OK;
+}
+
 int generator_set_pair_mask(pmn_generator* g, unsigned mask) {
     g->pair_mask = mask;
     return PMN_OK;
@@ -345,6 +365,7 @@ int generator_forward(
             // ... and writes the planes of lrelu(its output), the residual blocks' first operand
             PMN_TRY(launch_zero_plane_pads(w.a0, batch, up.c_out, t_len * kUpRate[s], stream));
             a.out_planes = w.a0; a.out_slope = kSlope;
+            a.out_f8 = g->f8 && tc_f8_plan(up.c_out, up.c_out, nullptr);
             PMN_TRY(launch_conv_transpose1d_tc(a, kUpRate[s], stream));
         } else {
             PMN_TRY(launch_conv_transpose1d(
@@ -358,6 +379,9 @@ int generator_forward(
             // launches over the fp32 stream (x0 -> cur -> xt -> mean); the others as six
             // launches with the activations travelling between them as bf16 hi/lo planes
             // of lrelu(.) next to the fp32 residual stream
+            // stage_f8: every plane of this stage is a "fp16 + 2 x fp8" operand (same bytes, same pad
+            // rows) and its convolutions take the fp8 slabs
+            const bool stage_f8 = g->f8 && tc_f8_plan(channels, channels, nullptr);
             bool fused[3], any_planes = false;
             for (int j = 0; j < 3; ++j) {
                 fused[j] = ((g->pair_mask >> (3 * s + j)) & 1u) != 0 &&
@@ -387,13 +411,20 @@ int generator_forward(
                     TcConvArgs a;
                     a.batch = batch; a.c_in = a.c_out = channels; a.t_len = t_len;
                     a.k = kResKernel[j]; a.out_slope = kSlope;
+                    const PackedConv& c1 = g->conv1[s][j][d];
+                    const PackedConv& c2 = g->conv2[s][j][d];
+                    a.f8x2 = a.out_f8 = stage_f8;
                     a.x_planes = d == 0 ? w.a0 : w.ac;
-                    a.w_slabs = g->conv1[s][j][d].slabs; a.bias = g->conv1[s][j][d].bias;
+                    a.w_slabs = stage_f8 ? static_cast<const __nv_bfloat16*>(c1.f8_slabs) : c1.slabs;
+                    a.f8_unscale = tc_f8_unscale(c1.f8_shift);
+                    a.bias = c1.bias;
                     a.dilation = kResDilation[d];
                     a.out_planes = w.at;
                     PMN_TRY(launch_conv1d_tc(a, stream));
                     a.x_planes = w.at;
-                    a.w_slabs = g->conv2[s][j][d].slabs; a.bias = g->conv2[s][j][d].bias;
+                    a.w_slabs = stage_f8 ? static_cast<const __nv_bfloat16*>(c2.f8_slabs) : c2.slabs;
+                    a.f8_unscale = tc_f8_unscale(c2.f8_shift);
+                    a.bias = c2.bias;
                     a.dilation = 1;
                     a.residual = d == 0 ? w.x0 : w.cur;
                     if (d < 2) {
@@ -410,6 +441,7 @@ int generator_forward(
                             // pair's first convolution)
                             a.out_planes = w.ac;
                             a.planes_from_accum = true;
+                            a.out_f8 = false;    // the transposed convolution takes bf16 hi / lo planes
                         }
                     }
                     PMN_TRY(launch_conv1d_tc(a, stream));

@@ -12,6 +12,7 @@ int generator_set_tensor(
     cudaStream_t stream);
 int generator_finalize(pmn_generator* g, int math, cudaStream_t stream);
 int generator_set_pair_mask(pmn_generator* g, unsigned mask);
+int generator_set_f8(pmn_generator* g, bool enabled);
 size_t generator_workspace_bytes(const pmn_generator* g, int batch, int frames);
 int generator_features(
     pmn_generator* g, const float* loudness, int rows, const float* pitch,

@@ -499,20 +499,10 @@ __global__ void __launch_bounds__(F8 ? 512 : 256) shared_norm_planes_kernel(
             const int row = j * step;
             if (F8) {
                 unsigned int half_words[8], z8[4], low8[4];
-                const __half2 scale_x = __float2half2_rn(kF8ScaleX);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-                    half_words[e] = *reinterpret_cast<const unsigned int*>(&h);
-                    const float2 back = __half22float2(h);
-                    // e4m3 of the fp16 value (not of x: the difference is 2^-11 of a term that is
-                    // itself 2^-11 of the product), straight from the packed halves
-                    const __half2 scaled = __hmul2(h, scale_x);
-                    const unsigned int z = __nv_cvt_halfraw2_to_fp8x2(
-                        *reinterpret_cast<const __half2_raw*>(&scaled), __NV_SATFINITE, __NV_E4M3);
-                    const unsigned int low = __nv_cvt_float2_to_fp8x2(
-                        make_float2((x[2 * e] - back.x) * kF8ScaleXLow, (x[2 * e + 1] - back.y) * kF8ScaleXLow),
-                        __NV_SATFINITE, __NV_E4M3);
+                    unsigned int z, low;
+                    tc::split_pair_f8(x[2 * e], x[2 * e + 1], half_words[e], z, low);
                     if (e % 2 == 0) { z8[e / 2] = z; low8[e / 2] = low; }
                     else { z8[e / 2] |= z << 16; low8[e / 2] |= low << 16; }
                 }
@@ -938,15 +928,8 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
                     // (3.7 -> 6.3), profiles/r2_preprocess_history.txt
                     const char* flag = getenv("PMN_PITCH_F8");
                     if (flag && flag[0] == '1') {
-                        std::vector<float> host(w->numel());
-                        PMN_TRY(check_cuda(cudaStreamSynchronize(stream), "sync"));
-                        PMN_TRY(check_cuda(
-                            cudaMemcpy(host.data(), w->data, host.size() * sizeof(float), cudaMemcpyDeviceToHost),
-                            "read block 1 weight"));
-                        float largest = 0.f;
-                        for (float value : host) largest = std::max(largest, fabsf(value));
-                        int shift = 0;
-                        while (shift < 16 && largest * (float)(2 << shift) <= 256.f) ++shift;
+                        int shift;
+                        PMN_TRY(tc_f8_weight_shift_of(w->data, w->numel(), stream, &shift));
                         float* f8_slabs;
                         PMN_TRY(alloc(p, folded_numel, &f8_slabs));
                         PMN_TRY(launch_pack_tc_weight_f8(
@@ -1260,7 +1243,7 @@ int pitch_forward(
                     if (shared0 && p->block1_shift >= 0) {
                         a.f8x2 = true;
                         a.w_slabs = static_cast<const __nv_bfloat16*>(p->block1_f8_slabs);
-                        a.correction_scale = tc_f8_correction_scale(p->block1_shift);
+                        a.f8_unscale = tc_f8_unscale(p->block1_shift);
                     }
                 } else {
                     a.c_in = kChannels[i]; a.k = kKernel; a.t_len = count * l_in;

@@ -4,6 +4,8 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace pmn {
@@ -141,6 +143,26 @@ __device__ __forceinline__ void split_pair(float y0, float y1, uint32_t& hi, uin
     const __nv_bfloat162 l = __floats2bfloat162_rn(
         y0 - __uint_as_float(hi << 16), y1 - __uint_as_float(hi & 0xffff0000u));
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// "fp16 + 2 x fp8" operand of two neighbouring channels (conv1d_tc.cuh): main = fp16x2 of
+// x kF8ScaleMain (saturating), coarse = e4m3x2 of x kF8ScaleX (in the low 16 bits), low = e4m3x2 of
+// (x - main / kF8ScaleMain) kF8ScaleXLow.  The coarse copy is taken from the fp16 value, not from x:
+// the difference is 2^-11 of a term that is itself 2^-11 of the product.
+constexpr float kF8Main = 128.f;        // = kF8ScaleMain
+constexpr float kF8Coarse = 8.f;        // = kF8ScaleX
+constexpr float kF8Low = 16384.f;       // = kF8ScaleXLow
+__device__ __forceinline__ void split_pair_f8(float y0, float y1, uint32_t& main, uint32_t& coarse, uint32_t& low) {
+    const float s0 = fminf(fmaxf(y0 * kF8Main, -65504.f), 65504.f);
+    const float s1 = fminf(fmaxf(y1 * kF8Main, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(s0, s1);
+    main = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 back = __half22float2(h);
+    const __half2 scaled = __hmul2(h, __float2half2_rn(kF8Coarse / kF8Main));
+    coarse = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&scaled), __NV_SATFINITE, __NV_E4M3);
+    low = __nv_cvt_float2_to_fp8x2(
+        make_float2((s0 - back.x) * (kF8Low / kF8Main), (s1 - back.y) * (kF8Low / kF8Main)),
+        __NV_SATFINITE, __NV_E4M3);
 }
 
 }  // namespace tc

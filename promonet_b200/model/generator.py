@@ -14,13 +14,19 @@ from promonet_b200 import _lib, config
 from promonet_b200.model import init
 
 
+# "fp16 + 2 x fp8" residual blocks at C >= 128 (pmn_generator_set_f8) unless asked otherwise
+F8_DEFAULT = False
+
+
 class Generator:
 
-    def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None, pair_mask=None):
+    def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None, pair_mask=None, f8=None):
         """pair_mask: which residual blocks run as fused pair kernels
         (pmn_generator_set_pair_mask); None = the library default, or the
         PMN_PAIR_MASK environment variable (an experiment knob: the output bits
-        do not depend on it)"""
+        do not depend on it).
+        f8: residual blocks of the C = 256 / 128 stages with "fp16 + 2 x fp8" operands
+        (pmn_generator_set_f8); None = the PMN_GENERATOR_F8 environment variable, else F8_DEFAULT"""
         if not torch.cuda.is_available():
             raise RuntimeError(
                 'promonet_b200.model.Generator needs a CUDA device (sm_100a); '
@@ -31,6 +37,9 @@ class Generator:
         if pair_mask is None and os.environ.get('PMN_PAIR_MASK'):
             pair_mask = int(os.environ['PMN_PAIR_MASK'], 0)
         self.pair_mask = pair_mask
+        if f8 is None:
+            f8 = os.environ.get('PMN_GENERATOR_F8', '1' if F8_DEFAULT else '0') == '1'
+        self.f8 = bool(f8) and math == _lib.MATH_BF16X3_TC
         self.handle = None
         self.default_previous_samples = torch.zeros(1, 1, 1, device=self.device)
         self._workspace = None
@@ -78,6 +87,8 @@ class Generator:
             _lib.check(lib.pmn_generator_finalize(handle, self.math, stream))
             if self.pair_mask is not None:
                 _lib.check(lib.pmn_generator_set_pair_mask(handle, self.pair_mask))
+            if self.f8:
+                _lib.check(lib.pmn_generator_set_f8(handle, 1))
             torch.cuda.current_stream().synchronize()
         self._state = {k: v.detach().cpu() for k, v in state.items()}
         return self

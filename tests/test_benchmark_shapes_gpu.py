@@ -39,6 +39,28 @@ def test_hifigan_batch_32_by_430_frames():
     assert torch.equal(host, audio.cpu())
 
 
+@pytest.mark.parametrize('seed', [1234, 7, 99])
+def test_hifigan_with_fp8_corrections_batch_32_by_430_frames(seed):
+    """The same shape with the residual blocks of the C = 256 / 128 stages on "fp16 + 2 x fp8"
+    operands (Generator(f8=True), pmn_generator_set_f8): three seeds for weights and inputs, two
+    utterances each against the oracle; the same 1e-4 bar"""
+    import promonet_b200
+    state = promonet_b200.model.init.hifigan_state(seed)
+    model = promonet_b200.model.Generator(state=state, f8=True)
+    args = inputs.synthesis(32, 430, seed=seed)
+    audio = model(*[a.cuda() for a in args])
+    again = model(*[a.cuda() for a in args])
+    assert torch.equal(audio, again)
+    assert bool(torch.isfinite(audio).all())
+    errors = []
+    for index in (3, 31):
+        with torch.no_grad():
+            expected = hifigan.generator(state, *[a[index:index + 1] for a in args])
+        errors.append(relative_error(audio[index:index + 1], expected))
+    print(f'fp8-corrected generator, seed {seed}: relative errors {errors}')
+    assert max(errors) < TOLERANCE, errors
+
+
 def test_preprocess_batch_32_by_10_seconds():
     """configs[2]: 32 utterances x 220 500 samples -> 861 frames each"""
     import promonet_b200

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def conv1d_tc(x, w, bias=None, residual=None, dilation=1, in_slope=1., out_slope=1.,
-              want_planes=False, accum=None, accum_mode=0, accum_scale=1., want_out=True):
+              want_planes=False, accum=None, accum_mode=0, accum_scale=1., want_out=True, f8=False):
     from promonet_b200 import _lib
     lib = _lib.library()
     batch, channels, t_len = x.shape
@@ -20,7 +20,8 @@ def conv1d_tc(x, w, bias=None, residual=None, dilation=1, in_slope=1., out_slope
     planes = torch.empty_like(xd) if want_planes else None
     size = lib.pmn_conv1d_tc_workspace_bytes(batch, channels, t_len, k)
     workspace = torch.empty(size, dtype=torch.uint8, device='cuda')
-    _lib.check(lib.pmn_conv1d_tc(
+    entry = lib.pmn_conv1d_tc_f8 if f8 else lib.pmn_conv1d_tc
+    _lib.check(entry(
         xd.data_ptr(), wd.data_ptr(), *[_lib.ptr(t) for t in keep], _lib.ptr(out),
         _lib.ptr(planes), _lib.ptr(accum), accum_mode, accum_scale,
         batch, channels, t_len, k, dilation, in_slope, out_slope,
@@ -54,6 +55,55 @@ def test_conv1d_tc_matches_fp64(channels, k, dilation, t_len, batch):
     out, _ = conv1d_tc(x, w, bias, dilation=dilation, in_slope=0.1)
     error = relative_error(out, expected)
     assert error < 1e-4, error
+
+
+@pytest.mark.parametrize('channels,k,dilation,t_len,batch', [
+    (128, 11, 1, 300, 2), (128, 11, 5, 1111, 1), (128, 7, 3, 256, 1), (128, 3, 1, 700, 2),
+    (256, 3, 5, 129, 2), (256, 11, 3, 1000, 1), (256, 7, 1, 128, 1), (256, 11, 5, 256 * 150 + 3, 1)])
+@pytest.mark.parametrize('weight_scale', [1., 1e-2])
+def test_conv1d_tc_f8_matches_fp64(channels, k, dilation, t_len, batch, weight_scale):
+    """"fp16 + 2 x fp8" operands (pmn_conv1d_tc_f8): x w = fp16 x fp16 + two e4m3 correction products
+    in one accumulator.  Same 1e-4 bar; measured 1-2e-5 on one layer (bf16 x 3: ~5e-6).  The weight
+    scale exercises the power-of-two weight shift"""
+    torch.manual_seed(channels + k + dilation)
+    x = torch.randn(batch, channels, t_len)
+    w = weight_scale * torch.randn(channels, channels, k) / (channels * k) ** .5
+    bias = weight_scale * torch.randn(channels)
+    expected = reference(x, w, bias, dilation, 0.1)
+    out, _ = conv1d_tc(x, w, bias, dilation=dilation, in_slope=0.1, f8=True)
+    error = relative_error(out, expected)
+    assert error < 5e-5, error
+
+
+@pytest.mark.parametrize('channels', [128, 256])
+def test_conv1d_tc_f8_epilogue(channels):
+    """Residual, MRF accumulate and the "fp16 + 2 x fp8" operand written by the epilogue"""
+    torch.manual_seed(3)
+    x = torch.randn(2, channels, 600)
+    w = torch.randn(channels, channels, 7) / (channels * 7) ** .5
+    bias, residual = torch.randn(channels), torch.randn(2, channels, 600)
+    y = reference(x, w, bias, 3, 0.1) + residual.double()
+    accum = torch.ones(2, channels, 600, device='cuda')
+    out, planes = conv1d_tc(
+        x, w, bias, residual, dilation=3, in_slope=0.1, out_slope=0.1, want_planes=True,
+        accum=accum, accum_mode=2, accum_scale=1 / 3, f8=True)
+    assert relative_error(out, y) < 5e-5
+    assert relative_error(accum, 1 + y / 3) < 5e-5
+    # fp16 part + e4m3 low part: 11 + 3 mantissa bits of lrelu(y) per element
+    expected = torch.nn.functional.leaky_relu(out.double().cpu(), 0.1)
+    worst = ((planes.double().cpu() - expected).abs() / expected.abs().clamp(min=1e-2)).max()
+    assert float(worst) < 2 ** -13, float(worst)
+
+
+def test_conv1d_tc_f8_saturates_instead_of_overflowing():
+    """|x| beyond the e4m3 / fp16 ranges of the operand must stay finite (saturating converts)"""
+    torch.manual_seed(4)
+    x = torch.randn(1, 128, 300)
+    x[0, 5, 100] = 3000.
+    x[0, 9, 7] = -100.
+    w = torch.randn(128, 128, 3) / (128 * 3) ** .5
+    out, _ = conv1d_tc(x, w, dilation=1, f8=True)
+    assert bool(torch.isfinite(out).all())
 
 
 def test_conv1d_tc_many_tiles_per_cta():
