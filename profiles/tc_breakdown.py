@@ -1,7 +1,7 @@
 """Where the tensor-core conv spends its time: CUDA-event time per launch and the
 in-kernel cycle counters of each warp role (producer / MMA issuer / epilogue).
 
-    python profiles/tc_breakdown.py [channels]
+    python profiles/tc_breakdown.py [channels] [f8]
 """
 import sys
 from pathlib import Path
@@ -19,12 +19,13 @@ def main():
     shapes = ((256, 3440), (128, 27520), (64, 55040), (32, 110080))
     if len(sys.argv) > 1:
         shapes = [s for s in shapes if s[0] == int(sys.argv[1])]
+    f8 = len(sys.argv) > 2 and sys.argv[2] == 'f8'
     for channels, t_len in shapes:
-        for kernel in (3, 11):
+        for kernel in (3, 7, 11) if f8 else (3, 11):
             for mode in ('c1', 'c2', 'c2acc'):
                 counters.zero_()
                 lib.pmn_debug_tc_counters(counters.data_ptr())
-                ms = run_tc_conv(32, channels, t_len, kernel, mode, repeats=3)
+                ms = run_tc_conv(32, channels, t_len, kernel, mode, repeats=3, f8=f8)
                 lib.pmn_debug_tc_counters(None)
                 c = counters.double().cpu()
                 prod, mma, epi = c[:, 0], c[:, 1], c[:, 2:].mean(1)

@@ -21,8 +21,9 @@
 //   warp 0    producer: bulk copies of activation slabs (per 64-channel block)
 //             and weight slabs (per tap x block) into shared-memory rings
 //   warp 1    MMA issuer: one thread issues tcgen05.mma, commits to mbarriers
-//   warps 2-5 epilogue: tcgen05.ld accumulators, bias + residual + LeakyReLU,
-//             fp32 and/or hi/lo-plane stores, MRF accumulate (hifigan.py:141-145)
+//   warps 4-11 epilogue (two warpgroups, registers raised with setmaxnreg): tcgen05.ld
+//             accumulators, bias + residual + LeakyReLU, fp32 and/or operand-plane stores,
+//             MRF accumulate (hifigan.py:141-145); warps 2-3 idle (they complete the first warpgroup)
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps
 // the MMAs of tile i + 1.
 #include <cuda_fp16.h>
@@ -40,7 +41,12 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 320;  // producer, MMA issuer, 8 epilogue warps
+// Three warpgroups: {producer, MMA issuer, two idle warps} and two of epilogue warps.  The launch
+// bound of 384 threads caps every thread at 168 registers, which the fully unrolled epilogue
+// overflows; the first warpgroup hands registers back (setmaxnreg.dec) and the epilogue warps take
+// them (setmaxnreg.inc): 128 x 56 + 256 x 224 = 384 x 168.
+constexpr int kThreads = 384;
+constexpr int kEpilogueWarp0 = 4;
 constexpr int kMaxHalo = 25;  // (11 - 1) / 2 * 5
 
 // ---------------------------------------------------------------------------
@@ -138,6 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < kEpilogueWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ===== producer =====
         if (lane == 0) {
@@ -301,12 +309,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 d[0] = clock64() - begin; d[1] = wait_x; d[2] = wait_w; d[3] = wait_acc;
             }
         }
+    }
     } else {
-        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        // ===== epilogue: warps 4..11; warp w owns TMEM lanes 32 * (w % 4) .. + 31 and
         // every other 16-column chunk of the tile =====
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - kEpilogueWarp0) >> 2;
         constexpr int kW = 16;                    // columns per chunk
+        // Rarely used epilogue options are compiled only into the variants that take them: the loop
+        // over a tile's chunks is fully unrolled and every extra branch in it costs registers and
+        // scheduling freedom in all of them (C = 128 / 32, k = 3 ran 20 - 45 % slower with these as
+        // run-time flags, profiles/r2_tc_epilogue_regression.txt)
+        constexpr bool kBiasBatch = MODE == kConv && C_IN == 128 && N == 256;   // HiFi-GAN's input conv
+        constexpr bool kOutF8 = MODE == kConv ? F8 : UP == 8;   // "fp16 + 2 x fp8" operand for the next layer
         constexpr int kPerSub = N / kW;
         constexpr int kChunks = S * kPerSub;      // (subtile, 16-channel) chunks per tile
         static_assert(kChunks % 2 == 0, "chunks are split between two warp sets");
@@ -394,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             }
                         }
                     }
-                    if (a.out_planes && a.out_f8 && i >= 0) {
+                    if (kOutF8 && a.out_planes && a.out_f8 && i >= 0) {
                         // the run's 8 channels: one fp16 row and half a row of each e4m3 section per sample
                         const size_t item = (size_t)b * (groups_out * 2);
                         const int half_row = (o_run / 8) & 1;
@@ -478,7 +494,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll
                 for (int i = 0; i < kW; ++i) {
                     float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
-                    if (a.bias_batch) y += a.bias_batch[(size_t)b * a.c_out + c_first + i];
+                    if constexpr (kBiasBatch) {
+                        if (a.bias_batch) y += a.bias_batch[(size_t)b * a.c_out + c_first + i];
+                    }
                     if (a.relu) y = fmaxf(y, 0.f);
                     v[i] = y;
                 }
@@ -504,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }
                     }
-                    if (a.out_planes && a.out_f8) {
+                    if (kOutF8 && a.out_planes && a.out_f8) {
                         // [C / 8 fp16 rows | C / 16 coarse rows | C / 16 low rows] per item
                         const int out_pad = tc_padded_length_device(t_out);
                         uint32_t main[8], coarse[4], low[4];
@@ -547,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             if (lane == 0) mbar_arrive(acc_empty + as);
         }
         if (a.debug && lane == 0) {
-            long long* d = a.debug + ((size_t)blockIdx.x * 10 + warp) * 4;
+            long long* d = a.debug + ((size_t)blockIdx.x * 10 + warp - 2) * 4;
             d[0] = clock64() - start_cycles;
             d[1] = wait_cycles;
         }
@@ -789,6 +807,10 @@ int launch_variant(const TcConvArgs& a, int n_tiles, cudaStream_t stream) {
     const int grid = min(num_tiles, sm_count());
     TcConvArgs args = a;
     if (!args.debug) args.debug = g_tc_debug;
+    PMN_REQUIRE(!a.bias_batch || (MODE == kConv && C_IN == 128 && N == 256),
+                "conv1d_tc: a per-item bias is compiled into the 128 -> 512 variant only");
+    PMN_REQUIRE(!(a.out_planes && a.out_f8) || (MODE == kConv ? F8 : UP == 8),
+                "conv1d_tc: this variant does not write the fp8 operand form");
     const char* name = MODE == kTranspose ? "conv_transpose1d_tc_kernel" : "conv1d_tc_kernel";
     LaunchScope scope(name, stream);
     kernel<<<grid, kThreads, Cfg::kSmem, stream>>>(

@@ -4,12 +4,12 @@ import torch
 from promonet_b200 import _lib
 
 
-def run_tc_conv(batch, channels, t_len, kernel, mode='c2', dilation=1, repeats=1):
+def run_tc_conv(batch, channels, t_len, kernel, mode='c2', dilation=1, repeats=1, f8=False):
     """Best CUDA-event ms of the conv kernel alone over `repeats` launches of
     pmn_conv1d_tc (timed through pmn_profile_*)
 
     mode: 'c1' planes out only; 'c2' residual + fp32 out + planes; 'c2acc'
-    residual + MRF accumulate (the three epilogues of Block.forward)"""
+    residual + MRF accumulate (the three epilogues of Block.forward); f8: pmn_conv1d_tc_f8"""
     lib = _lib.library()
     x = torch.randn(batch, channels, t_len, device='cuda')
     w = torch.randn(channels, channels, kernel, device='cuda') / (channels * kernel) ** .5
@@ -23,7 +23,7 @@ def run_tc_conv(batch, channels, t_len, kernel, mode='c2', dilation=1, repeats=1
     best = float('inf')
     for _ in range(repeats):
         _lib.profile(True)
-        _lib.check(lib.pmn_conv1d_tc(
+        _lib.check((lib.pmn_conv1d_tc_f8 if f8 else lib.pmn_conv1d_tc)(
             x.data_ptr(), w.data_ptr(), bias.data_ptr(), _lib.ptr(residual), _lib.ptr(out),
             _lib.ptr(planes), _lib.ptr(accum), 2 if accum is not None else 0, 1 / 3,
             batch, channels, t_len, kernel, dilation, 0.1, 0.1,
