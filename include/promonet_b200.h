@@ -76,10 +76,10 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream);
  * for every mask. */
 int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask);
 
-/* Tensor-core math only: run the residual blocks of the C = 256 and C = 128 stages (62 % of the
- * generator's FLOPs) with "fp16 + 2 x fp8" operands (pmn_conv1d_tc_f8): two thirds of the tensor
- * cycles of the bf16 x 3 form, output within the same 1e-4 bar but closer to it (measured at
- * B = 32 x 430 frames: DESIGN.md section 8).  Call after pmn_generator_finalize. */
+/* Tensor-core math only: run the unfused residual blocks of the C = 128 stage (a third of the
+ * generator's FLOPs) with "fp16 + 2 x fp8" operands (pmn_conv1d_tc_f8) instead of bf16 x 3: fewer
+ * tensor cycles, output within the same 1e-4 bar (measured 0.8 - 1.6e-5 at B = 32 x 430 frames
+ * against 0.8e-5).  Call after pmn_generator_finalize. */
 int pmn_generator_set_f8(pmn_generator* g, int enabled);
 
 size_t pmn_generator_workspace_bytes(const pmn_generator* g, int batch, int frames);

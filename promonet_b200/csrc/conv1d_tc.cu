@@ -475,6 +475,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             };
 #pragma unroll
             for (int d = 0; d < kDepth; ++d) fetch(a.residual, half + 2 * d, res[d]);
+            // the MRF partial sum this launch adds to (accum_mode 2), one chunk ahead as well
+            const float* accum_in = a.accum_mode == 2 ? a.accum : nullptr;
+            float acc[2][kW];
+            fetch(accum_in, half, acc[0]);
             const long long wait_start = a.debug ? clock64() : 0;
             mbar_wait(acc_full + as, aphase);
             if (a.debug) wait_cycles += clock64() - wait_start;
@@ -484,8 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 const int chunk = half + 2 * mine;
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = row_of(s);
-                float acc[kW];
-                fetch(a.accum_mode == 2 ? a.accum : nullptr, chunk, acc);
+                if (mine + 1 < kMine) fetch(accum_in, chunk + 2, acc[(mine + 1) & 1]);
                 uint32_t raw[kW];
                 load(s, c0, raw);
                 float (&r)[kW] = res[mine % kDepth];
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     if (a.accum_mode) {
 #pragma unroll
                         for (int i = 0; i < kW; ++i) {
-                            const float total = fmaf(v[i], a.accum_scale, acc[i]);
+                            const float total = fmaf(v[i], a.accum_scale, acc[mine & 1][i]);
                             a.accum[idx + (size_t)i * out_row] = total;
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }

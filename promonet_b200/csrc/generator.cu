@@ -60,8 +60,7 @@ struct pmn_generator {
     // bit (3 * stage + block): run that residual block's three c1 -> c2 pairs as fused
     // conv_pair_tc_kernel launches (tensor-core math, C <= 128) instead of six conv1d_tc ones
     unsigned pair_mask = pmn::kDefaultPairMask;
-    // residual blocks of the C = 256 / 128 stages with "fp16 + 2 x fp8" operands (two thirds of the
-    // tensor cycles of bf16 x 3; pmn_generator_set_f8)
+    // residual blocks of the C = 128 stage with "fp16 + 2 x fp8" operands (pmn_generator_set_f8)
     bool f8 = false;
 
     pmn::PackedConv up[pmn::kStages];
@@ -76,6 +75,12 @@ namespace pmn {
 namespace {
 
 int alloc(pmn_generator* g, size_t count, float** out) { return g->store.alloc(count, out); }
+
+// The stage whose residual blocks take "fp16 + 2 x fp8" operands when the generator's f8 switch is
+// on: C = 128 (k = 7 / 11 launches 8 - 13 % faster than bf16 x 3).  C = 256 is built and tested
+// (pmn_conv1d_tc_f8) but slower in that form -- its 128-column tiles lose more than the cheaper
+// corrections win (k = 11: 0.36 against 0.30 ms, profiles/r2_f8_breakdown.txt)
+bool f8_stage(int channels) { return channels == 128; }
 
 int find(const pmn_generator* g, const std::string& name, const Tensor** out) {
     return g->store.find(name, out);
@@ -120,7 +125,7 @@ int prepare_conv(pmn_generator* g, const std::string& prefix, int channels, int 
         float* slabs;  // two bf16 planes = the bytes of one fp32 tensor (+ the narrow layers' second format)
         PMN_TRY(alloc(g, (tc_weight_elements(channels, channels, k) + 1) / 2, &slabs));
         conv->slabs = reinterpret_cast<__nv_bfloat16*>(slabs);
-        if (tc_f8_plan(channels, channels, nullptr)) {
+        if (f8_stage(channels)) {
             float* f8_slabs;
             PMN_TRY(alloc(g, shape->numel(), &f8_slabs));
             PMN_TRY(tc_f8_weight_shift_of(w, shape->numel(), stream, &conv->f8_shift));
@@ -365,7 +370,7 @@ int generator_forward(
             // ... and writes the planes of lrelu(its output), the residual blocks' first operand
             PMN_TRY(launch_zero_plane_pads(w.a0, batch, up.c_out, t_len * kUpRate[s], stream));
             a.out_planes = w.a0; a.out_slope = kSlope;
-            a.out_f8 = g->f8 && tc_f8_plan(up.c_out, up.c_out, nullptr);
+            a.out_f8 = g->f8 && f8_stage(up.c_out);
             PMN_TRY(launch_conv_transpose1d_tc(a, kUpRate[s], stream));
         } else {
             PMN_TRY(launch_conv_transpose1d(
@@ -381,7 +386,7 @@ int generator_forward(
             // of lrelu(.) next to the fp32 residual stream
             // stage_f8: every plane of this stage is a "fp16 + 2 x fp8" operand (same bytes, same pad
             // rows) and its convolutions take the fp8 slabs
-            const bool stage_f8 = g->f8 && tc_f8_plan(channels, channels, nullptr);
+            const bool stage_f8 = g->f8 && f8_stage(channels);
             bool fused[3], any_planes = false;
             for (int j = 0; j < 3; ++j) {
                 fused[j] = ((g->pair_mask >> (3 * s + j)) & 1u) != 0 &&

@@ -14,8 +14,8 @@ from promonet_b200 import _lib, config
 from promonet_b200.model import init
 
 
-# "fp16 + 2 x fp8" residual blocks at C >= 128 (pmn_generator_set_f8) unless asked otherwise
-F8_DEFAULT = False
+# "fp16 + 2 x fp8" residual blocks at C = 128 (pmn_generator_set_f8) unless asked otherwise
+F8_DEFAULT = True
 
 
 class Generator:
@@ -25,7 +25,7 @@ class Generator:
         (pmn_generator_set_pair_mask); None = the library default, or the
         PMN_PAIR_MASK environment variable (an experiment knob: the output bits
         do not depend on it).
-        f8: residual blocks of the C = 256 / 128 stages with "fp16 + 2 x fp8" operands
+        f8: residual blocks of the C = 128 stage with "fp16 + 2 x fp8" operands
         (pmn_generator_set_f8); None = the PMN_GENERATOR_F8 environment variable, else F8_DEFAULT"""
         if not torch.cuda.is_available():
             raise RuntimeError(
