@@ -331,24 +331,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
         const int t_out = a.valid ? a.t_len - span : a.t_len;   // output rows per item
         const int out_row = a.out_row > 0 ? a.out_row : t_out;  // fp32 row length
         long long wait_cycles = 0, start_cycles = a.debug ? clock64() : 0;
+        // residual chunks in flight (kConv / kFrames epilogue): they outlive a tile
+        float res[(S * (N / kW) / 2) < 4 ? (S * (N / kW) / 2) : 4][kW];
+        // this thread's output row of subtile s of the tile at position of_tb of its item, or -1
+        auto row_at = [&](int of_tb, int s) {
+            const int within = quad * 32 + lane;
+            if constexpr (MODE == kFrames) {
+                const int frame = of_tb * kFramesPerTile + within / kFrameRows, t = within % kFrameRows;
+                return (frame < a.frames && t < a.frame_valid) ? frame * a.frame_length + t : -1;
+            } else {
+                const int t = of_tb * advance + s * 128 + within;
+                return t < t_out ? t : -1;
+            }
+        };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int nt = tile % n_tiles, rest = tile / n_tiles;
             const int b = rest / tiles_per_item;
             const int tb = rest % tiles_per_item;
-            const int t0 = tb * advance;
             const uint32_t as = tcount % AS, aphase = (tcount / AS) & 1;
             ++tcount;
-            // this thread's output row of subtile s, or -1
-            auto row_of = [&](int s) {
-                const int within = quad * 32 + lane;
-                if constexpr (MODE == kFrames) {
-                    const int frame = tb * kFramesPerTile + within / kFrameRows, t = within % kFrameRows;
-                    return (frame < a.frames && t < a.frame_valid) ? frame * a.frame_length + t : -1;
-                } else {
-                    const int t = t0 + s * 128 + within;
-                    return t < t_out ? t : -1;
-                }
-            };
+            auto row_of = [&](int s) { return row_at(tb, s); };
             auto load = [&](int s, int c0, uint32_t (&raw)[kW]) {
                 const uint32_t address =
                     tmem_base + ((uint32_t)(quad * 32) << 16) + as * Cfg::kStageCols + s * Cfg::kCols + c0;
@@ -458,40 +460,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 if (lane == 0) mbar_arrive(acc_empty + as);
                 continue;
             }
-            // Side inputs do not depend on the accumulators: fetch the first chunk's
-            // before waiting, and chunk i + 1's while chunk i is processed, so the
-            // DRAM latency is paid once per chunk batch instead of once per element
+            // Side inputs do not depend on the accumulators.  The residual of kDepth chunks is always
+            // in flight, across tile boundaries too (the first chunks of the next tile are requested
+            // while the last ones of this tile are processed), so its DRAM latency is paid once per
+            // launch; the MRF partial sum is fetched one chunk ahead.  The chunk loop is unrolled in
+            // groups of kDepth: fully unrolled, the larger variants' epilogue (160 KB of SASS)
+            // stalled on instruction fetch for a quarter of its cycles (ncu, profiles/r2_tc_epilogue_regression.txt)
             constexpr int kMine = kChunks / 2;                 // chunks of this warp set per tile
             constexpr int kDepth = kMine < 4 ? kMine : 4;      // residual chunks in flight
-            float res[kDepth][kW];
-            auto fetch = [&](const float* source, int chunk, float (&r)[kW]) {
+            constexpr int kGroup = kMine % kDepth == 0 ? kDepth : kMine;   // chunks per unrolled group
+            static_assert(kGroup % 2 == 0 || kGroup == kMine, "the accumulate buffers alternate");
+            // chunk c of every tile uses buffer c % kDepth: the pipeline runs across tiles when that
+            // agrees with the rotation, i.e. when kDepth divides kMine (all but the 160-column head)
+            constexpr bool kAcross = kMine % kDepth == 0;
+            auto fetch = [&](const float* source, int of_tile, int chunk, float (&r)[kW]) {
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
-                const int t = row_of(s);
-                const bool valid = source != nullptr && t >= 0;
-                const size_t idx = ((size_t)b * a.c_out + nt * N + c0) * out_row + t;
+                const int of_nt = of_tile % n_tiles, of_rest = of_tile / n_tiles;
+                const int of_b = of_rest / tiles_per_item, of_tb = of_rest % tiles_per_item;
+                const int t = row_at(of_tb, s);
+                const bool valid = source != nullptr && t >= 0 && of_tile < num_tiles;
+                const size_t idx = ((size_t)of_b * a.c_out + of_nt * N + c0) * out_row + t;
 #pragma unroll
                 for (int i = 0; i < kW; ++i)
                     r[i] = valid ? source[idx + (size_t)i * out_row] : 0.f;
             };
+            if (!kAcross || tile == (int)blockIdx.x) {
 #pragma unroll
-            for (int d = 0; d < kDepth; ++d) fetch(a.residual, half + 2 * d, res[d]);
-            // the MRF partial sum this launch adds to (accum_mode 2), one chunk ahead as well
+                for (int d = 0; d < kDepth; ++d) fetch(a.residual, tile, half + 2 * d, res[d]);
+            }
+            // the MRF partial sum this launch adds to (accum_mode 2)
             const float* accum_in = a.accum_mode == 2 ? a.accum : nullptr;
             float acc[2][kW];
-            fetch(accum_in, half, acc[0]);
+            fetch(accum_in, tile, half, acc[0]);
             const long long wait_start = a.debug ? clock64() : 0;
             mbar_wait(acc_full + as, aphase);
             if (a.debug) wait_cycles += clock64() - wait_start;
             tc_fence_after();
+#pragma unroll 1
+            for (int group = 0; group < kMine / kGroup; ++group) {
 #pragma unroll
-            for (int mine = 0; mine < kMine; ++mine) {
+            for (int g_index = 0; g_index < kGroup; ++g_index) {
+                const int mine = group * kGroup + g_index;
+                const int d = g_index % kDepth;     // static: the residual buffer of this chunk
                 const int chunk = half + 2 * mine;
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = row_of(s);
-                if (mine + 1 < kMine) fetch(accum_in, chunk + 2, acc[(mine + 1) & 1]);
+                if (mine + 1 < kMine) fetch(accum_in, tile, chunk + 2, acc[(d + 1) & 1]);
                 uint32_t raw[kW];
                 load(s, c0, raw);
-                float (&r)[kW] = res[mine % kDepth];
+                float (&r)[kW] = res[d];
                 float v[kW];
                 const int c_first = nt * N + c0;
 #pragma unroll
@@ -520,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     if (a.accum_mode) {
 #pragma unroll
                         for (int i = 0; i < kW; ++i) {
-                            const float total = fmaf(v[i], a.accum_scale, acc[mine & 1][i]);
+                            const float total = fmaf(v[i], a.accum_scale, acc[d & 1][i]);
                             a.accum[idx + (size_t)i * out_row] = total;
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }
@@ -561,7 +578,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                         }
                     }
                 }
-                if (mine + kDepth < kMine) fetch(a.residual, half + 2 * (mine + kDepth), r);
+                // the buffer is free: request the chunk kDepth further on, in this tile or the next
+                {
+                    const int ahead = mine + kDepth;
+                    const bool same = ahead < kMine;
+                    if (same || kAcross)
+                        fetch(a.residual, same ? tile : tile + (int)gridDim.x,
+                              half + 2 * (same ? ahead : ahead - kMine), r);
+                }
+            }
             }
             tc_fence_before();
             __syncwarp();
