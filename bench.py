@@ -408,7 +408,10 @@ def synthesis(ctx):
         'n_gpus': ctx.world, 'steps': args.steps, 'warmup': warmup,
         'ms_per_step': ms / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if math == _lib.MATH_FP32_SIMT else 'f32 (bf16x3 tensor-core products, fp32 accumulate)',
+        'dtype': 'f32' if math == _lib.MATH_FP32_SIMT else (
+            'f32 (bf16x3 tensor-core products; fp16 + 2 x e4m3 correction products in the C = 128 '
+            'residual blocks; fp32 accumulate)' if model.f8 else
+            'f32 (bf16x3 tensor-core products, fp32 accumulate)'),
         'data': 'synthetic',
         'config': workload_config(ctx.world),
         'clocks': clocks.summary(),

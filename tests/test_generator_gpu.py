@@ -27,12 +27,13 @@ def state():
     return init.hifigan_state(1234)
 
 
-@pytest.fixture(scope='module', params=['fp32', 'bf16x3'])
+@pytest.fixture(scope='module', params=['fp32', 'bf16x3', 'bf16x3+f8'])
 def model(state, request, lib):
-    """Both math modes must meet the same parity bar"""
+    """Every math mode must meet the same parity bar: fp32 FMAs, bf16 x 3 on the tensor cores, and
+    the latter with the C = 128 residual blocks on fp16 + 2 x fp8 operands (the default)"""
     import promonet_b200
     math = lib.MATH_FP32_SIMT if request.param == 'fp32' else lib.MATH_BF16X3_TC
-    return promonet_b200.model.Generator(state=state, math=math)
+    return promonet_b200.model.Generator(state=state, math=math, f8=request.param.endswith('+f8'))
 
 
 def conv1d(lib, x, weight, bias=None, bias2=None, residual=None, dilation=1,
