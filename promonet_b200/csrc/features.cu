@@ -299,7 +299,9 @@ int launch_speaker_bias(
     PMN_REQUIRE(speaker_embedding && speakers && sbr && lr && weight && out,
                 "speaker_bias: null pointer");
     LaunchScope scope("speaker_bias_kernel", stream);
-    speaker_bias_kernel<<<batch, 256, (speaker_channels + 2) * sizeof(float), stream>>>(
+    // the compiler reads g[] in 16-byte pieces, the last one past c_g floats: size the buffer for it
+    const size_t smem = (size_t)(speaker_channels + 2 + 3) / 4 * 4 * sizeof(float);
+    speaker_bias_kernel<<<batch, 256, smem, stream>>>(
         speaker_embedding, speakers, sbr, lr, weight, bias, out,
         speaker_channels, c_out, num_speakers);
     return launched("speaker_bias_kernel");
