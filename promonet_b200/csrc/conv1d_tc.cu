@@ -41,6 +41,9 @@ namespace {
 
 using namespace tc;
 
+// LeakyReLU for slopes in [0, 1] (1 = identity) as a multiply and a maximum
+__device__ __forceinline__ float leaky01(float x, float slope) { return fmaxf(x, x * slope); }
+
 // Three warpgroups: {producer, MMA issuer, two idle warps} and two of epilogue warps.  The launch
 // bound of 384 threads caps every thread at 168 registers, which the fully unrolled epilogue
 // overflows; the first warpgroup hands registers back (setmaxnreg.dec) and the epilogue warps take
@@ -330,6 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
         const int groups_out = a.c_out / 8;
         const int t_out = a.valid ? a.t_len - span : a.t_len;   // output rows per item
         const int out_row = a.out_row > 0 ? a.out_row : t_out;  // fp32 row length
+        const size_t item_elements = (size_t)a.c_out * out_row;    // < 2^31 (launcher)
+        const float relu_floor = a.relu ? 0.f : -INFINITY;
         long long wait_cycles = 0, start_cycles = a.debug ? clock64() : 0;
         // residual chunks in flight (kConv / kFrames epilogue): they outlive a tile
         float res[(S * (N / kW) / 2) < 4 ? (S * (N / kW) / 2) : 4][kW];
@@ -422,8 +427,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 uint32_t z, l;
-                                split_pair_f8(leaky(values[(2 * e) * UP + q], a.out_slope),
-                                              leaky(values[(2 * e + 1) * UP + q], a.out_slope), main[e], z, l);
+                                split_pair_f8(leaky01(values[(2 * e) * UP + q], a.out_slope),
+                                              leaky01(values[(2 * e + 1) * UP + q], a.out_slope), main[e], z, l);
                                 if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
                                 else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
                             }
@@ -445,8 +450,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                split_pair(leaky(values[(2 * e) * UP + q], a.out_slope),
-                                           leaky(values[(2 * e + 1) * UP + q], a.out_slope), hi[e], lo[e]);
+                                split_pair(leaky01(values[(2 * e) * UP + q], a.out_slope),
+                                           leaky01(values[(2 * e + 1) * UP + q], a.out_slope), hi[e], lo[e]);
                             const size_t row_hi =
                                 ((size_t)(b * 2) * groups_out + o_run / 8) * out_pad + kTcPad + (size_t)UP * i + q;
                             const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
@@ -478,11 +483,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 const int of_nt = of_tile % n_tiles, of_rest = of_tile / n_tiles;
                 const int of_b = of_rest / tiles_per_item, of_tb = of_rest % tiles_per_item;
                 const int t = row_at(of_tb, s);
-                const bool valid = source != nullptr && t >= 0 && of_tile < num_tiles;
-                const size_t idx = ((size_t)of_b * a.c_out + of_nt * N + c0) * out_row + t;
+                // one 64-bit base per chunk, 32-bit element offsets within the item (the integer
+                // address arithmetic was half of the epilogue's instructions)
+                if (source != nullptr && t >= 0 && of_tile < num_tiles) {
+                    const float* from = source + (size_t)of_b * item_elements +
+                                        ((uint32_t)(of_nt * N + c0) * (uint32_t)out_row + (uint32_t)t);
 #pragma unroll
-                for (int i = 0; i < kW; ++i)
-                    r[i] = valid ? source[idx + (size_t)i * out_row] : 0.f;
+                    for (int i = 0; i < kW; ++i, from += out_row) r[i] = *from;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kW; ++i) r[i] = 0.f;
+                }
             };
             if (!kAcross || tile == (int)blockIdx.x) {
 #pragma unroll
@@ -511,14 +522,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                 float (&r)[kW] = res[d];
                 float v[kW];
                 const int c_first = nt * N + c0;
+                float bias_of[kW];
+#pragma unroll
+                for (int q = 0; q < kW / 4; ++q) {
+                    const float4 four = *reinterpret_cast<const float4*>(bias_smem + c_first + 4 * q);
+                    bias_of[4 * q] = four.x; bias_of[4 * q + 1] = four.y;
+                    bias_of[4 * q + 2] = four.z; bias_of[4 * q + 3] = four.w;
+                }
 #pragma unroll
                 for (int i = 0; i < kW; ++i) {
-                    float y = __uint_as_float(raw[i]) + r[i] + bias_smem[c_first + i];
+                    float y = __uint_as_float(raw[i]) + r[i] + bias_of[i];
                     if constexpr (kBiasBatch) {
                         if (a.bias_batch) y += a.bias_batch[(size_t)b * a.c_out + c_first + i];
                     }
-                    if (a.relu) y = fmaxf(y, 0.f);
-                    v[i] = y;
+                    v[i] = fmaxf(y, relu_floor);
                 }
                 int row = t;
                 if (a.pool) {
@@ -529,16 +546,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
                     row = (t >= 0 && (lane & 1) == 0 && t + 1 < t_out) ? t / 2 : -1;
                 }
                 if (row >= 0) {
-                    const size_t idx = ((size_t)b * a.c_out + c_first) * out_row + row;
+                    const uint32_t first = (uint32_t)c_first * (uint32_t)out_row + (uint32_t)row;
                     if (a.out) {
+                        float* to = a.out + (size_t)b * item_elements + first;
 #pragma unroll
-                        for (int i = 0; i < kW; ++i) a.out[idx + (size_t)i * out_row] = v[i];
+                        for (int i = 0; i < kW; ++i, to += out_row) *to = v[i];
                     }
                     if (a.accum_mode) {
+                        float* to = a.accum + (size_t)b * item_elements + first;
 #pragma unroll
-                        for (int i = 0; i < kW; ++i) {
+                        for (int i = 0; i < kW; ++i, to += out_row) {
                             const float total = fmaf(v[i], a.accum_scale, acc[d & 1][i]);
-                            a.accum[idx + (size_t)i * out_row] = total;
+                            *to = total;
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }
                     }
@@ -549,32 +568,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             uint32_t z, l;
-                            split_pair_f8(leaky(v[2 * e], a.out_slope), leaky(v[2 * e + 1], a.out_slope), main[e], z, l);
+                            split_pair_f8(leaky01(v[2 * e], a.out_slope), leaky01(v[2 * e + 1], a.out_slope), main[e], z, l);
                             if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
                             else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
                         }
-                        const size_t item = (size_t)b * (groups_out * 2);
-                        uint4* rows = reinterpret_cast<uint4*>(a.out_planes);
-                        rows[(item + c_first / 8) * out_pad + kTcPad + t] = make_uint4(main[0], main[1], main[2], main[3]);
-                        rows[(item + c_first / 8 + 1) * out_pad + kTcPad + t] = make_uint4(main[4], main[5], main[6], main[7]);
-                        rows[(item + groups_out + c_first / 16) * out_pad + kTcPad + t] =
-                            make_uint4(coarse[0], coarse[1], coarse[2], coarse[3]);
-                        rows[(item + groups_out + groups_out / 2 + c_first / 16) * out_pad + kTcPad + t] =
-                            make_uint4(low[0], low[1], low[2], low[3]);
+                        uint4* rows = reinterpret_cast<uint4*>(a.out_planes) +
+                                      (size_t)b * (groups_out * 2) * out_pad + kTcPad + t;
+                        const uint32_t group = c_first / 8, pad = out_pad;
+                        rows[group * pad] = make_uint4(main[0], main[1], main[2], main[3]);
+                        rows[(group + 1) * pad] = make_uint4(main[4], main[5], main[6], main[7]);
+                        rows[(groups_out + group / 2) * pad] = make_uint4(coarse[0], coarse[1], coarse[2], coarse[3]);
+                        rows[(groups_out + groups_out / 2 + group / 2) * pad] = make_uint4(low[0], low[1], low[2], low[3]);
                     } else if (a.out_planes) {
                         const int out_pad = tc_padded_length_device(t_out);
+                        uint4* rows = reinterpret_cast<uint4*>(a.out_planes) +
+                                      (size_t)b * (groups_out * 2) * out_pad + kTcPad + t;
+                        const uint32_t pad = out_pad;
 #pragma unroll
                         for (int g = 0; g < kW / 8; ++g) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                split_pair(leaky(v[g * 8 + 2 * e], a.out_slope),
-                                           leaky(v[g * 8 + 2 * e + 1], a.out_slope), hi[e], lo[e]);
-                            const size_t row_hi =
-                                ((size_t)(b * 2) * groups_out + (c_first / 8 + g)) * out_pad + kTcPad + t;
-                            const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
-                            *reinterpret_cast<uint4*>(a.out_planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(a.out_planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                split_pair(leaky01(v[g * 8 + 2 * e], a.out_slope),
+                                           leaky01(v[g * 8 + 2 * e + 1], a.out_slope), hi[e], lo[e]);
+                            const uint32_t group = c_first / 8 + g;
+                            rows[group * pad] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            rows[(groups_out + group) * pad] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 }
@@ -625,7 +644,7 @@ __global__ void __launch_bounds__(128) planes_from_f32_kernel(
             const int c = g * 8 + 2 * e;       // channels past the source's are zero
             const float y0 = c < source_channels ? __ldg(src + (size_t)(2 * e) * t_len) : 0.f;
             const float y1 = c + 1 < source_channels ? __ldg(src + (size_t)(2 * e + 1) * t_len) : 0.f;
-            split_pair(leaky(y0, slope), leaky(y1, slope), hi[e], lo[e]);
+            split_pair(leaky01(y0, slope), leaky01(y1, slope), hi[e], lo[e]);
         }
     }
     const size_t row_hi = ((size_t)(b * 2) * groups + g) * t_pad + row;
@@ -649,8 +668,8 @@ __global__ void __launch_bounds__(128) planes_f8_from_f32_kernel(
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             uint32_t z, l;
-            split_pair_f8(leaky(__ldg(src + (size_t)(2 * e) * t_len), slope),
-                          leaky(__ldg(src + (size_t)(2 * e + 1) * t_len), slope), main[e], z, l);
+            split_pair_f8(leaky01(__ldg(src + (size_t)(2 * e) * t_len), slope),
+                          leaky01(__ldg(src + (size_t)(2 * e + 1) * t_len), slope), main[e], z, l);
             if (e % 2 == 0) { coarse[e / 2] = z; low[e / 2] = l; }
             else { coarse[e / 2] |= z << 16; low[e / 2] |= l << 16; }
         }
@@ -835,6 +854,9 @@ int launch_variant(const TcConvArgs& a, int n_tiles, cudaStream_t stream) {
     const int grid = min(num_tiles, sm_count());
     TcConvArgs args = a;
     if (!args.debug) args.debug = g_tc_debug;
+    PMN_REQUIRE((size_t)a.c_out * (size_t)(a.out_row > 0 ? a.out_row : a.t_len) < ((size_t)1 << 31) &&
+                    (size_t)a.c_out / 4 * tc_padded_length(a.t_len) < ((size_t)1 << 31),
+                "conv1d_tc: an item of the output exceeds 2^31 elements");
     PMN_REQUIRE(!a.bias_batch || (MODE == kConv && C_IN == 128 && N == 256),
                 "conv1d_tc: a per-item bias is compiled into the 128 -> 512 variant only");
     PMN_REQUIRE(!(a.out_planes && a.out_f8) || (MODE == kConv ? F8 : UP == 8),
@@ -910,6 +932,7 @@ int tcw_mode() {
 
 int launch_conv1d_tc(const TcConvArgs& a, cudaStream_t stream) {
     PMN_REQUIRE(a.x_planes && a.w_slabs, "conv1d_tc: null input");
+    PMN_REQUIRE(a.out_slope >= 0.f && a.out_slope <= 1.f, "conv1d_tc: the output slope lies in [0, 1]");
     PMN_REQUIRE(!a.f8x2 || (tc_f8_plan(a.c_in, a.c_out, nullptr) && a.frame_length == 0),
                 "conv1d_tc: no fp8 form for these channel counts");
     if (a.f8x2) {
@@ -1005,6 +1028,7 @@ int launch_planes_from_f32(
     cudaStream_t stream, int source_channels, bool f8) {
     PMN_REQUIRE(x && planes && channels % 8 == 0 && batch > 0 && t_len > 0, "planes_from_f32: bad argument");
     PMN_REQUIRE(source_channels >= 0 && source_channels <= channels, "planes_from_f32: bad channel count");
+    PMN_REQUIRE(slope >= 0.f && slope <= 1.f, "planes_from_f32: the slope lies in [0, 1]");
     const int t_pad = tc_padded_length(t_len);
     if (f8) {
         PMN_REQUIRE(channels % 16 == 0 && (source_channels == 0 || source_channels == channels),

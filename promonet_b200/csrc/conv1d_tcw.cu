@@ -204,14 +204,26 @@ __global__ void __launch_bounds__(64 + SETS * 128, 1) conv1d_tcw_kernel(
             auto fetch = [&](int chunk) {
                 const int t = t0 + chunk * kChunk + lane;
                 const bool valid = t < a.t_len;
+                // one 64-bit address per array, then pointer increments: computing every element's
+                // address from scratch took several integer instructions per load
                 const size_t idx = ((size_t)b * C + c_first) * a.t_len + t;
+                if (valid && a.residual != nullptr) {
+                    const float* from = a.residual + idx;
 #pragma unroll
-                for (int i = 0; i < kPerThread; ++i)
-                    res[i] = valid && a.residual != nullptr ? a.residual[idx + (size_t)i * a.t_len] : 0.f;
+                    for (int i = 0; i < kPerThread; ++i, from += a.t_len) res[i] = *from;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kPerThread; ++i) res[i] = 0.f;
+                }
                 if (accumulate) {
+                    if (valid) {
+                        const float* from = a.accum + idx;
 #pragma unroll
-                    for (int i = 0; i < kPerThread; ++i)
-                        acc[i] = valid ? a.accum[idx + (size_t)i * a.t_len] : 0.f;
+                        for (int i = 0; i < kPerThread; ++i, from += a.t_len) acc[i] = *from;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kPerThread; ++i) acc[i] = 0.f;
+                    }
                 }
             };
             if (set < kChunks) fetch(set);
@@ -262,18 +274,23 @@ __global__ void __launch_bounds__(64 + SETS * 128, 1) conv1d_tcw_kernel(
                 if (t < a.t_len) {
                     const size_t idx = ((size_t)b * C + c_first) * a.t_len + t;
                     if (a.out) {
+                        float* to = a.out + idx;
 #pragma unroll
-                        for (int i = 0; i < kPerThread; ++i) a.out[idx + (size_t)i * a.t_len] = v[i];
+                        for (int i = 0; i < kPerThread; ++i, to += a.t_len) *to = v[i];
                     }
                     if (a.accum_mode) {
+                        float* to = a.accum + idx;
 #pragma unroll
-                        for (int i = 0; i < kPerThread; ++i) {
+                        for (int i = 0; i < kPerThread; ++i, to += a.t_len) {
                             const float total = accumulate ? fmaf(v[i], a.accum_scale, previous[i]) : v[i] * a.accum_scale;
-                            a.accum[idx + (size_t)i * a.t_len] = total;
+                            *to = total;
                             if (a.planes_from_accum) v[i] = total;   // the planes below are those of the sum
                         }
                     }
                     if (a.out_planes) {
+                        uint4* rows = reinterpret_cast<uint4*>(a.out_planes) +
+                                      (size_t)(b * 2) * groups_out * out_pad + kTcPad + t;
+                        const uint32_t pad = out_pad;
 #pragma unroll
                         for (int g = 0; g < kPerThread / 8; ++g) {
                             uint32_t hi[4], lo[4];
@@ -281,11 +298,9 @@ __global__ void __launch_bounds__(64 + SETS * 128, 1) conv1d_tcw_kernel(
                             for (int e = 0; e < 4; ++e)
                                 split_pair(leaky(v[g * 8 + 2 * e], a.out_slope),
                                            leaky(v[g * 8 + 2 * e + 1], a.out_slope), hi[e], lo[e]);
-                            const size_t row_hi =
-                                ((size_t)(b * 2) * groups_out + (c_first / 8 + g)) * out_pad + kTcPad + t;
-                            const size_t row_lo = row_hi + (size_t)groups_out * out_pad;
-                            *reinterpret_cast<uint4*>(a.out_planes + row_hi * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4*>(a.out_planes + row_lo * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            const uint32_t group = c_first / 8 + g;
+                            rows[group * pad] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            rows[(groups_out + group) * pad] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 }
