@@ -390,14 +390,15 @@ size_t tcw_weight_elements(int channels, int k) {
     return (size_t)(channels / kKB) * ((k + stack - 1) / stack) * (kWSlab / 2);
 }
 
-// Where the kernel is the faster of the two on a B200 (profiles/r2_narrow_layers.txt, batch 32 at
-// the benchmark's lengths): everywhere at C = 64; at C = 32, where every output costs four partial
-// sums read from TMEM and staged through shared memory, only on the long kernels, where
-// conv1d_tc_kernel pays most for its idle tensor pipe
+// Where the kernel is the faster of the two on a B200 (profiles/r2_narrow_layers.txt, batch 32 at the
+// benchmark's lengths; second table: after conv1d_tc_kernel's epilogue lost half of its instructions):
+// the long kernels, where conv1d_tc_kernel pays most for its idle tensor pipe (k = 11: 1.12 - 1.56 x),
+// and the planes-only launches of the middle one (k = 7: 1.18 - 1.20 x); with a residual and an fp32
+// output the time-on-M kernel's epilogue is now the cheaper one up to k = 7 (0.81 - 0.96), and at
+// k = 3 it wins everywhere (0.68 - 0.94)
 bool tcw_preferred(const TcConvArgs& a) {
     const bool planes_only = a.out == nullptr && a.accum_mode == 0 && a.residual == nullptr;
-    if (a.c_in == 32) return a.k == 11 || (a.k == 7 && planes_only);
-    if (a.c_in == 64) return true;    // 1.25 x on the planes-only launches, 1.0 - 1.2 x on the others
+    if (a.c_in == 32 || a.c_in == 64) return a.k >= 9 || (a.k >= 5 && planes_only);
     return false;
 }
 

@@ -320,11 +320,17 @@ conv_pair_tc_kernel(TcPairArgs a, int tiles_per_item, int num_tiles) {
                             const int g = idx / quads, q = idx - g * quads;
                             const int t = first_time + 4 * q;
                             const bool live = idx < tasks && t >= 0 && t < a.t_len;
+                            // one address, then pointer increments (conv1d_tc.cu: per-element 64-bit
+                            // address arithmetic was half of that epilogue's instructions)
                             const float* p = src + (ptrdiff_t)(g * 8) * a.t_len + t;
+                            if (live) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                v[u][e] = live ? __ldg(reinterpret_cast<const float4*>(p + (size_t)e * a.t_len))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                                for (int e = 0; e < 8; ++e, p += a.t_len)
+                                    v[u][e] = __ldg(reinterpret_cast<const float4*>(p));
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[u][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
                         }
 #pragma unroll
                         for (int u = 0; u < kU; ++u) {
@@ -361,9 +367,13 @@ conv_pair_tc_kernel(TcPairArgs a, int tiles_per_item, int num_tiles) {
                             const int t = first_time + q;
                             const bool live = idx < tasks && t >= 0 && t < a.t_len;
                             const float* p = src + (ptrdiff_t)(g * 8) * a.t_len + t;
+                            if (live) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                v[u][e] = live ? __ldg(p + (size_t)e * a.t_len) : 0.f;
+                                for (int e = 0; e < 8; ++e, p += a.t_len) v[u][e] = __ldg(p);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+                            }
                         }
 #pragma unroll
                         for (int u = 0; u < kU; ++u) {
@@ -480,11 +490,14 @@ conv_pair_tc_kernel(TcPairArgs a, int tiles_per_item, int num_tiles) {
             auto fetch = [&](const float* source, int chunk, float (&r)[kW]) {
                 const int s = chunk / kPerSub, c0 = (chunk % kPerSub) * kW;
                 const int t = row_of(s);
-                const bool valid = source != nullptr && t >= 0;
-                const size_t idx = ((size_t)b * C + c0) * a.t_len + t;
+                if (source != nullptr && t >= 0) {
+                    const float* from = source + ((size_t)b * C + c0) * a.t_len + t;
 #pragma unroll
-                for (int e = 0; e < kW; ++e)
-                    r[e] = valid ? source[idx + (size_t)e * a.t_len] : 0.f;
+                    for (int e = 0; e < kW; ++e, from += a.t_len) r[e] = *from;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kW; ++e) r[e] = 0.f;
+                }
             };
             float res[kDepth][kW];
 #pragma unroll
@@ -515,11 +528,18 @@ conv_pair_tc_kernel(TcPairArgs a, int tiles_per_item, int num_tiles) {
                 float (&r)[kW] = res[mine % kDepth];
                 if (t >= 0) {
                     const size_t idx = ((size_t)b * C + c0) * a.t_len + t;
+                    float y[kW];
 #pragma unroll
-                    for (int e = 0; e < kW; ++e) {
-                        const float y = __uint_as_float(raw[e]) + r[e] + bias_smem[C + c0 + e];
-                        if (a.out) a.out[idx + (size_t)e * a.t_len] = y;
-                        if (a.accum_mode) a.accum[idx + (size_t)e * a.t_len] = fmaf(y, a.accum_scale, acc[e]);
+                    for (int e = 0; e < kW; ++e) y[e] = __uint_as_float(raw[e]) + r[e] + bias_smem[C + c0 + e];
+                    if (a.out) {
+                        float* to = a.out + idx;
+#pragma unroll
+                        for (int e = 0; e < kW; ++e, to += a.t_len) *to = y[e];
+                    }
+                    if (a.accum_mode) {
+                        float* to = a.accum + idx;
+#pragma unroll
+                        for (int e = 0; e < kW; ++e, to += a.t_len) *to = fmaf(y[e], a.accum_scale, acc[e]);
                     }
                 }
                 if (mine + kDepth < kMine) fetch(a.x, half + kSets * (mine + kDepth), r);
