@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     TcConvArgs a, int t_pad, int tiles_per_item, int n_tiles, int num_tiles) {
     using Cfg = TcConfig<C_IN, N, S, KB, NW, AS, MODE, CONCAT, XS, F8>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-byte alignment by pointer arithmetic on the __shared__ array: through an integer cast the
+    // compiler loses the address space and emits generic LD / ST for every access to the buffers
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t* x_slabs = smem;
     uint8_t* w_slabs = smem + Cfg::kXStages * Cfg::kXSlab;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_slabs + NW * Cfg::kWSlab);

@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(64 + SETS * 128, 1) conv1d_tcw_kernel(
     constexpr int kBlocks = C / kKB;
     constexpr int kPerThread = C / 4;            // channels a thread combines per chunk
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-byte alignment by pointer arithmetic on the __shared__ array: through an integer cast the
+    // compiler loses the address space and emits generic LD / ST for every access to the buffers
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t* x_slabs = smem;
     uint8_t* w_stage = x_slabs + kXStages * kXSlab;
     float* staging = reinterpret_cast<float*>(w_stage + kWStages * kWSlab);   // [set][buffer][128][kPitch]

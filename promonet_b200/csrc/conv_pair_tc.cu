@@ -102,7 +102,9 @@ conv_pair_tc_kernel(TcPairArgs a, int tiles_per_item, int num_tiles) {
     constexpr int kConverters = Cfg::kConverters;
     constexpr int kPairThreads = Cfg::kThreads;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-byte alignment by pointer arithmetic on the __shared__ array: through an integer cast the
+    // compiler loses the address space and emits generic LD / ST for every access to the buffers
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t* x_slabs = smem;
     uint8_t* mid = x_slabs + Cfg::kXStages * Cfg::kXSlab;
     uint8_t* w_slabs = mid + MB * Cfg::kMid;

@@ -31,11 +31,13 @@ constexpr int kResDilation[3] = {1, 3, 5};          // :253
 constexpr float kSlope = 0.1f;                      // :216
 // Which residual blocks take the fused pair kernel by default; bit 3 * stage + block, block =
 // kernel 3 / 7 / 11.  Measured on B200 (profiles/r2_pair_breakdown.txt, r2_pair_selection*.txt):
-// these convolutions are bound by the tensor pipe's operand fetch from shared memory (105-145
-// cycles per M128 MMA), not by HBM, so keeping the pair on chip only pays where the two-launch
-// path is HBM-bound: the k = 3 block of stage 1 (C = 128), +1 % of the step.  Everything else
-// is faster as two launches (larger tiles, half the weight streaming, no converter traffic).
-constexpr unsigned kDefaultPairMask = 0x008u;
+// the longer kernels are bound by the tensor pipe's operand fetch from shared memory, not by HBM,
+// and are faster as two launches (larger tiles, half the weight streaming, no converter traffic);
+// keeping the pair on chip pays where the two-launch path is HBM-bound, i.e. for the k = 3 blocks:
+// of stage 1 (C = 128) since the kernel was written, of stages 2 and 3 (C = 64, 32) since its
+// converter and epilogue warps address shared memory as such and step their global pointers
+// (each +0.2 ms of 25.7, together 0.55: profiles/r2_pair_selection_final.txt).
+constexpr unsigned kDefaultPairMask = 0x248u;
 
 
 struct PackedConv {
