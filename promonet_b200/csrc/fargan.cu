@@ -240,7 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     GroupState* __restrict__ groups, float* __restrict__ audio, int batch, int frames, int debug) {
     extern __shared__ __align__(16) float smem[];
     float* w = smem;
-    float* input[2] = {smem + kWeights, smem + kWeights + kInput * kGroupItems};
+    // the two feature buffers, addressed by offset from the __shared__ array: taken from a pointer
+    // array the compiler no longer knows their address space and reads them with generic loads
+    float* const input0 = smem + kWeights;
     float* staged = smem + kWeights + 2 * kInput * kGroupItems;
     float* scratch = staged + kStage;
 
@@ -250,21 +252,30 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     const int b = tid & (kGroupItems - 1);
     const int part = tid >> 4;
     const GroupState gs = groups[group];
+    // The 10 x 3 exchange buffers lie back to back in GroupState's member order (fargan_forward fills
+    // them so): buffer (member, slot) by arithmetic.  Indexing the pointer arrays with a run-time slot
+    // put the struct into local memory and a local load in front of every exchange access.
+    float* const exchange = gs.fw[0];
+    __builtin_assume(__isGlobal(exchange));      // pointers read from memory are generic otherwise
+    __builtin_assume(__isGlobal(gs.history));
+    auto buffer_of = [&](int member, int slot_index) {
+        return exchange + (size_t)(member * kSlots + slot_index) * (kHop * kGroupItems);
+    };
+    enum { kFw = 0, kFwg = 1, kH = 2, kG = 5, kSkip = 8, kSkipg = 9 };
     const int samples = frames * kHop;
     unsigned int target = 0;
 
     for (int i = tid; i < kWeights; i += kThreads) w[i] = weights[(size_t)cta * kWeights + i];
-    for (int i = tid; i < 2 * kInput * kGroupItems; i += kThreads) input[0][i] = 0.f;  // state3 = 0
+    for (int i = tid; i < 2 * kInput * kGroupItems; i += kThreads) input0[i] = 0.f;  // state3 = 0
     // Start-up: every exchanged slot holds the sentinel, except the GRU states "of subframe -1"
     // (slot 2), which start at zero (fargan.py:406-415); history[0:512] = previous samples, the rest
     // sentinel.  The 64 CTAs share the fill and meet once at a barrier.
     {
-        float* const* all = &gs.fw[0];     // the 10 x 3 buffer pointers are contiguous in GroupState
         for (int buffer = 0; buffer < kExchanged * kSlots; ++buffer) {
             // h[s][2] are buffers 2 * kSlots + s * kSlots + 2
             const bool zero = buffer >= 2 * kSlots && buffer < 5 * kSlots && (buffer - 2 * kSlots) % kSlots == 2;
             for (int i = cta * kThreads + tid; i < kHop * kGroupItems; i += kGroupCtas * kThreads)
-                all[buffer][i] = zero ? 0.f : sentinel();
+                exchange[(size_t)buffer * (kHop * kGroupItems) + i] = zero ? 0.f : sentinel();
         }
         const size_t total = (size_t)(kHistory + samples) * kGroupItems;
         for (size_t i = (size_t)cta * kThreads + tid; i < total; i += (size_t)kGroupCtas * kThreads) {
@@ -291,8 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
     for (int n = 0; n < frames * kSubframes; ++n) {
         const int f = n / kSubframes, sub = n % kSubframes;
         const int slot = n % kSlots, before = (n + kSlots - 1) % kSlots, after = (n + 1) % kSlots;
-        float* in = input[current];
-        const float* state3 = input[current ^ 1];
+        float* in = input0 + current * (kInput * kGroupItems);
+        const float* state3 = input0 + (current ^ 1) * (kInput * kGroupItems);
         const float* hist = gs.history + (size_t)n * kSub * kGroupItems;  // 512-sample window
 
         // ---- subframe input: cond[:, sub::4] (fargan.py:109-113), previous 64, lookback 68 ----
@@ -360,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             reduce<kUnits>(acc, scratch, part, b);
             tock2(t_reduce);
             if (tid < kUnits * kGroupItems)
-                __stcg(gs.fw[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
+                __stcg(buffer_of(kFw, slot) + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
                        tanhf(scratch[tid]));
         }
 
@@ -376,11 +387,11 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             const float* wih = w + kWGru + s * (kGruIh + kGruHh);
-            dot_global<3 * kUnits>(gh[s], wih + kGruIh, gs.h[s][before], part, b);
+            dot_global<3 * kUnits>(gh[s], wih + kGruIh, buffer_of(kH + s, before), part, b);
             dot<3 * kUnits>(gi_side[s], wih + kHop * 3 * kUnits, lookback, kSub, part, b);
             dot<3 * kUnits>(gi_side[s], wih + (kHop + kSub) * 3 * kUnits, last, kSub, part, b);
             if (tid < kUnits * kGroupItems)
-                h_previous[s] = __ldcg(gs.h[s][before] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems +
+                h_previous[s] = __ldcg(buffer_of(kH + s, before) + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems +
                                        (tid % kGroupItems));
         }
         dot<kUnits>(skip_acc, w + kWSkip + 4 * kHop * kUnits, lookback, kSub, part, b);
@@ -407,16 +418,15 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             }
         };
 
-        glu(w + kWFwGlu, gs.fw[slot], gs.fwg[slot]);
+        glu(w + kWFwGlu, buffer_of(kFw, slot), buffer_of(kFwg, slot));
         // fw of this subframe is complete everywhere (glu staged all of it): every CTA has finished
         // subframe n - 1, so nobody reads the slot of subframe n + 1 any more (last written in
         // n - 2, last read in n - 1): re-arm this CTA's slice of it, a whole subframe ahead of its
         // next readers
         if (tid < kUnits * kGroupItems) {
-            float* const* all = &gs.fw[0];
             const size_t at = (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems);
 #pragma unroll
-            for (int buffer = 0; buffer < kExchanged; ++buffer) __stcg(all[buffer * kSlots + after] + at, sentinel());
+            for (int buffer = 0; buffer < kExchanged; ++buffer) __stcg(buffer_of(buffer, after) + at, sentinel());
             __threadfence();
         }
 
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             const float* wih = w + kWGru + s * (kGruIh + kGruHh);
-            const float* x_global = s == 0 ? gs.fwg[slot] : gs.g[s - 1][slot];
+            const float* x_global = s == 0 ? buffer_of(kFwg, slot) : buffer_of(kG + s - 1, slot);
             tick();
             stage(staged, x_global, kHop);
             __syncthreads();
@@ -448,15 +458,15 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
                 const float r = sigmoid(at(3 * u) + at(3 * kUnits + 3 * u));
                 const float z = sigmoid(at(3 * u + 1) + at(3 * kUnits + 3 * u + 1));
                 const float c = tanhf(at(3 * u + 2) + r * at(3 * kUnits + 3 * u + 2));
-                __stcg(gs.h[s][slot] + (size_t)unit * kGroupItems + col, (1.f - z) * c + z * h_previous[s]);
+                __stcg(buffer_of(kH + s, slot) + (size_t)unit * kGroupItems + col, (1.f - z) * c + z * h_previous[s]);
             }
-            glu(w + kWGlu + s * kHop * kUnits, gs.h[s][slot], gs.g[s][slot]);
+            glu(w + kWGlu + s * kHop * kUnits, buffer_of(kH + s, slot), buffer_of(kG + s, slot));
         }
 
         // ---- skip: tanh(W [g1, g2, g3, fw, lookback, previous]) then GLU (fargan.py:311-325) ----
         {
             tick();
-            stage(staged, gs.g[2][slot], kHop);
+            stage(staged, buffer_of(kG + 2, slot), kHop);
             __syncthreads();
             tock(wait_stage);
             tick2();
@@ -466,15 +476,15 @@ __global__ void __launch_bounds__(kThreads, 1) fargan_kernel(
             reduce<kUnits>(skip_acc, scratch, part, b);
             tock2(t_reduce);
             if (tid < kUnits * kGroupItems)
-                __stcg(gs.skip[slot] + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
+                __stcg(buffer_of(kSkip, slot) + (size_t)(cta * kUnits + tid / kGroupItems) * kGroupItems + (tid % kGroupItems),
                        tanhf(scratch[tid]));
         }
-        glu(w + kWSkipGlu, gs.skip[slot], gs.skipg[slot]);
+        glu(w + kWSkipGlu, buffer_of(kSkip, slot), buffer_of(kSkipg, slot));
 
         // ---- output: tanh(W skip), one of the 64 samples per CTA (fargan.py:327-329) ----
         {
             tick();
-            stage(staged, gs.skipg[slot], kHop);
+            stage(staged, buffer_of(kSkipg, slot), kHop);
             __syncthreads();
             tock(wait_stage);
             float acc[1] = {};
