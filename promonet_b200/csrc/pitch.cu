@@ -90,7 +90,7 @@ struct pmn_pitch {
     const float* head_bias = nullptr;
     const float* folded_bias = nullptr;      // block 1 folded by 4: bias of column (q, o)
     // block 1 with "fp16 + 2 x fp8" operands (conv1d_tc.cuh): its slabs and the weights' power-of-two
-    // scale; -1: bf16 x 3 (the default; PMN_PITCH_F8=1 at model construction selects the fp8 form)
+    // scale; -1: bf16 x 3 (PMN_PITCH_F8=0 at model construction; the fp8 form is the default)
     void* block1_f8_slabs = nullptr;
     int block1_shift = -1;
     // resampling tables per input rate: (2 width + orig, new) transposed FIR bank
@@ -422,7 +422,7 @@ constexpr int kSharedFrames = 8;
 // shared memory per CTA it runs 512 threads, two per sample on alternate frames, so that as many
 // threads stay resident (at 256 it was 1.6 x slower; 8 channels per thread writing half e4m3 rows 2 x)
 template <bool F8>
-__global__ void __launch_bounds__(F8 ? 512 : 256) shared_norm_planes_kernel(
+__global__ void __launch_bounds__(F8 ? 512 : 256, F8 ? 2 : 5) shared_norm_planes_kernel(
     const float* __restrict__ in, const float* __restrict__ weight, const float* __restrict__ bias,
     const float2* __restrict__ stats, __nv_bfloat16* __restrict__ planes, int channels, int l_in,
     int l_out, size_t in_row, int count, int t_pad, int stride_out, int frames_per_item,
@@ -442,10 +442,23 @@ __global__ void __launch_bounds__(F8 ? 512 : 256) shared_norm_planes_kernel(
     const size_t offset0 = shared_frame_offset(first_frame + f0, frames_per_item, item_stride, l_in);
     const int needed = (same - 1) * l_in + l_out;
     const float* source = in + (size_t)(g * kC) * in_row + offset0;
+    if (F8) {
+        // two CTAs of 64 registers per SM; every channel's load of a position is issued before the
+        // first store waits for one (with 128 registers and one CTA the staging waited on its loads)
+        for (int pos = threadIdx.x; pos < needed; pos += blockDim.x) {
+            float staged[kC];
+            const float* from = source + pos;
 #pragma unroll
-    for (int c = 0; c < kC; ++c)
-        for (int pos = threadIdx.x; pos < needed; pos += blockDim.x)
-            tile[c * width + pos] = source[(size_t)c * in_row + pos];
+            for (int c = 0; c < kC; ++c, from += in_row) staged[c] = *from;
+#pragma unroll
+            for (int c = 0; c < kC; ++c) tile[c * width + pos] = staged[c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kC; ++c)
+            for (int pos = threadIdx.x; pos < needed; pos += blockDim.x)
+                tile[c * width + pos] = source[(size_t)c * in_row + pos];
+    }
     if (threadIdx.x < n_frames) frame_stats[threadIdx.x] = stats[f0 + threadIdx.x];
     __syncthreads();
     uint4* rows16 = reinterpret_cast<uint4*>(planes);
@@ -923,11 +936,11 @@ int pitch_finalize(pmn_pitch* p, int math, cudaStream_t stream) {
                 {
                     // "fp16 + 2 x fp8": block 1's input is a LayerNorm output (|x| of a few units), its
                     // weights are scaled by the power of two that brings the largest to (128, 256]
-                    // Opt-in (PMN_PITCH_F8=1): measured on 32 x 10 s the convolution gains 2.8 ms
-                    // (15.3 -> 12.5) and the kernel that writes its four-stream operand loses 2.4
-                    // (3.7 -> 6.3), profiles/r2_preprocess_history.txt
+                    // The default (PMN_PITCH_F8=0: bf16 x 3): measured on 32 x 10 s the convolution gains
+                    // 2.6 ms and the kernel that writes its four-stream operand loses 0.4 (two CTAs of
+                    // 64 registers per SM; at 128 registers it lost 3.8), profiles/r2_preprocess_history.txt
                     const char* flag = getenv("PMN_PITCH_F8");
-                    if (flag && flag[0] == '1') {
+                    if (!(flag && flag[0] == '0')) {
                         int shift;
                         PMN_TRY(tc_f8_weight_shift_of(w->data, w->numel(), stream, &shift));
                         float* f8_slabs;

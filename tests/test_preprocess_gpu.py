@@ -208,9 +208,11 @@ def test_pitch_pipeline_stages_match_oracle(pitch_model, pitch_state, batch, sam
     assert min(agreement) > 0.95, agreement
 
 
-def test_pitch_block1_with_fp8_corrections_matches_oracle(pb, pitch_state, monkeypatch):
-    """PMN_PITCH_F8=1: block 1 as fp16 x fp16 + two e4m3 correction products (conv1d_tc.cuh); same bar"""
-    monkeypatch.setenv('PMN_PITCH_F8', '1')
+@pytest.mark.parametrize('f8', ['1', '0'])
+def test_pitch_block1_with_and_without_fp8_corrections_matches_oracle(pb, pitch_state, monkeypatch, f8):
+    """PMN_PITCH_F8: block 1 as fp16 x fp16 + two e4m3 correction products (conv1d_tc.cuh; the default)
+    or as bf16 x 3; same bar"""
+    monkeypatch.setenv('PMN_PITCH_F8', f8)
     model = pb.preprocess.penn.Model(state=pitch_state, math=pb._lib.MATH_BF16X3_TC)
     audio = inputs.audio(2, 33000, seed=5)
     _, periodicity, logits, _ = model(audio, batch_size=64, return_intermediates=True)
