@@ -72,8 +72,9 @@ int pmn_generator_finalize(pmn_generator* g, int math, void* stream);
 /* Tensor-core math only: which residual blocks (Block.forward, hifigan.py:198-210) run
  * their three c1 -> c2 pairs as fused pmn_conv_pair_tc-style launches.  Bit
  * 3 * stage + block (block 0 / 1 / 2 = kernel 3 / 7 / 11); stage 0 (C = 256) is never
- * fused.  The default is the measured-fastest selection; results are bit-identical
- * for every mask. */
+ * fused.  The default (0x248: the k = 3 block of stages 1 - 3) is the measured-fastest
+ * selection.  Results agree within fp32 rounding for every mask, bit for bit where both
+ * paths run bf16 x 3 products in the same order. */
 int pmn_generator_set_pair_mask(pmn_generator* g, unsigned mask);
 
 /* Tensor-core math only: run the unfused residual blocks of the C = 128 stage (a third of the

@@ -23,8 +23,8 @@ class Generator:
     def __init__(self, device=None, math=_lib.MATH_BF16X3_TC, state=None, pair_mask=None, f8=None):
         """pair_mask: which residual blocks run as fused pair kernels
         (pmn_generator_set_pair_mask); None = the library default, or the
-        PMN_PAIR_MASK environment variable (an experiment knob: the output bits
-        do not depend on it).
+        PMN_PAIR_MASK environment variable (an experiment knob: outputs agree
+        within fp32 rounding for every mask).
         f8: residual blocks of the C = 128 stage with "fp16 + 2 x fp8" operands
         (pmn_generator_set_f8); None = the PMN_GENERATOR_F8 environment variable, else F8_DEFAULT"""
         if not torch.cuda.is_available():
