@@ -667,7 +667,7 @@ def train(ctx):
     ms = ctx.timed(step, steps) / steps
     names = (
         'conv_fprop_tc_kernel', 'conv_dgrad_tc_kernel', 'conv_wgrad_tc_kernel', 'fold_weights_kernel',
-        'pack_weights_kernel', 'weight_norm_backward_kernel', 'stft_train_kernel',
+        'pack_weights_kernel', 'weight_norm_backward_kernel', 'weight_norm_backward_table_kernel', 'stft_train_kernel',
         'stft_train_backward_kernel', 'mel_loss_kernel', 'l1_mean_kernel', 'mse_to_target_kernel',
         'adamw_kernel', 'adamw_peer_kernel', 'reflect_pad_kernel', 'copy_columns_kernel')
     kernels = ctx.kernels(lambda: trainer.step(*batch), names)

@@ -439,6 +439,20 @@ int pmn_weight_norm_backward(
     const float* v, const float* g, const float* gw, float* gv, float* gg, int dim0, int inner,
     void* stream);
 
+/* The same for every weight-normed convolution of a module in one launch: a DEVICE table with one
+ * entry per layer (train/core.py:255,338 call backward() once per step; autograd runs this per
+ * parameter).  max_dim0 = the largest dim0 in the table. */
+typedef struct {
+    const float* v;      /* weight_v (dim0, inner) */
+    const float* g;      /* weight_g (dim0) */
+    const float* gw;     /* gradient of the folded weight (dim0, inner) */
+    float* gv;           /* out: gradient of weight_v */
+    float* gg;           /* out: gradient of weight_g */
+    int dim0, inner;
+} pmn_weight_norm_desc;
+int pmn_weight_norm_backward_table(
+    const pmn_weight_norm_desc* table, int layers, int max_dim0, void* stream);
+
 /* torch.nn.functional.pad(x, (left, right), 'reflect') over rows of length t_in
  * (discriminator.py:78-81) and its adjoint */
 int pmn_reflect_pad(

@@ -30,7 +30,7 @@ KERNELS = (
     'conv_fprop_tc_kernel', 'conv_dgrad_tc_kernel', 'conv_wgrad_tc_kernel', 'pack_weight_taps_kernel',
     'fold_weights_kernel', 'pack_weights_kernel',
     'conv_fprop_kernel', 'conv_dgrad_kernel', 'conv_wgrad_kernel', 'conv_transpose1d_kernel',
-    'weight_norm_fold_kernel', 'weight_norm_backward_kernel', 'transpose_weight_kernel',
+    'weight_norm_fold_kernel', 'weight_norm_backward_kernel', 'weight_norm_backward_table_kernel', 'transpose_weight_kernel',
     'stft_train_kernel', 'stft_train_backward_kernel', 'mel_loss_kernel', 'mel_kernel',
     'l1_mean_kernel', 'mse_to_target_kernel', 'axpby_kernel', 'adamw_kernel', 'adamw_peer_kernel',
     'reflect_pad_kernel', 'reflect_pad_backward_kernel', 'copy_columns_kernel',

@@ -145,6 +145,7 @@ SIGNATURES = {
     'pmn_extract_grouped': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pmn_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pmn_transpose_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pmn_weight_norm_backward_table': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pmn_weight_norm_backward': (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pmn_reflect_pad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -216,6 +217,13 @@ class WeightDesc(ctypes.Structure):
         ('v', c_void_p), ('g', c_void_p), ('w', c_void_p), ('packed', c_void_p),
         ('packed_t', c_void_p), ('wt', c_void_p), ('dense', c_void_p),
         ('dim0', c_int), ('dim1', c_int), ('taps', c_int), ('groups', c_int)]
+
+
+class WeightNormDesc(ctypes.Structure):
+    """pmn_weight_norm_desc"""
+    _fields_ = [
+        ('v', c_void_p), ('g', c_void_p), ('gw', c_void_p), ('gv', c_void_p), ('gg', c_void_p),
+        ('dim0', c_int), ('inner', c_int)]
 
 
 class ConvGeometry(ctypes.Structure):

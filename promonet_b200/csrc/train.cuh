@@ -73,6 +73,8 @@ int launch_transpose_weight(
 int launch_weight_norm_backward(
     const float* v, const float* g, const float* gw, float* gv, float* gg, int dim0, int inner,
     cudaStream_t stream);
+int launch_weight_norm_backward_table(
+    const pmn_weight_norm_desc* table, int layers, int max_dim0, cudaStream_t stream);
 
 // train_ops.cu
 int launch_reflect_pad(

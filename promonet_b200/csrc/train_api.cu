@@ -110,6 +110,11 @@ int pmn_weight_norm_backward(
     return launch_weight_norm_backward(v, g, gw, gv, gg, dim0, inner, (cudaStream_t)stream);
 }
 
+int pmn_weight_norm_backward_table(
+    const pmn_weight_norm_desc* table, int layers, int max_dim0, void* stream) {
+    return launch_weight_norm_backward_table(table, layers, max_dim0, (cudaStream_t)stream);
+}
+
 int pmn_reflect_pad(
     const float* x, float* out, int rows, int t_in, int left, int right, void* stream) {
     return launch_reflect_pad(x, out, rows, t_in, left, right, (cudaStream_t)stream);

@@ -378,11 +378,11 @@ __global__ void transpose_weight_kernel(
 
 // Backward of w = g v / ||v|| over rows (torch.nn.utils.weight_norm dim=0, model/core.py:43-45):
 //   gg = <gw, v> / ||v||,   gv = g / ||v|| (gw - v <gw, v> / ||v||^2)
-__global__ void __launch_bounds__(256) weight_norm_backward_kernel(
+__device__ __forceinline__ void weight_norm_backward_row(
     const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ gw,
-    float* __restrict__ gv, float* __restrict__ gg, int inner) {
+    float* __restrict__ gv, float* __restrict__ gg, int inner, int row_index) {
     __shared__ float partial[2][32];
-    const size_t row = (size_t)blockIdx.x * inner;
+    const size_t row = (size_t)row_index * inner;
     float norm2 = 0.f, dot = 0.f;
     for (int i = threadIdx.x; i < inner; i += blockDim.x) {
         const float vi = v[row + i];
@@ -414,11 +414,26 @@ __global__ void __launch_bounds__(256) weight_norm_backward_kernel(
     norm2 = partial[0][0];
     dot = partial[1][0];
     const float inv = rsqrtf(norm2);
-    const float scale = g[blockIdx.x] * inv;
+    const float scale = g[row_index] * inv;
     const float project = dot / norm2;
     for (int i = threadIdx.x; i < inner; i += blockDim.x)
         gv[row + i] = scale * (gw[row + i] - v[row + i] * project);
-    if (threadIdx.x == 0) gg[blockIdx.x] = dot * inv;
+    if (threadIdx.x == 0) gg[row_index] = dot * inv;
+}
+
+__global__ void __launch_bounds__(256) weight_norm_backward_kernel(
+    const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ gw,
+    float* __restrict__ gv, float* __restrict__ gg, int inner) {
+    weight_norm_backward_row(v, g, gw, gv, gg, inner, blockIdx.x);
+}
+
+// The same for every weight-normed convolution of a module in one launch (block (row, layer); rows
+// past a layer's dim0 leave at once): 132 launches of a few microseconds each per training step were
+// 1.25 ms of launch latency
+__global__ void __launch_bounds__(256) weight_norm_backward_table_kernel(const pmn_weight_norm_desc* table) {
+    const pmn_weight_norm_desc d = table[blockIdx.y];
+    if ((int)blockIdx.x >= d.dim0) return;
+    weight_norm_backward_row(d.v, d.g, d.gw, d.gv, d.gg, d.inner, blockIdx.x);
 }
 
 }  // namespace
@@ -487,6 +502,14 @@ int launch_transpose_weight(
     LaunchScope scope("transpose_weight_kernel", stream);
     transpose_weight_kernel<<<blocks, 256, 0, stream>>>(w, wt, dim0, dim1, taps);
     return launched("transpose_weight_kernel");
+}
+
+int launch_weight_norm_backward_table(
+    const pmn_weight_norm_desc* table, int layers, int max_dim0, cudaStream_t stream) {
+    PMN_REQUIRE(table && layers > 0 && layers <= 65535 && max_dim0 > 0, "weight_norm_backward_table: bad argument");
+    LaunchScope scope("weight_norm_backward_table_kernel", stream);
+    weight_norm_backward_table_kernel<<<dim3(max_dim0, layers), 256, 0, stream>>>(table);
+    return launched("weight_norm_backward_table_kernel");
 }
 
 int launch_weight_norm_backward(

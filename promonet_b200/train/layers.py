@@ -152,6 +152,14 @@ class Layers:
                 'groups': layer.groups})
         self.table = ops.weight_table(entries, device)
         self.max_dim0 = max(layer.dim0 for layer in self.layers)
+        # weight-norm backward of every normed layer in one launch (finish)
+        self.normed = normed
+        self.norm_table = ops.weight_norm_table([{
+            'v': self.params[f'{layer.prefix}.weight_v'], 'g': self.params[f'{layer.prefix}.weight_g'],
+            'gw': layer.gw, 'gv': self.params.gradient(f'{layer.prefix}.weight_v'),
+            'gg': self.params.gradient(f'{layer.prefix}.weight_g'),
+            'dim0': layer.dim0, 'inner': layer.stored // layer.dim0} for layer in normed], device) \
+            if normed else None
 
     def refresh(self):
         """After an optimizer step: fold every weight norm and rebuild the operand
@@ -163,5 +171,12 @@ class Layers:
         self.scratch.zero_()
 
     def finish(self):
+        """Weight gradients -> parameter gradients: grouped layers keep the diagonal blocks of their
+        dense gradient, then one launch runs the weight-norm backward of every normed layer"""
         for layer in self.layers:
-            layer.finish()
+            if layer.groups > 1:
+                ops.extract_grouped(
+                    layer.gw_dense, layer.gw, layer.dim0, layer.dim1, layer.taps, layer.groups)
+        if self.normed:
+            ops.weight_norm_backward_table(
+                self.norm_table, len(self.normed), max(layer.dim0 for layer in self.normed))

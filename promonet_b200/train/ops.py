@@ -123,6 +123,21 @@ def weight_norm_fold(v, g, w, dim0, inner):
     return w
 
 
+def weight_norm_table(entries, device):
+    """Device copy of a pmn_weight_norm_desc array; entries are dicts of tensors / ints"""
+    table = (_lib.WeightNormDesc * len(entries))()
+    for desc, entry in zip(table, entries):
+        for name in ('v', 'g', 'gw', 'gv', 'gg'):
+            setattr(desc, name, _lib.ptr(entry[name]))
+        desc.dim0, desc.inner = entry['dim0'], entry['inner']
+    raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).clone()
+    return raw.to(device)
+
+
+def weight_norm_backward_table(table, layers, max_dim0):
+    _check(_lib.library().pmn_weight_norm_backward_table(_lib.ptr(table), layers, max_dim0, _lib.stream()))
+
+
 def weight_norm_backward(v, g, gw, gv, gg, dim0, inner):
     _check(_lib.library().pmn_weight_norm_backward(
         _lib.ptr(v), _lib.ptr(g), _lib.ptr(gw), _lib.ptr(gv), _lib.ptr(gg), dim0, inner,
