@@ -886,16 +886,17 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const pmn_weight_desc
     for (int t = 0; t < 2; ++t) {
         if (!out[t]) continue;
         const int tiles = (rows[t] + bn[t] - 1) / bn[t];
-        const size_t total = (size_t)tiles * bn[t] * d.taps * blocks[t] * kKStep;
-        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-             idx += (size_t)gridDim.x * blockDim.x) {
+        // 32-bit index arithmetic (a packing has < 2^31 elements: train/layers.py checks): the
+        // five 64-bit divisions per element made this pass instruction-bound at 13 x its memory time
+        const uint32_t total = (uint32_t)tiles * bn[t] * d.taps * blocks[t] * kKStep;
+        for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
             const int e = (int)(idx & 3);
-            size_t rest = idx >> 2;
-            const int local = (int)(rest % bn[t]); rest /= bn[t];
+            uint32_t rest = idx >> 2;
+            const int local = (int)(rest % (uint32_t)bn[t]); rest /= (uint32_t)bn[t];
             const int chunk = (int)(rest % (kKStep / 4)); rest /= (kKStep / 4);
-            const int cb = (int)(rest % blocks[t]); rest /= blocks[t];
-            const int tap = (int)(rest % d.taps);
-            const int tile = (int)(rest / d.taps);
+            const int cb = (int)(rest % (uint32_t)blocks[t]); rest /= (uint32_t)blocks[t];
+            const int tap = (int)(rest % (uint32_t)d.taps);
+            const int tile = (int)(rest / (uint32_t)d.taps);
             const int row = tile * bn[t] + local;
             const int c = cb * kKStep + chunk * 4 + e;
             const int reduce = t ? d.dim0 : d.dim1;
@@ -985,7 +986,7 @@ int launch_prepare_weights(const pmn_weight_desc* table, int layers, int max_dim
         PMN_TRY(launched("fold_weights_kernel"));
     }
     LaunchScope scope("pack_weights_kernel", stream);
-    pack_weights_kernel<<<dim3(64, layers), 256, 0, stream>>>(table);
+    pack_weights_kernel<<<dim3(256, layers), 256, 0, stream>>>(table);
     return launched("pack_weights_kernel");
 }
 

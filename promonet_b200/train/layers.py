@@ -114,6 +114,8 @@ class Layers:
             (ops.packed_floats(layer.dim0, layer.dim1, layer.taps),
              ops.packed_floats(layer.dim1, layer.dim0, layer.taps)) if tensor_cores else (0, 0)
             for layer in self.layers]
+        if any(max(a, b) >= 2 ** 31 for a, b in sizes):
+            raise ValueError('a packed weight exceeds 2^31 elements (pack_weights_kernel indexes with 32 bits)')
         self.packed = flat(sum(a + b for a, b in sizes))
         self.transposed = flat(0 if tensor_cores else sum(layer.numel for layer in self.layers))
         self.dense = flat(0 if tensor_cores else sum(layer.numel for layer in grouped))
