@@ -439,15 +439,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_tc_kernel(TcParams p) {
             uint32_t raw[16];
             __syncwarp();
             tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
+            // one 64-bit index per chunk, then a step of o_positions per channel: the per-element
+            // ((b o_ch + n) o_positions + rem) and the optional-input tests were most of this loop
+            if (!ok) continue;
+            const int n_first = n0 + c0;
+            size_t idx = ((size_t)b * p.o_ch + n_first) * p.o_positions + rem;
+            const float* bias = p.a.bias ? p.a.bias + n_first : nullptr;
+            const float* bias2 = p.a.bias2 ? p.a.bias2 + (size_t)b * p.o_ch + n_first : nullptr;
+            const bool lrelu = p.a.out_act == kOutLrelu;
+            const int live = min(16, p.o_ch - n_first);      // channels of this chunk that exist
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = n0 + c0 + i;
-                if (!ok || n >= p.o_ch) continue;
-                const size_t idx = ((size_t)b * p.o_ch + n) * p.o_positions + rem;
+            for (int i = 0; i < 16; ++i, idx += p.o_positions) {
+                if (i >= live) break;
                 float v = k_steps > 0 ? __uint_as_float(raw[i]) : 0.f;   // no tap reaches this phase
-                if (p.a.bias) v += __ldg(p.a.bias + n);
-                if (p.a.bias2) v += __ldg(p.a.bias2 + (size_t)b * p.o_ch + n);
-                if (p.a.out_act == kOutLrelu) v = leaky(v, p.a.out_slope);
+                if (bias) v += __ldg(bias + i);
+                if (bias2) v += __ldg(bias2 + i);
+                if (lrelu) v = leaky(v, p.a.out_slope);
                 if (p.a.mask_src) v = __ldg(p.a.mask_src + idx) > 0.f ? v : v * p.a.mask_slope;
                 if (p.a.residual) v += __ldg(p.a.residual + idx);
                 v *= p.a.alpha;
@@ -792,13 +799,21 @@ __global__ void __launch_bounds__(kProducers + 32, 1) conv_wgrad_tc_kernel(TcWgr
             uint32_t raw[16];
             __syncwarp();
             tc_load16(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, raw);
+            const int n_first = n0 + c0;
+            const int live = min(16, g.c_out - n_first);
+            if (col < p.ncols) {
+                float* target = p.a.gw + (size_t)n_first * p.ncols + col;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int n = n0 + c0 + i;
-                const float v = __uint_as_float(raw[i]);
-                if (n >= g.c_out || v == 0.f) continue;
-                if (col < p.ncols) atomicAdd(p.a.gw + (size_t)n * p.ncols + col, v);
-                else if (col == p.ncols && p.a.gbias) atomicAdd(p.a.gbias + n, v);
+                for (int i = 0; i < 16; ++i, target += p.ncols) {
+                    const float v = __uint_as_float(raw[i]);
+                    if (i < live && v != 0.f) atomicAdd(target, v);
+                }
+            } else if (col == p.ncols && p.a.gbias) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float v = __uint_as_float(raw[i]);
+                    if (i < live && v != 0.f) atomicAdd(p.a.gbias + n_first + i, v);
+                }
             }
         }
     }
