@@ -1023,8 +1023,29 @@ int launch_conv_wgrad_tc(const ConvWgradArgs& args, cudaStream_t stream) {
     p.steps_total = g.batch * p.steps_per_item;
     const int bn = tile_columns(g.c_out);
     const int tiles = ceil_div(p.rows_total, kBM) * ceil_div(g.c_out, bn);
-    // fill 148 SMs twice over, but keep at least 8 K steps per CTA
-    int splits = max(1, min(ceil_div(296, tiles), ceil_div(p.steps_total, 8)));
+    // Split the position range over gridDim.z so that the CTAs fill whole waves of the SMs: the cost
+    // of a launch is (waves) x (K steps of one CTA + its fixed prologue / epilogue, worth about 6
+    // steps), at least 8 steps per CTA.  The heaviest launches of a training step (MPD 1024 -> 1024:
+    // 328 tiles) ran unsplit in 3 waves with the last 22 % full, and "two waves' worth" of CTAs
+    // (296 / tiles splits) often landed just past two waves.
+    static int sms = 0;
+    if (!sms) {
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (sms <= 0) sms = 148;
+    }
+    int splits = 1;
+    {
+        const int most = max(1, min(64, p.steps_total / 8));
+        long long best = -1;
+        for (int candidate = 1; candidate <= most; ++candidate) {
+            const int per = ceil_div(p.steps_total, candidate);
+            const int real = ceil_div(p.steps_total, per);
+            const long long cost = (long long)ceil_div(tiles * real, sms) * (per + 6);
+            if (best < 0 || cost < best) { best = cost; splits = candidate; }
+        }
+    }
     p.steps_per_split = ceil_div(p.steps_total, splits);
     splits = ceil_div(p.steps_total, p.steps_per_split);
     dim3 grid(ceil_div(p.rows_total, kBM), ceil_div(g.c_out, bn), splits);
