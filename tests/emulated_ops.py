@@ -144,6 +144,21 @@ def weight_norm_backward(v, g, gw, gv, gg, dim0, inner):
     _store(gv, g.reshape(dim0, 1) / norm * (gw - v * projection / norm ** 2), False)
 
 
+def weight_norm_table(entries, device):
+    table = torch.zeros(max(1, len(entries)), dtype=torch.uint8)
+    _tables[table.data_ptr()] = (table, entries)
+    return table
+
+
+def weight_norm_backward_table(table, layers, max_dim0):
+    _, entries = _tables[table.data_ptr()]
+    assert len(entries) == layers
+    for entry in entries:
+        assert entry['dim0'] <= max_dim0
+        weight_norm_backward(
+            entry['v'], entry['g'], entry['gw'], entry['gv'], entry['gg'], entry['dim0'], entry['inner'])
+
+
 def reflect_pad(x, left, right):
     t = x.shape[-1]
     return F.pad(x.reshape(1, -1, t), (left, right), mode='reflect').reshape(
@@ -341,6 +356,7 @@ EMULATED = (
     conv_transpose1d, features, pitch_bins, global_features, embedding_backward, row_sum,
     channel_sum, linear_to_mel, mel_loss, extract_grouped, dft_basis, spectral_convergence,
     conv_gemm, conv_wgrad, weight_table, prepare_weights, transpose_weight, weight_norm_backward,
+    weight_norm_table, weight_norm_backward_table,
     reflect_pad, reflect_pad_backward, axpby, mse_to_target, l1_mean, stft_magnitude,
     stft_magnitude_backward, copy_columns, dft_basis_rect, complex_magnitude,
     complex_magnitude_backward, frame_overlap_add)
