@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < kEpilogueWarp0) {
+    // ---- first warpgroup: producer, MMA issuer, two idle warps (role bodies keep their indentation) ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ===== producer =====
@@ -509,6 +510,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv1d_tc_kernel(
             mbar_wait(acc_full + as, aphase);
             if (a.debug) wait_cycles += clock64() - wait_start;
             tc_fence_after();
+            // groups of kGroup chunks: the outer loop is a real loop, the inner one is unrolled (its body
+            // keeps the indentation it had as a single loop)
 #pragma unroll 1
             for (int group = 0; group < kMine / kGroup; ++group) {
 #pragma unroll
